@@ -1,0 +1,212 @@
+/* b200flac.h -- C ABI of the B200-native FLAC encoding engine.
+ *
+ * This is the drop-in boundary for the reference's FLAC-encode hot path
+ * (widgital/python-audio-tools, src/encoders/flac.c).  Plain pointers and
+ * sizes only; no CUDA, torch or Python types appear in any signature, so the
+ * library can be bound from C, cgo, JNI, ctypes or a CPython extension alike.
+ *
+ * Two layers:
+ *
+ *   frame layer  (b200flac_encoder_*)  replaces the reference's per-frame seam
+ *       flacenc_write_frame()            src/encoders/flac.h:128-131, flac.c:520-671
+ *     and everything below it (flacenc_write_subframe, the FIXED/LPC model
+ *     search, flacenc_encode_residuals, the BitstreamWriter bit packing and the
+ *     CRC-8/CRC-16 callbacks), for a whole batch of independent frames at once.
+ *
+ *   stream layer (b200flac_stream_*)   replaces the C-signature entry point
+ *       encoders_encode_flac()           src/encoders/flac.c:124-306
+ *     i.e. "fLaC" + STREAMINFO/VORBIS_COMMENT/PADDING, the frame loop, the
+ *     STREAMINFO MD5 (host thread, overlapped) and the final STREAMINFO rewrite.
+ *     audiotools.encoders.encode_flac (the CPython extension in
+ *     python-audio-tools_b200/audiotools/) is a thin wrapper over this layer.
+ *
+ * There is no CPU fallback: every entry point fails (returns NULL / non-zero
+ * and sets b200flac_last_error()) when no CUDA device is usable.
+ *
+ * PCM everywhere in this header is what the reference's standalone encoder
+ * reads and what its MD5 callback hashes (flac.c:188,1784-1790): interleaved,
+ * signed, little-endian, bits_per_sample/8 bytes per sample.
+ */
+#ifndef B200FLAC_H
+#define B200FLAC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FLAC_ABI_VERSION 1
+#define B200FLAC_MAX_CHANNELS 8
+#define B200FLAC_MAX_LPC_ORDER 32
+
+/* Encoding options: struct flac_encoding_options (src/encoders/flac.h:30-47)
+ * plus the three stream parameters the frame header needs
+ * (struct flac_STREAMINFO, flac.h:49-59).  The derived options
+ * qlp_coeff_precision / max_rice_parameter (flac.c:165-184) are computed by
+ * the library exactly as the reference does. */
+typedef struct b200flac_params {
+    uint32_t block_size;
+    uint32_t max_lpc_order;
+    uint32_t min_residual_partition_order; /* accepted and ignored, as in flac.c:1362 */
+    uint32_t max_residual_partition_order;
+    int32_t  mid_side;
+    int32_t  adaptive_mid_side;
+    int32_t  exhaustive_model_search;
+    int32_t  no_verbatim_subframes;  /* the reference's debug switches, flac.c:62-65 */
+    int32_t  no_constant_subframes;
+    int32_t  no_fixed_subframes;
+    int32_t  no_lpc_subframes;
+    uint32_t sample_rate;
+    uint32_t channels;          /* 1..8 */
+    uint32_t bits_per_sample;   /* 8, 16 or 24 */
+} b200flac_params;
+
+/* A run of PCM frames that is cut into blocks on its own: blocks of
+ * params.block_size frames, the last one possibly shorter (flac.c:244-274).
+ * One segment = (part of) one stream; a batch may carry many streams. */
+typedef struct b200flac_segment {
+    uint64_t pcm_frame_offset;   /* first PCM frame of the segment inside the pcm buffer */
+    uint64_t n_pcm_frames;
+    uint32_t first_frame_number; /* FLAC frame number of its first block (flac.c:592 total_flac_frames) */
+    uint32_t reserved;
+} b200flac_segment;
+
+typedef struct b200flac_encoder b200flac_encoder;
+typedef struct b200flac_stream b200flac_stream;
+
+/* ---- library ---- */
+int         b200flac_abi_version(void);
+int         b200flac_device_count(void);            /* usable CUDA devices; 0 if none */
+const char *b200flac_last_error(void);              /* thread-local, never NULL */
+
+/* ---- frame layer ---- */
+
+/* One encoder is bound to one CUDA device and owns `n_slots` in-flight batch
+ * slots (pinned staging + device buffers + one CUDA stream each), each able to
+ * hold max_pcm_frames_per_batch PCM frames.  Replaces flacenc_init_encoder
+ * (flac.c:310-341). */
+b200flac_encoder *b200flac_encoder_create(const b200flac_params *params, int device,
+                                          uint64_t max_pcm_frames_per_batch, int n_slots);
+void              b200flac_encoder_destroy(b200flac_encoder *enc); /* flacenc_free_encoder, flac.c:343-374 */
+
+/* upper bound on the bytes submit/collect can return for a batch */
+uint64_t b200flac_encoder_output_bound(const b200flac_encoder *enc, uint64_t n_pcm_frames,
+                                       uint32_t n_segments);
+/* pinned host staging buffer of a slot (write PCM here to skip one host copy) */
+uint8_t *b200flac_encoder_slot_pcm(b200flac_encoder *enc, int slot);
+
+/* Asynchronous: copy PCM host->device (pinned if pcm == slot buffer), run the
+ * kernels, start the device->host copy of the per-frame sizes.  Returns 0 on
+ * success.  `pcm` holds at least max(pcm_frame_offset + n_pcm_frames) frames. */
+int b200flac_encoder_submit(b200flac_encoder *enc, int slot, const uint8_t *pcm,
+                            const b200flac_segment *segments, uint32_t n_segments);
+
+/* Wait for the slot, copy the frame bytes device->host.
+ *   out          receives the frames of all segments back to back, in order
+ *   frame_bytes  receives the size of each frame (n_frames entries)
+ *   frame_pcm    receives the PCM-frame count of each frame (may be NULL)
+ * Exactly what flacenc_write_frame appended to the recorder per block. */
+int b200flac_encoder_collect(b200flac_encoder *enc, int slot, uint8_t *out, uint64_t out_capacity,
+                             uint64_t *out_bytes, uint32_t *frame_bytes, uint32_t *frame_pcm,
+                             uint32_t frame_capacity, uint32_t *n_frames);
+
+/* submit + collect on slot 0 */
+int b200flac_encoder_encode(b200flac_encoder *enc, const uint8_t *pcm,
+                            const b200flac_segment *segments, uint32_t n_segments,
+                            uint8_t *out, uint64_t out_capacity, uint64_t *out_bytes,
+                            uint32_t *frame_bytes, uint32_t *frame_pcm, uint32_t frame_capacity,
+                            uint32_t *n_frames);
+
+/* Device-resident variant (inputs already in HBM, frames left in HBM): `d_pcm`
+ * and `d_out` are device pointers on the encoder's device.  d_out must be
+ * 4-byte aligned and hold b200flac_encoder_output_bound() bytes.  Returns the
+ * total through *out_bytes (host) after synchronising the slot's stream.
+ * elapsed_ms (optional) receives the CUDA-event time of the kernels alone. */
+int b200flac_encoder_encode_device(b200flac_encoder *enc, int slot, const void *d_pcm,
+                                   const b200flac_segment *segments, uint32_t n_segments,
+                                   void *d_out, uint64_t out_capacity, uint64_t *out_bytes,
+                                   uint32_t *n_frames, float *elapsed_ms);
+
+/* per-kernel CUDA-event times of the slot's last batch, in ms:
+ * [0] lpc model (window/autocorrelation/Levinson/quantise), [1] subframe analysis,
+ * [2] frame select + offset scan + output clear, [3] bit packing, [4] CRC-16.
+ * Returns the number of entries written. */
+int b200flac_encoder_last_kernel_ms(b200flac_encoder *enc, int slot, float *ms, int capacity);
+/* number of kernel launches issued by this encoder so far */
+uint64_t b200flac_encoder_launch_count(const b200flac_encoder *enc);
+
+/* raw device memory helpers so a host language without a CUDA binding can stage
+ * device-resident input (bench.py uses them; torch is not required) */
+void *b200flac_device_alloc(int device, uint64_t bytes);
+void  b200flac_device_free(int device, void *ptr);
+int   b200flac_device_upload(int device, void *dst, const void *src, uint64_t bytes);
+int   b200flac_device_download(int device, void *dst, const void *src, uint64_t bytes);
+/* fill device memory with the deterministic synthetic PCM of SURVEY.md 8(d) */
+int   b200flac_device_synth_pcm(int device, void *d_pcm, uint64_t seed, uint32_t channels,
+                                uint32_t bits_per_sample, uint64_t first_frame, uint64_t n_frames);
+
+/* ---- debug / test hooks (forced-decision packing) ---- */
+
+/* what the analysis kernels decided for one subframe candidate */
+typedef struct b200flac_plan {
+    uint8_t  type;            /* 0 CONSTANT, 1 VERBATIM, 2 FIXED, 3 LPC */
+    uint8_t  order;
+    uint8_t  wasted;
+    uint8_t  precision;
+    int8_t   shift;
+    uint8_t  coding_method;
+    uint8_t  partition_order;
+    uint8_t  flags;           /* bit0: partition-length underflow level (flac.c:1462) */
+    uint32_t bits;            /* exact subframe size in bits */
+    int16_t  coeffs[B200FLAC_MAX_LPC_ORDER];
+} b200flac_plan;
+
+/* After a collect/encode on `slot`: copy out the plans of every candidate
+ * (n_frames * candidates_per_frame entries, candidate-major inside a frame:
+ * channels 0..C-1, or L,R,M,S when stereo decorrelation ran), their Rice
+ * parameters (rice_stride bytes per candidate) and each frame's channel
+ * assignment. Any pointer may be NULL. */
+int b200flac_encoder_get_plans(b200flac_encoder *enc, int slot, b200flac_plan *plans,
+                               uint8_t *rice, uint32_t *rice_stride,
+                               uint8_t *assignments, uint32_t *candidates_per_frame);
+
+/* ---- stream layer ---- */
+
+/* Opens `filename` for writing and emits the stream head exactly as
+ * flac.c:209-238: "fLaC", STREAMINFO placeholder, VORBIS_COMMENT with vendor
+ * string "Python Audio Tools " + version (NULL -> "2.22alpha1"), PADDING of
+ * padding_size bytes.  devices/n_devices: the CUDA devices to shard frame
+ * ranges over (NULL/0 -> device 0). */
+b200flac_stream *b200flac_stream_open(const char *filename, const b200flac_params *params,
+                                      uint32_t padding_size, const char *version,
+                                      const int *devices, int n_devices);
+/* Appends PCM (any number of PCM frames per call).  Blocks are cut every
+ * block_size frames across calls, like BufferedPCMReader feeding
+ * pcmreader->read(block_size) (flac.c:244,272). */
+int b200flac_stream_write(b200flac_stream *s, const uint8_t *pcm, uint64_t n_pcm_frames);
+/* Forces a frame boundary: PCM written since the last boundary that does not fill
+ * a whole block becomes a short frame -- what the reference does when
+ * pcmreader->read() returns fewer than block_size frames mid-stream
+ * (flac.c:247,525; it encodes whatever length it is given). */
+int b200flac_stream_end_block(b200flac_stream *s);
+/* Flushes the tail block, waits for the MD5 thread, rewrites STREAMINFO at
+ * byte 8 (flac.c:277-279) and closes the file.  The (offset, pcm_frames) list of
+ * flac.c:249-253 is returned through malloc'd arrays the caller frees with
+ * b200flac_free().  On abort != 0 the file is closed without finalising. */
+int b200flac_stream_close(b200flac_stream *s, int abort_encode, uint64_t **frame_offsets,
+                          uint32_t **frame_pcm_frames, uint64_t *n_frames);
+void b200flac_free(void *p);
+
+/* One-call form of the above for PCM already in memory: the standalone
+ * reference's `flacenc < pcm` (flac.c:1637-1804). */
+int b200flac_encode_file(const char *filename, const b200flac_params *params,
+                         uint32_t padding_size, const char *version,
+                         const uint8_t *pcm, uint64_t n_pcm_frames,
+                         const int *devices, int n_devices);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FLAC_H */

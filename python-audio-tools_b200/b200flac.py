@@ -1,0 +1,272 @@
+"""ctypes binding of the B200 FLAC engine's C ABI (include/b200flac.h).
+
+This is the thinnest possible host-language stub over ``libb200flac.so``; it is
+what bench.py, the GPU parity tests and ``__graft_entry__.smoke()`` call.  The
+CPython extension ``audiotools.encoders`` binds the same library from C.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device
+is usable, every entry point raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200flac.so")
+
+MAX_LPC_ORDER = 32
+
+
+class Params(C.Structure):
+    """struct b200flac_params (mirrors flac_encoding_options, src/encoders/flac.h:30-47)"""
+    _fields_ = [("block_size", C.c_uint32),
+                ("max_lpc_order", C.c_uint32),
+                ("min_residual_partition_order", C.c_uint32),
+                ("max_residual_partition_order", C.c_uint32),
+                ("mid_side", C.c_int32),
+                ("adaptive_mid_side", C.c_int32),
+                ("exhaustive_model_search", C.c_int32),
+                ("no_verbatim_subframes", C.c_int32),
+                ("no_constant_subframes", C.c_int32),
+                ("no_fixed_subframes", C.c_int32),
+                ("no_lpc_subframes", C.c_int32),
+                ("sample_rate", C.c_uint32),
+                ("channels", C.c_uint32),
+                ("bits_per_sample", C.c_uint32)]
+
+
+class Segment(C.Structure):
+    _fields_ = [("pcm_frame_offset", C.c_uint64),
+                ("n_pcm_frames", C.c_uint64),
+                ("first_frame_number", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class Plan(C.Structure):
+    _fields_ = [("type", C.c_uint8), ("order", C.c_uint8), ("wasted", C.c_uint8),
+                ("precision", C.c_uint8), ("shift", C.c_int8), ("coding_method", C.c_uint8),
+                ("partition_order", C.c_uint8), ("flags", C.c_uint8), ("bits", C.c_uint32),
+                ("coeffs", C.c_int16 * MAX_LPC_ORDER)]
+
+
+_lib = None
+
+
+def lib():
+    """loads libb200flac.so (built by python-audio-tools_b200/Makefile or __graft_entry__.build)"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the engine has no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, u32p, u64p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    L.b200flac_abi_version.restype = C.c_int
+    L.b200flac_device_count.restype = C.c_int
+    L.b200flac_last_error.restype = C.c_char_p
+    L.b200flac_encoder_create.restype = vp
+    L.b200flac_encoder_create.argtypes = [C.POINTER(Params), C.c_int, C.c_uint64, C.c_int]
+    L.b200flac_encoder_destroy.argtypes = [vp]
+    L.b200flac_encoder_output_bound.restype = C.c_uint64
+    L.b200flac_encoder_output_bound.argtypes = [vp, C.c_uint64, C.c_uint32]
+    L.b200flac_encoder_slot_pcm.restype = vp
+    L.b200flac_encoder_slot_pcm.argtypes = [vp, C.c_int]
+    L.b200flac_encoder_submit.argtypes = [vp, C.c_int, vp, C.POINTER(Segment), C.c_uint32]
+    L.b200flac_encoder_collect.argtypes = [vp, C.c_int, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, u32p]
+    L.b200flac_encoder_encode.argtypes = [vp, vp, C.POINTER(Segment), C.c_uint32, vp, C.c_uint64, u64p,
+                                          vp, vp, C.c_uint32, u32p]
+    L.b200flac_encoder_encode_device.argtypes = [vp, C.c_int, vp, C.POINTER(Segment), C.c_uint32, vp,
+                                                 C.c_uint64, u64p, u32p, C.POINTER(C.c_float)]
+    L.b200flac_encoder_last_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_int]
+    L.b200flac_encoder_launch_count.restype = C.c_uint64
+    L.b200flac_encoder_launch_count.argtypes = [vp]
+    L.b200flac_device_alloc.restype = vp
+    L.b200flac_device_alloc.argtypes = [C.c_int, C.c_uint64]
+    L.b200flac_device_free.argtypes = [C.c_int, vp]
+    L.b200flac_device_upload.argtypes = [C.c_int, vp, vp, C.c_uint64]
+    L.b200flac_device_download.argtypes = [C.c_int, vp, vp, C.c_uint64]
+    L.b200flac_device_synth_pcm.argtypes = [C.c_int, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64,
+                                            C.c_uint64]
+    L.b200flac_encoder_get_plans.argtypes = [vp, C.c_int, vp, vp, u32p, vp, u32p]
+    L.b200flac_stream_open.restype = vp
+    L.b200flac_stream_open.argtypes = [C.c_char_p, C.POINTER(Params), C.c_uint32, C.c_char_p,
+                                       C.POINTER(C.c_int), C.c_int]
+    L.b200flac_stream_write.argtypes = [vp, vp, C.c_uint64]
+    L.b200flac_stream_end_block.argtypes = [vp]
+    L.b200flac_stream_close.argtypes = [vp, C.c_int, C.POINTER(u64p), C.POINTER(u32p), u64p]
+    L.b200flac_free.argtypes = [vp]
+    L.b200flac_encode_file.argtypes = [C.c_char_p, C.POINTER(Params), C.c_uint32, C.c_char_p, vp,
+                                       C.c_uint64, C.POINTER(C.c_int), C.c_int]
+    _lib = L
+    return L
+
+
+class B200FlacError(RuntimeError):
+    pass
+
+
+def _err():
+    return B200FlacError(lib().b200flac_last_error().decode("utf-8", "replace"))
+
+
+def make_params(sample_rate=44100, channels=2, bits_per_sample=16, block_size=4096, max_lpc_order=8,
+                min_residual_partition_order=0, max_residual_partition_order=5, mid_side=False,
+                adaptive_mid_side=False, exhaustive_model_search=False,
+                disable_verbatim_subframes=False, disable_constant_subframes=False,
+                disable_fixed_subframes=False, disable_lpc_subframes=False):
+    return Params(block_size, max_lpc_order, min_residual_partition_order, max_residual_partition_order,
+                  int(bool(mid_side)), int(bool(adaptive_mid_side)), int(bool(exhaustive_model_search)),
+                  int(bool(disable_verbatim_subframes)), int(bool(disable_constant_subframes)),
+                  int(bool(disable_fixed_subframes)), int(bool(disable_lpc_subframes)),
+                  sample_rate, channels, bits_per_sample)
+
+
+def _buf_ptr(b):
+    """address of a bytes/bytearray/numpy buffer without copying"""
+    if isinstance(b, int):
+        return b
+    if hasattr(b, "ctypes"):
+        return b.ctypes.data
+    if isinstance(b, bytes):
+        return C.cast(C.c_char_p(b), C.c_void_p).value
+    return C.addressof((C.c_char * len(b)).from_buffer(b))
+
+
+class Encoder(object):
+    """frame layer: batches of PCM blocks -> FLAC frames on one CUDA device"""
+
+    def __init__(self, params, device=0, max_pcm_frames_per_batch=1 << 22, n_slots=2):
+        self.params = params
+        self.device = device
+        self.h = lib().b200flac_encoder_create(C.byref(params), device, max_pcm_frames_per_batch, n_slots)
+        if not self.h:
+            raise _err()
+        self.max_pcm_frames = max_pcm_frames_per_batch
+        self.n_slots = n_slots
+
+    def close(self):
+        if self.h:
+            lib().b200flac_encoder_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def output_bound(self, n_pcm_frames, n_segments=1):
+        return lib().b200flac_encoder_output_bound(self.h, n_pcm_frames, n_segments)
+
+    @staticmethod
+    def _segments(segments):
+        arr = (Segment * len(segments))()
+        for i, (off, n, first) in enumerate(segments):
+            arr[i] = Segment(off, n, first, 0)
+        return arr
+
+    def submit(self, slot, pcm, segments):
+        arr = self._segments(segments)
+        if lib().b200flac_encoder_submit(self.h, slot, _buf_ptr(pcm), arr, len(segments)):
+            raise _err()
+
+    def collect(self, slot, n_pcm_frames, n_segments=1):
+        import numpy as np
+        cap = self.output_bound(n_pcm_frames, n_segments)
+        fcap = n_pcm_frames // self.params.block_size + n_segments + 2
+        out = np.empty(cap, dtype=np.uint8)
+        fbytes = np.empty(fcap, dtype=np.uint32)
+        fpcm = np.empty(fcap, dtype=np.uint32)
+        nbytes, nfr = C.c_uint64(0), C.c_uint32(0)
+        if lib().b200flac_encoder_collect(self.h, slot, out.ctypes.data, cap, C.byref(nbytes),
+                                          fbytes.ctypes.data, fpcm.ctypes.data, fcap, C.byref(nfr)):
+            raise _err()
+        return out[:nbytes.value], fbytes[:nfr.value], fpcm[:nfr.value]
+
+    def encode(self, pcm, n_pcm_frames, first_frame_number=0, segments=None):
+        """host PCM bytes -> (frame bytes, per-frame sizes, per-frame PCM counts)"""
+        if segments is None:
+            segments = [(0, n_pcm_frames, first_frame_number)]
+        self.submit(0, pcm, segments)
+        return self.collect(0, n_pcm_frames, len(segments))
+
+    def encode_device(self, d_pcm, segments, d_out, out_capacity, slot=0):
+        """device pointers in, frames left on the device; returns (bytes, frames, kernel ms)"""
+        arr = self._segments(segments)
+        nbytes, nfr, ms = C.c_uint64(0), C.c_uint32(0), C.c_float(0)
+        if lib().b200flac_encoder_encode_device(self.h, slot, d_pcm, arr, len(segments), d_out, out_capacity,
+                                                C.byref(nbytes), C.byref(nfr), C.byref(ms)):
+            raise _err()
+        return nbytes.value, nfr.value, ms.value
+
+    def kernel_ms(self, slot=0):
+        ms = (C.c_float * 8)()
+        n = lib().b200flac_encoder_last_kernel_ms(self.h, slot, ms, 8)
+        return [ms[i] for i in range(n)]
+
+    def launch_count(self):
+        return lib().b200flac_encoder_launch_count(self.h)
+
+    def plans(self, slot, n_frames):
+        import numpy as np
+        stride, k = C.c_uint32(0), C.c_uint32(0)
+        if lib().b200flac_encoder_get_plans(self.h, slot, None, None, C.byref(stride), None, C.byref(k)):
+            raise _err()
+        units = n_frames * k.value
+        plans = (Plan * units)()
+        rice = np.zeros(units * stride.value, dtype=np.uint8)
+        asg = np.zeros(n_frames, dtype=np.uint8)
+        if lib().b200flac_encoder_get_plans(self.h, slot, plans, rice.ctypes.data, None, asg.ctypes.data, None):
+            raise _err()
+        return plans, rice.reshape(units, stride.value), asg, k.value
+
+
+def device_count():
+    return lib().b200flac_device_count()
+
+
+def encode_file(filename, params, pcm, n_pcm_frames, padding_size=4096, version=None, devices=None):
+    """standalone-reference equivalent: packed PCM in memory -> FLAC file (flac.c:124-306)"""
+    devs = None
+    ndev = 0
+    if devices:
+        devs = (C.c_int * len(devices))(*devices)
+        ndev = len(devices)
+    v = version.encode() if version else None
+    if lib().b200flac_encode_file(os.fsencode(filename), C.byref(params), padding_size, v, _buf_ptr(pcm),
+                                  n_pcm_frames, devs, ndev):
+        raise _err()
+
+
+class Stream(object):
+    """stream layer: open / write PCM / close, returns the (offset, frames) list of flac.c:249-253"""
+
+    def __init__(self, filename, params, padding_size=4096, version=None, devices=None):
+        devs, ndev = None, 0
+        if devices:
+            devs = (C.c_int * len(devices))(*devices)
+            ndev = len(devices)
+        v = version.encode() if version else None
+        self.h = lib().b200flac_stream_open(os.fsencode(filename), C.byref(params), padding_size, v, devs, ndev)
+        if not self.h:
+            raise _err()
+        self.frame_bytes = params.channels * (params.bits_per_sample // 8)
+
+    def write(self, pcm):
+        n = len(pcm) // self.frame_bytes
+        if lib().b200flac_stream_write(self.h, _buf_ptr(pcm), n):
+            raise _err()
+
+    def end_block(self):
+        if lib().b200flac_stream_end_block(self.h):
+            raise _err()
+
+    def close(self, abort=False):
+        if not self.h:
+            return []
+        offs, lens, n = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)(), C.c_uint64(0)
+        h, self.h = self.h, None
+        if lib().b200flac_stream_close(h, int(abort), C.byref(offs), C.byref(lens), C.byref(n)):
+            raise _err()
+        if abort:
+            return []
+        res = [(offs[i], lens[i]) for i in range(n.value)]
+        lib().b200flac_free(offs)
+        lib().b200flac_free(lens)
+        return res

@@ -1,0 +1,610 @@
+// b200flac_encoder.cu -- frame layer of the C ABI (include/b200flac.h): one
+// encoder per CUDA device, batches of independent frames through five kernels.
+//
+// Replaces, for a whole batch at a time, the reference's per-frame call
+//   flacenc_write_frame(encoder.frame, &encoder, samples)   src/encoders/flac.c:258, 520-671
+// No CPU fallback exists: without a usable CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <vector>
+
+#include "flac_types.h"
+#include "flac_common.cuh"
+#include "k_lpc_model.cuh"
+#include "k_analyze.cuh"
+#include "k_pack.cuh"
+#include "k_synth.cuh"
+
+#define BF_MAX_SEGMENTS 65536
+#define BF_NUM_EVENTS 6
+
+static thread_local char g_err[512] = "";
+
+static void set_err(const char* msg)
+{
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+}
+
+extern "C" void b200flac_internal_set_error(const char* msg) { set_err(msg); }
+
+#define CU_CHECK(call, ret)                                                              \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            snprintf(g_err, sizeof(g_err), "%s failed: %s (%s:%d)", #call,               \
+                     cudaGetErrorString(e_), __FILE__, __LINE__);                        \
+            return ret;                                                                  \
+        }                                                                                \
+    } while (0)
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[BF_NUM_EVENTS] = {};
+    uint8_t* h_pcm = nullptr;      // pinned
+    uint8_t* d_pcm = nullptr;
+    bf_frame_desc* h_fd = nullptr; // pinned
+    bf_frame_desc* d_fd = nullptr;
+    double* h_win = nullptr;       // pinned
+    double* d_win = nullptr;
+    size_t win_cap = 0;            // doubles
+    bf_lpc_head* d_heads = nullptr;
+    short* d_coefs = nullptr;
+    b200flac_plan* d_plans = nullptr;
+    uint8_t* d_rice = nullptr;
+    bf_frame_choice* d_choice = nullptr;
+    u32* d_frame_bytes = nullptr;
+    u64* d_frame_off = nullptr;
+    u64* d_total = nullptr;
+    uint8_t* d_out = nullptr;
+    u32* h_frame_bytes = nullptr;  // pinned
+    u64* h_total = nullptr;        // pinned
+    int* d_gsamples = nullptr;
+    u64* d_gheap = nullptr;
+    uint8_t* d_gkarr = nullptr;
+    u32 n_frames = 0;
+    bool busy = false;
+    bool timed = false;
+    std::vector<u32> frame_pcm;
+};
+
+struct b200flac_encoder {
+    b200flac_params params;
+    bf_dev_params P;
+    int device;
+    u64 max_pcm_frames;
+    u32 max_frames;       // frames per batch the buffers are sized for
+    u64 out_cap;          // bytes of d_out per slot
+    int n_slots;
+    Slot* slots;
+    int S;                // samples per thread (template selector)
+    int NT;               // threads per CTA for analyze/pack
+    size_t smem_analyze, smem_pack;
+    std::map<u32, std::vector<double>>* windows;
+    u64 launches;
+};
+
+// ---- derived options ------------------------------------------------------
+static u32 sample_rate_code(u32 sr) // flac.c:452-476
+{
+    switch (sr) {
+    case 88200: return 1; case 176400: return 2; case 192000: return 3; case 8000: return 4;
+    case 16000: return 5; case 22050: return 6; case 24000: return 7; case 32000: return 8;
+    case 44100: return 9; case 48000: return 10; case 96000: return 11;
+    default:
+        if (sr <= 255000 && sr % 1000 == 0) return 0xC;
+        if (sr <= 655350 && sr % 10 == 0) return 0xE;
+        if (sr <= 0xFFFF) return 0xD;
+        return 0;
+    }
+}
+
+static u32 bps_code(u32 bps) // flac.c:479-486
+{
+    switch (bps) { case 8: return 1; case 12: return 2; case 16: return 4; case 20: return 5; case 24: return 6; default: return 0; }
+}
+
+// Tukey window exactly as flac.c:1139-1161 computes it (host libm cos, same as the reference)
+static void tukey_window(u32 N, double* w)
+{
+    const double alpha = 0.5;
+    const unsigned window1 = (unsigned)(alpha * (N - 1)) / 2;
+    const unsigned window2 = (unsigned)((N - 1) * (1.0 - (alpha / 2.0)));
+    for (unsigned n = 0; n < N; n++) {
+        if (n <= window1) w[n] = 0.5 * (1.0 + cos(M_PI * (((2 * n) / (alpha * (N - 1))) - 1.0)));
+        else if (n <= window2) w[n] = 1.0;
+        else w[n] = 0.5 * (1.0 + cos(M_PI * (((2.0 * n) / (alpha * (N - 1))) - (2.0 / alpha) + 1.0)));
+    }
+}
+
+static void derive_params(const b200flac_params* p, bf_dev_params* P)
+{
+    memset(P, 0, sizeof(*P));
+    P->block_size = p->block_size;
+    P->max_lpc_order = p->max_lpc_order;
+    P->po_lim = p->max_residual_partition_order > BF_MAX_PO ? BF_MAX_PO : p->max_residual_partition_order;
+    P->channels = p->channels;
+    P->bps = p->bits_per_sample;
+    P->bytes_ps = p->bits_per_sample / 8;
+    P->sample_rate = p->sample_rate;
+    const u32 bs = p->block_size; // flac.c:165-178
+    P->precision = bs <= 192 ? 7 : bs <= 384 ? 8 : bs <= 576 ? 9 : bs <= 1152 ? 10 : bs <= 2304 ? 11 : bs <= 4608 ? 12 : 13;
+    P->max_rice = p->bits_per_sample <= 16 ? 0xE : 0x1E; // flac.c:180-184
+    P->stereo = (p->channels == 2 && (p->mid_side || p->adaptive_mid_side)) ? 1 : 0; // flac.c:532-533
+    P->K = P->stereo ? 4 : p->channels;
+    P->mid_side = p->mid_side ? 1 : 0;
+    P->exhaustive = p->exhaustive_model_search ? 1 : 0;
+    P->try_verbatim = !p->no_verbatim_subframes; // flac.c:681-685
+    P->try_constant = !p->no_constant_subframes;
+    P->try_fixed = !p->no_fixed_subframes;
+    P->try_lpc = !(p->no_lpc_subframes || p->max_lpc_order == 0);
+    P->rice_stride = 1u << P->po_lim;
+    const u32 L = p->max_lpc_order;
+    P->model_stride = L ? (L * (L + 1)) / 2 : 1;
+    P->heap_entries = 2u << P->po_lim;
+    const size_t padn = (size_t)PADI(bs) + 1;
+    P->samples_in_smem = (2 * padn * 4 <= 160 * 1024) ? 1 : 0;
+    P->heap_in_smem = (P->heap_entries <= 2048) ? 1 : 0;
+    P->samp_stride = (u32)padn;
+    P->sr_code = sample_rate_code(p->sample_rate);
+    P->bps_code = bps_code(p->bits_per_sample);
+}
+
+// ---- library ---------------------------------------------------------------
+extern "C" int b200flac_abi_version(void) { return B200FLAC_ABI_VERSION; }
+
+extern "C" int b200flac_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* b200flac_last_error(void) { return g_err; }
+
+extern "C" void* b200flac_device_alloc(int device, uint64_t bytes)
+{
+    void* p = nullptr;
+    CU_CHECK(cudaSetDevice(device), nullptr);
+    CU_CHECK(cudaMalloc(&p, (size_t)bytes + 64), nullptr);
+    return p;
+}
+
+extern "C" void b200flac_device_free(int device, void* ptr)
+{
+    if (cudaSetDevice(device) == cudaSuccess) cudaFree(ptr);
+}
+
+extern "C" int b200flac_device_upload(int device, void* dst, const void* src, uint64_t bytes)
+{
+    CU_CHECK(cudaSetDevice(device), 1);
+    CU_CHECK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice), 1);
+    return 0;
+}
+
+extern "C" int b200flac_device_download(int device, void* dst, const void* src, uint64_t bytes)
+{
+    CU_CHECK(cudaSetDevice(device), 1);
+    CU_CHECK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost), 1);
+    return 0;
+}
+
+extern "C" int b200flac_device_synth_pcm(int device, void* d_pcm, uint64_t seed, uint32_t channels,
+                                         uint32_t bits_per_sample, uint64_t first_frame, uint64_t n_frames)
+{
+    CU_CHECK(cudaSetDevice(device), 1);
+    k_synth_pcm<<<148 * 8, 256>>>((uint8_t*)d_pcm, seed, channels, bits_per_sample, first_frame, n_frames);
+    CU_CHECK(cudaGetLastError(), 1);
+    CU_CHECK(cudaDeviceSynchronize(), 1);
+    return 0;
+}
+
+// ---- encoder ---------------------------------------------------------------
+static u64 frame_bound_bytes(const b200flac_params* p, u32 n)
+{
+    // every subframe VERBATIM at bps+1 with a maximal wasted-bits field, plus header and CRC-16
+    const u64 sub_bits = 8 + 32 + (u64)(p->bits_per_sample + 1) * n;
+    return 16 + ((u64)p->channels * sub_bits + 7) / 8 + 2;
+}
+
+extern "C" uint64_t b200flac_encoder_output_bound(const b200flac_encoder* enc, uint64_t n_pcm_frames,
+                                                  uint32_t n_segments)
+{
+    const b200flac_params* p = &enc->params;
+    const u64 full = n_pcm_frames / p->block_size;
+    u64 b = full * frame_bound_bytes(p, p->block_size) +
+            ((u64)n_segments + 1) * frame_bound_bytes(p, p->block_size) + 64;
+    if (p->no_verbatim_subframes) b *= 2; // FIXED/LPC are then not bounded by VERBATIM; see submit's guard
+    return (b + 15) & ~15ull;
+}
+
+static void free_slot(Slot& s)
+{
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    for (int i = 0; i < BF_NUM_EVENTS; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+    if (s.h_pcm) cudaFreeHost(s.h_pcm);
+    if (s.h_fd) cudaFreeHost(s.h_fd);
+    if (s.h_win) cudaFreeHost(s.h_win);
+    if (s.h_frame_bytes) cudaFreeHost(s.h_frame_bytes);
+    if (s.h_total) cudaFreeHost(s.h_total);
+    cudaFree(s.d_pcm); cudaFree(s.d_fd); cudaFree(s.d_win); cudaFree(s.d_heads); cudaFree(s.d_coefs);
+    cudaFree(s.d_plans); cudaFree(s.d_rice); cudaFree(s.d_choice); cudaFree(s.d_frame_bytes);
+    cudaFree(s.d_frame_off); cudaFree(s.d_total); cudaFree(s.d_out); cudaFree(s.d_gsamples);
+    cudaFree(s.d_gheap); cudaFree(s.d_gkarr);
+    if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+extern "C" void b200flac_encoder_destroy(b200flac_encoder* enc)
+{
+    if (!enc) return;
+    cudaSetDevice(enc->device);
+    if (enc->slots) {
+        for (int i = 0; i < enc->n_slots; i++) free_slot(enc->slots[i]);
+        delete[] enc->slots;
+    }
+    delete enc->windows;
+    delete enc;
+}
+
+template <int S>
+static cudaError_t set_smem_attrs(size_t smem_a, size_t smem_p)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_analyze<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_pack_subframes<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+}
+
+extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* params, int device,
+                                                     uint64_t max_pcm_frames_per_batch, int n_slots)
+{
+    if (!params) { set_err("params is NULL"); return nullptr; }
+    if (params->channels < 1 || params->channels > B200FLAC_MAX_CHANNELS) { set_err("unsupported channel count"); return nullptr; }
+    if (params->bits_per_sample != 8 && params->bits_per_sample != 16 && params->bits_per_sample != 24) {
+        set_err("bits_per_sample must be 8, 16 or 24"); return nullptr;
+    }
+    if (params->block_size < 1 || params->block_size > 65535) { set_err("block_size must be 1..65535"); return nullptr; }
+    if (params->max_lpc_order > B200FLAC_MAX_LPC_ORDER) { set_err("max_lpc_order must be <= 32"); return nullptr; }
+    if (n_slots < 1) n_slots = 1;
+    if (max_pcm_frames_per_batch < params->block_size) max_pcm_frames_per_batch = params->block_size;
+    int ndev = b200flac_device_count();
+    if (ndev <= 0) { set_err("no CUDA device available: the B200 FLAC engine has no CPU fallback"); return nullptr; }
+    if (device < 0 || device >= ndev) { set_err("invalid CUDA device index"); return nullptr; }
+    CU_CHECK(cudaSetDevice(device), nullptr);
+
+    b200flac_encoder* enc = new b200flac_encoder();
+    enc->params = *params;
+    derive_params(params, &enc->P);
+    enc->device = device;
+    enc->max_pcm_frames = max_pcm_frames_per_batch;
+    enc->n_slots = n_slots;
+    enc->slots = nullptr;
+    enc->windows = new std::map<u32, std::vector<double>>();
+    enc->launches = 0;
+    const bf_dev_params& P = enc->P;
+
+    const u32 bs = params->block_size;
+    enc->S = bs >= 2048 ? 32 : (bs >= 512 ? 16 : 8);
+    int nt = (int)((bs + enc->S - 1) / enc->S);
+    nt = (nt + 31) & ~31;
+    if (nt < 32) nt = 32;
+    if (nt > 1024) nt = 1024;
+    enc->NT = nt;
+    const size_t padn = (size_t)PADI(bs) + 1;
+    size_t sa = 0, sp = 0;
+    if (P.samples_in_smem) { sa += 2 * padn * 4; sp += padn * 4; }
+    if (P.heap_in_smem) sa += 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride;
+    enc->smem_analyze = sa + 16;
+    enc->smem_pack = sp + 16;
+    cudaError_t e = enc->S == 32 ? set_smem_attrs<32>(enc->smem_analyze, enc->smem_pack)
+                  : enc->S == 16 ? set_smem_attrs<16>(enc->smem_analyze, enc->smem_pack)
+                                 : set_smem_attrs<8>(enc->smem_analyze, enc->smem_pack);
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        b200flac_encoder_destroy(enc);
+        return nullptr;
+    }
+
+    const u64 M = max_pcm_frames_per_batch;
+    const u64 maxf = M / bs + 2 + 1024; // room for up to 1024 segment tails per batch (checked in submit)
+    enc->max_frames = (u32)maxf;
+    const u64 U = maxf * P.K;
+    enc->out_cap = M / bs * frame_bound_bytes(params, bs) + 1026 * frame_bound_bytes(params, bs) + 64;
+    if (params->no_verbatim_subframes) enc->out_cap *= 2;
+    enc->out_cap = (enc->out_cap + 15) & ~15ull;
+
+    enc->slots = new Slot[n_slots];
+    const size_t pcm_bytes = (size_t)M * params->channels * P.bytes_ps + 64;
+    for (int i = 0; i < n_slots; i++) {
+        Slot& s = enc->slots[i];
+#define ALLOC(ptr, bytes) do { cudaError_t e2 = cudaMalloc((void**)&(ptr), (bytes)); if (e2 != cudaSuccess) { \
+        snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e2)); \
+        b200flac_encoder_destroy(enc); return nullptr; } } while (0)
+#define ALLOCH(ptr, bytes) do { cudaError_t e2 = cudaMallocHost((void**)&(ptr), (bytes)); if (e2 != cudaSuccess) { \
+        snprintf(g_err, sizeof(g_err), "cudaMallocHost(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e2)); \
+        b200flac_encoder_destroy(enc); return nullptr; } } while (0)
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            set_err("cudaStreamCreate failed"); b200flac_encoder_destroy(enc); return nullptr;
+        }
+        for (int k = 0; k < BF_NUM_EVENTS; k++) cudaEventCreate(&s.ev[k]);
+        ALLOCH(s.h_pcm, pcm_bytes);
+        ALLOC(s.d_pcm, pcm_bytes);
+        ALLOCH(s.h_fd, maxf * sizeof(bf_frame_desc));
+        ALLOC(s.d_fd, maxf * sizeof(bf_frame_desc));
+        s.win_cap = (size_t)bs * 4;
+        ALLOCH(s.h_win, s.win_cap * sizeof(double));
+        ALLOC(s.d_win, s.win_cap * sizeof(double));
+        ALLOC(s.d_heads, U * sizeof(bf_lpc_head));
+        ALLOC(s.d_coefs, U * P.model_stride * sizeof(short));
+        ALLOC(s.d_plans, U * sizeof(b200flac_plan));
+        ALLOC(s.d_rice, U * P.rice_stride);
+        ALLOC(s.d_choice, maxf * sizeof(bf_frame_choice));
+        ALLOC(s.d_frame_bytes, maxf * sizeof(u32));
+        ALLOC(s.d_frame_off, maxf * sizeof(u64));
+        ALLOC(s.d_total, 64);
+        ALLOC(s.d_out, enc->out_cap + 64);
+        ALLOCH(s.h_frame_bytes, maxf * sizeof(u32));
+        ALLOCH(s.h_total, 64);
+        if (!P.samples_in_smem) ALLOC(s.d_gsamples, U * 2 * (size_t)P.samp_stride * sizeof(int));
+        if (!P.heap_in_smem) {
+            ALLOC(s.d_gheap, U * (size_t)P.heap_entries * sizeof(u64));
+            ALLOC(s.d_gkarr, U * ((size_t)P.heap_entries + 2 * (size_t)P.rice_stride));
+        }
+#undef ALLOC
+#undef ALLOCH
+    }
+    return enc;
+}
+
+extern "C" uint8_t* b200flac_encoder_slot_pcm(b200flac_encoder* enc, int slot)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots) return nullptr;
+    return enc->slots[slot].h_pcm;
+}
+
+static const std::vector<double>& get_window(b200flac_encoder* enc, u32 n)
+{
+    auto it = enc->windows->find(n);
+    if (it != enc->windows->end()) return it->second;
+    std::vector<double> w(n);
+    tukey_window(n, w.data());
+    return enc->windows->emplace(n, std::move(w)).first->second;
+}
+
+// builds frame descriptors + windows for the batch; returns number of frames or -1
+static long build_batch(b200flac_encoder* enc, Slot& s, const b200flac_segment* segs, u32 nseg, u64* pcm_frames_needed)
+{
+    const u32 bs = enc->params.block_size;
+    std::map<u32, u32> woff;     // length -> offset in doubles
+    size_t wused = 0;
+    u64 nf = 0, need = 0;
+    s.frame_pcm.clear();
+    const bool want_windows = enc->P.try_lpc != 0;
+    for (u32 g = 0; g < nseg; g++) {
+        const b200flac_segment& sg = segs[g];
+        if (sg.pcm_frame_offset + sg.n_pcm_frames > need) need = sg.pcm_frame_offset + sg.n_pcm_frames;
+        u64 pos = 0;
+        u32 fn = sg.first_frame_number;
+        while (pos < sg.n_pcm_frames) {
+            const u32 n = (u32)((sg.n_pcm_frames - pos) < bs ? (sg.n_pcm_frames - pos) : bs);
+            if (nf >= enc->max_frames) { set_err("batch has more frames than the encoder was created for"); return -1; }
+            bf_frame_desc& d = s.h_fd[nf];
+            d.pcm_off = sg.pcm_frame_offset + pos;
+            d.nsamp = n;
+            d.frame_number = fn++;
+            d.pad = 0;
+            d.window_off = 0;
+            if (want_windows) {
+                auto it = woff.find(n);
+                if (it == woff.end()) {
+                    if (wused + n > s.win_cap) {
+                        // grow the window staging (rare: many distinct tail lengths in one batch)
+                        size_t ncap = s.win_cap * 2 + n;
+                        double *nh = nullptr, *nd = nullptr;
+                        if (cudaMallocHost((void**)&nh, ncap * sizeof(double)) != cudaSuccess ||
+                            cudaMalloc((void**)&nd, ncap * sizeof(double)) != cudaSuccess) {
+                            set_err("out of memory growing the window table"); return -1;
+                        }
+                        cudaStreamSynchronize(s.stream);
+                        memcpy(nh, s.h_win, wused * sizeof(double));
+                        cudaFreeHost(s.h_win); cudaFree(s.d_win);
+                        s.h_win = nh; s.d_win = nd; s.win_cap = ncap;
+                    }
+                    const std::vector<double>& w = get_window(enc, n);
+                    memcpy(s.h_win + wused, w.data(), (size_t)n * sizeof(double));
+                    it = woff.emplace(n, (u32)wused).first;
+                    wused += n;
+                }
+                d.window_off = it->second;
+            }
+            s.frame_pcm.push_back(n);
+            nf++;
+            pos += n;
+        }
+    }
+    if (need > enc->max_pcm_frames) { set_err("batch has more PCM frames than the encoder was created for"); return -1; }
+    *pcm_frames_needed = need;
+    s.n_frames = (u32)nf;
+    // windows upload size is remembered through woff/wused: stash in h_total[1]
+    s.h_total[1] = wused;
+    return (long)nf;
+}
+
+template <int S>
+static void launch_analyze_pack(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
+{
+    const bf_dev_params& P = enc->P;
+    const u32 nf = s.n_frames, U = nf * P.K;
+    cudaStream_t st = s.stream;
+    k_analyze<S><<<U, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, s.d_heads, s.d_coefs, s.d_plans, s.d_rice,
+                                                       s.d_gsamples, s.d_gheap, s.d_gkarr);
+    cudaEventRecord(s.ev[2], st);
+    k_frame_select<<<(nf + 127) / 128, 128, 0, st>>>(s.d_fd, nf, P, s.d_plans, s.d_choice, s.d_frame_bytes);
+    k_scan_offsets<<<1, 1024, 0, st>>>(s.d_frame_bytes, nf, s.d_frame_off, s.d_total);
+    k_zero_output<<<148 * 4, 256, 0, st>>>((uint4*)d_out, s.d_total, out_cap);
+    cudaEventRecord(s.ev[3], st);
+    k_pack_subframes<S><<<nf * P.channels, enc->NT, enc->smem_pack, st>>>(d_pcm, s.d_fd, P, s.d_plans, s.d_rice,
+                                                                         s.d_choice, s.d_frame_off, (u32*)d_out,
+                                                                         s.d_gsamples, s.d_total, out_cap);
+    cudaEventRecord(s.ev[4], st);
+    k_frame_crc16<<<(nf * 32 + 127) / 128, 128, 0, st>>>(s.d_frame_off, s.d_frame_bytes, nf, d_out, s.d_total, out_cap);
+    cudaEventRecord(s.ev[5], st);
+    enc->launches += 6;
+}
+
+// enqueue the kernels of one batch on the slot's stream
+static int launch_batch(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
+{
+    const bf_dev_params& P = enc->P;
+    const u32 nf = s.n_frames, U = nf * P.K;
+    cudaStream_t st = s.stream;
+    cudaEventRecord(s.ev[0], st);
+    if (P.try_lpc) {
+        const u32 blocks = (U + LPC_WARPS * 32 - 1) / (LPC_WARPS * 32);
+        const u32 L = P.max_lpc_order;
+        if (L <= 8) k_lpc_model<8><<<blocks, LPC_WARPS * 32, 0, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
+        else if (L <= 12) k_lpc_model<12><<<blocks, LPC_WARPS * 32, 0, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
+        else if (L <= 16) k_lpc_model<16><<<blocks, LPC_WARPS * 32, 0, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
+        else k_lpc_model<32><<<blocks, LPC_WARPS * 32, 0, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
+        enc->launches += 1;
+    }
+    cudaEventRecord(s.ev[1], st);
+    if (enc->S == 32) launch_analyze_pack<32>(enc, s, d_pcm, d_out, out_cap);
+    else if (enc->S == 16) launch_analyze_pack<16>(enc, s, d_pcm, d_out, out_cap);
+    else launch_analyze_pack<8>(enc, s, d_pcm, d_out, out_cap);
+    CU_CHECK(cudaGetLastError(), 1);
+    s.timed = true;
+    return 0;
+}
+
+extern "C" int b200flac_encoder_submit(b200flac_encoder* enc, int slot, const uint8_t* pcm,
+                                       const b200flac_segment* segments, uint32_t n_segments)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots) { set_err("bad encoder or slot"); return 1; }
+    if (!pcm || !segments || n_segments == 0 || n_segments > BF_MAX_SEGMENTS) { set_err("bad segments"); return 1; }
+    Slot& s = enc->slots[slot];
+    if (s.busy) { set_err("slot is busy: collect it first"); return 1; }
+    CU_CHECK(cudaSetDevice(enc->device), 1);
+    u64 need = 0;
+    const long nf = build_batch(enc, s, segments, n_segments, &need);
+    if (nf < 0) return 1;
+    if (nf == 0) { s.busy = true; s.timed = false; *s.h_total = 0; return 0; }
+    const size_t pcm_bytes = (size_t)need * enc->params.channels * enc->P.bytes_ps;
+    if (pcm != s.h_pcm) memcpy(s.h_pcm, pcm, pcm_bytes); // stage through pinned memory
+    cudaStream_t st = s.stream;
+    CU_CHECK(cudaMemcpyAsync(s.d_pcm, s.h_pcm, pcm_bytes, cudaMemcpyHostToDevice, st), 1);
+    CU_CHECK(cudaMemcpyAsync(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), cudaMemcpyHostToDevice, st), 1);
+    const size_t wused = (size_t)s.h_total[1];
+    if (wused) CU_CHECK(cudaMemcpyAsync(s.d_win, s.h_win, wused * sizeof(double), cudaMemcpyHostToDevice, st), 1);
+    if (launch_batch(enc, s, s.d_pcm, s.d_out, enc->out_cap)) return 1;
+    CU_CHECK(cudaMemcpyAsync(s.h_frame_bytes, s.d_frame_bytes, (size_t)nf * sizeof(u32), cudaMemcpyDeviceToHost, st), 1);
+    CU_CHECK(cudaMemcpyAsync(s.h_total, s.d_total, sizeof(u64), cudaMemcpyDeviceToHost, st), 1);
+    s.busy = true;
+    return 0;
+}
+
+extern "C" int b200flac_encoder_collect(b200flac_encoder* enc, int slot, uint8_t* out, uint64_t out_capacity,
+                                        uint64_t* out_bytes, uint32_t* frame_bytes, uint32_t* frame_pcm,
+                                        uint32_t frame_capacity, uint32_t* n_frames)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots) { set_err("bad encoder or slot"); return 1; }
+    Slot& s = enc->slots[slot];
+    if (!s.busy) { set_err("slot has no batch in flight"); return 1; }
+    CU_CHECK(cudaSetDevice(enc->device), 1);
+    s.busy = false;
+    if (s.n_frames == 0) { if (out_bytes) *out_bytes = 0; if (n_frames) *n_frames = 0; return 0; }
+    CU_CHECK(cudaStreamSynchronize(s.stream), 1);
+    const u64 total = *s.h_total;
+    if (total + 16 > enc->out_cap) { set_err("encoded batch exceeds the device output buffer (VERBATIM disabled?)"); return 1; }
+    if (total > out_capacity) { set_err("output buffer too small"); return 1; }
+    if (s.n_frames > frame_capacity && (frame_bytes || frame_pcm)) { set_err("frame arrays too small"); return 1; }
+    CU_CHECK(cudaMemcpyAsync(out, s.d_out, (size_t)total, cudaMemcpyDeviceToHost, s.stream), 1);
+    if (frame_bytes) memcpy(frame_bytes, s.h_frame_bytes, (size_t)s.n_frames * sizeof(u32));
+    if (frame_pcm) memcpy(frame_pcm, s.frame_pcm.data(), (size_t)s.n_frames * sizeof(u32));
+    CU_CHECK(cudaStreamSynchronize(s.stream), 1);
+    if (out_bytes) *out_bytes = total;
+    if (n_frames) *n_frames = s.n_frames;
+    return 0;
+}
+
+extern "C" int b200flac_encoder_encode(b200flac_encoder* enc, const uint8_t* pcm,
+                                       const b200flac_segment* segments, uint32_t n_segments,
+                                       uint8_t* out, uint64_t out_capacity, uint64_t* out_bytes,
+                                       uint32_t* frame_bytes, uint32_t* frame_pcm, uint32_t frame_capacity,
+                                       uint32_t* n_frames)
+{
+    if (b200flac_encoder_submit(enc, 0, pcm, segments, n_segments)) return 1;
+    return b200flac_encoder_collect(enc, 0, out, out_capacity, out_bytes, frame_bytes, frame_pcm, frame_capacity, n_frames);
+}
+
+extern "C" int b200flac_encoder_encode_device(b200flac_encoder* enc, int slot, const void* d_pcm,
+                                              const b200flac_segment* segments, uint32_t n_segments,
+                                              void* d_out, uint64_t out_capacity, uint64_t* out_bytes,
+                                              uint32_t* n_frames, float* elapsed_ms)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots) { set_err("bad encoder or slot"); return 1; }
+    if (!d_pcm || !d_out || !segments || n_segments == 0) { set_err("bad arguments"); return 1; }
+    if (((uintptr_t)d_out & 15) || ((uintptr_t)d_pcm & 3)) { set_err("d_out must be 16-byte and d_pcm 4-byte aligned"); return 1; }
+    Slot& s = enc->slots[slot];
+    if (s.busy) { set_err("slot is busy"); return 1; }
+    CU_CHECK(cudaSetDevice(enc->device), 1);
+    u64 need = 0;
+    const long nf = build_batch(enc, s, segments, n_segments, &need);
+    if (nf < 0) return 1;
+    if (nf == 0) { if (out_bytes) *out_bytes = 0; if (n_frames) *n_frames = 0; return 0; }
+    cudaStream_t st = s.stream;
+    CU_CHECK(cudaMemcpyAsync(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), cudaMemcpyHostToDevice, st), 1);
+    const size_t wused = (size_t)s.h_total[1];
+    if (wused) CU_CHECK(cudaMemcpyAsync(s.d_win, s.h_win, wused * sizeof(double), cudaMemcpyHostToDevice, st), 1);
+    const u64 cap = out_capacity & ~15ull;
+    if (launch_batch(enc, s, (const uint8_t*)d_pcm, (uint8_t*)d_out, cap)) return 1;
+    CU_CHECK(cudaMemcpyAsync(s.h_total, s.d_total, sizeof(u64), cudaMemcpyDeviceToHost, st), 1);
+    CU_CHECK(cudaMemcpyAsync(s.h_frame_bytes, s.d_frame_bytes, (size_t)nf * sizeof(u32), cudaMemcpyDeviceToHost, st), 1);
+    CU_CHECK(cudaStreamSynchronize(st), 1);
+    const u64 total = *s.h_total;
+    if (total + 16 > cap) { set_err("encoded batch exceeds the output buffer"); return 1; }
+    if (out_bytes) *out_bytes = total;
+    if (n_frames) *n_frames = (u32)nf;
+    if (elapsed_ms) cudaEventElapsedTime(elapsed_ms, s.ev[0], s.ev[5]);
+    return 0;
+}
+
+extern "C" int b200flac_encoder_last_kernel_ms(b200flac_encoder* enc, int slot, float* ms, int capacity)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots || !ms) return 0;
+    Slot& s = enc->slots[slot];
+    if (!s.timed) return 0;
+    cudaSetDevice(enc->device);
+    if (cudaEventSynchronize(s.ev[5]) != cudaSuccess) return 0;
+    int n = 0;
+    for (int i = 0; i < 5 && i < capacity; i++, n++) {
+        ms[i] = 0.f;
+        cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]);
+    }
+    return n;
+}
+
+extern "C" uint64_t b200flac_encoder_launch_count(const b200flac_encoder* enc) { return enc ? enc->launches : 0; }
+
+extern "C" int b200flac_encoder_get_plans(b200flac_encoder* enc, int slot, b200flac_plan* plans, uint8_t* rice,
+                                          uint32_t* rice_stride, uint8_t* assignments, uint32_t* candidates_per_frame)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots) { set_err("bad encoder or slot"); return 1; }
+    Slot& s = enc->slots[slot];
+    CU_CHECK(cudaSetDevice(enc->device), 1);
+    CU_CHECK(cudaStreamSynchronize(s.stream), 1);
+    const size_t U = (size_t)s.n_frames * enc->P.K;
+    if (plans) CU_CHECK(cudaMemcpy(plans, s.d_plans, U * sizeof(b200flac_plan), cudaMemcpyDeviceToHost), 1);
+    if (rice) CU_CHECK(cudaMemcpy(rice, s.d_rice, U * enc->P.rice_stride, cudaMemcpyDeviceToHost), 1);
+    if (rice_stride) *rice_stride = enc->P.rice_stride;
+    if (candidates_per_frame) *candidates_per_frame = enc->P.K;
+    if (assignments) {
+        std::vector<bf_frame_choice> ch(s.n_frames);
+        CU_CHECK(cudaMemcpy(ch.data(), s.d_choice, s.n_frames * sizeof(bf_frame_choice), cudaMemcpyDeviceToHost), 1);
+        for (u32 i = 0; i < s.n_frames; i++) assignments[i] = ch[i].assignment;
+    }
+    return 0;
+}
