@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- FLAC encode throughput of the B200 engine (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # this engine
+    python bench.py --impl reference --steps K --warmup W  # the reference's C encoder on host cores
+
+Workload (BASELINE.json configs[1]): 1 h of synthetic 44.1 kHz / 16-bit stereo PCM
+(158,760,000 PCM frames = 317.52 M channel-samples), block_size 4096, max_lpc_order 12,
+adaptive mid-side, max_residual_partition_order 6 (the reference standalone default,
+src/encoders/flac.c:1647), frames sharded by range: every rank (GPU) encodes its own hour.
+
+A step = one pass of the hot path (5 kernels) over the rank's whole hour.
+  value : whole-job Msamples/s with the PCM already resident in HBM and the frames left in
+          HBM (b200flac_encoder_encode_device), wall clock around K steps bracketed by
+          barrier + device synchronize, max over ranks.
+  e2e   : same metric through the host-buffer C-ABI calls (b200flac_encoder_submit/collect):
+          pinned host PCM -> H2D -> kernels -> D2H frame bytes, every step, 3 batches in flight.
+  roofline : dominant kernel, algorithmic bytes (PCM in + frame bytes out) / its CUDA-event time.
+  cpu_baseline : oracle/_ref/flacenc (the compiled reference) on the box's host cores, N=1 only.
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "python-audio-tools_b200"))
+
+SAMPLE_RATE, CHANNELS, BPS = 44100, 2, 16
+BLOCK, LPC, PO = 4096, 12, 6
+HOUR_FRAMES = 158760000
+METRIC = "flac_encode_msamples_per_s"
+UNIT = "Msamples/s"
+REF_FLACENC = os.path.join(ROOT, "oracle", "_ref", "flacenc")
+ORACLE_CLI = os.path.join(ROOT, "oracle", "flacenc_oracle")
+
+
+def workload_name(frames):
+    return ("%.0f s synthetic 44.1 kHz/16-bit stereo per GPU, block_size 4096, max_lpc_order 12, "
+            "adaptive mid-side, max_residual_partition_order 6" % (frames / SAMPLE_RATE))
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's own C encoder (oracle/_ref/flacenc), one process per host core
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_round(pcm_path, nproc, sample_frames, tmpdir):
+    """runs nproc reference encoders in parallel over the same sample; returns seconds"""
+    flags = ["-c", str(CHANNELS), "-r", str(SAMPLE_RATE), "-b", str(BPS), "-B", str(BLOCK), "-l", str(LPC),
+             "-R", str(PO), "-M"]
+    t0 = time.perf_counter()
+    procs = []
+    for i in range(nproc):
+        out = os.path.join(tmpdir, "ref%d.flac" % i)
+        procs.append(subprocess.Popen([REF_FLACENC] + flags + [out], stdin=open(pcm_path, "rb"),
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("reference flacenc failed")
+    return time.perf_counter() - t0
+
+
+def make_cpu_sample(seconds, tmpdir):
+    """synthetic PCM of the workload (same generator, seed 1235) written to tmpfs by the oracle CLI"""
+    frames = int(seconds * SAMPLE_RATE)
+    pcm_path = os.path.join(tmpdir, "sample.pcm")
+    subprocess.run([ORACLE_CLI, "--synth", "1235:%d" % frames, "--dump-pcm", pcm_path, "-B", "4096", "-l", "0",
+                    os.path.join(tmpdir, "discard.flac")], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    return pcm_path, frames
+
+
+def cpu_baseline(seconds_per_proc=120.0, rounds=1):
+    if not (os.path.exists(REF_FLACENC) and os.path.exists(ORACLE_CLI)):
+        return None
+    cores = os.cpu_count() or 1
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=shm) as d:
+        pcm_path, frames = make_cpu_sample(seconds_per_proc, d)
+        cpu_reference_round(pcm_path, min(cores, 2), frames, d)  # warm the page cache / binary
+        best = min(cpu_reference_round(pcm_path, cores, frames, d) for _ in range(rounds))
+        single = cpu_reference_round(pcm_path, 1, frames, d)
+    samples = frames * CHANNELS
+    return {"value": cores * samples / best / 1e6, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "%d s of the workload per process, one oracle/_ref/flacenc process per core, PCM and "
+                      "output on tmpfs" % seconds_per_proc,
+            "single_process_value": samples / single / 1e6}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    if not (os.path.exists(REF_FLACENC) and os.path.exists(ORACLE_CLI)):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/flacenc not built"}))
+        return
+    cores = os.cpu_count() or 1
+    seconds = 60.0
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=shm) as d:
+        pcm_path, frames = make_cpu_sample(seconds, d)
+        for _ in range(args.warmup):
+            cpu_reference_round(pcm_path, cores, frames, d)
+        t = 0.0
+        for _ in range(args.steps):
+            t += cpu_reference_round(pcm_path, cores, frames, d)
+    samples = frames * CHANNELS * cores * args.steps
+    value = samples / t / 1e6
+    sample = ("each step: %d processes (one per host core) x %d s of the workload through the compiled "
+              "reference encoder" % (cores, seconds))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32/i64/f64",
+        "data": "synthetic", "config": {"workload": workload_name(HOUR_FRAMES), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seconds", type=float, default=3600.0, help="audio per GPU per step (default: the 1 h config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import b200flac
+
+    if not torch.cuda.is_available() or b200flac.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L = b200flac.lib()
+    dev = local_rank
+    n_frames_pcm = int(args.seconds * SAMPLE_RATE)
+    frame_bytes = CHANNELS * BPS // 8
+    pcm_bytes = n_frames_pcm * frame_bytes
+    params = b200flac.make_params(SAMPLE_RATE, CHANNELS, BPS, block_size=BLOCK, max_lpc_order=LPC,
+                                  max_residual_partition_order=PO, adaptive_mid_side=True)
+
+    # ---- device-resident arm -----------------------------------------------------------------
+    enc = b200flac.Encoder(params, device=dev, max_pcm_frames_per_batch=n_frames_pcm, n_slots=1)
+    out_cap = enc.output_bound(n_frames_pcm, 1)
+    d_pcm = L.b200flac_device_alloc(dev, pcm_bytes)
+    d_out = L.b200flac_device_alloc(dev, out_cap)
+    if not d_pcm or not d_out:
+        raise SystemExit("device allocation failed: " + L.b200flac_last_error().decode())
+    if L.b200flac_device_synth_pcm(dev, d_pcm, 1235 + rank, CHANNELS, BPS, 0, n_frames_pcm):
+        raise SystemExit("synth failed")
+    segs = [(0, n_frames_pcm, 0)]
+
+    out_bytes = 0
+    for _ in range(max(args.warmup, 3)):
+        out_bytes, n_flac_frames, _ = enc.encode_device(d_pcm, segs, d_out, out_cap)
+    launches0 = enc.launch_count()
+    clocks = ClockSampler(dev)
+    barrier()
+    clocks.start()
+    kernel_ms = [0.0] * 5
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_bytes, n_flac_frames, _ = enc.encode_device(d_pcm, segs, d_out, out_cap)
+        for i, v in enumerate(enc.kernel_ms(0)):
+            kernel_ms[i] += v
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clk = clocks.stop()
+    launches = enc.launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    samples_per_step = n_frames_pcm * CHANNELS
+    value = world * samples_per_step * args.steps / elapsed / 1e6
+    kernel_ms = [v / args.steps for v in kernel_ms]
+    names = ["lpc_model", "analyze", "select_scan_zero", "pack", "crc16"]
+    dom = max(range(5), key=lambda i: kernel_ms[i])
+    algo_bytes = pcm_bytes + out_bytes            # PCM in at native width + frame bytes out
+    peak, peak_kind = peaks()
+    achieved = algo_bytes / (kernel_ms[dom] * 1e-3) / 1e9
+    pipeline = algo_bytes / (sum(kernel_ms) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel_ms": dict(zip(names, kernel_ms)),
+                "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak,
+                "bytes_per_sample": algo_bytes / samples_per_step}
+
+    # ---- end-to-end arm: pinned host PCM -> H2D -> kernels -> D2H, through submit/collect ---------
+    e2e = None
+    if not args.no_e2e:
+        batch_frames = BLOCK * 2048
+        nslots = 3
+        enc2 = b200flac.Encoder(params, device=dev, max_pcm_frames_per_batch=batch_frames, n_slots=nslots)
+        h_pcm = L.b200flac_host_alloc(pcm_bytes)
+        if not h_pcm:
+            raise SystemExit("pinned allocation failed")
+        L.b200flac_device_download(dev, h_pcm, d_pcm, pcm_bytes)
+        bcap = enc2.output_bound(batch_frames, 1)
+        fcap = batch_frames // BLOCK + 4
+        h_out = [L.b200flac_host_alloc(bcap) for _ in range(nslots)]
+        fb = [np.empty(fcap, dtype=np.uint32) for _ in range(nslots)]
+        batches = []
+        pos = 0
+        while pos < n_frames_pcm:
+            n = min(batch_frames, n_frames_pcm - pos)
+            batches.append((pos, n))
+            pos += n
+        nb64, nf32 = C.c_uint64(0), C.c_uint32(0)
+
+        def e2e_step():
+            total = 0
+            for b, (off, n) in enumerate(batches):
+                slot = b % nslots
+                if b >= nslots:
+                    if L.b200flac_encoder_collect(enc2.h, slot, h_out[slot], bcap, C.byref(nb64),
+                                                  fb[slot].ctypes.data, None, fcap, C.byref(nf32)):
+                        raise SystemExit(L.b200flac_last_error().decode())
+                    total += nb64.value
+                seg = b200flac.Segment(0, n, off // BLOCK, 0)
+                if L.b200flac_encoder_submit(enc2.h, slot, h_pcm + off * frame_bytes, C.byref(seg), 1):
+                    raise SystemExit(L.b200flac_last_error().decode())
+            for b in range(max(0, len(batches) - nslots), len(batches)):
+                slot = b % nslots
+                if L.b200flac_encoder_collect(enc2.h, slot, h_out[slot], bcap, C.byref(nb64),
+                                              fb[slot].ctypes.data, None, fcap, C.byref(nf32)):
+                    raise SystemExit(L.b200flac_last_error().decode())
+                total += nb64.value
+            return total
+
+        for _ in range(2):
+            e2e_bytes = e2e_step()
+        launches_e0 = enc2.launch_count()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_bytes = e2e_step()
+        barrier()
+        e_elapsed = time.perf_counter() - t0
+        launches += enc2.launch_count() - launches_e0
+        if dist is not None:
+            t = torch.tensor([e_elapsed], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_elapsed = float(t.item())
+        assert e2e_bytes == out_bytes, "e2e arm produced %d bytes, resident arm %d" % (e2e_bytes, out_bytes)
+        e2e = {"value": world * samples_per_step * args.steps / e_elapsed / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": pcm_bytes, "d2h_bytes_per_step": int(e2e_bytes + 4 * n_flac_frames),
+               "ms_per_step": 1000.0 * e_elapsed / args.steps,
+               "what": "b200flac_encoder_submit/collect, pinned host PCM in, frame bytes out to pinned host "
+                       "memory, %d-block batches, %d in flight" % (batch_frames // BLOCK, nslots)}
+        for p in h_out:
+            L.b200flac_host_free(p)
+        L.b200flac_host_free(h_pcm)
+        enc2.close()
+
+    base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base = cpu_baseline()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1000.0 * elapsed / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32/i64/f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(n_frames_pcm), "block_size": BLOCK, "max_lpc_order": LPC,
+                       "max_residual_partition_order": PO, "adaptive_mid_side": True,
+                       "flac_frames_per_step_per_gpu": int(n_flac_frames),
+                       "compressed_ratio": out_bytes / pcm_bytes,
+                       "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (pcm_bytes / 1e6),
+                       "sharding": "frame range per GPU, no collective"},
+            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+        }
+        print(json.dumps(line))
+    L.b200flac_device_free(dev, d_pcm)
+    L.b200flac_device_free(dev, d_out)
+    enc.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,12 @@ int b200flac_encoder_last_kernel_ms(b200flac_encoder *enc, int slot, float *ms, 
 /* number of kernel launches issued by this encoder so far */
 uint64_t b200flac_encoder_launch_count(const b200flac_encoder *enc);
 
+/* page-locked host memory: PCM handed to submit() from such memory (or from
+ * b200flac_encoder_slot_pcm) is copied host->device directly and asynchronously;
+ * pageable memory is first staged through the slot's pinned buffer */
+void *b200flac_host_alloc(uint64_t bytes);
+void  b200flac_host_free(void *p);
+
 /* raw device memory helpers so a host language without a CUDA binding can stage
  * device-resident input (bench.py uses them; torch is not required) */
 void *b200flac_device_alloc(int device, uint64_t bytes);

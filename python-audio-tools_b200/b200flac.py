@@ -80,6 +80,9 @@ def lib():
     L.b200flac_encoder_last_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_int]
     L.b200flac_encoder_launch_count.restype = C.c_uint64
     L.b200flac_encoder_launch_count.argtypes = [vp]
+    L.b200flac_host_alloc.restype = vp
+    L.b200flac_host_alloc.argtypes = [C.c_uint64]
+    L.b200flac_host_free.argtypes = [vp]
     L.b200flac_device_alloc.restype = vp
     L.b200flac_device_alloc.argtypes = [C.c_int, C.c_uint64]
     L.b200flac_device_free.argtypes = [C.c_int, vp]

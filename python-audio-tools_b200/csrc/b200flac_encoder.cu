@@ -317,7 +317,6 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     enc->out_cap = (enc->out_cap + 15) & ~15ull;
 
     enc->slots = new Slot[n_slots];
-    const size_t pcm_bytes = (size_t)M * params->channels * P.bytes_ps + 64;
     for (int i = 0; i < n_slots; i++) {
         Slot& s = enc->slots[i];
 #define ALLOC(ptr, bytes) do { cudaError_t e2 = cudaMalloc((void**)&(ptr), (bytes)); if (e2 != cudaSuccess) { \
@@ -330,8 +329,6 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
             set_err("cudaStreamCreate failed"); b200flac_encoder_destroy(enc); return nullptr;
         }
         for (int k = 0; k < BF_NUM_EVENTS; k++) cudaEventCreate(&s.ev[k]);
-        ALLOCH(s.h_pcm, pcm_bytes);
-        ALLOC(s.d_pcm, pcm_bytes);
         ALLOCH(s.h_fd, maxf * sizeof(bf_frame_desc));
         ALLOC(s.d_fd, maxf * sizeof(bf_frame_desc));
         s.win_cap = (size_t)bs * 4;
@@ -345,7 +342,6 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         ALLOC(s.d_frame_bytes, maxf * sizeof(u32));
         ALLOC(s.d_frame_off, maxf * sizeof(u64));
         ALLOC(s.d_total, 64);
-        ALLOC(s.d_out, enc->out_cap + 64);
         ALLOCH(s.h_frame_bytes, maxf * sizeof(u32));
         ALLOCH(s.h_total, 64);
         if (!P.samples_in_smem) ALLOC(s.d_gsamples, U * 2 * (size_t)P.samp_stride * sizeof(int));
@@ -359,11 +355,40 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     return enc;
 }
 
+// host-path buffers (device PCM + device output, pinned staging) are only needed by
+// submit/collect; encode_device works on caller-provided device memory
+static int ensure_host_path(b200flac_encoder* enc, Slot& s, bool want_staging)
+{
+    const size_t pcm_bytes = (size_t)enc->max_pcm_frames * enc->params.channels * enc->P.bytes_ps + 64;
+    if (!s.d_pcm) CU_CHECK(cudaMalloc((void**)&s.d_pcm, pcm_bytes), 1);
+    if (!s.d_out) CU_CHECK(cudaMalloc((void**)&s.d_out, enc->out_cap + 64), 1);
+    if (want_staging && !s.h_pcm) CU_CHECK(cudaMallocHost((void**)&s.h_pcm, pcm_bytes), 1);
+    return 0;
+}
+
+static bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" uint8_t* b200flac_encoder_slot_pcm(b200flac_encoder* enc, int slot)
 {
     if (!enc || slot < 0 || slot >= enc->n_slots) return nullptr;
+    if (cudaSetDevice(enc->device) != cudaSuccess) return nullptr;
+    if (ensure_host_path(enc, enc->slots[slot], true)) return nullptr;
     return enc->slots[slot].h_pcm;
 }
+
+extern "C" void* b200flac_host_alloc(uint64_t bytes)
+{
+    void* p = nullptr;
+    CU_CHECK(cudaMallocHost(&p, (size_t)bytes + 64), nullptr);
+    return p;
+}
+
+extern "C" void b200flac_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 static const std::vector<double>& get_window(b200flac_encoder* enc, u32 n)
 {
@@ -493,9 +518,15 @@ extern "C" int b200flac_encoder_submit(b200flac_encoder* enc, int slot, const ui
     if (nf < 0) return 1;
     if (nf == 0) { s.busy = true; s.timed = false; *s.h_total = 0; return 0; }
     const size_t pcm_bytes = (size_t)need * enc->params.channels * enc->P.bytes_ps;
-    if (pcm != s.h_pcm) memcpy(s.h_pcm, pcm, pcm_bytes); // stage through pinned memory
     cudaStream_t st = s.stream;
-    CU_CHECK(cudaMemcpyAsync(s.d_pcm, s.h_pcm, pcm_bytes, cudaMemcpyHostToDevice, st), 1);
+    const uint8_t* src = pcm;
+    if (pcm != s.h_pcm && !is_pinned(pcm)) {
+        // pageable caller memory: stage through the slot's pinned buffer so the copy is asynchronous
+        if (ensure_host_path(enc, s, true)) return 1;
+        memcpy(s.h_pcm, pcm, pcm_bytes);
+        src = s.h_pcm;
+    } else if (ensure_host_path(enc, s, false)) return 1;
+    CU_CHECK(cudaMemcpyAsync(s.d_pcm, src, pcm_bytes, cudaMemcpyHostToDevice, st), 1);
     CU_CHECK(cudaMemcpyAsync(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), cudaMemcpyHostToDevice, st), 1);
     const size_t wused = (size_t)s.h_total[1];
     if (wused) CU_CHECK(cudaMemcpyAsync(s.d_win, s.h_win, wused * sizeof(double), cudaMemcpyHostToDevice, st), 1);
