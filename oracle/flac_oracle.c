@@ -1086,6 +1086,51 @@ int orc_encode_stream(const orc_options *opt, unsigned sample_rate, unsigned cha
     return 1;
 }
 
+/* frames of a contiguous PCM range only (no stream head): what one shard of a frame-range
+ * sharded encode produces.  Frame numbers start at first_frame_number. */
+int orc_encode_range(const orc_options *opt, unsigned sample_rate, unsigned channels, unsigned bps,
+                     const uint8_t *pcm, size_t pcm_bytes, unsigned first_frame_number,
+                     uint8_t **frames_out, size_t *frames_len, uint32_t **frame_bytes_out,
+                     size_t *n_frames_out)
+{
+    orc_encoder *e = orc_encoder_new(opt, sample_rate, channels, bps);
+    const unsigned bytes_ps = bps / 8;
+    const size_t fb = (size_t)channels * bytes_ps;
+    const uint64_t total = pcm_bytes / fb;
+    const unsigned block = opt->block_size;
+    int32_t *chan[ORC_MAX_CHANNELS];
+    const int32_t *chanp[ORC_MAX_CHANNELS];
+    uint8_t *fbuf = (uint8_t *)malloc(orc_frame_bound(e, block) * 4 + 65536);
+    uint8_t *out = NULL;
+    size_t out_len = 0, out_cap = 0, nfr = 0, cap = 0;
+    uint32_t *sizes = NULL;
+    uint64_t pos = 0;
+    unsigned c, fn = first_frame_number;
+    for (c = 0; c < channels; c++) chan[c] = (int32_t *)malloc(sizeof(int32_t) * (block + 1));
+    while (pos < total) {
+        unsigned n = (unsigned)((total - pos) < block ? (total - pos) : block), i;
+        size_t flen;
+        for (i = 0; i < n; i++)
+            for (c = 0; c < channels; c++)
+                chan[c][i] = load_le_signed(pcm + ((pos + i) * channels + c) * bytes_ps, bytes_ps);
+        for (c = 0; c < channels; c++) chanp[c] = chan[c];
+        flen = orc_encode_frame(e, chanp, n, fn++, fbuf, NULL);
+        if (out_len + flen > out_cap) { out_cap = (out_cap + flen) * 2; out = (uint8_t *)realloc(out, out_cap); }
+        memcpy(out + out_len, fbuf, flen);
+        out_len += flen;
+        if (nfr == cap) { cap = cap ? cap * 2 : 256; sizes = (uint32_t *)realloc(sizes, cap * sizeof(uint32_t)); }
+        sizes[nfr++] = (uint32_t)flen;
+        pos += n;
+    }
+    for (c = 0; c < channels; c++) free(chan[c]);
+    free(fbuf);
+    orc_encoder_free(e);
+    *frames_out = out; *frames_len = out_len;
+    if (frame_bytes_out) *frame_bytes_out = sizes; else free(sizes);
+    if (n_frames_out) *n_frames_out = nfr;
+    return 1;
+}
+
 void orc_free(void *p) { free(p); }
 
 /* ------------------------------------------------------------------ */

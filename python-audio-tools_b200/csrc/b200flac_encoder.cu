@@ -291,7 +291,7 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     int nt = (int)((bs + enc->S - 1) / enc->S);
     nt = (nt + 31) & ~31;
     if (nt < 32) nt = 32;
-    if (nt > 1024) nt = 1024;
+    if (nt > 512) nt = 512; // register budget: 512 threads x <=128 regs; longer blocks take several passes
     enc->NT = nt;
     const size_t padn = (size_t)PADI(bs) + 1;
     size_t sa = 0, sp = 0;

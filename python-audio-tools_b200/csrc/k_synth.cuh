@@ -1,7 +1,7 @@
 // k_synth.cuh -- deterministic integer-only synthetic PCM, generated
-// directly in HBM as packed little-endian samples.  The formulas are the ones of
-// oracle/flac_oracle.c (orc_synth_pcm); tests/test_gpu_parity.py checks that both
-// produce the same bytes.  Benchmark/test input only -- not part of the encode path.
+// directly in HBM as packed little-endian samples.  The test suite carries a plain-C twin of
+// these formulas and checks that both produce the same bytes (tests/test_gpu_parity.py).
+// Benchmark/test input only -- not part of the encode path.
 #pragma once
 #include "flac_common.cuh"
 

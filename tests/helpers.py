@@ -39,6 +39,9 @@ def orc():
                                         C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.orc_free.argtypes = [C.c_void_p]
+        L.orc_encode_range.argtypes = [C.POINTER(OrcOptions), C.c_uint, C.c_uint, C.c_uint, C.c_void_p,
+                                       C.c_size_t, C.c_uint, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.orc_synth_pcm.argtypes = [C.c_uint64, C.c_uint, C.c_uint, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_crc8.restype = C.c_uint8
         L.orc_crc8.argtypes = [C.c_void_p, C.c_size_t]
@@ -130,6 +133,31 @@ def oracle_encode(pcm, sample_rate, channels, bits_per_sample, opts, want_offset
     orc().orc_free(offs)
     orc().orc_free(lens)
     return (data, res_offs) if want_offsets else data
+
+
+def _orc_options(opts):
+    return OrcOptions(opts["block_size"], opts["max_lpc_order"], opts["min_residual_partition_order"],
+                      opts["max_residual_partition_order"], int(opts["mid_side"]), int(opts["adaptive_mid_side"]),
+                      int(opts["exhaustive_model_search"]), int(opts["disable_verbatim_subframes"]),
+                      int(opts["disable_constant_subframes"]), int(opts["disable_fixed_subframes"]),
+                      int(opts["disable_lpc_subframes"]), opts["padding_size"], None)
+
+
+def oracle_encode_range(pcm, sample_rate, channels, bits_per_sample, opts, first_frame_number=0):
+    """frames only (no stream head) of a PCM range: (frame bytes, [size of each frame])"""
+    o = _orc_options(opts)
+    out, n, sizes, nfr = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+    buf = np.frombuffer(pcm, dtype=np.uint8)
+    ptr = buf.ctypes.data if len(buf) else None
+    orc().orc_encode_range(C.byref(o), sample_rate, channels, bits_per_sample, ptr, len(buf),
+                           first_frame_number, C.byref(out), C.byref(n), C.byref(sizes), C.byref(nfr))
+    data = C.string_at(out.value, n.value) if n.value else b""
+    sz = []
+    if nfr.value:
+        sz = np.ctypeslib.as_array(C.cast(sizes.value, C.POINTER(C.c_uint32)), (nfr.value,)).tolist()
+    orc().orc_free(out)
+    orc().orc_free(sizes)
+    return data, sz
 
 
 def have_ref():

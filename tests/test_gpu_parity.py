@@ -82,3 +82,157 @@ def test_device_synth_matches_oracle_generator(built):
         assert b.lib().b200flac_device_download(0, host.ctypes.data, d, nbytes) == 0
         b.lib().b200flac_device_free(0, d)
         assert host.tobytes() == helpers.synth_pcm(99, ch, bps, n, first_frame=12345)
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors: outputs of the COMPILED REFERENCE (tests/golden/golden.json)
+# ---------------------------------------------------------------------------------------------
+import hashlib  # noqa: E402
+import json  # noqa: E402
+
+from golden.golden_cases import CASES, LEVELS, case_pcm  # noqa: E402
+
+with open(os.path.join(helpers.GOLDEN, "golden.json")) as _fh:
+    GOLD = {c["name"]: c for c in json.load(_fh)["cases"]}
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_reference_outputs(case, tmp_path, built):
+    """the engine's file == the reference encoder's file (sha256 recorded from oracle/_ref/flacenc)"""
+    g = GOLD[case["name"]]
+    pcm = case_pcm(case)
+    got = _encode_b200(tmp_path, pcm, case["rate"], case["channels"], case["bps"], helpers.options(**case["options"]))
+    ff = helpers.first_frame_offset(got)
+    assert got[ff:ff + 64].hex() == g["first_frame_bytes"]
+    assert len(got) == g["length"]
+    assert hashlib.sha256(got).hexdigest() == g["sha256"]
+
+
+@pytest.mark.parametrize("mask", range(16))
+def test_disable_subframe_flags(mask, tmp_path, built):
+    """the reference's debug switches (flac.c:732-809 truth table); the oracle restates them"""
+    o = helpers.options(block_size=1024, max_lpc_order=8, max_residual_partition_order=4, mid_side=True,
+                        disable_verbatim_subframes=bool(mask & 1), disable_constant_subframes=bool(mask & 2),
+                        disable_fixed_subframes=bool(mask & 4), disable_lpc_subframes=bool(mask & 8))
+    # noise (VERBATIM wins), a constant block, silence and a tone, so every branch is reachable
+    rng = np.random.RandomState(mask)
+    parts = [rng.randint(-32768, 32768, size=2048), np.full(2048, 1234), np.zeros(2048, dtype=np.int64),
+             (8000 * np.sin(np.arange(4096) * 0.05)).astype(np.int64)]
+    pcm = helpers.pack_pcm(np.concatenate(parts).astype(np.int32), 16)
+    _check(tmp_path, pcm, 44100, 2, 16, o)
+
+
+def test_frame_layer_many_segments(built):
+    """b200flac_encoder_encode with several streams in one batch (config #5 shape): every segment is
+    blocked on its own and numbered from its own first_frame_number"""
+    b = _b200()
+    o = helpers.options(block_size=1152, max_lpc_order=8, max_residual_partition_order=4, adaptive_mid_side=True)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 2, 16, **kw)
+    lens = [1152 * 3 + 7, 1152 * 2, 5, 1152 * 4 + 1151]
+    firsts = [0, 100, 127, 70000]
+    tracks = [helpers.synth_pcm(900 + i, 2, 16, n) for i, n in enumerate(lens)]
+    pcm = b"".join(tracks)
+    segs, pos = [], 0
+    for n, f in zip(lens, firsts):
+        segs.append((pos, n, f))
+        pos += n
+    enc = b.Encoder(p, max_pcm_frames_per_batch=pos, n_slots=1)
+    out, fbytes, fpcm = enc.encode(pcm, pos, segments=segs)
+    want, want_sizes = b"", []
+    for t, f in zip(tracks, firsts):
+        fr, sz = helpers.oracle_encode_range(t, 44100, 2, 16, o, f)
+        want += fr
+        want_sizes += sz
+    assert fbytes.tolist() == want_sizes
+    assert out.tobytes() == want
+    assert fpcm.tolist() == [1152, 1152, 1152, 7, 1152, 1152, 5, 1152, 1152, 1152, 1152, 1151]
+    enc.close()
+
+
+def test_stream_write_chunking_and_batches(tmp_path, built):
+    """stream layer: odd write sizes, several device batches in flight (block 256 -> 2048-block batches)"""
+    b = _b200()
+    o = helpers.options(block_size=256, max_lpc_order=4, max_residual_partition_order=3, adaptive_mid_side=True)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 2, 16, **kw)
+    n = 256 * 2048 * 2 + 256 * 700 + 33
+    pcm = helpers.synth_pcm(77, 2, 16, n)
+    path = os.path.join(str(tmp_path), "s.flac")
+    s = b.Stream(path, p)
+    pos, k = 0, 0
+    sizes = [1, 4099, 100000, 17, 256 * 2048 * 4]
+    while pos < len(pcm):
+        take = min(sizes[k % len(sizes)] * 4, len(pcm) - pos)
+        s.write(pcm[pos:pos + take])
+        pos += take
+        k += 1
+    offs = s.close()
+    want, want_offs = helpers.oracle_encode(pcm, 44100, 2, 16, o, want_offsets=True)
+    got = open(path, "rb").read()
+    assert got == want
+    assert offs == want_offs
+
+
+def test_stream_end_block_short_reads(tmp_path, built):
+    """a reader that returns short blocks mid-stream: the reference encodes each read as its own frame
+    (flac.c:247,525)"""
+    b = _b200()
+    o = helpers.options(block_size=512, max_lpc_order=6, max_residual_partition_order=3)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(48000, 1, 16, **kw)
+    reads = [512, 512, 100, 512, 7, 512, 512, 300]
+    pcm = helpers.synth_pcm(5, 1, 16, sum(reads))
+    path = os.path.join(str(tmp_path), "e.flac")
+    s = b.Stream(path, p)
+    pos = 0
+    for r in reads:
+        s.write(pcm[pos * 2:(pos + r) * 2])
+        if r < 512:
+            s.end_block()
+        pos += r
+    offs = s.close()
+    assert [n for _, n in offs] == reads
+    # frames must equal the oracle's, read by read, with consecutive frame numbers
+    want, pos = b"", 0
+    for i, r in enumerate(reads):
+        fr, _ = helpers.oracle_encode_range(pcm[pos * 2:(pos + r) * 2], 48000, 1, 16, o, i)
+        want += fr
+        pos += r
+    got = open(path, "rb").read()
+    assert got[helpers.first_frame_offset(got):] == want
+    if helpers.have_ref():
+        assert helpers.ref_decode(got) == pcm
+
+
+def test_error_paths(tmp_path, built):
+    b = _b200()
+    p = b.make_params()
+    with pytest.raises(b.B200FlacError):
+        b.encode_file(os.path.join(str(tmp_path), "no", "such", "dir", "x.flac"), p, b"\0" * 16, 4)
+    bad = b.make_params(bits_per_sample=12)
+    with pytest.raises(b.B200FlacError):
+        b.Encoder(bad)
+    with pytest.raises(b.B200FlacError):
+        b.Encoder(b.make_params(channels=9))
+    # empty stream: head only, like the reference
+    path = os.path.join(str(tmp_path), "empty.flac")
+    b.encode_file(path, p, b"", 0)
+    assert open(path, "rb").read() == helpers.oracle_encode(b"", 44100, 2, 16, helpers.options(
+        block_size=4096, max_lpc_order=8, max_residual_partition_order=5))
+
+
+def test_full_size_properties(tmp_path, built):
+    """size-independent properties at a realistic size (10 min of stereo): the reference's own
+    decoder accepts the stream (CRC-16 of every frame, STREAMINFO MD5) and returns the input;
+    frame sizes sum to the file; where the compiled reference is present the bytes are equal too"""
+    b = _b200()
+    n = 44100 * 600
+    o = helpers.options(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, adaptive_mid_side=True)
+    pcm = helpers.synth_pcm(1235, 2, 16, n)
+    got = _encode_b200(tmp_path, pcm, 44100, 2, 16, o)
+    si = helpers.streaminfo(got)
+    assert si["total_samples"] == n and si["md5"] == hashlib.md5(pcm).digest()
+    if helpers.have_ref():
+        assert helpers.ref_decode(got) == pcm
+        assert got == helpers.ref_encode(pcm, 44100, 2, 16, o)
