@@ -1,0 +1,231 @@
+/* audiotools.encoders -- CPython 3 module exposing encode_flac() with the reference's
+ * exact signature, keyword names and return value, backed by the B200 engine.
+ *
+ * Reference being replaced:
+ *   encoders_encode_flac()           src/encoders/flac.c:43-307 (Python entry)
+ *   kwlist / format "sO&IIII|iiiiiiiI"   flac.c:52-67, 90-109
+ *   pcmreader_converter / pcmreader_read  src/pcmconv.c:127-297
+ *   method table row                 src/encoders.h:65-67
+ *
+ * Host code stays in C here; the per-frame work happens behind the C ABI of
+ * libb200flac.so (include/b200flac.h, stream layer).  There is no CPU fallback.
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <errno.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pcm.h"
+#include "../../include/b200flac.h"
+
+struct py_pcmreader {
+    PyObject *obj;            /* the Python PCMReader */
+    PyObject *framelist_type; /* audiotools.pcm.FrameList */
+    unsigned sample_rate, channels, channel_mask, bits_per_sample;
+};
+
+static int get_uint_attr(PyObject *obj, const char *name, unsigned *out)
+{
+    PyObject *a = PyObject_GetAttrString(obj, name);
+    if (!a) return 0;
+    long v = PyLong_AsLong(a);
+    Py_DECREF(a);
+    if (v == -1 && PyErr_Occurred()) return 0;
+    *out = (unsigned)v;
+    return 1;
+}
+
+/* "O&" converter: src/pcmconv.c:127-217 */
+static int pcmreader_converter(PyObject *obj, void **out)
+{
+    struct py_pcmreader *r = (struct py_pcmreader *)calloc(1, sizeof(*r));
+    if (!r) { PyErr_NoMemory(); return 0; }
+    if (!get_uint_attr(obj, "sample_rate", &r->sample_rate) || !get_uint_attr(obj, "bits_per_sample", &r->bits_per_sample) ||
+        !get_uint_attr(obj, "channels", &r->channels) || !get_uint_attr(obj, "channel_mask", &r->channel_mask)) {
+        free(r);
+        return 0;
+    }
+    if (!PyObject_HasAttrString(obj, "read")) { free(r); PyErr_SetString(PyExc_AttributeError, "pcmreader has no read() method"); return 0; }
+    if (!PyObject_HasAttrString(obj, "close")) { free(r); PyErr_SetString(PyExc_AttributeError, "pcmreader has no close() method"); return 0; }
+    PyObject *pcm = PyImport_ImportModule("audiotools.pcm");
+    if (!pcm) { free(r); return 0; }
+    r->framelist_type = PyObject_GetAttrString(pcm, "FrameList");
+    Py_DECREF(pcm);
+    if (!r->framelist_type) { free(r); return 0; }
+    Py_INCREF(obj);
+    r->obj = obj;
+    *out = r;
+    return 1;
+}
+
+static void pcmreader_del(struct py_pcmreader *r)
+{
+    if (!r) return;
+    Py_XDECREF(r->obj);
+    Py_XDECREF(r->framelist_type);
+    free(r);
+}
+
+/* signed little-endian packing: what the reference's MD5 callback is fed (flac.c:188) */
+static void pack_le_signed(const pcm_FrameList *f, uint8_t *out)
+{
+    const unsigned bytes = f->bits_per_sample / 8;
+    const int *s = f->samples;
+    const unsigned n = f->samples_length;
+    if (bytes == 2) {
+        int16_t *o = (int16_t *)out;
+        for (unsigned i = 0; i < n; i++) o[i] = (int16_t)s[i];
+    } else if (bytes == 3) {
+        for (unsigned i = 0; i < n; i++, out += 3) {
+            const uint32_t v = (uint32_t)s[i];
+            out[0] = (uint8_t)v; out[1] = (uint8_t)(v >> 8); out[2] = (uint8_t)(v >> 16);
+        }
+    } else {
+        for (unsigned i = 0; i < n; i++) out[i] = (uint8_t)s[i];
+    }
+}
+
+static PyObject *encoders_encode_flac(PyObject *dummy, PyObject *args, PyObject *keywds)
+{
+    static char *kwlist[] = {"filename", "pcmreader", "block_size", "max_lpc_order",
+                             "min_residual_partition_order", "max_residual_partition_order",
+                             "mid_side", "adaptive_mid_side", "exhaustive_model_search",
+                             "disable_verbatim_subframes", "disable_constant_subframes",
+                             "disable_fixed_subframes", "disable_lpc_subframes", "padding_size", NULL};
+    char *filename;
+    struct py_pcmreader *reader = NULL;
+    b200flac_params p;
+    unsigned padding_size = 4096; /* DEFAULT_PADDING_SIZE, flac.c:33 */
+    b200flac_stream *stream = NULL;
+    PyObject *offsets = NULL;
+    uint8_t *packed = NULL;
+    size_t packed_cap = 0;
+
+    memset(&p, 0, sizeof(p));
+    if (!PyArg_ParseTupleAndKeywords(args, keywds, "sO&IIII|iiiiiiiI", kwlist, &filename, pcmreader_converter, &reader,
+                                     &p.block_size, &p.max_lpc_order, &p.min_residual_partition_order,
+                                     &p.max_residual_partition_order, &p.mid_side, &p.adaptive_mid_side,
+                                     &p.exhaustive_model_search, &p.no_verbatim_subframes, &p.no_constant_subframes,
+                                     &p.no_fixed_subframes, &p.no_lpc_subframes, &padding_size))
+        return NULL;
+    p.sample_rate = reader->sample_rate;
+    p.channels = reader->channels;
+    p.bits_per_sample = reader->bits_per_sample;
+
+    /* flac.c:114-117: a file that cannot be opened is an IOError carrying errno and the name */
+    {
+        FILE *probe = fopen(filename, "wb");
+        if (!probe) { PyErr_SetFromErrnoWithFilename(PyExc_IOError, filename); pcmreader_del(reader); return NULL; }
+        fclose(probe);
+    }
+    Py_BEGIN_ALLOW_THREADS
+    stream = b200flac_stream_open(filename, &p, padding_size, NULL, NULL, 0);
+    Py_END_ALLOW_THREADS
+    if (!stream) {
+        PyErr_SetString(PyExc_RuntimeError, b200flac_last_error());
+        pcmreader_del(reader);
+        return NULL;
+    }
+
+    const unsigned bytes_ps = p.bits_per_sample / 8;
+    for (;;) {
+        /* pcmreader->read(block_size): src/pcmconv.c:236, with the exact-type check of :244 */
+        PyObject *fl_obj = PyObject_CallMethod(reader->obj, "read", "i", (int)p.block_size);
+        if (!fl_obj) goto error;
+        if ((PyObject *)Py_TYPE(fl_obj) != reader->framelist_type) {
+            Py_DECREF(fl_obj);
+            PyErr_SetString(PyExc_TypeError, "results from pcmreader.read() must be FrameLists");
+            goto error;
+        }
+        pcm_FrameList *fl = (pcm_FrameList *)fl_obj;
+        const unsigned frames = fl->frames;
+        if (frames == 0) { Py_DECREF(fl_obj); break; } /* flac.c:247 */
+        if (fl->channels != p.channels || fl->bits_per_sample != p.bits_per_sample) {
+            Py_DECREF(fl_obj);
+            PyErr_SetString(PyExc_ValueError, "FrameList does not match the pcmreader's channels / bits_per_sample");
+            goto error;
+        }
+        const size_t need = (size_t)fl->samples_length * bytes_ps;
+        if (need > packed_cap) {
+            uint8_t *np_ = (uint8_t *)realloc(packed, need);
+            if (!np_) { Py_DECREF(fl_obj); PyErr_NoMemory(); goto error; }
+            packed = np_; packed_cap = need;
+        }
+        int rc;
+        Py_BEGIN_ALLOW_THREADS /* flac.c:255-269 drops the GIL around the encode as well */
+        pack_le_signed(fl, packed);
+        rc = b200flac_stream_write(stream, packed, frames);
+        /* the reference makes one frame of whatever read() returned (H12): a short read mid-stream
+           becomes a short frame, so close the block here */
+        if (!rc && frames != p.block_size) rc = b200flac_stream_end_block(stream);
+        Py_END_ALLOW_THREADS
+        Py_DECREF(fl_obj);
+        if (rc) { PyErr_SetString(PyExc_IOError, b200flac_last_error()); goto error; }
+    }
+
+    {
+        uint64_t *offs = NULL, n = 0;
+        uint32_t *lens = NULL;
+        int rc;
+        Py_BEGIN_ALLOW_THREADS
+        rc = b200flac_stream_close(stream, 0, &offs, &lens, &n);
+        Py_END_ALLOW_THREADS
+        stream = NULL;
+        if (rc) { PyErr_SetString(PyExc_IOError, b200flac_last_error()); goto error; }
+        /* flac.c:249-253: list of (byte offset from the first frame, PCM frames) */
+        offsets = PyList_New((Py_ssize_t)n);
+        for (uint64_t i = 0; offsets && i < n; i++) {
+            PyObject *t = Py_BuildValue("(K, I)", (unsigned long long)offs[i], (unsigned)lens[i]);
+            if (!t) { Py_CLEAR(offsets); break; }
+            PyList_SET_ITEM(offsets, (Py_ssize_t)i, t);
+        }
+        b200flac_free(offs);
+        b200flac_free(lens);
+        if (!offsets) goto error;
+    }
+    free(packed);
+    /* success: close() then del, flac.c:282-283 */
+    {
+        PyObject *r = PyObject_CallMethod(reader->obj, "close", NULL);
+        if (!r) { Py_DECREF(offsets); pcmreader_del(reader); return NULL; }
+        Py_DECREF(r);
+    }
+    pcmreader_del(reader);
+    return offsets;
+
+error:
+    /* flac.c:288-296: no close() on the reader, the partial file is left for from_pcm to unlink */
+    if (stream) {
+        PyObject *et, *ev, *tb;
+        PyErr_Fetch(&et, &ev, &tb);
+        Py_BEGIN_ALLOW_THREADS
+        b200flac_stream_close(stream, 1, NULL, NULL, NULL);
+        Py_END_ALLOW_THREADS
+        PyErr_Restore(et, ev, tb);
+    }
+    free(packed);
+    pcmreader_del(reader);
+    return NULL;
+}
+
+static PyObject *encoders_device_count(PyObject *dummy, PyObject *args)
+{
+    return PyLong_FromLong(b200flac_device_count());
+}
+
+static PyMethodDef module_methods[] = {
+    {"encode_flac", (PyCFunction)encoders_encode_flac, METH_VARARGS | METH_KEYWORDS,
+     "encode_flac(filename, pcmreader, block_size, max_lpc_order, min_residual_partition_order, "
+     "max_residual_partition_order, mid_side=0, adaptive_mid_side=0, exhaustive_model_search=0, "
+     "disable_verbatim_subframes=0, disable_constant_subframes=0, disable_fixed_subframes=0, "
+     "disable_lpc_subframes=0, padding_size=4096) -> [(byte_offset, pcm_frames), ...]"},
+    {"b200_device_count", (PyCFunction)encoders_device_count, METH_NOARGS, "usable CUDA devices"},
+    {NULL}};
+
+static struct PyModuleDef encoders_module = {PyModuleDef_HEAD_INIT, "audiotools.encoders",
+                                             "Low-level audio format encoders (B200 FLAC engine)", -1, module_methods};
+
+PyMODINIT_FUNC PyInit_encoders(void) { return PyModule_Create(&encoders_module); }
