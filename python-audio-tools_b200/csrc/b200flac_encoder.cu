@@ -18,6 +18,8 @@
 #include "k_lpc_model.cuh"
 #include "k_analyze.cuh"
 #include "k_pack.cuh"
+#include "k_analyze_fast.cuh"
+#include "k_pack_fast.cuh"
 #include "k_synth.cuh"
 
 #define BF_MAX_SEGMENTS 65536
@@ -84,6 +86,8 @@ struct b200flac_encoder {
     int S;                // samples per thread (template selector)
     int NT;               // threads per CTA for analyze/pack
     size_t smem_analyze, smem_pack;
+    bool fast;            // register-resident kernels (k_analyze_fast / k_pack_fast) apply
+    u32 stage_words;      // shared-memory image of one subframe, in words (fast pack)
     std::map<u32, std::vector<double>>* windows;
     u64 launches;
 };
@@ -258,6 +262,14 @@ static cudaError_t set_smem_attrs(size_t smem_a, size_t smem_p)
     return cudaFuncSetAttribute(k_pack_subframes<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
 }
 
+template <int S>
+static cudaError_t set_smem_attrs_fast(size_t smem_a, size_t smem_p)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_analyze_fast<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_pack_fast<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+}
+
 extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* params, int device,
                                                      uint64_t max_pcm_frames_per_batch, int n_slots)
 {
@@ -287,21 +299,64 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     const bf_dev_params& P = enc->P;
 
     const u32 bs = params->block_size;
-    enc->S = bs >= 2048 ? 32 : (bs >= 512 ? 16 : 8);
-    int nt = (int)((bs + enc->S - 1) / enc->S);
-    nt = (nt + 31) & ~31;
-    if (nt < 32) nt = 32;
-    if (nt > 512) nt = 512; // register budget: 512 threads x <=128 regs; longer blocks take several passes
-    enc->NT = nt;
     const size_t padn = (size_t)PADI(bs) + 1;
+    // fast path: whole block in one pass of <= 512 threads x S samples, everything in shared memory,
+    // VERBATIM a candidate (bounds the subframe image).  Pick S with the least idle lanes.
+    enc->fast = false;
+    enc->stage_words = 0;
+    {
+        const int cand[5] = {32, 36, 16, 18, 8};
+        int bestS = 0, bestNT = 0;
+        long bestWaste = -1;
+        for (int i = 0; i < 5; i++) {
+            int nt = (int)((bs + cand[i] - 1) / cand[i]);
+            nt = (nt + 31) & ~31;
+            if (nt > 512) continue;
+            const long waste = (long)nt * cand[i] - (long)bs;
+            if (bestWaste < 0 || waste < bestWaste) { bestWaste = waste; bestS = cand[i]; bestNT = nt; }
+        }
+        const char* force = getenv("B200FLAC_FORCE_GENERIC");
+        if (bestS && P.samples_in_smem && P.heap_in_smem && P.try_verbatim && !(force && force[0] == '1')) {
+            enc->fast = true;
+            enc->S = bestS;
+            enc->NT = bestNT;
+            const u64 sub_bits = 8 + 32 + (u64)(params->bits_per_sample + 1) * bs;
+            enc->stage_words = (u32)((sub_bits + 31 + 31) / 32 + 2);
+        }
+    }
     size_t sa = 0, sp = 0;
-    if (P.samples_in_smem) { sa += 2 * padn * 4; sp += padn * 4; }
-    if (P.heap_in_smem) sa += 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride;
-    enc->smem_analyze = sa + 16;
-    enc->smem_pack = sp + 16;
-    cudaError_t e = enc->S == 32 ? set_smem_attrs<32>(enc->smem_analyze, enc->smem_pack)
-                  : enc->S == 16 ? set_smem_attrs<16>(enc->smem_analyze, enc->smem_pack)
-                                 : set_smem_attrs<8>(enc->smem_analyze, enc->smem_pack);
+    cudaError_t e = cudaSuccess;
+    if (enc->fast) {
+        sa = padn * 4 + 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride + 16;
+        sp = padn * 4 + (size_t)enc->stage_words * 4 + 16;
+        if (sa > 200 * 1024 || sp > 200 * 1024) enc->fast = false;
+    }
+    if (enc->fast) {
+        enc->smem_analyze = sa;
+        enc->smem_pack = sp;
+        switch (enc->S) {
+        case 8: e = set_smem_attrs_fast<8>(sa, sp); break;
+        case 16: e = set_smem_attrs_fast<16>(sa, sp); break;
+        case 18: e = set_smem_attrs_fast<18>(sa, sp); break;
+        case 32: e = set_smem_attrs_fast<32>(sa, sp); break;
+        default: e = set_smem_attrs_fast<36>(sa, sp); break;
+        }
+    } else {
+        enc->S = bs >= 2048 ? 32 : (bs >= 512 ? 16 : 8);
+        int nt = (int)((bs + enc->S - 1) / enc->S);
+        nt = (nt + 31) & ~31;
+        if (nt < 32) nt = 32;
+        if (nt > 512) nt = 512; // register budget: 512 threads x <=128 regs; longer blocks take several passes
+        enc->NT = nt;
+        sa = sp = 0;
+        if (P.samples_in_smem) { sa += 2 * padn * 4; sp += padn * 4; }
+        if (P.heap_in_smem) sa += 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride;
+        enc->smem_analyze = sa + 16;
+        enc->smem_pack = sp + 16;
+        e = enc->S == 32 ? set_smem_attrs<32>(enc->smem_analyze, enc->smem_pack)
+          : enc->S == 16 ? set_smem_attrs<16>(enc->smem_analyze, enc->smem_pack)
+                         : set_smem_attrs<8>(enc->smem_analyze, enc->smem_pack);
+    }
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         b200flac_encoder_destroy(enc);
@@ -480,6 +535,27 @@ static void launch_analyze_pack(b200flac_encoder* enc, Slot& s, const uint8_t* d
     enc->launches += 6;
 }
 
+template <int S>
+static void launch_analyze_pack_fast(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
+{
+    const bf_dev_params& P = enc->P;
+    const u32 nf = s.n_frames, U = nf * P.K;
+    cudaStream_t st = s.stream;
+    k_analyze_fast<S><<<U, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+    cudaEventRecord(s.ev[2], st);
+    k_frame_select<<<(nf + 127) / 128, 128, 0, st>>>(s.d_fd, nf, P, s.d_plans, s.d_choice, s.d_frame_bytes);
+    k_scan_offsets<<<1, 1024, 0, st>>>(s.d_frame_bytes, nf, s.d_frame_off, s.d_total);
+    k_zero_output<<<148 * 4, 256, 0, st>>>((uint4*)d_out, s.d_total, out_cap);
+    cudaEventRecord(s.ev[3], st);
+    k_pack_fast<S><<<nf * P.channels, enc->NT, enc->smem_pack, st>>>(d_pcm, s.d_fd, P, s.d_plans, s.d_rice, s.d_choice,
+                                                                    s.d_frame_off, (u32*)d_out, s.d_total, out_cap,
+                                                                    enc->stage_words);
+    cudaEventRecord(s.ev[4], st);
+    k_frame_crc16<<<(nf * 32 + 127) / 128, 128, 0, st>>>(s.d_frame_off, s.d_frame_bytes, nf, d_out, s.d_total, out_cap);
+    cudaEventRecord(s.ev[5], st);
+    enc->launches += 6;
+}
+
 // enqueue the kernels of one batch on the slot's stream
 static int launch_batch(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
 {
@@ -497,7 +573,15 @@ static int launch_batch(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, ui
         enc->launches += 1;
     }
     cudaEventRecord(s.ev[1], st);
-    if (enc->S == 32) launch_analyze_pack<32>(enc, s, d_pcm, d_out, out_cap);
+    if (enc->fast) {
+        switch (enc->S) {
+        case 8: launch_analyze_pack_fast<8>(enc, s, d_pcm, d_out, out_cap); break;
+        case 16: launch_analyze_pack_fast<16>(enc, s, d_pcm, d_out, out_cap); break;
+        case 18: launch_analyze_pack_fast<18>(enc, s, d_pcm, d_out, out_cap); break;
+        case 32: launch_analyze_pack_fast<32>(enc, s, d_pcm, d_out, out_cap); break;
+        default: launch_analyze_pack_fast<36>(enc, s, d_pcm, d_out, out_cap); break;
+        }
+    } else if (enc->S == 32) launch_analyze_pack<32>(enc, s, d_pcm, d_out, out_cap);
     else if (enc->S == 16) launch_analyze_pack<16>(enc, s, d_pcm, d_out, out_cap);
     else launch_analyze_pack<8>(enc, s, d_pcm, d_out, out_cap);
     CU_CHECK(cudaGetLastError(), 1);
