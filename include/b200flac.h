@@ -164,7 +164,8 @@ typedef struct b200flac_plan {
     int8_t   shift;
     uint8_t  coding_method;
     uint8_t  partition_order;
-    uint8_t  flags;           /* bit0: partition-length underflow level (flac.c:1462) */
+    uint8_t  flags;           /* bit0: partition-length underflow level (flac.c:1462);
+                                 bit1: hint, LPC sum provably fits 32 bits (packer may use int32) */
     uint32_t bits;            /* exact subframe size in bits */
     int16_t  coeffs[B200FLAC_MAX_LPC_ORDER];
 } b200flac_plan;

@@ -327,8 +327,9 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     size_t sa = 0, sp = 0;
     cudaError_t e = cudaSuccess;
     if (enc->fast) {
-        sa = padn * 4 + 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride + 16;
-        sp = padn * 4 + (size_t)enc->stage_words * 4 + 16;
+        const size_t fs = fast_samp_ints(bs, enc->S) * 4;
+        sa = fs + 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride + 16;
+        sp = fs + (size_t)enc->stage_words * 4 + 16;
         if (sa > 200 * 1024 || sp > 200 * 1024) enc->fast = false;
     }
     if (enc->fast) {

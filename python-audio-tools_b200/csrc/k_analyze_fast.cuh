@@ -4,19 +4,27 @@
 // Same decisions, bit for bit, as k_analyze (k_analyze.cuh) and therefore as the
 // reference (flac.c:673-1505); only the data movement differs:
 //   * every thread keeps its S contiguous samples (after the wasted-bits shift)
-//     in registers for the whole kernel; shared memory holds a copy only so that
-//     neighbours can fetch their predictor history;
+//     in registers for the whole kernel; shared memory holds a copy (one pad word
+//     per thread, so runs are bank-conflict free) only for the predictor history;
 //   * FIXED differences, the LPC multiply-accumulate and both residual passes of
-//     the Rice search are fully unrolled over those registers: no index math,
-//     no shared-memory traffic in the inner loops;
+//     the Rice search are fully unrolled over those registers;
 //   * the LPC accumulate runs in 32 bits whenever sum|q| * 2^(bps-1) < 2^31
 //     proves the 64-bit sum of flac.c:1000-1005 cannot leave int32 (always true
 //     for 16-bit input at order <= 15), in 64 bits otherwise;
-//   * the partition-order decision (merge, Rice parameters, estimates, argmin)
-//     is done by warp 0 alone between two block barriers.
+//   * the partition-order decision is data-parallel: a prefix sum over the finest
+//     partition sums gives every (level, partition) sum as a difference, one thread
+//     per partition computes the Rice parameter in closed form (falling back to the
+//     reference's loop where its 32-bit wrap could matter) and its size estimate.
 #pragma once
 #include "flac_common.cuh"
 #include "k_analyze.cuh"
+
+// shared-memory index of sample i when every thread owns S samples: one pad word per thread
+template <int S>
+__device__ __forceinline__ u32 pad_idx(u32 i) { return i + i / (u32)S; }
+
+// ints of shared memory needed for a block of bs samples in that layout
+static inline size_t fast_samp_ints(unsigned bs, int S) { return (size_t)bs + (bs + S - 1) / S + 2; }
 
 // order groups: coefficients are zero-padded to the group size (exact: 0 * x adds nothing)
 __device__ __forceinline__ int order_group(u32 o) { return o <= 4 ? 4 : o <= 8 ? 8 : o <= 12 ? 12 : o <= 16 ? 16 : o <= 24 ? 24 : 32; }
@@ -31,7 +39,7 @@ __device__ __forceinline__ void lpc_residual_regs(const int (&s)[S], const int* 
     for (int t = 0; t < OG; t++) {
         q[t] = q_sm[t];
         const int idx = (int)base - 1 - t;
-        h[t] = (idx >= 0 && idx < (int)n) ? samp[PADI(idx)] : 0; // idle threads (base >= n) must not read past the block
+        h[t] = (idx >= 0 && idx < (int)n) ? samp[pad_idx<S>((u32)idx)] : 0; // idle threads must not read past the block
     }
 #pragma unroll
     for (int j = 0; j < S; j++) {
@@ -71,15 +79,10 @@ __device__ __forceinline__ void lpc_residual_dispatch(const int (&s)[S], const i
     }
 }
 
-// FIXED residual of `order` for the thread's run (closed forms of the iterated differences)
-template <int S>
-__device__ __forceinline__ void fixed_residual_regs(const int (&s)[S], const int* samp, u32 base, u32 n, u32 order, int (&r)[S])
+// FIXED residual of ORDER for the thread's run (closed forms of the iterated differences)
+template <int S, int ORDER>
+__device__ __forceinline__ void fixed_residual_order(const int (&s)[S], u32 h1, u32 h2, u32 h3, u32 h4, int (&r)[S])
 {
-    u32 h1 = 0, h2 = 0, h3 = 0, h4 = 0;
-    if (base >= 1 && base - 1 < n) h1 = (u32)samp[PADI(base - 1)];
-    if (base >= 2 && base - 2 < n) h2 = (u32)samp[PADI(base - 2)];
-    if (base >= 3 && base - 3 < n) h3 = (u32)samp[PADI(base - 3)];
-    if (base >= 4 && base - 4 < n) h4 = (u32)samp[PADI(base - 4)];
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const u32 s0 = (u32)s[j];
@@ -88,14 +91,29 @@ __device__ __forceinline__ void fixed_residual_regs(const int (&s)[S], const int
         const u32 s3 = j >= 3 ? (u32)s[j >= 3 ? j - 3 : 0] : (j == 2 ? h1 : j == 1 ? h2 : h3);
         const u32 s4 = j >= 4 ? (u32)s[j >= 4 ? j - 4 : 0] : (j == 3 ? h1 : j == 2 ? h2 : j == 1 ? h3 : h4);
         u32 v;
-        switch (order) {
-        case 0: v = s0; break;
-        case 1: v = s0 - s1; break;
-        case 2: v = s0 - 2u * s1 + s2; break;
-        case 3: v = s0 - 3u * s1 + 3u * s2 - s3; break;
-        default: v = s0 - 4u * s1 + 6u * s2 - 4u * s3 + s4; break;
-        }
+        if (ORDER == 0) v = s0;
+        else if (ORDER == 1) v = s0 - s1;
+        else if (ORDER == 2) v = s0 - 2u * s1 + s2;
+        else if (ORDER == 3) v = s0 - 3u * s1 + 3u * s2 - s3;
+        else v = s0 - 4u * s1 + 6u * s2 - 4u * s3 + s4;
         r[j] = (int)v;
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void fixed_residual_regs(const int (&s)[S], const int* samp, u32 base, u32 n, u32 order, int (&r)[S])
+{
+    u32 h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+    if (base >= 1 && base - 1 < n) h1 = (u32)samp[pad_idx<S>(base - 1)];
+    if (base >= 2 && base - 2 < n) h2 = (u32)samp[pad_idx<S>(base - 2)];
+    if (base >= 3 && base - 3 < n) h3 = (u32)samp[pad_idx<S>(base - 3)];
+    if (base >= 4 && base - 4 < n) h4 = (u32)samp[pad_idx<S>(base - 4)];
+    switch (order) {
+    case 0: fixed_residual_order<S, 0>(s, h1, h2, h3, h4, r); break;
+    case 1: fixed_residual_order<S, 1>(s, h1, h2, h3, h4, r); break;
+    case 2: fixed_residual_order<S, 2>(s, h1, h2, h3, h4, r); break;
+    case 3: fixed_residual_order<S, 3>(s, h1, h2, h3, h4, r); break;
+    default: fixed_residual_order<S, 4>(s, h1, h2, h3, h4, r); break;
     }
 }
 
@@ -112,104 +130,156 @@ __device__ __forceinline__ void mask_residuals(int (&r)[S], u32 base, u32 order,
     }
 }
 
+// Rice parameter + estimate of one partition, same results as partition_estimate():
+// closed form when no shift of the reference's loop can wrap 32 bits, the loop itself otherwise.
+__device__ __forceinline__ u64 partition_estimate_fast(u32 plength, u64 S_, u32 max_rice, u32* k_out)
+{
+    u32 k;
+    if (S_ <= (u64)plength) {
+        k = 0;
+    } else if (plength == 0 || ((u64)plength << max_rice) >= (1ull << 32)) {
+        return partition_estimate(plength, S_, max_rice, k_out);
+    } else {
+        // smallest k with (plength << k) >= S_; none of the shifts up to max_rice wraps
+        int kc = (64 - __clzll((long long)S_)) - (32 - __clz((int)plength)) - 1;
+        if (kc < 0) kc = 0;
+        while (((u64)plength << kc) < S_) kc++;
+        k = (u32)kc < max_rice ? (u32)kc : max_rice;
+    }
+    u64 est;
+    if (k > 0) est = 4ull + (S_ >> (k - 1)) + (u64)(u32)((1u + k) * plength) - (u64)(plength / 2);
+    else       est = 4ull + (S_ << 1) + (u64)plength - (u64)(plength / 2);
+    *k_out = k;
+    return est;
+}
+
+// shared scratch of the fast Rice search (double buffered by search parity, see rice_search_regs)
+struct RiceScratch {
+    u64 lvl_total[2][16];
+    u64 bits_total[2];
+    u32 lvl_maxk[2][16];
+};
+
 // Rice search over the thread-resident residual r[] (already masked).  Same algorithm and
-// same results as rice_search() in k_analyze.cuh.
+// same results as rice_search() in k_analyze.cuh.  `parity` alternates between consecutive
+// calls so that a fast thread zeroing the next search's totals never races a slow reader.
 template <int S>
-__device__ __forceinline__ void rice_search_regs(const AnalyzeCtx& c, const int (&r)[S], u32 base, u32 order,
-                                                 const bf_dev_params& P, RiceChoice* out)
+__device__ __forceinline__ void rice_search_regs(const AnalyzeCtx& c, RiceScratch* rs, u32 parity, const int (&r)[S],
+                                                 u32 base, u32 order, const bf_dev_params& P, RiceChoice* out)
 {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const u32 n = (u32)c.n;
     const u32 po_eff = min(P.po_lim, (u32)(__ffs((int)n) - 1));
     u32 F = po_eff;
     while (F > 0 && (n >> F) < order) F--;
+    const u32 nfine = 1u << F;
     const u32 plenF = n >> F;
     const u32 lo = max(base, order), hi = min(base + (u32)S, n);
+    u64* fine = c.psum;              // [nfine] finest partition sums, then inclusive prefix sums in place
+    u64* lvl_total = rs->lvl_total[parity];
+    u32* lvl_maxk = rs->lvl_maxk[parity];
 
-    for (u32 i = tid; i < (1u << F); i += nt) c.psum[(1u << F) - 1u + i] = 0ull;
+    for (u32 i = tid; i < nfine; i += nt) fine[i] = 0ull;
+    if (tid < 16) { lvl_total[tid] = 0ull; lvl_maxk[tid] = 0u; }
+    if (tid == 0) rs->bits_total[parity] = 0ull;
     __syncthreads();
 
     // ---- pass 1: sum |r| per finest partition ----
     if (lo < hi) {
         const u32 p0 = lo / plenF;
         if ((hi - 1) / plenF == p0) {
-            // whole run inside one partition (the common case: partition length multiple of S)
             u64 run = 0;
 #pragma unroll
             for (int j = 0; j < S; j++) run += (u64)(u32)abs(r[j]);
-            atomicAdd(&c.psum[(1u << F) - 1u + p0], run);
+            atomicAdd(&fine[p0], run);
         } else {
             u32 p = p0;
-            u32 next = (p + 1) * plenF - base; // relative index of the next boundary
+            u32 next = (p + 1) * plenF - base;
             u64 run = 0;
 #pragma unroll
             for (int j = 0; j < S; j++) {
                 if ((u32)j == next) {
-                    if (p < (1u << F)) atomicAdd(&c.psum[(1u << F) - 1u + p], run);
+                    if (p < nfine) atomicAdd(&fine[p], run);
                     run = 0; p++; next += plenF;
                 }
                 run += (u64)(u32)abs(r[j]);
             }
-            if (p < (1u << F)) atomicAdd(&c.psum[(1u << F) - 1u + p], run);
+            if (p < nfine) atomicAdd(&fine[p], run);
         }
     }
     __syncthreads();
 
-    // ---- decision by warp 0: merge levels, Rice parameters, estimates, first strict minimum ----
+    // ---- inclusive prefix sum of the finest sums (warp 0) ----
     if (tid < 32) {
-        for (int l = (int)F - 1; l >= 0; l--) {
-            for (u32 p = lane; p < (1u << l); p += 32)
-                c.psum[(1u << l) - 1u + p] = c.psum[(2u << l) - 1u + 2 * p] + c.psum[(2u << l) - 1u + 2 * p + 1];
-            __syncwarp();
-        }
-        u64 best = ~0ull;
-        u32 best_l = 0, best_k0 = 0;
-        for (u32 l = 0; l <= po_eff; l++) {
-            u64 tot = 0;
-            u32 k0 = 0;
-            if (l <= F) {
-                for (u32 p = lane; p < (1u << l); p += 32) {
-                    const u32 plength = (n >> l) - (p == 0 ? order : 0u);
-                    u32 k;
-                    tot += partition_estimate(plength, c.psum[(1u << l) - 1u + p], P.max_rice, &k);
-                    c.karr[(1u << l) - 1u + p] = (uint8_t)k;
-                }
+        const u32 per = (nfine + 31) >> 5;
+        const u32 b = lane * per;
+        u64 run = 0;
+        for (u32 i = 0; i < per; i++) if (b + i < nfine) { run += fine[b + i]; fine[b + i] = run; }
+        u64 inc = run;
 #pragma unroll
-                for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
-            } else {
-                const u32 pl = n >> l;
-                tot = partition_estimate(pl - order, c.psum[0], P.max_rice, &k0);
-                tot += (u64)((1u << l) - 1u) * (4ull + (u64)pl - (u64)(pl / 2));
-            }
-            if (tot < best) { best = tot; best_l = l; best_k0 = k0; }
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += t;
         }
-        if (lane == 0) { c.sc[0] = best_l; c.sc[1] = (best_l > F) ? 1u : 0u; c.sc[2] = best_k0; }
+        const u64 excl = inc - run;
+        for (u32 i = 0; i < per; i++) if (b + i < nfine) fine[b + i] += excl;
     }
     __syncthreads();
-    const u32 po = c.sc[0], under = c.sc[1], k0 = c.sc[2];
+
+    // ---- one thread per (level, partition): Rice parameter, estimate ----
+    const u32 heapn = 2 * nfine - 1;
+    for (u32 idx = tid; idx < heapn; idx += nt) {
+        const u32 l = 31u - (u32)__clz((int)(idx + 1));
+        const u32 p = idx + 1 - (1u << l);
+        const u32 w = nfine >> l;                       // finest partitions per partition of level l
+        const u64 hi_sum = fine[(p + 1) * w - 1];
+        const u64 lo_sum = p ? fine[p * w - 1] : 0ull;
+        const u32 plength = (n >> l) - (p == 0 ? order : 0u);
+        u32 k;
+        const u64 est = partition_estimate_fast(plength, hi_sum - lo_sum, P.max_rice, &k);
+        c.karr[idx] = (uint8_t)k;
+        atomicAdd(&lvl_total[l], est);
+        atomicMax(&lvl_maxk[l], k);
+    }
+    __syncthreads();
+
+    // ---- first strict minimum over the levels (every thread, redundantly) ----
+    u64 best = lvl_total[0];
+    u32 po = 0, k0 = 0;
+    for (u32 l = 1; l <= po_eff; l++) {
+        u64 tot;
+        u32 kk = 0;
+        if (l <= F) {
+            tot = lvl_total[l];
+        } else {
+            // underflow level: partition 0 swallows every residual, the others are empty (H3)
+            const u32 pl = n >> l;
+            tot = partition_estimate(pl - order, fine[nfine - 1], P.max_rice, &kk);
+            tot += (u64)((1u << l) - 1u) * (4ull + (u64)pl - (u64)(pl / 2));
+        }
+        if (tot < best) { best = tot; po = l; k0 = kk; }
+    }
+    const u32 under = po > F ? 1u : 0u;
     const u32 koff = (1u << po) - 1u;
     const u32 plen = n >> po;
+    const u32 maxk = under ? k0 : lvl_maxk[po];
 
     // ---- pass 2: exact size ----
-    u32 maxk = 0;
-    if (under) maxk = k0;
-    else for (u32 p = tid; p < (1u << po); p += nt) maxk = max(maxk, (u32)c.karr[koff + p]);
     u64 bits = 0;
     if (lo < hi) {
         const u32 p0 = under ? 0u : lo / plen;
         if (under || (hi - 1) / plen == p0) {
             const u32 k = under ? k0 : (u32)c.karr[koff + p0];
-            u32 acc = 0; // S * (2^32 >> k) can overflow 32 bits only for k == 0 with huge residuals: use 64
-            u64 acc64 = 0;
             if (k >= 6) {
+                u32 acc = 0; // S * (2^32 >> 6) < 2^32
 #pragma unroll
                 for (int j = 0; j < S; j++) acc += zigzag(r[j]) >> k;
-                acc64 = acc;
+                bits = acc;
             } else {
 #pragma unroll
-                for (int j = 0; j < S; j++) acc64 += (u64)(zigzag(r[j]) >> k);
+                for (int j = 0; j < S; j++) bits += (u64)(zigzag(r[j]) >> k);
             }
-            bits = acc64 + (u64)(hi - lo) * (1u + k);
+            bits += (u64)(hi - lo) * (1u + k);
         } else {
             u32 p = p0;
             u32 next = (p + 1) * plen - base;
@@ -222,11 +292,19 @@ __device__ __forceinline__ void rice_search_regs(const AnalyzeCtx& c, const int 
             }
         }
     }
-    maxk = block_max_u32(maxk, c.red);
-    bits = block_sum_u64(bits, c.red);
+    // warp sum (32-bit REDUX when it cannot overflow), one shared atomic per warp
+    if (!__any_sync(0xFFFFFFFFu, (bits >> 26) != 0)) {
+        const u32 wsum = __reduce_add_sync(0xFFFFFFFFu, (u32)bits);
+        if (lane == 0) atomicAdd(&rs->bits_total[parity], (u64)wsum);
+    } else {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, o);
+        if (lane == 0) atomicAdd(&rs->bits_total[parity], bits);
+    }
+    __syncthreads();
     out->po = po; out->under = under; out->k0 = k0;
     out->method = maxk > 14 ? 1u : 0u;
-    out->bits = bits + 6ull + (u64)(1u << po) * (maxk > 14 ? 5ull : 4ull);
+    out->bits = rs->bits_total[parity] + 6ull + (u64)(1u << po) * (maxk > 14 ? 5ull : 4ull);
 }
 
 // loads the thread's run of candidate samples into registers (0 beyond n)
@@ -235,16 +313,26 @@ __device__ __forceinline__ void load_run(const uint8_t* __restrict__ pcm, u64 pc
                                          const bf_dev_params& P, int (&s)[S])
 {
     if (P.stereo && P.bytes_ps == 2 && base + S <= n && (((pcm_off + base) * 4) & 15) == 0 && (S % 4) == 0) {
+        // stereo 16-bit: 16-byte loads of left/right pairs, candidate chosen once per thread
         const uint4* src = (const uint4*)(pcm + (pcm_off + base) * 4);
+        u32 raw[S];
 #pragma unroll
         for (int v = 0; v < S / 4; v++) {
             const uint4 w = __ldg(src + v);
-            const u32 ws[4] = {w.x, w.y, w.z, w.w};
+            raw[v * 4 + 0] = w.x; raw[v * 4 + 1] = w.y; raw[v * 4 + 2] = w.z; raw[v * 4 + 3] = w.w;
+        }
+        if (cand == 0) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int L = (int)(short)(ws[e] & 0xFFFF), R = (int)(short)(ws[e] >> 16);
-                s[v * 4 + e] = cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
-            }
+            for (int j = 0; j < S; j++) s[j] = (int)(short)(raw[j] & 0xFFFF);
+        } else if (cand == 1) {
+#pragma unroll
+            for (int j = 0; j < S; j++) s[j] = (int)raw[j] >> 16;
+        } else if (cand == 2) {
+#pragma unroll
+            for (int j = 0; j < S; j++) s[j] = ((int)(short)(raw[j] & 0xFFFF) + ((int)raw[j] >> 16)) >> 1;
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; j++) s[j] = (int)(short)(raw[j] & 0xFFFF) - ((int)raw[j] >> 16);
         }
     } else {
 #pragma unroll
@@ -252,6 +340,20 @@ __device__ __forceinline__ void load_run(const uint8_t* __restrict__ pcm, u64 pc
             const u32 i = base + j;
             s[j] = i < n ? ld_candidate(pcm, pcm_off + i, cand, P) : 0;
         }
+    }
+}
+
+// copies the thread's run to shared memory (one pad word per thread)
+template <int S>
+__device__ __forceinline__ void store_run(int* samp, const int (&s)[S], u32 tid, u32 base, u32 n)
+{
+    int* dst = samp + (size_t)tid * (S + 1);
+    if (base + S <= n) {
+#pragma unroll
+        for (int j = 0; j < S; j++) dst[j] = s[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < S; j++) if (base + j < n) dst[j] = s[j];
     }
 }
 
@@ -263,11 +365,13 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ u64 red[40];
-    __shared__ u64 lvl_total[16];
+    __shared__ RiceScratch rs;
+    __shared__ u64 fsum[5];
     __shared__ u32 sc[8];
     __shared__ short s_q[BF_MAX_ORDER];
+    __shared__ bf_lpc_head s_head;
 
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const u32 unit = blockIdx.x;
     const u32 frame = unit / P.K, cand = unit % P.K;
     const bf_frame_desc d = fd[frame];
@@ -276,9 +380,9 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
     const u32 base = (u32)tid * S;
 
     AnalyzeCtx c;
-    c.n = (int)n; c.red = red; c.lvl_total = lvl_total; c.sc = sc; c.resid = nullptr;
+    c.n = (int)n; c.red = red; c.lvl_total = nullptr; c.sc = sc; c.resid = nullptr;
     unsigned char* sp = dyn_smem;
-    c.samp = (int*)sp; sp += ((size_t)PADI(P.block_size) + 1) * 4;
+    c.samp = (int*)sp; sp += ((size_t)P.block_size + (P.block_size + S - 1) / S + 2) * 4;
     sp = (unsigned char*)(((uintptr_t)sp + 7) & ~(uintptr_t)7);
     c.psum = (u64*)sp; sp += (size_t)P.heap_entries * 8;
     c.karr = sp; sp += P.heap_entries;
@@ -292,32 +396,40 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
     for (int i = 0; i < BF_MAX_ORDER; i++) plan.coeffs[i] = 0;
     uint8_t* my_rice = rice_out + (size_t)unit * P.rice_stride;
 
+    if (tid == 0 && P.try_lpc) s_head = heads[unit];
+    if (tid < 5) fsum[tid] = 0ull;
+
     // ---- load, constant check, wasted bits ----
     int s[S];
     load_run<S>(pcm, d.pcm_off, base, n, cand, P, s);
     const int first = ld_candidate(pcm, d.pcm_off, cand, P);
     u32 orv = 0, diff = 0;
+    if (base + S <= n) {
 #pragma unroll
-    for (int j = 0; j < S; j++) {
-        orv |= (u32)s[j];
-        diff |= (base + j < n) ? (u32)(s[j] ^ first) : 0u;
+        for (int j = 0; j < S; j++) { orv |= (u32)s[j]; diff |= (u32)(s[j] ^ first); }
+    } else {
+#pragma unroll
+        for (int j = 0; j < S; j++) { orv |= (u32)s[j]; if (base + j < n) diff |= (u32)(s[j] ^ first); }
     }
-    orv = block_or_u32(orv, red);
-    diff = block_or_u32(diff, red);
+    orv = __reduce_or_sync(0xFFFFFFFFu, orv);
+    diff = __reduce_or_sync(0xFFFFFFFFu, diff);
+    if (lane == 0) { red[tid >> 5] = orv; red[16 + (tid >> 5)] = diff; }
+    __syncthreads();
+    orv = 0; diff = 0;
+    for (int w = 0; w < (nt >> 5); w++) { orv |= (u32)red[w]; diff |= (u32)red[16 + w]; }
     if (P.try_constant && diff == 0) {
         if (tid == 0) { plan.type = BF_CONSTANT; plan.bits = 8 + bps; plans[unit] = plan; }
         return;
     }
     const u32 wasted = orv ? (u32)(__ffs((int)orv) - 1) : 0u;
 #pragma unroll
-    for (int j = 0; j < S; j++) {
-        s[j] >>= wasted;
-        if (base + j < n) c.samp[PADI(base + j)] = s[j];
-    }
+    for (int j = 0; j < S; j++) s[j] >>= wasted;
+    store_run<S>(c.samp, s, (u32)tid, base, n);
     __syncthreads();
     const u32 sub_bps = bps - wasted;
     const u32 hdr_bits = 8 + wasted;
     int r[S];
+    u32 search = 0;
 
     // ---- FIXED ----
     u64 fixed_bits = 0;
@@ -325,21 +437,20 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
     RiceChoice rfix; rfix.po = 0; rfix.under = 0; rfix.k0 = 0; rfix.method = 0; rfix.bits = 0;
     if (P.try_fixed) {
         if (n > 4) {
-            u64 e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
             const u32 lo = max(base, 4u), hi = min(base + (u32)S, n);
+            u32 f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;       // 32-bit partial sums (fast threads)
+            u64 e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;       // 64-bit partial sums (edge threads / wide samples)
+            bool slow = false;
             if (lo < hi) {
-                // differences of the samples before the run
                 u32 a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-                if (base >= 1) a1 = (u32)c.samp[PADI(base - 1)]; // lo < hi <= n here, so base < n
-                if (base >= 2) a2 = (u32)c.samp[PADI(base - 2)];
-                if (base >= 3) a3 = (u32)c.samp[PADI(base - 3)];
-                if (base >= 4) a4 = (u32)c.samp[PADI(base - 4)];
+                if (base >= 1) a1 = (u32)c.samp[pad_idx<S>(base - 1)]; // lo < hi <= n here, so base < n
+                if (base >= 2) a2 = (u32)c.samp[pad_idx<S>(base - 2)];
+                if (base >= 3) a3 = (u32)c.samp[pad_idx<S>(base - 3)];
+                if (base >= 4) a4 = (u32)c.samp[pad_idx<S>(base - 4)];
                 u32 p1 = a1 - a2, p2 = p1 - (a2 - a3), p3 = p2 - ((a2 - a3) - (a3 - a4));
                 u32 prev = a1;
-                const bool full = (base >= 4) && (base + S <= n);
-                if (full && sub_bps <= 18) {
-                    // |d4| < 2^(bps+4): 32 terms fit 32 bits
-                    u32 f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+                if ((base >= 4) && (base + S <= n) && sub_bps <= 18) {
+                    // |d4| < 2^(sub_bps+3) <= 2^21: S <= 36 terms and then 32 lanes still fit 32 bits
 #pragma unroll
                     for (int j = 0; j < S; j++) {
                         const u32 x = (u32)s[j];
@@ -348,8 +459,8 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
                         f3 += (u32)abs((int)d3); f4 += (u32)abs((int)d4);
                         prev = x; p1 = d1; p2 = d2; p3 = d3;
                     }
-                    e0 = f0; e1 = f1; e2 = f2; e3 = f3; e4 = f4;
                 } else {
+                    slow = true;
 #pragma unroll
                     for (int j = 0; j < S; j++) {
                         const u32 x = (u32)s[j];
@@ -364,17 +475,28 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
                     }
                 }
             }
-            e0 = block_sum_u64(e0, red); e1 = block_sum_u64(e1, red); e2 = block_sum_u64(e2, red);
-            e3 = block_sum_u64(e3, red); e4 = block_sum_u64(e4, red);
-            u64 best = e0;
-            if (e1 < best) { best = e1; fixed_order = 1; }
-            if (e2 < best) { best = e2; fixed_order = 2; }
-            if (e3 < best) { best = e3; fixed_order = 3; }
-            if (e4 < best) { best = e4; fixed_order = 4; }
+            f0 = __reduce_add_sync(0xFFFFFFFFu, f0); f1 = __reduce_add_sync(0xFFFFFFFFu, f1);
+            f2 = __reduce_add_sync(0xFFFFFFFFu, f2); f3 = __reduce_add_sync(0xFFFFFFFFu, f3);
+            f4 = __reduce_add_sync(0xFFFFFFFFu, f4);
+            if (lane == 0) {
+                atomicAdd(&fsum[0], (u64)f0); atomicAdd(&fsum[1], (u64)f1); atomicAdd(&fsum[2], (u64)f2);
+                atomicAdd(&fsum[3], (u64)f3); atomicAdd(&fsum[4], (u64)f4);
+            }
+            if (slow) {
+                atomicAdd(&fsum[0], e0); atomicAdd(&fsum[1], e1); atomicAdd(&fsum[2], e2);
+                atomicAdd(&fsum[3], e3); atomicAdd(&fsum[4], e4);
+            }
+            __syncthreads();
+            // flac.c:877-893: first strict minimum over orders 0..4
+            u64 best = fsum[0];
+            if (fsum[1] < best) { best = fsum[1]; fixed_order = 1; }
+            if (fsum[2] < best) { best = fsum[2]; fixed_order = 2; }
+            if (fsum[3] < best) { best = fsum[3]; fixed_order = 3; }
+            if (fsum[4] < best) { best = fsum[4]; fixed_order = 4; }
         }
         fixed_residual_regs<S>(s, c.samp, base, n, fixed_order, r);
         mask_residuals<S>(r, base, fixed_order, n);
-        rice_search_regs<S>(c, r, base, fixed_order, P, &rfix);
+        rice_search_regs<S>(c, &rs, (search++) & 1u, r, base, fixed_order, P, &rfix);
         save_rice(c, rfix, kfix);
         fixed_bits = hdr_bits + (u64)fixed_order * sub_bps + rfix.bits;
     }
@@ -384,32 +506,34 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
     u32 lpc_order = 0, lpc_precision = 0;
     int lpc_shift = 0;
     RiceChoice rlpc; rlpc.po = 0; rlpc.under = 0; rlpc.k0 = 0; rlpc.method = 0; rlpc.bits = 0;
+    const short* mycoef = coefs + (size_t)unit * P.model_stride;
     if (P.try_lpc) {
-        const bf_lpc_head head = heads[unit];
-        const short* mycoef = coefs + (size_t)unit * P.model_stride;
-        const u32 o_first = (P.exhaustive && !head.dummy) ? 1u : head.best_order;
-        const u32 o_last = (P.exhaustive && !head.dummy) ? P.max_lpc_order : head.best_order;
+        const u32 best_order = s_head.best_order, dummy = s_head.dummy, precision = s_head.precision;
+        const u32 o_first = (P.exhaustive && !dummy) ? 1u : best_order;
+        const u32 o_last = (P.exhaustive && !dummy) ? P.max_lpc_order : best_order;
         u64 best_bits = 0xFFFFFFFFull;
         bool have = false;
         for (u32 o = o_first; o <= o_last; o++) {
             __syncthreads();
-            if (tid < BF_MAX_ORDER) s_q[tid] = tid < (int)o ? mycoef[(o * (o - 1)) / 2 + tid] : (short)0;
+            if (tid < 32) {
+                const int q = tid < (int)o ? (int)mycoef[(o * (o - 1)) / 2 + tid] : 0;
+                s_q[tid] = (short)q;
+                // sum|q| * 2^(sub_bps-1) < 2^31  =>  the 64-bit accumulator of flac.c:1000-1005 stays inside int32
+                const u32 sumq = __reduce_add_sync(0xFFFFFFFFu, (u32)abs(q));
+                if (tid == 0) sc[4] = (((u64)sumq << (sub_bps - 1)) < (1ull << 31)) ? 1u : 0u;
+            }
             __syncthreads();
-            const int shift = head.shift[o - 1];
-            // sum|q| * 2^(sub_bps-1) < 2^31  =>  the 64-bit accumulator of flac.c:1000-1005 stays inside int32
-            u32 sumq = 0;
-            for (u32 j = 0; j < o; j++) sumq += (u32)abs((int)s_q[j]);
-            const bool narrow = ((u64)sumq << (sub_bps - 1)) < (1ull << 31);
-            if (narrow) lpc_residual_dispatch<S, false>(s, c.samp, base, n, o, s_q, shift, r);
+            const int shift = s_head.shift[o - 1];
+            if (sc[4]) lpc_residual_dispatch<S, false>(s, c.samp, base, n, o, s_q, shift, r);
             else lpc_residual_dispatch<S, true>(s, c.samp, base, n, o, s_q, shift, r);
             mask_residuals<S>(r, base, o, n);
             RiceChoice rc;
-            rice_search_regs<S>(c, r, base, o, P, &rc);
-            const u64 bits = hdr_bits + (u64)o * sub_bps + 4 + 5 + (u64)o * head.precision + rc.bits;
+            rice_search_regs<S>(c, &rs, (search++) & 1u, r, base, o, P, &rc);
+            const u64 bits = hdr_bits + (u64)o * sub_bps + 4 + 5 + (u64)o * precision + rc.bits;
             if (!have || (u32)bits < best_bits) {
                 have = true;
                 best_bits = (u32)bits;
-                lpc_bits = bits; lpc_order = o; lpc_shift = shift; lpc_precision = head.precision;
+                lpc_bits = bits; lpc_order = o; lpc_shift = shift; lpc_precision = precision;
                 rlpc = rc;
                 save_rice(c, rc, klpc);
             }
@@ -442,8 +566,11 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
         plan.coding_method = (uint8_t)rlpc.method; plan.partition_order = (uint8_t)rlpc.po;
         plan.flags = (uint8_t)rlpc.under; plan.bits = lb;
         if (tid == 0) {
-            const short* mycoef = coefs + (size_t)unit * P.model_stride + (lpc_order * (lpc_order - 1)) / 2;
-            for (u32 j = 0; j < lpc_order; j++) plan.coeffs[j] = mycoef[j];
+            const short* bc = mycoef + (lpc_order * (lpc_order - 1)) / 2;
+            u32 sumq = 0;
+            for (u32 j = 0; j < lpc_order; j++) { plan.coeffs[j] = bc[j]; sumq += (u32)abs((int)bc[j]); }
+            // bit 1: the packer may accumulate this predictor in 32 bits (same test as above)
+            if (((u64)sumq << (sub_bps - 1)) < (1ull << 31)) plan.flags |= 2;
         }
         for (u32 p = tid; p < (1u << rlpc.po); p += nt) my_rice[p] = klpc[p];
     } else {

@@ -1,21 +1,70 @@
 // k_pack_fast.cuh -- bit packing with register-resident residuals and a shared-memory
-// staging buffer, for blocks that fit one pass (n <= blockDim * S).
+// image of the subframe, for blocks that fit one pass (n <= blockDim * S).
 //
 // Same bytes as k_pack_subframes (k_pack.cuh).  Differences:
 //   * the chosen model's residual is recomputed into registers with the unrolled
-//     multiply-accumulate of k_analyze_fast.cuh;
-//   * every thread writes its run into a zeroed shared-memory image of the subframe
-//     (atomicOr on shared memory); the image is then copied to its final position with
-//     coalesced 32-bit stores -- only the first and last word, which may be shared with the
-//     neighbouring subframe, go through a global atomicOr;
-//   * a code whose unary part and binary part fit 32 bits together is emitted in one put.
+//     multiply-accumulate of k_analyze_fast.cuh and zig-zag folded once;
+//   * every thread writes its run into a zeroed shared-memory image of the subframe.
+//     Words that lie wholly inside a thread's bit range are plain stores; the thread's
+//     first and last (possibly shared) words are kept in registers and merged with one
+//     shared-memory atomicOr each at the end;
+//   * the image is copied to its final position with coalesced 32-bit stores -- only its
+//     first and last word, which may be shared with the neighbouring subframe, go through
+//     a global atomicOr;
+//   * a code whose unary and binary parts fit 32 bits together is emitted in one put.
 #pragma once
 #include "flac_common.cuh"
 #include "k_analyze_fast.cuh"
 #include "k_pack.cuh"
 
+// MSB-first writer into the shared image.  The first word the thread touches is kept in
+// `first_w` (merged later); every further completed word is exclusively the thread's.
+struct RunSink {
+    u32* words;
+    u32 widx, widx0;
+    u64 acc;
+    u32 fill;
+    u32 first_w;
+    __device__ __forceinline__ void init(u32* base, u32 bitpos)
+    {
+        words = base; widx = bitpos >> 5; widx0 = widx; fill = bitpos & 31; acc = 0; first_w = 0;
+    }
+    __device__ __forceinline__ void put(u32 v, u32 nbits) // 1 <= nbits <= 32, v < 2^nbits
+    {
+        acc |= (u64)v << (64 - fill - nbits);
+        fill += nbits;
+        if (fill >= 32) {
+            const u32 w = (u32)(acc >> 32);
+            if (widx == widx0) first_w = w; else words[widx] = w;
+            widx++; acc <<= 32; fill -= 32;
+        }
+    }
+    __device__ __forceinline__ void zeros(u32 nz)
+    {
+        const u32 tot = fill + nz;
+        if (tot >= 32) {
+            const u32 w = (u32)(acc >> 32);
+            if (widx == widx0) first_w = w; else words[widx] = w; // following all-zero words are already zero
+            widx += tot >> 5; acc = 0; fill = tot & 31;
+        } else fill = tot;
+    }
+    // merge the two boundary words
+    __device__ __forceinline__ void finish()
+    {
+        if (widx == widx0) {
+            const u32 w = (u32)(acc >> 32);
+            if (w) atomicOr(words + widx0, w);
+        } else {
+            if (first_w) atomicOr(words + widx0, first_w);
+            const u32 w = (u32)(acc >> 32);
+            if (fill && w) atomicOr(words + widx, w);
+        }
+    }
+};
+
+// generic small writer (headers): everything through shared atomics
 struct SmemSink {
-    u32* words;   // shared-memory image, big-endian value per word
+    u32* words;
     u32 widx;
     u64 acc;
     u32 fill;
@@ -62,33 +111,42 @@ k_pack_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ f
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ u64 red[40];
     __shared__ short s_q[BF_MAX_ORDER];
+    __shared__ b200flac_plan s_plan;
+    __shared__ bf_frame_choice s_choice;
 
     const int tid = threadIdx.x, nt = blockDim.x;
     const u32 frame = blockIdx.x / P.channels, slot = blockIdx.x % P.channels;
-    const bf_frame_choice ch = choice[frame];
-    if (slot >= ch.n_sub) return;
+    if (tid == 0) s_choice = choice[frame];
+    __syncthreads();
+    if (slot >= s_choice.n_sub) return;
     const bf_frame_desc d = fd[frame];
     const u32 n = d.nsamp;
-    const u32 unit = ch.unit[slot];
+    const u32 unit = s_choice.unit[slot];
     const u32 cand = unit % P.K;
-    const b200flac_plan plan = plans[unit];
+    if (tid == 0) s_plan = plans[unit];
     const uint8_t* krice = rice + (size_t)unit * P.rice_stride;
     const u32 bps = candidate_bps(cand, P);
     const u64 frame_bit0 = frame_off[frame] * 8;
-    const u64 start = frame_bit0 + ch.bitoff[slot];
+    const u64 start = frame_bit0 + s_choice.bitoff[slot];
     const u32 base = (u32)tid * S;
 
     int* samp = (int*)dyn_smem;
-    u32* stage = (u32*)(dyn_smem + ((size_t)PADI(P.block_size) + 1) * 4);
+    u32* stage = (u32*)(dyn_smem + ((size_t)P.block_size + (P.block_size + S - 1) / S + 2) * 4);
+
+    // the PCM load does not depend on the plan: issue it before waiting for the plan
+    int s[S];
+    load_run<S>(pcm, d.pcm_off, base, n, cand, P, s);
+    __syncthreads();
+    const u32 ptype = s_plan.type, wasted = s_plan.wasted, order = s_plan.order;
+    const u32 pbits = s_plan.bits;
 
     if (slot == 0 && tid == 0) {
         BitSink hs; hs.init(out_words, frame_bit0);
-        put_frame_header(hs, d, P, ch.assignment);
+        put_frame_header(hs, d, P, s_choice.assignment);
         hs.flush();
     }
-    const u32 wasted = plan.wasted;
     const u32 sub_bps = bps - wasted;
-    if (plan.type == BF_CONSTANT) {
+    if (ptype == BF_CONSTANT) {
         if (tid == 0) {
             BitSink bs; bs.init(out_words, start);
             put_subframe_header(bs, 0, 0);
@@ -98,108 +156,122 @@ k_pack_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ f
         return;
     }
 
-    const u32 bit0 = (u32)(start & 31);             // position of the subframe inside staging word 0
-    const u32 nwords = (bit0 + plan.bits + 31) >> 5; // words of the image (<= stage_words, checked by the host bound)
-    if (nwords > stage_words) __trap(); // cannot happen while VERBATIM is a candidate (host only then picks this kernel)
+    const u32 bit0 = (u32)(start & 31);          // position of the subframe inside image word 0
+    const u32 nwords = (bit0 + pbits + 31) >> 5; // words of the image
+    if (nwords > stage_words) __trap();          // cannot happen while VERBATIM is a candidate (host only then picks this kernel)
     for (u32 w = tid; w < nwords; w += nt) stage[w] = 0;
-
-    int s[S];
-    load_run<S>(pcm, d.pcm_off, base, n, cand, P, s);
 #pragma unroll
-    for (int j = 0; j < S; j++) {
-        s[j] >>= wasted;
-        if (base + j < n) samp[PADI(base + j)] = s[j];
-    }
-    if (plan.type == BF_LPC && tid < BF_MAX_ORDER) s_q[tid] = tid < (int)plan.order ? plan.coeffs[tid] : (short)0;
+    for (int j = 0; j < S; j++) s[j] >>= wasted;
+    store_run<S>(samp, s, (u32)tid, base, n);
+    if (ptype == BF_LPC && tid < BF_MAX_ORDER) s_q[tid] = tid < (int)order ? s_plan.coeffs[tid] : (short)0;
     __syncthreads();
 
-    if (plan.type == BF_VERBATIM) {
+    if (ptype == BF_VERBATIM) {
         if (tid == 0) {
             SmemSink bs; bs.init(stage, bit0);
             put_subframe_header_s(bs, 1, wasted);
             bs.flush();
         }
         if (base < n) {
-            SmemSink bs; bs.init(stage, bit0 + 8 + wasted + base * sub_bps);
+            RunSink bs; bs.init(stage, bit0 + 8 + wasted + base * sub_bps);
+            const u32 mask = sub_bps >= 32 ? 0xFFFFFFFFu : ((1u << sub_bps) - 1u);
 #pragma unroll
-            for (int j = 0; j < S; j++) if (base + j < n) bs.put_signed(s[j], sub_bps);
-            bs.flush();
+            for (int j = 0; j < S; j++) if (base + j < n) bs.put((u32)s[j] & mask, sub_bps);
+            bs.finish();
         }
     } else {
-        const u32 order = plan.order;
-        const u32 po = plan.partition_order, under = plan.flags & 1u;
+        const u32 po = s_plan.partition_order, under = s_plan.flags & 1u, narrow = s_plan.flags & 2u;
         const u32 plen = n >> po;
-        const u32 kbits = plan.coding_method ? 5u : 4u;
+        const u32 kbits = s_plan.coding_method ? 5u : 4u;
         u32 hdr_end = bit0 + 8 + wasted + order * sub_bps;
-        if (plan.type == BF_LPC) hdr_end += 4 + 5 + order * plan.precision;
+        if (ptype == BF_LPC) hdr_end += 4 + 5 + order * s_plan.precision;
         if (tid == 0) {
             SmemSink bs; bs.init(stage, bit0);
-            if (plan.type == BF_FIXED) put_subframe_header_s(bs, 0x8 | order, wasted);
+            if (ptype == BF_FIXED) put_subframe_header_s(bs, 0x8 | order, wasted);
             else put_subframe_header_s(bs, 0x20 | (order - 1), wasted);
-            for (u32 i = 0; i < order; i++) bs.put_signed(samp[PADI(i)], sub_bps);
-            if (plan.type == BF_LPC) {
-                bs.put(plan.precision - 1, 4);
-                bs.put_signed(plan.shift, 5);
-                for (u32 i = 0; i < order; i++) bs.put_signed(plan.coeffs[i], plan.precision);
+            for (u32 i = 0; i < order; i++) bs.put_signed(samp[pad_idx<S>(i)], sub_bps);
+            if (ptype == BF_LPC) {
+                bs.put(s_plan.precision - 1, 4);
+                bs.put_signed(s_plan.shift, 5);
+                for (u32 i = 0; i < order; i++) bs.put_signed(s_plan.coeffs[i], s_plan.precision);
             }
-            bs.put(plan.coding_method, 2);
+            bs.put(s_plan.coding_method, 2);
             bs.put(po, 4);
             bs.flush();
         }
         const u32 res0 = hdr_end + 6;
         int r[S];
-        if (plan.type == BF_FIXED) {
-            fixed_residual_regs<S>(s, samp, base, n, order, r);
-        } else {
-            u32 sumq = 0;
-            for (u32 j = 0; j < order; j++) sumq += (u32)abs((int)s_q[j]);
-            const bool narrow = ((u64)sumq << (sub_bps - 1)) < (1ull << 31);
-            if (narrow) lpc_residual_dispatch<S, false>(s, samp, base, n, order, s_q, plan.shift, r);
-            else lpc_residual_dispatch<S, true>(s, samp, base, n, order, s_q, plan.shift, r);
-        }
-        const u32 lo = max(base, order), hi = min(base + (u32)S, n);
-        u32 mybits = 0;
-        u32 p_first = 0;
-        if (lo < hi) {
-            u32 p = under ? 0u : lo / plen;
-            p_first = p;
-            u32 next = under ? 0xFFFFFFFFu : (p + 1) * plen - base;
-            u32 k = krice[p];
-            if (lo == order) mybits += kbits * (under ? 1u : (lo / plen + 1u));
-            else if (!under && lo == p * plen) mybits += kbits;
+        if (ptype == BF_FIXED) fixed_residual_regs<S>(s, samp, base, n, order, r);
+        else if (narrow) lpc_residual_dispatch<S, false>(s, samp, base, n, order, s_q, s_plan.shift, r);
+        else lpc_residual_dispatch<S, true>(s, samp, base, n, order, s_q, s_plan.shift, r);
+        // fold once: r[] now holds the unsigned zig-zag values
 #pragma unroll
-            for (int j = 0; j < S; j++) {
-                const u32 i = base + j;
-                if ((u32)j == next) { p++; next += plen; if (i < hi) { k = krice[p]; mybits += kbits; } }
-                if (i >= lo && i < hi) mybits += (zigzag(r[j]) >> k) + 1u + k;
+        for (int j = 0; j < S; j++) r[j] = (int)zigzag(r[j]);
+
+        const u32 lo = max(base, order), hi = min(base + (u32)S, n);
+        const bool have = lo < hi;
+        const u32 p_first = (have && !under) ? lo / plen : 0u;
+        // single: the whole run lies in one partition and needs no per-sample bounds checks
+        const bool single = have && base >= order && base + S <= n && (under || (hi - 1) / plen == p_first);
+        u32 mybits = 0;
+        u32 lead = 0; // Rice-parameter fields emitted before the run's first residual
+        if (have) {
+            if (lo == order) lead = under ? 1u : (lo / plen + 1u);      // partitions 0..p_first (an empty leading one too)
+            else if (!under && lo == p_first * plen) lead = 1;
+            mybits = lead * kbits;
+            if (single) {
+                const u32 k = krice[p_first];
+                u32 acc = 0;
+#pragma unroll
+                for (int j = 0; j < S; j++) acc += (u32)r[j] >> k;
+                mybits += acc + (u32)S * (1u + k);
+            } else {
+                u32 p = p_first;
+                u32 next = under ? 0xFFFFFFFFu : (p + 1) * plen - base;
+                u32 k = krice[p];
+#pragma unroll
+                for (int j = 0; j < S; j++) {
+                    const u32 i = base + j;
+                    if ((u32)j == next) { p++; next += plen; if (i < hi) { k = krice[p]; mybits += kbits; } }
+                    if (i >= lo && i < hi) mybits += ((u32)r[j] >> k) + 1u + k;
+                }
             }
         }
         u32 totalbits;
         const u32 off = block_exscan_u32(mybits, red, &totalbits);
-        if (lo < hi) {
-            SmemSink bs; bs.init(stage, res0 + off);
-            u32 p = p_first;
-            u32 next = under ? 0xFFFFFFFFu : (p + 1) * plen - base;
-            u32 k = krice[p];
-            if (lo == order) {
-                const u32 lead = under ? 1u : (lo / plen + 1u);
-                for (u32 q = 0; q < lead; q++) bs.put(krice[q], kbits);
-            } else if (!under && lo == p * plen) {
-                bs.put(k, kbits);
-            }
+        if (have) {
+            RunSink bs; bs.init(stage, res0 + off);
+            if (lo == order) { for (u32 q = 0; q < lead; q++) bs.put(krice[q], kbits); }
+            else if (lead) bs.put(krice[p_first], kbits);
+            if (single) {
+                const u32 k = krice[p_first];
+                const u32 kmask = (1u << k) - 1u, kone = 1u << k;
 #pragma unroll
-            for (int j = 0; j < S; j++) {
-                const u32 i = base + j;
-                if ((u32)j == next) { p++; next += plen; if (i < hi) { k = krice[p]; bs.put(k, kbits); } }
-                if (i >= lo && i < hi) {
-                    const u32 u = zigzag(r[j]);
+                for (int j = 0; j < S; j++) {
+                    const u32 u = (u32)r[j];
                     const u32 msb = u >> k;
-                    const u32 code = (1u << k) | (u & ((1u << k) - 1u));
+                    const u32 code = kone | (u & kmask);
                     if (msb + k + 1 <= 32) bs.put(code, msb + k + 1);
                     else { bs.zeros(msb); bs.put(code, k + 1); }
                 }
+            } else {
+                u32 p = p_first;
+                u32 next = under ? 0xFFFFFFFFu : (p + 1) * plen - base;
+                u32 k = krice[p];
+#pragma unroll
+                for (int j = 0; j < S; j++) {
+                    const u32 i = base + j;
+                    if ((u32)j == next) { p++; next += plen; if (i < hi) { k = krice[p]; bs.put(k, kbits); } }
+                    if (i >= lo && i < hi) {
+                        const u32 u = (u32)r[j];
+                        const u32 msb = u >> k;
+                        const u32 code = (1u << k) | (u & ((1u << k) - 1u));
+                        if (msb + k + 1 <= 32) bs.put(code, msb + k + 1);
+                        else { bs.zeros(msb); bs.put(code, k + 1); }
+                    }
+                }
             }
-            bs.flush();
+            bs.finish();
         }
         if (tid == 0) {
             u32 first_trailing;
