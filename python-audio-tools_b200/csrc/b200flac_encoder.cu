@@ -315,6 +315,15 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
             const long waste = (long)nt * cand[i] - (long)bs;
             if (bestWaste < 0 || waste < bestWaste) { bestWaste = waste; bestS = cand[i]; bestNT = nt; }
         }
+        const char* sforce = getenv("B200FLAC_S"); // tuning knob: force the samples-per-thread of the fast kernels
+        if (sforce) {
+            const int fs = atoi(sforce);
+            for (int i = 0; i < 5; i++) if (cand[i] == fs) {
+                int nt = (int)((bs + fs - 1) / fs);
+                nt = (nt + 31) & ~31;
+                if (nt <= 512) { bestS = fs; bestNT = nt; }
+            }
+        }
         const char* force = getenv("B200FLAC_FORCE_GENERIC");
         if (bestS && P.samples_in_smem && P.heap_in_smem && P.try_verbatim && !(force && force[0] == '1')) {
             enc->fast = true;
@@ -567,10 +576,11 @@ static int launch_batch(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, ui
     if (P.try_lpc) {
         const u32 blocks = (U + LPC_WARPS * 32 - 1) / (LPC_WARPS * 32);
         const u32 L = P.max_lpc_order;
-        if (L <= 8) k_lpc_model<8><<<blocks, LPC_WARPS * 32, 0, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
-        else if (L <= 12) k_lpc_model<12><<<blocks, LPC_WARPS * 32, 0, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
-        else if (L <= 16) k_lpc_model<16><<<blocks, LPC_WARPS * 32, 0, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
-        else k_lpc_model<32><<<blocks, LPC_WARPS * 32, 0, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
+        const size_t lsm = LPC_WARPS * sizeof(LpcWarpStage);
+        if (L <= 8) k_lpc_model<8><<<blocks, LPC_WARPS * 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
+        else if (L <= 12) k_lpc_model<12><<<blocks, LPC_WARPS * 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
+        else if (L <= 16) k_lpc_model<16><<<blocks, LPC_WARPS * 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
+        else k_lpc_model<32><<<blocks, LPC_WARPS * 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
         enc->launches += 1;
     }
     cudaEventRecord(s.ev[1], st);

@@ -27,7 +27,8 @@ __device__ __forceinline__ u32 pad_idx(u32 i) { return i + i / (u32)S; }
 static inline size_t fast_samp_ints(unsigned bs, int S) { return (size_t)bs + (bs + S - 1) / S + 2; }
 
 // order groups: coefficients are zero-padded to the group size (exact: 0 * x adds nothing)
-__device__ __forceinline__ int order_group(u32 o) { return o <= 4 ? 4 : o <= 8 ? 8 : o <= 12 ? 12 : o <= 16 ? 16 : o <= 24 ? 24 : 32; }
+// (few groups on purpose: the multiply-accumulate is not the bottleneck, instruction fetch is)
+__device__ __forceinline__ int order_group(u32 o) { return o <= 12 ? 12 : 32; }
 
 // r[j] = s[j] - (int)((sum_t q[t] * x[j-1-t]) >> shift), x = own samples then history from smem
 template <int S, int OG, bool WIDE>
@@ -69,14 +70,8 @@ template <int S, bool WIDE>
 __device__ __forceinline__ void lpc_residual_dispatch(const int (&s)[S], const int* samp, u32 base, u32 n, u32 order,
                                                       const short* q_sm, int shift, int (&r)[S])
 {
-    switch (order_group(order)) {
-    case 4: lpc_residual_regs<S, 4, WIDE>(s, samp, base, n, q_sm, shift, r); break;
-    case 8: lpc_residual_regs<S, 8, WIDE>(s, samp, base, n, q_sm, shift, r); break;
-    case 12: lpc_residual_regs<S, 12, WIDE>(s, samp, base, n, q_sm, shift, r); break;
-    case 16: lpc_residual_regs<S, 16, WIDE>(s, samp, base, n, q_sm, shift, r); break;
-    case 24: lpc_residual_regs<S, 24, WIDE>(s, samp, base, n, q_sm, shift, r); break;
-    default: lpc_residual_regs<S, 32, WIDE>(s, samp, base, n, q_sm, shift, r); break;
-    }
+    if (order_group(order) == 12) lpc_residual_regs<S, 12, WIDE>(s, samp, base, n, q_sm, shift, r);
+    else lpc_residual_regs<S, 32, WIDE>(s, samp, base, n, q_sm, shift, r);
 }
 
 // FIXED residual of ORDER for the thread's run (closed forms of the iterated differences)
@@ -179,33 +174,56 @@ __device__ __forceinline__ void rice_search_regs(const AnalyzeCtx& c, RiceScratc
     u64* lvl_total = rs->lvl_total[parity];
     u32* lvl_maxk = rs->lvl_maxk[parity];
 
-    for (u32 i = tid; i < nfine; i += nt) fine[i] = 0ull;
+    // How the per-thread sums reach the finest partitions, decided once per CTA:
+    //   grouped : a partition is g = plenF/S whole runs, g a power of two <= 32 -> warp shuffles, plain store
+    //   owned   : a run is S/plenF whole partitions                            -> plain stores
+    //   else    : shared-memory atomics into a zeroed array (odd tail blocks)
+    const u32 g = plenF / S;
+    const bool grouped = (plenF >= (u32)S) && (plenF % S == 0) && ((g & (g - 1)) == 0) && g <= 32;
+    const bool owned = (plenF < (u32)S) && ((u32)S % plenF == 0);
+    if (!grouped && !owned) for (u32 i = tid; i < nfine; i += nt) fine[i] = 0ull;
     if (tid < 16) { lvl_total[tid] = 0ull; lvl_maxk[tid] = 0u; }
     if (tid == 0) rs->bits_total[parity] = 0ull;
-    __syncthreads();
+    if (!grouped && !owned) __syncthreads();
 
-    // ---- pass 1: sum |r| per finest partition ----
-    if (lo < hi) {
-        const u32 p0 = lo / plenF;
-        if ((hi - 1) / plenF == p0) {
-            u64 run = 0;
+    // ---- pass 1: sum |r| per finest partition (r[] is zero outside [order, n)) ----
+    if (grouped) {
+        u64 run = 0;
 #pragma unroll
-            for (int j = 0; j < S; j++) run += (u64)(u32)abs(r[j]);
-            atomicAdd(&fine[p0], run);
-        } else {
-            u32 p = p0;
-            u32 next = (p + 1) * plenF - base;
-            u64 run = 0;
+        for (int j = 0; j < S; j++) run += (u64)(u32)abs(r[j]);
 #pragma unroll
-            for (int j = 0; j < S; j++) {
-                if ((u32)j == next) {
-                    if (p < nfine) atomicAdd(&fine[p], run);
-                    run = 0; p++; next += plenF;
-                }
-                run += (u64)(u32)abs(r[j]);
-            }
-            if (p < nfine) atomicAdd(&fine[p], run);
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 t = __shfl_xor_sync(0xFFFFFFFFu, run, o);
+            if ((u32)o < g) run += t;
         }
+        const u32 p = (u32)tid / g;
+        if (((u32)tid & (g - 1)) == 0 && p < nfine) fine[p] = run;
+    } else if (owned) {
+        u32 p = base / plenF;
+        u32 next = plenF;
+        u64 run = 0;
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+            if ((u32)j == next) {
+                if (p < nfine) fine[p] = run;
+                run = 0; p++; next += plenF;
+            }
+            run += (u64)(u32)abs(r[j]);
+        }
+        if (p < nfine) fine[p] = run;
+    } else if (lo < hi) {
+        u32 p = lo / plenF;
+        u32 next = (p + 1) * plenF - base;
+        u64 run = 0;
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+            if ((u32)j == next) {
+                if (p < nfine) atomicAdd(&fine[p], run);
+                run = 0; p++; next += plenF;
+            }
+            run += (u64)(u32)abs(r[j]);
+        }
+        if (p < nfine) atomicAdd(&fine[p], run);
     }
     __syncthreads();
 
@@ -226,38 +244,64 @@ __device__ __forceinline__ void rice_search_regs(const AnalyzeCtx& c, RiceScratc
     }
     __syncthreads();
 
-    // ---- one thread per (level, partition): Rice parameter, estimate ----
+    // ---- one thread per (level, partition): Rice parameter, estimate.  Nodes are numbered as in a
+    // binary heap (node 1 = level 0; level l = nodes 2^l .. 2^(l+1)-1), thread t takes node t, so a
+    // level's nodes are an aligned lane group: its total and max are warp reductions, not atomics ----
     const u32 heapn = 2 * nfine - 1;
-    for (u32 idx = tid; idx < heapn; idx += nt) {
-        const u32 l = 31u - (u32)__clz((int)(idx + 1));
-        const u32 p = idx + 1 - (1u << l);
-        const u32 w = nfine >> l;                       // finest partitions per partition of level l
-        const u64 hi_sum = fine[(p + 1) * w - 1];
-        const u64 lo_sum = p ? fine[p * w - 1] : 0ull;
-        const u32 plength = (n >> l) - (p == 0 ? order : 0u);
-        u32 k;
-        const u64 est = partition_estimate_fast(plength, hi_sum - lo_sum, P.max_rice, &k);
-        c.karr[idx] = (uint8_t)k;
-        atomicAdd(&lvl_total[l], est);
-        atomicMax(&lvl_maxk[l], k);
+    for (u32 node0 = 0; node0 <= heapn; node0 += nt) {
+        const u32 node = node0 + tid;
+        const bool act = node >= 1 && node <= heapn;
+        u32 l = 0, k = 0;
+        u64 est = 0;
+        if (act) {
+            l = 31u - (u32)__clz((int)node);
+            const u32 p = node - (1u << l);
+            const u32 w = nfine >> l;                   // finest partitions per partition of level l
+            const u64 hi_sum = fine[(p + 1) * w - 1];
+            const u64 lo_sum = p ? fine[p * w - 1] : 0ull;
+            const u32 plength = (n >> l) - (p == 0 ? order : 0u);
+            est = partition_estimate_fast(plength, hi_sum - lo_sum, P.max_rice, &k);
+            c.karr[node - 1] = (uint8_t)k;
+        }
+        if (node0 + (u32)(tid & ~31) >= 32) {
+            // the whole warp sits inside one level (or past the heap)
+            u32 km = __reduce_max_sync(0xFFFFFFFFu, k);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) est += __shfl_xor_sync(0xFFFFFFFFu, est, o);
+            const u32 l0 = __shfl_sync(0xFFFFFFFFu, l, 0);
+            if (lane == 0 && node <= heapn) { atomicAdd(&lvl_total[l0], est); atomicMax(&lvl_maxk[l0], km); }
+        } else {
+            // nodes 1..31 = levels 0..4: segmented butterfly inside groups of 2^l lanes
+            const u32 gs = act ? (1u << l) : 1u;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const u64 te = __shfl_xor_sync(0xFFFFFFFFu, est, o);
+                const u32 tk = __shfl_xor_sync(0xFFFFFFFFu, k, o);
+                if ((u32)o < gs) { est += te; k = max(k, tk); }
+            }
+            if (act && node == gs) { lvl_total[l] = est; lvl_maxk[l] = k; }
+        }
     }
     __syncthreads();
 
     // ---- first strict minimum over the levels (every thread, redundantly) ----
     u64 best = lvl_total[0];
     u32 po = 0, k0 = 0;
-    for (u32 l = 1; l <= po_eff; l++) {
-        u64 tot;
-        u32 kk = 0;
-        if (l <= F) {
-            tot = lvl_total[l];
-        } else {
-            // underflow level: partition 0 swallows every residual, the others are empty (H3)
-            const u32 pl = n >> l;
-            tot = partition_estimate(pl - order, fine[nfine - 1], P.max_rice, &kk);
-            tot += (u64)((1u << l) - 1u) * (4ull + (u64)pl - (u64)(pl / 2));
+#pragma unroll
+    for (u32 l = 1; l <= BF_MAX_PO; l++) {
+        if (l <= po_eff) {
+            u64 tot;
+            u32 kk = 0;
+            if (l <= F) {
+                tot = lvl_total[l];
+            } else {
+                // underflow level: partition 0 swallows every residual, the others are empty (H3)
+                const u32 pl = n >> l;
+                tot = partition_estimate(pl - order, fine[nfine - 1], P.max_rice, &kk);
+                tot += (u64)((1u << l) - 1u) * (4ull + (u64)pl - (u64)(pl / 2));
+            }
+            if (tot < best) { best = tot; po = l; k0 = kk; }
         }
-        if (tot < best) { best = tot; po = l; k0 = kk; }
     }
     const u32 under = po > F ? 1u : 0u;
     const u32 koff = (1u << po) - 1u;
@@ -449,7 +493,7 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
                 if (base >= 4) a4 = (u32)c.samp[pad_idx<S>(base - 4)];
                 u32 p1 = a1 - a2, p2 = p1 - (a2 - a3), p3 = p2 - ((a2 - a3) - (a3 - a4));
                 u32 prev = a1;
-                if ((base >= 4) && (base + S <= n) && sub_bps <= 18) {
+                if ((base + S <= n) && sub_bps <= 18) {
                     // |d4| < 2^(sub_bps+3) <= 2^21: S <= 36 terms and then 32 lanes still fit 32 bits
 #pragma unroll
                     for (int j = 0; j < S; j++) {
@@ -458,6 +502,21 @@ k_analyze_fast(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict_
                         f0 += (u32)abs((int)x); f1 += (u32)abs((int)d1); f2 += (u32)abs((int)d2);
                         f3 += (u32)abs((int)d3); f4 += (u32)abs((int)d4);
                         prev = x; p1 = d1; p2 = d2; p3 = d3;
+                    }
+                    if (base < 4) {
+                        // the block's first four samples are warm-up for every order (flac.c:877-889):
+                        // take their terms (computed above with a zero history) out again
+                        u32 q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+#pragma unroll
+                        for (int j = 0; j < 4 && j < S; j++) {
+                            if (base + j < 4) {
+                                const u32 x = (u32)s[j];
+                                const u32 d1 = x - q0, d2 = d1 - q1, d3 = d2 - q2, d4 = d3 - q3;
+                                f0 -= (u32)abs((int)x); f1 -= (u32)abs((int)d1); f2 -= (u32)abs((int)d2);
+                                f3 -= (u32)abs((int)d3); f4 -= (u32)abs((int)d4);
+                                q0 = x; q1 = d1; q2 = d2; q3 = d3;
+                            }
+                        }
                     }
                 } else {
                     slow = true;

@@ -23,7 +23,8 @@
 #include "flac_common.cuh"
 
 #define LPC_WARPS 4
-#define LPC_STAGE_WORDS 1664         // per-warp staging: rows * (TS*C*B + 8) bytes fits for C <= 8, B <= 3
+#define LPC_STAGE_WORDS 1344         // words per staging buffer and warp (two buffers per warp)
+#define LPC_MAX_ROWS 34              // frames a warp's 32 units can span (K = 1: 32)
 
 // (int)round(x) the way x86-64 cvttsd2si does it: NaN / out of range -> INT_MIN
 // (CUDA's own conversion would give 0 / saturate)
@@ -69,23 +70,43 @@ __device__ void quantize_coefficients(const double* c, u32 order, u32 precision,
     *shift_out = shift;
 }
 
+// ---- cp.async (LDGSTS) helpers: 4-byte copies work for any sample width / alignment ----
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// per-warp staging area (dynamic shared memory): two tile buffers + the rows' descriptors
+struct LpcWarpStage {
+    u32 buf[2][LPC_STAGE_WORDS];
+    u64 row_byte0[LPC_MAX_ROWS];   // byte offset of the row's first PCM frame
+    u32 row_n[LPC_MAX_ROWS];       // PCM frames in the row (0: no such frame)
+};
+
 // One pass over the warp's units accumulating lags LB .. LB+NL-1.
-// hist is a ring of H = LB+NL windowed samples with compile-time indexing.
+// hist is a ring of H = LB+NL windowed samples with compile-time indexing; tiles of TS = H*M
+// PCM frames per row are staged with cp.async, double buffered, so the copy of tile t+1 is in
+// flight while tile t is consumed.
 template <int LB, int NL>
-__device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
-                                           const double* __restrict__ windows, const bf_dev_params& P,
-                                           u32 n_frames, u32 f0, u32 nrows, u32 nmax,
-                                           bool valid, u32 myrow, u32 cand, u32 n, u64 pcm_off, u32 woff,
-                                           u32* stage, double* acc, u32* or_out)
+__device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, const double* __restrict__ windows,
+                                           const bf_dev_params& P, u32 nrows, u32 nmax,
+                                           bool valid, u32 myrow, u32 cand, u32 n, u32 woff,
+                                           LpcWarpStage* st, double* acc, u32* or_out)
 {
     constexpr int H = LB + NL;
-    constexpr int M = (H <= 16) ? 2 : 1;
-    constexpr int TS = H * M;
     const int lane = threadIdx.x & 31;
     const u32 C = P.channels, B = P.bytes_ps;
     const u32 rowbytes = C * B;
-
+    // tile length: as many ring rotations as fit the staging buffer (at most 8)
+    u32 M = ((LPC_STAGE_WORDS / nrows - 3) * 4) / (H * rowbytes);
+    M = M < 1 ? 1 : (M > 8 ? 8 : M);
+    const u32 TS = H * M;
     const u32 row_words = ((TS * rowbytes + 4 + 3) >> 2) + 1;
+
     double hist[H];
     double a_[NL];          // private accumulators: stay in registers
 #pragma unroll
@@ -94,30 +115,37 @@ __device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, cons
     for (int i = 0; i < NL; i++) a_[i] = 0.0;
     u32 orv = 0;
 
-    for (u32 i0 = 0; i0 < nmax; i0 += TS) {
-        // ---- stage TS PCM frames of every row, coalesced ----
-        __syncwarp();
+    auto issue_tile = [&](u32 i0, u32 b) {
         for (u32 r = 0; r < nrows; r++) {
-            const u32 f = f0 + r;
-            if (f >= n_frames) break;
-            const bf_frame_desc d = fd[f];
-            if (i0 >= d.nsamp) continue;
-            const u32 take = min((u32)TS, d.nsamp - i0);
-            const u64 a = (d.pcm_off + i0) * rowbytes;
-            const u32 mis = (u32)(a & 3);
-            const u32 nwords = (mis + take * rowbytes + 3) >> 2;
-            const u32* src = (const u32*)(pcm + (a - mis));
-            u32* dst = stage + r * row_words;
-            for (u32 w = lane; w < nwords; w += 32) dst[w] = __ldg(src + w);
+            const u32 rn = st->row_n[r];
+            if (i0 < rn) {
+                const u32 take = min(TS, rn - i0);
+                const u64 a = st->row_byte0[r] + (u64)i0 * rowbytes;
+                const u32 mis = (u32)(a & 3);
+                const u32 nwords = (mis + take * rowbytes + 3) >> 2;
+                const u32* src = (const u32*)(pcm + (a - mis));
+                u32* dst = st->buf[b] + r * row_words;
+                for (u32 w = lane; w < nwords; w += 32) cp_async4(dst + w, src + w);
+            }
         }
+        cp_async_commit();
+    };
+
+    const u64 my_byte0 = st->row_byte0[myrow];
+    issue_tile(0, 0);
+    u32 b = 0;
+    for (u32 i0 = 0; i0 < nmax; i0 += TS, b ^= 1) {
+        if (i0 + TS < nmax) { issue_tile(i0 + TS, b ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
         __syncwarp();
-        // ---- every lane walks its own row ----
-        const uint8_t* row = (const uint8_t*)(stage + myrow * row_words) + (u32)(((pcm_off + i0) * rowbytes) & 3);
-#pragma unroll
-        for (int m = 0; m < M; m++) {
+        const uint8_t* row = (const uint8_t*)(st->buf[b] + myrow * row_words) + (u32)((my_byte0 + (u64)i0 * rowbytes) & 3);
+#pragma unroll 1
+        for (u32 m = 0; m < M; m++) {
+            const u32 tbase = m * H;
+            if (i0 + tbase >= nmax) break;
 #pragma unroll
             for (int u = 0; u < H; u++) {
-                const u32 t = m * H + u;
+                const u32 t = tbase + u;
                 const u32 i = i0 + t;
                 double x = 0.0;
                 if (valid && i < n) {
@@ -139,6 +167,7 @@ __device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, cons
                 }
             }
         }
+        __syncwarp(); // everyone is done with buf[b] before it is refilled two tiles later
     }
 #pragma unroll
     for (int i = 0; i < NL; i++) acc[i] = a_[i];
@@ -152,9 +181,9 @@ k_lpc_model(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ f
             const double* __restrict__ windows, bf_dev_params P,
             bf_lpc_head* __restrict__ heads, short* __restrict__ coefs)
 {
-    __shared__ u32 stage_all[LPC_WARPS][LPC_STAGE_WORDS];
+    extern __shared__ __align__(16) unsigned char lpc_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32* stage = stage_all[warp];
+    LpcWarpStage* st = (LpcWarpStage*)lpc_smem + warp;
 
     const u32 K = P.K;
     const u32 U = n_frames * K;
@@ -172,17 +201,23 @@ k_lpc_model(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ f
     const u32 nmax = __reduce_max_sync(0xFFFFFFFFu, n);
     const u32 L = P.max_lpc_order;
 
+    // row descriptors, once
+    for (u32 r = lane; r < nrows; r += 32) {
+        const bf_frame_desc rd = fd[f0 + r];
+        st->row_byte0[r] = rd.pcm_off * (u64)(P.channels * P.bytes_ps);
+        st->row_n[r] = rd.nsamp;
+    }
+    __syncwarp();
+
     double autoc[MAXL + 1];
     u32 orv = 0;
     if constexpr (MAXL <= 16) {
-        autoc_pass<0, MAXL + 1>(pcm, fd, windows, P, n_frames, f0, nrows, nmax, valid, frame - f0, cand, n,
-                                d.pcm_off, d.window_off, stage, autoc, &orv);
+        autoc_pass<0, MAXL + 1>(pcm, windows, P, nrows, nmax, valid, frame - f0, cand, n, d.window_off, st, autoc, &orv);
     } else {
         u32 dummy;
-        autoc_pass<0, 17>(pcm, fd, windows, P, n_frames, f0, nrows, nmax, valid, frame - f0, cand, n,
-                          d.pcm_off, d.window_off, stage, autoc, &orv);
-        autoc_pass<17, 16>(pcm, fd, windows, P, n_frames, f0, nrows, nmax, valid, frame - f0, cand, n,
-                           d.pcm_off, d.window_off, stage, autoc + 17, &dummy);
+        autoc_pass<0, 17>(pcm, windows, P, nrows, nmax, valid, frame - f0, cand, n, d.window_off, st, autoc, &orv);
+        __syncwarp();
+        autoc_pass<17, 16>(pcm, windows, P, nrows, nmax, valid, frame - f0, cand, n, d.window_off, st, autoc + 17, &dummy);
     }
     if (!valid) return;
 

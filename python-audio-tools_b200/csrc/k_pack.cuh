@@ -341,22 +341,36 @@ __global__ void k_pack_subframes(const uint8_t* __restrict__ pcm, const bf_frame
     }
 }
 
-// one warp per frame: CRC-16 over every byte before it, appended big-endian
+// one warp per frame: CRC-16 over every byte before it, appended big-endian.
+// Byte-table CRC per lane over a contiguous chunk (aligned 32-bit loads), then
+// crc(A||B) = crc(A) * x^(8|B|) + crc(B) to combine the 32 chunks.
 __global__ void k_frame_crc16(const u64* __restrict__ frame_off, const u32* __restrict__ frame_bytes,
                               u32 n_frames, uint8_t* __restrict__ out, const u64* __restrict__ total,
                               u64 capacity_bytes)
 {
+    __shared__ unsigned short tab[256];
+    for (u32 t = threadIdx.x; t < 256; t += blockDim.x) tab[t] = (unsigned short)crc16_byte(0, t);
+    __syncthreads();
     if (*total + 16 > capacity_bytes) return;
     const u32 f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (f >= n_frames) return;
     const uint8_t* p = out + frame_off[f];
     const u32 nb = frame_bytes[f] - 2;
-    const u32 per = (nb + 31) / 32;
+    const u32 per = ((nb + 31) / 32 + 3) & ~3u;
     const u32 b0 = min(lane * per, nb), b1 = min(b0 + per, nb);
     u32 crc = 0;
-    for (u32 i = b0; i < b1; i++) crc = crc16_byte(crc, p[i]);
-    // crc(A||B) = crc(A) * x^(8|B|) + crc(B): shift each lane's CRC past the bytes after it
+    u32 i = b0;
+    // head bytes up to 4-byte alignment, then whole words, then the tail
+    while (i < b1 && ((uintptr_t)(p + i) & 3)) { crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ p[i]]; i++; }
+    for (; i + 4 <= b1; i += 4) {
+        const u32 w = *(const u32*)(p + i);
+        crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ (w & 0xFF)];
+        crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ ((w >> 8) & 0xFF)];
+        crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ ((w >> 16) & 0xFF)];
+        crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ (w >> 24)];
+    }
+    for (; i < b1; i++) crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ p[i]];
     crc = gf16_mul(crc, gf16_xpow8(nb - b1));
 #pragma unroll
     for (int o = 16; o; o >>= 1) crc ^= __shfl_xor_sync(0xFFFFFFFFu, crc, o);
