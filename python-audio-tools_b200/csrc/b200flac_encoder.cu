@@ -20,6 +20,8 @@
 #include "k_pack.cuh"
 #include "k_analyze_fast.cuh"
 #include "k_pack_fast.cuh"
+#include "k_analyze_v2.cuh"
+#include "k_pack_v2.cuh"
 #include "k_synth.cuh"
 
 #define BF_MAX_SEGMENTS 65536
@@ -262,14 +264,6 @@ static cudaError_t set_smem_attrs(size_t smem_a, size_t smem_p)
     return cudaFuncSetAttribute(k_pack_subframes<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
 }
 
-template <int S>
-static cudaError_t set_smem_attrs_fast(size_t smem_a, size_t smem_p)
-{
-    cudaError_t e = cudaFuncSetAttribute(k_analyze_fast<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_pack_fast<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
-}
-
 extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* params, int device,
                                                      uint64_t max_pcm_frames_per_batch, int n_slots)
 {
@@ -300,25 +294,25 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
 
     const u32 bs = params->block_size;
     const size_t padn = (size_t)PADI(bs) + 1;
-    // fast path: whole block in one pass of <= 512 threads x S samples, everything in shared memory,
-    // VERBATIM a candidate (bounds the subframe image).  Pick S with the least idle lanes.
+    // v2 kernels: whole block in one pass of <= 512 threads x S samples (S a multiple of 8), samples,
+    // residual and partition heap in shared memory, VERBATIM a candidate (bounds the subframe image).
     enc->fast = false;
     enc->stage_words = 0;
     {
-        const int cand[5] = {32, 36, 16, 18, 8};
         int bestS = 0, bestNT = 0;
-        long bestWaste = -1;
-        for (int i = 0; i < 5; i++) {
-            int nt = (int)((bs + cand[i] - 1) / cand[i]);
+        long bestCost = -1;
+        for (int cs = 8; cs <= 128; cs += 8) {
+            int nt = (int)((bs + cs - 1) / cs);
             nt = (nt + 31) & ~31;
             if (nt > 512) continue;
-            const long waste = (long)nt * cand[i] - (long)bs;
-            if (bestWaste < 0 || waste < bestWaste) { bestWaste = waste; bestS = cand[i]; bestNT = nt; }
+            if (cs > 32 && bestS) break;                       // longer runs only when the block needs them
+            const long cost = (long)nt * (cs + 24);            // per-thread fixed work ~ 24 samples' worth
+            if (bestCost < 0 || cost < bestCost) { bestCost = cost; bestS = cs; bestNT = nt; }
         }
-        const char* sforce = getenv("B200FLAC_S"); // tuning knob: force the samples-per-thread of the fast kernels
+        const char* sforce = getenv("B200FLAC_S"); // tuning knob: force the samples-per-thread
         if (sforce) {
             const int fs = atoi(sforce);
-            for (int i = 0; i < 5; i++) if (cand[i] == fs) {
+            if (fs >= 8 && fs % 8 == 0) {
                 int nt = (int)((bs + fs - 1) / fs);
                 nt = (nt + 31) & ~31;
                 if (nt <= 512) { bestS = fs; bestNT = nt; }
@@ -336,21 +330,15 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     size_t sa = 0, sp = 0;
     cudaError_t e = cudaSuccess;
     if (enc->fast) {
-        const size_t fs = fast_samp_ints(bs, enc->S) * 4;
-        sa = fs + 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride + 16;
-        sp = fs + (size_t)enc->stage_words * 4 + 16;
+        sa = 2 * padn * 4 + 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride + 16;
+        sp = 2 * padn * 4 + (size_t)enc->stage_words * 4 + 16;
         if (sa > 200 * 1024 || sp > 200 * 1024) enc->fast = false;
     }
     if (enc->fast) {
         enc->smem_analyze = sa;
         enc->smem_pack = sp;
-        switch (enc->S) {
-        case 8: e = set_smem_attrs_fast<8>(sa, sp); break;
-        case 16: e = set_smem_attrs_fast<16>(sa, sp); break;
-        case 18: e = set_smem_attrs_fast<18>(sa, sp); break;
-        case 32: e = set_smem_attrs_fast<32>(sa, sp); break;
-        default: e = set_smem_attrs_fast<36>(sa, sp); break;
-        }
+        e = cudaFuncSetAttribute(k_analyze_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pack_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
     } else {
         enc->S = bs >= 2048 ? 32 : (bs >= 512 ? 16 : 8);
         int nt = (int)((bs + enc->S - 1) / enc->S);
@@ -545,21 +533,20 @@ static void launch_analyze_pack(b200flac_encoder* enc, Slot& s, const uint8_t* d
     enc->launches += 6;
 }
 
-template <int S>
-static void launch_analyze_pack_fast(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
+static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
 {
     const bf_dev_params& P = enc->P;
     const u32 nf = s.n_frames, U = nf * P.K;
     cudaStream_t st = s.stream;
-    k_analyze_fast<S><<<U, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+    k_analyze_v2<<<U, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
     cudaEventRecord(s.ev[2], st);
     k_frame_select<<<(nf + 127) / 128, 128, 0, st>>>(s.d_fd, nf, P, s.d_plans, s.d_choice, s.d_frame_bytes);
     k_scan_offsets<<<1, 1024, 0, st>>>(s.d_frame_bytes, nf, s.d_frame_off, s.d_total);
     k_zero_output<<<148 * 4, 256, 0, st>>>((uint4*)d_out, s.d_total, out_cap);
     cudaEventRecord(s.ev[3], st);
-    k_pack_fast<S><<<nf * P.channels, enc->NT, enc->smem_pack, st>>>(d_pcm, s.d_fd, P, s.d_plans, s.d_rice, s.d_choice,
-                                                                    s.d_frame_off, (u32*)d_out, s.d_total, out_cap,
-                                                                    enc->stage_words);
+    k_pack_v2<<<nf * P.channels, enc->NT, enc->smem_pack, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
+                                                               s.d_frame_off, (u32*)d_out, s.d_total, out_cap,
+                                                               enc->stage_words);
     cudaEventRecord(s.ev[4], st);
     k_frame_crc16<<<(nf * 32 + 127) / 128, 128, 0, st>>>(s.d_frame_off, s.d_frame_bytes, nf, d_out, s.d_total, out_cap);
     cudaEventRecord(s.ev[5], st);
@@ -585,13 +572,7 @@ static int launch_batch(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, ui
     }
     cudaEventRecord(s.ev[1], st);
     if (enc->fast) {
-        switch (enc->S) {
-        case 8: launch_analyze_pack_fast<8>(enc, s, d_pcm, d_out, out_cap); break;
-        case 16: launch_analyze_pack_fast<16>(enc, s, d_pcm, d_out, out_cap); break;
-        case 18: launch_analyze_pack_fast<18>(enc, s, d_pcm, d_out, out_cap); break;
-        case 32: launch_analyze_pack_fast<32>(enc, s, d_pcm, d_out, out_cap); break;
-        default: launch_analyze_pack_fast<36>(enc, s, d_pcm, d_out, out_cap); break;
-        }
+        launch_analyze_pack_v2(enc, s, d_pcm, d_out, out_cap);
     } else if (enc->S == 32) launch_analyze_pack<32>(enc, s, d_pcm, d_out, out_cap);
     else if (enc->S == 16) launch_analyze_pack<16>(enc, s, d_pcm, d_out, out_cap);
     else launch_analyze_pack<8>(enc, s, d_pcm, d_out, out_cap);
