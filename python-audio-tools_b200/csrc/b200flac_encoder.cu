@@ -18,8 +18,6 @@
 #include "k_lpc_model.cuh"
 #include "k_analyze.cuh"
 #include "k_pack.cuh"
-#include "k_analyze_fast.cuh"
-#include "k_pack_fast.cuh"
 #include "k_analyze_v2.cuh"
 #include "k_pack_v2.cuh"
 #include "k_synth.cuh"
@@ -88,8 +86,8 @@ struct b200flac_encoder {
     int S;                // samples per thread (template selector)
     int NT;               // threads per CTA for analyze/pack
     size_t smem_analyze, smem_pack;
-    bool fast;            // register-resident kernels (k_analyze_fast / k_pack_fast) apply
-    u32 stage_words;      // shared-memory image of one subframe, in words (fast pack)
+    bool fast;            // the shared-memory resident kernels (k_analyze_v2 / k_pack_v2) apply
+    u32 stage_words;      // shared-memory image of one subframe, in words (k_pack_v2)
     std::map<u32, std::vector<double>>* windows;
     u64 launches;
 };
@@ -337,8 +335,14 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     if (enc->fast) {
         enc->smem_analyze = sa;
         enc->smem_pack = sp;
-        e = cudaFuncSetAttribute(k_analyze_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pack_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
+        // two register budgets: small CTAs (<= 192 threads) are compiled for 6 resident CTAs per SM
+        if (enc->NT <= 192) {
+            e = cudaFuncSetAttribute(k_analyze_v2<192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pack_v2<192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
+        } else {
+            e = cudaFuncSetAttribute(k_analyze_v2<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pack_v2<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
+        }
     } else {
         enc->S = bs >= 2048 ? 32 : (bs >= 512 ? 16 : 8);
         int nt = (int)((bs + enc->S - 1) / enc->S);
@@ -538,15 +542,23 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
     const bf_dev_params& P = enc->P;
     const u32 nf = s.n_frames, U = nf * P.K;
     cudaStream_t st = s.stream;
-    k_analyze_v2<<<U, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+    if (enc->NT <= 192)
+        k_analyze_v2<192, 4><<<U, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+    else
+        k_analyze_v2<512, 1><<<U, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
     cudaEventRecord(s.ev[2], st);
     k_frame_select<<<(nf + 127) / 128, 128, 0, st>>>(s.d_fd, nf, P, s.d_plans, s.d_choice, s.d_frame_bytes);
     k_scan_offsets<<<1, 1024, 0, st>>>(s.d_frame_bytes, nf, s.d_frame_off, s.d_total);
     k_zero_output<<<148 * 4, 256, 0, st>>>((uint4*)d_out, s.d_total, out_cap);
     cudaEventRecord(s.ev[3], st);
-    k_pack_v2<<<nf * P.channels, enc->NT, enc->smem_pack, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
-                                                               s.d_frame_off, (u32*)d_out, s.d_total, out_cap,
-                                                               enc->stage_words);
+    if (enc->NT <= 192)
+        k_pack_v2<192, 4><<<nf * P.channels, enc->NT, enc->smem_pack, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice,
+                                                                         s.d_choice, s.d_frame_off, (u32*)d_out, s.d_total,
+                                                                         out_cap, enc->stage_words);
+    else
+        k_pack_v2<512, 1><<<nf * P.channels, enc->NT, enc->smem_pack, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice,
+                                                                         s.d_choice, s.d_frame_off, (u32*)d_out, s.d_total,
+                                                                         out_cap, enc->stage_words);
     cudaEventRecord(s.ev[4], st);
     k_frame_crc16<<<(nf * 32 + 127) / 128, 128, 0, st>>>(s.d_frame_off, s.d_frame_bytes, nf, d_out, s.d_total, out_cap);
     cudaEventRecord(s.ev[5], st);

@@ -16,7 +16,37 @@
 #pragma once
 #include "flac_common.cuh"
 #include "k_analyze.cuh"
-#include "k_analyze_fast.cuh"   // partition_estimate_fast, RiceScratch
+
+// Rice parameter + estimate of one partition, same results as partition_estimate():
+// closed form when no shift of the reference's loop can wrap 32 bits, the loop itself otherwise.
+__device__ __forceinline__ u64 partition_estimate_fast(u32 plength, u64 S_, u32 max_rice, u32* k_out)
+{
+    u32 k;
+    if (S_ <= (u64)plength) {
+        k = 0;
+    } else if (plength == 0 || ((u64)plength << max_rice) >= (1ull << 32)) {
+        return partition_estimate(plength, S_, max_rice, k_out);
+    } else {
+        // smallest k with (plength << k) >= S_; none of the shifts up to max_rice wraps
+        int kc = (64 - __clzll((long long)S_)) - (32 - __clz((int)plength)) - 1;
+        if (kc < 0) kc = 0;
+        while (((u64)plength << kc) < S_) kc++;
+        k = (u32)kc < max_rice ? (u32)kc : max_rice;
+    }
+    u64 est;
+    if (k > 0) est = 4ull + (S_ >> (k - 1)) + (u64)(u32)((1u + k) * plength) - (u64)(plength / 2);
+    else       est = 4ull + (S_ << 1) + (u64)plength - (u64)(plength / 2);
+    *k_out = k;
+    return est;
+}
+
+// shared scratch of the Rice search (double buffered by search parity, see rice_search_v2)
+struct RiceScratch {
+    u64 lvl_total[2][16];
+    u64 bits_total[2];
+    u32 lvl_maxk[2][16];
+};
+
 
 #define V2_CH 8
 // address of the chunk starting at sample i0 (i0 % 8 == 0): the 8 samples are contiguous words,
@@ -450,7 +480,8 @@ __device__ __forceinline__ void fixed_residual_v2(const V2Ctx& c, u32 order)
     }
 }
 
-__global__ void __launch_bounds__(512)
+template <int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB)
 k_analyze_v2(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S,
              const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
              b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out)

@@ -13,10 +13,93 @@
 #pragma once
 #include "flac_common.cuh"
 #include "k_analyze_v2.cuh"
-#include "k_pack_fast.cuh"   // RunSink, SmemSink, put_subframe_header_s
 #include "k_pack.cuh"
 
-__global__ void __launch_bounds__(512)
+// MSB-first writer into the shared image.  The first word the thread touches is kept in
+// `first_w` (merged later); every further completed word is exclusively the thread's.
+struct RunSink {
+    u32* words;
+    u32 widx, widx0;
+    u64 acc;
+    u32 fill;
+    u32 first_w;
+    __device__ __forceinline__ void init(u32* base, u32 bitpos)
+    {
+        words = base; widx = bitpos >> 5; widx0 = widx; fill = bitpos & 31; acc = 0; first_w = 0;
+    }
+    __device__ __forceinline__ void put(u32 v, u32 nbits) // 1 <= nbits <= 32, v < 2^nbits
+    {
+        acc |= (u64)v << (64 - fill - nbits);
+        fill += nbits;
+        if (fill >= 32) {
+            const u32 w = (u32)(acc >> 32);
+            if (widx == widx0) first_w = w; else words[widx] = w;
+            widx++; acc <<= 32; fill -= 32;
+        }
+    }
+    __device__ __forceinline__ void zeros(u32 nz)
+    {
+        const u32 tot = fill + nz;
+        if (tot >= 32) {
+            const u32 w = (u32)(acc >> 32);
+            if (widx == widx0) first_w = w; else words[widx] = w; // following all-zero words are already zero
+            widx += tot >> 5; acc = 0; fill = tot & 31;
+        } else fill = tot;
+    }
+    // merge the two boundary words
+    __device__ __forceinline__ void finish()
+    {
+        if (widx == widx0) {
+            const u32 w = (u32)(acc >> 32);
+            if (w) atomicOr(words + widx0, w);
+        } else {
+            if (first_w) atomicOr(words + widx0, first_w);
+            const u32 w = (u32)(acc >> 32);
+            if (fill && w) atomicOr(words + widx, w);
+        }
+    }
+};
+
+// generic small writer (headers): everything through shared atomics
+struct SmemSink {
+    u32* words;
+    u32 widx;
+    u64 acc;
+    u32 fill;
+    __device__ __forceinline__ void init(u32* base, u32 bitpos) { words = base; widx = bitpos >> 5; fill = bitpos & 31; acc = 0; }
+    __device__ __forceinline__ void put(u32 v, u32 nbits)
+    {
+        if (nbits == 0) return;
+        acc |= (u64)v << (64 - fill - nbits);
+        fill += nbits;
+        if (fill >= 32) {
+            const u32 w = (u32)(acc >> 32);
+            if (w) atomicOr(words + widx, w);
+            widx++; acc <<= 32; fill -= 32;
+        }
+    }
+    __device__ __forceinline__ void put_signed(int v, u32 nbits) { put(nbits >= 32 ? (u32)v : ((u32)v & ((1u << nbits) - 1u)), nbits); }
+    __device__ __forceinline__ void zeros(u32 n)
+    {
+        const u32 tot = fill + n;
+        if (tot >= 32) {
+            const u32 top = (u32)(acc >> 32);
+            if (top) atomicOr(words + widx, top);
+            widx += tot >> 5; acc = 0; fill = tot & 31;
+        } else fill = tot;
+    }
+    __device__ __forceinline__ void flush() { if (fill) { const u32 top = (u32)(acc >> 32); if (top) atomicOr(words + widx, top); } }
+};
+
+__device__ __forceinline__ void put_subframe_header_s(SmemSink& bs, u32 type_bits, u32 wasted)
+{
+    bs.put(type_bits & 0x3F, 7);
+    if (wasted) { bs.put(1, 1); bs.zeros(wasted - 1); bs.put(1, 1); }
+    else bs.put(0, 1);
+}
+
+template <int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB)
 k_pack_v2(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S,
           const b200flac_plan* __restrict__ plans, const uint8_t* __restrict__ rice,
           const bf_frame_choice* __restrict__ choice, const u64* __restrict__ frame_off,
@@ -118,7 +201,6 @@ k_pack_v2(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
         const u32 res0 = hdr_end + 6;
         const int shift = s_plan.shift;
         if (ptype == BF_FIXED) fixed_residual_v2(c, order);
-        else if (order <= 8) { if (narrow) lpc_residual_v2<8, false>(c, s_q, shift); else lpc_residual_v2<8, true>(c, s_q, shift); }
         else if (order <= 12) { if (narrow) lpc_residual_v2<12, false>(c, s_q, shift); else lpc_residual_v2<12, true>(c, s_q, shift); }
         else { if (narrow) lpc_residual_v2<32, false>(c, s_q, shift); else lpc_residual_v2<32, true>(c, s_q, shift); }
 
