@@ -132,6 +132,13 @@ __device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, cons
     };
 
     const u64 my_byte0 = st->row_byte0[myrow];
+    // per-lane constants of the fast paths
+    const bool st16 = P.stereo && B == 2;
+    const int cl = cand == 1 ? 0 : 1, cr = cand == 0 ? 0 : (cand == 3 ? -1 : 1), sh = cand == 2 ? 1 : 0;
+    const u32 nmin = __reduce_min_sync(0xFFFFFFFFu, valid ? n : nmax);
+    // flat part of the Tukey window of length n (flac.c:1140-1152): window1 < i <= window2
+    const u32 flat_lo = valid ? ((u32)(0.5 * (n - 1)) / 2 + 1) : 0u;
+    const u32 flat_hi = valid ? (u32)((n - 1) * (1.0 - (0.5 / 2.0))) : 0xFFFFFFFFu;
     issue_tile(0, 0);
     u32 b = 0;
     for (u32 i0 = 0; i0 < nmax; i0 += TS, b ^= 1) {
@@ -142,28 +149,68 @@ __device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, cons
 #pragma unroll 1
         for (u32 m = 0; m < M; m++) {
             const u32 tbase = m * H;
-            if (i0 + tbase >= nmax) break;
+            const u32 ig = i0 + tbase;                 // first sample of this ring rotation
+            if (ig >= nmax) break;
+            // whole rotation in range for every lane, stereo 16-bit rows (always 4-byte aligned)?
+            const bool full = st16 && (ig + H <= nmin);
+            // ... and inside the flat part of every lane's Tukey window, partners included: samples are
+            // exact integers there and their products are exact in double, so fma(x, y, acc) rounds
+            // exactly like the reference's multiply-then-add
+            const bool flat = full && __all_sync(0xFFFFFFFFu, ig >= flat_lo + (H - 1) && ig + H - 1 <= flat_hi);
+            if (flat) {
+                const u32* rw = (const u32*)row + tbase;
 #pragma unroll
-            for (int u = 0; u < H; u++) {
-                const u32 t = tbase + u;
-                const u32 i = i0 + t;
-                double x = 0.0;
-                if (valid && i < n) {
-                    int s;
-                    if (!P.stereo) {
-                        s = ld_pcm(row, t * C + cand, B);
-                    } else {
-                        const int L = ld_pcm(row, t * 2, B), R = ld_pcm(row, t * 2 + 1, B);
-                        s = cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
+                for (int u = 0; u < H; u++) {
+                    const u32 pr = rw[u];
+                    const int sv = (cl * (int)(short)(pr & 0xFFFF) + cr * ((int)pr >> 16)) >> sh;
+                    orv |= (u32)sv;
+                    const double x = (double)sv;
+                    hist[u] = x;
+#pragma unroll
+                    for (int l = 0; l < NL; l++) {
+                        const int partner = (u - (LB + l) + 2 * H) % H;
+                        a_[l] = __fma_rn(x, hist[partner], a_[l]);
                     }
-                    orv |= (u32)s;
-                    x = __dmul_rn((double)s, windows[woff + i]);
                 }
-                hist[u] = x;
+            } else if (full) {
+                const u32* rw = (const u32*)row + tbase;
+                const double* wp = windows + woff + ig;
 #pragma unroll
-                for (int l = 0; l < NL; l++) {
-                    const int partner = (u - (LB + l) + 2 * H) % H;
-                    a_[l] = __dadd_rn(a_[l], __dmul_rn(x, hist[partner]));
+                for (int u = 0; u < H; u++) {
+                    const u32 pr = rw[u];
+                    const int sv = (cl * (int)(short)(pr & 0xFFFF) + cr * ((int)pr >> 16)) >> sh;
+                    orv |= (u32)sv;
+                    const double x = __dmul_rn((double)sv, wp[u]);
+                    hist[u] = x;
+#pragma unroll
+                    for (int l = 0; l < NL; l++) {
+                        const int partner = (u - (LB + l) + 2 * H) % H;
+                        a_[l] = __dadd_rn(a_[l], __dmul_rn(x, hist[partner]));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < H; u++) {
+                    const u32 t = tbase + u;
+                    const u32 i = i0 + t;
+                    double x = 0.0;
+                    if (valid && i < n) {
+                        int sv;
+                        if (!P.stereo) {
+                            sv = ld_pcm(row, t * C + cand, B);
+                        } else {
+                            const int L = ld_pcm(row, t * 2, B), R = ld_pcm(row, t * 2 + 1, B);
+                            sv = cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
+                        }
+                        orv |= (u32)sv;
+                        x = __dmul_rn((double)sv, windows[woff + i]);
+                    }
+                    hist[u] = x;
+#pragma unroll
+                    for (int l = 0; l < NL; l++) {
+                        const int partner = (u - (LB + l) + 2 * H) % H;
+                        a_[l] = __dadd_rn(a_[l], __dmul_rn(x, hist[partner]));
+                    }
                 }
             }
         }
