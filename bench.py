@@ -153,11 +153,11 @@ def cpu_baseline(seconds_per_proc=120.0, rounds=1):
             "single_process_value": samples / single / 1e6}
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit):
     if rank != 0:
         return
     if not (os.path.exists(REF_FLACENC) and os.path.exists(ORACLE_CLI)):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/flacenc not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/flacenc not built"})
         return
     cores = os.cpu_count() or 1
     seconds = 60.0
@@ -173,14 +173,14 @@ def run_reference_arm(args, rank, world):
     value = samples / t / 1e6
     sample = ("each step: %d processes (one per host core) x %d s of the workload through the compiled "
               "reference encoder" % (cores, seconds))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32/i64/f64",
         "data": "synthetic", "config": {"workload": workload_name(HOUR_FRAMES), "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 # ----------------------------------------------------------------------------------------------
@@ -199,8 +199,17 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version
+    # there) are sent to stderr, the result line goes to the saved descriptor
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return
 
     import numpy as np
@@ -362,7 +371,7 @@ def main():
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         }
-        print(json.dumps(line))
+        emit(line)
     L.b200flac_device_free(dev, d_pcm)
     L.b200flac_device_free(dev, d_out)
     enc.close()
