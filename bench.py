@@ -193,6 +193,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=3600.0, help="audio per GPU per step (default: the 1 h config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-slots", type=int, default=4, help="batches in flight in the end-to-end arm")
+    ap.add_argument("--e2e-batch-blocks", type=int, default=2048, help="FLAC frames per end-to-end batch")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -288,8 +290,8 @@ def main():
     # ---- end-to-end arm: pinned host PCM -> H2D -> kernels -> D2H, through submit/collect ---------
     e2e = None
     if not args.no_e2e:
-        batch_frames = BLOCK * 2048
-        nslots = 3
+        batch_frames = BLOCK * args.e2e_batch_blocks
+        nslots = args.e2e_slots
         enc2 = b200flac.Encoder(params, device=dev, max_pcm_frames_per_batch=batch_frames, n_slots=nslots)
         h_pcm = L.b200flac_host_alloc(pcm_bytes)
         if not h_pcm:

@@ -55,6 +55,12 @@ struct Slot {
     double* d_win = nullptr;
     size_t win_cap = 0;            // doubles
     bf_lpc_head* d_heads = nullptr;
+    double* d_autoc = nullptr;     // [units][maxl + 1] lag sums (k_lpc_autoc -> k_lpc_finish)
+    uint8_t* d_lpc_wasted = nullptr;
+    u32* d_ticket = nullptr;       // task counter of the persistent autocorrelation kernel
+    bf_lpc_task* h_tasks = nullptr; // pinned: runs of equal-length frames (one warp task each)
+    bf_lpc_task* d_tasks = nullptr;
+    u32 n_tasks = 0;
     short* d_coefs = nullptr;
     b200flac_plan* d_plans = nullptr;
     uint8_t* d_rice = nullptr;
@@ -90,6 +96,8 @@ struct b200flac_encoder {
     u32 stage_words;      // shared-memory image of one subframe, in words (k_pack_v2)
     std::map<u32, std::vector<double>>* windows;
     u64 launches;
+    int lpc_occ[2];       // resident one-warp CTAs per SM of k_lpc_autoc (G = 1, 2)
+    int n_sms;
 };
 
 // ---- derived options ------------------------------------------------------
@@ -239,6 +247,8 @@ static void free_slot(Slot& s)
     cudaFree(s.d_plans); cudaFree(s.d_rice); cudaFree(s.d_choice); cudaFree(s.d_frame_bytes);
     cudaFree(s.d_frame_off); cudaFree(s.d_total); cudaFree(s.d_out); cudaFree(s.d_gsamples);
     cudaFree(s.d_gheap); cudaFree(s.d_gkarr);
+    cudaFree(s.d_autoc); cudaFree(s.d_lpc_wasted); cudaFree(s.d_ticket); cudaFree(s.d_tasks);
+    if (s.h_tasks) cudaFreeHost(s.h_tasks);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -252,6 +262,36 @@ extern "C" void b200flac_encoder_destroy(b200flac_encoder* enc)
     }
     delete enc->windows;
     delete enc;
+}
+
+static u32 lpc_maxl(u32 L) { return L <= 8 ? 8 : L <= 12 ? 12 : L <= 16 ? 16 : 32; }
+
+template <int MAXL>
+static cudaError_t lpc_prepare_one(b200flac_encoder* enc, size_t smem)
+{
+    // the opt-in limit is raised to the maximum so that a small batch can pad its request and
+    // spread its few CTAs over all SMs (see launch_batch)
+    const int lim = 200 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(k_lpc_autoc<MAXL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->lpc_occ[1], k_lpc_autoc<MAXL, 2>, 32, smem);
+    if (e != cudaSuccess) return e;
+    if constexpr (MAXL <= 16) {
+        e = cudaFuncSetAttribute(k_lpc_autoc<MAXL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->lpc_occ[0], k_lpc_autoc<MAXL, 1>, 32, smem);
+    } else enc->lpc_occ[0] = 0;
+    return e;
+}
+
+static cudaError_t lpc_prepare(b200flac_encoder* enc)
+{
+    const bf_dev_params& P = enc->P;
+    cudaDeviceGetAttribute(&enc->n_sms, cudaDevAttrMultiProcessorCount, enc->device);
+    const u32 maxl = lpc_maxl(P.max_lpc_order);
+    const size_t smem = lpc_geometry(P.K, P.channels * P.bytes_ps, maxl + 1).smem_bytes;
+    return maxl == 8 ? lpc_prepare_one<8>(enc, smem) : maxl == 12 ? lpc_prepare_one<12>(enc, smem)
+         : maxl == 16 ? lpc_prepare_one<16>(enc, smem) : lpc_prepare_one<32>(enc, smem);
 }
 
 template <int S>
@@ -359,6 +399,7 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
           : enc->S == 16 ? set_smem_attrs<16>(enc->smem_analyze, enc->smem_pack)
                          : set_smem_attrs<8>(enc->smem_analyze, enc->smem_pack);
     }
+    if (e == cudaSuccess && P.try_lpc) e = lpc_prepare(enc);
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         b200flac_encoder_destroy(enc);
@@ -393,6 +434,13 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         ALLOC(s.d_win, s.win_cap * sizeof(double));
         ALLOC(s.d_heads, U * sizeof(bf_lpc_head));
         ALLOC(s.d_coefs, U * P.model_stride * sizeof(short));
+        if (P.try_lpc) {
+            ALLOC(s.d_autoc, U * (size_t)(lpc_maxl(P.max_lpc_order) + 1) * sizeof(double));
+            ALLOC(s.d_lpc_wasted, U);
+            ALLOC(s.d_ticket, 64);
+            ALLOCH(s.h_tasks, maxf * sizeof(bf_lpc_task));
+            ALLOC(s.d_tasks, maxf * sizeof(bf_lpc_task));
+        }
         ALLOC(s.d_plans, U * sizeof(b200flac_plan));
         ALLOC(s.d_rice, U * P.rice_stride);
         ALLOC(s.d_choice, maxf * sizeof(bf_frame_choice));
@@ -508,6 +556,20 @@ static long build_batch(b200flac_encoder* enc, Slot& s, const b200flac_segment* 
         }
     }
     if (need > enc->max_pcm_frames) { set_err("batch has more PCM frames than the encoder was created for"); return -1; }
+    if (want_windows) {
+        // tasks of the autocorrelation kernel: runs of up to 32/K consecutive frames of one length
+        const u32 per = 32 / enc->P.K;
+        u32 nt = 0;
+        for (u64 f = 0; f < nf;) {
+            u32 c = 1;
+            while (c < per && f + c < nf && s.h_fd[f + c].nsamp == s.h_fd[f].nsamp) c++;
+            s.h_tasks[nt].first_frame = (u32)f;
+            s.h_tasks[nt].n_frames = c;
+            nt++;
+            f += c;
+        }
+        s.n_tasks = nt;
+    }
     *pcm_frames_needed = need;
     s.n_frames = (u32)nf;
     // windows upload size is remembered through woff/wused: stash in h_total[1]
@@ -573,14 +635,38 @@ static int launch_batch(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, ui
     cudaStream_t st = s.stream;
     cudaEventRecord(s.ev[0], st);
     if (P.try_lpc) {
-        const u32 blocks = (U + LPC_WARPS * 32 - 1) / (LPC_WARPS * 32);
-        const u32 L = P.max_lpc_order;
-        const size_t lsm = LPC_WARPS * sizeof(LpcWarpStage);
-        if (L <= 8) k_lpc_model<8><<<blocks, LPC_WARPS * 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
-        else if (L <= 12) k_lpc_model<12><<<blocks, LPC_WARPS * 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
-        else if (L <= 16) k_lpc_model<16><<<blocks, LPC_WARPS * 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
-        else k_lpc_model<32><<<blocks, LPC_WARPS * 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_heads, s.d_coefs);
-        enc->launches += 1;
+        // persistent one-warp CTAs drawing (32 units, lag group) tasks from a ticket counter; the lag
+        // split halves a thread's sequential work, which is what a small batch's duration is made of
+        const u32 maxl = lpc_maxl(P.max_lpc_order);
+        const u32 groups = s.n_tasks;
+        bool split = maxl == 32 || groups < (u32)enc->n_sms * 12u;
+        if (getenv("B200FLAC_LPC_G") && maxl != 32) split = atoi(getenv("B200FLAC_LPC_G")) == 2; // tuning knob
+        const u32 G = split ? 2 : 1;
+        const u32 n_tasks = groups * G;
+        const int occ = enc->lpc_occ[G - 1] > 0 ? enc->lpc_occ[G - 1] : 1;
+        size_t lsm = lpc_geometry(P.K, P.channels * P.bytes_ps, maxl + 1).smem_bytes;
+        u32 grid = (u32)enc->n_sms * (u32)occ;
+        if (n_tasks < grid) {
+            // few tasks: the block scheduler fills an SM before it moves to the next, so pad the
+            // shared-memory request until only ceil(tasks / SMs) CTAs fit on one
+            grid = n_tasks;
+            const u32 per_sm = (n_tasks + enc->n_sms - 1) / enc->n_sms;
+            const size_t pad = (size_t)(220 * 1024) / per_sm - 1024;
+            if (pad > lsm) lsm = pad < (size_t)(200 * 1024) ? pad : (size_t)(200 * 1024);
+        }
+        cudaMemsetAsync(s.d_ticket, 0, sizeof(u32), st);
+#define LPC_LAUNCH(MAXL_, G_) k_lpc_autoc<MAXL_, G_><<<grid, 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_tasks, n_tasks, s.d_ticket, s.d_autoc, s.d_lpc_wasted)
+        if (maxl == 8) { if (split) LPC_LAUNCH(8, 2); else LPC_LAUNCH(8, 1); }
+        else if (maxl == 12) { if (split) LPC_LAUNCH(12, 2); else LPC_LAUNCH(12, 1); }
+        else if (maxl == 16) { if (split) LPC_LAUNCH(16, 2); else LPC_LAUNCH(16, 1); }
+        else LPC_LAUNCH(32, 2);
+#undef LPC_LAUNCH
+        const u32 fb = (U + 127) / 128;
+        if (maxl == 8) k_lpc_finish<8><<<fb, 128, 0, st>>>(s.d_fd, nf, P, s.d_autoc, s.d_lpc_wasted, s.d_heads, s.d_coefs);
+        else if (maxl == 12) k_lpc_finish<12><<<fb, 128, 0, st>>>(s.d_fd, nf, P, s.d_autoc, s.d_lpc_wasted, s.d_heads, s.d_coefs);
+        else if (maxl == 16) k_lpc_finish<16><<<fb, 128, 0, st>>>(s.d_fd, nf, P, s.d_autoc, s.d_lpc_wasted, s.d_heads, s.d_coefs);
+        else k_lpc_finish<32><<<fb, 128, 0, st>>>(s.d_fd, nf, P, s.d_autoc, s.d_lpc_wasted, s.d_heads, s.d_coefs);
+        enc->launches += 2;
     }
     cudaEventRecord(s.ev[1], st);
     if (enc->fast) {
@@ -616,6 +702,7 @@ extern "C" int b200flac_encoder_submit(b200flac_encoder* enc, int slot, const ui
     } else if (ensure_host_path(enc, s, false)) return 1;
     CU_CHECK(cudaMemcpyAsync(s.d_pcm, src, pcm_bytes, cudaMemcpyHostToDevice, st), 1);
     CU_CHECK(cudaMemcpyAsync(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), cudaMemcpyHostToDevice, st), 1);
+    if (enc->P.try_lpc) CU_CHECK(cudaMemcpyAsync(s.d_tasks, s.h_tasks, (size_t)s.n_tasks * sizeof(bf_lpc_task), cudaMemcpyHostToDevice, st), 1);
     const size_t wused = (size_t)s.h_total[1];
     if (wused) CU_CHECK(cudaMemcpyAsync(s.d_win, s.h_win, wused * sizeof(double), cudaMemcpyHostToDevice, st), 1);
     if (launch_batch(enc, s, s.d_pcm, s.d_out, enc->out_cap)) return 1;
@@ -676,6 +763,7 @@ extern "C" int b200flac_encoder_encode_device(b200flac_encoder* enc, int slot, c
     if (nf == 0) { if (out_bytes) *out_bytes = 0; if (n_frames) *n_frames = 0; return 0; }
     cudaStream_t st = s.stream;
     CU_CHECK(cudaMemcpyAsync(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), cudaMemcpyHostToDevice, st), 1);
+    if (enc->P.try_lpc) CU_CHECK(cudaMemcpyAsync(s.d_tasks, s.h_tasks, (size_t)s.n_tasks * sizeof(bf_lpc_task), cudaMemcpyHostToDevice, st), 1);
     const size_t wused = (size_t)s.h_total[1];
     if (wused) CU_CHECK(cudaMemcpyAsync(s.d_win, s.h_win, wused * sizeof(double), cudaMemcpyHostToDevice, st), 1);
     const u64 cap = out_capacity & ~15ull;

@@ -57,6 +57,12 @@ typedef struct bf_frame_desc {
     uint32_t pad;
 } bf_frame_desc;
 
+/* work item of the autocorrelation kernel: a run of consecutive frames of one length */
+typedef struct bf_lpc_task {
+    uint32_t first_frame;
+    uint32_t n_frames;       /* <= 32 / K */
+} bf_lpc_task;
+
 /* LPC model of one unit, written by the model kernel:
  *   shift[o-1], coefficient set of order o at coef[o*(o-1)/2 .. +o)
  * Non-exhaustive search fills only the estimated best order. */

@@ -1,30 +1,34 @@
 // k_lpc_model.cuh -- the floating-point stage of the encoder, one THREAD per
-// unit (frame, candidate):
+// unit (frame, candidate) and lag group:
 //
-//   window apply          flacenc_window_signal           flac.c:1129-1167
-//   autocorrelation       flacenc_autocorrelate           flac.c:1169-1188
-//   Levinson-Durbin       flacenc_compute_lp_coefficients flac.c:1190-1231
-//   order estimate        flacenc_estimate_best_lpc_order flac.c:1233-1268
-//   quantisation          flacenc_quantize_coefficients   flac.c:1270-1324
+//   k_lpc_autoc   window apply          flacenc_window_signal           flac.c:1129-1167
+//                 autocorrelation       flacenc_autocorrelate           flac.c:1169-1188
+//   k_lpc_finish  Levinson-Durbin       flacenc_compute_lp_coefficients flac.c:1190-1231
+//                 order estimate        flacenc_estimate_best_lpc_order flac.c:1233-1268
+//                 quantisation          flacenc_quantize_coefficients   flac.c:1270-1324
 //
-// Why one thread per unit: the reference sums each autocorrelation lag
+// Why one thread per chain: the reference sums each autocorrelation lag
 // sequentially in double precision, one rounding per multiply and one per add.
 // Any tree or warp-shuffle reduction changes the rounding and, now and then,
 // a quantised coefficient -- and with it the file bytes.  A thread that walks
 // its block in the reference's order with IEEE mul/add (no FMA contraction)
 // reproduces every bit; the parallelism comes from the ~10^5 independent units
-// of a batch instead.  The (max_lpc_order+1) lag sums are independent
-// dependency chains inside the thread, which hides the FP64 latency.
+// of a batch, and, for small batches, from splitting a unit's independent lag
+// sums over G threads.  The lag sums a thread owns are independent dependency
+// chains, which hides the FP64 latency.
 //
-// A warp owns 32 consecutive units = all candidates of ~32/K consecutive
-// frames.  PCM is staged through shared memory in tiles of TS PCM frames per
-// frame row with coalesced 32-bit loads, then every lane walks its own row.
+// k_lpc_autoc is a persistent kernel of one-warp CTAs.  A TASK is (a run of up to
+// 32/K consecutive frames OF THE SAME LENGTH -- the host cuts the runs, bf_lpc_task --
+// with all their candidates, lag group); warps draw tasks from a global ticket counter, so the last
+// tasks of a batch land on whichever SMs are free (a static grid's last wave
+// was packed onto a few SMs by the block scheduler and ran at a third of the
+// speed).  A task's PCM rows (the frames its units belong to) are staged through
+// shared memory in tiles with cp.async, double buffered, together with the
+// matching tile of the Tukey window; every lane then walks its own row.
 #pragma once
 #include "flac_common.cuh"
 
-#define LPC_WARPS 4
-#define LPC_STAGE_WORDS 1344         // words per staging buffer and warp (two buffers per warp)
-#define LPC_MAX_ROWS 34              // frames a warp's 32 units can span (K = 1: 32)
+#define LPC_MAX_ROWS 32              // frames of a task (K = 1: 32)
 
 // (int)round(x) the way x86-64 cvttsd2si does it: NaN / out of range -> INT_MIN
 // (CUDA's own conversion would give 0 / saturate)
@@ -76,36 +80,95 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// per-warp staging area (dynamic shared memory): two tile buffers + the rows' descriptors
-struct LpcWarpStage {
-    u32 buf[2][LPC_STAGE_WORDS];
+// staging area of a warp (dynamic shared memory):
+//   hdr | window tiles [2][T] (double) | PCM tiles [2][rows][row_words] (u32)
+struct LpcStageHdr {
     u64 row_byte0[LPC_MAX_ROWS];   // byte offset of the row's first PCM frame
     u32 row_n[LPC_MAX_ROWS];       // PCM frames in the row (0: no such frame)
 };
 
-// One pass over the warp's units accumulating lags LB .. LB+NL-1.
+// tile geometry, shared by host and device: T = PCM frames per staged tile (>= the longest ring),
+// rows = frames a task can span, row_words = u32 words per staged row (odd: rows start in
+// different banks)
+struct LpcGeom { u32 T, rows, row_words, smem_bytes; };
+__host__ __device__ inline LpcGeom lpc_geometry(u32 K, u32 rowbytes, u32 ring)
+{
+    LpcGeom g;
+    g.rows = 32 / K;
+    u32 T = 9216 / (g.rows * rowbytes);           // ~9 KB per PCM tile
+    if (T > 160) T = 160;
+    if (T < ring) T = ring;
+    g.T = T;
+    g.row_words = (((T * rowbytes + 6) >> 2) + 1) | 1u;
+    g.smem_bytes = (u32)sizeof(LpcStageHdr) + 2 * T * 8 + 2 * g.rows * g.row_words * 4 + 16;
+    return g;
+}
+
+// int -> double without the (quarter-rate) I2F.F64: 2^52 + 2^31 + v is exact for any 32-bit v,
+// and so is the subtraction that follows
+__device__ __forceinline__ double int2double_exact(int v)
+{
+    return __dsub_rn(__hiloint2double(0x43300000, (int)((u32)v ^ 0x80000000u)), 4503601774854144.0);
+}
+
+// candidate signal of a 16-bit stereo pair (flacenc_average_difference, flac.c:1507-1529) as ONE
+// dot product: (cl*L + cr*R) >> sh with (cl, cr, sh) = (1,0,0) left, (0,1,0) right, (1,1,1) average,
+// (1,-1,0) difference; coef packs cl and cr as two signed bytes (IDP.2A.LO.S16.S8).  One code path
+// for the four candidates: lanes of a warp hold different candidates.
+__device__ __forceinline__ int stereo16_candidate(u32 pr, int coef, int sh)
+{
+    return __dp2a_lo((int)pr, coef, 0) >> sh;
+}
+__device__ __forceinline__ int stereo16_coef(u32 cand) { return cand == 0 ? 0x0001 : cand == 1 ? 0x0100 : cand == 2 ? 0x0101 : 0xFF01; }
+
+// One task: lags LB .. LB+NL-1 of the 32 units u0 .. u0+31 (one unit per lane).
 // hist is a ring of H = LB+NL windowed samples with compile-time indexing; tiles of TS = H*M
 // PCM frames per row are staged with cp.async, double buffered, so the copy of tile t+1 is in
 // flight while tile t is consumed.
-template <int LB, int NL>
-__device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, const double* __restrict__ windows,
-                                           const bf_dev_params& P, u32 nrows, u32 nmax,
-                                           bool valid, u32 myrow, u32 cand, u32 n, u32 woff,
-                                           LpcWarpStage* st, double* acc, u32* or_out)
+// FAST: 16-bit stereo (fast paths compiled in).
+template <int LB, int NL, bool FAST>
+__device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
+                                           const double* __restrict__ windows, const bf_dev_params& P,
+                                           const LpcGeom& g, u32 f0, u32 nrows, unsigned char* smem,
+                                           double* __restrict__ autoc_out, u32 autoc_stride, uint8_t* __restrict__ wasted_out)
 {
     constexpr int H = LB + NL;
     const int lane = threadIdx.x & 31;
-    const u32 C = P.channels, B = P.bytes_ps;
+    LpcStageHdr* hdr = (LpcStageHdr*)smem;
+    double* wbuf = (double*)(smem + sizeof(LpcStageHdr));
+    u32* tbuf = (u32*)(wbuf + 2 * g.T);
+    const u32 K = P.K, C = P.channels, B = P.bytes_ps;
     const u32 rowbytes = C * B;
-    // tile length: as many ring rotations as fit the staging buffer (at most 8)
-    u32 M = ((LPC_STAGE_WORDS / nrows - 3) * 4) / (H * rowbytes);
-    M = M < 1 ? 1 : (M > 8 ? 8 : M);
+    const u32 row_words = g.row_words;
+    const u32 M = g.T / H;
     const u32 TS = H * M;
-    const u32 row_words = ((TS * rowbytes + 4 + 3) >> 2) + 1;
+
+    // lane -> (row, candidate); every frame of the task has the same length n, hence one window
+    const bool valid = (u32)lane < nrows * K;
+    const u32 myrow = valid ? (u32)lane / K : 0;
+    const u32 cand = valid ? (u32)lane % K : 0;
+    const u32 frame = f0 + myrow;
+    const u32 unit = frame * K + cand;
+    const bf_frame_desc d0 = fd[f0];
+    const u32 n = d0.nsamp, nmax = n;
+    const u32 woff0 = d0.window_off;
+
+    __syncwarp();                           // the previous task is done with the staging area
+    for (u32 r = lane; r < nrows; r += 32) {
+        const bf_frame_desc rd = fd[f0 + r];
+        hdr->row_byte0[r] = rd.pcm_off * (u64)rowbytes;
+        hdr->row_n[r] = rd.nsamp;
+    }
+    __syncwarp();
 
     double hist[H];
     double a_[NL];          // private accumulators: stay in registers
@@ -114,57 +177,60 @@ __device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, cons
 #pragma unroll
     for (int i = 0; i < NL; i++) a_[i] = 0.0;
     u32 orv = 0;
+    const int coef = stereo16_coef(cand), sh = cand == 2 ? 1 : 0;
 
     auto issue_tile = [&](u32 i0, u32 b) {
+        u32* base = tbuf + (size_t)b * g.rows * row_words;
         for (u32 r = 0; r < nrows; r++) {
-            const u32 rn = st->row_n[r];
+            const u32 rn = hdr->row_n[r];
             if (i0 < rn) {
                 const u32 take = min(TS, rn - i0);
-                const u64 a = st->row_byte0[r] + (u64)i0 * rowbytes;
+                const u64 a = hdr->row_byte0[r] + (u64)i0 * rowbytes;
                 const u32 mis = (u32)(a & 3);
                 const u32 nwords = (mis + take * rowbytes + 3) >> 2;
                 const u32* src = (const u32*)(pcm + (a - mis));
-                u32* dst = st->buf[b] + r * row_words;
+                u32* dst = base + r * row_words;
                 for (u32 w = lane; w < nwords; w += 32) cp_async4(dst + w, src + w);
             }
         }
+        const u32 take = min(TS, nmax - i0);
+        for (u32 w = lane; w < take; w += 32) cp_async8(wbuf + b * g.T + w, windows + woff0 + i0 + w);
         cp_async_commit();
     };
 
-    const u64 my_byte0 = st->row_byte0[myrow];
-    // per-lane constants of the fast paths
-    const bool st16 = P.stereo && B == 2;
-    const int cl = cand == 1 ? 0 : 1, cr = cand == 0 ? 0 : (cand == 3 ? -1 : 1), sh = cand == 2 ? 1 : 0;
-    const u32 nmin = __reduce_min_sync(0xFFFFFFFFu, valid ? n : nmax);
+    const u64 my_byte0 = hdr->row_byte0[myrow];
     // flat part of the Tukey window of length n (flac.c:1140-1152): window1 < i <= window2
-    const u32 flat_lo = valid ? ((u32)(0.5 * (n - 1)) / 2 + 1) : 0u;
-    const u32 flat_hi = valid ? (u32)((n - 1) * (1.0 - (0.5 / 2.0))) : 0xFFFFFFFFu;
+    const u32 flat_lo = (u32)(0.5 * (n - 1)) / 2 + 1;
+    const u32 flat_hi = (u32)((n - 1) * (1.0 - (0.5 / 2.0)));
+    const u32 flat_first = flat_lo + (H - 1);   // first rotation start whose partners are flat too
+    const u32 flat_last = flat_hi;              // need ig + H - 1 <= flat_last
     issue_tile(0, 0);
     u32 b = 0;
     for (u32 i0 = 0; i0 < nmax; i0 += TS, b ^= 1) {
         if (i0 + TS < nmax) { issue_tile(i0 + TS, b ^ 1); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncwarp();
-        const uint8_t* row = (const uint8_t*)(st->buf[b] + myrow * row_words) + (u32)((my_byte0 + (u64)i0 * rowbytes) & 3);
+        const uint8_t* row = (const uint8_t*)(tbuf + ((size_t)b * g.rows + myrow) * row_words) +
+                             (u32)((my_byte0 + (u64)i0 * rowbytes) & 3);
+        const double* wt = wbuf + b * g.T;
 #pragma unroll 1
         for (u32 m = 0; m < M; m++) {
             const u32 tbase = m * H;
             const u32 ig = i0 + tbase;                 // first sample of this ring rotation
             if (ig >= nmax) break;
-            // whole rotation in range for every lane, stereo 16-bit rows (always 4-byte aligned)?
-            const bool full = st16 && (ig + H <= nmin);
+            // whole rotation in range for every lane (16-bit stereo rows are always 4-byte aligned)?
+            const bool full = FAST && (ig + H <= n);
             // ... and inside the flat part of every lane's Tukey window, partners included: samples are
             // exact integers there and their products are exact in double, so fma(x, y, acc) rounds
             // exactly like the reference's multiply-then-add
-            const bool flat = full && __all_sync(0xFFFFFFFFu, ig >= flat_lo + (H - 1) && ig + H - 1 <= flat_hi);
-            if (flat) {
+            const bool flat = full && ig >= flat_first && ig + H - 1 <= flat_last;
+            if (FAST && flat) {
                 const u32* rw = (const u32*)row + tbase;
 #pragma unroll
                 for (int u = 0; u < H; u++) {
-                    const u32 pr = rw[u];
-                    const int sv = (cl * (int)(short)(pr & 0xFFFF) + cr * ((int)pr >> 16)) >> sh;
-                    orv |= (u32)sv;
-                    const double x = (double)sv;
+                    const int sv = stereo16_candidate(rw[u], coef, sh);
+                    if (LB == 0) orv |= (u32)sv;
+                    const double x = int2double_exact(sv);
                     hist[u] = x;
 #pragma unroll
                     for (int l = 0; l < NL; l++) {
@@ -172,15 +238,17 @@ __device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, cons
                         a_[l] = __fma_rn(x, hist[partner], a_[l]);
                     }
                 }
-            } else if (full) {
+            } else if (FAST) {
+                // tapered part of the window, and the block's last, partial rotation: out-of-range
+                // samples count as zero, which leaves the sums untouched
                 const u32* rw = (const u32*)row + tbase;
-                const double* wp = windows + woff + ig;
+                const double* wp = wt + tbase;
 #pragma unroll
                 for (int u = 0; u < H; u++) {
-                    const u32 pr = rw[u];
-                    const int sv = (cl * (int)(short)(pr & 0xFFFF) + cr * ((int)pr >> 16)) >> sh;
-                    orv |= (u32)sv;
-                    const double x = __dmul_rn((double)sv, wp[u]);
+                    const bool in = full || (ig + u < n);
+                    const int sv = in ? stereo16_candidate(rw[u], coef, sh) : 0;
+                    if (LB == 0) orv |= (u32)sv;
+                    const double x = in ? __dmul_rn(int2double_exact(sv), wp[u]) : 0.0;
                     hist[u] = x;
 #pragma unroll
                     for (int l = 0; l < NL; l++) {
@@ -203,7 +271,7 @@ __device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, cons
                             sv = cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
                         }
                         orv |= (u32)sv;
-                        x = __dmul_rn((double)sv, windows[woff + i]);
+                        x = __dmul_rn(int2double_exact(sv), wt[t]);
                     }
                     hist[u] = x;
 #pragma unroll
@@ -216,57 +284,63 @@ __device__ __forceinline__ void autoc_pass(const uint8_t* __restrict__ pcm, cons
         }
         __syncwarp(); // everyone is done with buf[b] before it is refilled two tiles later
     }
+    if (valid && n > 0) {
+        double* o = autoc_out + (size_t)unit * autoc_stride + LB;
 #pragma unroll
-    for (int i = 0; i < NL; i++) acc[i] = a_[i];
-    *or_out = orv;
+        for (int i = 0; i < NL; i++) o[i] = a_[i];
+        if (LB == 0) wasted_out[unit] = (uint8_t)(orv ? (u32)(__ffs((int)orv) - 1) : 0u);
+    }
 }
 
-// MAXL: compile-time bound on max_lpc_order handled by this instantiation (8, 12, 16 or 32)
-template <int MAXL>
-__global__ void __launch_bounds__(LPC_WARPS * 32)
-k_lpc_model(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, u32 n_frames,
-            const double* __restrict__ windows, bf_dev_params P,
-            bf_lpc_head* __restrict__ heads, short* __restrict__ coefs)
+// MAXL: compile-time bound on max_lpc_order handled by this instantiation (8, 12, 16 or 32).
+// G: lag groups a unit is split into (1 or 2; MAXL = 32 always uses 2 -- 33 sums and their ring do
+// not fit the register file).  Large batches use G = 1 (the unpack/window work is not duplicated),
+// small ones G = 2 (half the sequential work per thread, twice the warps).
+template <int MAXL, int G>
+__global__ void __launch_bounds__(32)
+k_lpc_autoc(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, u32 n_frames,
+            const double* __restrict__ windows, bf_dev_params P, const bf_lpc_task* __restrict__ tasks,
+            u32 n_tasks, u32* __restrict__ ticket,
+            double* __restrict__ autoc_out, uint8_t* __restrict__ wasted_out)
 {
     extern __shared__ __align__(16) unsigned char lpc_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    LpcWarpStage* st = (LpcWarpStage*)lpc_smem + warp;
+    constexpr int NL0 = (G == 1) ? MAXL + 1 : (MAXL + 2) / 2, NL1 = MAXL + 1 - NL0;
+    const int lane = threadIdx.x & 31;
+    const LpcGeom g = lpc_geometry(P.K, P.channels * P.bytes_ps, MAXL + 1);
+    const bool st16 = P.stereo && P.bytes_ps == 2;
+    for (;;) {
+        u32 t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= n_tasks) break;
+        const bf_lpc_task tk = tasks[t / G];
+        if (G == 1 || (t % G) == 0) {
+            if (st16) autoc_task<0, NL0, true>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out);
+            else autoc_task<0, NL0, false>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out);
+        } else if constexpr (G == 2) {
+            if (st16) autoc_task<NL0, NL1, true>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out);
+            else autoc_task<NL0, NL1, false>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out);
+        }
+    }
+}
 
+// Levinson-Durbin, order estimate and quantisation: one thread per unit.
+template <int MAXL>
+__global__ void __launch_bounds__(128)
+k_lpc_finish(const bf_frame_desc* __restrict__ fd, u32 n_frames, bf_dev_params P,
+             const double* __restrict__ autoc_in, const uint8_t* __restrict__ wasted_in,
+             bf_lpc_head* __restrict__ heads, short* __restrict__ coefs)
+{
+    const u32 unit = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 K = P.K;
-    const u32 U = n_frames * K;
-    const u32 u0 = (blockIdx.x * LPC_WARPS + warp) * 32;
-    if (u0 >= U) return;
-    const u32 unit = u0 + lane;
-    const bool valid = unit < U;
-    const u32 f0 = u0 / K;
-    const u32 ulast = min(u0 + 31, U - 1);
-    const u32 nrows = ulast / K - f0 + 1;
-    const u32 frame = valid ? unit / K : f0;
-    const u32 cand = valid ? unit % K : 0;
-    const bf_frame_desc d = fd[frame];
-    const u32 n = valid ? d.nsamp : 0;
-    const u32 nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+    if (unit >= n_frames * K) return;
+    const u32 frame = unit / K, cand = unit % K;
+    const u32 n = fd[frame].nsamp;
     const u32 L = P.max_lpc_order;
-
-    // row descriptors, once
-    for (u32 r = lane; r < nrows; r += 32) {
-        const bf_frame_desc rd = fd[f0 + r];
-        st->row_byte0[r] = rd.pcm_off * (u64)(P.channels * P.bytes_ps);
-        st->row_n[r] = rd.nsamp;
-    }
-    __syncwarp();
-
     double autoc[MAXL + 1];
-    u32 orv = 0;
-    if constexpr (MAXL <= 16) {
-        autoc_pass<0, MAXL + 1>(pcm, windows, P, nrows, nmax, valid, frame - f0, cand, n, d.window_off, st, autoc, &orv);
-    } else {
-        u32 dummy;
-        autoc_pass<0, 17>(pcm, windows, P, nrows, nmax, valid, frame - f0, cand, n, d.window_off, st, autoc, &orv);
-        __syncwarp();
-        autoc_pass<17, 16>(pcm, windows, P, nrows, nmax, valid, frame - f0, cand, n, d.window_off, st, autoc + 17, &dummy);
-    }
-    if (!valid) return;
+#pragma unroll
+    for (int i = 0; i <= MAXL; i++) autoc[i] = autoc_in[(size_t)unit * (MAXL + 1) + i];
+    const u32 wasted = wasted_in[unit];
 
     bf_lpc_head head;
     head.best_order = 0; head.precision = (uint8_t)P.precision; head.dummy = 0; head.pad = 0;
@@ -284,7 +358,6 @@ k_lpc_model(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ f
     // wasted bits: the reference windows the samples AFTER shifting them right by
     // `wasted` (flac.c:700-724).  s>>w is exact, so every product and partial sum
     // is the unshifted one scaled by 2^-2w, also exactly: scale once at the end.
-    const u32 wasted = orv ? (u32)(__ffs((int)orv) - 1) : 0u;
     if (wasted) {
         const double sc = ldexp(1.0, -2 * (int)wasted);
         for (u32 i = 0; i <= L; i++) autoc[i] = autoc[i] * sc;
