@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <vector>
 
@@ -19,6 +20,7 @@
 #include "k_analyze.cuh"
 #include "k_pack.cuh"
 #include "k_analyze_v2.cuh"
+#include "k_analyze_v3.cuh"
 #include "k_pack_v2.cuh"
 #include "k_synth.cuh"
 
@@ -61,6 +63,9 @@ struct Slot {
     bf_lpc_task* h_tasks = nullptr; // pinned: runs of equal-length frames (one warp task each)
     bf_lpc_task* d_tasks = nullptr;
     u32 n_tasks = 0;
+    u32* h_odd = nullptr;          // pinned: frames whose length is not block_size (k_analyze_v2 takes them)
+    u32* d_odd = nullptr;
+    u32 n_odd = 0;
     short* d_coefs = nullptr;
     b200flac_plan* d_plans = nullptr;
     uint8_t* d_rice = nullptr;
@@ -94,6 +99,9 @@ struct b200flac_encoder {
     size_t smem_analyze, smem_pack;
     bool fast;            // the shared-memory resident kernels (k_analyze_v2 / k_pack_v2) apply
     u32 stage_words;      // shared-memory image of one subframe, in words (k_pack_v2)
+    bool v3;              // k_analyze_v3 applies to the full-length blocks
+    u32 v3_S, v3_F, v3_NT;
+    size_t v3_smem;
     std::map<u32, std::vector<double>>* windows;
     u64 launches;
     int lpc_occ[2];       // resident one-warp CTAs per SM of k_lpc_autoc (G = 1, 2)
@@ -249,6 +257,8 @@ static void free_slot(Slot& s)
     cudaFree(s.d_gheap); cudaFree(s.d_gkarr);
     cudaFree(s.d_autoc); cudaFree(s.d_lpc_wasted); cudaFree(s.d_ticket); cudaFree(s.d_tasks);
     if (s.h_tasks) cudaFreeHost(s.h_tasks);
+    if (s.h_odd) cudaFreeHost(s.h_odd);
+    cudaFree(s.d_odd);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -367,6 +377,32 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     }
     size_t sa = 0, sp = 0;
     cudaError_t e = cudaSuccess;
+    // k_analyze_v3: full-length blocks, every subframe type enabled, estimated LPC order, and a
+    // finest partition that is a whole number of thread runs
+    enc->v3 = false;
+    {
+        const char* force = getenv("B200FLAC_NO_V3");
+        const u32 F = std::min<u32>(P.po_lim, (u32)__builtin_ctz(bs));
+        if (enc->fast && P.try_lpc && P.try_fixed && P.try_constant && P.try_verbatim && !P.exhaustive &&
+            F <= V3_MAX_F && bs > P.max_lpc_order + 1 && !(force && force[0] == '1')) {
+            for (u32 S3 = 32; S3 >= 8; S3 -= 8) {
+                if (bs % S3 || (bs >> F) % S3) continue;
+                const u32 nt = bs / S3;
+                if (nt % 32 || nt < 32 || nt > 512) continue;
+                const size_t sm = v3_smem_bytes(bs, nt);
+                if (sm > 200 * 1024) continue;
+                enc->v3 = true; enc->v3_S = S3; enc->v3_F = F; enc->v3_NT = nt; enc->v3_smem = sm;
+                break;
+            }
+        }
+        if (enc->v3) {
+            e = enc->v3_NT <= 128
+                    ? cudaFuncSetAttribute(k_analyze_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem)
+                    : cudaFuncSetAttribute(k_analyze_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem);
+            if (e != cudaSuccess) enc->v3 = false;
+            e = cudaSuccess;
+        }
+    }
     if (enc->fast) {
         sa = 2 * padn * 4 + 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride + 16;
         sp = 2 * padn * 4 + (size_t)enc->stage_words * 4 + 16;
@@ -428,6 +464,8 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         }
         for (int k = 0; k < BF_NUM_EVENTS; k++) cudaEventCreate(&s.ev[k]);
         ALLOCH(s.h_fd, maxf * sizeof(bf_frame_desc));
+        ALLOCH(s.h_odd, maxf * sizeof(u32));
+        ALLOC(s.d_odd, maxf * sizeof(u32));
         ALLOC(s.d_fd, maxf * sizeof(bf_frame_desc));
         s.win_cap = (size_t)bs * 4;
         ALLOCH(s.h_win, s.win_cap * sizeof(double));
@@ -556,6 +594,8 @@ static long build_batch(b200flac_encoder* enc, Slot& s, const b200flac_segment* 
         }
     }
     if (need > enc->max_pcm_frames) { set_err("batch has more PCM frames than the encoder was created for"); return -1; }
+    s.n_odd = 0;
+    for (u64 f = 0; f < nf; f++) if (s.h_fd[f].nsamp != bs) s.h_odd[s.n_odd++] = (u32)f;
     if (want_windows) {
         // tasks of the autocorrelation kernel: runs of up to 32/K consecutive frames of one length
         const u32 per = 32 / enc->P.K;
@@ -604,10 +644,23 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
     const bf_dev_params& P = enc->P;
     const u32 nf = s.n_frames, U = nf * P.K;
     cudaStream_t st = s.stream;
-    if (enc->NT <= 192)
-        k_analyze_v2<192, 4><<<U, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
-    else
-        k_analyze_v2<512, 1><<<U, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+    u32 gridv2 = U;
+    const u32* flist = nullptr;
+    if (enc->v3) {
+        if (enc->v3_NT <= 128)
+            k_analyze_v3<5><<<U, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+        else
+            k_analyze_v3<1><<<U, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+        enc->launches += 1;
+        gridv2 = s.n_odd * P.K;      // the other block lengths (a stream's last block)
+        flist = s.d_odd;
+    }
+    if (gridv2) {
+        if (enc->NT <= 192)
+            k_analyze_v2<192, 4><<<gridv2, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice, flist);
+        else
+            k_analyze_v2<512, 1><<<gridv2, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice, flist);
+    }
     cudaEventRecord(s.ev[2], st);
     k_frame_select<<<(nf + 127) / 128, 128, 0, st>>>(s.d_fd, nf, P, s.d_plans, s.d_choice, s.d_frame_bytes);
     k_scan_offsets<<<1, 1024, 0, st>>>(s.d_frame_bytes, nf, s.d_frame_off, s.d_total);
@@ -624,7 +677,7 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
     cudaEventRecord(s.ev[4], st);
     k_frame_crc16<<<(nf * 32 + 127) / 128, 128, 0, st>>>(s.d_frame_off, s.d_frame_bytes, nf, d_out, s.d_total, out_cap);
     cudaEventRecord(s.ev[5], st);
-    enc->launches += 6;
+    enc->launches += 5 + (gridv2 ? 1 : 0);
 }
 
 // enqueue the kernels of one batch on the slot's stream
@@ -702,6 +755,7 @@ extern "C" int b200flac_encoder_submit(b200flac_encoder* enc, int slot, const ui
     } else if (ensure_host_path(enc, s, false)) return 1;
     CU_CHECK(cudaMemcpyAsync(s.d_pcm, src, pcm_bytes, cudaMemcpyHostToDevice, st), 1);
     CU_CHECK(cudaMemcpyAsync(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), cudaMemcpyHostToDevice, st), 1);
+    if (s.n_odd) CU_CHECK(cudaMemcpyAsync(s.d_odd, s.h_odd, (size_t)s.n_odd * sizeof(u32), cudaMemcpyHostToDevice, st), 1);
     if (enc->P.try_lpc) CU_CHECK(cudaMemcpyAsync(s.d_tasks, s.h_tasks, (size_t)s.n_tasks * sizeof(bf_lpc_task), cudaMemcpyHostToDevice, st), 1);
     const size_t wused = (size_t)s.h_total[1];
     if (wused) CU_CHECK(cudaMemcpyAsync(s.d_win, s.h_win, wused * sizeof(double), cudaMemcpyHostToDevice, st), 1);
@@ -763,6 +817,7 @@ extern "C" int b200flac_encoder_encode_device(b200flac_encoder* enc, int slot, c
     if (nf == 0) { if (out_bytes) *out_bytes = 0; if (n_frames) *n_frames = 0; return 0; }
     cudaStream_t st = s.stream;
     CU_CHECK(cudaMemcpyAsync(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), cudaMemcpyHostToDevice, st), 1);
+    if (s.n_odd) CU_CHECK(cudaMemcpyAsync(s.d_odd, s.h_odd, (size_t)s.n_odd * sizeof(u32), cudaMemcpyHostToDevice, st), 1);
     if (enc->P.try_lpc) CU_CHECK(cudaMemcpyAsync(s.d_tasks, s.h_tasks, (size_t)s.n_tasks * sizeof(bf_lpc_task), cudaMemcpyHostToDevice, st), 1);
     const size_t wused = (size_t)s.h_total[1];
     if (wused) CU_CHECK(cudaMemcpyAsync(s.d_win, s.h_win, wused * sizeof(double), cudaMemcpyHostToDevice, st), 1);

@@ -484,7 +484,8 @@ template <int NTMAX, int MINB>
 __global__ void __launch_bounds__(NTMAX, MINB)
 k_analyze_v2(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S,
              const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
-             b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out)
+             b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out,
+             const u32* __restrict__ frame_list)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ u64 red[40];
@@ -495,8 +496,10 @@ k_analyze_v2(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
     __shared__ bf_lpc_head s_head;
 
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    const u32 unit = blockIdx.x;
-    const u32 frame = unit / P.K, cand = unit % P.K;
+    // frame_list: the frames this launch covers (k_analyze_v3 took the others), or NULL for all
+    const u32 cand = blockIdx.x % P.K;
+    const u32 frame = frame_list ? frame_list[blockIdx.x / P.K] : blockIdx.x / P.K;
+    const u32 unit = frame * P.K + cand;
     const bf_frame_desc d = fd[frame];
     const u32 n = d.nsamp;
     const u32 bps = candidate_bps(cand, P);

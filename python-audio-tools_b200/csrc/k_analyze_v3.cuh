@@ -1,0 +1,508 @@
+// k_analyze_v3.cuh -- the model-search kernel for full-length blocks of the common shapes
+// (k_analyze_v2 takes every other block: tails, exhaustive search, disabled subframe types,
+// partition lengths that are not a whole number of thread runs).
+//
+// Same decisions, bit for bit, as k_analyze / k_analyze_v2 (and the reference, flac.c:673-1505);
+// one CTA per unit (frame, candidate), every thread owns a contiguous run of S samples.  What
+// v3 changes is how little it executes around the arithmetic the reference defines:
+//   * one pass over the samples yields the FIXED error sums of all five orders AND, per thread
+//     run, the sums of |residual| the Rice search needs for whichever order wins -- the FIXED
+//     residual is never written anywhere;
+//   * the LPC residual pass accumulates its own run sums while it stores the residual;
+//   * the two Rice searches (FIXED, LPC) run side by side, each inside ONE warp, on prefix sums
+//     of the run sums: no block-wide barrier, no redundant per-thread level loops;
+//   * one fused pass then counts the exact bits of both models (FIXED residual recomputed on the
+//     fly, LPC residual re-read); the per-partition (1 + k) terms come from the search warp;
+//   * samples are skewed four words per 32 in shared memory, so every 8-sample chunk is two
+//     conflict-free 128-bit accesses;
+//   * five block-wide barriers per unit instead of fourteen.
+#pragma once
+#include "flac_common.cuh"
+#include "k_analyze.cuh"
+#include "k_analyze_v2.cuh"
+
+#define V3_CH 8
+#define V3_SK(i) ((i) + (((i) >> 5) << 2))      // four words of skew per 32 samples
+#define V3_MAX_F 7                               // finest partition order handled (<= 128 partitions)
+#define V3_HEAP (2 << V3_MAX_F)
+
+// what the search warp of a model hands to the rest of the CTA
+struct V3Decision {
+    u32 po;          // partition order
+    u32 method;      // coding method (1 iff some k > 14)
+    u32 order;       // predictor order of the model
+    u32 pad;
+    u64 side_bits;   // 6 + 2^po * (4|5) + sum over partitions of (1 + k) * residuals in it
+};
+
+struct V3Shared {
+    u64 lvl_tot[2][V3_MAX_F + 1];
+    u64 lvl_cnt[2][V3_MAX_F + 1];
+    u32 lvl_maxk[2][V3_MAX_F + 1];
+    V3Decision dec[2];
+    u64 corr[5];          // FIXED: sum of |r_k[i]| for k <= i < 4 (in the partition sums, not in the order choice)
+    u64 bits[2];          // exact sum of (u >> k) over the block, per model
+    u32 red_or[16], red_diff[16];
+    u32 lpc_narrow;       // LPC sum provably fits 32 bits
+    short q[BF_MAX_ORDER];
+    bf_lpc_head head;
+    uint8_t kheap[2][V3_HEAP];
+};
+
+// host and device agree on the dynamic shared memory through this
+__host__ __device__ inline size_t v3_smem_bytes(u32 n, u32 NT)
+{
+    const size_t padn = (size_t)V3_SK(n) + 8;
+    return 2 * padn * 4 + (size_t)5 * NT * 8 + (size_t)NT * 8 + 32;
+}
+
+// one warp: partition-order search over the run sums of one model.
+//   runs[t] = sum of |r| over thread run t (run 0 without its first `order` samples); overwritten
+//   with its inclusive prefix sums.
+__device__ __forceinline__ void v3_search(u64* runs, u32 NT, u32 S, u32 n, u32 order, u32 F, u32 max_rice,
+                                          uint8_t* kheap, u64* lvl_tot, u64* lvl_cnt, u32* lvl_maxk, V3Decision* dec)
+{
+    const u32 lane = threadIdx.x & 31;
+    if (lane <= V3_MAX_F) { lvl_tot[lane] = 0ull; lvl_cnt[lane] = 0ull; lvl_maxk[lane] = 0u; }
+    // inclusive prefix sums of the run sums
+    {
+        const u32 per = (NT + 31) >> 5, b = lane * per;
+        u64 run = 0;
+        for (u32 i = 0; i < per; i++) if (b + i < NT) { run += runs[b + i]; runs[b + i] = run; }
+        u64 inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= (u32)o) inc += t;
+        }
+        const u64 excl = inc - run;
+        for (u32 i = 0; i < per; i++) if (b + i < NT) runs[b + i] += excl;
+    }
+    __syncwarp();
+    const u32 nfine = 1u << F;
+    const u32 g = (n >> F) / S;             // thread runs per finest partition
+    const u32 heapn = 2 * nfine - 1;
+    for (u32 node0 = 0; node0 <= heapn; node0 += 32) {
+        const u32 node = node0 + lane;
+        const bool act = node >= 1 && node <= heapn;
+        u32 l = 0, k = 0;
+        u64 est = 0, cnt = 0;
+        if (act) {
+            l = 31u - (u32)__clz((int)node);
+            const u32 p = node - (1u << l);
+            const u32 w = (nfine >> l) * g;                 // thread runs per partition of this level
+            const u64 hi = runs[(p + 1) * w - 1];
+            const u64 lo = p ? runs[p * w - 1] : 0ull;
+            const u32 plength = (n >> l) - (p == 0 ? order : 0u);
+            est = partition_estimate_fast(plength, hi - lo, max_rice, &k);
+            kheap[node - 1] = (uint8_t)k;
+            cnt = (u64)(1u + k) * plength;
+        }
+        if (node0 >= 32) {
+            // all 32 nodes of this step belong to one level
+            const u32 km = __reduce_max_sync(0xFFFFFFFFu, k);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                est += __shfl_xor_sync(0xFFFFFFFFu, est, o);
+                cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+            }
+            if (lane == 0) { lvl_tot[l] += est; lvl_cnt[l] += cnt; lvl_maxk[l] = max(lvl_maxk[l], km); }
+        } else {
+            // nodes 1..31: levels 0..4, level l occupies lanes 2^l .. 2^(l+1)-1
+            const u32 gs = act ? (1u << l) : 1u;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const u64 te = __shfl_xor_sync(0xFFFFFFFFu, est, o);
+                const u64 tc = __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+                const u32 tk = __shfl_xor_sync(0xFFFFFFFFu, k, o);
+                if ((u32)o < gs) { est += te; cnt += tc; k = max(k, tk); }
+            }
+            if (act && node == gs) { lvl_tot[l] = est; lvl_cnt[l] = cnt; lvl_maxk[l] = k; }
+        }
+        __syncwarp();
+    }
+    // first strict minimum over the levels (flac.c:1365-1400)
+    u64 best = lvl_tot[0];
+    u32 po = 0;
+    for (u32 l = 1; l <= F; l++) {
+        const u64 tot = lvl_tot[l];
+        if (tot < best) { best = tot; po = l; }
+    }
+    if (lane == 0) {
+        const u32 maxk = lvl_maxk[po];
+        dec->po = po;
+        dec->method = maxk > 14 ? 1u : 0u;
+        dec->order = order;
+        dec->side_bits = 6ull + (u64)(1u << po) * (maxk > 14 ? 5ull : 4ull) + lvl_cnt[po];
+    }
+}
+
+// FIXED error sums of orders 0..4 over the thread's run: e[k] = sum of |r_k[i]| (flac.c:877-893).
+// FIRST: the run starts at sample 0 -- samples 0..3 are left out of e[] (the reference sums from
+// sample 4 for every order) and corr[k] collects |r_k[i]| for k <= i < 4.
+template <typename SumT, bool FIRST>
+__device__ __forceinline__ void v3_fixed_sums(const int* __restrict__ samp, u32 base, u32 S, SumT (&e)[5], u64* corr)
+{
+    u32 prev = 0, p1 = 0, p2 = 0, p3 = 0;
+    if (!FIRST) {
+        const u32 a1 = (u32)samp[V3_SK(base - 1)], a2 = (u32)samp[V3_SK(base - 2)];
+        const u32 a3 = (u32)samp[V3_SK(base - 3)], a4 = (u32)samp[V3_SK(base - 4)];
+        p1 = a1 - a2; p2 = p1 - (a2 - a3); p3 = p2 - ((a2 - a3) - (a3 - a4));
+        prev = a1;
+    }
+    SumT f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+    u64 c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+        const int4 va = *(const int4*)(samp + V3_SK(i0));
+        const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
+        const int xs[V3_CH] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        if (FIRST && i0 == base) {
+#pragma unroll
+            for (int j = 0; j < V3_CH; j++) {
+                const u32 x = (u32)xs[j];
+                const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+                if (j >= 4) {
+                    f0 += (u32)abs((int)x); f1 += (u32)abs((int)d1); f2 += (u32)abs((int)d2);
+                    f3 += (u32)abs((int)d3); f4 += (u32)abs((int)d4);
+                } else {
+                    c0 += (u32)abs((int)x);
+                    if (j >= 1) c1 += (u32)abs((int)d1);
+                    if (j >= 2) c2 += (u32)abs((int)d2);
+                    if (j >= 3) c3 += (u32)abs((int)d3);
+                }
+                prev = x; p1 = d1; p2 = d2; p3 = d3;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < V3_CH; j++) {
+                const u32 x = (u32)xs[j];
+                const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+                f0 += (u32)abs((int)x); f1 += (u32)abs((int)d1); f2 += (u32)abs((int)d2);
+                f3 += (u32)abs((int)d3); f4 += (u32)abs((int)d4);
+                prev = x; p1 = d1; p2 = d2; p3 = d3;
+            }
+        }
+    }
+    e[0] = f0; e[1] = f1; e[2] = f2; e[3] = f3; e[4] = f4;
+    if (FIRST) { corr[0] = c0; corr[1] = c1; corr[2] = c2; corr[3] = c3; corr[4] = 0ull; }
+}
+
+// LPC residual of the thread's run (flac.c:999-1008) into resid, chunks of 8, history window in
+// registers; returns the run's sum of |r|.  OG: taps (coefficients zero-padded, exact).
+// WIDE: 64-bit accumulate, otherwise 32-bit (only chosen when the sum provably fits).
+template <int OG, bool WIDE>
+__device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int* __restrict__ resid, u32 base, u32 S,
+                                               const short* q_sm, int shift)
+{
+    int q[OG];
+#pragma unroll
+    for (int t = 0; t < OG; t++) q[t] = q_sm[t];
+    int w[OG + V3_CH]; // w[OG + j] = sample i0 + j, w[OG - 1 - t] = sample i0 - 1 - t
+#pragma unroll
+    for (int t = 0; t < OG; t++) {
+        const int idx = (int)base - 1 - t;
+        w[OG - 1 - t] = idx >= 0 ? samp[V3_SK(idx)] : 0;
+    }
+    u64 run = 0;
+    for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+        const int4 va = *(const int4*)(samp + V3_SK(i0));
+        const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
+        w[OG + 0] = va.x; w[OG + 1] = va.y; w[OG + 2] = va.z; w[OG + 3] = va.w;
+        w[OG + 4] = vb.x; w[OG + 5] = vb.y; w[OG + 6] = vb.z; w[OG + 7] = vb.w;
+        int res[V3_CH];
+#pragma unroll
+        for (int j = 0; j < V3_CH; j++) {
+            int pred;
+            if (WIDE) {
+                long long acc = 0;
+#pragma unroll
+                for (int t = 0; t < OG; t++) acc += (long long)q[t] * (long long)w[OG + j - 1 - t];
+                pred = (int)(acc >> shift);
+            } else {
+                int acc = 0;
+#pragma unroll
+                for (int t = 0; t < OG; t++) acc += q[t] * w[OG + j - 1 - t];
+                pred = acc >> shift;
+            }
+            res[j] = (int)((u32)w[OG + j] - (u32)pred);
+        }
+#pragma unroll
+        for (int j = 0; j < V3_CH; j++) run += (u64)(u32)abs(res[j]);
+        *(int4*)(resid + V3_SK(i0)) = make_int4(res[0], res[1], res[2], res[3]);
+        *(int4*)(resid + V3_SK(i0) + 4) = make_int4(res[4], res[5], res[6], res[7]);
+#pragma unroll
+        for (int t = 0; t < OG; t++) w[t] = w[t + V3_CH];
+    }
+    return run;
+}
+
+// sum of (zigzag(r) >> k) over the thread's run for the FIXED residual of ORDER, recomputed from
+// the samples (the sum fits 32 bits: see the Rice parameter rule, flac.c:1478)
+template <int ORDER>
+__device__ __forceinline__ u32 v3_fixed_bits(const int* __restrict__ samp, u32 base, u32 S, u32 k, u32 skip)
+{
+    u32 prev = 0, p1 = 0, p2 = 0, p3 = 0;
+    if (base) {
+        const u32 a1 = (u32)samp[V3_SK(base - 1)], a2 = (u32)samp[V3_SK(base - 2)];
+        const u32 a3 = (u32)samp[V3_SK(base - 3)], a4 = (u32)samp[V3_SK(base - 4)];
+        p1 = a1 - a2; p2 = p1 - (a2 - a3); p3 = p2 - ((a2 - a3) - (a3 - a4));
+        prev = a1;
+    }
+    u32 acc = 0, head = 0;
+    for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+        const int4 va = *(const int4*)(samp + V3_SK(i0));
+        const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
+        const int xs[V3_CH] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int j = 0; j < V3_CH; j++) {
+            const u32 x = (u32)xs[j];
+            u32 v = x;
+            if (ORDER >= 1) { const u32 d1 = x - prev; v = d1;
+                if (ORDER >= 2) { const u32 d2 = d1 - p1; v = d2;
+                    if (ORDER >= 3) { const u32 d3 = d2 - p2; v = d3;
+                        if (ORDER >= 4) { const u32 d4 = d3 - p3; v = d4; }
+                        p3 = d3; }
+                    p2 = d2; }
+                p1 = d1; prev = x; }
+            const u32 t = zigzag((int)v) >> k;
+            acc += t;
+            if (ORDER > 0 && j < ORDER && i0 == base) head += t;   // warm-up positions (only matter for run 0)
+        }
+    }
+    return acc - (skip ? head : 0u);
+}
+
+__device__ __forceinline__ u32 v3_fixed_bits_any(const int* __restrict__ samp, u32 base, u32 S, u32 k, u32 order, u32 skip)
+{
+    switch (order) {
+    case 0: return v3_fixed_bits<0>(samp, base, S, k, skip);
+    case 1: return v3_fixed_bits<1>(samp, base, S, k, skip);
+    case 2: return v3_fixed_bits<2>(samp, base, S, k, skip);
+    case 3: return v3_fixed_bits<3>(samp, base, S, k, skip);
+    default: return v3_fixed_bits<4>(samp, base, S, k, skip);
+    }
+}
+
+// sum of (zigzag(r) >> k) over the thread's run of a stored residual; the first `skip` entries
+// (warm-up positions of run 0) are left out
+__device__ __forceinline__ u32 v3_stored_bits(const int* __restrict__ resid, u32 base, u32 S, u32 k, u32 skip)
+{
+    u32 acc = 0;
+    for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+        const int4 va = *(const int4*)(resid + V3_SK(i0));
+        const int4 vb = *(const int4*)(resid + V3_SK(i0) + 4);
+        acc += (zigzag(va.x) >> k) + (zigzag(va.y) >> k) + (zigzag(va.z) >> k) + (zigzag(va.w) >> k);
+        acc += (zigzag(vb.x) >> k) + (zigzag(vb.y) >> k) + (zigzag(vb.z) >> k) + (zigzag(vb.w) >> k);
+    }
+    for (u32 i = 0; i < skip; i++) acc -= zigzag(resid[V3_SK(base + i)]) >> k;
+    return acc;
+}
+
+// S: samples per thread (multiple of 8, <= 32); blockDim.x * S == block_size; F: finest partition
+// order searched, (block_size >> F) a multiple of S.  Units whose block is not block_size long are
+// left to k_analyze_v2 (launched over the same grid, which skips the others).
+template <int MINB>
+__global__ void __launch_bounds__(512 / (MINB >= 5 ? 4 : 1), MINB)
+k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S, u32 F,
+             const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
+             b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ V3Shared sh;
+
+    const u32 tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const u32 unit = blockIdx.x;
+    const u32 frame = unit / P.K, cand = unit % P.K;
+    const bf_frame_desc d = fd[frame];
+    const u32 n = d.nsamp;
+    if (n != P.block_size) return;
+    const u32 bps = candidate_bps(cand, P);
+    const u32 base = tid * S;
+
+    const size_t padn = (size_t)V3_SK(n) + 8;
+    int* samp = (int*)dyn_smem;
+    int* resid = samp + padn;
+    u64* runsF = (u64*)(resid + padn);          // [5][nt]
+    u64* runsL = runsF + 5 * (size_t)nt;        // [nt]
+
+    // ---- LPC model of the unit (last warp; overlaps the PCM load of the others) ----
+    const short* mycoef = coefs + (size_t)unit * P.model_stride;
+    if (warp == nw - 1) {
+        if (lane == 0) sh.head = heads[unit];
+        __syncwarp();
+        const u32 o = sh.head.best_order;
+        const int q = lane < o ? (int)mycoef[(o * (o - 1)) / 2 + lane] : 0;
+        sh.q[lane] = (short)q;
+        const u32 sumq = __reduce_add_sync(0xFFFFFFFFu, (u32)abs(q));
+        if (lane == 0) sh.lpc_narrow = sumq;     // turned into the flag once wasted bits are known
+    }
+    if (tid < 2) sh.bits[tid] = 0ull;
+
+    // ---- load, constant check, wasted bits (flac.c:691-724) ----
+    u32 orv = 0, diff = 0;
+    {
+        const int first = ld_candidate(pcm, d.pcm_off, cand, P);
+        if (P.stereo && P.bytes_ps == 2) {
+            const int coef = cand == 0 ? 0x0001 : cand == 1 ? 0x0100 : cand == 2 ? 0x0101 : 0xFF01;
+            const int shv = cand == 2 ? 1 : 0;
+            const uint8_t* src = pcm + d.pcm_off * 4;
+            if ((((uintptr_t)src) & 15) == 0) {
+                const uint4* s4 = (const uint4*)src;
+                for (u32 i = tid * 4; i < n; i += nt * 4) {
+                    const uint4 w4 = __ldg(s4 + (i >> 2));
+                    int4 v;
+                    v.x = __dp2a_lo((int)w4.x, coef, 0) >> shv; v.y = __dp2a_lo((int)w4.y, coef, 0) >> shv;
+                    v.z = __dp2a_lo((int)w4.z, coef, 0) >> shv; v.w = __dp2a_lo((int)w4.w, coef, 0) >> shv;
+                    *(int4*)(samp + V3_SK(i)) = v;
+                    orv |= (u32)(v.x | v.y | v.z | v.w);
+                    diff |= (u32)((v.x ^ first) | (v.y ^ first) | (v.z ^ first) | (v.w ^ first));
+                }
+            } else {
+                const u32* s1 = (const u32*)src;
+                for (u32 i = tid; i < n; i += nt) {
+                    const int v = __dp2a_lo((int)__ldg(s1 + i), coef, 0) >> shv;
+                    samp[V3_SK(i)] = v;
+                    orv |= (u32)v; diff |= (u32)(v ^ first);
+                }
+            }
+        } else {
+            for (u32 i = tid; i < n; i += nt) {
+                const int v = ld_candidate(pcm, d.pcm_off + i, cand, P);
+                samp[V3_SK(i)] = v;
+                orv |= (u32)v; diff |= (u32)(v ^ first);
+            }
+        }
+    }
+    orv = __reduce_or_sync(0xFFFFFFFFu, orv);
+    diff = __reduce_or_sync(0xFFFFFFFFu, diff);
+    if (lane == 0) { sh.red_or[warp] = orv; sh.red_diff[warp] = diff; }
+    __syncthreads();                                                             // (1)
+    orv = 0; diff = 0;
+    for (u32 w = 0; w < nw; w++) { orv |= sh.red_or[w]; diff |= sh.red_diff[w]; }
+
+    b200flac_plan plan;
+    plan.type = BF_VERBATIM; plan.order = 0; plan.wasted = 0; plan.precision = 0; plan.shift = 0;
+    plan.coding_method = 0; plan.partition_order = 0; plan.flags = 0; plan.bits = 0;
+#pragma unroll
+    for (int i = 0; i < BF_MAX_ORDER; i++) plan.coeffs[i] = 0;
+    if (diff == 0) {
+        // CONSTANT, always written with wasted = 0 (H8)
+        if (tid == 0) { plan.type = BF_CONSTANT; plan.bits = 8 + bps; plans[unit] = plan; }
+        return;
+    }
+    const u32 wasted = orv ? (u32)(__ffs((int)orv) - 1) : 0u;
+    if (wasted) {
+        for (u32 i = tid; i < n; i += nt) samp[V3_SK(i)] >>= wasted;                 // arithmetic (H10)
+        __syncthreads();
+    }
+    const u32 sub_bps = bps - wasted;
+    const u32 hdr_bits = 8 + wasted;
+
+    // ---- pass A: FIXED sums of all orders + LPC residual, run sums to shared memory ----
+    {
+        if (sub_bps <= 23) {
+            u32 e[5];
+            if (tid == 0) v3_fixed_sums<u32, true>(samp, base, S, e, sh.corr);
+            else v3_fixed_sums<u32, false>(samp, base, S, e, nullptr);
+#pragma unroll
+            for (int k = 0; k < 5; k++) runsF[k * nt + tid] = (u64)e[k];
+        } else {
+            u64 e[5];
+            if (tid == 0) v3_fixed_sums<u64, true>(samp, base, S, e, sh.corr);
+            else v3_fixed_sums<u64, false>(samp, base, S, e, nullptr);
+#pragma unroll
+            for (int k = 0; k < 5; k++) runsF[k * nt + tid] = e[k];
+        }
+    }
+    const u32 lpc_order = sh.head.best_order, precision = sh.head.precision;
+    const int lpc_shift = sh.head.shift[lpc_order - 1];
+    {
+        const bool narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
+        u64 run;
+        if (lpc_order <= 8) run = narrow ? v3_lpc_residual<8, false>(samp, resid, base, S, sh.q, lpc_shift)
+                                         : v3_lpc_residual<8, true>(samp, resid, base, S, sh.q, lpc_shift);
+        else if (lpc_order <= 12) run = narrow ? v3_lpc_residual<12, false>(samp, resid, base, S, sh.q, lpc_shift)
+                                               : v3_lpc_residual<12, true>(samp, resid, base, S, sh.q, lpc_shift);
+        else run = narrow ? v3_lpc_residual<32, false>(samp, resid, base, S, sh.q, lpc_shift)
+                          : v3_lpc_residual<32, true>(samp, resid, base, S, sh.q, lpc_shift);
+        if (tid == 0) for (u32 i = 0; i < lpc_order; i++) run -= (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions
+        runsL[tid] = run;
+        if (tid == 0) plan.flags = narrow ? 2 : 0;   // packer may accumulate in 32 bits
+    }
+    __syncthreads();                                                             // (2)
+
+    // ---- the two Rice searches, one warp each ----
+    const u32 wF = 0, wL = nw > 1 ? 1u : 0u;
+    if (warp == wF) {
+        // order choice: first strict minimum of the block totals (flac.c:877-893)
+        u64 tot[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            u64 a = 0;
+            for (u32 t = lane; t < nt; t += 32) a += runsF[k * nt + t];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            tot[k] = a;
+        }
+        u32 fo = 0;
+        u64 best = tot[0];
+        if (tot[1] < best) { best = tot[1]; fo = 1; }
+        if (tot[2] < best) { best = tot[2]; fo = 2; }
+        if (tot[3] < best) { best = tot[3]; fo = 3; }
+        if (tot[4] < best) { best = tot[4]; fo = 4; }
+        u64* runs = runsF + (size_t)fo * nt;
+        if (lane == 0) runs[0] += sh.corr[fo];
+        __syncwarp();
+        v3_search(runs, nt, S, n, fo, F, P.max_rice, sh.kheap[0], sh.lvl_tot[0], sh.lvl_cnt[0], sh.lvl_maxk[0], &sh.dec[0]);
+    }
+    if (warp == wL) {
+        v3_search(runsL, nt, S, n, lpc_order, F, P.max_rice, sh.kheap[1], sh.lvl_tot[1], sh.lvl_cnt[1], sh.lvl_maxk[1], &sh.dec[1]);
+    }
+    __syncthreads();                                                             // (3)
+
+    // ---- pass B: exact bits of both models ----
+    const u32 poF = sh.dec[0].po, poL = sh.dec[1].po, fixed_order = sh.dec[0].order;
+    {
+        const u32 kF = sh.kheap[0][(1u << poF) - 1u + base / (n >> poF)];
+        const u32 kL = sh.kheap[1][(1u << poL) - 1u + base / (n >> poL)];
+        u32 bF = v3_fixed_bits_any(samp, base, S, kF, fixed_order, tid == 0 ? 1u : 0u);
+        u32 bL = v3_stored_bits(resid, base, S, kL, tid == 0 ? lpc_order : 0u);
+        // a warp's sum stays far below 2^32 (each run's is bounded by ~2 * partition length + 32 * 2^18)
+        bF = __reduce_add_sync(0xFFFFFFFFu, bF);
+        bL = __reduce_add_sync(0xFFFFFFFFu, bL);
+        if (lane == 0) { atomicAdd(&sh.bits[0], (u64)bF); atomicAdd(&sh.bits[1], (u64)bL); }
+    }
+    __syncthreads();                                                             // (4)
+
+    // ---- choice, flac.c:727-809 (every subframe type enabled) ----
+    const u64 fixed_bits = hdr_bits + (u64)fixed_order * sub_bps + sh.dec[0].side_bits + sh.bits[0];
+    const u64 lpc_bits = hdr_bits + (u64)lpc_order * sub_bps + 4 + 5 + (u64)lpc_order * precision + sh.dec[1].side_bits + sh.bits[1];
+    const u32 fb = (u32)fixed_bits, lb = (u32)lpc_bits;
+    const u32 vb = sub_bps * n;                       // header NOT counted (H2)
+    const u32 choice = (fb < min(lb, vb)) ? BF_FIXED : (lb < vb) ? BF_LPC : BF_VERBATIM;
+    uint8_t* my_rice = rice_out + (size_t)unit * P.rice_stride;
+    plan.wasted = (uint8_t)wasted;
+    if (choice == BF_FIXED) {
+        const u32 koff = (1u << poF) - 1u;
+        for (u32 p = tid; p < (1u << poF); p += nt) my_rice[p] = sh.kheap[0][koff + p];
+        if (tid == 0) {
+            plan.type = BF_FIXED; plan.order = (uint8_t)fixed_order;
+            plan.coding_method = (uint8_t)sh.dec[0].method; plan.partition_order = (uint8_t)poF;
+            plan.flags = 0; plan.bits = fb;
+        }
+    } else if (choice == BF_LPC) {
+        const u32 koff = (1u << poL) - 1u;
+        for (u32 p = tid; p < (1u << poL); p += nt) my_rice[p] = sh.kheap[1][koff + p];
+        if (tid == 0) {
+            plan.type = BF_LPC; plan.order = (uint8_t)lpc_order;
+            plan.precision = (uint8_t)precision; plan.shift = (int8_t)lpc_shift;
+            plan.coding_method = (uint8_t)sh.dec[1].method; plan.partition_order = (uint8_t)poL;
+            plan.bits = lb;
+            for (u32 j = 0; j < lpc_order; j++) plan.coeffs[j] = sh.q[j];
+        }
+    } else if (tid == 0) {
+        plan.type = BF_VERBATIM; plan.flags = 0;
+        plan.bits = hdr_bits + sub_bps * n;           // flac.c:832-854
+    }
+    if (tid == 0) plans[unit] = plan;
+}
