@@ -26,20 +26,16 @@
 #define V3_MAX_F 7                               // finest partition order handled (<= 128 partitions)
 #define V3_HEAP (2 << V3_MAX_F)
 
-// what the search warp of a model hands to the rest of the CTA
-struct V3Decision {
-    u32 po;          // partition order
-    u32 method;      // coding method (1 iff some k > 14)
-    u32 order;       // predictor order of the model
-    u32 pad;
-    u64 side_bits;   // 6 + 2^po * (4|5) + sum over partitions of (1 + k) * residuals in it
+// totals of one partition order of one model (written by whichever warp evaluated the level)
+struct V3Level {
+    u64 tot;         // the reference's size estimate of the residual block at this order
+    u32 cnt;         // sum over partitions of (1 + k) * residuals in it
+    u32 maxk;
 };
 
 struct V3Shared {
-    u64 lvl_tot[2][V3_MAX_F + 1];
-    u64 lvl_cnt[2][V3_MAX_F + 1];
-    u32 lvl_maxk[2][V3_MAX_F + 1];
-    V3Decision dec[2];
+    V3Level lvl[2][V3_MAX_F + 1];
+    u64 totF[5];          // FIXED: block totals of the error sums (flac.c:877-893)
     u64 corr[5];          // FIXED: sum of |r_k[i]| for k <= i < 4 (in the partition sums, not in the order choice)
     u64 bits[2];          // exact sum of (u >> k) over the block, per model
     u32 red_or[16], red_diff[16];
@@ -56,19 +52,61 @@ __host__ __device__ inline size_t v3_smem_bytes(u32 n, u32 NT)
     return 2 * padn * 4 + (size_t)5 * NT * 8 + (size_t)NT * 8 + 32;
 }
 
-// one warp: partition-order search over the run sums of one model.
-//   runs[t] = sum of |r| over thread run t (run 0 without its first `order` samples); overwritten
-//   with its inclusive prefix sums.
-__device__ __forceinline__ void v3_search(u64* runs, u32 NT, u32 S, u32 n, u32 order, u32 F, u32 max_rice,
-                                          uint8_t* kheap, u64* lvl_tot, u64* lvl_cnt, u32* lvl_maxk, V3Decision* dec)
+__device__ __forceinline__ u64 v3_warp_sum_u64(u64 v)
+{
+    if (!__any_sync(0xFFFFFFFFu, (v >> 26) != 0)) return (u64)__reduce_add_sync(0xFFFFFFFFu, (u32)v);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// One warp evaluates a share of the partition orders of one model (flac.c:1437-1505) from the run
+// sums: runs[t] = sum of |r| over thread run t (run 0 without its first `order` samples, up to
+// first_extra, which is added here).  One lane per partition ("node"), 32 nodes per step.
+//   part 0: the finest order F -- a node is g consecutive run sums;
+//   part 1: every order below F -- nodes are differences of the prefix sums of the finest sums,
+//           which this warp builds in `pre` (shared, nfine entries) first.
+// The two parts are independent, so two warps can run them side by side.
+__device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_extra, u32 S, u32 n, u32 order,
+                                       u32 F, u32 max_rice, uint8_t* kheap, V3Level* lvl, u64* pre, u32 part)
 {
     const u32 lane = threadIdx.x & 31;
-    if (lane <= V3_MAX_F) { lvl_tot[lane] = 0ull; lvl_cnt[lane] = 0ull; lvl_maxk[lane] = 0u; }
-    // inclusive prefix sums of the run sums
+    const u32 nfine = 1u << F;
+    const u32 g = (n >> F) / S;                          // thread runs per finest partition
+    if (part == 0) {
+        u64 est_acc = 0; u32 cnt_acc = 0, k_acc = 0;
+        for (u32 p = lane; p < nfine; p += 32) {
+            const u64* r = runs + (size_t)p * g;
+            u64 sum = p == 0 ? first_extra : 0ull;
+            for (u32 j = 0; j < g; j++) sum += r[j];
+            const u32 plength = (n >> F) - (p == 0 ? order : 0u);
+            u32 k;
+            est_acc += partition_estimate_fast(plength, sum, max_rice, &k);
+            kheap[nfine - 1u + p] = (uint8_t)k;
+            cnt_acc += (1u + k) * plength;
+            k_acc = max(k_acc, k);
+        }
+        const u64 tot = v3_warp_sum_u64(est_acc);
+        const u32 cnt = __reduce_add_sync(0xFFFFFFFFu, cnt_acc);
+        const u32 mk = __reduce_max_sync(0xFFFFFFFFu, k_acc);
+        if (lane == 0) { lvl[F].tot = tot; lvl[F].cnt = cnt; lvl[F].maxk = mk; }
+        return;
+    }
+    if (F == 0) return;
+    // inclusive prefix sums of the finest sums: lane owns c = ceil(nfine / 32) consecutive ones
     {
-        const u32 per = (NT + 31) >> 5, b = lane * per;
+        const u32 c = (nfine + 31) >> 5, b = lane * c;
         u64 run = 0;
-        for (u32 i = 0; i < per; i++) if (b + i < NT) { run += runs[b + i]; runs[b + i] = run; }
+        for (u32 i = 0; i < c; i++) {
+            const u32 p = b + i;
+            if (p < nfine) {
+                const u64* r = runs + (size_t)p * g;
+                u64 sum = p == 0 ? first_extra : 0ull;
+                for (u32 j = 0; j < g; j++) sum += r[j];
+                run += sum;
+                pre[p] = run;
+            }
+        }
         u64 inc = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -76,115 +114,120 @@ __device__ __forceinline__ void v3_search(u64* runs, u32 NT, u32 S, u32 n, u32 o
             if (lane >= (u32)o) inc += t;
         }
         const u64 excl = inc - run;
-        for (u32 i = 0; i < per; i++) if (b + i < NT) runs[b + i] += excl;
+        for (u32 i = 0; i < c; i++) if (b + i < nfine) pre[b + i] += excl;
     }
     __syncwarp();
-    const u32 nfine = 1u << F;
-    const u32 g = (n >> F) / S;             // thread runs per finest partition
-    const u32 heapn = 2 * nfine - 1;
-    for (u32 node0 = 0; node0 <= heapn; node0 += 32) {
+    for (u32 node0 = 0; node0 < nfine; node0 += 32) {
         const u32 node = node0 + lane;
-        const bool act = node >= 1 && node <= heapn;
-        u32 l = 0, k = 0;
-        u64 est = 0, cnt = 0;
+        const bool act = node >= 1 && node < nfine;
+        u32 l = 0, k = 0, cnt = 0;
+        u64 est = 0;
         if (act) {
             l = 31u - (u32)__clz((int)node);
             const u32 p = node - (1u << l);
-            const u32 w = (nfine >> l) * g;                 // thread runs per partition of this level
-            const u64 hi = runs[(p + 1) * w - 1];
-            const u64 lo = p ? runs[p * w - 1] : 0ull;
+            const u32 w = nfine >> l;                       // finest partitions per partition of this order
+            const u64 hi = pre[(p + 1) * w - 1];
+            const u64 lo = p ? pre[p * w - 1] : 0ull;
             const u32 plength = (n >> l) - (p == 0 ? order : 0u);
             est = partition_estimate_fast(plength, hi - lo, max_rice, &k);
             kheap[node - 1] = (uint8_t)k;
-            cnt = (u64)(1u + k) * plength;
+            cnt = (1u + k) * plength;
         }
         if (node0 >= 32) {
-            // all 32 nodes of this step belong to one level
+            // all 32 nodes of this step belong to one order; an order of 64 partitions takes two steps
+            const u32 l0 = 31u - (u32)__clz((int)node0);
+            const u64 tot = v3_warp_sum_u64(est);
+            const u32 cs = __reduce_add_sync(0xFFFFFFFFu, cnt);
             const u32 km = __reduce_max_sync(0xFFFFFFFFu, k);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                est += __shfl_xor_sync(0xFFFFFFFFu, est, o);
-                cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+            if (lane == 0) {
+                if ((node0 & (node0 - 1)) == 0) { lvl[l0].tot = tot; lvl[l0].cnt = cs; lvl[l0].maxk = km; }
+                else { lvl[l0].tot += tot; lvl[l0].cnt += cs; lvl[l0].maxk = max(lvl[l0].maxk, km); }
             }
-            if (lane == 0) { lvl_tot[l] += est; lvl_cnt[l] += cnt; lvl_maxk[l] = max(lvl_maxk[l], km); }
         } else {
-            // nodes 1..31: levels 0..4, level l occupies lanes 2^l .. 2^(l+1)-1
+            // nodes 1..31: orders 0..4, order l occupies lanes 2^l .. 2^(l+1)-1
             const u32 gs = act ? (1u << l) : 1u;
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) {
                 const u64 te = __shfl_xor_sync(0xFFFFFFFFu, est, o);
-                const u64 tc = __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+                const u32 tc = __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
                 const u32 tk = __shfl_xor_sync(0xFFFFFFFFu, k, o);
                 if ((u32)o < gs) { est += te; cnt += tc; k = max(k, tk); }
             }
-            if (act && node == gs) { lvl_tot[l] = est; lvl_cnt[l] = cnt; lvl_maxk[l] = k; }
+            if (act && node == gs) { lvl[l].tot = est; lvl[l].cnt = cnt; lvl[l].maxk = k; }
         }
-        __syncwarp();
-    }
-    // first strict minimum over the levels (flac.c:1365-1400)
-    u64 best = lvl_tot[0];
-    u32 po = 0;
-    for (u32 l = 1; l <= F; l++) {
-        const u64 tot = lvl_tot[l];
-        if (tot < best) { best = tot; po = l; }
-    }
-    if (lane == 0) {
-        const u32 maxk = lvl_maxk[po];
-        dec->po = po;
-        dec->method = maxk > 14 ? 1u : 0u;
-        dec->order = order;
-        dec->side_bits = 6ull + (u64)(1u << po) * (maxk > 14 ? 5ull : 4ull) + lvl_cnt[po];
     }
 }
 
-// FIXED error sums of orders 0..4 over the thread's run: e[k] = sum of |r_k[i]| (flac.c:877-893).
-// FIRST: the run starts at sample 0 -- samples 0..3 are left out of e[] (the reference sums from
-// sample 4 for every order) and corr[k] collects |r_k[i]| for k <= i < 4.
-template <typename SumT, bool FIRST>
-__device__ __forceinline__ void v3_fixed_sums(const int* __restrict__ samp, u32 base, u32 S, SumT (&e)[5], u64* corr)
+// every thread: first strict minimum of the estimates over the partition orders (flac.c:1365-1400)
+__device__ __forceinline__ void v3_pick_level(const V3Level* lvl, u32 F, u32* po_out, u32* method_out, u64* side_bits)
 {
-    u32 prev = 0, p1 = 0, p2 = 0, p3 = 0;
-    if (!FIRST) {
-        const u32 a1 = (u32)samp[V3_SK(base - 1)], a2 = (u32)samp[V3_SK(base - 2)];
-        const u32 a3 = (u32)samp[V3_SK(base - 3)], a4 = (u32)samp[V3_SK(base - 4)];
-        p1 = a1 - a2; p2 = p1 - (a2 - a3); p3 = p2 - ((a2 - a3) - (a3 - a4));
-        prev = a1;
+    u64 best = lvl[0].tot;
+    u32 po = 0;
+    for (u32 l = 1; l <= F; l++) {
+        const u64 tot = lvl[l].tot;
+        if (tot < best) { best = tot; po = l; }
     }
+    const u32 maxk = lvl[po].maxk;
+    *po_out = po;
+    *method_out = maxk > 14 ? 1u : 0u;
+    *side_bits = 6ull + (u64)(1u << po) * (maxk > 14 ? 5ull : 4ull) + (u64)lvl[po].cnt;
+}
+
+// predictor history of a FIXED pass: differences of the four samples before `base` (zeros for run 0)
+__device__ __forceinline__ void v3_fixed_history(const int* __restrict__ samp, u32 base, u32& prev, u32& p1, u32& p2, u32& p3)
+{
+    int4 h = make_int4(0, 0, 0, 0);
+    if (base) h = *(const int4*)(samp + V3_SK(base - 4));
+    const u32 a4 = (u32)h.x, a3 = (u32)h.y, a2 = (u32)h.z, a1 = (u32)h.w;
+    p1 = a1 - a2; p2 = p1 - (a2 - a3); p3 = p2 - ((a2 - a3) - (a3 - a4));
+    prev = a1;
+}
+
+// FIXED error sums of orders 0..4 over the thread's run: e[k] = sum of |r_k[i]| (flac.c:877-893).
+// Run 0 is summed like the others (zero history) and corrected by v3_fixed_head afterwards.
+template <typename SumT>
+__device__ __forceinline__ void v3_fixed_sums(const int* __restrict__ samp, u32 base, u32 S, SumT (&e)[5])
+{
+    u32 prev, p1, p2, p3;
+    v3_fixed_history(samp, base, prev, p1, p2, p3);
     SumT f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
-    u64 c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
         const int4 va = *(const int4*)(samp + V3_SK(i0));
         const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
         const int xs[V3_CH] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-        if (FIRST && i0 == base) {
 #pragma unroll
-            for (int j = 0; j < V3_CH; j++) {
-                const u32 x = (u32)xs[j];
-                const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
-                if (j >= 4) {
-                    f0 += (u32)abs((int)x); f1 += (u32)abs((int)d1); f2 += (u32)abs((int)d2);
-                    f3 += (u32)abs((int)d3); f4 += (u32)abs((int)d4);
-                } else {
-                    c0 += (u32)abs((int)x);
-                    if (j >= 1) c1 += (u32)abs((int)d1);
-                    if (j >= 2) c2 += (u32)abs((int)d2);
-                    if (j >= 3) c3 += (u32)abs((int)d3);
-                }
-                prev = x; p1 = d1; p2 = d2; p3 = d3;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < V3_CH; j++) {
-                const u32 x = (u32)xs[j];
-                const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
-                f0 += (u32)abs((int)x); f1 += (u32)abs((int)d1); f2 += (u32)abs((int)d2);
-                f3 += (u32)abs((int)d3); f4 += (u32)abs((int)d4);
-                prev = x; p1 = d1; p2 = d2; p3 = d3;
-            }
+        for (int j = 0; j < V3_CH; j++) {
+            const u32 x = (u32)xs[j];
+            const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+            f0 += (u32)abs((int)x); f1 += (u32)abs((int)d1); f2 += (u32)abs((int)d2);
+            f3 += (u32)abs((int)d3); f4 += (u32)abs((int)d4);
+            prev = x; p1 = d1; p2 = d2; p3 = d3;
         }
     }
     e[0] = f0; e[1] = f1; e[2] = f2; e[3] = f3; e[4] = f4;
-    if (FIRST) { corr[0] = c0; corr[1] = c1; corr[2] = c2; corr[3] = c3; corr[4] = 0ull; }
+}
+
+// run 0 only: the reference sums the errors from sample 4 for every order, so take samples 0..3
+// (as v3_fixed_sums counted them, with zero history) out of e[], and collect in corr[k] the true
+// residuals |r_k[i]|, k <= i < 4, which the partition sums of order k do contain
+template <typename SumT>
+__device__ __forceinline__ void v3_fixed_head(const int* __restrict__ samp, SumT (&e)[5], u64* corr)
+{
+    const int4 v = *(const int4*)samp;
+    const u32 xs[4] = {(u32)v.x, (u32)v.y, (u32)v.z, (u32)v.w};
+    u32 prev = 0, p1 = 0, p2 = 0, p3 = 0;
+    u32 g[5] = {0, 0, 0, 0, 0}, c[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const u32 x = xs[j];
+        const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+        const u32 a[5] = {(u32)abs((int)x), (u32)abs((int)d1), (u32)abs((int)d2), (u32)abs((int)d3), (u32)abs((int)d4)};
+#pragma unroll
+        for (int k = 0; k < 5; k++) { g[k] += a[k]; if (j >= k) c[k] += a[k]; }
+        prev = x; p1 = d1; p2 = d2; p3 = d3;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) { e[k] -= (SumT)g[k]; corr[k] = (u64)c[k]; }
 }
 
 // LPC residual of the thread's run (flac.c:999-1008) into resid, chunks of 8, history window in
@@ -198,10 +241,12 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
 #pragma unroll
     for (int t = 0; t < OG; t++) q[t] = q_sm[t];
     int w[OG + V3_CH]; // w[OG + j] = sample i0 + j, w[OG - 1 - t] = sample i0 - 1 - t
+    // the OG samples before the run: whole 128-bit words of the previous run (OG is a multiple of 4)
 #pragma unroll
-    for (int t = 0; t < OG; t++) {
-        const int idx = (int)base - 1 - t;
-        w[OG - 1 - t] = idx >= 0 ? samp[V3_SK(idx)] : 0;
+    for (int t = 0; t < OG; t += 4) {
+        int4 h = make_int4(0, 0, 0, 0);
+        if (base >= (u32)(OG - t)) h = *(const int4*)(samp + V3_SK(base - (OG - t)));
+        w[t] = h.x; w[t + 1] = h.y; w[t + 2] = h.z; w[t + 3] = h.w;
     }
     u64 run = 0;
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
@@ -241,13 +286,8 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
 template <int ORDER>
 __device__ __forceinline__ u32 v3_fixed_bits(const int* __restrict__ samp, u32 base, u32 S, u32 k, u32 skip)
 {
-    u32 prev = 0, p1 = 0, p2 = 0, p3 = 0;
-    if (base) {
-        const u32 a1 = (u32)samp[V3_SK(base - 1)], a2 = (u32)samp[V3_SK(base - 2)];
-        const u32 a3 = (u32)samp[V3_SK(base - 3)], a4 = (u32)samp[V3_SK(base - 4)];
-        p1 = a1 - a2; p2 = p1 - (a2 - a3); p3 = p2 - ((a2 - a3) - (a3 - a4));
-        prev = a1;
-    }
+    u32 prev, p1, p2, p3;
+    v3_fixed_history(samp, base, prev, p1, p2, p3);
     u32 acc = 0, head = 0;
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
         const int4 va = *(const int4*)(samp + V3_SK(i0));
@@ -337,6 +377,7 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
         if (lane == 0) sh.lpc_narrow = sumq;     // turned into the flag once wasted bits are known
     }
     if (tid < 2) sh.bits[tid] = 0ull;
+    if (tid < 5) sh.totF[tid] = 0ull;
 
     // ---- load, constant check, wasted bits (flac.c:691-724) ----
     u32 orv = 0, diff = 0;
@@ -348,7 +389,25 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
             const uint8_t* src = pcm + d.pcm_off * 4;
             if ((((uintptr_t)src) & 15) == 0) {
                 const uint4* s4 = (const uint4*)src;
-                for (u32 i = tid * 4; i < n; i += nt * 4) {
+                // all the loads of a batch are issued before the first is used: one memory latency
+                // per batch of 8 x 16 bytes, not per load
+                const u32 stride = nt * 4;
+                u32 i = tid * 4;
+                for (; i + 7 * stride < n; i += 8 * stride) {
+                    uint4 w8[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) w8[q] = __ldg(s4 + ((i + q * stride) >> 2));
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        int4 v;
+                        v.x = __dp2a_lo((int)w8[q].x, coef, 0) >> shv; v.y = __dp2a_lo((int)w8[q].y, coef, 0) >> shv;
+                        v.z = __dp2a_lo((int)w8[q].z, coef, 0) >> shv; v.w = __dp2a_lo((int)w8[q].w, coef, 0) >> shv;
+                        *(int4*)(samp + V3_SK(i + q * stride)) = v;
+                        orv |= (u32)(v.x | v.y | v.z | v.w);
+                        diff |= (u32)((v.x ^ first) | (v.y ^ first) | (v.z ^ first) | (v.w ^ first));
+                    }
+                }
+                for (; i < n; i += stride) {
                     const uint4 w4 = __ldg(s4 + (i >> 2));
                     int4 v;
                     v.x = __dp2a_lo((int)w4.x, coef, 0) >> shv; v.y = __dp2a_lo((int)w4.y, coef, 0) >> shv;
@@ -380,14 +439,14 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
     orv = 0; diff = 0;
     for (u32 w = 0; w < nw; w++) { orv |= sh.red_or[w]; diff |= sh.red_diff[w]; }
 
-    b200flac_plan plan;
-    plan.type = BF_VERBATIM; plan.order = 0; plan.wasted = 0; plan.precision = 0; plan.shift = 0;
-    plan.coding_method = 0; plan.partition_order = 0; plan.flags = 0; plan.bits = 0;
-#pragma unroll
-    for (int i = 0; i < BF_MAX_ORDER; i++) plan.coeffs[i] = 0;
     if (diff == 0) {
         // CONSTANT, always written with wasted = 0 (H8)
-        if (tid == 0) { plan.type = BF_CONSTANT; plan.bits = 8 + bps; plans[unit] = plan; }
+        if (tid == 0) {
+            b200flac_plan plan;
+            memset(&plan, 0, sizeof(plan));
+            plan.type = BF_CONSTANT; plan.bits = 8 + bps;
+            plans[unit] = plan;
+        }
         return;
     }
     const u32 wasted = orv ? (u32)(__ffs((int)orv) - 1) : 0u;
@@ -402,19 +461,30 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
     {
         if (sub_bps <= 23) {
             u32 e[5];
-            if (tid == 0) v3_fixed_sums<u32, true>(samp, base, S, e, sh.corr);
-            else v3_fixed_sums<u32, false>(samp, base, S, e, nullptr);
+            v3_fixed_sums<u32>(samp, base, S, e);
+            if (tid == 0) v3_fixed_head<u32>(samp, e, sh.corr);
 #pragma unroll
-            for (int k = 0; k < 5; k++) runsF[k * nt + tid] = (u64)e[k];
+            for (int k = 0; k < 5; k++) {
+                runsF[k * nt + tid] = (u64)e[k];
+                const u32 ws = __reduce_add_sync(0xFFFFFFFFu, e[k]);     // 32 runs x 2^26: fits
+                if (lane == 0) atomicAdd(&sh.totF[k], (u64)ws);
+            }
         } else {
             u64 e[5];
-            if (tid == 0) v3_fixed_sums<u64, true>(samp, base, S, e, sh.corr);
-            else v3_fixed_sums<u64, false>(samp, base, S, e, nullptr);
+            v3_fixed_sums<u64>(samp, base, S, e);
+            if (tid == 0) v3_fixed_head<u64>(samp, e, sh.corr);
 #pragma unroll
-            for (int k = 0; k < 5; k++) runsF[k * nt + tid] = e[k];
+            for (int k = 0; k < 5; k++) {
+                runsF[k * nt + tid] = e[k];
+                u64 ws = e[k];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) ws += __shfl_xor_sync(0xFFFFFFFFu, ws, o);
+                if (lane == 0) atomicAdd(&sh.totF[k], ws);
+            }
         }
     }
     const u32 lpc_order = sh.head.best_order, precision = sh.head.precision;
+    bool lpc_narrow;
     const int lpc_shift = sh.head.shift[lpc_order - 1];
     {
         const bool narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
@@ -427,41 +497,38 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
                           : v3_lpc_residual<32, true>(samp, resid, base, S, sh.q, lpc_shift);
         if (tid == 0) for (u32 i = 0; i < lpc_order; i++) run -= (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions
         runsL[tid] = run;
-        if (tid == 0) plan.flags = narrow ? 2 : 0;   // packer may accumulate in 32 bits
+        lpc_narrow = narrow;
     }
     __syncthreads();                                                             // (2)
 
-    // ---- the two Rice searches, one warp each ----
-    const u32 wF = 0, wL = nw > 1 ? 1u : 0u;
-    if (warp == wF) {
-        // order choice: first strict minimum of the block totals (flac.c:877-893)
-        u64 tot[5];
+    // ---- FIXED order: first strict minimum of the block totals (flac.c:877-893) ----
+    u32 fixed_order = 0;
+    {
+        u64 best = sh.totF[0];
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            u64 a = 0;
-            for (u32 t = lane; t < nt; t += 32) a += runsF[k * nt + t];
-#pragma unroll
-            for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-            tot[k] = a;
-        }
-        u32 fo = 0;
-        u64 best = tot[0];
-        if (tot[1] < best) { best = tot[1]; fo = 1; }
-        if (tot[2] < best) { best = tot[2]; fo = 2; }
-        if (tot[3] < best) { best = tot[3]; fo = 3; }
-        if (tot[4] < best) { best = tot[4]; fo = 4; }
-        u64* runs = runsF + (size_t)fo * nt;
-        if (lane == 0) runs[0] += sh.corr[fo];
-        __syncwarp();
-        v3_search(runs, nt, S, n, fo, F, P.max_rice, sh.kheap[0], sh.lvl_tot[0], sh.lvl_cnt[0], sh.lvl_maxk[0], &sh.dec[0]);
+        for (int k = 1; k < 5; k++) { const u64 t = sh.totF[k]; if (t < best) { best = t; fixed_order = k; } }
     }
-    if (warp == wL) {
-        v3_search(runsL, nt, S, n, lpc_order, F, P.max_rice, sh.kheap[1], sh.lvl_tot[1], sh.lvl_cnt[1], sh.lvl_maxk[1], &sh.dec[1]);
+    // ---- the two Rice searches as four warp tasks (model x part, see v3_levels); the tasks rotate
+    // over the warps with the unit so that no scheduler always gets the extra work ----
+    {
+        const u32 role = (warp + nw - unit % nw) % nw;
+        for (u32 task = role; task < 4; task += nw) {
+            // prefix sums go to the run-sum rows of two FIXED orders that lost
+            if (task < 2)
+                v3_levels(runsF + (size_t)fixed_order * nt, sh.corr[fixed_order], S, n, fixed_order, F, P.max_rice,
+                          sh.kheap[0], sh.lvl[0], runsF + (size_t)((fixed_order + 1) % 5) * nt, task);
+            else
+                v3_levels(runsL, 0ull, S, n, lpc_order, F, P.max_rice,
+                          sh.kheap[1], sh.lvl[1], runsF + (size_t)((fixed_order + 2) % 5) * nt, task - 2);
+        }
     }
     __syncthreads();                                                             // (3)
 
     // ---- pass B: exact bits of both models ----
-    const u32 poF = sh.dec[0].po, poL = sh.dec[1].po, fixed_order = sh.dec[0].order;
+    u32 poF, poL, methodF, methodL;
+    u64 sideF, sideL;
+    v3_pick_level(sh.lvl[0], F, &poF, &methodF, &sideF);
+    v3_pick_level(sh.lvl[1], F, &poL, &methodL, &sideL);
     {
         const u32 kF = sh.kheap[0][(1u << poF) - 1u + base / (n >> poF)];
         const u32 kL = sh.kheap[1][(1u << poL) - 1u + base / (n >> poL)];
@@ -475,34 +542,38 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
     __syncthreads();                                                             // (4)
 
     // ---- choice, flac.c:727-809 (every subframe type enabled) ----
-    const u64 fixed_bits = hdr_bits + (u64)fixed_order * sub_bps + sh.dec[0].side_bits + sh.bits[0];
-    const u64 lpc_bits = hdr_bits + (u64)lpc_order * sub_bps + 4 + 5 + (u64)lpc_order * precision + sh.dec[1].side_bits + sh.bits[1];
+    const u64 fixed_bits = hdr_bits + (u64)fixed_order * sub_bps + sideF + sh.bits[0];
+    const u64 lpc_bits = hdr_bits + (u64)lpc_order * sub_bps + 4 + 5 + (u64)lpc_order * precision + sideL + sh.bits[1];
     const u32 fb = (u32)fixed_bits, lb = (u32)lpc_bits;
     const u32 vb = sub_bps * n;                       // header NOT counted (H2)
     const u32 choice = (fb < min(lb, vb)) ? BF_FIXED : (lb < vb) ? BF_LPC : BF_VERBATIM;
     uint8_t* my_rice = rice_out + (size_t)unit * P.rice_stride;
-    plan.wasted = (uint8_t)wasted;
     if (choice == BF_FIXED) {
         const u32 koff = (1u << poF) - 1u;
         for (u32 p = tid; p < (1u << poF); p += nt) my_rice[p] = sh.kheap[0][koff + p];
-        if (tid == 0) {
-            plan.type = BF_FIXED; plan.order = (uint8_t)fixed_order;
-            plan.coding_method = (uint8_t)sh.dec[0].method; plan.partition_order = (uint8_t)poF;
-            plan.flags = 0; plan.bits = fb;
-        }
     } else if (choice == BF_LPC) {
         const u32 koff = (1u << poL) - 1u;
         for (u32 p = tid; p < (1u << poL); p += nt) my_rice[p] = sh.kheap[1][koff + p];
-        if (tid == 0) {
+    }
+    if (tid == 0) {
+        b200flac_plan plan;
+        memset(&plan, 0, sizeof(plan));
+        plan.wasted = (uint8_t)wasted;
+        if (choice == BF_FIXED) {
+            plan.type = BF_FIXED; plan.order = (uint8_t)fixed_order;
+            plan.coding_method = (uint8_t)methodF; plan.partition_order = (uint8_t)poF;
+            plan.bits = fb;
+        } else if (choice == BF_LPC) {
             plan.type = BF_LPC; plan.order = (uint8_t)lpc_order;
             plan.precision = (uint8_t)precision; plan.shift = (int8_t)lpc_shift;
-            plan.coding_method = (uint8_t)sh.dec[1].method; plan.partition_order = (uint8_t)poL;
+            plan.coding_method = (uint8_t)methodL; plan.partition_order = (uint8_t)poL;
+            plan.flags = lpc_narrow ? 2 : 0;          // packer may accumulate in 32 bits
             plan.bits = lb;
             for (u32 j = 0; j < lpc_order; j++) plan.coeffs[j] = sh.q[j];
+        } else {
+            plan.type = BF_VERBATIM;
+            plan.bits = hdr_bits + sub_bps * n;       // flac.c:832-854
         }
-    } else if (tid == 0) {
-        plan.type = BF_VERBATIM; plan.flags = 0;
-        plan.bits = hdr_bits + sub_bps * n;           // flac.c:832-854
+        plans[unit] = plan;
     }
-    if (tid == 0) plans[unit] = plan;
 }
