@@ -35,9 +35,10 @@ struct V3Level {
 
 struct V3Shared {
     V3Level lvl[2][V3_MAX_F + 1];
-    u64 totF[5];          // FIXED: block totals of the error sums (flac.c:877-893)
+    u64 totF[5];          // FIXED: block totals of the error sums (flac.c:877-893), wide blocks
+    u32 totF16[5][2];     // ... narrow blocks: sums of the low 16 bits / the rest of the warp sums
+    u32 bits16[2][2];     // exact sum of (u >> k), per model, split the same way
     u64 corr[5];          // FIXED: sum of |r_k[i]| for k <= i < 4 (in the partition sums, not in the order choice)
-    u64 bits[2];          // exact sum of (u >> k) over the block, per model
     u32 red_or[16], red_diff[16];
     u32 lpc_narrow;       // LPC sum provably fits 32 bits
     short q[BF_MAX_ORDER];
@@ -158,15 +159,16 @@ __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_e
     }
 }
 
-// every thread: first strict minimum of the estimates over the partition orders (flac.c:1365-1400)
+// every warp: first strict minimum of the estimates over the partition orders (flac.c:1365-1400);
+// lane l looks at order l, the minimum of (estimate, order) pairs is taken with two warp reductions
 __device__ __forceinline__ void v3_pick_level(const V3Level* lvl, u32 F, u32* po_out, u32* method_out, u64* side_bits)
 {
-    u64 best = lvl[0].tot;
-    u32 po = 0;
-    for (u32 l = 1; l <= F; l++) {
-        const u64 tot = lvl[l].tot;
-        if (tot < best) { best = tot; po = l; }
-    }
+    const u32 lane = threadIdx.x & 31;
+    const u64 tot = lane <= F ? lvl[lane].tot : ~0ull;
+    const u32 hi = (u32)(tot >> 32), lo = (u32)tot;
+    const u32 mhi = __reduce_min_sync(0xFFFFFFFFu, hi);
+    const u32 mlo = __reduce_min_sync(0xFFFFFFFFu, hi == mhi ? lo : 0xFFFFFFFFu);
+    const u32 po = __reduce_min_sync(0xFFFFFFFFu, (hi == mhi && lo == mlo) ? lane : 32u);
     const u32 maxk = lvl[po].maxk;
     *po_out = po;
     *method_out = maxk > 14 ? 1u : 0u;
@@ -376,8 +378,8 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
         const u32 sumq = __reduce_add_sync(0xFFFFFFFFu, (u32)abs(q));
         if (lane == 0) sh.lpc_narrow = sumq;     // turned into the flag once wasted bits are known
     }
-    if (tid < 2) sh.bits[tid] = 0ull;
-    if (tid < 5) sh.totF[tid] = 0ull;
+    if (tid < 5) { sh.totF[tid] = 0ull; sh.totF16[tid][0] = 0u; sh.totF16[tid][1] = 0u; }
+    if (tid < 4) sh.bits16[tid >> 1][tid & 1] = 0u;
 
     // ---- load, constant check, wasted bits (flac.c:691-724) ----
     u32 orv = 0, diff = 0;
@@ -466,8 +468,10 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 runsF[k * nt + tid] = (u64)e[k];
-                const u32 ws = __reduce_add_sync(0xFFFFFFFFu, e[k]);     // 32 runs x 2^26: fits
-                if (lane == 0) atomicAdd(&sh.totF[k], (u64)ws);
+                // 32 runs x 2^26 fit 32 bits; the two halves are summed over <= 16 warps with native
+                // 32-bit shared atomics (a 64-bit one is a compare-and-swap loop)
+                const u32 ws = __reduce_add_sync(0xFFFFFFFFu, e[k]);
+                if (lane == 0) { atomicAdd(&sh.totF16[k][0], ws & 0xFFFFu); atomicAdd(&sh.totF16[k][1], ws >> 16); }
             }
         } else {
             u64 e[5];
@@ -504,14 +508,17 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
     // ---- FIXED order: first strict minimum of the block totals (flac.c:877-893) ----
     u32 fixed_order = 0;
     {
-        u64 best = sh.totF[0];
+        u64 best = 0;
 #pragma unroll
-        for (int k = 1; k < 5; k++) { const u64 t = sh.totF[k]; if (t < best) { best = t; fixed_order = k; } }
+        for (int k = 0; k < 5; k++) {
+            const u64 t = sh.totF[k] + (u64)sh.totF16[k][0] + ((u64)sh.totF16[k][1] << 16);
+            if (k == 0 || t < best) { best = t; fixed_order = k; }
+        }
     }
     // ---- the two Rice searches as four warp tasks (model x part, see v3_levels); the tasks rotate
     // over the warps with the unit so that no scheduler always gets the extra work ----
     {
-        const u32 role = (warp + nw - unit % nw) % nw;
+        const u32 role = (nw & (nw - 1)) == 0 ? ((warp - unit) & (nw - 1)) : (warp + nw - unit % nw) % nw;
         for (u32 task = role; task < 4; task += nw) {
             // prefix sums go to the run-sum rows of two FIXED orders that lost
             if (task < 2)
@@ -537,13 +544,16 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
         // a warp's sum stays far below 2^32 (each run's is bounded by ~2 * partition length + 32 * 2^18)
         bF = __reduce_add_sync(0xFFFFFFFFu, bF);
         bL = __reduce_add_sync(0xFFFFFFFFu, bL);
-        if (lane == 0) { atomicAdd(&sh.bits[0], (u64)bF); atomicAdd(&sh.bits[1], (u64)bL); }
+        if (lane == 0) {
+            atomicAdd(&sh.bits16[0][0], bF & 0xFFFFu); atomicAdd(&sh.bits16[0][1], bF >> 16);
+            atomicAdd(&sh.bits16[1][0], bL & 0xFFFFu); atomicAdd(&sh.bits16[1][1], bL >> 16);
+        }
     }
     __syncthreads();                                                             // (4)
 
     // ---- choice, flac.c:727-809 (every subframe type enabled) ----
-    const u64 fixed_bits = hdr_bits + (u64)fixed_order * sub_bps + sideF + sh.bits[0];
-    const u64 lpc_bits = hdr_bits + (u64)lpc_order * sub_bps + 4 + 5 + (u64)lpc_order * precision + sideL + sh.bits[1];
+    const u64 fixed_bits = hdr_bits + (u64)fixed_order * sub_bps + sideF + (u64)sh.bits16[0][0] + ((u64)sh.bits16[0][1] << 16);
+    const u64 lpc_bits = hdr_bits + (u64)lpc_order * sub_bps + 4 + 5 + (u64)lpc_order * precision + sideL + (u64)sh.bits16[1][0] + ((u64)sh.bits16[1][1] << 16);
     const u32 fb = (u32)fixed_bits, lb = (u32)lpc_bits;
     const u32 vb = sub_bps * n;                       // header NOT counted (H2)
     const u32 choice = (fb < min(lb, vb)) ? BF_FIXED : (lb < vb) ? BF_LPC : BF_VERBATIM;
