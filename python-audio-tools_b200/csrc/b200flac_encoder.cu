@@ -22,6 +22,7 @@
 #include "k_analyze_v2.cuh"
 #include "k_analyze_v3.cuh"
 #include "k_pack_v2.cuh"
+#include "k_pack_v3.cuh"
 #include "k_synth.cuh"
 
 #define BF_MAX_SEGMENTS 65536
@@ -100,6 +101,10 @@ struct b200flac_encoder {
     bool fast;            // the shared-memory resident kernels (k_analyze_v2 / k_pack_v2) apply
     u32 stage_words;      // shared-memory image of one subframe, in words (k_pack_v2)
     bool v3;              // k_analyze_v3 applies to the full-length blocks
+    bool p3;              // k_pack_v3 (whole frame per CTA, CRC-16 fused) applies
+    u32 p3_img_words;
+    size_t p3_smem;
+    unsigned short* d_crc_tab;   // [256] byte table + [69 + n] powers of x (see k_pack_v3)
     u32 v3_S, v3_F, v3_NT;
     size_t v3_smem;
     std::map<u32, std::vector<double>>* windows;
@@ -270,6 +275,7 @@ extern "C" void b200flac_encoder_destroy(b200flac_encoder* enc)
         for (int i = 0; i < enc->n_slots; i++) free_slot(enc->slots[i]);
         delete[] enc->slots;
     }
+    cudaFree(enc->d_crc_tab);
     delete enc->windows;
     delete enc;
 }
@@ -407,6 +413,45 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         sa = 2 * padn * 4 + 8 + (size_t)P.heap_entries * 9 + 2 * (size_t)P.rice_stride + 16;
         sp = 2 * padn * 4 + (size_t)enc->stage_words * 4 + 16;
         if (sa > 200 * 1024 || sp > 200 * 1024) enc->fast = false;
+    }
+    enc->p3 = false;
+    enc->d_crc_tab = nullptr;
+    if (enc->fast && !(getenv("B200FLAC_NO_P3") && getenv("B200FLAC_NO_P3")[0] == '1')) {
+        const u64 fb = frame_bound_bytes(params, bs);
+        const u32 iw = (u32)((fb + 3) / 4 + 2);
+        const size_t sm = p3_smem_bytes(bs, iw);
+        if (sm <= 200 * 1024 && 2 * enc->NT <= 1024) {
+            enc->p3 = true; enc->p3_img_words = iw; enc->p3_smem = sm;
+            // CRC-16 tables: byte table, x^(8 r) for r <= 68, x^(8 * 68 * j)
+            const u32 nchunks = (u32)(fb / P3_CHUNK_BYTES + 4);
+            std::vector<unsigned short> t(256 + 69 + nchunks);
+            for (u32 b = 0; b < 256; b++) {
+                u32 c = b << 8;
+                for (int k = 0; k < 8; k++) c = (c & 0x8000) ? ((c << 1) ^ 0x8005) & 0xFFFF : (c << 1) & 0xFFFF;
+                t[b] = (unsigned short)c;
+            }
+            auto mul = [](u32 a, u32 b) {
+                u32 r = 0;
+                for (int i = 0; i < 16; i++) if ((b >> i) & 1u) r ^= a << i;
+                for (int i = 30; i >= 16; i--) if ((r >> i) & 1u) r ^= 0x18005u << (i - 16);
+                return r;
+            };
+            u32 x8 = 0x100, acc = 1;                 // x^8
+            for (u32 r = 0; r <= 68; r++) { t[256 + r] = (unsigned short)acc; acc = mul(acc, x8); }
+            const u32 xc = t[256 + 68];              // x^(8 * 68)
+            acc = 1;
+            for (u32 j = 0; j < nchunks; j++) { t[256 + 69 + j] = (unsigned short)acc; acc = mul(acc, xc); }
+            if (cudaMalloc((void**)&enc->d_crc_tab, t.size() * sizeof(unsigned short)) != cudaSuccess ||
+                cudaMemcpy(enc->d_crc_tab, t.data(), t.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess) {
+                enc->p3 = false;
+            } else {
+                e = 2 * enc->NT <= 384
+                        ? cudaFuncSetAttribute(k_pack_v3<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+                        : cudaFuncSetAttribute(k_pack_v3<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                if (e != cudaSuccess) enc->p3 = false;
+                e = cudaSuccess;
+            }
+        }
     }
     if (enc->fast) {
         enc->smem_analyze = sa;
@@ -664,6 +709,21 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
     cudaEventRecord(s.ev[2], st);
     k_frame_select<<<(nf + 127) / 128, 128, 0, st>>>(s.d_fd, nf, P, s.d_plans, s.d_choice, s.d_frame_bytes);
     k_scan_offsets<<<1, 1024, 0, st>>>(s.d_frame_bytes, nf, s.d_frame_off, s.d_total);
+    if (enc->p3) {
+        cudaEventRecord(s.ev[3], st);
+        if (2 * enc->NT <= 384)
+            k_pack_v3<384, 2><<<nf, 2 * enc->NT, enc->p3_smem, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
+                                                                     s.d_frame_off, d_out, s.d_total, out_cap, enc->p3_img_words,
+                                                                     enc->d_crc_tab, enc->d_crc_tab + 256);
+        else
+            k_pack_v3<1024, 1><<<nf, 2 * enc->NT, enc->p3_smem, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
+                                                                      s.d_frame_off, d_out, s.d_total, out_cap, enc->p3_img_words,
+                                                                      enc->d_crc_tab, enc->d_crc_tab + 256);
+        cudaEventRecord(s.ev[4], st);
+        cudaEventRecord(s.ev[5], st);
+        enc->launches += 3 + (gridv2 ? 1 : 0);
+        return;
+    }
     k_zero_output<<<148 * 4, 256, 0, st>>>((uint4*)d_out, s.d_total, out_cap);
     cudaEventRecord(s.ev[3], st);
     if (enc->NT <= 192)

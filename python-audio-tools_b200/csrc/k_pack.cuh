@@ -135,7 +135,8 @@ __device__ __forceinline__ void put_subframe_header(BitSink& bs, u32 type_bits, 
 }
 
 // frame header, flac.c:488-517, with its CRC-8
-__device__ void put_frame_header(BitSink& bs, const bf_frame_desc& d, const bf_dev_params& P, u32 assignment)
+template <class Sink>
+__device__ void put_frame_header(Sink& bs, const bf_frame_desc& d, const bf_dev_params& P, u32 assignment)
 {
     uint8_t h[16];
     u32 nb = 0;

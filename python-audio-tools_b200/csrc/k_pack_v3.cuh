@@ -1,0 +1,435 @@
+// k_pack_v3.cuh -- frame packing: one CTA builds a WHOLE frame in shared memory and writes it out.
+//
+// Same bytes as k_pack_v2 + k_frame_crc16 (and the reference: frame header + CRC-8 flac.c:412-518,
+// subframes :813-854, 897-915, 977-1015, Rice coding :1406-1434, CRC-16 :530,668-670).  What differs:
+//   * the CTA is two thread groups, each packing one subframe at a time into a shared-memory image
+//     of the frame at its final bit offset (the subframe sizes are known from the analysis);
+//   * the chosen model's residual is computed IN PLACE over the samples (history first, then a group
+//     barrier), zig-zag folded and bit-counted in the same pass;
+//   * the frame's CRC-16 is computed from the image: 68-byte chunks (17 words: consecutive threads
+//     hit different banks), one table CRC per thread, chunk results moved to their position with one
+//     GF(2) multiply by a tabulated power of x, XOR-reduced;
+//   * the finished frame goes to its byte offset in the output with coalesced 32-bit stores (a byte
+//     permute handles both the byte order and the misalignment), head and tail bytes singly: no
+//     zeroing of the output, no global atomics, no separate CRC kernel.
+#pragma once
+#include "flac_common.cuh"
+#include "k_pack.cuh"
+#include "k_pack_v2.cuh"
+#include "k_analyze_v3.cuh"
+
+#define P3_CHUNK_WORDS 17
+#define P3_CHUNK_BYTES 68
+
+__device__ __forceinline__ void p3_group_bar(u32 g, u32 gt)
+{
+    asm volatile("bar.sync %0, %1;\n" ::"r"(g + 1), "r"(gt) : "memory");
+}
+
+// exclusive prefix sum of one u32 per thread over a group of gt threads; red: >= 16 words of the group
+__device__ __forceinline__ u32 p3_group_exscan(u32 v, u32* red, u32 g, u32 gt, u32 gtid, u32* total)
+{
+    const u32 lane = gtid & 31, warp = gtid >> 5, nw = gt >> 5;
+    u32 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (u32)o) inc += t;
+    }
+    if (lane == 31) red[warp] = inc;
+    p3_group_bar(g, gt);
+    u32 off = 0, tot = 0;
+    for (u32 w = 0; w < nw; w++) { const u32 t = red[w]; off += w < warp ? t : 0u; tot += t; }
+    p3_group_bar(g, gt);
+    *total = tot;
+    return off + inc - v;
+}
+
+struct P3Shared {
+    b200flac_plan plan[2];
+    bf_frame_choice choice;
+    u32 red[2][16];
+    short q[2][BF_MAX_ORDER];
+    u32 crc_part[32];
+    u32 crc_last;
+};
+
+// residual of the chosen model over the thread's run, in place, zig-zag folded; returns the run's
+// bit count.  The caller has already read what it needs from the samples that other threads overwrite.
+struct P3Count {
+    u32 lo, hi, plen, kbits, under, order;
+    const uint8_t* krice;
+};
+
+__device__ __forceinline__ void p3_count_chunk(const u32 (&u)[8], u32 i0, const P3Count& c, u32& p, u32& next, u32& k, u32& mybits)
+{
+    if (i0 >= c.lo && i0 + 8 <= c.hi && i0 + 8 <= next) {
+        u32 a = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) a += u[j] >> k;
+        mybits += a + 8 * (1u + k);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const u32 i = i0 + j;
+            if (i >= c.lo && i < c.hi) {
+                if (i == next) { p++; next += c.plen; k = c.krice[p]; mybits += c.kbits; }
+                mybits += (u[j] >> k) + 1u + k;
+            }
+        }
+    }
+    if (i0 + 8 == next && i0 + 8 < c.hi) { p++; next += c.plen; k = c.krice[p]; mybits += c.kbits; }
+}
+
+template <int OG, bool WIDE>
+__device__ __forceinline__ u32 p3_lpc_inplace(int* __restrict__ buf, u32 base, u32 end, const short* q_sm, int shift,
+                                              const P3Count& c, u32 p, u32 next, u32 k, u32 g, u32 gt)
+{
+    int q[OG];
+#pragma unroll
+    for (int t = 0; t < OG; t++) q[t] = q_sm[t];
+    int w[OG + 8];
+#pragma unroll
+    for (int t = 0; t < OG; t += 4) {
+        int4 h = make_int4(0, 0, 0, 0);
+        if (base < end && base >= (u32)(OG - t)) h = *(const int4*)(buf + V3_SK(base - (OG - t)));
+        w[t] = h.x; w[t + 1] = h.y; w[t + 2] = h.z; w[t + 3] = h.w;
+    }
+    p3_group_bar(g, gt);          // every thread holds its history: the samples may be overwritten now
+    u32 mybits = 0;
+    for (u32 i0 = base; i0 < end; i0 += 8) {
+        const int4 va = *(const int4*)(buf + V3_SK(i0));
+        const int4 vb = *(const int4*)(buf + V3_SK(i0) + 4);
+        w[OG + 0] = va.x; w[OG + 1] = va.y; w[OG + 2] = va.z; w[OG + 3] = va.w;
+        w[OG + 4] = vb.x; w[OG + 5] = vb.y; w[OG + 6] = vb.z; w[OG + 7] = vb.w;
+        u32 u[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int pred;
+            if (WIDE) {
+                long long acc = 0;
+#pragma unroll
+                for (int t = 0; t < OG; t++) acc += (long long)q[t] * (long long)w[OG + j - 1 - t];
+                pred = (int)(acc >> shift);
+            } else {
+                int acc = 0;
+#pragma unroll
+                for (int t = 0; t < OG; t++) acc += q[t] * w[OG + j - 1 - t];
+                pred = acc >> shift;
+            }
+            u[j] = zigzag((int)((u32)w[OG + j] - (u32)pred));
+        }
+        *(uint4*)(buf + V3_SK(i0)) = make_uint4(u[0], u[1], u[2], u[3]);
+        *(uint4*)(buf + V3_SK(i0) + 4) = make_uint4(u[4], u[5], u[6], u[7]);
+        p3_count_chunk(u, i0, c, p, next, k, mybits);
+#pragma unroll
+        for (int t = 0; t < OG; t++) w[t] = w[t + 8];
+    }
+    return mybits;
+}
+
+__device__ __forceinline__ u32 p3_fixed_inplace(int* __restrict__ buf, u32 base, u32 end, u32 order,
+                                                const P3Count& c, u32 p, u32 next, u32 k, u32 g, u32 gt)
+{
+    u32 prev, p1, p2, p3;
+    v3_fixed_history(buf, base < end ? base : 0u, prev, p1, p2, p3);
+    p3_group_bar(g, gt);
+    u32 mybits = 0;
+    for (u32 i0 = base; i0 < end; i0 += 8) {
+        const int4 va = *(const int4*)(buf + V3_SK(i0));
+        const int4 vb = *(const int4*)(buf + V3_SK(i0) + 4);
+        const int xs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        u32 u[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const u32 x = (u32)xs[j];
+            const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+            const u32 v = order == 0 ? x : order == 1 ? d1 : order == 2 ? d2 : order == 3 ? d3 : d4;
+            u[j] = zigzag((int)v);
+            prev = x; p1 = d1; p2 = d2; p3 = d3;
+        }
+        *(uint4*)(buf + V3_SK(i0)) = make_uint4(u[0], u[1], u[2], u[3]);
+        *(uint4*)(buf + V3_SK(i0) + 4) = make_uint4(u[4], u[5], u[6], u[7]);
+        p3_count_chunk(u, i0, c, p, next, k, mybits);
+    }
+    return mybits;
+}
+
+// host and device agree on the dynamic shared memory through this
+__host__ __device__ inline size_t p3_smem_bytes(u32 block_size, u32 img_words)
+{
+    const size_t padn = (size_t)V3_SK(block_size) + 40;
+    return 2 * padn * 4 + (size_t)(img_words + 4) * 4 + 512 + 32;
+}
+
+// blockDim.x = 2 * gt; gt * S >= block_size; S a multiple of 8.
+//   crc_tab[256]: CRC-16 of one byte; crc_pow[0..68] = x^(8 r), crc_pow[69 + j] = x^(8 * 68 * j) mod the
+//   CRC-16 polynomial (built by the host).
+template <int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB)
+k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S,
+          const b200flac_plan* __restrict__ plans, const uint8_t* __restrict__ rice,
+          const bf_frame_choice* __restrict__ choice, const u64* __restrict__ frame_off,
+          uint8_t* __restrict__ out, const u64* __restrict__ total, u64 capacity_bytes, u32 img_words,
+          const unsigned short* __restrict__ crc_tab, const unsigned short* __restrict__ crc_pow)
+{
+    if (*total + 16 > capacity_bytes) return;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ P3Shared sh;
+
+    const u32 tid = threadIdx.x, nt = blockDim.x, gt = nt >> 1;
+    const u32 g = tid / gt, gtid = tid - g * gt;
+    const u32 frame = blockIdx.x;
+    const size_t padn = (size_t)V3_SK(P.block_size) + 40;
+    int* buf = (int*)dyn_smem + (size_t)g * padn;
+    u32* img = (u32*)((int*)dyn_smem + 2 * padn);
+    unsigned short* tab = (unsigned short*)(img + img_words + 4);
+
+    if (tid == 0) sh.choice = choice[frame];
+    for (u32 t = tid; t < 256; t += nt) tab[t] = crc_tab[t];
+    const bf_frame_desc d = fd[frame];
+    const u32 n = d.nsamp;
+    __syncthreads();
+    const u32 frame_bytes = sh.choice.frame_bytes, n_sub = sh.choice.n_sub;
+    const u32 nwords = (frame_bytes + 3) >> 2;
+    if (nwords + 2 > img_words + 4) __trap();    // cannot happen: the image is sized for the largest frame
+    for (u32 w = tid; w < nwords + 2; w += nt) img[w] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        SmemSink hs; hs.init(img, 0);
+        put_frame_header(hs, d, P, sh.choice.assignment);
+        hs.flush();
+    }
+
+    const u32 base = gtid * S;
+    const u32 end = min(base + S, n);
+    for (u32 slot0 = 0; slot0 < n_sub; slot0 += 2) {
+        const u32 slot = slot0 + g;
+        if (slot >= n_sub) break;                // this group is done (group-uniform)
+        const u32 unit = sh.choice.unit[slot];
+        const u32 cand = unit % P.K;
+        const u32 bps = candidate_bps(cand, P);
+        const u32 bit0 = sh.choice.bitoff[slot];
+        const uint8_t* krice = rice + (size_t)unit * P.rice_stride;
+        if (gtid == 0) sh.plan[g] = plans[unit];
+
+        // ---- samples of the candidate, coalesced ----
+        if (P.stereo && P.bytes_ps == 2) {
+            const int coef = cand == 0 ? 0x0001 : cand == 1 ? 0x0100 : cand == 2 ? 0x0101 : 0xFF01;
+            const int shv = cand == 2 ? 1 : 0;
+            const uint8_t* src = pcm + d.pcm_off * 4;
+            if ((((uintptr_t)src) & 15) == 0 && (n & 3) == 0) {
+                const uint4* s4 = (const uint4*)src;
+                const u32 stride = gt * 4;
+                u32 i = gtid * 4;
+                for (; i + 3 * stride < n; i += 4 * stride) {
+                    uint4 w4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) w4[q] = __ldg(s4 + ((i + q * stride) >> 2));
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        int4 v;
+                        v.x = __dp2a_lo((int)w4[q].x, coef, 0) >> shv; v.y = __dp2a_lo((int)w4[q].y, coef, 0) >> shv;
+                        v.z = __dp2a_lo((int)w4[q].z, coef, 0) >> shv; v.w = __dp2a_lo((int)w4[q].w, coef, 0) >> shv;
+                        *(int4*)(buf + V3_SK(i + q * stride)) = v;
+                    }
+                }
+                for (; i < n; i += stride) {
+                    const uint4 w1 = __ldg(s4 + (i >> 2));
+                    int4 v;
+                    v.x = __dp2a_lo((int)w1.x, coef, 0) >> shv; v.y = __dp2a_lo((int)w1.y, coef, 0) >> shv;
+                    v.z = __dp2a_lo((int)w1.z, coef, 0) >> shv; v.w = __dp2a_lo((int)w1.w, coef, 0) >> shv;
+                    *(int4*)(buf + V3_SK(i)) = v;
+                }
+            } else {
+                const u32* s1 = (const u32*)src;
+                for (u32 i = gtid; i < n; i += gt) buf[V3_SK(i)] = __dp2a_lo((int)__ldg(s1 + i), coef, 0) >> shv;
+            }
+        } else {
+            for (u32 i = gtid; i < n; i += gt) buf[V3_SK(i)] = ld_candidate(pcm, d.pcm_off + i, cand, P);
+        }
+        p3_group_bar(g, gt);
+        const u32 ptype = sh.plan[g].type, wasted = sh.plan[g].wasted, order = sh.plan[g].order;
+        const u32 sub_bps = bps - wasted;
+
+        if (ptype == BF_CONSTANT) {
+            if (gtid == 0) {
+                SmemSink bs; bs.init(img, bit0);
+                put_subframe_header_s(bs, 0, 0);
+                bs.put_signed(buf[0], bps);
+                bs.flush();
+            }
+        } else {
+            if (wasted) for (u32 i = gtid; i < n; i += gt) buf[V3_SK(i)] >>= wasted;
+            if (ptype == BF_LPC && gtid < BF_MAX_ORDER) sh.q[g][gtid] = gtid < order ? sh.plan[g].coeffs[gtid] : (short)0;
+            p3_group_bar(g, gt);
+            if (ptype == BF_VERBATIM) {
+                if (gtid == 0) {
+                    SmemSink bs; bs.init(img, bit0);
+                    put_subframe_header_s(bs, 1, wasted);
+                    bs.flush();
+                }
+                if (base < n) {
+                    RunSink bs; bs.init(img, bit0 + 8 + wasted + base * sub_bps);
+                    const u32 mask = sub_bps >= 32 ? 0xFFFFFFFFu : ((1u << sub_bps) - 1u);
+                    for (u32 i = base; i < end; i++) bs.put((u32)buf[V3_SK(i)] & mask, sub_bps);
+                    bs.finish();
+                }
+            } else {
+                const u32 po = sh.plan[g].partition_order, under = sh.plan[g].flags & 1u, narrow = sh.plan[g].flags & 2u;
+                const u32 plen = n >> po;
+                const u32 kbits = sh.plan[g].coding_method ? 5u : 4u;
+                u32 hdr_end = bit0 + 8 + wasted + order * sub_bps;
+                if (ptype == BF_LPC) hdr_end += 4 + 5 + order * sh.plan[g].precision;
+                if (gtid == 0) {
+                    // header and warm-up samples: read before anyone passes the barrier below
+                    SmemSink bs; bs.init(img, bit0);
+                    if (ptype == BF_FIXED) put_subframe_header_s(bs, 0x8 | order, wasted);
+                    else put_subframe_header_s(bs, 0x20 | (order - 1), wasted);
+                    for (u32 i = 0; i < order; i++) bs.put_signed(buf[V3_SK(i)], sub_bps);
+                    if (ptype == BF_LPC) {
+                        bs.put(sh.plan[g].precision - 1, 4);
+                        bs.put_signed(sh.plan[g].shift, 5);
+                        for (u32 i = 0; i < order; i++) bs.put_signed(sh.plan[g].coeffs[i], sh.plan[g].precision);
+                    }
+                    bs.put(sh.plan[g].coding_method, 2);
+                    bs.put(po, 4);
+                    bs.flush();
+                }
+                const u32 res0 = hdr_end + 6;
+                const int shift = sh.plan[g].shift;
+
+                // ---- residual in place + bit count of the run ----
+                P3Count c;
+                c.lo = max(base, order); c.hi = end; c.plen = plen; c.kbits = kbits; c.under = under; c.order = order;
+                c.krice = krice;
+                const bool have = c.lo < c.hi;
+                const u32 p_first = (have && !under) ? c.lo / plen : 0u;
+                u32 lead = 0;
+                if (have) {
+                    if (c.lo == order) lead = under ? 1u : (c.lo / plen + 1u);    // partitions 0..p_first (an empty leading one too)
+                    else if (!under && c.lo == p_first * plen) lead = 1;
+                }
+                const u32 next0 = under ? 0xFFFFFFFFu : (p_first + 1) * plen;
+                const u32 k0 = have ? (u32)krice[p_first] : 0u;
+                const u32 rend = base < n ? end : base;   // threads past the block only take part in the barriers
+                u32 mybits;
+                if (ptype == BF_FIXED) mybits = p3_fixed_inplace(buf, base, rend, order, c, p_first, next0, k0, g, gt);
+                else if (order <= 12) mybits = narrow ? p3_lpc_inplace<12, false>(buf, base, rend, sh.q[g], shift, c, p_first, next0, k0, g, gt)
+                                                      : p3_lpc_inplace<12, true>(buf, base, rend, sh.q[g], shift, c, p_first, next0, k0, g, gt);
+                else mybits = narrow ? p3_lpc_inplace<32, false>(buf, base, rend, sh.q[g], shift, c, p_first, next0, k0, g, gt)
+                                     : p3_lpc_inplace<32, true>(buf, base, rend, sh.q[g], shift, c, p_first, next0, k0, g, gt);
+                mybits = have ? mybits + lead * kbits : 0u;
+
+                u32 totalbits;
+                const u32 off = p3_group_exscan(mybits, sh.red[g], g, gt, gtid, &totalbits);
+                if (have) {
+                    RunSink bs; bs.init(img, res0 + off);
+                    if (c.lo == order) { for (u32 q = 0; q < lead; q++) bs.put(krice[q], kbits); }
+                    else if (lead) bs.put(krice[p_first], kbits);
+                    u32 p = p_first;
+                    u32 next = next0;
+                    u32 k = k0;
+                    for (u32 i0 = c.lo & ~7u; i0 < c.hi; i0 += 8) {
+                        const uint4 ua = *(const uint4*)(buf + V3_SK(i0));
+                        const uint4 ub = *(const uint4*)(buf + V3_SK(i0) + 4);
+                        const u32 us[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+                        if (i0 >= c.lo && i0 + 8 <= c.hi && i0 + 8 <= next) {
+                            const u32 kmask = (1u << k) - 1u, kone = 1u << k;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const u32 u = us[j];
+                                const u32 msb = u >> k;
+                                const u32 code = kone | (u & kmask);
+                                if (msb + k + 1 <= 32) bs.put(code, msb + k + 1);
+                                else { bs.zeros(msb); bs.put(code, k + 1); }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const u32 i = i0 + j;
+                                if (i >= c.lo && i < c.hi) {
+                                    if (i == next) { p++; next += plen; k = krice[p]; bs.put(k, kbits); }
+                                    const u32 u = us[j];
+                                    const u32 msb = u >> k;
+                                    const u32 code = (1u << k) | (u & ((1u << k) - 1u));
+                                    if (msb + k + 1 <= 32) bs.put(code, msb + k + 1);
+                                    else { bs.zeros(msb); bs.put(code, k + 1); }
+                                }
+                            }
+                        }
+                        if (i0 + 8 == next && i0 + 8 < c.hi) { p++; next += plen; k = krice[p]; bs.put(k, kbits); }
+                    }
+                    bs.finish();
+                }
+                if (gtid == 0) {
+                    u32 first_trailing;
+                    if (n == order) first_trailing = 0;
+                    else if (under) first_trailing = 1;
+                    else first_trailing = 1u << po;
+                    if (first_trailing < (1u << po)) {
+                        SmemSink bs; bs.init(img, res0 + totalbits);
+                        for (u32 p = first_trailing; p < (1u << po); p++) bs.put(krice[p], kbits);
+                        bs.flush();
+                    }
+                }
+            }
+        }
+        p3_group_bar(g, gt);      // the group's buffer and plan are free for its next subframe
+    }
+    __syncthreads();
+
+    // ---- CRC-16 of the frame (every byte before it), flac.c:530,668-670 ----
+    const u32 nb = frame_bytes - 2;
+    const u32 T = (nb + P3_CHUNK_BYTES - 1) / P3_CHUNK_BYTES;
+    u32 acc = 0;
+    for (u32 c = tid; c < T; c += nt) {
+        const u32 b0 = c * P3_CHUNK_BYTES, b1 = min(b0 + P3_CHUNK_BYTES, nb);
+        const u32* wp = img + c * P3_CHUNK_WORDS;
+        u32 crc = 0;
+        u32 b = b0;
+        for (; b + 4 <= b1; b += 4) {
+            const u32 w = *wp++;
+            crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ (w >> 24)];
+            crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ ((w >> 16) & 0xFF)];
+            crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ ((w >> 8) & 0xFF)];
+            crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ (w & 0xFF)];
+        }
+        if (b < b1) {
+            const u32 w = *wp;
+            for (u32 i = 0; b < b1; b++, i++) crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ ((w >> (24 - 8 * i)) & 0xFF)];
+        }
+        if (c + 1 < T) acc ^= gf16_mul(crc, (u32)crc_pow[69 + (T - 2 - c)]);
+        else sh.crc_last = crc;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((tid & 31) == 0) sh.crc_part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        u32 a = 0;
+        for (u32 w = 0; w < (nt >> 5); w++) a ^= sh.crc_part[w];
+        const u32 r = nb - (T - 1) * P3_CHUNK_BYTES;          // bytes of the last chunk, 1..68
+        const u32 crc = gf16_mul(a, (u32)crc_pow[r]) ^ sh.crc_last;
+        SmemSink bs; bs.init(img, nb * 8);
+        bs.put(crc, 16);
+        bs.flush();
+    }
+    __syncthreads();
+
+    // ---- the frame to its byte offset in the output ----
+    uint8_t* dst = out + frame_off[frame];
+    const u32 h = (4u - (u32)((uintptr_t)dst & 3)) & 3u;      // bytes before the first aligned word
+    const u32 hb = min(h, frame_bytes);
+    if (tid < hb) dst[tid] = (uint8_t)(img[0] >> (24 - 8 * tid));
+    const u32 body = (frame_bytes - hb) >> 2;
+    u32* dw = (u32*)(dst + hb);
+    // output byte i of word j is image byte h + 4 j + i: bytes h..3 of img[j], then 0..h-1 of img[j + 1]
+    const u32 sel = h == 0 ? 0x0123u : h == 1 ? 0x7012u : h == 2 ? 0x6701u : 0x5670u;
+    for (u32 j = tid; j < body; j += nt) dw[j] = __byte_perm(img[j], img[j + 1], sel);
+    const u32 done = hb + 4 * body;
+    if (tid < frame_bytes - done) {
+        const u32 b = done + tid;
+        dst[b] = (uint8_t)(img[b >> 2] >> (24 - 8 * (b & 3)));
+    }
+}
