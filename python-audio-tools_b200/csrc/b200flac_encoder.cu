@@ -445,8 +445,8 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
                 cudaMemcpy(enc->d_crc_tab, t.data(), t.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess) {
                 enc->p3 = false;
             } else {
-                e = 2 * enc->NT <= 384
-                        ? cudaFuncSetAttribute(k_pack_v3<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+                e = 2 * enc->NT <= 256
+                        ? cudaFuncSetAttribute(k_pack_v3<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
                         : cudaFuncSetAttribute(k_pack_v3<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
                 if (e != cudaSuccess) enc->p3 = false;
                 e = cudaSuccess;
@@ -711,8 +711,8 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
     k_scan_offsets<<<1, 1024, 0, st>>>(s.d_frame_bytes, nf, s.d_frame_off, s.d_total);
     if (enc->p3) {
         cudaEventRecord(s.ev[3], st);
-        if (2 * enc->NT <= 384)
-            k_pack_v3<384, 2><<<nf, 2 * enc->NT, enc->p3_smem, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
+        if (2 * enc->NT <= 256)
+            k_pack_v3<256, 4><<<nf, 2 * enc->NT, enc->p3_smem, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
                                                                      s.d_frame_off, d_out, s.d_total, out_cap, enc->p3_img_words,
                                                                      enc->d_crc_tab, enc->d_crc_tab + 256);
         else

@@ -281,20 +281,34 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                 const u32 kbits = sh.plan[g].coding_method ? 5u : 4u;
                 u32 hdr_end = bit0 + 8 + wasted + order * sub_bps;
                 if (ptype == BF_LPC) hdr_end += 4 + 5 + order * sh.plan[g].precision;
+                // header, warm-up samples and coefficients, every field at its known bit position: lane i
+                // writes warm-up sample i and coefficient i (read before anyone passes the barrier below)
+                if (gtid < order) {
+                    SmemSink bs; bs.init(img, bit0 + 8 + wasted + gtid * sub_bps);
+                    bs.put_signed(buf[V3_SK(gtid)], sub_bps);
+                    bs.flush();
+                    if (ptype == BF_LPC) {
+                        const u32 prec = sh.plan[g].precision;
+                        SmemSink cs; cs.init(img, bit0 + 8 + wasted + order * sub_bps + 9 + gtid * prec);
+                        cs.put_signed(sh.plan[g].coeffs[gtid], prec);
+                        cs.flush();
+                    }
+                }
                 if (gtid == 0) {
-                    // header and warm-up samples: read before anyone passes the barrier below
                     SmemSink bs; bs.init(img, bit0);
                     if (ptype == BF_FIXED) put_subframe_header_s(bs, 0x8 | order, wasted);
                     else put_subframe_header_s(bs, 0x20 | (order - 1), wasted);
-                    for (u32 i = 0; i < order; i++) bs.put_signed(buf[V3_SK(i)], sub_bps);
-                    if (ptype == BF_LPC) {
-                        bs.put(sh.plan[g].precision - 1, 4);
-                        bs.put_signed(sh.plan[g].shift, 5);
-                        for (u32 i = 0; i < order; i++) bs.put_signed(sh.plan[g].coeffs[i], sh.plan[g].precision);
-                    }
-                    bs.put(sh.plan[g].coding_method, 2);
-                    bs.put(po, 4);
                     bs.flush();
+                    if (ptype == BF_LPC) {
+                        SmemSink ps; ps.init(img, bit0 + 8 + wasted + order * sub_bps);
+                        ps.put(sh.plan[g].precision - 1, 4);
+                        ps.put_signed(sh.plan[g].shift, 5);
+                        ps.flush();
+                    }
+                    SmemSink ms; ms.init(img, hdr_end);
+                    ms.put(sh.plan[g].coding_method, 2);
+                    ms.put(po, 4);
+                    ms.flush();
                 }
                 const u32 res0 = hdr_end + 6;
                 const int shift = sh.plan[g].shift;
