@@ -236,3 +236,127 @@ def test_full_size_properties(tmp_path, built):
     if helpers.have_ref():
         assert helpers.ref_decode(got) == pcm
         assert got == helpers.ref_encode(pcm, 44100, 2, 16, o)
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel generations: k_analyze_v3 / k_pack_v3 (full-length blocks of the common shapes) against the
+# oracle on shapes that reach their special cases, and against k_analyze_v2 / k_pack_v2 / the generic
+# kernels, which the same library selects through tuning knobs read at encoder creation
+# ---------------------------------------------------------------------------------------------
+V3_GRID = [
+    # 8192-sample blocks: 256-thread CTAs, partition order 7 (finest partition = 2 thread runs)
+    (44100, 2, 16, 8192 * 3 + 4000, dict(block_size=8192, max_lpc_order=12, max_residual_partition_order=7, mid_side=True)),
+    # 4608: 24 samples per thread, a finest partition is three thread runs
+    (48000, 2, 16, 4608 * 4 + 11, dict(block_size=4608, max_lpc_order=10, max_residual_partition_order=6, adaptive_mid_side=True)),
+    # one warp per unit, four partitions
+    (44100, 1, 16, 512 * 9 + 1, dict(block_size=512, max_lpc_order=4, max_residual_partition_order=2)),
+    # 24-bit: 64-bit FIXED sums, 64-bit LPC accumulation, Rice parameters above 14 (coding method 1)
+    (96000, 2, 24, 4096 * 3 + 9, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, mid_side=True)),
+    (96000, 6, 24, 4096 * 2 + 500, dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=5)),
+    # orders above 12 (32-tap kernels), 16 (zero padded to 32)
+    (44100, 2, 16, 4096 * 3, dict(block_size=4096, max_lpc_order=32, max_residual_partition_order=6, mid_side=True)),
+    (44100, 2, 16, 4096 * 3, dict(block_size=4096, max_lpc_order=16, max_residual_partition_order=4)),
+    # partition order 0 only
+    (44100, 2, 16, 4096 * 2 + 77, dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=0, adaptive_mid_side=True)),
+]
+
+
+@pytest.mark.parametrize("case", range(len(V3_GRID)))
+def test_v3_shapes_identical(case, tmp_path, built):
+    rate, ch, bps, n, o = V3_GRID[case]
+    pcm = helpers.synth_pcm(4321 + case, ch, bps, n)
+    _check(tmp_path, pcm, rate, ch, bps, helpers.options(**o))
+
+
+def _special_signal(bps, n_blocks, block):
+    """blocks that reach the rare branches: wasted bits, constant, silence, full scale noise (VERBATIM),
+    a near-constant block (Rice parameter 0), alternating extremes (largest FIXED residuals)"""
+    rng = np.random.RandomState(7)
+    full = 1 << (bps - 1)
+    t = np.arange(block)
+    parts = [
+        ((3000 * np.sin(t * 0.03)).astype(np.int64) << 3),                  # 3 wasted bits
+        np.full(block, -1234, dtype=np.int64),                              # constant
+        np.zeros(block, dtype=np.int64),                                    # silence (constant 0)
+        rng.randint(-full, full, size=block).astype(np.int64),              # noise: VERBATIM
+        (t % 7 == 0).astype(np.int64),                                      # k = 0 partitions
+        np.where(t & 1, full - 1, -full).astype(np.int64),                  # alternating extremes
+        (rng.randint(-full // 4, full // 4, size=block).astype(np.int64) & ~1),  # noise with 1 wasted bit
+        (20000 * np.sin(t * 0.2) * np.exp(-t / 900.0)).astype(np.int64),    # decaying tone: k varies over partitions
+    ]
+    mono = np.concatenate([parts[i % len(parts)] for i in range(n_blocks)])
+    return mono
+
+
+@pytest.mark.parametrize("bps,opts", [
+    (16, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, adaptive_mid_side=True)),
+    (16, dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=5, mid_side=True)),
+    (24, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, mid_side=True)),
+])
+def test_v3_special_blocks(bps, opts, tmp_path, built):
+    block = opts["block_size"]
+    left = _special_signal(bps, 10, block)
+    right = np.roll(left, block * 3) // 2 + (np.arange(len(left)) % 5)      # a different block type per channel
+    full = 1 << (bps - 1)
+    right = np.clip(right, -full, full - 1)
+    inter = np.empty(2 * len(left), dtype=np.int32)
+    inter[0::2] = left
+    inter[1::2] = right
+    pcm = helpers.pack_pcm(inter, bps)
+    _check(tmp_path, pcm, 44100, 2, bps, helpers.options(**opts))
+
+
+def _with_env(env, fn):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("case", [0, 1, 3])
+def test_kernel_generations_agree(case, tmp_path, built):
+    """the v3 kernels, the v2 kernels and the generic kernels write the same file"""
+    rate, ch, bps, n, o = (GRID[1], V3_GRID[1], V3_GRID[3], V3_GRID[0])[case]
+    pcm = helpers.synth_pcm(99 + case, ch, bps, n)
+    opts = helpers.options(**o)
+    a = _encode_b200(tmp_path, pcm, rate, ch, bps, opts, "a.flac")
+    b = _with_env({"B200FLAC_NO_V3": "1", "B200FLAC_NO_P3": "1"},
+                  lambda: _encode_b200(tmp_path, pcm, rate, ch, bps, opts, "b.flac"))
+    c = _with_env({"B200FLAC_FORCE_GENERIC": "1"},
+                  lambda: _encode_b200(tmp_path, pcm, rate, ch, bps, opts, "c.flac"))
+    d = _with_env({"B200FLAC_LPC_G": "1"}, lambda: _encode_b200(tmp_path, pcm, rate, ch, bps, opts, "d.flac"))
+    assert a == b, "v3 and v2 kernels differ at byte %d" % _first_diff(a, b)
+    assert a == c, "v3 and generic kernels differ at byte %d" % _first_diff(a, c)
+    assert a == d, "lag-split and unsplit autocorrelation differ at byte %d" % _first_diff(a, d)
+
+
+def test_many_short_tracks_one_batch(built):
+    """config #5 shape on the v3 kernels: tracks of 4096-sample blocks with short tails in one batch;
+    tail frames go through k_analyze_v2, full ones through k_analyze_v3, all through k_pack_v3"""
+    b = _b200()
+    o = helpers.options(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, mid_side=True)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 2, 16, **kw)
+    lens = [4096 * 2 + 100, 4096, 17, 4096 * 3 + 4095, 4096 * 1 + 1]
+    tracks = [helpers.synth_pcm(300 + i, 2, 16, n) for i, n in enumerate(lens)]
+    pcm = b"".join(tracks)
+    segs, pos = [], 0
+    for n in lens:
+        segs.append((pos, n, 0))
+        pos += n
+    enc = b.Encoder(p, max_pcm_frames_per_batch=pos, n_slots=1)
+    out, fbytes, fpcm = enc.encode(pcm, pos, segments=segs)
+    want, want_sizes = b"", []
+    for t in tracks:
+        fr, sz = helpers.oracle_encode_range(t, 44100, 2, 16, o, 0)
+        want += fr
+        want_sizes += sz
+    assert fbytes.tolist() == want_sizes
+    assert out.tobytes() == want
+    enc.close()
