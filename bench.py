@@ -9,7 +9,8 @@ Workload (BASELINE.json configs[1]): 1 h of synthetic 44.1 kHz / 16-bit stereo P
 adaptive mid-side, max_residual_partition_order 6 (the reference standalone default,
 src/encoders/flac.c:1647), frames sharded by range: every rank (GPU) encodes its own hour.
 
-A step = one pass of the hot path (5 kernels) over the rank's whole hour.
+A step = one pass of the hot path (6 kernels: autocorrelation, Levinson/quantise, model search,
+frame select, offset scan, frame pack + CRC-16) over the rank's whole hour.
   value : whole-job Msamples/s with the PCM already resident in HBM and the frames left in
           HBM (b200flac_encoder_encode_device), wall clock around K steps bracketed by
           barrier + device synchronize, max over ranks.
@@ -258,9 +259,11 @@ def main():
     barrier()
     clocks.start()
     kernel_ms = [0.0] * 5
+    device_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_bytes, n_flac_frames, _ = enc.encode_device(d_pcm, segs, d_out, out_cap)
+        out_bytes, n_flac_frames, dev_ms = enc.encode_device(d_pcm, segs, d_out, out_cap)
+        device_ms += dev_ms
         for i, v in enumerate(enc.kernel_ms(0)):
             kernel_ms[i] += v
     barrier()
@@ -274,16 +277,24 @@ def main():
     samples_per_step = n_frames_pcm * CHANNELS
     value = world * samples_per_step * args.steps / elapsed / 1e6
     kernel_ms = [v / args.steps for v in kernel_ms]
-    names = ["lpc_model", "analyze", "select_scan_zero", "pack", "crc16"]
+    # CUDA-event intervals recorded by the library on the stream it launches on.  "crc16" is the separate
+    # CRC kernel of the k_pack_v2 path; k_pack_v3 (the default) computes the CRC-16 inside "pack".
+    names = ["lpc_model", "analyze", "select_scan", "pack", "crc16"]
     dom = max(range(5), key=lambda i: kernel_ms[i])
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, from the ncu --set full
+    # capture summarised in profiles/r01_v4_summary.txt (only valid for the default 3600 s workload)
+    traffic_ncu = {"lpc_model": 636.3e6 + 14.5e6, "analyze": 673.3e6 + 21.7e6, "pack": 656.7e6 + 406.0e6}
+    traffic = traffic_ncu.get(names[dom]) if n_frames_pcm == HOUR_FRAMES else None
     algo_bytes = pcm_bytes + out_bytes            # PCM in at native width + frame bytes out
     peak, peak_kind = peaks()
     achieved = algo_bytes / (kernel_ms[dom] * 1e-3) / 1e9
     pipeline = algo_bytes / (sum(kernel_ms) * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                "traffic_source": "profiles/r01_v4_summary.txt (ncu --set full, bytes per launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": dict(zip(names, kernel_ms)),
+                "device_ms_per_step": device_ms / args.steps,
                 "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak,
                 "bytes_per_sample": algo_bytes / samples_per_step}
 
