@@ -45,6 +45,48 @@ __device__ __forceinline__ u32 p3_group_exscan(u32 v, u32* red, u32 g, u32 gt, u
     return off + inc - v;
 }
 
+// MSB-first writer of a thread's run into the shared image, pending bits RIGHT-aligned in a 64-bit
+// register: appending is a shift and an OR, a completed word is one funnel shift.  Bits above `fill`
+// in acc are stale and never read.  Every completed word is OR-merged (shared atomicOr on a
+// zero-initialised image), so the word a run shares with its predecessor needs no special case.
+struct RunSink3 {
+    u32* words;
+    u32 widx;
+    u64 acc;
+    u32 fill;
+    __device__ __forceinline__ void init(u32* base, u32 bitpos)
+    {
+        words = base; widx = bitpos >> 5; fill = bitpos & 31; acc = 0;
+    }
+    __device__ __forceinline__ void put(u32 v, u32 nbits) // 1 <= nbits <= 32, v < 2^nbits
+    {
+        acc = (acc << nbits) | (u64)v;
+        fill += nbits;
+        if (fill >= 32) {
+            fill -= 32;
+            atomicOr(words + widx, (u32)(acc >> fill));
+            widx++;
+        }
+    }
+    __device__ __forceinline__ void zeros(u32 nz)
+    {
+        if (fill + nz < 64) {
+            acc <<= nz;
+            fill += nz;
+            if (fill >= 32) { fill -= 32; atomicOr(words + widx, (u32)(acc >> fill)); widx++; }
+        } else {
+            // the pending bits complete a word with zeros; whole zero words follow
+            if (fill) atomicOr(words + widx, (u32)(acc << (32 - fill)));
+            const u32 tot = fill + nz;
+            widx += tot >> 5; fill = tot & 31; acc = 0;
+        }
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (fill) atomicOr(words + widx, (u32)(acc << (32 - fill)));
+    }
+};
+
 struct P3Shared {
     b200flac_plan plan[2];
     bf_frame_choice choice;
@@ -158,12 +200,12 @@ __device__ __forceinline__ u32 p3_fixed_inplace(int* __restrict__ buf, u32 base,
 // host and device agree on the dynamic shared memory through this
 __host__ __device__ inline size_t p3_smem_bytes(u32 block_size, u32 img_words)
 {
-    const size_t padn = (size_t)V3_SK(block_size) + 40;
-    return 2 * padn * 4 + (size_t)(img_words + 4) * 4 + 512 + 32;
+    const size_t padn = ((size_t)V3_SK(block_size) + 40 + 3) & ~(size_t)3;
+    return 2 * padn * 4 + (size_t)(img_words + 12) * 4 + 2048 + 32;
 }
 
 // blockDim.x = 2 * gt; gt * S >= block_size; S a multiple of 8.
-//   crc_tab[256]: CRC-16 of one byte; crc_pow[0..68] = x^(8 r), crc_pow[69 + j] = x^(8 * 68 * j) mod the
+//   crc_tab[4][256]: CRC-16 of one byte followed by 0..3 zero bytes; crc_pow[0..68] = x^(8 r), crc_pow[69 + j] = x^(8 * 68 * j) mod the
 //   CRC-16 polynomial (built by the host).
 template <int NTMAX, int MINB>
 __global__ void __launch_bounds__(NTMAX, MINB)
@@ -180,20 +222,20 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
     const u32 tid = threadIdx.x, nt = blockDim.x, gt = nt >> 1;
     const u32 g = tid / gt, gtid = tid - g * gt;
     const u32 frame = blockIdx.x;
-    const size_t padn = (size_t)V3_SK(P.block_size) + 40;
+    const size_t padn = ((size_t)V3_SK(P.block_size) + 40 + 3) & ~(size_t)3;    // keeps the image 16-byte aligned
     int* buf = (int*)dyn_smem + (size_t)g * padn;
     u32* img = (u32*)((int*)dyn_smem + 2 * padn);
-    unsigned short* tab = (unsigned short*)(img + img_words + 4);
+    unsigned short* tab = (unsigned short*)(img + ((img_words + 8 + 3) & ~3u));   // past the zeroing's overshoot
 
     if (tid == 0) sh.choice = choice[frame];
-    for (u32 t = tid; t < 256; t += nt) tab[t] = crc_tab[t];
+    for (u32 t = tid; t < 512; t += nt) ((u32*)tab)[t] = ((const u32*)crc_tab)[t];      // 4 x 256 entries
     const bf_frame_desc d = fd[frame];
     const u32 n = d.nsamp;
     __syncthreads();
     const u32 frame_bytes = sh.choice.frame_bytes, n_sub = sh.choice.n_sub;
     const u32 nwords = (frame_bytes + 3) >> 2;
     if (nwords + 2 > img_words + 4) __trap();    // cannot happen: the image is sized for the largest frame
-    for (u32 w = tid; w < nwords + 2; w += nt) img[w] = 0;
+    for (u32 w = tid * 4; w < nwords + 2; w += nt * 4) *(uint4*)(img + w) = make_uint4(0, 0, 0, 0);   // img is 16-byte aligned, padded
     __syncthreads();
     if (tid == 0) {
         SmemSink hs; hs.init(img, 0);
@@ -270,7 +312,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                     bs.flush();
                 }
                 if (base < n) {
-                    RunSink bs; bs.init(img, bit0 + 8 + wasted + base * sub_bps);
+                    RunSink3 bs; bs.init(img, bit0 + 8 + wasted + base * sub_bps);
                     const u32 mask = sub_bps >= 32 ? 0xFFFFFFFFu : ((1u << sub_bps) - 1u);
                     for (u32 i = base; i < end; i++) bs.put((u32)buf[V3_SK(i)] & mask, sub_bps);
                     bs.finish();
@@ -338,7 +380,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                 u32 totalbits;
                 const u32 off = p3_group_exscan(mybits, sh.red[g], g, gt, gtid, &totalbits);
                 if (have) {
-                    RunSink bs; bs.init(img, res0 + off);
+                    RunSink3 bs; bs.init(img, res0 + off);
                     if (c.lo == order) { for (u32 q = 0; q < lead; q++) bs.put(krice[q], kbits); }
                     else if (lead) bs.put(krice[p_first], kbits);
                     u32 p = p_first;
@@ -403,11 +445,10 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
         u32 crc = 0;
         u32 b = b0;
         for (; b + 4 <= b1; b += 4) {
-            const u32 w = *wp++;
-            crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ (w >> 24)];
-            crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ ((w >> 16) & 0xFF)];
-            crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ ((w >> 8) & 0xFF)];
-            crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ (w & 0xFF)];
+            // four bytes at once: tab[256 * n + x] = CRC of byte x followed by n zero bytes
+            const u32 w = *wp++ ^ (crc << 16);
+            crc = (u32)tab[768 + (w >> 24)] ^ (u32)tab[512 + ((w >> 16) & 0xFF)] ^
+                  (u32)tab[256 + ((w >> 8) & 0xFF)] ^ (u32)tab[w & 0xFF];
         }
         if (b < b1) {
             const u32 w = *wp;
