@@ -417,21 +417,22 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     enc->p3 = false;
     enc->d_crc_tab = nullptr;
     if (enc->fast && !(getenv("B200FLAC_NO_P3") && getenv("B200FLAC_NO_P3")[0] == '1')) {
-        const u64 fb = frame_bound_bytes(params, bs);
+        // largest frame: every subframe VERBATIM, at most one of them (the side channel) at bps + 1
+        const u64 fb = 16 + ((u64)params->channels * (8 + 32 + (u64)params->bits_per_sample * bs) + bs + 7) / 8 + 2;
         const u32 iw = (u32)((fb + 3) / 4 + 2);
         const size_t sm = p3_smem_bytes(bs, iw);
         if (sm <= 200 * 1024 && 2 * enc->NT <= 1024) {
             enc->p3 = true; enc->p3_img_words = iw; enc->p3_smem = sm;
             // CRC-16 tables: byte table, x^(8 r) for r <= 68, x^(8 * 68 * j)
             const u32 nchunks = (u32)(fb / P3_CHUNK_BYTES + 4);
-            std::vector<unsigned short> t(1024 + 69 + nchunks);
+            std::vector<unsigned short> t(512 + 69 + nchunks);
             for (u32 b = 0; b < 256; b++) {
                 u32 c = b << 8;
                 for (int k = 0; k < 8; k++) c = (c & 0x8000) ? ((c << 1) ^ 0x8005) & 0xFFFF : (c << 1) & 0xFFFF;
                 t[b] = (unsigned short)c;
             }
-            // t[256 n + x]: CRC of byte x followed by n zero bytes (slicing by four)
-            for (u32 n = 1; n < 4; n++)
+            // t[256 n + x]: CRC of byte x followed by n zero bytes (slicing by two)
+            for (u32 n = 1; n < 2; n++)
                 for (u32 b = 0; b < 256; b++) {
                     const u32 c = t[256 * (n - 1) + b];
                     t[256 * n + b] = (unsigned short)(((c << 8) & 0xFFFF) ^ t[c >> 8]);
@@ -443,10 +444,10 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
                 return r;
             };
             u32 x8 = 0x100, acc = 1;                 // x^8
-            for (u32 r = 0; r <= 68; r++) { t[1024 + r] = (unsigned short)acc; acc = mul(acc, x8); }
-            const u32 xc = t[1024 + 68];             // x^(8 * 68)
+            for (u32 r = 0; r <= 68; r++) { t[512 + r] = (unsigned short)acc; acc = mul(acc, x8); }
+            const u32 xc = t[512 + 68];              // x^(8 * 68)
             acc = 1;
-            for (u32 j = 0; j < nchunks; j++) { t[1024 + 69 + j] = (unsigned short)acc; acc = mul(acc, xc); }
+            for (u32 j = 0; j < nchunks; j++) { t[512 + 69 + j] = (unsigned short)acc; acc = mul(acc, xc); }
             if (cudaMalloc((void**)&enc->d_crc_tab, t.size() * sizeof(unsigned short)) != cudaSuccess ||
                 cudaMemcpy(enc->d_crc_tab, t.data(), t.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess) {
                 enc->p3 = false;
@@ -720,11 +721,11 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
         if (2 * enc->NT <= 256)
             k_pack_v3<256, 4><<<nf, 2 * enc->NT, enc->p3_smem, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
                                                                      s.d_frame_off, d_out, s.d_total, out_cap, enc->p3_img_words,
-                                                                     enc->d_crc_tab, enc->d_crc_tab + 1024);
+                                                                     enc->d_crc_tab, enc->d_crc_tab + 512);
         else
             k_pack_v3<1024, 1><<<nf, 2 * enc->NT, enc->p3_smem, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
                                                                       s.d_frame_off, d_out, s.d_total, out_cap, enc->p3_img_words,
-                                                                      enc->d_crc_tab, enc->d_crc_tab + 1024);
+                                                                      enc->d_crc_tab, enc->d_crc_tab + 512);
         cudaEventRecord(s.ev[4], st);
         cudaEventRecord(s.ev[5], st);
         enc->launches += 3 + (gridv2 ? 1 : 0);

@@ -40,8 +40,7 @@ __device__ __forceinline__ u32 p3_group_exscan(u32 v, u32* red, u32 g, u32 gt, u
     p3_group_bar(g, gt);
     u32 off = 0, tot = 0;
     for (u32 w = 0; w < nw; w++) { const u32 t = red[w]; off += w < warp ? t : 0u; tot += t; }
-    p3_group_bar(g, gt);
-    *total = tot;
+    *total = tot;              // (the caller alternates between two `red` buffers: no second barrier)
     return off + inc - v;
 }
 
@@ -90,7 +89,7 @@ struct RunSink3 {
 struct P3Shared {
     b200flac_plan plan[2];
     bf_frame_choice choice;
-    u32 red[2][16];
+    u32 red[2][2][16];
     short q[2][BF_MAX_ORDER];
     u32 crc_part[32];
     u32 crc_last;
@@ -200,12 +199,12 @@ __device__ __forceinline__ u32 p3_fixed_inplace(int* __restrict__ buf, u32 base,
 // host and device agree on the dynamic shared memory through this
 __host__ __device__ inline size_t p3_smem_bytes(u32 block_size, u32 img_words)
 {
-    const size_t padn = ((size_t)V3_SK(block_size) + 40 + 3) & ~(size_t)3;
-    return 2 * padn * 4 + (size_t)(img_words + 12) * 4 + 2048 + 32;
+    const size_t padn = ((size_t)V3_SK(block_size) + 8 + 3) & ~(size_t)3;
+    return 2 * padn * 4 + (size_t)(img_words + 12) * 4 + 1024 + 32;
 }
 
 // blockDim.x = 2 * gt; gt * S >= block_size; S a multiple of 8.
-//   crc_tab[4][256]: CRC-16 of one byte followed by 0..3 zero bytes; crc_pow[0..68] = x^(8 r), crc_pow[69 + j] = x^(8 * 68 * j) mod the
+//   crc_tab[2][256]: CRC-16 of one byte followed by 0..1 zero bytes; crc_pow[0..68] = x^(8 r), crc_pow[69 + j] = x^(8 * 68 * j) mod the
 //   CRC-16 polynomial (built by the host).
 template <int NTMAX, int MINB>
 __global__ void __launch_bounds__(NTMAX, MINB)
@@ -222,21 +221,21 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
     const u32 tid = threadIdx.x, nt = blockDim.x, gt = nt >> 1;
     const u32 g = tid / gt, gtid = tid - g * gt;
     const u32 frame = blockIdx.x;
-    const size_t padn = ((size_t)V3_SK(P.block_size) + 40 + 3) & ~(size_t)3;    // keeps the image 16-byte aligned
+    const size_t padn = ((size_t)V3_SK(P.block_size) + 8 + 3) & ~(size_t)3;     // keeps the image 16-byte aligned
     int* buf = (int*)dyn_smem + (size_t)g * padn;
     u32* img = (u32*)((int*)dyn_smem + 2 * padn);
     unsigned short* tab = (unsigned short*)(img + ((img_words + 8 + 3) & ~3u));   // past the zeroing's overshoot
 
     if (tid == 0) sh.choice = choice[frame];
-    for (u32 t = tid; t < 512; t += nt) ((u32*)tab)[t] = ((const u32*)crc_tab)[t];      // 4 x 256 entries
+    for (u32 t = tid; t < 256; t += nt) ((u32*)tab)[t] = ((const u32*)crc_tab)[t];      // 2 x 256 entries
     const bf_frame_desc d = fd[frame];
     const u32 n = d.nsamp;
+    // the whole image is cleared (not just this frame's extent) so that one barrier covers everything
+    for (u32 w = tid * 4; w < img_words + 4; w += nt * 4) *(uint4*)(img + w) = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const u32 frame_bytes = sh.choice.frame_bytes, n_sub = sh.choice.n_sub;
     const u32 nwords = (frame_bytes + 3) >> 2;
     if (nwords + 2 > img_words + 4) __trap();    // cannot happen: the image is sized for the largest frame
-    for (u32 w = tid * 4; w < nwords + 2; w += nt * 4) *(uint4*)(img + w) = make_uint4(0, 0, 0, 0);   // img is 16-byte aligned, padded
-    __syncthreads();
     if (tid == 0) {
         SmemSink hs; hs.init(img, 0);
         put_frame_header(hs, d, P, sh.choice.assignment);
@@ -254,6 +253,10 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
         const u32 bit0 = sh.choice.bitoff[slot];
         const uint8_t* krice = rice + (size_t)unit * P.rice_stride;
         if (gtid == 0) sh.plan[g] = plans[unit];
+        if (gtid < BF_MAX_ORDER) {
+            const b200flac_plan* gp = plans + unit;
+            sh.q[g][gtid] = (gp->type == BF_LPC && gtid < gp->order) ? gp->coeffs[gtid] : (short)0;
+        }
 
         // ---- samples of the candidate, coalesced ----
         if (P.stereo && P.bytes_ps == 2) {
@@ -302,9 +305,10 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                 bs.flush();
             }
         } else {
-            if (wasted) for (u32 i = gtid; i < n; i += gt) buf[V3_SK(i)] >>= wasted;
-            if (ptype == BF_LPC && gtid < BF_MAX_ORDER) sh.q[g][gtid] = gtid < order ? sh.plan[g].coeffs[gtid] : (short)0;
-            p3_group_bar(g, gt);
+            if (wasted) {
+                for (u32 i = gtid; i < n; i += gt) buf[V3_SK(i)] >>= wasted;
+                p3_group_bar(g, gt);
+            }
             if (ptype == BF_VERBATIM) {
                 if (gtid == 0) {
                     SmemSink bs; bs.init(img, bit0);
@@ -378,7 +382,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                 mybits = have ? mybits + lead * kbits : 0u;
 
                 u32 totalbits;
-                const u32 off = p3_group_exscan(mybits, sh.red[g], g, gt, gtid, &totalbits);
+                const u32 off = p3_group_exscan(mybits, sh.red[g][(slot0 >> 1) & 1], g, gt, gtid, &totalbits);
                 if (have) {
                     RunSink3 bs; bs.init(img, res0 + off);
                     if (c.lo == order) { for (u32 q = 0; q < lead; q++) bs.put(krice[q], kbits); }
@@ -431,7 +435,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                 }
             }
         }
-        p3_group_bar(g, gt);      // the group's buffer and plan are free for its next subframe
+        if (slot0 + 2 < n_sub) p3_group_bar(g, gt);      // the group's buffer and plan are free for its next subframe
     }
     __syncthreads();
 
@@ -445,10 +449,12 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
         u32 crc = 0;
         u32 b = b0;
         for (; b + 4 <= b1; b += 4) {
-            // four bytes at once: tab[256 * n + x] = CRC of byte x followed by n zero bytes
-            const u32 w = *wp++ ^ (crc << 16);
-            crc = (u32)tab[768 + (w >> 24)] ^ (u32)tab[512 + ((w >> 16) & 0xFF)] ^
-                  (u32)tab[256 + ((w >> 8) & 0xFF)] ^ (u32)tab[w & 0xFF];
+            // two bytes at once: tab[256 + x] = CRC of byte x followed by a zero byte
+            const u32 w = *wp++;
+            const u32 a = (w >> 16) ^ crc;
+            crc = (u32)tab[256 + (a >> 8)] ^ (u32)tab[a & 0xFF];
+            const u32 b2 = (w & 0xFFFF) ^ crc;
+            crc = (u32)tab[256 + (b2 >> 8)] ^ (u32)tab[b2 & 0xFF];
         }
         if (b < b1) {
             const u32 w = *wp;
@@ -461,29 +467,27 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
     for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
     if ((tid & 31) == 0) sh.crc_part[tid >> 5] = acc;
     __syncthreads();
+    // ---- the frame to its byte offset in the output; thread 0 finishes the CRC and writes its two
+    // bytes itself, everybody else moves the nb bytes before it ----
+    uint8_t* dst = out + frame_off[frame];
     if (tid == 0) {
         u32 a = 0;
         for (u32 w = 0; w < (nt >> 5); w++) a ^= sh.crc_part[w];
         const u32 r = nb - (T - 1) * P3_CHUNK_BYTES;          // bytes of the last chunk, 1..68
         const u32 crc = gf16_mul(a, (u32)crc_pow[r]) ^ sh.crc_last;
-        SmemSink bs; bs.init(img, nb * 8);
-        bs.put(crc, 16);
-        bs.flush();
+        dst[nb] = (uint8_t)(crc >> 8);
+        dst[nb + 1] = (uint8_t)crc;
     }
-    __syncthreads();
-
-    // ---- the frame to its byte offset in the output ----
-    uint8_t* dst = out + frame_off[frame];
     const u32 h = (4u - (u32)((uintptr_t)dst & 3)) & 3u;      // bytes before the first aligned word
-    const u32 hb = min(h, frame_bytes);
+    const u32 hb = min(h, nb);
     if (tid < hb) dst[tid] = (uint8_t)(img[0] >> (24 - 8 * tid));
-    const u32 body = (frame_bytes - hb) >> 2;
+    const u32 body = (nb - hb) >> 2;
     u32* dw = (u32*)(dst + hb);
     // output byte i of word j is image byte h + 4 j + i: bytes h..3 of img[j], then 0..h-1 of img[j + 1]
     const u32 sel = h == 0 ? 0x0123u : h == 1 ? 0x7012u : h == 2 ? 0x6701u : 0x5670u;
     for (u32 j = tid; j < body; j += nt) dw[j] = __byte_perm(img[j], img[j + 1], sel);
     const u32 done = hb + 4 * body;
-    if (tid < frame_bytes - done) {
+    if (tid < nb - done) {
         const u32 b = done + tid;
         dst[b] = (uint8_t)(img[b >> 2] >> (24 - 8 * (b & 3)));
     }
