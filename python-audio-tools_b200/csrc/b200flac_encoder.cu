@@ -107,6 +107,7 @@ struct b200flac_encoder {
     unsigned short* d_crc_tab;   // [256] byte table + [69 + n] powers of x (see k_pack_v3)
     u32 v3_S, v3_F, v3_NT;
     size_t v3_smem;
+    int v3_occ;           // resident CTAs per SM of k_analyze_v3 (the kernel is persistent)
     std::map<u32, std::vector<double>>* windows;
     u64 launches;
     int lpc_occ[2];       // resident one-warp CTAs per SM of k_lpc_autoc (G = 1, 2)
@@ -406,6 +407,13 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
                     ? cudaFuncSetAttribute(k_analyze_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem)
                     : cudaFuncSetAttribute(k_analyze_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem);
             if (e != cudaSuccess) enc->v3 = false;
+            enc->v3_occ = 1;
+            if (enc->v3) {
+                if (enc->v3_NT <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<5>, (int)enc->v3_NT, enc->v3_smem);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<1>, (int)enc->v3_NT, enc->v3_smem);
+                if (enc->v3_occ < 1) enc->v3_occ = 1;
+            }
+            cudaDeviceGetAttribute(&enc->n_sms, cudaDevAttrMultiProcessorCount, enc->device);
             e = cudaSuccess;
         }
     }
@@ -699,10 +707,16 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
     u32 gridv2 = U;
     const u32* flist = nullptr;
     if (enc->v3) {
+        // one CTA per unit.  (The kernel also runs as a persistent grid -- B200FLAC_V3_GRID=740 is one wave
+        // -- but CTAs that start together stay in the same phase of the unit and overlap their load and
+        // search phases worse: 3.16 ms against 2.87 ms per hour on B200.)
+        u32 g3 = U;
+        if (getenv("B200FLAC_V3_GRID")) g3 = (u32)atoi(getenv("B200FLAC_V3_GRID"));   // tuning knob
+        if (g3 > U || g3 == 0) g3 = U;
         if (enc->v3_NT <= 128)
-            k_analyze_v3<5><<<U, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+            k_analyze_v3<5><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, U, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
         else
-            k_analyze_v3<1><<<U, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+            k_analyze_v3<1><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, U, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
         enc->launches += 1;
         gridv2 = s.n_odd * P.K;      // the other block lengths (a stream's last block)
         flist = s.d_odd;

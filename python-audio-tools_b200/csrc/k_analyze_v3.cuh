@@ -343,17 +343,13 @@ __device__ __forceinline__ u32 v3_stored_bits(const int* __restrict__ resid, u32
 // S: samples per thread (multiple of 8, <= 32); blockDim.x * S == block_size; F: finest partition
 // order searched, (block_size >> F) a multiple of S.  Units whose block is not block_size long are
 // left to k_analyze_v2 (launched over the same grid, which skips the others).
-template <int MINB>
-__global__ void __launch_bounds__(512 / (MINB >= 5 ? 4 : 1), MINB)
-k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S, u32 F,
-             const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
-             b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out)
+__device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u32 unit,
+                                        const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
+                                        const bf_dev_params& P, u32 S, u32 F,
+                                        const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
+                                        b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out)
 {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ V3Shared sh;
-
     const u32 tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    const u32 unit = blockIdx.x;
     const u32 frame = unit / P.K, cand = unit % P.K;
     const bf_frame_desc d = fd[frame];
     const u32 n = d.nsamp;
@@ -585,5 +581,22 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
             plan.bits = hdr_bits + sub_bps * n;       // flac.c:832-854
         }
         plans[unit] = plan;
+    }
+}
+
+// The grid is normally one CTA per unit; any smaller grid walks the units with the grid's stride
+// (measured: a persistent single wave keeps the CTAs of an SM in the same phase of the unit, which
+// overlaps their load and search phases worse than staggered CTAs do).
+template <int MINB>
+__global__ void __launch_bounds__(512 / (MINB >= 5 ? 4 : 1), MINB)
+k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S, u32 F,
+             u32 n_units, const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
+             b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ V3Shared sh;
+    for (u32 unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        v3_unit(dyn_smem, sh, unit, pcm, fd, P, S, F, heads, coefs, plans, rice_out);
+        __syncthreads();        // shared memory is reused by the next unit
     }
 }
