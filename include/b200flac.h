@@ -206,6 +206,17 @@ int b200flac_stream_close(b200flac_stream *s, int abort_encode, uint64_t **frame
                           uint32_t **frame_pcm_frames, uint64_t *n_frames);
 void b200flac_free(void *p);
 
+/* Metadata finalisation of a finished file, host only: what FlacAudio.from_pcm does in Python after
+ * encode_flac returns (audiotools/flac.py:1811-1832).  Builds the SEEKTABLE from the encoder's
+ * (byte offset, PCM frames) list, one point every seekpoint_interval PCM frames (0 -> 10 s, flac.py:1847-1876),
+ * inserts it in FlacMetaData.add_block's order (flac.py:53-75), adds
+ * WAVEFORMATEXTENSIBLE_CHANNEL_MASK=0x%.4X to the VORBIS_COMMENT when channel_mask != 0 (flac.py:1827-1832)
+ * and writes the metadata back by update_metadata's rule (flac.py:1369-1462): the PADDING blocks absorb
+ * the growth when they can (frames do not move), else the file is rewritten.  Returns 0 on success. */
+int b200flac_finalize_metadata(const char *filename, const uint64_t *frame_offsets,
+                               const uint32_t *frame_pcm_frames, uint64_t n_frames,
+                               uint32_t seekpoint_interval, uint32_t channel_mask);
+
 /* One-call form of the above for PCM already in memory: the standalone
  * reference's `flacenc < pcm` (flac.c:1637-1804). */
 int b200flac_encode_file(const char *filename, const b200flac_params *params,

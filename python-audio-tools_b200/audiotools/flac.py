@@ -16,6 +16,19 @@ BLOCK_STREAMINFO, BLOCK_PADDING, BLOCK_SEEKTABLE, BLOCK_VORBIS_COMMENT = 0, 1, 3
 PREFERRED_ORDER = [0, 3, 5, 4, 6, 2, 1]
 
 
+def _native_finalize(filename, offsets, seekpoint_interval, channel_mask):
+    import ctypes as C
+    from . import encoders
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(encoders.__file__))), "libb200flac.so"))
+    lib.b200flac_last_error.restype = C.c_char_p
+    n = len(offsets)
+    offs = (C.c_uint64 * max(n, 1))(*[o for o, _ in offsets])
+    lens = (C.c_uint32 * max(n, 1))(*[f for _, f in offsets])
+    if lib.b200flac_finalize_metadata(os.fsencode(filename), offs, lens, C.c_uint64(n), C.c_uint32(seekpoint_interval),
+                                      C.c_uint32(channel_mask)):
+        raise IOError(lib.b200flac_last_error().decode())
+
+
 class FlacMetaData(object):
     """ordered list of (block_id, payload) metadata blocks"""
 
@@ -50,6 +63,9 @@ class FlacAudio(object):
 
     SUFFIX = "flac"
     NAME = SUFFIX
+    # True: SEEKTABLE / channel-mask tag / PADDING adjustment by the engine library (C); False: the
+    # Python restatement of flac.py:1811-1832 below (kept as the checker of the native path)
+    NATIVE_FINALIZE = True
     DEFAULT_COMPRESSION = "8"
     COMPRESSION_MODES = tuple(map(str, range(0, 9)))
 
@@ -206,6 +222,12 @@ class FlacAudio(object):
             offsets = (encode_flac if encoding_function is None else encoding_function)(
                 filename, pcmreader=BufferedPCMReader(pcmreader), padding_size=padding_size, **encoding_options)
             flac = FlacAudio(filename)
+            mask_tag = channel_mask if (((pcmreader.channels > 2) or (pcmreader.bits_per_sample > 16)) and
+                                        channel_mask != 0) else 0
+            if cls.NATIVE_FINALIZE:
+                # the same three steps in C (b200flac_finalize_metadata): no Python pass over the file
+                _native_finalize(filename, list(offsets), pcmreader.sample_rate * 10, mask_tag)
+                return FlacAudio(filename)
             metadata = flac.get_metadata()
             assert metadata is not None
             metadata.add_block(flac.seektable(list(offsets), pcmreader.sample_rate * 10))

@@ -98,6 +98,7 @@ def lib():
     L.b200flac_stream_end_block.argtypes = [vp]
     L.b200flac_stream_close.argtypes = [vp, C.c_int, C.POINTER(u64p), C.POINTER(u32p), u64p]
     L.b200flac_free.argtypes = [vp]
+    L.b200flac_finalize_metadata.argtypes = [C.c_char_p, u64p, u32p, C.c_uint64, C.c_uint32, C.c_uint32]
     L.b200flac_encode_file.argtypes = [C.c_char_p, C.POINTER(Params), C.c_uint32, C.c_char_p, vp,
                                        C.c_uint64, C.POINTER(C.c_int), C.c_int]
     _lib = L
@@ -273,3 +274,13 @@ class Stream(object):
         lib().b200flac_free(offs)
         lib().b200flac_free(lens)
         return res
+
+
+def finalize_metadata(filename, offsets, seekpoint_interval=0, channel_mask=0):
+    """SEEKTABLE (+ channel-mask tag) into the finished file, natively: what FlacAudio.from_pcm does after
+    encode_flac returns (audiotools/flac.py:1811-1832).  offsets: the encoder's [(byte offset, PCM frames)]."""
+    n = len(offsets)
+    offs = (C.c_uint64 * max(n, 1))(*[o for o, _ in offsets])
+    lens = (C.c_uint32 * max(n, 1))(*[f for _, f in offsets])
+    if lib().b200flac_finalize_metadata(os.fsencode(filename), offs, lens, n, seekpoint_interval, channel_mask):
+        raise _err()

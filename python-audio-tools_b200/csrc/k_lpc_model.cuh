@@ -134,7 +134,8 @@ __device__ __forceinline__ int stereo16_coef(u32 cand) { return cand == 0 ? 0x00
 // hist is a ring of H = LB+NL windowed samples with compile-time indexing; tiles of TS = H*M
 // PCM frames per row are staged with cp.async, double buffered, so the copy of tile t+1 is in
 // flight while tile t is consumed.
-// FAST: 16-bit stereo (fast paths compiled in).
+// FAST: 16-bit stereo (one 32-bit load and a dot product per sample); otherwise samples are
+// assembled from the staged bytes.
 template <int LB, int NL, bool FAST>
 __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                                            const double* __restrict__ windows, const bf_dev_params& P,
@@ -218,17 +219,23 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
             const u32 tbase = m * H;
             const u32 ig = i0 + tbase;                 // first sample of this ring rotation
             if (ig >= nmax) break;
-            // whole rotation in range for every lane (16-bit stereo rows are always 4-byte aligned)?
-            const bool full = FAST && (ig + H <= n);
-            // ... and inside the flat part of every lane's Tukey window, partners included: samples are
-            // exact integers there and their products are exact in double, so fma(x, y, acc) rounds
-            // exactly like the reference's multiply-then-add
+            // whole rotation in range?
+            const bool full = ig + H <= n;
+            // ... and inside the flat part of the Tukey window, partners included: samples are exact
+            // integers there and their products are exact in double, so fma(x, y, acc) rounds exactly
+            // like the reference's multiply-then-add
             const bool flat = full && ig >= flat_first && ig + H - 1 <= flat_last;
-            if (FAST && flat) {
-                const u32* rw = (const u32*)row + tbase;
+            // candidate sample t of this lane's row in the staged tile
+            auto fetch = [&](u32 t) -> int {
+                if (FAST) return stereo16_candidate(((const u32*)row)[t], coef, sh);
+                if (!P.stereo) return ld_pcm(row, t * C + cand, B);
+                const int L = ld_pcm(row, t * 2, B), R = ld_pcm(row, t * 2 + 1, B);
+                return cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
+            };
+            if (flat) {
 #pragma unroll
                 for (int u = 0; u < H; u++) {
-                    const int sv = stereo16_candidate(rw[u], coef, sh);
+                    const int sv = fetch(tbase + u);
                     if (LB == 0) orv |= (u32)sv;
                     const double x = int2double_exact(sv);
                     hist[u] = x;
@@ -238,41 +245,16 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
                         a_[l] = __fma_rn(x, hist[partner], a_[l]);
                     }
                 }
-            } else if (FAST) {
+            } else {
                 // tapered part of the window, and the block's last, partial rotation: out-of-range
                 // samples count as zero, which leaves the sums untouched
-                const u32* rw = (const u32*)row + tbase;
                 const double* wp = wt + tbase;
 #pragma unroll
                 for (int u = 0; u < H; u++) {
                     const bool in = full || (ig + u < n);
-                    const int sv = in ? stereo16_candidate(rw[u], coef, sh) : 0;
+                    const int sv = in ? fetch(tbase + u) : 0;
                     if (LB == 0) orv |= (u32)sv;
                     const double x = in ? __dmul_rn(int2double_exact(sv), wp[u]) : 0.0;
-                    hist[u] = x;
-#pragma unroll
-                    for (int l = 0; l < NL; l++) {
-                        const int partner = (u - (LB + l) + 2 * H) % H;
-                        a_[l] = __dadd_rn(a_[l], __dmul_rn(x, hist[partner]));
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < H; u++) {
-                    const u32 t = tbase + u;
-                    const u32 i = i0 + t;
-                    double x = 0.0;
-                    if (valid && i < n) {
-                        int sv;
-                        if (!P.stereo) {
-                            sv = ld_pcm(row, t * C + cand, B);
-                        } else {
-                            const int L = ld_pcm(row, t * 2, B), R = ld_pcm(row, t * 2 + 1, B);
-                            sv = cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
-                        }
-                        orv |= (u32)sv;
-                        x = __dmul_rn(int2double_exact(sv), wt[t]);
-                    }
                     hist[u] = x;
 #pragma unroll
                     for (int l = 0; l < NL; l++) {

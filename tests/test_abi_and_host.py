@@ -127,3 +127,69 @@ def test_two_rank_frame_range_sharding_gloo(built):
     assert table == offs and total == len(flac) - ff
     si = helpers.streaminfo(flac)
     assert (mn, mx) == (si["min_frame"], si["max_frame"])
+
+
+# ---------------------------------------------------------------------------------------------
+# metadata finalisation in C: b200flac_finalize_metadata against the Python
+# restatement of FlacAudio.from_pcm's tail (audiotools/flac.py:1811-1832 -> our audiotools/flac.py).
+# Host-only: the files come from the CPU oracle.
+# ---------------------------------------------------------------------------------------------
+def _python_finalize(path, offsets, interval, mask):
+    from audiotools import flac as aflac
+    f = aflac.FlacAudio(path)
+    md = f.get_metadata()
+    md.add_block(f.seektable(list(offsets), interval))
+    if mask:
+        for i, (bid, payload) in enumerate(md.block_list):
+            if bid == aflac.BLOCK_VORBIS_COMMENT:
+                vlen = int.from_bytes(payload[0:4], "little")
+                count = int.from_bytes(payload[4 + vlen:8 + vlen], "little")
+                comment = ("WAVEFORMATEXTENSIBLE_CHANNEL_MASK=0x%.4X" % mask).encode()
+                md.block_list[i] = (bid, payload[:4 + vlen] + (count + 1).to_bytes(4, "little") + payload[8 + vlen:] +
+                                    len(comment).to_bytes(4, "little") + comment)
+                break
+    f.update_metadata(md)
+
+
+@pytest.mark.parametrize("padding,mask,rate,n", [
+    (4096, 0, 44100, 44100 * 25 + 17),        # three seek points, fits the padding: frames do not move
+    (4096 + 4 + 3 * 18, 0x3F, 44100, 44100 * 25 + 17),   # from_pcm's own padding size, channel-mask tag
+    (0, 0, 8000, 8000 * 31),                  # a zero-length PADDING cannot take the SEEKTABLE: file rewritten
+    (30, 0x0603, 8000, 8000 * 45),            # padding smaller than the growth: rewritten
+    (4096, 0, 44100, 0),                      # empty stream: empty SEEKTABLE
+    (4096, 0, 44100, 100),                    # one short frame
+])
+def test_native_metadata_finalisation_matches_python(padding, mask, rate, n, tmp_path, built):
+    import shutil
+    import b200flac
+    o = helpers.options(block_size=1152, max_lpc_order=0, max_residual_partition_order=2, padding_size=padding)
+    pcm = helpers.synth_pcm(11, 1, 16, n)
+    data, offsets = helpers.oracle_encode(pcm, rate, 1, 16, o, want_offsets=True)
+    a, b = os.path.join(str(tmp_path), "a.flac"), os.path.join(str(tmp_path), "b.flac")
+    with open(a, "wb") as fh:
+        fh.write(data)
+    shutil.copy(a, b)
+    _python_finalize(a, offsets, rate * 10, mask)
+    b200flac.finalize_metadata(b, offsets, rate * 10, mask)
+    got, want = open(b, "rb").read(), open(a, "rb").read()
+    assert got == want
+    # frames are intact and, when the padding could absorb the SEEKTABLE, did not move
+    ff = helpers.first_frame_offset(data)
+    assert want.endswith(data[ff:])
+    if padding >= 4096:
+        assert helpers.first_frame_offset(want) == ff
+    if helpers.have_ref() and n:
+        assert helpers.ref_decode(got) == pcm
+    # interval 0 means 10 s, like FlacAudio.seektable's default
+    shutil.copy(os.path.join(str(tmp_path), "a.flac"), os.path.join(str(tmp_path), "c.flac"))
+
+
+def test_native_metadata_finalisation_errors(tmp_path, built):
+    import b200flac
+    with pytest.raises(b200flac.B200FlacError):
+        b200flac.finalize_metadata(os.path.join(str(tmp_path), "missing.flac"), [(0, 1)])
+    bad = os.path.join(str(tmp_path), "bad.flac")
+    with open(bad, "wb") as fh:
+        fh.write(b"RIFFxxxxWAVE")
+    with pytest.raises(b200flac.B200FlacError):
+        b200flac.finalize_metadata(bad, [(0, 1)])

@@ -116,6 +116,14 @@ def test_from_pcm_every_compression_level(level, tmp_path, built):
     assert first_point == (0, 0, offs[0][1])
     if helpers.have_ref():
         assert helpers.ref_decode(data) == pcm
+    # the C finalisation (default) and the Python restatement of flac.py:1811-1832 write the same file
+    at.FlacAudio.NATIVE_FINALIZE = False
+    try:
+        path2 = os.path.join(str(tmp_path), "p%s.flac" % level)
+        at.FlacAudio.from_pcm(path2, at.PCMBytesReader(pcm, 44100, 2, 0x3, 16), level, total_pcm_frames=n)
+    finally:
+        at.FlacAudio.NATIVE_FINALIZE = True
+    assert open(path2, "rb").read() == data
 
 
 @pytest.mark.gpu
