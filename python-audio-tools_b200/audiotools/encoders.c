@@ -216,12 +216,53 @@ static PyObject *encoders_device_count(PyObject *dummy, PyObject *args)
     return PyLong_FromLong(b200flac_device_count());
 }
 
+/* finalize_flac_metadata(filename, offsets, seekpoint_interval=0, channel_mask=0)
+ * the tail of FlacAudio.from_pcm (audiotools/flac.py:1811-1832) in C: see b200flac_finalize_metadata */
+static PyObject *encoders_finalize_flac_metadata(PyObject *dummy, PyObject *args, PyObject *keywds)
+{
+    static char *kwlist[] = {"filename", "offsets", "seekpoint_interval", "channel_mask", NULL};
+    const char *filename;
+    PyObject *offsets, *seq;
+    unsigned interval = 0, mask = 0;
+    Py_ssize_t n, i;
+    uint64_t *offs;
+    uint32_t *lens;
+    int rc;
+    if (!PyArg_ParseTupleAndKeywords(args, keywds, "sO|II", kwlist, &filename, &offsets, &interval, &mask)) return NULL;
+    if ((seq = PySequence_Fast(offsets, "offsets must be a sequence of (byte_offset, pcm_frames)")) == NULL) return NULL;
+    n = PySequence_Fast_GET_SIZE(seq);
+    offs = malloc(sizeof(uint64_t) * (size_t)(n ? n : 1));
+    lens = malloc(sizeof(uint32_t) * (size_t)(n ? n : 1));
+    if (!offs || !lens) { free(offs); free(lens); Py_DECREF(seq); return PyErr_NoMemory(); }
+    for (i = 0; i < n; i++) {
+        unsigned long long o;
+        unsigned int f;
+        if (!PyArg_ParseTuple(PySequence_Fast_GET_ITEM(seq, i), "KI", &o, &f)) {
+            free(offs); free(lens); Py_DECREF(seq);
+            return NULL;
+        }
+        offs[i] = o;
+        lens[i] = f;
+    }
+    Py_DECREF(seq);
+    Py_BEGIN_ALLOW_THREADS
+    rc = b200flac_finalize_metadata(filename, offs, lens, (uint64_t)n, interval, mask);
+    Py_END_ALLOW_THREADS
+    free(offs);
+    free(lens);
+    if (rc) { PyErr_SetString(PyExc_IOError, b200flac_last_error()); return NULL; }
+    Py_RETURN_NONE;
+}
+
 static PyMethodDef module_methods[] = {
     {"encode_flac", (PyCFunction)encoders_encode_flac, METH_VARARGS | METH_KEYWORDS,
      "encode_flac(filename, pcmreader, block_size, max_lpc_order, min_residual_partition_order, "
      "max_residual_partition_order, mid_side=0, adaptive_mid_side=0, exhaustive_model_search=0, "
      "disable_verbatim_subframes=0, disable_constant_subframes=0, disable_fixed_subframes=0, "
      "disable_lpc_subframes=0, padding_size=4096) -> [(byte_offset, pcm_frames), ...]"},
+    {"finalize_flac_metadata", (PyCFunction)encoders_finalize_flac_metadata, METH_VARARGS | METH_KEYWORDS,
+     "finalize_flac_metadata(filename, offsets, seekpoint_interval=0, channel_mask=0): SEEKTABLE from the "
+     "encoder's offsets, channel-mask tag, PADDING adjustment -- FlacAudio.from_pcm's tail in C"},
     {"b200_device_count", (PyCFunction)encoders_device_count, METH_NOARGS, "usable CUDA devices"},
     {NULL}};
 

@@ -17,16 +17,8 @@ PREFERRED_ORDER = [0, 3, 5, 4, 6, 2, 1]
 
 
 def _native_finalize(filename, offsets, seekpoint_interval, channel_mask):
-    import ctypes as C
     from . import encoders
-    lib = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(encoders.__file__))), "libb200flac.so"))
-    lib.b200flac_last_error.restype = C.c_char_p
-    n = len(offsets)
-    offs = (C.c_uint64 * max(n, 1))(*[o for o, _ in offsets])
-    lens = (C.c_uint32 * max(n, 1))(*[f for _, f in offsets])
-    if lib.b200flac_finalize_metadata(os.fsencode(filename), offs, lens, C.c_uint64(n), C.c_uint32(seekpoint_interval),
-                                      C.c_uint32(channel_mask)):
-        raise IOError(lib.b200flac_last_error().decode())
+    encoders.finalize_flac_metadata(filename, offsets, seekpoint_interval, channel_mask)
 
 
 class FlacMetaData(object):

@@ -196,3 +196,28 @@ def test_from_pcm_multichannel_adds_channel_mask(tmp_path, built):
     assert b"WAVEFORMATEXTENSIBLE_CHANNEL_MASK=0x003F" in vc
     if helpers.have_ref():
         assert helpers.ref_decode(open(path, "rb").read()) == pcm
+
+
+def test_finalize_flac_metadata_extension_entry(tmp_path, built):
+    """audiotools.encoders.finalize_flac_metadata (host only): same file as the Python tail of from_pcm"""
+    import shutil
+    at = _at()
+    from audiotools import encoders, flac as aflac
+    o = helpers.options(block_size=1152, max_lpc_order=0, max_residual_partition_order=2, padding_size=4096)
+    pcm = helpers.synth_pcm(5, 2, 16, 44100 * 21)
+    data, offsets = helpers.oracle_encode(pcm, 44100, 2, 16, o, want_offsets=True)
+    a, b = os.path.join(str(tmp_path), "a.flac"), os.path.join(str(tmp_path), "b.flac")
+    with open(a, "wb") as fh:
+        fh.write(data)
+    shutil.copy(a, b)
+    f = aflac.FlacAudio(a)
+    md = f.get_metadata()
+    md.add_block(f.seektable(list(offsets), 441000))
+    f.update_metadata(md)
+    encoders.finalize_flac_metadata(b, offsets, seekpoint_interval=441000)
+    assert open(b, "rb").read() == open(a, "rb").read()
+    assert [blk[0] for blk in at.FlacAudio(b).get_metadata().block_list] == [0, 3, 4, 1]
+    with pytest.raises(IOError):
+        encoders.finalize_flac_metadata(os.path.join(str(tmp_path), "nope.flac"), offsets)
+    with pytest.raises(TypeError):
+        encoders.finalize_flac_metadata(b, [("x", 1)])
