@@ -611,6 +611,7 @@ static long build_batch(b200flac_encoder* enc, Slot& s, const b200flac_segment* 
     u64 nf = 0, need = 0;
     s.frame_pcm.clear();
     const bool want_windows = enc->P.try_lpc != 0;
+    u32 last_n = 0xFFFFFFFFu, last_woff = 0;
     for (u32 g = 0; g < nseg; g++) {
         const b200flac_segment& sg = segs[g];
         if (sg.pcm_frame_offset + sg.n_pcm_frames > need) need = sg.pcm_frame_offset + sg.n_pcm_frames;
@@ -626,6 +627,9 @@ static long build_batch(b200flac_encoder* enc, Slot& s, const b200flac_segment* 
             d.pad = 0;
             d.window_off = 0;
             if (want_windows) {
+                if (n == last_n) {
+                    d.window_off = last_woff;            // same length as the previous frame: no lookup
+                } else {
                 auto it = woff.find(n);
                 if (it == woff.end()) {
                     if (wused + n > s.win_cap) {
@@ -647,6 +651,8 @@ static long build_batch(b200flac_encoder* enc, Slot& s, const b200flac_segment* 
                     wused += n;
                 }
                 d.window_off = it->second;
+                last_n = n; last_woff = it->second;
+                }
             }
             s.frame_pcm.push_back(n);
             nf++;
