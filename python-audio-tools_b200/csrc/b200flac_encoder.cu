@@ -390,7 +390,7 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     {
         const char* force = getenv("B200FLAC_NO_V3");
         const u32 F = std::min<u32>(P.po_lim, (u32)__builtin_ctz(bs));
-        if (enc->fast && P.try_lpc && P.try_fixed && P.try_constant && P.try_verbatim && !P.exhaustive &&
+        if (enc->fast && P.try_lpc && P.try_fixed && P.try_constant && P.try_verbatim &&
             F <= V3_MAX_F && bs > P.max_lpc_order + 1 && !(force && force[0] == '1')) {
             for (u32 S3 = 32; S3 >= 8; S3 -= 8) {
                 if (bs % S3 || (bs >> F) % S3) continue;
@@ -403,14 +403,19 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
             }
         }
         if (enc->v3) {
-            e = enc->v3_NT <= 128
-                    ? cudaFuncSetAttribute(k_analyze_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem)
-                    : cudaFuncSetAttribute(k_analyze_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem);
+            if (P.exhaustive)
+                e = enc->v3_NT <= 128
+                        ? cudaFuncSetAttribute(k_analyze_v3<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem)
+                        : cudaFuncSetAttribute(k_analyze_v3<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem);
+            else
+                e = enc->v3_NT <= 128
+                        ? cudaFuncSetAttribute(k_analyze_v3<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem)
+                        : cudaFuncSetAttribute(k_analyze_v3<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem);
             if (e != cudaSuccess) enc->v3 = false;
             enc->v3_occ = 1;
             if (enc->v3) {
-                if (enc->v3_NT <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<5>, (int)enc->v3_NT, enc->v3_smem);
-                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<1>, (int)enc->v3_NT, enc->v3_smem);
+                if (enc->v3_NT <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<5, false>, (int)enc->v3_NT, enc->v3_smem);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<1, false>, (int)enc->v3_NT, enc->v3_smem);
                 if (enc->v3_occ < 1) enc->v3_occ = 1;
             }
             cudaDeviceGetAttribute(&enc->n_sms, cudaDevAttrMultiProcessorCount, enc->device);
@@ -719,10 +724,10 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
         u32 g3 = U;
         if (getenv("B200FLAC_V3_GRID")) g3 = (u32)atoi(getenv("B200FLAC_V3_GRID"));   // tuning knob
         if (g3 > U || g3 == 0) g3 = U;
-        if (enc->v3_NT <= 128)
-            k_analyze_v3<5><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, U, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
-        else
-            k_analyze_v3<1><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, U, s.d_heads, s.d_coefs, s.d_plans, s.d_rice);
+#define V3_LAUNCH(MINB_, EXH_) k_analyze_v3<MINB_, EXH_><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, U, s.d_heads, s.d_coefs, s.d_plans, s.d_rice)
+        if (enc->v3_NT <= 128) { if (P.exhaustive) V3_LAUNCH(5, true); else V3_LAUNCH(5, false); }
+        else { if (P.exhaustive) V3_LAUNCH(1, true); else V3_LAUNCH(1, false); }
+#undef V3_LAUNCH
         enc->launches += 1;
         gridv2 = s.n_odd * P.K;      // the other block lengths (a stream's last block)
         flist = s.d_odd;

@@ -23,7 +23,7 @@
 
 #define V3_CH 8
 #define V3_SK(i) ((i) + (((i) >> 5) << 2))      // four words of skew per 32 samples
-#define V3_MAX_F 7                               // finest partition order handled (<= 128 partitions)
+#define V3_MAX_F 7                               // finest partition order handled (<= 128 partitions; order 8 measured slower than k_analyze_v2)
 #define V3_HEAP (2 << V3_MAX_F)
 
 // totals of one partition order of one model (written by whichever warp evaluated the level)
@@ -44,6 +44,7 @@ struct V3Shared {
     short q[BF_MAX_ORDER];
     bf_lpc_head head;
     uint8_t kheap[2][V3_HEAP];
+    uint8_t kbest[V3_HEAP / 2];   // exhaustive search: Rice parameters of the best LPC order so far
 };
 
 // host and device agree on the dynamic shared memory through this
@@ -343,6 +344,9 @@ __device__ __forceinline__ u32 v3_stored_bits(const int* __restrict__ resid, u32
 // S: samples per thread (multiple of 8, <= 32); blockDim.x * S == block_size; F: finest partition
 // order searched, (block_size >> F) a multiple of S.  Units whose block is not block_size long are
 // left to k_analyze_v2 (launched over the same grid, which skips the others).
+// EXH: exhaustive order search (flac.c:1070-1120): FIXED as usual, then every LPC order 1..max in turn
+// (residual, Rice search, exact bits), keeping the first strict minimum of the exact sizes.
+template <bool EXH>
 __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u32 unit,
                                         const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                                         const bf_dev_params& P, u32 S, u32 F,
@@ -368,11 +372,13 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     if (warp == nw - 1) {
         if (lane == 0) sh.head = heads[unit];
         __syncwarp();
-        const u32 o = sh.head.best_order;
-        const int q = lane < o ? (int)mycoef[(o * (o - 1)) / 2 + lane] : 0;
-        sh.q[lane] = (short)q;
-        const u32 sumq = __reduce_add_sync(0xFFFFFFFFu, (u32)abs(q));
-        if (lane == 0) sh.lpc_narrow = sumq;     // turned into the flag once wasted bits are known
+        if (!EXH) {
+            const u32 o = sh.head.best_order;
+            const int q = lane < o ? (int)mycoef[(o * (o - 1)) / 2 + lane] : 0;
+            sh.q[lane] = (short)q;
+            const u32 sumq = __reduce_add_sync(0xFFFFFFFFu, (u32)abs(q));
+            if (lane == 0) sh.lpc_narrow = sumq;     // turned into the flag once wasted bits are known
+        }
     }
     if (tid < 5) { sh.totF[tid] = 0ull; sh.totF16[tid][0] = 0u; sh.totF16[tid][1] = 0u; }
     if (tid < 4) sh.bits16[tid >> 1][tid & 1] = 0u;
@@ -483,21 +489,26 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
             }
         }
     }
-    const u32 lpc_order = sh.head.best_order, precision = sh.head.precision;
-    bool lpc_narrow;
-    const int lpc_shift = sh.head.shift[lpc_order - 1];
-    {
-        const bool narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
+    u32 lpc_order = sh.head.best_order;
+    const u32 precision = sh.head.precision;
+    bool lpc_narrow = false;
+    int lpc_shift = 0;
+    // residual of order o with the coefficients staged in sh.q; returns the thread's run sum
+    auto lpc_pass = [&](u32 o, int shift, bool narrow) -> u64 {
         u64 run;
-        if (lpc_order <= 8) run = narrow ? v3_lpc_residual<8, false>(samp, resid, base, S, sh.q, lpc_shift)
-                                         : v3_lpc_residual<8, true>(samp, resid, base, S, sh.q, lpc_shift);
-        else if (lpc_order <= 12) run = narrow ? v3_lpc_residual<12, false>(samp, resid, base, S, sh.q, lpc_shift)
-                                               : v3_lpc_residual<12, true>(samp, resid, base, S, sh.q, lpc_shift);
-        else run = narrow ? v3_lpc_residual<32, false>(samp, resid, base, S, sh.q, lpc_shift)
-                          : v3_lpc_residual<32, true>(samp, resid, base, S, sh.q, lpc_shift);
-        if (tid == 0) for (u32 i = 0; i < lpc_order; i++) run -= (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions
-        runsL[tid] = run;
-        lpc_narrow = narrow;
+        if (o <= 8) run = narrow ? v3_lpc_residual<8, false>(samp, resid, base, S, sh.q, shift)
+                                 : v3_lpc_residual<8, true>(samp, resid, base, S, sh.q, shift);
+        else if (o <= 12) run = narrow ? v3_lpc_residual<12, false>(samp, resid, base, S, sh.q, shift)
+                                       : v3_lpc_residual<12, true>(samp, resid, base, S, sh.q, shift);
+        else run = narrow ? v3_lpc_residual<32, false>(samp, resid, base, S, sh.q, shift)
+                          : v3_lpc_residual<32, true>(samp, resid, base, S, sh.q, shift);
+        if (tid == 0) for (u32 i = 0; i < o; i++) run -= (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions
+        return run;
+    };
+    if (!EXH) {
+        lpc_shift = sh.head.shift[lpc_order - 1];
+        lpc_narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
+        runsL[tid] = lpc_pass(lpc_order, lpc_shift, lpc_narrow);
     }
     __syncthreads();                                                             // (2)
 
@@ -515,7 +526,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     // over the warps with the unit so that no scheduler always gets the extra work ----
     {
         const u32 role = (nw & (nw - 1)) == 0 ? ((warp - unit) & (nw - 1)) : (warp + nw - unit % nw) % nw;
-        for (u32 task = role; task < 4; task += nw) {
+        for (u32 task = role; task < (EXH ? 2u : 4u); task += nw) {
             // prefix sums go to the run-sum rows of two FIXED orders that lost
             if (task < 2)
                 v3_levels(runsF + (size_t)fixed_order * nt, sh.corr[fixed_order], S, n, fixed_order, F, P.max_rice,
@@ -528,28 +539,72 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     __syncthreads();                                                             // (3)
 
     // ---- pass B: exact bits of both models ----
-    u32 poF, poL, methodF, methodL;
-    u64 sideF, sideL;
+    u32 poF, poL = 0, methodF, methodL = 0;
+    u64 sideF, sideL = 0;
     v3_pick_level(sh.lvl[0], F, &poF, &methodF, &sideF);
-    v3_pick_level(sh.lvl[1], F, &poL, &methodL, &sideL);
+    if (!EXH) v3_pick_level(sh.lvl[1], F, &poL, &methodL, &sideL);
     {
         const u32 kF = sh.kheap[0][(1u << poF) - 1u + base / (n >> poF)];
-        const u32 kL = sh.kheap[1][(1u << poL) - 1u + base / (n >> poL)];
-        u32 bF = v3_fixed_bits_any(samp, base, S, kF, fixed_order, tid == 0 ? 1u : 0u);
-        u32 bL = v3_stored_bits(resid, base, S, kL, tid == 0 ? lpc_order : 0u);
         // a warp's sum stays far below 2^32 (each run's is bounded by ~2 * partition length + 32 * 2^18)
-        bF = __reduce_add_sync(0xFFFFFFFFu, bF);
-        bL = __reduce_add_sync(0xFFFFFFFFu, bL);
-        if (lane == 0) {
-            atomicAdd(&sh.bits16[0][0], bF & 0xFFFFu); atomicAdd(&sh.bits16[0][1], bF >> 16);
-            atomicAdd(&sh.bits16[1][0], bL & 0xFFFFu); atomicAdd(&sh.bits16[1][1], bL >> 16);
+        const u32 bF = __reduce_add_sync(0xFFFFFFFFu, v3_fixed_bits_any(samp, base, S, kF, fixed_order, tid == 0 ? 1u : 0u));
+        if (lane == 0) { atomicAdd(&sh.bits16[0][0], bF & 0xFFFFu); atomicAdd(&sh.bits16[0][1], bF >> 16); }
+        if (!EXH) {
+            const u32 kL = sh.kheap[1][(1u << poL) - 1u + base / (n >> poL)];
+            const u32 bL = __reduce_add_sync(0xFFFFFFFFu, v3_stored_bits(resid, base, S, kL, tid == 0 ? lpc_order : 0u));
+            if (lane == 0) { atomicAdd(&sh.bits16[1][0], bL & 0xFFFFu); atomicAdd(&sh.bits16[1][1], bL >> 16); }
         }
     }
     __syncthreads();                                                             // (4)
 
+    u64 lpc_bits = 0;
+    if (!EXH) {
+        lpc_bits = hdr_bits + (u64)lpc_order * sub_bps + 4 + 5 + (u64)lpc_order * precision + sideL +
+                   (u64)sh.bits16[1][0] + ((u64)sh.bits16[1][1] << 16);
+    } else {
+        // ---- every LPC order in turn; `unsigned best_bits = UINT_MAX`, strict <, ascending (flac.c:1079-1108) ----
+        u32 best32 = 0xFFFFFFFFu;
+        bool have = false;
+        const u32 role = (nw & (nw - 1)) == 0 ? ((warp - unit) & (nw - 1)) : (warp + nw - unit % nw) % nw;
+        for (u32 o = 1; o <= P.max_lpc_order; o++) {
+            if (warp == nw - 1) {
+                const int q = lane < o ? (int)mycoef[(o * (o - 1)) / 2 + lane] : 0;
+                sh.q[lane] = (short)q;
+                const u32 sumq = __reduce_add_sync(0xFFFFFFFFu, (u32)abs(q));
+                if (lane == 0) sh.lpc_narrow = sumq;
+            }
+            __syncthreads();
+            if (tid < 2) sh.bits16[1][tid] = 0u;     // everyone has read the previous order's sum by now
+            const int shift = sh.head.shift[o - 1];
+            const bool narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
+            runsL[tid] = lpc_pass(o, shift, narrow);
+            __syncthreads();
+            for (u32 task = role; task < 2; task += nw)
+                v3_levels(runsL, 0ull, S, n, o, F, P.max_rice, sh.kheap[1], sh.lvl[1],
+                          runsF + (size_t)((fixed_order + 2) % 5) * nt, task);
+            __syncthreads();
+            u32 po, method;
+            u64 side;
+            v3_pick_level(sh.lvl[1], F, &po, &method, &side);
+            const u32 kL = sh.kheap[1][(1u << po) - 1u + base / (n >> po)];
+            const u32 bL = __reduce_add_sync(0xFFFFFFFFu, v3_stored_bits(resid, base, S, kL, tid == 0 ? o : 0u));
+            if (lane == 0) { atomicAdd(&sh.bits16[1][0], bL & 0xFFFFu); atomicAdd(&sh.bits16[1][1], bL >> 16); }
+            __syncthreads();
+            const u64 bits = hdr_bits + (u64)o * sub_bps + 4 + 5 + (u64)o * precision + side +
+                             (u64)sh.bits16[1][0] + ((u64)sh.bits16[1][1] << 16);
+            if (!have || (u32)bits < best32) {
+                have = true;
+                best32 = (u32)bits;
+                lpc_bits = bits; lpc_order = o; lpc_shift = shift; lpc_narrow = narrow;
+                poL = po; methodL = method;
+                const u32 koff = (1u << po) - 1u;
+                for (u32 p = tid; p < (1u << po); p += nt) sh.kbest[p] = sh.kheap[1][koff + p];
+            }
+        }
+        __syncthreads();
+    }
+
     // ---- choice, flac.c:727-809 (every subframe type enabled) ----
     const u64 fixed_bits = hdr_bits + (u64)fixed_order * sub_bps + sideF + (u64)sh.bits16[0][0] + ((u64)sh.bits16[0][1] << 16);
-    const u64 lpc_bits = hdr_bits + (u64)lpc_order * sub_bps + 4 + 5 + (u64)lpc_order * precision + sideL + (u64)sh.bits16[1][0] + ((u64)sh.bits16[1][1] << 16);
     const u32 fb = (u32)fixed_bits, lb = (u32)lpc_bits;
     const u32 vb = sub_bps * n;                       // header NOT counted (H2)
     const u32 choice = (fb < min(lb, vb)) ? BF_FIXED : (lb < vb) ? BF_LPC : BF_VERBATIM;
@@ -559,7 +614,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
         for (u32 p = tid; p < (1u << poF); p += nt) my_rice[p] = sh.kheap[0][koff + p];
     } else if (choice == BF_LPC) {
         const u32 koff = (1u << poL) - 1u;
-        for (u32 p = tid; p < (1u << poL); p += nt) my_rice[p] = sh.kheap[1][koff + p];
+        for (u32 p = tid; p < (1u << poL); p += nt) my_rice[p] = EXH ? sh.kbest[p] : sh.kheap[1][koff + p];
     }
     if (tid == 0) {
         b200flac_plan plan;
@@ -575,7 +630,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
             plan.coding_method = (uint8_t)methodL; plan.partition_order = (uint8_t)poL;
             plan.flags = lpc_narrow ? 2 : 0;          // packer may accumulate in 32 bits
             plan.bits = lb;
-            for (u32 j = 0; j < lpc_order; j++) plan.coeffs[j] = sh.q[j];
+            for (u32 j = 0; j < lpc_order; j++) plan.coeffs[j] = EXH ? mycoef[(lpc_order * (lpc_order - 1)) / 2 + j] : sh.q[j];
         } else {
             plan.type = BF_VERBATIM;
             plan.bits = hdr_bits + sub_bps * n;       // flac.c:832-854
@@ -587,7 +642,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
 // The grid is normally one CTA per unit; any smaller grid walks the units with the grid's stride
 // (measured: a persistent single wave keeps the CTAs of an SM in the same phase of the unit, which
 // overlaps their load and search phases worse than staggered CTAs do).
-template <int MINB>
+template <int MINB, bool EXH>
 __global__ void __launch_bounds__(512 / (MINB >= 5 ? 4 : 1), MINB)
 k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S, u32 F,
              u32 n_units, const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
@@ -596,7 +651,7 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ V3Shared sh;
     for (u32 unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        v3_unit(dyn_smem, sh, unit, pcm, fd, P, S, F, heads, coefs, plans, rice_out);
+        v3_unit<EXH>(dyn_smem, sh, unit, pcm, fd, P, S, F, heads, coefs, plans, rice_out);
         __syncthreads();        // shared memory is reused by the next unit
     }
 }
