@@ -403,19 +403,16 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
             }
         }
         if (enc->v3) {
-            if (P.exhaustive)
-                e = enc->v3_NT <= 128
-                        ? cudaFuncSetAttribute(k_analyze_v3<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem)
-                        : cudaFuncSetAttribute(k_analyze_v3<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem);
-            else
-                e = enc->v3_NT <= 128
-                        ? cudaFuncSetAttribute(k_analyze_v3<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem)
-                        : cudaFuncSetAttribute(k_analyze_v3<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem);
+            const bool s32 = enc->v3_NT <= 128 && enc->v3_S == 32;   // samples per thread known at compile time
+#define V3_ATTR(MINB_, EXH_, SC_) cudaFuncSetAttribute(k_analyze_v3<MINB_, EXH_, SC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem)
+            if (P.exhaustive) e = s32 ? V3_ATTR(5, true, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, true, 0) : V3_ATTR(1, true, 0);
+            else e = s32 ? V3_ATTR(5, false, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, false, 0) : V3_ATTR(1, false, 0);
+#undef V3_ATTR
             if (e != cudaSuccess) enc->v3 = false;
             enc->v3_occ = 1;
             if (enc->v3) {
-                if (enc->v3_NT <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<5, false>, (int)enc->v3_NT, enc->v3_smem);
-                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<1, false>, (int)enc->v3_NT, enc->v3_smem);
+                if (enc->v3_NT <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<5, false, 0>, (int)enc->v3_NT, enc->v3_smem);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<1, false, 0>, (int)enc->v3_NT, enc->v3_smem);
                 if (enc->v3_occ < 1) enc->v3_occ = 1;
             }
             cudaDeviceGetAttribute(&enc->n_sms, cudaDevAttrMultiProcessorCount, enc->device);
@@ -724,9 +721,10 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
         u32 g3 = U;
         if (getenv("B200FLAC_V3_GRID")) g3 = (u32)atoi(getenv("B200FLAC_V3_GRID"));   // tuning knob
         if (g3 > U || g3 == 0) g3 = U;
-#define V3_LAUNCH(MINB_, EXH_) k_analyze_v3<MINB_, EXH_><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, U, s.d_heads, s.d_coefs, s.d_plans, s.d_rice)
-        if (enc->v3_NT <= 128) { if (P.exhaustive) V3_LAUNCH(5, true); else V3_LAUNCH(5, false); }
-        else { if (P.exhaustive) V3_LAUNCH(1, true); else V3_LAUNCH(1, false); }
+#define V3_LAUNCH(MINB_, EXH_, SC_) k_analyze_v3<MINB_, EXH_, SC_><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, U, s.d_heads, s.d_coefs, s.d_plans, s.d_rice)
+        if (enc->v3_NT <= 128 && enc->v3_S == 32) { if (P.exhaustive) V3_LAUNCH(5, true, 32); else V3_LAUNCH(5, false, 32); }
+        else if (enc->v3_NT <= 128) { if (P.exhaustive) V3_LAUNCH(5, true, 0); else V3_LAUNCH(5, false, 0); }
+        else { if (P.exhaustive) V3_LAUNCH(1, true, 0); else V3_LAUNCH(1, false, 0); }
 #undef V3_LAUNCH
         enc->launches += 1;
         gridv2 = s.n_odd * P.K;      // the other block lengths (a stream's last block)

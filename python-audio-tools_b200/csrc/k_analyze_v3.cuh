@@ -284,6 +284,13 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
     return run;
 }
 
+// zigzag(r) >> k for k >= 1 without forming zigzag(r): with t = r >= 0 ? r : ~r, zigzag(r) = 2 t + (r < 0),
+// and the low bit falls off: (2 t + s) >> k == t >> (k - 1)
+__device__ __forceinline__ u32 v3_fold_shift(int r, u32 km1)
+{
+    return ((u32)(r ^ (r >> 31))) >> km1;
+}
+
 // sum of (zigzag(r) >> k) over the thread's run for the FIXED residual of ORDER, recomputed from
 // the samples (the sum fits 32 bits: see the Rice parameter rule, flac.c:1478)
 template <int ORDER>
@@ -307,7 +314,7 @@ __device__ __forceinline__ u32 v3_fixed_bits(const int* __restrict__ samp, u32 b
                         p3 = d3; }
                     p2 = d2; }
                 p1 = d1; prev = x; }
-            const u32 t = zigzag((int)v) >> k;
+            const u32 t = k ? v3_fold_shift((int)v, k - 1) : zigzag((int)v);
             acc += t;
             if (ORDER > 0 && j < ORDER && i0 == base) head += t;   // warm-up positions (only matter for run 0)
         }
@@ -331,11 +338,21 @@ __device__ __forceinline__ u32 v3_fixed_bits_any(const int* __restrict__ samp, u
 __device__ __forceinline__ u32 v3_stored_bits(const int* __restrict__ resid, u32 base, u32 S, u32 k, u32 skip)
 {
     u32 acc = 0;
-    for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
-        const int4 va = *(const int4*)(resid + V3_SK(i0));
-        const int4 vb = *(const int4*)(resid + V3_SK(i0) + 4);
-        acc += (zigzag(va.x) >> k) + (zigzag(va.y) >> k) + (zigzag(va.z) >> k) + (zigzag(va.w) >> k);
-        acc += (zigzag(vb.x) >> k) + (zigzag(vb.y) >> k) + (zigzag(vb.z) >> k) + (zigzag(vb.w) >> k);
+    if (k) {
+        const u32 km1 = k - 1;
+        for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+            const int4 va = *(const int4*)(resid + V3_SK(i0));
+            const int4 vb = *(const int4*)(resid + V3_SK(i0) + 4);
+            acc += v3_fold_shift(va.x, km1) + v3_fold_shift(va.y, km1) + v3_fold_shift(va.z, km1) + v3_fold_shift(va.w, km1);
+            acc += v3_fold_shift(vb.x, km1) + v3_fold_shift(vb.y, km1) + v3_fold_shift(vb.z, km1) + v3_fold_shift(vb.w, km1);
+        }
+    } else {
+        for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+            const int4 va = *(const int4*)(resid + V3_SK(i0));
+            const int4 vb = *(const int4*)(resid + V3_SK(i0) + 4);
+            acc += zigzag(va.x) + zigzag(va.y) + zigzag(va.z) + zigzag(va.w);
+            acc += zigzag(vb.x) + zigzag(vb.y) + zigzag(vb.z) + zigzag(vb.w);
+        }
     }
     for (u32 i = 0; i < skip; i++) acc -= zigzag(resid[V3_SK(base + i)]) >> k;
     return acc;
@@ -346,13 +363,14 @@ __device__ __forceinline__ u32 v3_stored_bits(const int* __restrict__ resid, u32
 // left to k_analyze_v2 (launched over the same grid, which skips the others).
 // EXH: exhaustive order search (flac.c:1070-1120): FIXED as usual, then every LPC order 1..max in turn
 // (residual, Rice search, exact bits), keeping the first strict minimum of the exact sizes.
-template <bool EXH>
+template <bool EXH, int SC>
 __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u32 unit,
                                         const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
-                                        const bf_dev_params& P, u32 S, u32 F,
+                                        const bf_dev_params& P, u32 S_rt, u32 F,
                                         const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
                                         b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out)
 {
+    const u32 S = SC ? (u32)SC : S_rt;       // samples per thread: a compile-time 32 for the common shapes
     const u32 tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     const u32 frame = unit / P.K, cand = unit % P.K;
     const bf_frame_desc d = fd[frame];
@@ -539,17 +557,20 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     __syncthreads();                                                             // (3)
 
     // ---- pass B: exact bits of both models ----
+    // finest partition this thread's run lies in (its partition at order po is pF >> (F - po))
+    const u32 gruns = (n >> F) / S;
+    const u32 pF = (gruns & (gruns - 1)) == 0 ? tid >> (31 - __clz((int)gruns)) : tid / gruns;
     u32 poF, poL = 0, methodF, methodL = 0;
     u64 sideF, sideL = 0;
     v3_pick_level(sh.lvl[0], F, &poF, &methodF, &sideF);
     if (!EXH) v3_pick_level(sh.lvl[1], F, &poL, &methodL, &sideL);
     {
-        const u32 kF = sh.kheap[0][(1u << poF) - 1u + base / (n >> poF)];
+        const u32 kF = sh.kheap[0][(1u << poF) - 1u + (pF >> (F - poF))];
         // a warp's sum stays far below 2^32 (each run's is bounded by ~2 * partition length + 32 * 2^18)
         const u32 bF = __reduce_add_sync(0xFFFFFFFFu, v3_fixed_bits_any(samp, base, S, kF, fixed_order, tid == 0 ? 1u : 0u));
         if (lane == 0) { atomicAdd(&sh.bits16[0][0], bF & 0xFFFFu); atomicAdd(&sh.bits16[0][1], bF >> 16); }
         if (!EXH) {
-            const u32 kL = sh.kheap[1][(1u << poL) - 1u + base / (n >> poL)];
+            const u32 kL = sh.kheap[1][(1u << poL) - 1u + (pF >> (F - poL))];
             const u32 bL = __reduce_add_sync(0xFFFFFFFFu, v3_stored_bits(resid, base, S, kL, tid == 0 ? lpc_order : 0u));
             if (lane == 0) { atomicAdd(&sh.bits16[1][0], bL & 0xFFFFu); atomicAdd(&sh.bits16[1][1], bL >> 16); }
         }
@@ -585,7 +606,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
             u32 po, method;
             u64 side;
             v3_pick_level(sh.lvl[1], F, &po, &method, &side);
-            const u32 kL = sh.kheap[1][(1u << po) - 1u + base / (n >> po)];
+            const u32 kL = sh.kheap[1][(1u << po) - 1u + (pF >> (F - po))];
             const u32 bL = __reduce_add_sync(0xFFFFFFFFu, v3_stored_bits(resid, base, S, kL, tid == 0 ? o : 0u));
             if (lane == 0) { atomicAdd(&sh.bits16[1][0], bL & 0xFFFFu); atomicAdd(&sh.bits16[1][1], bL >> 16); }
             __syncthreads();
@@ -642,7 +663,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
 // The grid is normally one CTA per unit; any smaller grid walks the units with the grid's stride
 // (measured: a persistent single wave keeps the CTAs of an SM in the same phase of the unit, which
 // overlaps their load and search phases worse than staggered CTAs do).
-template <int MINB, bool EXH>
+template <int MINB, bool EXH, int SC>
 __global__ void __launch_bounds__(512 / (MINB >= 5 ? 4 : 1), MINB)
 k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S, u32 F,
              u32 n_units, const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
@@ -651,7 +672,7 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ V3Shared sh;
     for (u32 unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        v3_unit<EXH>(dyn_smem, sh, unit, pcm, fd, P, S, F, heads, coefs, plans, rice_out);
+        v3_unit<EXH, SC>(dyn_smem, sh, unit, pcm, fd, P, S, F, heads, coefs, plans, rice_out);
         __syncthreads();        // shared memory is reused by the next unit
     }
 }
