@@ -462,9 +462,11 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
                 cudaMemcpy(enc->d_crc_tab, t.data(), t.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess) {
                 enc->p3 = false;
             } else {
-                e = 2 * enc->NT <= 256
-                        ? cudaFuncSetAttribute(k_pack_v3<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
-                        : cudaFuncSetAttribute(k_pack_v3<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                e = 2 * enc->NT <= 256 && enc->S == 32
+                        ? cudaFuncSetAttribute(k_pack_v3<256, 4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+                    : 2 * enc->NT <= 256
+                        ? cudaFuncSetAttribute(k_pack_v3<256, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+                        : cudaFuncSetAttribute(k_pack_v3<1024, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
                 if (e != cudaSuccess) enc->p3 = false;
                 e = cudaSuccess;
             }
@@ -741,14 +743,13 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
     k_scan_offsets<<<1, 1024, 0, st>>>(s.d_frame_bytes, nf, s.d_frame_off, s.d_total);
     if (enc->p3) {
         cudaEventRecord(s.ev[3], st);
-        if (2 * enc->NT <= 256)
-            k_pack_v3<256, 4><<<nf, 2 * enc->NT, enc->p3_smem, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
-                                                                     s.d_frame_off, d_out, s.d_total, out_cap, enc->p3_img_words,
-                                                                     enc->d_crc_tab, enc->d_crc_tab + 512);
-        else
-            k_pack_v3<1024, 1><<<nf, 2 * enc->NT, enc->p3_smem, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice,
-                                                                      s.d_frame_off, d_out, s.d_total, out_cap, enc->p3_img_words,
-                                                                      enc->d_crc_tab, enc->d_crc_tab + 512);
+#define P3_LAUNCH(NTMAX_, MINB_, SC_) k_pack_v3<NTMAX_, MINB_, SC_><<<nf, 2 * enc->NT, enc->p3_smem, st>>>( \
+            d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice, s.d_frame_off, d_out, s.d_total, out_cap, \
+            enc->p3_img_words, enc->d_crc_tab, enc->d_crc_tab + 512)
+        if (2 * enc->NT <= 256 && enc->S == 32) P3_LAUNCH(256, 4, 32);
+        else if (2 * enc->NT <= 256) P3_LAUNCH(256, 4, 0);
+        else P3_LAUNCH(1024, 1, 0);
+#undef P3_LAUNCH
         cudaEventRecord(s.ev[4], st);
         cudaEventRecord(s.ev[5], st);
         enc->launches += 3 + (gridv2 ? 1 : 0);

@@ -206,9 +206,9 @@ __host__ __device__ inline size_t p3_smem_bytes(u32 block_size, u32 img_words)
 // blockDim.x = 2 * gt; gt * S >= block_size; S a multiple of 8.
 //   crc_tab[2][256]: CRC-16 of one byte followed by 0..1 zero bytes; crc_pow[0..68] = x^(8 r), crc_pow[69 + j] = x^(8 * 68 * j) mod the
 //   CRC-16 polynomial (built by the host).
-template <int NTMAX, int MINB>
+template <int NTMAX, int MINB, int SC>
 __global__ void __launch_bounds__(NTMAX, MINB)
-k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S,
+k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S_rt,
           const b200flac_plan* __restrict__ plans, const uint8_t* __restrict__ rice,
           const bf_frame_choice* __restrict__ choice, const u64* __restrict__ frame_off,
           uint8_t* __restrict__ out, const u64* __restrict__ total, u64 capacity_bytes, u32 img_words,
@@ -217,6 +217,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
     if (*total + 16 > capacity_bytes) return;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ P3Shared sh;
+    const u32 S = SC ? (u32)SC : S_rt;       // samples per thread: a compile-time 32 for the common shapes
 
     const u32 tid = threadIdx.x, nt = blockDim.x, gt = nt >> 1;
     const u32 g = tid / gt, gtid = tid - g * gt;
