@@ -86,6 +86,13 @@ struct RunSink3 {
     }
 };
 
+// a Rice code longer than 32 bits: a run of zeros, then the stop bit and the k low bits (rare)
+__device__ __forceinline__ void p3_put_long(RunSink3& bs, u32 msb, u32 code, u32 k)
+{
+    bs.zeros(msb);
+    bs.put(code, k + 1);
+}
+
 struct P3Shared {
     b200flac_plan plan[2];
     bf_frame_choice choice;
@@ -102,7 +109,8 @@ struct P3Count {
     const uint8_t* krice;
 };
 
-__device__ __forceinline__ void p3_count_chunk(const u32 (&u)[8], u32 i0, const P3Count& c, u32& p, u32& next, u32& k, u32& mybits)
+__device__ __forceinline__ void p3_count_chunk(const u32 (&u)[8], const int* __restrict__ buf, u32 i0, const P3Count& c,
+                                               u32& p, u32& next, u32& k, u32& mybits)
 {
     if (i0 >= c.lo && i0 + 8 <= c.hi && i0 + 8 <= next) {
         u32 a = 0;
@@ -110,13 +118,12 @@ __device__ __forceinline__ void p3_count_chunk(const u32 (&u)[8], u32 i0, const 
         for (int j = 0; j < 8; j++) a += u[j] >> k;
         mybits += a + 8 * (1u + k);
     } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const u32 i = i0 + j;
-            if (i >= c.lo && i < c.hi) {
-                if (i == next) { p++; next += c.plen; k = c.krice[p]; mybits += c.kbits; }
-                mybits += (u[j] >> k) + 1u + k;
-            }
+        // rare (warm-up samples, a partition boundary inside the chunk, the block's tail): a rolled loop
+        // over the folded residuals just stored, to keep the hot code small
+#pragma unroll 1
+        for (u32 i = max(i0, c.lo); i < min(i0 + 8, c.hi); i++) {
+            if (i == next) { p++; next += c.plen; k = c.krice[p]; mybits += c.kbits; }
+            mybits += ((u32)buf[V3_SK(i)] >> k) + 1u + k;
         }
     }
     if (i0 + 8 == next && i0 + 8 < c.hi) { p++; next += c.plen; k = c.krice[p]; mybits += c.kbits; }
@@ -162,7 +169,7 @@ __device__ __forceinline__ u32 p3_lpc_inplace(int* __restrict__ buf, u32 base, u
         }
         *(uint4*)(buf + V3_SK(i0)) = make_uint4(u[0], u[1], u[2], u[3]);
         *(uint4*)(buf + V3_SK(i0) + 4) = make_uint4(u[4], u[5], u[6], u[7]);
-        p3_count_chunk(u, i0, c, p, next, k, mybits);
+        p3_count_chunk(u, buf, i0, c, p, next, k, mybits);
 #pragma unroll
         for (int t = 0; t < OG; t++) w[t] = w[t + 8];
     }
@@ -191,7 +198,7 @@ __device__ __forceinline__ u32 p3_fixed_inplace(int* __restrict__ buf, u32 base,
         }
         *(uint4*)(buf + V3_SK(i0)) = make_uint4(u[0], u[1], u[2], u[3]);
         *(uint4*)(buf + V3_SK(i0) + 4) = make_uint4(u[4], u[5], u[6], u[7]);
-        p3_count_chunk(u, i0, c, p, next, k, mybits);
+        p3_count_chunk(u, buf, i0, c, p, next, k, mybits);
     }
     return mybits;
 }
@@ -403,20 +410,17 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                                 const u32 msb = u >> k;
                                 const u32 code = kone | (u & kmask);
                                 if (msb + k + 1 <= 32) bs.put(code, msb + k + 1);
-                                else { bs.zeros(msb); bs.put(code, k + 1); }
+                                else p3_put_long(bs, msb, code, k);
                             }
                         } else {
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const u32 i = i0 + j;
-                                if (i >= c.lo && i < c.hi) {
-                                    if (i == next) { p++; next += plen; k = krice[p]; bs.put(k, kbits); }
-                                    const u32 u = us[j];
-                                    const u32 msb = u >> k;
-                                    const u32 code = (1u << k) | (u & ((1u << k) - 1u));
-                                    if (msb + k + 1 <= 32) bs.put(code, msb + k + 1);
-                                    else { bs.zeros(msb); bs.put(code, k + 1); }
-                                }
+#pragma unroll 1
+                            for (u32 i = max(i0, c.lo); i < min(i0 + 8, c.hi); i++) {
+                                if (i == next) { p++; next += plen; k = krice[p]; bs.put(k, kbits); }
+                                const u32 u = (u32)buf[V3_SK(i)];
+                                const u32 msb = u >> k;
+                                const u32 code = (1u << k) | (u & ((1u << k) - 1u));
+                                if (msb + k + 1 <= 32) bs.put(code, msb + k + 1);
+                                else p3_put_long(bs, msb, code, k);
                             }
                         }
                         if (i0 + 8 == next && i0 + 8 < c.hi) { p++; next += plen; k = krice[p]; bs.put(k, kbits); }
