@@ -433,9 +433,9 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         const size_t sm = p3_smem_bytes(bs, iw);
         if (sm <= 200 * 1024 && 2 * enc->NT <= 1024) {
             enc->p3 = true; enc->p3_img_words = iw; enc->p3_smem = sm;
-            // CRC-16 tables: byte table, x^(8 r) for r <= 68, x^(8 * 68 * j)
+            // CRC-16 tables: byte tables, x^(8 r) for r <= CHUNK, x^(8 * CHUNK * j)
             const u32 nchunks = (u32)(fb / P3_CHUNK_BYTES + 4);
-            std::vector<unsigned short> t(512 + 69 + nchunks);
+            std::vector<unsigned short> t(512 + P3_CHUNK_BYTES + 1 + nchunks);
             for (u32 b = 0; b < 256; b++) {
                 u32 c = b << 8;
                 for (int k = 0; k < 8; k++) c = (c & 0x8000) ? ((c << 1) ^ 0x8005) & 0xFFFF : (c << 1) & 0xFFFF;
@@ -454,10 +454,10 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
                 return r;
             };
             u32 x8 = 0x100, acc = 1;                 // x^8
-            for (u32 r = 0; r <= 68; r++) { t[512 + r] = (unsigned short)acc; acc = mul(acc, x8); }
-            const u32 xc = t[512 + 68];              // x^(8 * 68)
+            for (u32 r = 0; r <= P3_CHUNK_BYTES; r++) { t[512 + r] = (unsigned short)acc; acc = mul(acc, x8); }
+            const u32 xc = t[512 + P3_CHUNK_BYTES];  // x^(8 * CHUNK)
             acc = 1;
-            for (u32 j = 0; j < nchunks; j++) { t[512 + 69 + j] = (unsigned short)acc; acc = mul(acc, xc); }
+            for (u32 j = 0; j < nchunks; j++) { t[512 + P3_CHUNK_BYTES + 1 + j] = (unsigned short)acc; acc = mul(acc, xc); }
             if (cudaMalloc((void**)&enc->d_crc_tab, t.size() * sizeof(unsigned short)) != cudaSuccess ||
                 cudaMemcpy(enc->d_crc_tab, t.data(), t.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess) {
                 enc->p3 = false;

@@ -6,7 +6,7 @@
 //     of the frame at its final bit offset (the subframe sizes are known from the analysis);
 //   * the chosen model's residual is computed IN PLACE over the samples (history first, then a group
 //     barrier), zig-zag folded and bit-counted in the same pass;
-//   * the frame's CRC-16 is computed from the image: 68-byte chunks (17 words: consecutive threads
+//   * the frame's CRC-16 is computed from the image: 60-byte chunks (15 words: consecutive threads
 //     hit different banks), one table CRC per thread, chunk results moved to their position with one
 //     GF(2) multiply by a tabulated power of x, XOR-reduced;
 //   * the finished frame goes to its byte offset in the output with coalesced 32-bit stores (a byte
@@ -18,8 +18,8 @@
 #include "k_pack_v2.cuh"
 #include "k_analyze_v3.cuh"
 
-#define P3_CHUNK_WORDS 17
-#define P3_CHUNK_BYTES 68
+#define P3_CHUNK_WORDS 15      // odd: consecutive threads' chunks start in different banks; ~1 chunk per thread
+#define P3_CHUNK_BYTES 60
 
 __device__ __forceinline__ void p3_group_bar(u32 g, u32 gt)
 {
@@ -91,6 +91,17 @@ __device__ __forceinline__ void p3_put_long(RunSink3& bs, u32 msb, u32 code, u32
 {
     bs.zeros(msb);
     bs.put(code, k + 1);
+}
+
+// a * b modulo the CRC-16 polynomial: 16 shift-and-add steps, then the upper half is folded back with
+// the byte tables (the CRC of the two-byte message `hi` is hi * x^16 mod P)
+__device__ __forceinline__ u32 p3_gf16_mul(u32 a, u32 b, const unsigned short* tab)
+{
+    u32 r = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) r ^= ((b >> i) & 1u) ? (a << i) : 0u;
+    const u32 hi = r >> 16;
+    return (r & 0xFFFFu) ^ (u32)tab[256 + (hi >> 8)] ^ (u32)tab[hi & 0xFF];
 }
 
 struct P3Shared {
@@ -211,7 +222,7 @@ __host__ __device__ inline size_t p3_smem_bytes(u32 block_size, u32 img_words)
 }
 
 // blockDim.x = 2 * gt; gt * S >= block_size; S a multiple of 8.
-//   crc_tab[2][256]: CRC-16 of one byte followed by 0..1 zero bytes; crc_pow[0..68] = x^(8 r), crc_pow[69 + j] = x^(8 * 68 * j) mod the
+//   crc_tab[2][256]: CRC-16 of one byte followed by 0..1 zero bytes; crc_pow[0..CHUNK] = x^(8 r), crc_pow[CHUNK + 1 + j] = x^(8 * CHUNK * j), CHUNK = 60 bytes, mod the
 //   CRC-16 polynomial (built by the host).
 template <int NTMAX, int MINB, int SC>
 __global__ void __launch_bounds__(NTMAX, MINB)
@@ -465,7 +476,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
             const u32 w = *wp;
             for (u32 i = 0; b < b1; b++, i++) crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ ((w >> (24 - 8 * i)) & 0xFF)];
         }
-        if (c + 1 < T) acc ^= gf16_mul(crc, (u32)crc_pow[69 + (T - 2 - c)]);
+        if (c + 1 < T) acc ^= p3_gf16_mul(crc, (u32)crc_pow[P3_CHUNK_BYTES + 1 + (T - 2 - c)], tab);
         else sh.crc_last = crc;
     }
 #pragma unroll
@@ -478,8 +489,8 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
     if (tid == 0) {
         u32 a = 0;
         for (u32 w = 0; w < (nt >> 5); w++) a ^= sh.crc_part[w];
-        const u32 r = nb - (T - 1) * P3_CHUNK_BYTES;          // bytes of the last chunk, 1..68
-        const u32 crc = gf16_mul(a, (u32)crc_pow[r]) ^ sh.crc_last;
+        const u32 r = nb - (T - 1) * P3_CHUNK_BYTES;          // bytes of the last chunk, 1..60
+        const u32 crc = p3_gf16_mul(a, (u32)crc_pow[r], tab) ^ sh.crc_last;
         dst[nb] = (uint8_t)(crc >> 8);
         dst[nb + 1] = (uint8_t)crc;
     }
