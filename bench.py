@@ -57,7 +57,10 @@ def peaks():
 
 
 class ClockSampler(object):
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi polled every 50 ms from before the warm-up to the end of the last timed region; the
+    reported clocks are the samples whose timestamps fall inside a timed region (mark() brackets them),
+    or, when a region is shorter than the polling period, every sample taken while the GPU was working"""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -65,46 +68,57 @@ class ClockSampler(object):
         self.index = index
         self.proc = None
         self.path = None
+        self.windows = []
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            self.t_start = time.time()
         except Exception:
             self.proc = None
 
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "samples_in_timed_regions": 0}
         if not self.proc:
             return out
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[2]), float(f[3]), f[6:10]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                     f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if any(a - 0.03 <= r[0] <= b + 0.03 for a, b in self.windows)]
+        use = inside if inside else rows
+        reasons = set()
+        for r in use:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if use:
+            out.update(sm_mhz=statistics.median(r[1] for r in use), sm_max_mhz=max(r[2] for r in use),
+                       reasons=sorted(reasons), samples=len(rows), samples_in_timed_regions=len(inside))
         return out
 
 
@@ -252,12 +266,13 @@ def main():
     segs = [(0, n_frames_pcm, 0)]
 
     out_bytes = 0
+    clocks = ClockSampler(dev)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         out_bytes, n_flac_frames, _ = enc.encode_device(d_pcm, segs, d_out, out_cap)
     launches0 = enc.launch_count()
-    clocks = ClockSampler(dev)
     barrier()
-    clocks.start()
+    w0 = time.time()
     kernel_ms = [0.0] * 5
     device_ms = 0.0
     t0 = time.perf_counter()
@@ -268,7 +283,7 @@ def main():
             kernel_ms[i] += v
     barrier()
     elapsed = time.perf_counter() - t0
-    clk = clocks.stop()
+    clocks.mark(w0, time.time())
     launches = enc.launch_count() - launches0
     if dist is not None:
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
@@ -344,11 +359,13 @@ def main():
             e2e_bytes = e2e_step()
         launches_e0 = enc2.launch_count()
         barrier()
+        w0 = time.time()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_bytes = e2e_step()
         barrier()
         e_elapsed = time.perf_counter() - t0
+        clocks.mark(w0, time.time())
         launches += enc2.launch_count() - launches_e0
         if dist is not None:
             t = torch.tensor([e_elapsed], device="cuda", dtype=torch.float64)
@@ -365,6 +382,7 @@ def main():
         L.b200flac_host_free(h_pcm)
         enc2.close()
 
+    clk = clocks.stop()
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base = cpu_baseline()
@@ -382,7 +400,8 @@ def main():
                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (pcm_bytes / 1e6),
                        "sharding": "frame range per GPU, no collective"},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
+                       "samples": clk["samples"], "samples_in_timed_regions": clk["samples_in_timed_regions"]},
         }
         emit(line)
     L.b200flac_device_free(dev, d_pcm)

@@ -238,7 +238,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
     const u32 S = SC ? (u32)SC : S_rt;       // samples per thread: a compile-time 32 for the common shapes
 
     const u32 tid = threadIdx.x, nt = blockDim.x, gt = nt >> 1;
-    const u32 g = tid / gt, gtid = tid - g * gt;
+    const u32 g = tid >= gt ? 1u : 0u, gtid = tid - g * gt;
     const u32 frame = blockIdx.x;
     const size_t padn = ((size_t)V3_SK(P.block_size) + 8 + 3) & ~(size_t)3;     // keeps the image 16-byte aligned
     int* buf = (int*)dyn_smem + (size_t)g * padn;
