@@ -28,6 +28,9 @@
 #pragma once
 #include "flac_common.cuh"
 
+#ifndef LPC_MIN_CTAS
+#define LPC_MIN_CTAS 1
+#endif
 #define LPC_MAX_ROWS 32              // frames of a task (K = 1: 32)
 
 // (int)round(x) the way x86-64 cvttsd2si does it: NaN / out of range -> INT_MIN
@@ -279,7 +282,7 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
 // not fit the register file).  Large batches use G = 1 (the unpack/window work is not duplicated),
 // small ones G = 2 (half the sequential work per thread, twice the warps).
 template <int MAXL, int G>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, LPC_MIN_CTAS)
 k_lpc_autoc(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, u32 n_frames,
             const double* __restrict__ windows, bf_dev_params P, const bf_lpc_task* __restrict__ tasks,
             u32 n_tasks, u32* __restrict__ ticket,
