@@ -25,6 +25,10 @@
 #include "k_pack_v3.cuh"
 #include "k_synth.cuh"
 
+// opt-in dynamic shared memory ceiling set on every kernel that may need more than 48 KB.  The attribute
+// belongs to the kernel, not to an encoder: setting each encoder's own size let one encoder lower the
+// limit under another (concurrent or pooled) encoder with a larger block size.
+#define BF_SMEM_OPTIN (200 * 1024)
 #define BF_MAX_SEGMENTS 65536
 #define BF_NUM_EVENTS 6
 
@@ -314,9 +318,9 @@ static cudaError_t lpc_prepare(b200flac_encoder* enc)
 template <int S>
 static cudaError_t set_smem_attrs(size_t smem_a, size_t smem_p)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_analyze<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    cudaError_t e = cudaFuncSetAttribute(k_analyze<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_pack_subframes<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+    return cudaFuncSetAttribute(k_pack_subframes<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
 }
 
 extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* params, int device,
@@ -404,7 +408,7 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         }
         if (enc->v3) {
             const bool s32 = enc->v3_NT <= 128 && enc->v3_S == 32;   // samples per thread known at compile time
-#define V3_ATTR(MINB_, EXH_, SC_) cudaFuncSetAttribute(k_analyze_v3<MINB_, EXH_, SC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc->v3_smem)
+#define V3_ATTR(MINB_, EXH_, SC_) cudaFuncSetAttribute(k_analyze_v3<MINB_, EXH_, SC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
             if (P.exhaustive) e = s32 ? V3_ATTR(5, true, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, true, 0) : V3_ATTR(1, true, 0);
             else e = s32 ? V3_ATTR(5, false, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, false, 0) : V3_ATTR(1, false, 0);
 #undef V3_ATTR
@@ -463,10 +467,10 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
                 enc->p3 = false;
             } else {
                 e = 2 * enc->NT <= 256 && enc->S == 32
-                        ? cudaFuncSetAttribute(k_pack_v3<256, 4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+                        ? cudaFuncSetAttribute(k_pack_v3<256, 4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
                     : 2 * enc->NT <= 256
-                        ? cudaFuncSetAttribute(k_pack_v3<256, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
-                        : cudaFuncSetAttribute(k_pack_v3<1024, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                        ? cudaFuncSetAttribute(k_pack_v3<256, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
+                        : cudaFuncSetAttribute(k_pack_v3<1024, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
                 if (e != cudaSuccess) enc->p3 = false;
                 e = cudaSuccess;
             }
@@ -477,11 +481,11 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         enc->smem_pack = sp;
         // two register budgets: small CTAs (<= 192 threads) are compiled for 6 resident CTAs per SM
         if (enc->NT <= 192) {
-            e = cudaFuncSetAttribute(k_analyze_v2<192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pack_v2<192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
+            e = cudaFuncSetAttribute(k_analyze_v2<192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pack_v2<192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
         } else {
-            e = cudaFuncSetAttribute(k_analyze_v2<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pack_v2<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
+            e = cudaFuncSetAttribute(k_analyze_v2<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pack_v2<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
         }
     } else {
         enc->S = bs >= 2048 ? 32 : (bs >= 512 ? 16 : 8);

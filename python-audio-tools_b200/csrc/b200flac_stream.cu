@@ -132,6 +132,9 @@ struct b200flac_stream {
     b200flac_params params;
     uint32_t padding_size;
     std::vector<b200flac_encoder*> encs;
+    std::vector<int> enc_devices;
+    int slots_per_dev;
+    bool reusable;              // encoders may go back to the pool (no failure so far)
     std::vector<Lane> lanes;
     size_t cur;                 // lane being filled
     size_t oldest;              // next lane to collect
@@ -208,6 +211,61 @@ static void build_streaminfo(const b200flac_stream* s, const uint8_t md5[16], ui
     memcpy(out + 18, md5, 16);
 }
 
+// ---- encoder pool -------------------------------------------------------------------------------
+// Creating an encoder costs far more than encoding a short file with it (pinned staging and device
+// buffers for 2 x 2048 blocks: ~100 ms of cudaMallocHost/cudaMalloc against ~2 ms of kernels for ten
+// minutes of audio), so idle encoders are kept for the next stream with the same options -- the
+// 10,000-track batch of BASELINE.json config #5 pays the set-up once per worker, not once per file.
+struct PoolEntry {
+    b200flac_params params;
+    int device;
+    uint64_t batch_frames;
+    int slots;
+    b200flac_encoder* enc;
+};
+static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
+static std::vector<PoolEntry> g_pool;
+static const size_t kPoolCapacity = 8;
+
+static b200flac_encoder* pool_acquire(const b200flac_params* p, int device, uint64_t batch_frames, int slots)
+{
+    b200flac_encoder* e = nullptr;
+    pthread_mutex_lock(&g_pool_mu);
+    for (size_t i = 0; i < g_pool.size(); i++) {
+        const PoolEntry& pe = g_pool[i];
+        if (pe.device == device && pe.batch_frames == batch_frames && pe.slots == slots &&
+            memcmp(&pe.params, p, sizeof(*p)) == 0) {
+            e = pe.enc;
+            g_pool.erase(g_pool.begin() + (long)i);
+            break;
+        }
+    }
+    pthread_mutex_unlock(&g_pool_mu);
+    return e ? e : b200flac_encoder_create(p, device, batch_frames, slots);
+}
+
+static void pool_release(const b200flac_params* p, int device, uint64_t batch_frames, int slots, b200flac_encoder* e)
+{
+    b200flac_encoder* evict = nullptr;
+    pthread_mutex_lock(&g_pool_mu);
+    if (g_pool.size() >= kPoolCapacity) { evict = g_pool.front().enc; g_pool.erase(g_pool.begin()); }
+    PoolEntry pe;
+    memset(&pe, 0, sizeof(pe));
+    pe.params = *p; pe.device = device; pe.batch_frames = batch_frames; pe.slots = slots; pe.enc = e;
+    g_pool.push_back(pe);
+    pthread_mutex_unlock(&g_pool_mu);
+    if (evict) b200flac_encoder_destroy(evict);
+}
+
+extern "C" void b200flac_pool_clear(void)
+{
+    std::vector<PoolEntry> all;
+    pthread_mutex_lock(&g_pool_mu);
+    all.swap(g_pool);
+    pthread_mutex_unlock(&g_pool_mu);
+    for (auto& pe : all) b200flac_encoder_destroy(pe.enc);
+}
+
 static void destroy_stream(b200flac_stream* s)
 {
     if (!s) return;
@@ -216,7 +274,12 @@ static void destroy_stream(b200flac_stream* s)
     pthread_cond_broadcast(&s->cv_job);
     pthread_mutex_unlock(&s->mu);
     pthread_join(s->md5_thread, nullptr);
-    for (auto* e : s->encs) b200flac_encoder_destroy(e);
+    for (size_t i = 0; i < s->encs.size(); i++) {
+        // an encoder with nothing in flight goes back to the pool; after a failure or an abort with
+        // batches in flight it is destroyed (destroy synchronises its streams)
+        if (s->reusable && !s->failed && s->n_in_flight == 0) pool_release(&s->params, s->enc_devices[i], s->batch_frames, s->slots_per_dev, s->encs[i]);
+        else b200flac_encoder_destroy(s->encs[i]);
+    }
     if (s->f) fclose(s->f);
     pthread_mutex_destroy(&s->mu);
     pthread_cond_destroy(&s->cv_job);
@@ -269,10 +332,13 @@ extern "C" b200flac_stream* b200flac_stream_open(const char* filename, const b20
     int dev0 = 0;
     if (!devices || n_devices <= 0) { devices = &dev0; n_devices = 1; }
     const int slots_per_dev = 2;
+    s->slots_per_dev = slots_per_dev;
+    s->reusable = true;
     for (int i = 0; i < n_devices; i++) {
-        b200flac_encoder* e = b200flac_encoder_create(params, devices[i], s->batch_frames, slots_per_dev);
+        b200flac_encoder* e = pool_acquire(params, devices[i], s->batch_frames, slots_per_dev);
         if (!e) { stream_err(b200flac_last_error()); destroy_stream(s); return nullptr; }
         s->encs.push_back(e);
+        s->enc_devices.push_back(devices[i]);
     }
     for (int k = 0; k < slots_per_dev; k++)
         for (int i = 0; i < n_devices; i++) {
