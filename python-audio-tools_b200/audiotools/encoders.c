@@ -131,9 +131,24 @@ static PyObject *encoders_encode_flac(PyObject *dummy, PyObject *args, PyObject 
     }
 
     const unsigned bytes_ps = p.bits_per_sample / 8;
+    /* The reference asks for block_size frames per call (flac.c:244).  audiotools.BufferedPCMReader --
+       what FlacAudio.from_pcm always passes -- returns exactly the count it is asked for until the
+       stream ends (audiotools/__init__.py:2561-2603), so asking it for 64 blocks at a time yields the
+       same blocks with 1/64 of the Python calls.  Any other reader keeps the per-block protocol, because
+       a short read mid-stream must become a short frame (H12). */
+    unsigned read_blocks = 1;
+    {
+        PyObject *mod = PyImport_ImportModule("audiotools");
+        PyObject *cls = mod ? PyObject_GetAttrString(mod, "BufferedPCMReader") : NULL;
+        if (cls && (PyObject *)Py_TYPE(reader->obj) == cls && p.block_size <= (1u << 20)) read_blocks = 64;
+        Py_XDECREF(cls);
+        Py_XDECREF(mod);
+        PyErr_Clear();
+    }
+    const unsigned read_frames = p.block_size * read_blocks;
     for (;;) {
         /* pcmreader->read(block_size): src/pcmconv.c:236, with the exact-type check of :244 */
-        PyObject *fl_obj = PyObject_CallMethod(reader->obj, "read", "i", (int)p.block_size);
+        PyObject *fl_obj = PyObject_CallMethod(reader->obj, "read", "i", (int)read_frames);
         if (!fl_obj) goto error;
         if ((PyObject *)Py_TYPE(fl_obj) != reader->framelist_type) {
             Py_DECREF(fl_obj);
@@ -160,7 +175,7 @@ static PyObject *encoders_encode_flac(PyObject *dummy, PyObject *args, PyObject 
         rc = b200flac_stream_write(stream, packed, frames);
         /* the reference makes one frame of whatever read() returned (H12): a short read mid-stream
            becomes a short frame, so close the block here */
-        if (!rc && frames != p.block_size) rc = b200flac_stream_end_block(stream);
+        if (!rc && frames != read_frames) rc = b200flac_stream_end_block(stream);
         Py_END_ALLOW_THREADS
         Py_DECREF(fl_obj);
         if (rc) { PyErr_SetString(PyExc_IOError, b200flac_last_error()); goto error; }
