@@ -205,7 +205,7 @@ int b200flac_stream_end_block(b200flac_stream *s);
 int b200flac_stream_close(b200flac_stream *s, int abort_encode, uint64_t **frame_offsets,
                           uint32_t **frame_pcm_frames, uint64_t *n_frames);
 void b200flac_free(void *p);
-/* The stream layer keeps up to 8 idle encoders (device buffers, pinned staging) for the next stream with
+/* The stream layer keeps up to 16 (env B200FLAC_POOL) idle encoders (device buffers, pinned staging) for the next stream with
  * the same options and device: set-up costs ~100 ms, a short file a few ms.  This releases them. */
 void b200flac_pool_clear(void);
 

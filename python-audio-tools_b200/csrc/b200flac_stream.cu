@@ -225,7 +225,13 @@ struct PoolEntry {
 };
 static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
 static std::vector<PoolEntry> g_pool;
-static const size_t kPoolCapacity = 8;
+static size_t pool_capacity()
+{
+    // idle encoders kept (each: ~70 MB pinned, ~250 MB device at 16-bit stereo); B200FLAC_POOL=0 disables
+    static long cap = -1;
+    if (cap < 0) { const char* e = getenv("B200FLAC_POOL"); cap = e ? atol(e) : 16; if (cap < 0) cap = 0; }
+    return (size_t)cap;
+}
 
 static b200flac_encoder* pool_acquire(const b200flac_params* p, int device, uint64_t batch_frames, int slots)
 {
@@ -248,7 +254,8 @@ static void pool_release(const b200flac_params* p, int device, uint64_t batch_fr
 {
     b200flac_encoder* evict = nullptr;
     pthread_mutex_lock(&g_pool_mu);
-    if (g_pool.size() >= kPoolCapacity) { evict = g_pool.front().enc; g_pool.erase(g_pool.begin()); }
+    if (pool_capacity() == 0) { pthread_mutex_unlock(&g_pool_mu); b200flac_encoder_destroy(e); return; }
+    if (g_pool.size() >= pool_capacity()) { evict = g_pool.front().enc; g_pool.erase(g_pool.begin()); }
     PoolEntry pe;
     memset(&pe, 0, sizeof(pe));
     pe.params = *p; pe.device = device; pe.batch_frames = batch_frames; pe.slots = slots; pe.enc = e;
