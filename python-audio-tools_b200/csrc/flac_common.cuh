@@ -23,7 +23,11 @@ __device__ __forceinline__ int ld_pcm(const uint8_t* __restrict__ pcm, u64 sidx,
     const uint8_t* p = pcm + sidx * B;
     if (B == 2) return (int)(*(const short*)p);
     if (B == 3) {
-        u32 v = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16);
+        // aligned 32-bit loads and a funnel shift instead of three byte loads; the second word is only
+        // touched when the sample straddles it, so nothing past the last sample's word is read
+        const u32* w = (const u32*)((uintptr_t)p & ~(uintptr_t)3);
+        const u32 sh = ((u32)(uintptr_t)p & 3u) * 8u;
+        const u32 v = __funnelshift_r(w[0], sh > 8u ? w[1] : 0u, sh);
         return ((int)(v << 8)) >> 8;
     }
     if (B == 1) return (int)(*(const signed char*)p);

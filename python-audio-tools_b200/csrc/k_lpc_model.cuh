@@ -107,7 +107,7 @@ __host__ __device__ inline LpcGeom lpc_geometry(u32 K, u32 rowbytes, u32 ring)
 {
     LpcGeom g;
     g.rows = 32 / K;
-    u32 T = 9216 / (g.rows * rowbytes);           // ~9 KB per PCM tile
+    u32 T = 4608 / (g.rows * rowbytes);           // ~4.5 KB per PCM tile: 20 one-warp CTAs per SM fit at any sample width
     if (T > 160) T = 160;
     if (T < ring) T = ring;
     g.T = T;
