@@ -664,7 +664,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
 // (measured: a persistent single wave keeps the CTAs of an SM in the same phase of the unit, which
 // overlaps their load and search phases worse than staggered CTAs do).
 template <int MINB, bool EXH, int SC>
-__global__ void __launch_bounds__(512 / (MINB >= 5 ? 4 : 1), MINB)
+__global__ void __launch_bounds__(MINB >= 5 ? 128 : MINB >= 3 ? 256 : 512, MINB)
 k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S, u32 F,
              u32 n_units, const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
              b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out)
