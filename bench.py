@@ -211,8 +211,8 @@ def main():
     ap.add_argument("--e2e-slots", type=int, default=4, help="batches in flight in the end-to-end arm")
     ap.add_argument("--e2e-batch-blocks", type=int, default=2048, help="FLAC frames per end-to-end batch")
     ap.add_argument("--verify-seconds", type=float, default=120.0,
-                    help="correctness gate (SURVEY 8d): this much of the workload is encoded to a file through the "
-                         "stream layer and decoded by the compiled reference decoder (CRC-16 per frame, MD5); 0 skips")
+                    help="correctness gate inside the CPU leg (SURVEY 8d): this much of the workload is encoded to a "
+                         "file through the stream layer and decoded by the compiled reference decoder; 0 skips")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -387,26 +387,31 @@ def main():
 
     clk = clocks.stop()
 
-    # ---- correctness gate, outside the timed regions: reference decoder on a sample of the workload ----
-    verified = None
-    REF_FLACDEC = os.path.join(ROOT, "oracle", "_ref", "flacdec")
-    if rank == 0 and args.verify_seconds > 0 and os.path.exists(REF_FLACDEC):
-        vn = min(n_frames_pcm, int(args.verify_seconds * SAMPLE_RATE))
-        host = np.empty(vn * frame_bytes, dtype=np.uint8)
-        L.b200flac_device_download(dev, host.ctypes.data, d_pcm, vn * frame_bytes)
-        shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
-        with tempfile.TemporaryDirectory(dir=shm) as vd:
-            vpath = os.path.join(vd, "v.flac")
-            b200flac.encode_file(vpath, params, host, vn)
-            r = subprocess.run([REF_FLACDEC, vpath], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-            ok = r.returncode == 0 and r.stdout == host.tobytes()
-            verified = {"decoder": "oracle/_ref/flacdec (reference src/decoders/flac.c)", "seconds": vn / SAMPLE_RATE,
-                        "lossless": bool(ok), "file_bytes": os.path.getsize(vpath)}
-        if not ok:
-            raise SystemExit("correctness gate failed: the reference decoder did not return the input PCM")
+    # ---- CPU leg (rank 0, N = 1): the compiled reference as baseline and as checker.  The only place this
+    # arm executes anything under oracle/: the reference encoder is timed, and the reference decoder
+    # (CRC-16 of every frame, STREAMINFO MD5) must return the input PCM for a sample of the workload
+    # encoded through the stream layer -- SURVEY 8(d)'s correctness gate, outside the timed regions ----
     base = None
+    verified = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base = cpu_baseline()
+        REF_FLACDEC = os.path.join(ROOT, "oracle", "_ref", "flacdec")
+        if args.verify_seconds > 0 and os.path.exists(REF_FLACDEC):
+            vn = min(n_frames_pcm, int(args.verify_seconds * SAMPLE_RATE))
+            host = np.empty(vn * frame_bytes, dtype=np.uint8)
+            L.b200flac_device_download(dev, host.ctypes.data, d_pcm, vn * frame_bytes)
+            shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+            with tempfile.TemporaryDirectory(dir=shm) as vd:
+                vpath = os.path.join(vd, "v.flac")
+                b200flac.encode_file(vpath, params, host, vn)
+                r = subprocess.run([REF_FLACDEC, vpath], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+                ok = r.returncode == 0 and r.stdout == host.tobytes()
+                verified = {"decoder": "oracle/_ref/flacdec (reference src/decoders/flac.c)", "seconds": vn / SAMPLE_RATE,
+                            "lossless": bool(ok), "file_bytes": os.path.getsize(vpath)}
+            if not ok:
+                raise SystemExit("correctness gate failed: the reference decoder did not return the input PCM")
+        if base is not None:
+            base["checked"] = verified
 
     if rank == 0:
         line = {
@@ -421,7 +426,6 @@ def main():
                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (pcm_bytes / 1e6),
                        "sharding": "frame range per GPU, no collective"},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
-            "verified": verified,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
                        "samples": clk["samples"], "samples_in_timed_regions": clk["samples_in_timed_regions"]},
         }
