@@ -256,6 +256,13 @@ V3_GRID = [
     # orders above 12 (32-tap kernels), 16 (zero padded to 32)
     (44100, 2, 16, 4096 * 3, dict(block_size=4096, max_lpc_order=32, max_residual_partition_order=6, mid_side=True)),
     (44100, 2, 16, 4096 * 3, dict(block_size=4096, max_lpc_order=16, max_residual_partition_order=4)),
+    # exhaustive order search on the v3 kernel, orders above 12 (32-tap residual), 8192-sample blocks
+    (44100, 2, 16, 4096 * 2 + 50, dict(block_size=4096, max_lpc_order=16, max_residual_partition_order=6, mid_side=True,
+                                      exhaustive_model_search=True)),
+    (44100, 2, 16, 8192 * 2 + 50, dict(block_size=8192, max_lpc_order=8, max_residual_partition_order=6, adaptive_mid_side=True,
+                                      exhaustive_model_search=True)),
+    (96000, 2, 24, 4096 * 2 + 50, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, mid_side=True,
+                                      exhaustive_model_search=True)),
     # partition order 0 only
     (44100, 2, 16, 4096 * 2 + 77, dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=0, adaptive_mid_side=True)),
 ]
