@@ -130,8 +130,9 @@ int b200flac_encoder_encode_device(b200flac_encoder *enc, int slot, const void *
                                    uint32_t *n_frames, float *elapsed_ms);
 
 /* per-kernel CUDA-event times of the slot's last batch, in ms:
- * [0] lpc model (window/autocorrelation/Levinson/quantise), [1] subframe analysis,
- * [2] frame select + offset scan + output clear, [3] bit packing, [4] CRC-16.
+ * [0] lpc model (window/autocorrelation, then Levinson/quantise), [1] subframe analysis,
+ * [2] frame select + offset scan (+ output clear on the k_pack_v2 path), [3] frame packing
+ * (k_pack_v3 computes the CRC-16 here too), [4] the separate CRC-16 kernel of the k_pack_v2 path (else ~0).
  * Returns the number of entries written. */
 int b200flac_encoder_last_kernel_ms(b200flac_encoder *enc, int slot, float *ms, int capacity);
 /* number of kernel launches issued by this encoder so far */

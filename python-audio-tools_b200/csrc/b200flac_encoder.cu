@@ -1,5 +1,7 @@
 // b200flac_encoder.cu -- frame layer of the C ABI (include/b200flac.h): one
-// encoder per CUDA device, batches of independent frames through five kernels.
+// encoder per CUDA device, batches of independent frames through six kernels
+// (k_lpc_autoc, k_lpc_finish, k_analyze_v3 [+ k_analyze_v2 for the shapes v3 does not take],
+// k_frame_select, k_scan_offsets, k_pack_v3 [or k_zero_output + k_pack_v2 + k_frame_crc16]).
 //
 // Replaces, for a whole batch at a time, the reference's per-frame call
 //   flacenc_write_frame(encoder.frame, &encoder, samples)   src/encoders/flac.c:258, 520-671

@@ -1,4 +1,6 @@
-// k_pack.cuh -- frame assembly: stereo decision, offsets, bit packing, CRCs.
+// k_pack.cuh -- frame assembly: stereo decision, offsets, and the generic bit packing / CRC kernels
+// (k_pack_v3.cuh packs whole frames with the CRC-16 fused; it uses k_frame_select and k_scan_offsets
+// from here and leaves the rest to the shapes it does not take).
 //
 //   k_frame_select   stereo assignment by exact bit counts + frame sizes
 //                    flacenc_write_frame                  flac.c:532-666
