@@ -193,3 +193,23 @@ def test_native_metadata_finalisation_errors(tmp_path, built):
         fh.write(b"RIFFxxxxWAVE")
     with pytest.raises(b200flac.B200FlacError):
         b200flac.finalize_metadata(bad, [(0, 1)])
+
+
+def test_standalone_driver_cli(tmp_path, built):
+    """b200flacenc: the reference driver's options (flac.c:1652-1666); without a GPU it fails loudly"""
+    import subprocess
+    exe = os.path.join(ROOT, "python-audio-tools_b200", "b200flacenc")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, "--help"], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0
+    for flag in ("--channels", "--sample_rate", "--bits-per-sample", "--block-size", "--max-lpc-order",
+                 "--min-partition-order", "--max-partition-order", "--mid-side", "--adaptive-mid-side",
+                 "--exhaustive-model-search"):
+        assert flag in r.stdout
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "exactly 1 output file required" in r.stdout
+    import b200flac
+    if b200flac.device_count() == 0:
+        r = subprocess.run([exe, "-q", os.path.join(str(tmp_path), "x.flac")], input=b"\0" * 64, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE)
+        assert r.returncode == 1 and b"no CPU fallback" in r.stderr

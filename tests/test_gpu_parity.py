@@ -367,3 +367,26 @@ def test_many_short_tracks_one_batch(built):
     assert fbytes.tolist() == want_sizes
     assert out.tobytes() == want
     enc.close()
+
+
+def test_standalone_driver_matches_reference_driver(tmp_path, built):
+    """`b200flacenc [options] out.flac < pcm` writes the file `flacenc` (the compiled reference's driver,
+    src/encoders/flac.c:1637-1804) writes for the same options"""
+    import subprocess
+    exe = os.path.join(helpers.ROOT, "python-audio-tools_b200", "b200flacenc")
+    for ch, bps, rate, n, flags, o in (
+        (2, 16, 44100, 4096 * 5 + 77, ["-M"], dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, adaptive_mid_side=True)),
+        (1, 8, 8000, 3000, ["-B", "256", "-l", "4", "-R", "3"], dict(block_size=256, max_lpc_order=4, max_residual_partition_order=3)),
+        (2, 24, 96000, 4096 * 2 + 5, ["-m", "-e", "-l", "8", "-R", "5"],
+         dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=5, mid_side=True, exhaustive_model_search=True)),
+    ):
+        pcm = helpers.synth_pcm(70 + ch, ch, bps, n)
+        out = os.path.join(str(tmp_path), "cli.flac")
+        r = subprocess.run([exe, "-c", str(ch), "-b", str(bps), "-r", str(rate)] + flags + [out], input=pcm,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr
+        assert b"Encoding from stdin using parameters:" in r.stdout
+        got = open(out, "rb").read()
+        want = helpers.ref_encode(pcm, rate, ch, bps, helpers.options(**o)) if helpers.have_ref() else \
+            helpers.oracle_encode(pcm, rate, ch, bps, helpers.options(**o))
+        assert got == want
