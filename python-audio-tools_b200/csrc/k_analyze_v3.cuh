@@ -198,13 +198,35 @@ __device__ __forceinline__ void v3_fixed_sums(const int* __restrict__ samp, u32 
         const int4 va = *(const int4*)(samp + V3_SK(i0));
         const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
         const int xs[V3_CH] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        if (sizeof(SumT) == 4) {
+            // 32-bit sums (samples of at most 23 bits): |a - b| + c is ONE instruction (VABSDIFF, __sad), so
+            // an order's error never needs its difference formed first -- 3 subtractions and 5 VABSDIFFs per
+            // sample instead of 4 + 5 IABS + 5 adds.  No difference can overflow 32 bits here, so the true
+            // |a - b| equals the reference's abs() of its wrapped int difference.
+            u32 g0 = (u32)f0, g1 = (u32)f1, g2 = (u32)f2, g3 = (u32)f3, g4 = (u32)f4;
 #pragma unroll
-        for (int j = 0; j < V3_CH; j++) {
-            const u32 x = (u32)xs[j];
-            const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
-            f0 += (u32)abs((int)x); f1 += (u32)abs((int)d1); f2 += (u32)abs((int)d2);
-            f3 += (u32)abs((int)d3); f4 += (u32)abs((int)d4);
-            prev = x; p1 = d1; p2 = d2; p3 = d3;
+            for (int j = 0; j < V3_CH; j++) {
+                const int x = xs[j];
+                g0 = __sad(x, 0, g0);
+                g1 = __sad(x, (int)prev, g1);
+                const u32 d1 = (u32)x - prev;
+                g2 = __sad((int)d1, (int)p1, g2);
+                const u32 d2 = d1 - p1;
+                g3 = __sad((int)d2, (int)p2, g3);
+                const u32 d3 = d2 - p2;
+                g4 = __sad((int)d3, (int)p3, g4);
+                prev = (u32)x; p1 = d1; p2 = d2; p3 = d3;
+            }
+            f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4;
+        } else {
+#pragma unroll
+            for (int j = 0; j < V3_CH; j++) {
+                const u32 x = (u32)xs[j];
+                const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+                f0 += (u32)abs((int)x); f1 += (u32)abs((int)d1); f2 += (u32)abs((int)d2);
+                f3 += (u32)abs((int)d3); f4 += (u32)abs((int)d4);
+                prev = x; p1 = d1; p2 = d2; p3 = d3;
+            }
         }
     }
     e[0] = f0; e[1] = f1; e[2] = f2; e[3] = f3; e[4] = f4;
