@@ -536,8 +536,11 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     // residual of order o with the coefficients staged in sh.q; returns the thread's run sum
     auto lpc_pass = [&](u32 o, int shift, bool narrow) -> u64 {
         u64 run;
-        if (o <= 8) run = narrow ? v3_lpc_residual<8, false>(samp, resid, base, S, sh.q, shift)
-                                 : v3_lpc_residual<8, true>(samp, resid, base, S, sh.q, shift);
+        // (no 8-tap variant: a second hot copy of the residual loop costs more in instruction fetch than
+        // the four extra multiply-adds of a padded low order cost on the otherwise idle FMA pipe)
+        // (the exhaustive search walks every order, so there the 8-tap copy pays for itself)
+        if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, false>(samp, resid, base, S, sh.q, shift)
+                                        : v3_lpc_residual<8, true>(samp, resid, base, S, sh.q, shift);
         else if (o <= 12) run = narrow ? v3_lpc_residual<12, false>(samp, resid, base, S, sh.q, shift)
                                        : v3_lpc_residual<12, true>(samp, resid, base, S, sh.q, shift);
         else run = narrow ? v3_lpc_residual<32, false>(samp, resid, base, S, sh.q, shift)
