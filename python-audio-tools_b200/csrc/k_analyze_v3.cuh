@@ -313,46 +313,58 @@ __device__ __forceinline__ u32 v3_fold_shift(int r, u32 km1)
     return ((u32)(r ^ (r >> 31))) >> km1;
 }
 
-// sum of (zigzag(r) >> k) over the thread's run for the FIXED residual of ORDER, recomputed from
-// the samples (the sum fits 32 bits: see the Rice parameter rule, flac.c:1478)
-template <int ORDER>
-__device__ __forceinline__ u32 v3_fixed_bits(const int* __restrict__ samp, u32 base, u32 S, u32 k, u32 skip)
+// FIXED residual of any order in closed form: r[i] = s[i] + c1 s[i-1] + c2 s[i-2] + c3 s[i-3] + c4 s[i-4] with
+// the binomial coefficients of the order -- identical modulo 2^32 to the iterated differences of
+// flac.c:918-930.  Four multiply-adds on the FMA pipe, and ONE copy of the loop for the five orders.
+struct V3FixedCoef { int c1, c2, c3, c4; };
+__device__ __forceinline__ V3FixedCoef v3_fixed_coef(u32 order)
 {
-    u32 prev, p1, p2, p3;
-    v3_fixed_history(samp, base, prev, p1, p2, p3);
-    u32 acc = 0, head = 0;
+    V3FixedCoef c;
+    c.c1 = -(int)order;
+    c.c2 = order < 2 ? 0 : order == 2 ? 1 : order == 3 ? 3 : 6;
+    c.c3 = order < 3 ? 0 : order == 3 ? -1 : -4;
+    c.c4 = order == 4 ? 1 : 0;
+    return c;
+}
+
+// sum of (zigzag(r) >> k) over the thread's run for the FIXED residual of `order`, recomputed from the
+// samples (the sum fits 32 bits: see the Rice parameter rule, flac.c:1478).  skip: this is run 0, whose
+// first `order` positions are warm-up samples and do not count.
+template <bool KZERO>
+__device__ __forceinline__ u32 v3_fixed_bits_loop(const int* __restrict__ samp, u32 base, u32 S, u32 km1, const V3FixedCoef c)
+{
+    int4 h = make_int4(0, 0, 0, 0);                       // samples base-4 .. base-1
+    if (base) h = *(const int4*)(samp + V3_SK(base - 4));
+    u32 acc = 0;
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
         const int4 va = *(const int4*)(samp + V3_SK(i0));
         const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
-        const int xs[V3_CH] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        const int w[V3_CH + 4] = {h.x, h.y, h.z, h.w, va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
         for (int j = 0; j < V3_CH; j++) {
-            const u32 x = (u32)xs[j];
-            u32 v = x;
-            if (ORDER >= 1) { const u32 d1 = x - prev; v = d1;
-                if (ORDER >= 2) { const u32 d2 = d1 - p1; v = d2;
-                    if (ORDER >= 3) { const u32 d3 = d2 - p2; v = d3;
-                        if (ORDER >= 4) { const u32 d4 = d3 - p3; v = d4; }
-                        p3 = d3; }
-                    p2 = d2; }
-                p1 = d1; prev = x; }
-            const u32 t = k ? v3_fold_shift((int)v, k - 1) : zigzag((int)v);
-            acc += t;
-            if (ORDER > 0 && j < ORDER && i0 == base) head += t;   // warm-up positions (only matter for run 0)
+            const int r = w[j + 4] + c.c1 * w[j + 3] + c.c2 * w[j + 2] + c.c3 * w[j + 1] + c.c4 * w[j];
+            acc += KZERO ? zigzag(r) : v3_fold_shift(r, km1);
         }
+        h = vb;
     }
-    return acc - (skip ? head : 0u);
+    return acc;
 }
 
 __device__ __forceinline__ u32 v3_fixed_bits_any(const int* __restrict__ samp, u32 base, u32 S, u32 k, u32 order, u32 skip)
 {
-    switch (order) {
-    case 0: return v3_fixed_bits<0>(samp, base, S, k, skip);
-    case 1: return v3_fixed_bits<1>(samp, base, S, k, skip);
-    case 2: return v3_fixed_bits<2>(samp, base, S, k, skip);
-    case 3: return v3_fixed_bits<3>(samp, base, S, k, skip);
-    default: return v3_fixed_bits<4>(samp, base, S, k, skip);
+    const V3FixedCoef c = v3_fixed_coef(order);
+    u32 acc = k ? v3_fixed_bits_loop<false>(samp, base, S, k - 1, c) : v3_fixed_bits_loop<true>(samp, base, S, 0, c);
+    if (skip) {
+        // run 0: take the warm-up positions back out (they were evaluated with zeros before the block)
+        for (u32 j = 0; j < order; j++) {
+            const int s0 = samp[V3_SK(j)];
+            const int s1 = j >= 1 ? samp[V3_SK(j - 1)] : 0, s2 = j >= 2 ? samp[V3_SK(j - 2)] : 0;
+            const int s3 = j >= 3 ? samp[V3_SK(j - 3)] : 0;
+            const int r = s0 + c.c1 * s1 + c.c2 * s2 + c.c3 * s3;     // (s[j-4] is before the block for j < 4)
+            acc -= zigzag(r) >> k;
+        }
     }
+    return acc;
 }
 
 // sum of (zigzag(r) >> k) over the thread's run of a stored residual; the first `skip` entries

@@ -190,26 +190,24 @@ __device__ __forceinline__ u32 p3_lpc_inplace(int* __restrict__ buf, u32 base, u
 __device__ __forceinline__ u32 p3_fixed_inplace(int* __restrict__ buf, u32 base, u32 end, u32 order,
                                                 const P3Count& c, u32 p, u32 next, u32 k, u32 g, u32 gt)
 {
-    u32 prev, p1, p2, p3;
-    v3_fixed_history(buf, base < end ? base : 0u, prev, p1, p2, p3);
+    // closed form of the iterated differences (v3_fixed_coef): one loop for the five orders
+    const V3FixedCoef fc = v3_fixed_coef(order);
+    int4 h = make_int4(0, 0, 0, 0);                       // samples base-4 .. base-1
+    if (base && base < end) h = *(const int4*)(buf + V3_SK(base - 4));
     p3_group_bar(g, gt);
     u32 mybits = 0;
     for (u32 i0 = base; i0 < end; i0 += 8) {
         const int4 va = *(const int4*)(buf + V3_SK(i0));
         const int4 vb = *(const int4*)(buf + V3_SK(i0) + 4);
-        const int xs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        const int w[12] = {h.x, h.y, h.z, h.w, va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
         u32 u[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const u32 x = (u32)xs[j];
-            const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
-            const u32 v = order == 0 ? x : order == 1 ? d1 : order == 2 ? d2 : order == 3 ? d3 : d4;
-            u[j] = zigzag((int)v);
-            prev = x; p1 = d1; p2 = d2; p3 = d3;
-        }
+        for (int j = 0; j < 8; j++)
+            u[j] = zigzag(w[j + 4] + fc.c1 * w[j + 3] + fc.c2 * w[j + 2] + fc.c3 * w[j + 1] + fc.c4 * w[j]);
         *(uint4*)(buf + V3_SK(i0)) = make_uint4(u[0], u[1], u[2], u[3]);
         *(uint4*)(buf + V3_SK(i0) + 4) = make_uint4(u[4], u[5], u[6], u[7]);
         p3_count_chunk(u, buf, i0, c, p, next, k, mybits);
+        h = vb;
     }
     return mybits;
 }
