@@ -300,8 +300,8 @@ def main():
     names = ["lpc_model", "analyze", "select_scan", "pack", "crc16"]
     dom = max(range(5), key=lambda i: kernel_ms[i])
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, from the ncu --set full
-    # capture summarised in profiles/r01_v5_summary.txt (only valid for the default 3600 s workload)
-    traffic_ncu = {"lpc_model": 636.3e6 + 15.0e6, "analyze": 672.7e6 + 20.4e6, "pack": 655.5e6 + 404.1e6}
+    # capture summarised in profiles/r01_v7_summary.txt (only valid for the default 3600 s workload)
+    traffic_ncu = {"lpc_model": 636.3e6 + 14.6e6, "analyze": 673.2e6 + 20.6e6, "pack": 655.5e6 + 403.7e6}
     traffic = traffic_ncu.get(names[dom]) if n_frames_pcm == HOUR_FRAMES else None
     algo_bytes = pcm_bytes + out_bytes            # PCM in at native width + frame bytes out
     peak, peak_kind = peaks()
@@ -309,7 +309,7 @@ def main():
     pipeline = algo_bytes / (sum(kernel_ms) * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                "traffic_source": "profiles/r01_v5_summary.txt (ncu --set full, bytes per launch)" if traffic else None,
+                "traffic_source": "profiles/r01_v7_summary.txt (ncu --set full, bytes per launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": dict(zip(names, kernel_ms)),
                 "device_ms_per_step": device_ms / args.steps,
