@@ -228,6 +228,52 @@ int b200flac_encode_file(const char *filename, const b200flac_params *params,
                          const uint8_t *pcm, uint64_t n_pcm_frames,
                          const int *devices, int n_devices);
 
+/* ---- file-backed PCM feed ----
+ * The reference feeds the encoder through a Python PCMReader: WaveReader / AiffReader read the file,
+ * build an int FrameList per call (audiotools/wav.py:504-527, aiff.py:434-456) and pcmreader_read
+ * converts it again (src/pcmconv.c:219-297).  These entry points restate the two container parsers in C
+ * and move the PCM from the file straight into the stream's pinned staging, one batch per read. */
+#define B200FLAC_PCM_BIG_ENDIAN 1u /* samples are big-endian in the file (AIFF, aiff.py:452-456) */
+#define B200FLAC_PCM_UNSIGNED   2u /* samples are unsigned in the file (8-bit WAVE, wav.py:523-527) */
+
+typedef struct b200flac_pcm_source {
+    uint32_t sample_rate, channels, bits_per_sample, channel_mask;
+    uint32_t flags;             /* B200FLAC_PCM_* */
+    uint32_t reserved;
+    uint64_t data_offset;       /* file offset of the first PCM byte */
+    uint64_t total_pcm_frames;  /* what the container says: data size / frame size (WAVE), COMM (AIFF) */
+} b200flac_pcm_source;
+
+/* WaveReader.__init__ + parse_fmt (audiotools/wav.py:424-502, 288-354) / AiffReader.__init__ + parse_comm
+ * (audiotools/aiff.py:353-432, 327-347), chunk walk, checks and defaults included (the channel mask a
+ * plain WAVE gets from its channel count, the `fmt ` remainder the reference does not skip).
+ * Returns 0, or: 1 = the reference raises ValueError, 2 = IOError (unreadable/truncated header);
+ * b200flac_last_error() then holds the reference's message text (audiotools/text.py:530-544,621-634). */
+int b200flac_wave_probe(const char *path, b200flac_pcm_source *src);
+int b200flac_aiff_probe(const char *path, b200flac_pcm_source *src);
+
+/* Appends n_pcm_frames PCM frames read from `path` at byte_offset, exactly as if the same frames had gone
+ * through b200flac_stream_write() after conversion to signed little-endian (flags: B200FLAC_PCM_*), but
+ * read directly into the pinned staging of the batch being filled.  Returns 0; 1 on an encoder or I/O
+ * error; 2 when the file ends early -- the reference's "premature end of data chunk" IOError
+ * (wav.py:516-518, aiff.py:445-447); the stream is then failed and only good for b200flac_stream_close(abort). */
+int b200flac_stream_write_file(b200flac_stream *s, const char *path, uint64_t byte_offset,
+                               uint64_t n_pcm_frames, uint32_t flags);
+
+/* One call, file to file: FlacAudio.from_pcm(flac, WaveAudio(wave).to_pcm() / AiffAudio(aiff).to_pcm())
+ * without its metadata tail -- probe, stream head, feed, STREAMINFO.  sample_rate / channels /
+ * bits_per_sample in *params are ignored and taken from the file.  `src` (optional) receives the probe
+ * result (the caller needs channel_mask for b200flac_finalize_metadata); the (offset, pcm_frames) list
+ * comes back as in b200flac_stream_close.  Returns 0, or 1/2 as the probe, or 3 for an encode error. */
+int b200flac_encode_wave(const char *flac_filename, const char *wave_filename, const b200flac_params *params,
+                         uint32_t padding_size, const char *version, const int *devices, int n_devices,
+                         b200flac_pcm_source *src, uint64_t **frame_offsets, uint32_t **frame_pcm_frames,
+                         uint64_t *n_frames);
+int b200flac_encode_aiff(const char *flac_filename, const char *aiff_filename, const b200flac_params *params,
+                         uint32_t padding_size, const char *version, const int *devices, int n_devices,
+                         b200flac_pcm_source *src, uint64_t **frame_offsets, uint32_t **frame_pcm_frames,
+                         uint64_t *n_frames);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,8 @@ Only what `FlacAudio.from_pcm` -> `audiotools.encoders.encode_flac` needs is her
   BufferedPCMReader      audiotools/__init__.py:2561-2603
   EncodingError & co.    audiotools/__init__.py (exception classes)
   FlacAudio              audiotools/flac.py:1251 (from_pcm, seektable, update_metadata)
+  WaveReader/WaveAudio   audiotools/wav.py:421-757, AiffReader/AiffAudio audiotools/aiff.py:350-560
+                         (the file-backed PCM sources in front of from_pcm)
 
 `audiotools.pcm` and `audiotools.encoders` are C extension modules (pcm.c, encoders.c);
 encoders.encode_flac keeps the reference's signature and returns the same
@@ -104,3 +106,6 @@ class PCMBytesReader(object):
 
 
 from .flac import FlacAudio  # noqa: E402,F401
+from . import wav, aiff  # noqa: E402,F401
+from .wav import WaveAudio, WaveReader  # noqa: E402,F401
+from .aiff import AiffAudio, AiffReader  # noqa: E402,F401

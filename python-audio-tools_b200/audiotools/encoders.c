@@ -145,6 +145,50 @@ static PyObject *encoders_encode_flac(PyObject *dummy, PyObject *args, PyObject 
         Py_XDECREF(mod);
         PyErr_Clear();
     }
+    /* File-backed readers: when from_pcm's BufferedPCMReader wraps a reader that knows
+       where its PCM lies in a file (audiotools.wav.WaveReader, audiotools.aiff.AiffReader: b200_file_span)
+       and nothing is buffered yet, the engine reads that span itself, batch by batch, straight into its
+       pinned staging -- no FrameList per read().  The reader is left as if it had been read to the end, and
+       the loop below then sees the empty FrameList that ends the stream.  B200FLAC_FILE_FEED=0 turns this off. */
+    if (read_blocks == 64) {
+        const char *knob = getenv("B200FLAC_FILE_FEED");
+        PyObject *inner = (knob && knob[0] == '0') ? NULL : PyObject_GetAttrString(reader->obj, "pcmreader");
+        PyObject *buffered = inner ? PyObject_GetAttrString(reader->obj, "buffer") : NULL;
+        PyObject *span = NULL;
+        if (inner && buffered && (PyObject *)Py_TYPE(buffered) == reader->framelist_type &&
+            ((pcm_FrameList *)buffered)->frames == 0 && PyObject_HasAttrString(inner, "b200_file_span") &&
+            PyObject_HasAttrString(inner, "b200_file_span_consumed"))
+            span = PyObject_CallMethod(inner, "b200_file_span", NULL);
+        Py_XDECREF(buffered);
+        if (span) {
+            PyObject *path_obj = NULL, *path_bytes = NULL;
+            unsigned long long offset = 0, frames = 0;
+            unsigned flags = 0;
+            const char *truncated = "premature end of data chunk";
+            int ok = PyArg_ParseTuple(span, "OKKI|s", &path_obj, &offset, &frames, &flags, &truncated) &&
+                     PyUnicode_FSConverter(path_obj, &path_bytes);
+            if (ok && frames) {
+                int rc;
+                const char *path = PyBytes_AS_STRING(path_bytes);
+                Py_BEGIN_ALLOW_THREADS
+                rc = b200flac_stream_write_file(stream, path, offset, frames, flags);
+                Py_END_ALLOW_THREADS
+                if (rc) {
+                    /* rc 2: the file ended early -- the IOError WaveReader.read() raises (wav.py:516-518) */
+                    PyErr_SetString(PyExc_IOError, rc == 2 ? truncated : b200flac_last_error());
+                    Py_DECREF(path_bytes); Py_DECREF(span); Py_DECREF(inner);
+                    goto error;
+                }
+                PyObject *r = PyObject_CallMethod(inner, "b200_file_span_consumed", "K", frames);
+                if (!r) { Py_DECREF(path_bytes); Py_DECREF(span); Py_DECREF(inner); goto error; }
+                Py_DECREF(r);
+            }
+            Py_XDECREF(path_bytes);
+            Py_DECREF(span);
+        }
+        Py_XDECREF(inner);
+        PyErr_Clear(); /* a reader without a usable span simply takes the FrameList path */
+    }
     const unsigned read_frames = p.block_size * read_blocks;
     for (;;) {
         /* pcmreader->read(block_size): src/pcmconv.c:236, with the exact-type check of :244 */

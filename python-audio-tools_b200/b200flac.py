@@ -48,6 +48,16 @@ class Plan(C.Structure):
                 ("coeffs", C.c_int16 * MAX_LPC_ORDER)]
 
 
+class PcmSource(C.Structure):
+    """struct b200flac_pcm_source: what WaveReader / AiffReader learn from the container
+    (audiotools/wav.py:424-502, aiff.py:353-432)"""
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
+                ("channel_mask", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("data_offset", C.c_uint64), ("total_pcm_frames", C.c_uint64)]
+
+
+PCM_BIG_ENDIAN, PCM_UNSIGNED = 1, 2
+
 _lib = None
 
 
@@ -101,6 +111,12 @@ def lib():
     L.b200flac_finalize_metadata.argtypes = [C.c_char_p, u64p, u32p, C.c_uint64, C.c_uint32, C.c_uint32]
     L.b200flac_encode_file.argtypes = [C.c_char_p, C.POINTER(Params), C.c_uint32, C.c_char_p, vp,
                                        C.c_uint64, C.POINTER(C.c_int), C.c_int]
+    L.b200flac_wave_probe.argtypes = [C.c_char_p, C.POINTER(PcmSource)]
+    L.b200flac_aiff_probe.argtypes = [C.c_char_p, C.POINTER(PcmSource)]
+    L.b200flac_stream_write_file.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32]
+    for fn in (L.b200flac_encode_wave, L.b200flac_encode_aiff):
+        fn.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_uint32, C.c_char_p, C.POINTER(C.c_int),
+                       C.c_int, C.POINTER(PcmSource), C.POINTER(u64p), C.POINTER(u32p), u64p]
     _lib = L
     return L
 
@@ -261,6 +277,14 @@ class Stream(object):
         if lib().b200flac_stream_end_block(self.h):
             raise _err()
 
+    def write_file(self, path, byte_offset, n_pcm_frames, flags=0):
+        """PCM frames straight from a file into the pinned staging (b200flac_stream_write_file)"""
+        rc = lib().b200flac_stream_write_file(self.h, os.fsencode(path), byte_offset, n_pcm_frames, flags)
+        if rc == 2:
+            raise IOError(lib().b200flac_last_error().decode())
+        if rc:
+            raise _err()
+
     def close(self, abort=False):
         if not self.h:
             return []
@@ -284,3 +308,47 @@ def finalize_metadata(filename, offsets, seekpoint_interval=0, channel_mask=0):
     lens = (C.c_uint32 * max(n, 1))(*[f for _, f in offsets])
     if lib().b200flac_finalize_metadata(os.fsencode(filename), offs, lens, n, seekpoint_interval, channel_mask):
         raise _err()
+
+
+def _probe(fn, path):
+    src = PcmSource()
+    rc = fn(os.fsencode(path), C.byref(src))
+    if rc == 1:
+        raise ValueError(lib().b200flac_last_error().decode())
+    if rc:
+        raise IOError(lib().b200flac_last_error().decode())
+    return src
+
+
+def wave_probe(path):
+    """WaveReader.__init__ in C (audiotools/wav.py:424-502): ValueError / IOError as the reference raises"""
+    return _probe(lib().b200flac_wave_probe, path)
+
+
+def aiff_probe(path):
+    """AiffReader.__init__ in C (audiotools/aiff.py:353-432)"""
+    return _probe(lib().b200flac_aiff_probe, path)
+
+
+def encode_container(flac_filename, in_filename, params, kind="wave", padding_size=4096, version=None, devices=None):
+    """file to file: b200flac_encode_wave / b200flac_encode_aiff; returns (PcmSource, [(offset, pcm_frames)])"""
+    devs, ndev = None, 0
+    if devices:
+        devs = (C.c_int * len(devices))(*devices)
+        ndev = len(devices)
+    v = version.encode() if version else None
+    fn = lib().b200flac_encode_wave if kind == "wave" else lib().b200flac_encode_aiff
+    src = PcmSource()
+    offs, lens, n = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)(), C.c_uint64(0)
+    rc = fn(os.fsencode(flac_filename), os.fsencode(in_filename), C.byref(params), padding_size, v, devs, ndev,
+            C.byref(src), C.byref(offs), C.byref(lens), C.byref(n))
+    if rc == 1:
+        raise ValueError(lib().b200flac_last_error().decode())
+    if rc == 2:
+        raise IOError(lib().b200flac_last_error().decode())
+    if rc:
+        raise _err()
+    res = [(offs[i], lens[i]) for i in range(n.value)]
+    lib().b200flac_free(offs)
+    lib().b200flac_free(lens)
+    return src, res

@@ -481,6 +481,62 @@ extern "C" int b200flac_stream_write(b200flac_stream* s, const uint8_t* pcm, uin
     return 0;
 }
 
+// file bytes -> signed little-endian, in place (FrameList(data, ..., is_big_endian, is_signed) of
+// wav.py:523-527 / aiff.py:452-456 followed by the little-endian packing the MD5 callback sees)
+static void to_signed_le(uint8_t* p, size_t n_samples, unsigned bytes, uint32_t flags)
+{
+    if ((flags & B200FLAC_PCM_BIG_ENDIAN) && bytes == 2) {
+        uint16_t* w = (uint16_t*)p;
+        for (size_t i = 0; i < n_samples; i++) w[i] = (uint16_t)((w[i] << 8) | (w[i] >> 8));
+    } else if ((flags & B200FLAC_PCM_BIG_ENDIAN) && bytes == 3) {
+        for (size_t i = 0; i < n_samples; i++, p += 3) { const uint8_t t = p[0]; p[0] = p[2]; p[2] = t; }
+        p -= n_samples * 3;
+    }
+    if (flags & B200FLAC_PCM_UNSIGNED)
+        for (size_t i = 0; i < n_samples; i++) p[i * bytes + bytes - 1] ^= 0x80; // value - 2^(bps-1)
+}
+
+extern "C" int b200flac_stream_write_file(b200flac_stream* s, const char* path, uint64_t byte_offset,
+                                          uint64_t n_pcm_frames, uint32_t flags)
+{
+    if (!s || s->failed) { if (!s) stream_err("stream is NULL"); return 1; }
+    if (!path) { stream_err("path is NULL"); return 1; }
+    FILE* in = fopen(path, "rb");
+    if (!in) {
+        char msg[400];
+        snprintf(msg, sizeof(msg), "cannot open \"%.300s\" for reading", path);
+        stream_err(msg);
+        return 1;
+    }
+    setvbuf(in, nullptr, _IONBF, 0); // whole batches go straight to the pinned staging
+    if (fseeko(in, (off_t)byte_offset, SEEK_SET) != 0) { fclose(in); stream_err("seek error"); return 1; }
+    const unsigned sample_bytes = s->params.bits_per_sample / 8;
+    const size_t frame_bytes = (size_t)s->params.channels * sample_bytes;
+    const uint32_t bs = s->params.block_size;
+    int rc = 0;
+    while (n_pcm_frames && !rc) {
+        Lane& l = s->lanes[s->cur];
+        const uint64_t cap = l.seg_start + (s->batch_frames - l.seg_start) / bs * bs;
+        const uint64_t room = cap - l.fill;
+        if (room == 0) { rc = submit_current(s); continue; }
+        const uint64_t take = n_pcm_frames < room ? n_pcm_frames : room;
+        uint8_t* dst = l.pcm + (size_t)l.fill * frame_bytes;
+        const size_t want = (size_t)take * frame_bytes;
+        if (fread(dst, 1, want, in) != want) {
+            stream_err(ferror(in) ? "read error" : "premature end of data chunk");
+            s->failed = true;
+            rc = ferror(in) ? 1 : 2;
+            break;
+        }
+        if (flags) to_signed_le(dst, (size_t)take * s->params.channels, sample_bytes, flags);
+        l.fill += take;
+        n_pcm_frames -= take;
+        if (l.fill == cap) rc = submit_current(s);
+    }
+    fclose(in);
+    return rc;
+}
+
 // Force a frame boundary here: the PCM written since the last boundary that does not fill a
 // whole block becomes a short frame (what the reference does when read() returns fewer frames
 // than block_size mid-stream, flac.c:247,525).
