@@ -274,6 +274,42 @@ int b200flac_encode_aiff(const char *flac_filename, const char *aiff_filename, c
                          b200flac_pcm_source *src, uint64_t **frame_offsets, uint32_t **frame_pcm_frames,
                          uint64_t *n_frames);
 
+/* ---- decode / verify ----
+ * Frame-parallel restatement of the reference decoder, src/decoders/flac.c:174-286 (FlacDecoder_read),
+ * :569-1270 (metadata, frame header, subframes, residuals, channel decorrelation) and :1340-1510 (flacdec):
+ * every position holding a header that is valid for the stream is decoded speculatively by its own GPU
+ * thread, the host follows the chain of frame ends as the reference's loop would, and a last kernel
+ * writes the interleaved PCM (signed little-endian, the bytes the STREAMINFO MD5 is taken over).
+ * Return codes: 0; 1 = the reference raises ValueError (flacdec: "*** Error: <text>"), 2 = IOError
+ * (EOF), 3 = engine error; b200flac_last_error() holds the reference's message text
+ * (FlacDecoder_strerror, flac.c:1273-1311; "invalid checksum in frame"; "MD5 mismatch at end of stream"). */
+typedef struct b200flac_stream_info {
+    uint32_t min_block_size, max_block_size, min_frame_size, max_frame_size;
+    uint32_t sample_rate, channels, bits_per_sample, reserved;
+    uint64_t total_pcm_frames;
+    uint64_t first_frame_offset;  /* byte offset of the first frame in the file */
+    uint8_t  md5[16];
+} b200flac_stream_info;
+
+/* flacdec_read_metadata (flac.c:569-708) as far as decoding needs it */
+int b200flac_read_streaminfo(const uint8_t *flac, uint64_t n_bytes, b200flac_stream_info *info);
+/* A whole FLAC file image in host memory -> PCM in host memory.  pcm == NULL only fills *info (size the
+ * buffer as total_pcm_frames * channels * bits_per_sample/8).  check_md5: compare with STREAMINFO as
+ * FlacDecoder_verify_okay does (flac.c:479-490).  The frames' byte offsets (relative to the first frame)
+ * and PCM lengths come back like the encoder's list (free with b200flac_free); kernel_ms[3] (optional):
+ * candidate scan, frame decode, chain walk + PCM emit. */
+int b200flac_decode_memory(const uint8_t *flac, uint64_t n_bytes, int device, uint8_t *pcm,
+                           uint64_t pcm_capacity, b200flac_stream_info *info, int check_md5,
+                           uint64_t **frame_offsets, uint32_t **frame_pcm_frames, uint64_t *n_frames,
+                           float *kernel_ms);
+/* The same with the frames (first frame to end of file; 4-byte aligned, 32 readable bytes of padding
+ * after n_bytes) already in device memory and the PCM left in device memory. */
+int b200flac_decode_device(const b200flac_stream_info *info, const void *d_frames, uint64_t n_bytes,
+                           int device, void *d_pcm, uint64_t pcm_capacity, uint64_t *n_frames,
+                           float *kernel_ms);
+/* flacdec without output: decode everything, check every CRC-16 and the STREAMINFO MD5 */
+int b200flac_verify_file(const char *flac_filename, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,14 @@ class PcmSource(C.Structure):
 
 PCM_BIG_ENDIAN, PCM_UNSIGNED = 1, 2
 
+
+class StreamInfo(C.Structure):
+    """struct b200flac_stream_info: STREAMINFO as flacdec_read_metadata reads it (src/decoders/flac.c:569-708)"""
+    _fields_ = [("min_block_size", C.c_uint32), ("max_block_size", C.c_uint32), ("min_frame_size", C.c_uint32),
+                ("max_frame_size", C.c_uint32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
+                ("bits_per_sample", C.c_uint32), ("reserved", C.c_uint32), ("total_pcm_frames", C.c_uint64),
+                ("first_frame_offset", C.c_uint64), ("md5", C.c_uint8 * 16)]
+
 _lib = None
 
 
@@ -117,6 +125,12 @@ def lib():
     for fn in (L.b200flac_encode_wave, L.b200flac_encode_aiff):
         fn.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_uint32, C.c_char_p, C.POINTER(C.c_int),
                        C.c_int, C.POINTER(PcmSource), C.POINTER(u64p), C.POINTER(u32p), u64p]
+    L.b200flac_read_streaminfo.argtypes = [vp, C.c_uint64, C.POINTER(StreamInfo)]
+    L.b200flac_decode_memory.argtypes = [vp, C.c_uint64, C.c_int, vp, C.c_uint64, C.POINTER(StreamInfo), C.c_int,
+                                         C.POINTER(u64p), C.POINTER(u32p), u64p, C.POINTER(C.c_float)]
+    L.b200flac_decode_device.argtypes = [C.POINTER(StreamInfo), vp, C.c_uint64, C.c_int, vp, C.c_uint64, u64p,
+                                         C.POINTER(C.c_float)]
+    L.b200flac_verify_file.argtypes = [C.c_char_p, C.c_int]
     _lib = L
     return L
 
@@ -352,3 +366,51 @@ def encode_container(flac_filename, in_filename, params, kind="wave", padding_si
     lib().b200flac_free(offs)
     lib().b200flac_free(lens)
     return src, res
+
+
+def _raise_decode(rc):
+    msg = lib().b200flac_last_error().decode("utf-8", "replace")
+    if rc == 1:
+        raise ValueError(msg)        # what FlacDecoder.read() raises (src/decoders/flac.c:218-253)
+    if rc == 2:
+        raise IOError(msg)           # "EOF reading frame", flac.c:262
+    raise B200FlacError(msg)
+
+
+def read_streaminfo(flac):
+    info = StreamInfo()
+    rc = lib().b200flac_read_streaminfo(_buf_ptr(flac), len(flac), C.byref(info))
+    if rc:
+        _raise_decode(rc)
+    return info
+
+
+def decode(flac, device=0, check_md5=True, want_frames=False):
+    """a FLAC file image (bytes) -> (StreamInfo, PCM bytes[, [(frame offset, pcm frames)], kernel ms]):
+    b200flac_decode_memory; raises ValueError / IOError with the reference decoder's messages"""
+    import numpy as np
+    info = read_streaminfo(flac)
+    nbytes = info.total_pcm_frames * info.channels * (info.bits_per_sample // 8)
+    pcm = np.empty(max(nbytes, 1), dtype=np.uint8)
+    offs, lens, n = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)(), C.c_uint64(0)
+    ms = (C.c_float * 3)()
+    rc = lib().b200flac_decode_memory(_buf_ptr(flac), len(flac), device, pcm.ctypes.data, nbytes, None, int(check_md5),
+                                      C.byref(offs), C.byref(lens), C.byref(n), ms)
+    if rc:
+        _raise_decode(rc)
+    out = pcm[:nbytes].tobytes()
+    if not want_frames:
+        return info, out
+    frames = [(offs[i], lens[i]) for i in range(n.value)]
+    if n.value:
+        lib().b200flac_free(offs)
+        lib().b200flac_free(lens)
+    return info, out, frames, list(ms)
+
+
+def verify_file(path, device=0):
+    """flacdec without output (b200flac_verify_file): every frame CRC-16 and the STREAMINFO MD5"""
+    rc = lib().b200flac_verify_file(os.fsencode(path), device)
+    if rc:
+        _raise_decode(rc)
+    return True

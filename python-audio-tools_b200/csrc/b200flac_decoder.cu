@@ -1,0 +1,684 @@
+// b200flac_decoder.cu -- frame-parallel FLAC decode / verify on the GPU.
+//
+// Reference being restated (src/decoders/flac.c of widgital/python-audio-tools):
+//   flacdec_read_metadata          :569-708   STREAMINFO (host, here: parse_streaminfo)
+//   flacdec_read_frame_header      :710-852   + read_utf8 :1313-1323     (dec_parse_header, host and device)
+//   flacdec_read_subframe(_header) :854-950, subframe bits per sample :952-965
+//   flacdec_read_constant/verbatim/fixed/lpc_subframe :967-1133
+//   flacdec_read_residual          :1135-1210
+//   flacdec_decorrelate_channels   :1213-1270
+//   frame loop, CRC-16, MD5        :174-286 (FlacDecoder_read), :1395-1501 (standalone flacdec)
+//
+// The reference walks the stream serially because a frame's length is only known once its last
+// residual has been read.  Here every byte position that holds a header which is valid for this
+// stream (sync code, field codes, CRC-8, agreement with STREAMINFO) is a *candidate*; one thread
+// decodes each candidate to the end of its frame, speculatively and all at once, and reports where
+// the frame ended and whether its CRC-16 holds.  The host then follows the chain first frame ->
+// end -> next frame -> ... exactly as the reference's loop does (a position without a valid
+// candidate is diagnosed by parsing that header on the host, which yields the reference's error),
+// and a last kernel undoes the channel decorrelation of the frames on the chain and writes the
+// interleaved PCM at their final positions.  False candidates (a header look-alike inside
+// compressed data: about one per 16 MB) cost one wasted thread each.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/b200flac.h"
+
+extern "C" void b200flac_internal_set_error(const char* msg);                         // b200flac_encoder.cu
+extern "C" void b200flac_internal_md5(const uint8_t* p, size_t n, uint8_t out[16]);   // b200flac_stream.cu
+
+typedef unsigned char u8;
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+// flac_status, src/decoders/flac.h:68-81, plus the two conditions the reference reports through
+// other channels (EOF via br_abort -> "EOF reading frame"; the frame CRC-16)
+enum {
+    DS_OK = 0, DS_ERROR, DS_INVALID_SYNC_CODE, DS_INVALID_RESERVED_BIT, DS_INVALID_BITS_PER_SAMPLE,
+    DS_INVALID_SAMPLE_RATE, DS_INVALID_FRAME_CRC, DS_SAMPLE_RATE_MISMATCH, DS_CHANNEL_COUNT_MISMATCH,
+    DS_BITS_PER_SAMPLE_MISMATCH, DS_MAXIMUM_BLOCK_SIZE_EXCEEDED, DS_INVALID_CODING_METHOD,
+    DS_INVALID_FIXED_ORDER, DS_INVALID_SUBFRAME_TYPE,
+    DS_EOF = 32, DS_FRAME_CRC16 = 33, DS_MALFORMED = 34
+};
+
+static const char* ds_strerror(u32 s)
+{
+    switch (s) { // FlacDecoder_strerror, src/decoders/flac.c:1273-1311
+    case DS_OK: return "No Error";
+    case DS_INVALID_SYNC_CODE: return "invalid sync code";
+    case DS_INVALID_RESERVED_BIT: return "invalid reserved bit";
+    case DS_INVALID_BITS_PER_SAMPLE: return "invalid bits per sample";
+    case DS_INVALID_SAMPLE_RATE: return "invalid sample rate";
+    case DS_INVALID_FRAME_CRC: return "invalid checksum in frame header";
+    case DS_SAMPLE_RATE_MISMATCH: return "frame sample rate does not match STREAMINFO sample rate";
+    case DS_CHANNEL_COUNT_MISMATCH: return "frame channel count does not match STREAMINFO channel count";
+    case DS_BITS_PER_SAMPLE_MISMATCH: return "frame bits-per-sample does not match STREAMINFO bits per sample";
+    case DS_MAXIMUM_BLOCK_SIZE_EXCEEDED: return "frame block size exceeds STREAMINFO's maximum block size";
+    case DS_INVALID_CODING_METHOD: return "invalid residual partition coding method";
+    case DS_INVALID_FIXED_ORDER: return "invalid FIXED subframe order";
+    case DS_INVALID_SUBFRAME_TYPE: return "invalid subframe type";
+    case DS_EOF: return "EOF reading frame";                      // flac.c:262, :1470
+    case DS_FRAME_CRC16: return "invalid checksum in frame";      // flac.c:252, :1459
+    case DS_MALFORMED: return "malformed frame (residual count does not match the block size)";
+    default: return "Error";
+    }
+}
+
+struct DecStream {
+    u32 sample_rate, channels, bits_per_sample, max_block_size;
+};
+
+struct DecHeader {
+    u32 block_size, assignment, length; // length: header bytes including the CRC-8
+};
+
+struct bf_dec_cand {
+    u64 pos;          // byte offset of the sync code inside the frame region
+    u64 end;          // byte offset just past the frame's CRC-16
+    u32 block_size;
+    u32 status;       // DS_*
+    u32 assignment;
+    u8 wasted[B200FLAC_MAX_CHANNELS];
+    u32 pad;
+};
+
+struct bf_dec_emit {  // one frame on the chain
+    u64 pcm_frame;    // index of its first PCM frame in the output
+    u32 cand;
+    u32 n;            // PCM frames to write
+};
+
+// ---- frame header, host and device (flacdec_read_frame_header, flac.c:710-852) -------------------
+__host__ __device__ inline u32 dec_crc8(const u8* p, u32 n)
+{
+    u32 crc = 0;
+    for (u32 i = 0; i < n; i++) {
+        crc ^= p[i];
+        for (int k = 0; k < 8; k++) crc = (crc & 0x80) ? ((crc << 1) ^ 0x07) & 0xFF : (crc << 1) & 0xFF;
+    }
+    return crc;
+}
+
+__host__ __device__ inline u32 dec_parse_header(const u8* b, u64 avail, const DecStream& S, DecHeader* h)
+{
+    if (avail < 2) return DS_EOF;
+    if (b[0] != 0xFF || (b[1] & 0xFC) != 0xF8) return DS_INVALID_SYNC_CODE;
+    if (b[1] & 0x02) return DS_INVALID_RESERVED_BIT;
+    if (avail < 5) return DS_EOF;
+    const u32 bs_bits = b[2] >> 4, sr_bits = b[2] & 15;
+    h->assignment = b[3] >> 4;
+    const u32 channel_count = (h->assignment >= 8 && h->assignment <= 10) ? 2 : h->assignment + 1;
+    u32 bps;
+    switch ((b[3] >> 1) & 7) {
+    case 0: bps = S.bits_per_sample; break;
+    case 1: bps = 8; break;
+    case 2: bps = 12; break;
+    case 4: bps = 16; break;
+    case 5: bps = 20; break;
+    case 6: bps = 24; break;
+    default: return DS_INVALID_BITS_PER_SAMPLE;
+    }
+    // read_utf8 (flac.c:1313-1323): leading one bits = byte count; only the length matters here
+    u32 ones = 0;
+    while (ones < 8 && (b[4] & (0x80u >> ones))) ones++;
+    if (ones == 8) return DS_INVALID_FRAME_CRC; // the reference's read(7 - 8) is undefined; such a header never checks
+    u32 n = 5 + (ones > 1 ? ones - 1 : 0);
+    if (avail < n + 5) return DS_EOF;
+    switch (bs_bits) {
+    case 0: h->block_size = S.max_block_size; break;
+    case 1: h->block_size = 192; break;
+    case 2: case 3: case 4: case 5: h->block_size = 576u << (bs_bits - 2); break;
+    case 6: h->block_size = (u32)b[n] + 1; n += 1; break;
+    case 7: h->block_size = (((u32)b[n] << 8) | b[n + 1]) + 1; n += 2; break;
+    default: h->block_size = 256u << (bs_bits - 8); break;
+    }
+    u32 rate;
+    switch (sr_bits) {
+    case 0: rate = S.sample_rate; break;
+    case 1: rate = 88200; break;
+    case 2: rate = 176400; break;
+    case 3: rate = 192000; break;
+    case 4: rate = 8000; break;
+    case 5: rate = 16000; break;
+    case 6: rate = 22050; break;
+    case 7: rate = 24000; break;
+    case 8: rate = 32000; break;
+    case 9: rate = 44100; break;
+    case 10: rate = 48000; break;
+    case 11: rate = 96000; break;
+    case 12: rate = (u32)b[n] * 1000; n += 1; break;
+    case 13: rate = ((u32)b[n] << 8) | b[n + 1]; n += 2; break;
+    case 14: rate = (((u32)b[n] << 8) | b[n + 1]) * 10; n += 2; break;
+    default: return DS_INVALID_SAMPLE_RATE;
+    }
+    n += 1; // the CRC-8 byte
+    if (dec_crc8(b, n) != 0) return DS_INVALID_FRAME_CRC;
+    h->length = n;
+    if (S.sample_rate != rate) return DS_SAMPLE_RATE_MISMATCH;
+    if (S.channels != channel_count) return DS_CHANNEL_COUNT_MISMATCH;
+    if (S.bits_per_sample != bps) return DS_BITS_PER_SAMPLE_MISMATCH;
+    if (h->block_size > S.max_block_size) return DS_MAXIMUM_BLOCK_SIZE_EXCEEDED;
+    return DS_OK;
+}
+
+// ---- kernel 1: candidate scan ---------------------------------------------------------------------
+__global__ void k_dec_scan(const u8* __restrict__ data, u64 n_bytes, DecStream S, bf_dec_cand* __restrict__ cands,
+                           u32 cap, u32* __restrict__ count)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p + 1 < n_bytes; p += stride) {
+        if (data[p] != 0xFF || (data[p + 1] & 0xFE) != 0xF8) continue;
+        DecHeader h;
+        if (dec_parse_header(data + p, n_bytes - p, S, &h) != DS_OK) continue;
+        const u32 idx = atomicAdd(count, 1u);
+        if (idx < cap) {
+            cands[idx].pos = p;
+            cands[idx].status = DS_ERROR;
+        }
+    }
+}
+
+// ---- kernel 2: one thread decodes one candidate frame ------------------------------------------------
+// MSB-first bit reader over global memory (the reference's BitstreamReader, big-endian): 64-bit window,
+// refilled with aligned 32-bit loads.  The buffer is padded with zeros, so reads past the end are safe;
+// they raise `eof`, which the caller reports as the reference's "EOF reading frame".
+struct DecBits {
+    const u8* base;
+    u64 n_bytes, next, buf;
+    int avail;
+    bool eof;
+
+    __device__ __forceinline__ void refill()
+    {
+        while (avail <= 32) {
+            if (next >= n_bytes + 16) { avail += 32; eof = true; continue; }
+            if ((next & 3) == 0) {
+                const u32 w = __byte_perm(*(const u32*)(base + next), 0, 0x0123);
+                buf |= (u64)w << (32 - avail);
+                avail += 32;
+                next += 4;
+            } else {
+                buf |= (u64)base[next] << (56 - avail);
+                avail += 8;
+                next += 1;
+            }
+        }
+    }
+    __device__ __forceinline__ void init(const u8* b, u64 n, u64 pos)
+    {
+        base = b; n_bytes = n; next = pos; buf = 0; avail = 0; eof = false;
+        refill();
+    }
+    __device__ __forceinline__ u32 read(u32 n) // 0..32 bits
+    {
+        if (n == 0) return 0;
+        const u32 v = (u32)(buf >> (64 - n));
+        buf <<= n;
+        avail -= (int)n;
+        refill();
+        return v;
+    }
+    __device__ __forceinline__ int read_signed(u32 n) // two's complement, 1..32 bits (bitstream.c read_signed)
+    {
+        if (n == 0) return 0;
+        const u32 v = read(n);
+        return (int)(v << (32 - n)) >> (32 - n);
+    }
+    __device__ __forceinline__ u32 unary1() // zeros before the next one bit (read_unary(bs, 1))
+    {
+        u32 cnt = 0;
+        for (;;) {
+            if (buf) {
+                const int z = __clzll((long long)buf);
+                cnt += (u32)z;
+                buf = (buf << z) << 1;
+                avail -= z + 1;
+                refill();
+                return cnt;
+            }
+            cnt += (u32)avail;
+            avail = 0;
+            if (eof) return cnt;
+            refill();
+        }
+    }
+    __device__ __forceinline__ u64 bits_consumed() const { return next * 8 - (u64)avail; }
+};
+
+#define DEC_FAST_ORDER 12
+
+// One subframe into row[0..n): flacdec_read_subframe (flac.c:854-916) with the residual decode
+// (flac.c:1135-1210) and the predictor (flac.c:1025-1062, 1118-1130) fused sample by sample; the
+// wasted bits are re-inserted by the emit kernel.  FIXED orders are the LPC recurrence with binomial
+// coefficients and shift 0 (the same value modulo 2^32 as the reference's int expressions).
+__device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, u32* wasted_out)
+{
+    rd.read(1);
+    const u32 type = rd.read(6);
+    u32 wasted = 0;
+    if (rd.read(1)) wasted = rd.unary1() + 1;
+    *wasted_out = wasted;
+    if (wasted >= bps) return DS_MALFORMED;
+    bps -= wasted;
+    if (rd.eof) return DS_EOF;
+
+    if (type == 0) { // CONSTANT
+        const int v = rd.read_signed(bps);
+        for (u32 i = 0; i < n; i++) row[i] = v;
+        return DS_OK;
+    }
+    if (type == 1) { // VERBATIM
+        for (u32 i = 0; i < n; i++) row[i] = rd.read_signed(bps);
+        return rd.eof ? DS_EOF : DS_OK;
+    }
+    u32 order, shift = 0;
+    int q[B200FLAC_MAX_LPC_ORDER];
+    const bool fixed = (type & 0x38) == 0x08;
+    if (fixed) {
+        order = type & 7;
+        if (order > 4) return DS_INVALID_FIXED_ORDER;
+    } else if (type & 0x20) {
+        order = (type & 0x1F) + 1;
+    } else {
+        return DS_INVALID_SUBFRAME_TYPE;
+    }
+    if (order > n) return DS_MALFORMED;
+    for (u32 i = 0; i < order; i++) row[i] = rd.read_signed(bps); // warm-up samples
+#pragma unroll
+    for (int j = 0; j < B200FLAC_MAX_LPC_ORDER; j++) q[j] = 0;
+    if (fixed) {
+        const int c1[5] = {0, 1, 2, 3, 4}, c2[5] = {0, 0, -1, -3, -6}, c3[5] = {0, 0, 0, 1, 4}, c4[5] = {0, 0, 0, 0, -1};
+        q[0] = c1[order]; q[1] = c2[order]; q[2] = c3[order]; q[3] = c4[order];
+    } else {
+        const u32 precision = rd.read(4) + 1;
+        const int sh = rd.read_signed(5);
+        shift = sh > 0 ? (u32)sh : 0u; // MAX(qlp_shift_needed, 0), flac.c:1102
+        for (u32 j = 0; j < order; j++) q[j] = rd.read_signed(precision);
+    }
+
+    // residual header, flac.c:1140-1143
+    const u32 method = rd.read(2);
+    if (method > 1) return DS_INVALID_CODING_METHOD;
+    const u32 po = rd.read(4);
+    const u32 plen = n >> po;
+    // otherwise the reference appends a residual count that is not n - order and then indexes past it
+    if (((u64)plen << po) != n || plen < order) return DS_MALFORMED;
+    if (rd.eof) return DS_EOF;
+
+    // recent samples, most recent first, for orders up to DEC_FAST_ORDER; longer predictors read the row
+    int h[DEC_FAST_ORDER], qf[DEC_FAST_ORDER];
+#pragma unroll
+    for (int j = 0; j < DEC_FAST_ORDER; j++) {
+        qf[j] = q[j];
+        h[j] = ((u32)j < order) ? row[order - 1 - j] : 0;
+    }
+    const bool fast = order <= DEC_FAST_ORDER;
+    u32 i = order;
+    for (u32 part = 0; part < (1u << po); part++) {
+        u32 count = part == 0 ? plen - order : plen;
+        u32 k = rd.read(method ? 5 : 4);
+        u32 escape = 0;
+        if (k == (method ? 31u : 15u)) escape = rd.read(5);
+        if (rd.eof) return DS_EOF;
+        for (; count; count--, i++) {
+            int r;
+            if (!escape) {
+                const u32 msb = rd.unary1();
+                const u32 lsb = rd.read(k);
+                const u32 v = (msb << k) | lsb;
+                r = (v & 1) ? -(int)(v >> 1) - 1 : (int)(v >> 1);
+            } else {
+                r = rd.read_signed(escape);
+            }
+            long long acc = 0;
+            if (fast) {
+#pragma unroll
+                for (int j = 0; j < DEC_FAST_ORDER; j++) acc += (long long)qf[j] * (long long)h[j];
+            } else {
+                for (u32 j = 0; j < order; j++) acc += (long long)q[j] * (long long)row[i - 1 - j];
+            }
+            const int s = (int)(acc >> shift) + r;
+            row[i] = s;
+#pragma unroll
+            for (int j = DEC_FAST_ORDER - 1; j > 0; j--) h[j] = h[j - 1];
+            h[0] = s;
+        }
+        if (rd.eof) return DS_EOF;
+    }
+    return DS_OK;
+}
+
+// CRC-16 of src/common/flac_crc.c:62-100 over a byte range, one table look-up per byte
+__device__ u32 dec_crc16(const u8* __restrict__ p, u64 n, const unsigned short* __restrict__ tab)
+{
+    u32 crc = 0;
+    for (u64 i = 0; i < n; i++) crc = ((crc << 8) ^ tab[((crc >> 8) ^ p[i]) & 0xFF]) & 0xFFFF;
+    return crc;
+}
+
+__global__ void __launch_bounds__(32) k_dec_frames(const u8* __restrict__ data, u64 n_bytes, DecStream S,
+                                                   bf_dec_cand* __restrict__ cands, u32 n_cands,
+                                                   int* __restrict__ scratch, u32 row_stride)
+{
+    __shared__ unsigned short tab[256];
+    for (u32 b = threadIdx.x; b < 256; b += blockDim.x) {
+        u32 crc = b << 8;
+        for (int k = 0; k < 8; k++) crc = (crc & 0x8000) ? ((crc << 1) ^ 0x8005) & 0xFFFF : (crc << 1) & 0xFFFF;
+        tab[b] = (unsigned short)crc;
+    }
+    __syncthreads();
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cands) return;
+    bf_dec_cand cd = cands[c];
+    DecHeader h;
+    u32 status = dec_parse_header(data + cd.pos, n_bytes - cd.pos, S, &h);
+    cd.block_size = h.block_size;
+    cd.assignment = h.assignment;
+    DecBits rd;
+    if (status == DS_OK) {
+        rd.init(data, n_bytes, cd.pos + h.length);
+        for (u32 ch = 0; ch < S.channels && status == DS_OK; ch++) {
+            // flacdec_subframe_bits_per_sample, flac.c:952-965
+            const bool side = (h.assignment == 8 && ch == 1) || (h.assignment == 9 && ch == 0) || (h.assignment == 10 && ch == 1);
+            u32 w = 0;
+            status = dec_subframe(rd, h.block_size, S.bits_per_sample + (side ? 1u : 0u),
+                                  scratch + ((u64)c * S.channels + ch) * row_stride, &w);
+            cd.wasted[ch] = (u8)w;
+        }
+    }
+    if (status == DS_OK) {
+        if (rd.eof) status = DS_EOF;
+        const u64 end = (rd.bits_consumed() + 7) / 8 + 2; // byte_align, then the CRC-16 (flac.c:247-249)
+        if (status == DS_OK && end > n_bytes) status = DS_EOF;
+        if (status == DS_OK) {
+            cd.end = end;
+            if (dec_crc16(data + cd.pos, end - cd.pos, tab) != 0) status = DS_FRAME_CRC16;
+        }
+    }
+    cd.status = status;
+    cands[c] = cd;
+}
+
+// ---- kernel 3: decorrelate, re-insert wasted bits, interleave, pack (flac.c:1213-1270, 905-913) ------
+__global__ void k_dec_emit(const bf_dec_cand* __restrict__ cands, const bf_dec_emit* __restrict__ emits,
+                           const int* __restrict__ scratch, u32 row_stride, DecStream S, u8* __restrict__ out)
+{
+    const bf_dec_emit e = emits[blockIdx.x];
+    const bf_dec_cand cd = cands[e.cand];
+    const u32 C = S.channels, B = S.bits_per_sample / 8;
+    const int* rows = scratch + (u64)e.cand * C * row_stride;
+    u8* dst = out + e.pcm_frame * C * B;
+    if (C == 2) {
+        const u32 w0 = cd.wasted[0], w1 = cd.wasted[1];
+        for (u32 i = threadIdx.x; i < e.n; i += blockDim.x) {
+            const int a = (int)((u32)rows[i] << w0), b = (int)((u32)rows[row_stride + i] << w1);
+            int l, r;
+            if (cd.assignment == 8) { l = a; r = a - b; }
+            else if (cd.assignment == 9) { l = a + b; r = b; }
+            else if (cd.assignment == 10) {
+                const long long mid = ((long long)a << 1) | (b & 1);
+                l = (int)((mid + b) >> 1);
+                r = (int)((mid - b) >> 1);
+            } else { l = a; r = b; }
+            if (B == 2) {
+                ((u32*)dst)[i] = ((u32)l & 0xFFFF) | ((u32)r << 16);
+            } else {
+                u8* o = dst + (u64)i * 2 * B;
+                for (u32 k = 0; k < B; k++) { o[k] = (u8)((u32)l >> (8 * k)); o[B + k] = (u8)((u32)r >> (8 * k)); }
+            }
+        }
+        return;
+    }
+    for (u32 t = threadIdx.x; t < e.n * C; t += blockDim.x) {
+        const u32 i = t / C, ch = t - i * C;
+        const u32 v = (u32)rows[(u64)ch * row_stride + i] << cd.wasted[ch];
+        u8* o = dst + (u64)t * B;
+        for (u32 k = 0; k < B; k++) o[k] = (u8)(v >> (8 * k));
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+static int dfail(int rc, const char* msg)
+{
+    b200flac_internal_set_error(msg);
+    return rc;
+}
+
+#define DCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char m_[256]; \
+        snprintf(m_, sizeof(m_), "%s failed: %s", #call, cudaGetErrorString(e_)); b200flac_internal_set_error(m_); \
+        rc = 3; goto done; } } while (0)
+
+// flacdec_read_metadata, src/decoders/flac.c:569-708: "fLaC", then blocks until the last-block flag;
+// STREAMINFO gives the stream parameters, everything else is skipped here
+extern "C" int b200flac_read_streaminfo(const uint8_t* flac, uint64_t n_bytes, b200flac_stream_info* info)
+{
+    if (!flac || !info) return dfail(1, "flac/info is NULL");
+    memset(info, 0, sizeof(*info));
+    if (n_bytes < 4 || memcmp(flac, "fLaC", 4) != 0) return dfail(1, "not a FLAC file");
+    u64 p = 4;
+    bool have = false;
+    for (;;) {
+        if (p + 4 > n_bytes) return dfail(2, "EOF while reading metadata");
+        const u32 last = flac[p] >> 7, type = flac[p] & 0x7F;
+        const u32 len = ((u32)flac[p + 1] << 16) | ((u32)flac[p + 2] << 8) | flac[p + 3];
+        p += 4;
+        if (p + len > n_bytes) return dfail(2, "EOF while reading metadata");
+        if (type == 0) {
+            if (len < 34) return dfail(2, "EOF while reading metadata");
+            const u8* s = flac + p;
+            info->min_block_size = ((u32)s[0] << 8) | s[1];
+            info->max_block_size = ((u32)s[2] << 8) | s[3];
+            info->min_frame_size = ((u32)s[4] << 16) | ((u32)s[5] << 8) | s[6];
+            info->max_frame_size = ((u32)s[7] << 16) | ((u32)s[8] << 8) | s[9];
+            info->sample_rate = ((u32)s[10] << 12) | ((u32)s[11] << 4) | (s[12] >> 4);
+            info->channels = ((s[12] >> 1) & 7) + 1;
+            info->bits_per_sample = (((u32)(s[12] & 1) << 4) | (s[13] >> 4)) + 1;
+            info->total_pcm_frames = ((u64)(s[13] & 15) << 32) | ((u64)s[14] << 24) | ((u64)s[15] << 16) | ((u64)s[16] << 8) | s[17];
+            memcpy(info->md5, s + 18, 16);
+            have = true;
+        }
+        p += len;
+        if (last) break;
+    }
+    if (!have) return dfail(1, "STREAMINFO not found");
+    info->first_frame_offset = p;
+    return 0;
+}
+
+struct DecWork {
+    u8* d_data = nullptr;
+    bf_dec_cand* d_cands = nullptr;
+    bf_dec_emit* d_emits = nullptr;
+    u32* d_count = nullptr;
+    int* d_scratch = nullptr;
+    u8* d_pcm = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~DecWork()
+    {
+        cudaFree(d_data); cudaFree(d_cands); cudaFree(d_emits); cudaFree(d_count); cudaFree(d_scratch); cudaFree(d_pcm);
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+    }
+};
+
+// frames: the bytes from the first frame to the end of the file (host or device memory, see flags)
+static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, uint64_t n_bytes, int frames_on_device,
+                       int device, uint8_t* pcm_out, int pcm_on_device, uint64_t pcm_capacity,
+                       uint64_t** frame_offsets, uint32_t** frame_pcm_frames, uint64_t* n_frames, float* kernel_ms)
+{
+    int rc = 0;
+    if (b200flac_device_count() <= 0) return dfail(3, "no CUDA device available: the B200 FLAC engine has no CPU fallback");
+    if (info->bits_per_sample % 8 || info->bits_per_sample < 8 || info->bits_per_sample > 24 || info->channels < 1 ||
+        info->channels > B200FLAC_MAX_CHANNELS || info->max_block_size == 0)
+        return dfail(3, "unsupported stream parameters");
+    const u32 C = info->channels, B = info->bits_per_sample / 8;
+    const u64 total = info->total_pcm_frames;
+    const u64 pcm_bytes = total * C * B;
+    if (pcm_out && pcm_capacity < pcm_bytes) return dfail(3, "PCM buffer too small");
+    if (n_frames) *n_frames = 0;
+    if (total == 0) return 0; // the reference's loops run while remaining samples > 0 (flac.c:196, :1402)
+
+    DecStream S;
+    S.sample_rate = info->sample_rate; S.channels = C; S.bits_per_sample = info->bits_per_sample;
+    S.max_block_size = info->max_block_size;
+    DecWork w;
+    std::vector<bf_dec_cand> cands;
+    std::vector<bf_dec_emit> emits;
+    std::vector<u64> offs;
+    std::vector<u32> lens;
+    const u32 row_stride = (info->max_block_size + 3) & ~3u;
+    // candidates: the real frames (at least min_block_size PCM frames each, except the last) plus look-alikes
+    const u32 minb = info->min_block_size ? info->min_block_size : 16;
+    u32 cap = (u32)std::min<u64>(total / minb + n_bytes / (1u << 16) + 4096, 0x7FFFFFFFu);
+    u32 count = 0;
+    const u8* d_frames = nullptr;
+    DCK(cudaSetDevice(device));
+    for (auto& e : w.ev) DCK(cudaEventCreate(&e));
+    if (frames_on_device) d_frames = frames;
+    else {
+        DCK(cudaMalloc((void**)&w.d_data, n_bytes + 64));
+        DCK(cudaMemcpy(w.d_data, frames, n_bytes, cudaMemcpyHostToDevice));
+        DCK(cudaMemset(w.d_data + n_bytes, 0, 64));
+        d_frames = w.d_data;
+    }
+    DCK(cudaMalloc((void**)&w.d_count, sizeof(u32)));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        DCK(cudaMalloc((void**)&w.d_cands, (size_t)cap * sizeof(bf_dec_cand)));
+        DCK(cudaMemset(w.d_count, 0, sizeof(u32)));
+        DCK(cudaEventRecord(w.ev[0]));
+        k_dec_scan<<<148 * 8, 256>>>(d_frames, n_bytes, S, w.d_cands, cap, w.d_count);
+        DCK(cudaGetLastError());
+        DCK(cudaMemcpy(&count, w.d_count, sizeof(u32), cudaMemcpyDeviceToHost));
+        if (count <= cap) break;
+        cudaFree(w.d_cands); w.d_cands = nullptr; // more look-alikes than allowed for: size for what was found
+        cap = count;
+    }
+    if (count == 0) { rc = dfail(1, "invalid sync code"); goto done; }
+    DCK(cudaMalloc((void**)&w.d_scratch, (size_t)count * C * row_stride * sizeof(int)));
+    DCK(cudaEventRecord(w.ev[1]));
+    k_dec_frames<<<(count + 31) / 32, 32>>>(d_frames, n_bytes, S, w.d_cands, count, w.d_scratch, row_stride);
+    DCK(cudaGetLastError());
+    DCK(cudaEventRecord(w.ev[2]));
+    cands.resize(count);
+    DCK(cudaMemcpy(cands.data(), w.d_cands, (size_t)count * sizeof(bf_dec_cand), cudaMemcpyDeviceToHost));
+
+    // ---- the reference's frame loop (flac.c:196-268, :1402-1476) over the decoded candidates ----
+    {
+        std::vector<u32> order(count);
+        for (u32 i = 0; i < count; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return cands[a].pos < cands[b].pos; });
+        u64 pos = 0, done_frames = 0;
+        while (done_frames < total) {
+            auto it = std::lower_bound(order.begin(), order.end(), pos, [&](u32 a, u64 p) { return cands[a].pos < p; });
+            u32 status;
+            const bf_dec_cand* cd = nullptr;
+            if (it != order.end() && cands[*it].pos == pos) {
+                cd = &cands[*it];
+                status = cd->status;
+            } else if (frames_on_device) {
+                status = DS_INVALID_SYNC_CODE; // (the header bytes are not on the host to say more)
+            } else {
+                DecHeader h;
+                status = pos >= n_bytes ? (u32)DS_EOF : dec_parse_header(frames + pos, n_bytes - pos, S, &h);
+                if (status == DS_OK) status = DS_ERROR;
+            }
+            if (status == DS_OK && cd->block_size > total - done_frames) status = DS_MALFORMED;
+            if (status != DS_OK) { rc = dfail(status == DS_EOF ? 2 : 1, ds_strerror(status)); goto done; }
+            bf_dec_emit e;
+            e.pcm_frame = done_frames; e.cand = *it; e.n = cd->block_size;
+            emits.push_back(e);
+            offs.push_back(pos);
+            lens.push_back(cd->block_size);
+            done_frames += cd->block_size;
+            pos = cd->end;
+        }
+    }
+    if (pcm_out) {
+        u8* d_pcm = pcm_out;
+        if (!pcm_on_device) { DCK(cudaMalloc((void**)&w.d_pcm, pcm_bytes + 64)); d_pcm = w.d_pcm; }
+        DCK(cudaMalloc((void**)&w.d_emits, emits.size() * sizeof(bf_dec_emit)));
+        DCK(cudaMemcpy(w.d_emits, emits.data(), emits.size() * sizeof(bf_dec_emit), cudaMemcpyHostToDevice));
+        k_dec_emit<<<(u32)emits.size(), 256>>>(w.d_cands, w.d_emits, w.d_scratch, row_stride, S, d_pcm);
+        DCK(cudaGetLastError());
+        DCK(cudaEventRecord(w.ev[3]));
+        if (!pcm_on_device) DCK(cudaMemcpy(pcm_out, d_pcm, pcm_bytes, cudaMemcpyDeviceToHost));
+        else DCK(cudaDeviceSynchronize());
+        if (kernel_ms) {
+            DCK(cudaEventElapsedTime(&kernel_ms[0], w.ev[0], w.ev[1]));
+            DCK(cudaEventElapsedTime(&kernel_ms[1], w.ev[1], w.ev[2]));
+            DCK(cudaEventElapsedTime(&kernel_ms[2], w.ev[2], w.ev[3])); // includes the host's chain walk
+        }
+    }
+    if (n_frames) *n_frames = emits.size();
+    if (frame_offsets) {
+        *frame_offsets = (uint64_t*)malloc((offs.size() ? offs.size() : 1) * sizeof(uint64_t));
+        memcpy(*frame_offsets, offs.data(), offs.size() * sizeof(uint64_t));
+    }
+    if (frame_pcm_frames) {
+        *frame_pcm_frames = (uint32_t*)malloc((lens.size() ? lens.size() : 1) * sizeof(uint32_t));
+        memcpy(*frame_pcm_frames, lens.data(), lens.size() * sizeof(uint32_t));
+    }
+done:
+    return rc;
+}
+
+extern "C" int b200flac_decode_memory(const uint8_t* flac, uint64_t n_bytes, int device, uint8_t* pcm,
+                                      uint64_t pcm_capacity, b200flac_stream_info* info_out, int check_md5,
+                                      uint64_t** frame_offsets, uint32_t** frame_pcm_frames, uint64_t* n_frames,
+                                      float* kernel_ms)
+{
+    b200flac_stream_info info;
+    int rc = b200flac_read_streaminfo(flac, n_bytes, &info);
+    if (rc) return rc;
+    if (info_out) *info_out = info;
+    if (!pcm) return 0; // sizing call
+    rc = decode_core(&info, flac + info.first_frame_offset, n_bytes - info.first_frame_offset, 0, device, pcm, 0,
+                     pcm_capacity, frame_offsets, frame_pcm_frames, n_frames, kernel_ms);
+    if (rc) return rc;
+    if (check_md5) {
+        // FlacDecoder_verify_okay, flac.c:479-490: a blank MD5 in STREAMINFO always passes
+        static const uint8_t blank[16] = {0};
+        uint8_t digest[16];
+        b200flac_internal_md5(pcm, (size_t)(info.total_pcm_frames * info.channels * (info.bits_per_sample / 8)), digest);
+        if (memcmp(info.md5, blank, 16) != 0 && memcmp(info.md5, digest, 16) != 0)
+            return dfail(1, "MD5 mismatch at end of stream");
+    }
+    return 0;
+}
+
+extern "C" int b200flac_decode_device(const b200flac_stream_info* info, const void* d_frames, uint64_t n_bytes,
+                                      int device, void* d_pcm, uint64_t pcm_capacity, uint64_t* n_frames,
+                                      float* kernel_ms)
+{
+    if (!info || !d_frames || !d_pcm) return dfail(3, "info/d_frames/d_pcm is NULL");
+    if (((size_t)d_frames & 3) || ((size_t)d_pcm & 3)) return dfail(3, "device buffers must be 4-byte aligned");
+    return decode_core(info, (const uint8_t*)d_frames, n_bytes, 1, device, (uint8_t*)d_pcm, 1, pcm_capacity, nullptr,
+                       nullptr, n_frames, kernel_ms);
+}
+
+extern "C" int b200flac_verify_file(const char* flac_filename, int device)
+{
+    if (!flac_filename) return dfail(3, "filename is NULL");
+    FILE* f = fopen(flac_filename, "rb");
+    if (!f) {
+        char msg[400];
+        snprintf(msg, sizeof(msg), "cannot open \"%.300s\" for reading", flac_filename);
+        return dfail(2, msg);
+    }
+    fseeko(f, 0, SEEK_END);
+    const u64 n = (u64)ftello(f);
+    fseeko(f, 0, SEEK_SET);
+    std::vector<uint8_t> data(n + 1);
+    const size_t got = fread(data.data(), 1, n, f);
+    fclose(f);
+    if (got != n) return dfail(2, "read error");
+    b200flac_stream_info info;
+    int rc = b200flac_read_streaminfo(data.data(), n, &info);
+    if (rc) return rc;
+    std::vector<uint8_t> pcm((size_t)(info.total_pcm_frames * info.channels * (info.bits_per_sample / 8)) + 1);
+    return b200flac_decode_memory(data.data(), n, device, pcm.data(), pcm.size(), nullptr, 1, nullptr, nullptr, nullptr, nullptr);
+}

@@ -113,6 +113,15 @@ static void md5_final(Md5* m, uint8_t out[16])
     for (int i = 0; i < 16; i++) out[i] = (uint8_t)(h[i >> 2] >> (8 * (i & 3)));
 }
 
+// one-shot digest for the decode/verify layer (b200flac_decoder.cu)
+extern "C" void b200flac_internal_md5(const uint8_t* p, size_t n, uint8_t out[16])
+{
+    Md5 m;
+    md5_init(&m);
+    md5_update(&m, p, n);
+    md5_final(&m, out);
+}
+
 // ---------------------------------------------------------------------------
 struct Lane {
     b200flac_encoder* enc;

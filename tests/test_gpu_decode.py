@@ -1,0 +1,216 @@
+"""GPU FLAC decode / verify (reference src/decoders/flac.c:174-286, 569-1270, 1340-1510).
+
+Streams come from the CPU oracle encoder (byte-identical to the reference encoder's) at every
+compression level and shape; the GPU decoder must return the PCM that went in (and what the compiled
+reference decoder returns), the same frame list, and the reference's error for damaged streams.
+A hand-assembled stream covers what the reference encoder never writes: escape-coded partitions,
+Rice parameter 15 with escape 0, wasted bits on a side channel, an 8-bit block-size escape."""
+import hashlib
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+LEVELS = {
+    "0": dict(block_size=1152, max_lpc_order=0, max_residual_partition_order=3),
+    "3": dict(block_size=1152, max_lpc_order=6, max_residual_partition_order=3, adaptive_mid_side=True),
+    "5": dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=5, mid_side=True),
+    "8": dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, mid_side=True, exhaustive_model_search=True),
+    "l32": dict(block_size=4096, max_lpc_order=32, max_residual_partition_order=8, mid_side=True),
+}
+
+
+def _decode(flac, **kw):
+    import b200flac
+    return b200flac.decode(flac, **kw)
+
+
+@pytest.mark.parametrize("level", sorted(LEVELS))
+@pytest.mark.parametrize("rate,ch,bps,n", [(44100, 2, 16, 44100 * 3 + 17), (96000, 2, 24, 50000), (8000, 1, 8, 9000),
+                                           (96000, 6, 24, 4608 * 5 + 100)])
+def test_decode_round_trip(level, rate, ch, bps, n, built):
+    pcm = helpers.synth_pcm(11 + ch + bps, ch, bps, n)
+    opts = helpers.options(**LEVELS[level])
+    flac, offs = helpers.oracle_encode(pcm, rate, ch, bps, opts, want_offsets=True)
+    info, got, frames, ms = _decode(flac, want_frames=True)
+    assert (info.sample_rate, info.channels, info.bits_per_sample, info.total_pcm_frames) == (rate, ch, bps, n)
+    assert bytes(info.md5) == hashlib.md5(pcm).digest()
+    assert got == pcm
+    assert frames == offs                      # same (byte offset, PCM frames) list as the encoder reported
+    if helpers.have_ref() and level in ("5", "l32"):
+        assert helpers.ref_decode(flac) == got
+
+
+@pytest.mark.parametrize("name", ["silence", "constant", "noise", "wasted", "full_scale", "tiny", "one_sample"])
+def test_decode_special_blocks(name, built):
+    rng = np.random.default_rng(5)
+    if name == "silence":
+        pcm, ch, bps = bytes(4 * 10000), 2, 16
+    elif name == "constant":
+        pcm, ch, bps = helpers.pack_pcm(np.full((9000, 2), -1234, dtype=np.int32), 16), 2, 16
+    elif name == "noise":       # VERBATIM subframes
+        pcm, ch, bps = helpers.pack_pcm(rng.integers(-32768, 32768, size=(12000, 2)).astype(np.int32), 16), 2, 16
+    elif name == "wasted":
+        pcm, ch, bps = helpers.wasted_bps16(20000), 2, 16
+    elif name == "full_scale":
+        pat = helpers.full_scale_patterns(24)[4]
+        pcm, ch, bps = helpers.pack_pcm(np.array((pat * 3000)[:16000], dtype=np.int32).reshape(-1, 2), 24), 2, 24
+    elif name == "tiny":
+        pcm, ch, bps = helpers.synth_pcm(3, 2, 16, 10), 2, 16
+    else:
+        pcm, ch, bps = helpers.synth_pcm(3, 1, 16, 1), 1, 16
+    flac = helpers.oracle_encode(pcm, 44100, ch, bps, helpers.options(**LEVELS["8"]))
+    info, got = _decode(flac)
+    assert got == pcm
+    if helpers.have_ref():
+        assert helpers.ref_decode(flac) == got
+
+
+def test_decode_empty_stream(built):
+    flac = helpers.oracle_encode(b"", 44100, 2, 16, helpers.options())
+    info, got = _decode(flac)
+    assert info.total_pcm_frames == 0 and got == b""
+
+
+def test_decode_short_frames_mid_stream(tmp_path, built):
+    """frames of unequal length in one stream (the stream layer's end_block)"""
+    import b200flac
+    p = b200flac.make_params(44100, 2, 16, block_size=4096, max_lpc_order=8, max_residual_partition_order=5)
+    path = os.path.join(str(tmp_path), "s.flac")
+    pcm = helpers.synth_pcm(9, 2, 16, 30000)
+    s = b200flac.Stream(path, p)
+    for a, b in ((0, 5000), (5000, 5001), (5001, 20000), (20000, 30000)):
+        s.write(pcm[a * 4:b * 4])
+        s.end_block()
+    offs = s.close()
+    flac = open(path, "rb").read()
+    info, got, frames, ms = _decode(flac, want_frames=True)
+    assert got == pcm and frames == offs
+    assert len({f[1] for f in frames}) > 2
+
+
+def _flip(data, pos, mask=0x10):
+    b = bytearray(data)
+    b[pos] ^= mask
+    return bytes(b)
+
+
+def _ref_error(flac):
+    try:
+        helpers.ref_decode(flac)
+    except RuntimeError as e:
+        return str(e)
+    return None
+
+
+def test_decode_damaged_streams_fail_like_the_reference(built):
+    pcm = helpers.synth_pcm(21, 2, 16, 4096 * 6 + 50)
+    flac, offs = helpers.oracle_encode(pcm, 44100, 2, 16, helpers.options(**LEVELS["5"]), want_offsets=True)
+    first = helpers.first_frame_offset(flac)
+    cases = [
+        (_flip(flac, first + offs[2][0] + 40), ValueError, "invalid checksum in frame"),            # payload bit
+        (_flip(flac, first + offs[3][0] + 2), ValueError, "invalid checksum in frame header"),      # header field
+        (_flip(flac, first + offs[1][0] + 1, 0x02), ValueError, "invalid reserved bit"),
+        (_flip(flac, first + offs[1][0], 0x80), ValueError, "invalid sync code"),
+        (_flip(flac, 8 + 18 + 3), ValueError, "MD5 mismatch at end of stream"),                      # STREAMINFO MD5
+        (flac[:first + offs[5][0] + 3], IOError, "EOF reading frame"),
+        (b"fLaX" + flac[4:], ValueError, "not a FLAC file"),
+    ]
+    for bad, exc, text in cases:
+        with pytest.raises(exc, match=text):
+            _decode(bad)
+        if helpers.have_ref() and text not in ("not a FLAC file",):
+            err = _ref_error(bad)
+            assert err is not None
+            want = {"EOF reading frame": "I/O Error reading frame"}.get(text, text)
+            assert want in err, (text, err)
+
+
+class Bits(object):
+    def __init__(self):
+        self.v, self.n = 0, 0
+
+    def put(self, value, bits):
+        self.v = (self.v << bits) | (value & ((1 << bits) - 1))
+        self.n += bits
+
+    def unary(self, zeros):
+        self.put(1, zeros + 1)
+
+    def align(self):
+        if self.n % 8:
+            self.put(0, 8 - self.n % 8)
+
+    def bytes(self):
+        return self.v.to_bytes(self.n // 8, "big")
+
+
+def _crc(data, poly, width):
+    crc, top, mask = 0, 1 << (width - 1), (1 << width) - 1
+    for byte in data:
+        crc ^= byte << (width - 8)
+        for _ in range(8):
+            crc = ((crc << 1) ^ poly) & mask if crc & top else (crc << 1) & mask
+    return crc
+
+
+def test_decode_hand_made_frame(built):
+    """one left/side frame of 16 samples: FIXED order 1 with an escape-coded partition and a Rice partition
+    with parameter 15 whose escape field is 0 (the reference keeps Rice coding, flac.c:1180-1186,1195), then a
+    side channel with 2 wasted bits as FIXED order 0 at coding method 1; block size through the 8-bit escape"""
+    n = 16
+    left = [100, 103, 99, 120, -70, -71, -69, 0, 5, 6, 7, 8, 9, 10, 11, 12]
+    side = [4 * v for v in (1, -2, 3, -4, 5, -6, 7, -8, 0, 0, 1, 1, -1, -1, 2, -2)]
+    b = Bits()
+    b.put(0x3FFE, 14); b.put(0, 1); b.put(0, 1)
+    b.put(6, 4); b.put(9, 4); b.put(8, 4); b.put(4, 3); b.put(0, 1)      # 8-bit block size, 44.1 kHz, left/side, 16 bit
+    b.put(0, 8)                                                           # frame number 0
+    b.put(n - 1, 8)
+    b.put(_crc(b.bytes(), 0x07, 8), 8)
+    # subframe 0: FIXED order 1, 16 bits, partition order 1: [7 residuals escape-coded at 9 bits][8 residuals Rice 15 / escape 0]
+    b.put(0, 1); b.put(0b001001, 6); b.put(0, 1)
+    b.put(left[0], 16)
+    res = [left[i] - left[i - 1] for i in range(1, n)]
+    b.put(0, 2); b.put(1, 4)
+    b.put(15, 4); b.put(9, 5)
+    for r in res[:7]:
+        b.put(r, 9)
+    b.put(15, 4); b.put(0, 5)
+    for r in res[7:]:
+        u = 2 * r if r >= 0 else -2 * r - 1
+        b.unary(u >> 15); b.put(u, 15)
+    # subframe 1: side at 17 bits, 2 wasted bits, FIXED order 0, coding method 1, partition order 0, Rice 3
+    b.put(0, 1); b.put(0b001000, 6); b.put(1, 1); b.unary(1)
+    b.put(1, 2); b.put(0, 4); b.put(3, 5)
+    for v in side:
+        r = v >> 2
+        u = 2 * r if r >= 0 else -2 * r - 1
+        b.unary(u >> 3); b.put(u, 3)
+    b.align()
+    frame = b.bytes()
+    frame += struct.pack(">H", _crc(frame, 0x8005, 16))
+    right = [l - s for l, s in zip(left, side)]
+    pcm = helpers.pack_pcm(np.array(list(zip(left, right)), dtype=np.int32), 16)
+    si = struct.pack(">HH", 16, 16) + b"\x00" * 6 + ((44100 << 44) | (1 << 41) | (15 << 36) | n).to_bytes(8, "big") + hashlib.md5(pcm).digest()
+    flac = b"fLaC" + bytes([0x80, 0, 0, 34]) + si + frame
+    if helpers.have_ref():
+        assert helpers.ref_decode(flac) == pcm
+    info, got = _decode(flac)
+    assert got == pcm
+
+
+def test_verify_file(tmp_path, built):
+    import b200flac
+    pcm = helpers.synth_pcm(2, 2, 16, 100000)
+    flac = helpers.oracle_encode(pcm, 44100, 2, 16, helpers.options(**LEVELS["8"]))
+    good, bad = os.path.join(str(tmp_path), "g.flac"), os.path.join(str(tmp_path), "b.flac")
+    open(good, "wb").write(flac)
+    open(bad, "wb").write(_flip(flac, len(flac) - 100))
+    assert b200flac.verify_file(good)
+    with pytest.raises(ValueError, match="invalid checksum in frame"):
+        b200flac.verify_file(bad)
