@@ -20,6 +20,7 @@
 // interleaved PCM at their final positions.  False candidates (a header look-alike inside
 // compressed data: about one per 16 MB) cost one wasted thread each.
 #include <cuda_runtime.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -170,15 +171,26 @@ __host__ __device__ inline u32 dec_parse_header(const u8* b, u64 avail, const De
 __global__ void k_dec_scan(const u8* __restrict__ data, u64 n_bytes, DecStream S, bf_dec_cand* __restrict__ cands,
                            u32 cap, u32* __restrict__ count)
 {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p + 1 < n_bytes; p += stride) {
-        if (data[p] != 0xFF || (data[p + 1] & 0xFE) != 0xF8) continue;
-        DecHeader h;
-        if (dec_parse_header(data + p, n_bytes - p, S, &h) != DS_OK) continue;
-        const u32 idx = atomicAdd(count, 1u);
-        if (idx < cap) {
-            cands[idx].pos = p;
-            cands[idx].status = DS_ERROR;
+    // four byte positions per thread from two aligned 32-bit loads (the buffer is padded past n_bytes)
+    const u32* __restrict__ words = (const u32*)data;
+    const u64 n_words = (n_bytes + 3) / 4, stride = (u64)gridDim.x * blockDim.x;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n_words; t += stride) {
+        const u32 a = words[t];
+        // no 0xFF byte in this word: no sync code starts here (zero-byte test on the complement)
+        if ((((~a) - 0x01010101u) & a & 0x80808080u) == 0) continue;
+        const u64 v = (u64)a | ((u64)words[t + 1] << 32);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (((v >> (8 * j)) & 0xFF) != 0xFF || ((v >> (8 * j + 8)) & 0xFE) != 0xF8) continue;
+            const u64 p = t * 4 + j;
+            if (p + 1 >= n_bytes) continue;
+            DecHeader h;
+            if (dec_parse_header(data + p, n_bytes - p, S, &h) != DS_OK) continue;
+            const u32 idx = atomicAdd(count, 1u);
+            if (idx < cap) {
+                cands[idx].pos = p;
+                cands[idx].status = DS_ERROR;
+            }
         }
     }
 }
@@ -318,38 +330,47 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
         h[j] = ((u32)j < order) ? row[order - 1 - j] : 0;
     }
     const bool fast = order <= DEC_FAST_ORDER;
-    u32 i = order;
-    for (u32 part = 0; part < (1u << po); part++) {
-        u32 count = part == 0 ? plen - order : plen;
-        u32 k = rd.read(method ? 5 : 4);
-        u32 escape = 0;
-        if (k == (method ? 31u : 15u)) escape = rd.read(5);
-        if (rd.eof) return DS_EOF;
-        for (; count; count--, i++) {
-            int r;
-            if (!escape) {
-                const u32 msb = rd.unary1();
-                const u32 lsb = rd.read(k);
-                const u32 v = (msb << k) | lsb;
-                r = (v & 1) ? -(int)(v >> 1) - 1 : (int)(v >> 1);
-            } else {
-                r = rd.read_signed(escape);
-            }
-            long long acc = 0;
-            if (fast) {
-#pragma unroll
-                for (int j = 0; j < DEC_FAST_ORDER; j++) acc += (long long)qf[j] * (long long)h[j];
-            } else {
-                for (u32 j = 0; j < order; j++) acc += (long long)q[j] * (long long)row[i - 1 - j];
-            }
-            const int s = (int)(acc >> shift) + r;
-            row[i] = s;
-#pragma unroll
-            for (int j = DEC_FAST_ORDER - 1; j > 0; j--) h[j] = h[j - 1];
-            h[0] = s;
+    // ONE loop over the samples of the subframe, whatever the partition order: the lanes of a warp decode
+    // different frames, and nested partition/sample loops would leave lanes with different partition
+    // orders waiting for each other at every partition boundary.  The partition header (flac.c:1157-1186)
+    // is a short predicated detour inside the sample loop instead.
+    const u32 kbits = method ? 5u : 4u, kesc = method ? 31u : 15u, n_parts = 1u << po;
+    u32 part = 0, left = 0, k = 0, escape = 0;
+    for (u32 i = order; i < n; i++) {
+        while (left == 0) {
+            left = part == 0 ? plen - order : plen;
+            part++;
+            k = rd.read(kbits);
+            escape = (k == kesc) ? rd.read(5) : 0u;
         }
+        left--;
+        int r;
+        if (!escape) {
+            const u32 msb = rd.unary1();
+            const u32 lsb = rd.read(k);
+            const u32 v = (msb << k) | lsb;
+            r = (int)(v >> 1) ^ -(int)(v & 1);
+        } else {
+            r = rd.read_signed(escape);
+        }
+        long long acc = 0;
+        if (fast) {
+#pragma unroll
+            for (int j = 0; j < DEC_FAST_ORDER; j++) acc += (long long)qf[j] * (long long)h[j];
+        } else {
+            for (u32 j = 0; j < order; j++) acc += (long long)q[j] * (long long)row[i - 1 - j];
+        }
+        const int s = (int)(acc >> shift) + r;
+        row[i] = s;
+#pragma unroll
+        for (int j = DEC_FAST_ORDER - 1; j > 0; j--) h[j] = h[j - 1];
+        h[0] = s;
         if (rd.eof) return DS_EOF;
     }
+    for (; part < n_parts; part++) { // headers of partitions without residuals (order == partition length)
+        if (rd.read(kbits) == kesc) rd.read(5);
+    }
+    if (rd.eof) return DS_EOF;
     return DS_OK;
 }
 
@@ -490,20 +511,47 @@ extern "C" int b200flac_read_streaminfo(const uint8_t* flac, uint64_t n_bytes, b
     return 0;
 }
 
+// Device buffers are kept between calls (grow-only, one set per process, calls serialised): allocating
+// and freeing 1-2 GB per decode costs more than the kernels.  b200flac_pool_clear() releases them.
 struct DecWork {
-    u8* d_data = nullptr;
-    bf_dec_cand* d_cands = nullptr;
-    bf_dec_emit* d_emits = nullptr;
+    int device = -1;
+    u8* d_data = nullptr;        size_t cap_data = 0;
+    bf_dec_cand* d_cands = nullptr; size_t cap_cands = 0;
+    bf_dec_emit* d_emits = nullptr; size_t cap_emits = 0;
+    int* d_scratch = nullptr;    size_t cap_scratch = 0;
+    u8* d_pcm = nullptr;         size_t cap_pcm = 0;
     u32* d_count = nullptr;
-    int* d_scratch = nullptr;
-    u8* d_pcm = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    ~DecWork()
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void release()
     {
+        if (device >= 0) cudaSetDevice(device);
         cudaFree(d_data); cudaFree(d_cands); cudaFree(d_emits); cudaFree(d_count); cudaFree(d_scratch); cudaFree(d_pcm);
-        for (auto e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        d_data = nullptr; d_cands = nullptr; d_emits = nullptr; d_count = nullptr; d_scratch = nullptr; d_pcm = nullptr;
+        cap_data = cap_cands = cap_emits = cap_scratch = cap_pcm = 0;
+        device = -1;
     }
 };
+static DecWork g_work;
+static pthread_mutex_t g_work_mu = PTHREAD_MUTEX_INITIALIZER;
+
+extern "C" void b200flac_internal_decoder_clear(void)
+{
+    pthread_mutex_lock(&g_work_mu);
+    g_work.release();
+    pthread_mutex_unlock(&g_work_mu);
+}
+
+template <typename T>
+static cudaError_t grow(T** p, size_t* cap, size_t bytes)
+{
+    if (*cap >= bytes && *p) return cudaSuccess;
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    const cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e == cudaSuccess) *cap = bytes;
+    return e;
+}
 
 // frames: the bytes from the first frame to the end of the file (host or device memory, see flags)
 static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, uint64_t n_bytes, int frames_on_device,
@@ -525,7 +573,8 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
     DecStream S;
     S.sample_rate = info->sample_rate; S.channels = C; S.bits_per_sample = info->bits_per_sample;
     S.max_block_size = info->max_block_size;
-    DecWork w;
+    struct Guard { Guard() { pthread_mutex_lock(&g_work_mu); } ~Guard() { pthread_mutex_unlock(&g_work_mu); } } guard;
+    DecWork& w = g_work;
     std::vector<bf_dec_cand> cands;
     std::vector<bf_dec_emit> emits;
     std::vector<u64> offs;
@@ -536,33 +585,35 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
     u32 cap = (u32)std::min<u64>(total / minb + n_bytes / (1u << 16) + 4096, 0x7FFFFFFFu);
     u32 count = 0;
     const u8* d_frames = nullptr;
+    if (w.device != device) w.release();
     DCK(cudaSetDevice(device));
-    for (auto& e : w.ev) DCK(cudaEventCreate(&e));
+    w.device = device;
+    for (auto& e : w.ev) if (!e) DCK(cudaEventCreate(&e));
     if (frames_on_device) d_frames = frames;
     else {
-        DCK(cudaMalloc((void**)&w.d_data, n_bytes + 64));
+        DCK(grow(&w.d_data, &w.cap_data, n_bytes + 64));
         DCK(cudaMemcpy(w.d_data, frames, n_bytes, cudaMemcpyHostToDevice));
         DCK(cudaMemset(w.d_data + n_bytes, 0, 64));
         d_frames = w.d_data;
     }
-    DCK(cudaMalloc((void**)&w.d_count, sizeof(u32)));
+    if (!w.d_count) DCK(cudaMalloc((void**)&w.d_count, sizeof(u32)));
     for (int attempt = 0; attempt < 2; attempt++) {
-        DCK(cudaMalloc((void**)&w.d_cands, (size_t)cap * sizeof(bf_dec_cand)));
+        DCK(grow(&w.d_cands, &w.cap_cands, (size_t)cap * sizeof(bf_dec_cand)));
         DCK(cudaMemset(w.d_count, 0, sizeof(u32)));
         DCK(cudaEventRecord(w.ev[0]));
         k_dec_scan<<<148 * 8, 256>>>(d_frames, n_bytes, S, w.d_cands, cap, w.d_count);
         DCK(cudaGetLastError());
+        DCK(cudaEventRecord(w.ev[1]));
         DCK(cudaMemcpy(&count, w.d_count, sizeof(u32), cudaMemcpyDeviceToHost));
         if (count <= cap) break;
-        cudaFree(w.d_cands); w.d_cands = nullptr; // more look-alikes than allowed for: size for what was found
-        cap = count;
+        cap = count; // more look-alikes than allowed for: size for what was found
     }
     if (count == 0) { rc = dfail(1, "invalid sync code"); goto done; }
-    DCK(cudaMalloc((void**)&w.d_scratch, (size_t)count * C * row_stride * sizeof(int)));
-    DCK(cudaEventRecord(w.ev[1]));
+    DCK(grow(&w.d_scratch, &w.cap_scratch, (size_t)count * C * row_stride * sizeof(int)));
+    DCK(cudaEventRecord(w.ev[2]));
     k_dec_frames<<<(count + 31) / 32, 32>>>(d_frames, n_bytes, S, w.d_cands, count, w.d_scratch, row_stride);
     DCK(cudaGetLastError());
-    DCK(cudaEventRecord(w.ev[2]));
+    DCK(cudaEventRecord(w.ev[3]));
     cands.resize(count);
     DCK(cudaMemcpy(cands.data(), w.d_cands, (size_t)count * sizeof(bf_dec_cand), cudaMemcpyDeviceToHost));
 
@@ -572,12 +623,13 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
         for (u32 i = 0; i < count; i++) order[i] = i;
         std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return cands[a].pos < cands[b].pos; });
         u64 pos = 0, done_frames = 0;
+        size_t cursor = 0; // the chain only moves forward
         while (done_frames < total) {
-            auto it = std::lower_bound(order.begin(), order.end(), pos, [&](u32 a, u64 p) { return cands[a].pos < p; });
+            while (cursor < order.size() && cands[order[cursor]].pos < pos) cursor++;
             u32 status;
             const bf_dec_cand* cd = nullptr;
-            if (it != order.end() && cands[*it].pos == pos) {
-                cd = &cands[*it];
+            if (cursor < order.size() && cands[order[cursor]].pos == pos) {
+                cd = &cands[order[cursor]];
                 status = cd->status;
             } else if (frames_on_device) {
                 status = DS_INVALID_SYNC_CODE; // (the header bytes are not on the host to say more)
@@ -589,7 +641,7 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
             if (status == DS_OK && cd->block_size > total - done_frames) status = DS_MALFORMED;
             if (status != DS_OK) { rc = dfail(status == DS_EOF ? 2 : 1, ds_strerror(status)); goto done; }
             bf_dec_emit e;
-            e.pcm_frame = done_frames; e.cand = *it; e.n = cd->block_size;
+            e.pcm_frame = done_frames; e.cand = order[cursor]; e.n = cd->block_size;
             emits.push_back(e);
             offs.push_back(pos);
             lens.push_back(cd->block_size);
@@ -599,18 +651,18 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
     }
     if (pcm_out) {
         u8* d_pcm = pcm_out;
-        if (!pcm_on_device) { DCK(cudaMalloc((void**)&w.d_pcm, pcm_bytes + 64)); d_pcm = w.d_pcm; }
-        DCK(cudaMalloc((void**)&w.d_emits, emits.size() * sizeof(bf_dec_emit)));
+        if (!pcm_on_device) { DCK(grow(&w.d_pcm, &w.cap_pcm, pcm_bytes + 64)); d_pcm = w.d_pcm; }
+        DCK(grow(&w.d_emits, &w.cap_emits, emits.size() * sizeof(bf_dec_emit)));
         DCK(cudaMemcpy(w.d_emits, emits.data(), emits.size() * sizeof(bf_dec_emit), cudaMemcpyHostToDevice));
         k_dec_emit<<<(u32)emits.size(), 256>>>(w.d_cands, w.d_emits, w.d_scratch, row_stride, S, d_pcm);
         DCK(cudaGetLastError());
-        DCK(cudaEventRecord(w.ev[3]));
+        DCK(cudaEventRecord(w.ev[4]));
         if (!pcm_on_device) DCK(cudaMemcpy(pcm_out, d_pcm, pcm_bytes, cudaMemcpyDeviceToHost));
         else DCK(cudaDeviceSynchronize());
         if (kernel_ms) {
             DCK(cudaEventElapsedTime(&kernel_ms[0], w.ev[0], w.ev[1]));
-            DCK(cudaEventElapsedTime(&kernel_ms[1], w.ev[1], w.ev[2]));
-            DCK(cudaEventElapsedTime(&kernel_ms[2], w.ev[2], w.ev[3])); // includes the host's chain walk
+            DCK(cudaEventElapsedTime(&kernel_ms[1], w.ev[2], w.ev[3]));
+            DCK(cudaEventElapsedTime(&kernel_ms[2], w.ev[3], w.ev[4])); // includes the host's chain walk
         }
     }
     if (n_frames) *n_frames = emits.size();

@@ -273,8 +273,11 @@ static void pool_release(const b200flac_params* p, int device, uint64_t batch_fr
     if (evict) b200flac_encoder_destroy(evict);
 }
 
+extern "C" void b200flac_internal_decoder_clear(void); // b200flac_decoder.cu
+
 extern "C" void b200flac_pool_clear(void)
 {
+    b200flac_internal_decoder_clear();
     std::vector<PoolEntry> all;
     pthread_mutex_lock(&g_pool_mu);
     all.swap(g_pool);
