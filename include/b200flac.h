@@ -285,7 +285,8 @@ int b200flac_encode_aiff(const char *flac_filename, const char *aiff_filename, c
  * (FlacDecoder_strerror, flac.c:1273-1311; "invalid checksum in frame"; "MD5 mismatch at end of stream"). */
 typedef struct b200flac_stream_info {
     uint32_t min_block_size, max_block_size, min_frame_size, max_frame_size;
-    uint32_t sample_rate, channels, bits_per_sample, reserved;
+    uint32_t sample_rate, channels, bits_per_sample;
+    uint32_t channel_mask;        /* from the channel count, or the VORBIS_COMMENT's WAVEFORMATEXTENSIBLE_CHANNEL_MASK (flac.c:509-566,626-658) */
     uint64_t total_pcm_frames;
     uint64_t first_frame_offset;  /* byte offset of the first frame in the file */
     uint8_t  md5[16];

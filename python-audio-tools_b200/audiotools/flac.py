@@ -112,6 +112,25 @@ class FlacAudio(object):
     def total_frames(self):
         return self.__total_frames__
 
+    def to_pcm(self):
+        """returns a PCMReader object containing the track's PCM data (flac.py:1674-1693)"""
+        from . import decoders
+        flac = open(self.filename, "rb")
+        if self.__stream_offset__ > 0:
+            flac.seek(self.__stream_offset__)
+        return decoders.FlacDecoder(flac)
+
+    def verify(self, progress=None):
+        """decodes the whole file, checking every frame CRC-16 and the STREAMINFO MD5 (AudioFile.verify reads
+        to_pcm() to its end, audiotools/__init__.py); on the engine that is one call, b200flac_verify_file.
+        Returns True or raises InvalidFLAC with the decoder's message"""
+        from . import InvalidFLAC
+        from . import decoders
+        try:
+            return decoders.b200flac.verify_file(self.filename)
+        except (IOError, ValueError) as err:
+            raise InvalidFLAC(str(err))
+
     def get_metadata(self):
         blocks = []
         with open(self.filename, "rb") as f:

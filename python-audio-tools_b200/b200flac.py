@@ -63,7 +63,7 @@ class StreamInfo(C.Structure):
     """struct b200flac_stream_info: STREAMINFO as flacdec_read_metadata reads it (src/decoders/flac.c:569-708)"""
     _fields_ = [("min_block_size", C.c_uint32), ("max_block_size", C.c_uint32), ("min_frame_size", C.c_uint32),
                 ("max_frame_size", C.c_uint32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
-                ("bits_per_sample", C.c_uint32), ("reserved", C.c_uint32), ("total_pcm_frames", C.c_uint64),
+                ("bits_per_sample", C.c_uint32), ("channel_mask", C.c_uint32), ("total_pcm_frames", C.c_uint64),
                 ("first_frame_offset", C.c_uint64), ("md5", C.c_uint8 * 16)]
 
 _lib = None

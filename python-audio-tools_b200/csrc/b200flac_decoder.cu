@@ -197,7 +197,8 @@ __global__ void k_dec_scan(const u8* __restrict__ data, u64 n_bytes, DecStream S
 
 // ---- kernel 2: one thread decodes one candidate frame ------------------------------------------------
 // MSB-first bit reader over global memory (the reference's BitstreamReader, big-endian): 64-bit window,
-// refilled with aligned 32-bit loads.  The buffer is padded with zeros, so reads past the end are safe;
+// refilled with aligned 32-bit loads (tried and measured slower: a 16-byte look-ahead feed that hides the L1
+// latency of the refills -- its extra instructions cost the Rice loop more than the stalls it removes).  The buffer is padded with zeros, so reads past the end are safe;
 // they raise `eof`, which the caller reports as the reference's "EOF reading frame".
 struct DecBits {
     const u8* base;
@@ -501,7 +502,45 @@ extern "C" int b200flac_read_streaminfo(const uint8_t* flac, uint64_t n_bytes, b
             info->bits_per_sample = (((u32)(s[12] & 1) << 4) | (s[13] >> 4)) + 1;
             info->total_pcm_frames = ((u64)(s[13] & 15) << 32) | ((u64)s[14] << 24) | ((u64)s[15] << 16) | ((u64)s[16] << 8) | s[17];
             memcpy(info->md5, s + 18, 16);
+            // default channel mask from the channel count, flac.c:626-658
+            static const u32 by_count[9] = {0, 0x4, 0x3, 0x7, 0x33, 0x37, 0x3F, 0x70F, 0x63F};
+            info->channel_mask = by_count[info->channels];
             have = true;
+        } else if (type == 4 && have) {
+            // a WAVEFORMATEXTENSIBLE_CHANNEL_MASK entry overrides it when its bit count equals the
+            // channel count (flacdec_read_vorbis_comment, flac.c:509-566; entries compared in upper case)
+            const u8* c = flac + p;
+            const u64 end = len;
+            u64 q = 0;
+            auto rd32 = [&](u32* v) { if (q + 4 > end) return false; *v = (u32)c[q] | ((u32)c[q + 1] << 8) | ((u32)c[q + 2] << 16) | ((u32)c[q + 3] << 24); q += 4; return true; };
+            u32 n = 0, lines = 0;
+            if (rd32(&n) && q + n <= end) {
+                q += n;
+                if (rd32(&lines)) {
+                    static const char prefix[] = "WAVEFORMATEXTENSIBLE_CHANNEL_MASK=";
+                    const size_t plen = sizeof(prefix) - 1;
+                    for (; lines > 0; lines--) {
+                        u32 l = 0;
+                        if (!rd32(&l) || q + l > end) break;
+                        if (l > plen) {
+                            bool match = true;
+                            for (size_t k = 0; k < plen && match; k++) {
+                                u8 ch = c[q + k];
+                                if (ch >= 'a' && ch <= 'z') ch = (u8)(ch - 32);
+                                match = ch == (u8)prefix[k];
+                            }
+                            if (match) {
+                                char hex[17] = {0};
+                                const size_t hl = std::min<size_t>(l - plen, 16);
+                                memcpy(hex, c + q + plen, hl);
+                                const u32 mask = (u32)strtoul(hex, nullptr, 16);
+                                if ((u32)__builtin_popcount(mask) == info->channels) info->channel_mask = mask;
+                            }
+                        }
+                        q += l;
+                    }
+                }
+            }
         }
         p += len;
         if (last) break;
@@ -619,9 +658,18 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
 
     // ---- the reference's frame loop (flac.c:196-268, :1402-1476) over the decoded candidates ----
     {
+        // candidates in stream order: (position, index) packed in one 64-bit key (positions < 2^40, indices < 2^24;
+        // larger inputs fall back to an indirect sort)
         std::vector<u32> order(count);
-        for (u32 i = 0; i < count; i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return cands[a].pos < cands[b].pos; });
+        if (n_bytes < (1ull << 40) && count < (1u << 24)) {
+            std::vector<u64> key(count);
+            for (u32 i = 0; i < count; i++) key[i] = (cands[i].pos << 24) | i;
+            std::sort(key.begin(), key.end());
+            for (u32 i = 0; i < count; i++) order[i] = (u32)(key[i] & 0xFFFFFF);
+        } else {
+            for (u32 i = 0; i < count; i++) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return cands[a].pos < cands[b].pos; });
+        }
         u64 pos = 0, done_frames = 0;
         size_t cursor = 0; // the chain only moves forward
         while (done_frames < total) {

@@ -1,0 +1,73 @@
+"""CPU: the host side of the decode layer -- STREAMINFO / channel mask as flacdec_read_metadata reads them
+(src/decoders/flac.c:569-708, 509-566), the reference's metadata errors, and the no-fallback rule."""
+import io
+import struct
+
+import pytest
+
+import helpers
+
+
+def _flac(channels=2, bps=16, rate=44100, n=1000, comments=(), extra_blocks=()):
+    pcm = helpers.synth_pcm(1, channels, bps, n)
+    data = helpers.oracle_encode(pcm, rate, channels, bps, helpers.options())
+    if not comments and not extra_blocks:
+        return data
+    # rebuild the metadata: STREAMINFO, a VORBIS_COMMENT with the given entries, the extra blocks, then the frames
+    first = helpers.first_frame_offset(data)
+    vendor = b"test"
+    body = struct.pack("<I", len(vendor)) + vendor + struct.pack("<I", len(comments)) + \
+        b"".join(struct.pack("<I", len(c)) + c for c in comments)
+    blocks = [(4, body)] + list(extra_blocks)
+    out = data[:4] + bytes([0]) + data[5:8] + data[8:42]
+    for i, (bid, payload) in enumerate(blocks):
+        last = 0x80 if i == len(blocks) - 1 else 0
+        out += bytes([last | bid]) + len(payload).to_bytes(3, "big") + payload
+    return out + data[first:]
+
+
+def test_streaminfo_fields(built):
+    import b200flac
+    data = _flac(2, 16, 44100, 12345)
+    info = b200flac.read_streaminfo(data)
+    si = helpers.streaminfo(data)
+    assert (info.sample_rate, info.channels, info.bits_per_sample, info.total_pcm_frames) == (44100, 2, 16, 12345)
+    assert bytes(info.md5) == si["md5"] and info.first_frame_offset == helpers.first_frame_offset(data)
+    assert info.min_block_size == info.max_block_size == 4096 and info.channel_mask == 0x3
+
+
+@pytest.mark.parametrize("channels,mask", [(1, 0x4), (2, 0x3), (3, 0x7), (4, 0x33), (5, 0x37), (6, 0x3F), (7, 0x70F), (8, 0x63F)])
+def test_default_channel_mask_by_count(channels, mask, built):
+    import b200flac
+    assert b200flac.read_streaminfo(_flac(channels, 16, 48000, 100)).channel_mask == mask
+
+
+def test_vorbis_comment_channel_mask_override(built):
+    import b200flac
+    # taken when its bit count equals the channel count; compared in upper case; otherwise ignored
+    assert b200flac.read_streaminfo(_flac(6, 24, 96000, 100, [b"TITLE=x", b"WAVEFORMATEXTENSIBLE_CHANNEL_MASK=0x060F"])).channel_mask == 0x60F
+    assert b200flac.read_streaminfo(_flac(6, 24, 96000, 100, [b"waveformatextensible_channel_mask=0x060f"])).channel_mask == 0x60F
+    assert b200flac.read_streaminfo(_flac(6, 24, 96000, 100, [b"WAVEFORMATEXTENSIBLE_CHANNEL_MASK=0x0003"])).channel_mask == 0x3F
+    assert b200flac.read_streaminfo(_flac(2, 16, 44100, 100, [b"WAVEFORMATEXTENSIBLE_CHANNEL_MASK=0x0030"], [(1, bytes(10))])).channel_mask == 0x30
+
+
+def test_metadata_errors_like_the_reference(built):
+    import b200flac
+    data = _flac()
+    with pytest.raises(ValueError, match="not a FLAC file"):
+        b200flac.read_streaminfo(b"RIFF" + data[4:])
+    with pytest.raises(IOError, match="EOF while reading metadata"):
+        b200flac.read_streaminfo(data[:30])
+    with pytest.raises(IOError, match="EOF while reading metadata"):
+        b200flac.read_streaminfo(data[:4] + bytes([0x00]) + data[5:60])   # last-block flag cleared, then nothing
+
+
+def test_decode_without_gpu_fails_loudly(built):
+    import audiotools.decoders
+    import b200flac
+    if b200flac.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    d = audiotools.decoders.FlacDecoder(io.BytesIO(_flac()))
+    assert (d.sample_rate, d.channels, d.bits_per_sample, d.channel_mask) == (44100, 2, 16, 0x3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        d.read(4096)

@@ -214,3 +214,66 @@ def test_verify_file(tmp_path, built):
     assert b200flac.verify_file(good)
     with pytest.raises(ValueError, match="invalid checksum in frame"):
         b200flac.verify_file(bad)
+
+
+def test_flacdecoder_reads_frame_by_frame(tmp_path, built):
+    """decoders.FlacDecoder (src/decoders/flac.c:28-286): PCMReader attributes, one FLAC frame per read(),
+    an empty FrameList at the end, ValueError after close()"""
+    import audiotools
+    import audiotools.decoders
+    n = 4096 * 7 + 99
+    pcm = helpers.synth_pcm(8, 2, 16, n)
+    path = os.path.join(str(tmp_path), "d.flac")
+    flac = audiotools.FlacAudio.from_pcm(path, audiotools.PCMBytesReader(pcm, 44100, 2, 0x3, 16), "6")
+    d = flac.to_pcm()
+    assert (d.sample_rate, d.channels, d.bits_per_sample, d.channel_mask) == (44100, 2, 16, 0x3)
+    sizes, got = [], []
+    while True:
+        f = d.read(4096)
+        if f.frames == 0:
+            break
+        sizes.append(f.frames)
+        got.extend(list(f))
+    assert sizes == [4096] * 7 + [99] and got == list(helpers.unpack_pcm(pcm, 16))
+    assert d.read(4096).frames == 0
+    assert [o[1] for o in d.offsets()] == sizes
+    d.close()
+    with pytest.raises(ValueError, match="cannot read closed stream"):
+        d.read(4096)
+    assert flac.verify() is True
+
+
+def test_flacdecoder_md5_mismatch_at_end_of_stream(tmp_path, built):
+    import audiotools
+    import audiotools.decoders
+    pcm = helpers.synth_pcm(8, 2, 16, 10000)
+    flac = helpers.oracle_encode(pcm, 44100, 2, 16, helpers.options())
+    path = os.path.join(str(tmp_path), "m.flac")
+    open(path, "wb").write(_flip(flac, 8 + 18 + 5))
+    d = audiotools.FlacAudio(path).to_pcm()
+    frames = 0
+    with pytest.raises(ValueError, match="MD5 mismatch at end of stream"):
+        while True:
+            f = d.read(4096)
+            assert f.frames > 0        # every frame is delivered before the mismatch is reported
+            frames += f.frames
+    assert frames == 10000
+    with pytest.raises(audiotools.InvalidFLAC, match="MD5 mismatch at end of stream"):
+        audiotools.FlacAudio(path).verify()
+
+
+def test_transcode_round_trip_through_both_engines(tmp_path, built):
+    """WAVE -> FLAC (file feed) -> PCM (GPU decoder) == the WAVE's data chunk"""
+    import audiotools
+    import struct as st
+    n = 4096 * 20 + 7
+    pcm = helpers.synth_pcm(77, 2, 24, n)
+    wav = os.path.join(str(tmp_path), "t.wav")
+    fmt = st.pack("<HHIIHH", 1, 2, 96000, 96000 * 6, 6, 24)
+    open(wav, "wb").write(b"RIFF" + st.pack("<I", 4 + 8 + len(fmt) + 8 + len(pcm)) + b"WAVE" + b"fmt " + st.pack("<I", len(fmt)) + fmt +
+                          b"data" + st.pack("<I", len(pcm)) + pcm)
+    path = os.path.join(str(tmp_path), "t.flac")
+    flac = audiotools.FlacAudio.from_pcm(path, audiotools.WaveAudio(wav).to_pcm(), "8")
+    import b200flac
+    info, got = b200flac.decode(open(path, "rb").read())
+    assert got == pcm and info.channel_mask == 0x3
