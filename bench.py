@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=3600.0, help="audio per GPU per step (default: the 1 h config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-check", action="store_true", help="skip decoding the whole step on the GPU after the timed region")
     ap.add_argument("--e2e-slots", type=int, default=4, help="batches in flight in the end-to-end arm")
     ap.add_argument("--e2e-batch-blocks", type=int, default=2048, help="FLAC frames per end-to-end batch")
     ap.add_argument("--verify-seconds", type=float, default=120.0,
@@ -294,6 +295,37 @@ def main():
         elapsed = float(t.item())
     samples_per_step = n_frames_pcm * CHANNELS
     value = world * samples_per_step * args.steps / elapsed / 1e6
+
+    # ---- whole-step check, outside the timed region: the frames the last step left in HBM are decoded by
+    # the engine's own GPU decoder (every frame header CRC-8 and frame CRC-16 checked) and the
+    # PCM must equal the step's input, all of it -- the size-independent round trip at full size.  (The
+    # reference decoder checks a sample of the workload in the CPU leg below.) ----
+    full_check = None
+    if not args.no_full_check:
+        info = b200flac.StreamInfo()
+        info.min_block_size = info.max_block_size = BLOCK
+        info.sample_rate, info.channels, info.bits_per_sample, info.total_pcm_frames = SAMPLE_RATE, CHANNELS, BPS, n_frames_pcm
+        d_dec = L.b200flac_device_alloc(dev, pcm_bytes + 64)
+        if not d_dec:
+            raise SystemExit("device allocation failed: " + L.b200flac_last_error().decode())
+        nf, kms = C.c_uint64(0), (C.c_float * 3)()
+        t0 = time.perf_counter()
+        if L.b200flac_decode_device(C.byref(info), d_out, out_bytes, dev, d_dec, pcm_bytes, C.byref(nf), kms):
+            raise SystemExit("whole-step check failed: " + L.b200flac_last_error().decode())
+        dec_s = time.perf_counter() - t0
+        a = np.empty(pcm_bytes, dtype=np.uint8)
+        b = np.empty(pcm_bytes, dtype=np.uint8)
+        L.b200flac_device_download(dev, a.ctypes.data, d_pcm, pcm_bytes)
+        L.b200flac_device_download(dev, b.ctypes.data, d_dec, pcm_bytes)
+        same = bool(np.array_equal(a, b))
+        del a, b
+        L.b200flac_device_free(dev, d_dec)
+        L.b200flac_pool_clear()   # (releases the decoder's scratch before the end-to-end arm)
+        full_check = {"what": "GPU decode of the step's %d frames back to PCM, compared with the input" % nf.value,
+                      "pcm_identical": same, "decode_ms": dec_s * 1e3,
+                      "decode_kernel_ms": {"scan": kms[0], "frames": kms[1], "chain_emit": kms[2]}}
+        if not same or nf.value != n_flac_frames:
+            raise SystemExit("whole-step check failed: decoded PCM differs from the input")
     kernel_ms = [v / args.steps for v in kernel_ms]
     # CUDA-event intervals recorded by the library on the stream it launches on.  "crc16" is the separate
     # CRC kernel of the k_pack_v2 path; k_pack_v3 (the default) computes the CRC-16 inside "pack".
@@ -426,6 +458,7 @@ def main():
                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (pcm_bytes / 1e6),
                        "sharding": "frame range per GPU, no collective"},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
+            "full_check": full_check,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
                        "samples": clk["samples"], "samples_in_timed_regions": clk["samples_in_timed_regions"]},
         }

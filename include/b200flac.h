@@ -303,8 +303,8 @@ int b200flac_decode_memory(const uint8_t *flac, uint64_t n_bytes, int device, ui
                            uint64_t pcm_capacity, b200flac_stream_info *info, int check_md5,
                            uint64_t **frame_offsets, uint32_t **frame_pcm_frames, uint64_t *n_frames,
                            float *kernel_ms);
-/* The same with the frames (first frame to end of file; 4-byte aligned, 32 readable bytes of padding
- * after n_bytes) already in device memory and the PCM left in device memory. */
+/* The same with the frames (first frame to end of file; 16-byte aligned, 64 readable bytes of padding
+ * after n_bytes) already in device memory and the PCM left in device memory (4-byte aligned). */
 int b200flac_decode_device(const b200flac_stream_info *info, const void *d_frames, uint64_t n_bytes,
                            int device, void *d_pcm, uint64_t pcm_capacity, uint64_t *n_frames,
                            float *kernel_ms);

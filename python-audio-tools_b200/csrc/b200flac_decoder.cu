@@ -197,34 +197,44 @@ __global__ void k_dec_scan(const u8* __restrict__ data, u64 n_bytes, DecStream S
 
 // ---- kernel 2: one thread decodes one candidate frame ------------------------------------------------
 // MSB-first bit reader over global memory (the reference's BitstreamReader, big-endian): 64-bit window,
-// refilled with aligned 32-bit loads (tried and measured slower: a 16-byte look-ahead feed that hides the L1
-// latency of the refills -- its extra instructions cost the Rice loop more than the stalls it removes).  The buffer is padded with zeros, so reads past the end are safe;
+// refilled with aligned 32-bit loads.  The buffer is padded with zeros, so reads past the end are safe;
 // they raise `eof`, which the caller reports as the reference's "EOF reading frame".
 struct DecBits {
     const u8* base;
-    u64 n_bytes, next, buf;
+    u64 n_bytes, next, buf; // next: byte offset (a multiple of 4) of `ahead`
+    u32 ahead;              // the word at `next`, as loaded (little-endian), fetched one refill EARLY: the lanes of a warp
+                            // walk 32 different frames, so a refill load usually misses L1 for some lane;
+                            // issued a refill ahead (about three samples), it has landed when it is needed
     int avail;
     bool eof;
 
+    // (the word is kept as loaded and byte-swapped only when it is consumed: nothing may read the
+    // load's register before the next refill, or the warp waits for the load right here)
+    __device__ __forceinline__ u32 word(u64 off) const
+    {
+        u32 w = 0;
+        if (off < n_bytes + 32) w = *(const u32*)(base + off);
+        return w;
+    }
     __device__ __forceinline__ void refill()
     {
         while (avail <= 32) {
-            if (next >= n_bytes + 16) { avail += 32; eof = true; continue; }
-            if ((next & 3) == 0) {
-                const u32 w = __byte_perm(*(const u32*)(base + next), 0, 0x0123);
-                buf |= (u64)w << (32 - avail);
-                avail += 32;
-                next += 4;
-            } else {
-                buf |= (u64)base[next] << (56 - avail);
-                avail += 8;
-                next += 1;
-            }
+            if (next >= n_bytes + 16) eof = true;
+            buf |= (u64)__byte_perm(ahead, 0, 0x0123) << (32 - avail);
+            avail += 32;
+            next += 4;
+            ahead = word(next);
         }
     }
     __device__ __forceinline__ void init(const u8* b, u64 n, u64 pos)
     {
-        base = b; n_bytes = n; next = pos; buf = 0; avail = 0; eof = false;
+        base = b; n_bytes = n; eof = false;
+        // the first word holds pos & 3 bytes that precede the position
+        const u32 skip = (u32)(pos & 3);
+        buf = ((u64)__byte_perm(word(pos & ~3ull), 0, 0x0123) << 32) << (8 * skip);
+        avail = 32 - 8 * (int)skip;
+        next = (pos & ~3ull) + 4;
+        ahead = word(next);
         refill();
     }
     __device__ __forceinline__ u32 read(u32 n) // 0..32 bits
@@ -375,11 +385,36 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
     return DS_OK;
 }
 
-// CRC-16 of src/common/flac_crc.c:62-100 over a byte range, one table look-up per byte
-__device__ u32 dec_crc16(const u8* __restrict__ p, u64 n, const unsigned short* __restrict__ tab)
+// CRC-16 of src/common/flac_crc.c:62-100 over [pos, pos + n): the aligned middle sixteen bytes per step --
+// the next 16-byte load is issued before the current one is folded in, four bytes per table step
+// (tab[k][b] = CRC of byte b followed by k zero bytes) -- head and tail bytes singly
+__device__ __forceinline__ u32 dec_crc16_word(u32 crc, u32 w, const unsigned short (*tab)[256])
+{
+    return tab[3][((crc >> 8) ^ w) & 0xFF] ^ tab[2][(crc ^ (w >> 8)) & 0xFF] ^ tab[1][(w >> 16) & 0xFF] ^ tab[0][w >> 24];
+}
+
+__device__ u32 dec_crc16(const u8* __restrict__ data, u64 pos, u64 n, const unsigned short (*tab)[256])
 {
     u32 crc = 0;
-    for (u64 i = 0; i < n; i++) crc = ((crc << 8) ^ tab[((crc >> 8) ^ p[i]) & 0xFF]) & 0xFFFF;
+    const u8* p = data + pos;
+    for (; n && ((size_t)p & 15); p++, n--) crc = ((crc << 8) ^ tab[0][((crc >> 8) ^ *p) & 0xFF]) & 0xFFFF;
+    if (n >= 16) {
+        uint4 cur = *(const uint4*)p;
+        for (;;) {
+            n -= 16;
+            p += 16;
+            const bool more = n >= 16;
+            uint4 nx = cur;
+            if (more) nx = *(const uint4*)p;
+            crc = dec_crc16_word(crc, cur.x, tab);
+            crc = dec_crc16_word(crc, cur.y, tab);
+            crc = dec_crc16_word(crc, cur.z, tab);
+            crc = dec_crc16_word(crc, cur.w, tab);
+            if (!more) break;
+            cur = nx;
+        }
+    }
+    for (; n; p++, n--) crc = ((crc << 8) ^ tab[0][((crc >> 8) ^ *p) & 0xFF]) & 0xFFFF;
     return crc;
 }
 
@@ -387,13 +422,20 @@ __global__ void __launch_bounds__(32) k_dec_frames(const u8* __restrict__ data, 
                                                    bf_dec_cand* __restrict__ cands, u32 n_cands,
                                                    int* __restrict__ scratch, u32 row_stride)
 {
-    __shared__ unsigned short tab[256];
+    __shared__ unsigned short tab[4][256];
     for (u32 b = threadIdx.x; b < 256; b += blockDim.x) {
         u32 crc = b << 8;
         for (int k = 0; k < 8; k++) crc = (crc & 0x8000) ? ((crc << 1) ^ 0x8005) & 0xFFFF : (crc << 1) & 0xFFFF;
-        tab[b] = (unsigned short)crc;
+        tab[0][b] = (unsigned short)crc;
     }
     __syncthreads();
+    for (int k = 1; k < 4; k++) {
+        for (u32 b = threadIdx.x; b < 256; b += blockDim.x) {
+            const u32 c = tab[k - 1][b];
+            tab[k][b] = (unsigned short)(((c << 8) ^ tab[0][c >> 8]) & 0xFFFF);
+        }
+        __syncthreads();
+    }
     const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cands) return;
     bf_dec_cand cd = cands[c];
@@ -419,7 +461,7 @@ __global__ void __launch_bounds__(32) k_dec_frames(const u8* __restrict__ data, 
         if (status == DS_OK && end > n_bytes) status = DS_EOF;
         if (status == DS_OK) {
             cd.end = end;
-            if (dec_crc16(data + cd.pos, end - cd.pos, tab) != 0) status = DS_FRAME_CRC16;
+            if (dec_crc16(data, cd.pos, end - cd.pos, tab) != 0) status = DS_FRAME_CRC16;
         }
     }
     cd.status = status;
@@ -755,7 +797,7 @@ extern "C" int b200flac_decode_device(const b200flac_stream_info* info, const vo
                                       float* kernel_ms)
 {
     if (!info || !d_frames || !d_pcm) return dfail(3, "info/d_frames/d_pcm is NULL");
-    if (((size_t)d_frames & 3) || ((size_t)d_pcm & 3)) return dfail(3, "device buffers must be 4-byte aligned");
+    if (((size_t)d_frames & 15) || ((size_t)d_pcm & 3)) return dfail(3, "d_frames must be 16-byte aligned, d_pcm 4-byte aligned");
     return decode_core(info, (const uint8_t*)d_frames, n_bytes, 1, device, (uint8_t*)d_pcm, 1, pcm_capacity, nullptr,
                        nullptr, n_frames, kernel_ms);
 }
