@@ -255,6 +255,25 @@ def device_count():
     return lib().b200flac_device_count()
 
 
+def synth_pcm(seed, channels, bits_per_sample, n_pcm_frames, device=0, first_frame=0):
+    """the bench's integer synthetic signal (k_synth.cuh), generated on the device and downloaded: packed PCM bytes"""
+    import numpy as np
+    L = lib()
+    nbytes = n_pcm_frames * channels * (bits_per_sample // 8)
+    d = L.b200flac_device_alloc(device, max(nbytes, 1))
+    if not d:
+        raise _err()
+    try:
+        if L.b200flac_device_synth_pcm(device, d, seed, channels, bits_per_sample, first_frame, n_pcm_frames):
+            raise _err()
+        out = np.empty(max(nbytes, 1), dtype=np.uint8)
+        if L.b200flac_device_download(device, out.ctypes.data, d, nbytes):
+            raise _err()
+    finally:
+        L.b200flac_device_free(device, d)
+    return out[:nbytes].tobytes()
+
+
 def encode_file(filename, params, pcm, n_pcm_frames, padding_size=4096, version=None, devices=None):
     """standalone-reference equivalent: packed PCM in memory -> FLAC file (flac.c:124-306)"""
     devs = None

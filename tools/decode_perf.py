@@ -14,7 +14,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "python-audio-tools_b200"))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import b200flac  # noqa: E402
 
 
@@ -60,9 +59,8 @@ def main():
     # the reference decoder on one host core over 120 s of the same stream shape
     ref = os.path.join(ROOT, "oracle", "_ref", "flacdec")
     if os.path.exists(ref):
-        import helpers
         m = 120 * rate
-        pcm = helpers.synth_pcm(1235, ch, bps, m)
+        pcm = b200flac.synth_pcm(1235, ch, bps, m)
         with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
             path = os.path.join(d, "s.flac")
             b200flac.encode_file(path, p, pcm, m)

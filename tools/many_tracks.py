@@ -10,16 +10,14 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "python-audio-tools_b200"))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import b200flac  # noqa: E402
-import helpers  # noqa: E402
 
 
 def main():
     tracks = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     threads = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 8)
     n = 7938000                                   # 3 minutes at 44.1 kHz
-    pcms = [helpers.synth_pcm(2000 + i, 2, 16, n) for i in range(4)]
+    pcms = [b200flac.synth_pcm(2000 + i, 2, 16, n) for i in range(4)]
     d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     for label, kw in (("level 8 (from_pcm default: -m -e, lpc 12)", dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6,
                                                                         mid_side=True, exhaustive_model_search=True)),

@@ -9,16 +9,14 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "python-audio-tools_b200"))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import audiotools  # noqa: E402
 import b200flac  # noqa: E402
-import helpers  # noqa: E402
 
 
 def main():
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 600.0
     n = int(seconds * 44100)
-    pcm = helpers.synth_pcm(1235, 2, 16, n)
+    pcm = b200flac.synth_pcm(1235, 2, 16, n)
     d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     t0 = time.perf_counter(); hashlib.md5(pcm).digest(); t_md5 = time.perf_counter() - t0
     p = b200flac.make_params(44100, 2, 16, block_size=4096, max_lpc_order=12, max_residual_partition_order=6,
