@@ -39,11 +39,14 @@ static void md5_block(Md5* m, const uint8_t* p)
     uint32_t x[16];
     memcpy(x, p, 64); // little-endian host
     uint32_t a = m->a, b = m->b, c = m->c, d = m->d;
+    // x_ is the value produced by the previous step, so each round function is written with as little
+    // work as possible after x_: F2's two terms have no bits in common and join the additions
+    // ((x & z) + (y & ~z)), F3 folds y ^ z first, and w + data never waits for x_ at all
 #define F1(x, y, z) (z ^ (x & (y ^ z)))
-#define F2(x, y, z) F1(z, x, y)
-#define F3(x, y, z) (x ^ y ^ z)
+#define F2(x, y, z) ((x & z) + (y & ~z))
+#define F3(x, y, z) (x ^ (y ^ z))
 #define F4(x, y, z) (y ^ (x | ~z))
-#define STEP(f, w, x_, y, z, data, s) (w += f(x_, y, z) + data, w = rol(w, s) + x_)
+#define STEP(f, w, x_, y, z, data, s) (w = (w + (data)) + f(x_, y, z), w = rol(w, s) + x_)
     STEP(F1, a, b, c, d, x[0] + 0xd76aa478, 7);   STEP(F1, d, a, b, c, x[1] + 0xe8c7b756, 12);
     STEP(F1, c, d, a, b, x[2] + 0x242070db, 17);  STEP(F1, b, c, d, a, x[3] + 0xc1bdceee, 22);
     STEP(F1, a, b, c, d, x[4] + 0xf57c0faf, 7);   STEP(F1, d, a, b, c, x[5] + 0x4787c62a, 12);
@@ -128,6 +131,7 @@ struct Lane {
     int slot;
     uint8_t* pcm;          // pinned staging of this lane
     uint64_t fill;         // PCM frames staged
+    uint64_t md5_enq;      // PCM frames of this batch already handed to the MD5 thread
     std::vector<b200flac_segment> segs;
     uint64_t seg_start;    // first PCM frame of the open segment
     bool in_flight;
@@ -135,6 +139,7 @@ struct Lane {
 };
 
 struct Md5Job { const uint8_t* p; size_t n; };
+static const size_t MD5_PIECE = 4u << 20; // bytes of a filling batch handed to the MD5 thread at a time
 
 struct b200flac_stream {
     FILE* f;
@@ -363,7 +368,7 @@ extern "C" b200flac_stream* b200flac_stream_open(const char* filename, const b20
         for (int i = 0; i < n_devices; i++) {
             Lane l;
             l.enc = s->encs[i]; l.slot = k; l.pcm = b200flac_encoder_slot_pcm(l.enc, k);
-            l.fill = 0; l.seg_start = 0; l.in_flight = false; l.md5_ticket = 0;
+            l.fill = 0; l.md5_enq = 0; l.seg_start = 0; l.in_flight = false; l.md5_ticket = 0;
             s->lanes.push_back(l);
         }
 
@@ -424,6 +429,7 @@ static int collect_oldest(b200flac_stream* s)
     }
     l.in_flight = false;
     l.fill = 0;
+    l.md5_enq = 0;
     l.segs.clear();
     s->oldest = (s->oldest + 1) % s->lanes.size();
     s->n_in_flight--;
@@ -445,18 +451,29 @@ static void close_segment(b200flac_stream* s, Lane& l)
     }
 }
 
+// Hands the staged PCM the MD5 thread has not seen yet to it -- while a batch is still filling, in pieces
+// of at least `min_bytes`, so the (serial) hash runs under the copy or file read that fills the batch
+// instead of starting when the batch is complete.  The lane's ticket is its last job.
+static void md5_enqueue(b200flac_stream* s, Lane& l, size_t min_bytes)
+{
+    const size_t frame_bytes = (size_t)s->params.channels * (s->params.bits_per_sample / 8);
+    const size_t pending = (size_t)(l.fill - l.md5_enq) * frame_bytes;
+    if (pending == 0 || pending < min_bytes) return;
+    pthread_mutex_lock(&s->mu);
+    s->jobs.push_back(Md5Job{l.pcm + (size_t)l.md5_enq * frame_bytes, pending});
+    l.md5_ticket = ++s->jobs_submitted;
+    pthread_cond_signal(&s->cv_job);
+    pthread_mutex_unlock(&s->mu);
+    l.md5_enq = l.fill;
+}
+
 // hand the current lane to its device and move on to the next lane
 static int submit_current(b200flac_stream* s)
 {
     Lane& l = s->lanes[s->cur];
     close_segment(s, l);
     if (l.segs.empty()) return 0;
-    const size_t frame_bytes = (size_t)s->params.channels * (s->params.bits_per_sample / 8);
-    pthread_mutex_lock(&s->mu);
-    s->jobs.push_back(Md5Job{l.pcm, (size_t)l.fill * frame_bytes});
-    l.md5_ticket = ++s->jobs_submitted;
-    pthread_cond_signal(&s->cv_job);
-    pthread_mutex_unlock(&s->mu);
+    md5_enqueue(s, l, 0); // whatever of this batch the MD5 thread has not been given yet
     if (b200flac_encoder_submit(l.enc, l.slot, l.pcm, l.segs.data(), (uint32_t)l.segs.size())) {
         stream_err(b200flac_last_error());
         s->failed = true;
@@ -468,7 +485,7 @@ static int submit_current(b200flac_stream* s)
     Lane& nx = s->lanes[s->cur];
     if (nx.in_flight && collect_oldest(s)) return 1; // lanes are reused in order, so nx is the oldest
     md5_wait(s, nx.md5_ticket);                      // its staging must not be hashed any more
-    nx.fill = 0; nx.seg_start = 0; nx.segs.clear();
+    nx.fill = 0; nx.md5_enq = 0; nx.seg_start = 0; nx.segs.clear();
     return 0;
 }
 
@@ -483,9 +500,12 @@ extern "C" int b200flac_stream_write(b200flac_stream* s, const uint8_t* pcm, uin
         const uint64_t cap = l.seg_start + (s->batch_frames - l.seg_start) / bs * bs;
         const uint64_t room = cap - l.fill;
         if (room == 0) { if (submit_current(s)) return 1; continue; }
-        const uint64_t take = n_pcm_frames < room ? n_pcm_frames : room;
+        uint64_t take = n_pcm_frames < room ? n_pcm_frames : room;
+        const uint64_t piece = MD5_PIECE / frame_bytes + 1; // copy in pieces so the MD5 thread starts early
+        if (take > piece) take = piece;
         memcpy(l.pcm + (size_t)l.fill * frame_bytes, pcm, (size_t)take * frame_bytes);
         l.fill += take;
+        md5_enqueue(s, l, MD5_PIECE);
         pcm += (size_t)take * frame_bytes;
         n_pcm_frames -= take;
         if (l.fill == cap && submit_current(s)) return 1;
@@ -531,7 +551,9 @@ extern "C" int b200flac_stream_write_file(b200flac_stream* s, const char* path, 
         const uint64_t cap = l.seg_start + (s->batch_frames - l.seg_start) / bs * bs;
         const uint64_t room = cap - l.fill;
         if (room == 0) { rc = submit_current(s); continue; }
-        const uint64_t take = n_pcm_frames < room ? n_pcm_frames : room;
+        uint64_t take = n_pcm_frames < room ? n_pcm_frames : room;
+        const uint64_t piece = MD5_PIECE / frame_bytes + 1; // read in pieces so the MD5 thread starts early
+        if (take > piece) take = piece;
         uint8_t* dst = l.pcm + (size_t)l.fill * frame_bytes;
         const size_t want = (size_t)take * frame_bytes;
         if (fread(dst, 1, want, in) != want) {
@@ -542,6 +564,7 @@ extern "C" int b200flac_stream_write_file(b200flac_stream* s, const char* path, 
         }
         if (flags) to_signed_le(dst, (size_t)take * s->params.channels, sample_bytes, flags);
         l.fill += take;
+        md5_enqueue(s, l, MD5_PIECE);
         n_pcm_frames -= take;
         if (l.fill == cap) rc = submit_current(s);
     }
