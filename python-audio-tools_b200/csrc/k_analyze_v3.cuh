@@ -23,7 +23,8 @@
 
 #define V3_CH 8
 #define V3_SK(i) ((i) + (((i) >> 5) << 2))      // four words of skew per 32 samples
-#define V3_MAX_F 7                               // finest partition order handled (<= 128 partitions; order 8 measured slower than k_analyze_v2)
+#define V3_MAX_F 7                               // finest partition order handled (<= 128 partitions; order 8 measured slower than k_analyze_v2,
+                                                 // with and without the exhaustive search: 96 kHz/24-bit -e R8 10.6 vs 7.2 ms per 5 minutes)
 #define V3_HEAP (2 << V3_MAX_F)
 
 // totals of one partition order of one model (written by whichever warp evaluated the level)
