@@ -277,3 +277,34 @@ def test_transcode_round_trip_through_both_engines(tmp_path, built):
     import b200flac
     info, got = b200flac.decode(open(path, "rb").read())
     assert got == pcm and info.channel_mask == 0x3
+
+
+def test_standalone_decoder_driver_matches_reference_driver(tmp_path, built):
+    """`b200flacdec file.flac > pcm` against `flacdec` (the compiled reference's driver,
+    src/decoders/flac.c:1340-1527): same PCM and exit status for good streams, same stderr line and exit
+    status for damaged ones (the reference additionally writes the frames before the damage)"""
+    import subprocess
+    exe = os.path.join(helpers.ROOT, "python-audio-tools_b200", "b200flacdec")
+    ref = os.path.join(helpers.ROOT, "oracle", "_ref", "flacdec")
+    pcm = helpers.synth_pcm(31, 2, 16, 4096 * 5 + 9)
+    flac, offs = helpers.oracle_encode(pcm, 44100, 2, 16, helpers.options(**LEVELS["8"]), want_offsets=True)
+    first = helpers.first_frame_offset(flac)
+    variants = {"good": flac, "crc16": _flip(flac, first + offs[2][0] + 50), "crc8": _flip(flac, first + offs[2][0] + 3),
+                "md5": _flip(flac, 8 + 18 + 9), "cut": flac[:first + offs[4][0] + 10], "notflac": b"OggS" + flac[4:]}
+    for name, data in variants.items():
+        path = os.path.join(str(tmp_path), name + ".flac")
+        open(path, "wb").write(data)
+        r = subprocess.run([exe, path], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if name == "good":
+            assert r.returncode == 0 and r.stdout == pcm and r.stderr == b""
+        else:
+            assert r.returncode == 1
+        if name == "md5":
+            assert r.stdout == pcm          # reported after the PCM, as in the reference
+        if helpers.have_ref():
+            q = subprocess.run([ref, path], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            assert (q.returncode, q.stderr) == (r.returncode, r.stderr), name
+            if name in ("good", "md5"):
+                assert q.stdout == r.stdout
+    r = subprocess.run([exe, os.path.join(str(tmp_path), "missing.flac")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and r.stderr.startswith(b"*** ") and b"No such file" in r.stderr
