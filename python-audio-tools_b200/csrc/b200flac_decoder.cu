@@ -216,9 +216,12 @@ struct DecBits {
         if (off < n_bytes + 32) w = *(const u32*)(base + off);
         return w;
     }
+    // keeps at least 32 valid bits in the window.  Every consumer takes at most `avail` bits, so one word
+    // always restores the invariant -- a plain `if`, not a loop (as a loop the compiler unrolled it into
+    // some fifty instructions of trip-count arithmetic per sample)
     __device__ __forceinline__ void refill()
     {
-        while (avail <= 32) {
+        if (avail < 32) {
             if (next >= n_bytes + 16) eof = true;
             buf |= (u64)__byte_perm(ahead, 0, 0x0123) << (32 - avail);
             avail += 32;
