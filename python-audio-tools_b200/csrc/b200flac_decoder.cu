@@ -637,6 +637,12 @@ static cudaError_t grow(T** p, size_t* cap, size_t bytes)
     return e;
 }
 
+#include <chrono>
+static double dec_now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // frames: the bytes from the first frame to the end of the file (host or device memory, see flags)
 static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, uint64_t n_bytes, int frames_on_device,
                        int device, uint8_t* pcm_out, int pcm_on_device, uint64_t pcm_capacity,
@@ -668,6 +674,7 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
     const u32 minb = info->min_block_size ? info->min_block_size : 16;
     u32 cap = (u32)std::min<u64>(total / minb + n_bytes / (1u << 16) + 4096, 0x7FFFFFFFu);
     u32 count = 0;
+    double t_d2h = 0.0;
     const u8* d_frames = nullptr;
     if (w.device != device) w.release();
     DCK(cudaSetDevice(device));
@@ -700,29 +707,32 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
     DCK(cudaEventRecord(w.ev[3]));
     cands.resize(count);
     DCK(cudaMemcpy(cands.data(), w.d_cands, (size_t)count * sizeof(bf_dec_cand), cudaMemcpyDeviceToHost));
+    t_d2h = dec_now();
 
     // ---- the reference's frame loop (flac.c:196-268, :1402-1476) over the decoded candidates ----
     {
-        // candidates in stream order: (position, index) packed in one 64-bit key (positions < 2^40, indices < 2^24;
-        // larger inputs fall back to an indirect sort)
-        std::vector<u32> order(count);
-        if (n_bytes < (1ull << 40) && count < (1u << 24)) {
-            std::vector<u64> key(count);
-            for (u32 i = 0; i < count; i++) key[i] = (cands[i].pos << 24) | i;
-            std::sort(key.begin(), key.end());
-            for (u32 i = 0; i < count; i++) order[i] = (u32)(key[i] & 0xFFFFFF);
-        } else {
-            for (u32 i = 0; i < count; i++) order[i] = i;
-            std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return cands[a].pos < cands[b].pos; });
+        // position -> candidate through an open-addressing hash table (no sort: the walk itself visits the
+        // frames in stream order; sorting 38,760 keys cost three times the rest of this block)
+        u32 bits = 4;
+        while ((1u << bits) < 2 * count) bits++;
+        const u32 mask = (1u << bits) - 1;
+        std::vector<u32> table((size_t)mask + 1, 0u);
+        auto slot_of = [&](u64 pos) { return (u32)((pos * 0x9E3779B97F4A7C15ull) >> (64 - bits)); };
+        for (u32 i = 0; i < count; i++) {
+            u32 h = slot_of(cands[i].pos);
+            while (table[h]) h = (h + 1) & mask;
+            table[h] = i + 1;
         }
+        emits.reserve(count); offs.reserve(count); lens.reserve(count);
         u64 pos = 0, done_frames = 0;
-        size_t cursor = 0; // the chain only moves forward
         while (done_frames < total) {
-            while (cursor < order.size() && cands[order[cursor]].pos < pos) cursor++;
+            u32 found = 0;
+            for (u32 h = slot_of(pos); table[h]; h = (h + 1) & mask)
+                if (cands[table[h] - 1].pos == pos) { found = table[h]; break; }
             u32 status;
             const bf_dec_cand* cd = nullptr;
-            if (cursor < order.size() && cands[order[cursor]].pos == pos) {
-                cd = &cands[order[cursor]];
+            if (found) {
+                cd = &cands[found - 1];
                 status = cd->status;
             } else if (frames_on_device) {
                 status = DS_INVALID_SYNC_CODE; // (the header bytes are not on the host to say more)
@@ -734,7 +744,7 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
             if (status == DS_OK && cd->block_size > total - done_frames) status = DS_MALFORMED;
             if (status != DS_OK) { rc = dfail(status == DS_EOF ? 2 : 1, ds_strerror(status)); goto done; }
             bf_dec_emit e;
-            e.pcm_frame = done_frames; e.cand = order[cursor]; e.n = cd->block_size;
+            e.pcm_frame = done_frames; e.cand = found - 1; e.n = cd->block_size;
             emits.push_back(e);
             offs.push_back(pos);
             lens.push_back(cd->block_size);
@@ -742,6 +752,7 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
             pos = cd->end;
         }
     }
+    if (getenv("B200FLAC_DEC_TIMING")) fprintf(stderr, "decode host: sort+walk %.3f ms (after the candidates' D2H)\n", (dec_now() - t_d2h) * 1e3);
     if (pcm_out) {
         u8* d_pcm = pcm_out;
         if (!pcm_on_device) { DCK(grow(&w.d_pcm, &w.cap_pcm, pcm_bytes + 64)); d_pcm = w.d_pcm; }
