@@ -350,6 +350,7 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
     // is a short predicated detour inside the sample loop instead.
     const u32 kbits = method ? 5u : 4u, kesc = method ? 31u : 15u, n_parts = 1u << po;
     u32 part = 0, left = 0, k = 0, escape = 0;
+#pragma unroll 4
     for (u32 i = order; i < n; i++) {
         while (left == 0) {
             left = part == 0 ? plen - order : plen;
