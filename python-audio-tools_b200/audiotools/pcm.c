@@ -65,7 +65,16 @@ static int FrameList_init(pcm_FrameList *self, PyObject *args, PyObject *kwds)
     self->samples = (int *)malloc(sizeof(int) * (n ? n : 1));
     if (!self->samples) { PyBuffer_Release(&data); PyErr_NoMemory(); return -1; }
     const uint8_t *p = (const uint8_t *)data.buf;
-    for (size_t i = 0; i < n; i++, p += bytes) {
+    const size_t n_all = n;
+    size_t first = 0;
+    if (bytes == 2 && !big_endian && is_signed) {
+        /* the common case (16-bit WAVE data), in a form the compiler vectorises */
+        int *restrict dst = self->samples;
+        for (size_t i = 0; i < n; i++) { int16_t v; memcpy(&v, p + 2 * i, 2); dst[i] = v; }
+        first = n;
+    }
+    p += first * bytes;
+    for (size_t i = first; i < n; i++, p += bytes) {
         uint32_t v = 0;
         for (unsigned b = 0; b < bytes; b++) v |= (uint32_t)p[big_endian ? (bytes - 1 - b) : b] << (8 * b);
         if (is_signed) {
@@ -75,10 +84,10 @@ static int FrameList_init(pcm_FrameList *self, PyObject *args, PyObject *kwds)
             self->samples[i] = (int)v - (1 << (bps - 1));
         }
     }
-    self->samples_length = (unsigned)n;
+    self->samples_length = (unsigned)n_all;
     self->channels = (unsigned)channels;
     self->bits_per_sample = (unsigned)bps;
-    self->frames = (unsigned)(n / (unsigned)channels);
+    self->frames = (unsigned)(n_all / (unsigned)channels);
     PyBuffer_Release(&data);
     return 0;
 }
@@ -104,6 +113,10 @@ static PyObject *FrameList_concat(pcm_FrameList *a, PyObject *bb)
 {
     if (!same_shape(a, bb)) return NULL;
     pcm_FrameList *b = (pcm_FrameList *)bb;
+    /* FrameLists never change after construction, so an empty operand needs no copy (BufferedPCMReader's
+       `buffer += frame` with an empty buffer, audiotools/__init__.py:2585-2590) */
+    if (a->frames == 0) { Py_INCREF(bb); return bb; }
+    if (b->frames == 0) { Py_INCREF(a); return (PyObject *)a; }
     pcm_FrameList *r = framelist_alloc(a->frames + b->frames, a->channels, a->bits_per_sample);
     if (!r) return NULL;
     memcpy(r->samples, a->samples, sizeof(int) * a->samples_length);
@@ -117,6 +130,13 @@ static PyObject *FrameList_split(pcm_FrameList *self, PyObject *args)
     if (!PyArg_ParseTuple(args, "i", &n)) return NULL;
     if (n < 0) { PyErr_SetString(PyExc_IndexError, "split point must be positive"); return NULL; }
     unsigned head = (unsigned)n < self->frames ? (unsigned)n : self->frames;
+    if (head == self->frames || head == 0) {
+        /* one side is the whole list (immutable: shared, not copied), the other is empty */
+        pcm_FrameList *e = framelist_alloc(0, self->channels, self->bits_per_sample);
+        if (!e) return NULL;
+        Py_INCREF(self);
+        return head ? Py_BuildValue("(NN)", self, e) : Py_BuildValue("(NN)", e, self);
+    }
     pcm_FrameList *h = framelist_alloc(head, self->channels, self->bits_per_sample);
     if (!h) return NULL;
     pcm_FrameList *t = framelist_alloc(self->frames - head, self->channels, self->bits_per_sample);

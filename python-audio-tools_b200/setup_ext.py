@@ -12,11 +12,11 @@ setup(
     version="0.1",
     packages=["audiotools"],
     ext_modules=[
-        Extension("audiotools.pcm", ["audiotools/pcm.c"], extra_compile_args=["-O2", "-std=c11"]),
+        Extension("audiotools.pcm", ["audiotools/pcm.c"], extra_compile_args=["-O3", "-std=c11"]),
         Extension("audiotools.encoders", ["audiotools/encoders.c"],
                   include_dirs=[os.path.join(HERE, "..", "include")],
                   library_dirs=[HERE], libraries=["b200flac"],
                   runtime_library_dirs=["$ORIGIN/.."],
-                  extra_compile_args=["-O2", "-std=c11"]),
+                  extra_compile_args=["-O3", "-std=c11"]),
     ],
 )
