@@ -44,7 +44,7 @@ enum {
     DS_INVALID_SAMPLE_RATE, DS_INVALID_FRAME_CRC, DS_SAMPLE_RATE_MISMATCH, DS_CHANNEL_COUNT_MISMATCH,
     DS_BITS_PER_SAMPLE_MISMATCH, DS_MAXIMUM_BLOCK_SIZE_EXCEEDED, DS_INVALID_CODING_METHOD,
     DS_INVALID_FIXED_ORDER, DS_INVALID_SUBFRAME_TYPE,
-    DS_EOF = 32, DS_FRAME_CRC16 = 33, DS_MALFORMED = 34
+    DS_EOF = 32, DS_FRAME_CRC16 = 33, DS_MALFORMED = 34, DS_UNDEFINED = 35
 };
 
 static const char* ds_strerror(u32 s)
@@ -65,7 +65,13 @@ static const char* ds_strerror(u32 s)
     case DS_INVALID_SUBFRAME_TYPE: return "invalid subframe type";
     case DS_EOF: return "EOF reading frame";                      // flac.c:262, :1470
     case DS_FRAME_CRC16: return "invalid checksum in frame";      // flac.c:252, :1459
-    case DS_MALFORMED: return "malformed frame (residual count does not match the block size)";
+    // a residual block whose partitions do not add up to the block size: the reference reads what the
+    // partition arithmetic says (flac.c:1157-1163), indexes past the residuals it got, and then fails the
+    // frame's CRC-16 -- that is the error its caller sees
+    case DS_MALFORMED: return "invalid checksum in frame";
+    // more wasted bits than bits per sample: the reference's read count underflows (flac.c:872-873); no defined
+    // behaviour to follow, reported like any other damaged frame
+    case DS_UNDEFINED: return "invalid checksum in frame";
     default: return "Error";
     }
 }
@@ -289,7 +295,7 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
     u32 wasted = 0;
     if (rd.read(1)) wasted = rd.unary1() + 1;
     *wasted_out = wasted;
-    if (wasted >= bps) return DS_MALFORMED;
+    if (wasted >= bps) return DS_UNDEFINED;
     bps -= wasted;
     if (rd.eof) return DS_EOF;
 
@@ -306,19 +312,23 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
     int q[B200FLAC_MAX_LPC_ORDER];
     const bool fixed = (type & 0x38) == 0x08;
     if (fixed) {
+        // orders 5..7 are only rejected after the warm-up samples and the residual have been read
+        // (the switch of flac.c:1030-1062), so an error inside the residual comes first
         order = type & 7;
-        if (order > 4) return DS_INVALID_FIXED_ORDER;
     } else if (type & 0x20) {
         order = (type & 0x1F) + 1;
     } else {
         return DS_INVALID_SUBFRAME_TYPE;
     }
-    if (order > n) return DS_MALFORMED;
-    for (u32 i = 0; i < order; i++) row[i] = rd.read_signed(bps); // warm-up samples
+    for (u32 i = 0; i < order; i++) { // warm-up samples (read even when the block is shorter than the order)
+        const int v = rd.read_signed(bps);
+        if (i < n) row[i] = v;
+    }
 #pragma unroll
     for (int j = 0; j < B200FLAC_MAX_LPC_ORDER; j++) q[j] = 0;
     if (fixed) {
-        const int c1[5] = {0, 1, 2, 3, 4}, c2[5] = {0, 0, -1, -3, -6}, c3[5] = {0, 0, 0, 1, 4}, c4[5] = {0, 0, 0, 0, -1};
+        const int c1[8] = {0, 1, 2, 3, 4, 0, 0, 0}, c2[8] = {0, 0, -1, -3, -6, 0, 0, 0}, c3[8] = {0, 0, 0, 1, 4, 0, 0, 0},
+                  c4[8] = {0, 0, 0, 0, -1, 0, 0, 0};
         q[0] = c1[order]; q[1] = c2[order]; q[2] = c3[order]; q[3] = c4[order];
     } else {
         const u32 precision = rd.read(4) + 1;
@@ -332,9 +342,27 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
     if (method > 1) return DS_INVALID_CODING_METHOD;
     const u32 po = rd.read(4);
     const u32 plen = n >> po;
-    // otherwise the reference appends a residual count that is not n - order and then indexes past it
-    if (((u64)plen << po) != n || plen < order) return DS_MALFORMED;
     if (rd.eof) return DS_EOF;
+    const u32 kbits = method ? 5u : 4u, kesc = method ? 31u : 15u, n_parts = 1u << po;
+    if (((u64)plen << po) != n || plen < order) {
+        // The partitions do not add up to n - order residuals.  The reference reads what its partition
+        // arithmetic says (flac.c:1150-1206: max(plen - order, 0) in the first partition, plen in the others),
+        // then builds samples from residuals it never read; what its caller sees is decided by the reads
+        // alone -- EOF, a later subframe's error, or the frame's CRC-16 -- so the same bits are consumed here,
+        // the values dropped, and the frame is marked for the CRC verdict.
+        for (u32 part = 0; part < n_parts; part++) {
+            u32 count = part == 0 ? (plen > order ? plen - order : 0u) : plen;
+            const u32 k = rd.read(kbits);
+            const u32 escape = (k == kesc) ? rd.read(5) : 0u;
+            for (; count && !rd.eof; count--) {
+                if (!escape) { rd.unary1(); rd.read(k); }
+                else rd.read(escape);
+            }
+            if (rd.eof) return DS_EOF;
+        }
+        if (fixed && order > 4) return DS_INVALID_FIXED_ORDER;
+        return DS_MALFORMED;
+    }
 
     // recent samples, most recent first, for orders up to DEC_FAST_ORDER; longer predictors read the row
     int h[DEC_FAST_ORDER], qf[DEC_FAST_ORDER];
@@ -348,7 +376,6 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
     // different frames, and nested partition/sample loops would leave lanes with different partition
     // orders waiting for each other at every partition boundary.  The partition header (flac.c:1157-1186)
     // is a short predicated detour inside the sample loop instead.
-    const u32 kbits = method ? 5u : 4u, kesc = method ? 31u : 15u, n_parts = 1u << po;
     u32 part = 0, left = 0, k = 0, escape = 0;
 #pragma unroll 4
     for (u32 i = order; i < n; i++) {
@@ -386,6 +413,7 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
         if (rd.read(kbits) == kesc) rd.read(5);
     }
     if (rd.eof) return DS_EOF;
+    if (fixed && order > 4) return DS_INVALID_FIXED_ORDER;
     return DS_OK;
 }
 
@@ -450,6 +478,7 @@ __global__ void __launch_bounds__(32) k_dec_frames(const u8* __restrict__ data, 
     DecBits rd;
     if (status == DS_OK) {
         rd.init(data, n_bytes, cd.pos + h.length);
+        bool malformed = false; // a subframe whose residual partitions do not add up: verdict by the CRC-16 below
         for (u32 ch = 0; ch < S.channels && status == DS_OK; ch++) {
             // flacdec_subframe_bits_per_sample, flac.c:952-965
             const bool side = (h.assignment == 8 && ch == 1) || (h.assignment == 9 && ch == 0) || (h.assignment == 10 && ch == 1);
@@ -457,8 +486,12 @@ __global__ void __launch_bounds__(32) k_dec_frames(const u8* __restrict__ data, 
             status = dec_subframe(rd, h.block_size, S.bits_per_sample + (side ? 1u : 0u),
                                   scratch + ((u64)c * S.channels + ch) * row_stride, &w);
             cd.wasted[ch] = (u8)w;
+            if (status == DS_MALFORMED) { malformed = true; status = DS_OK; }
         }
+        if (status == DS_OK && malformed) status = DS_MALFORMED + 1000; // resolved after the CRC-16
     }
+    const bool soft = status == DS_MALFORMED + 1000;
+    if (soft) status = DS_OK;
     if (status == DS_OK) {
         if (rd.eof) status = DS_EOF;
         const u64 end = (rd.bits_consumed() + 7) / 8 + 2; // byte_align, then the CRC-16 (flac.c:247-249)
@@ -466,6 +499,7 @@ __global__ void __launch_bounds__(32) k_dec_frames(const u8* __restrict__ data, 
         if (status == DS_OK) {
             cd.end = end;
             if (dec_crc16(data, cd.pos, end - cd.pos, tab) != 0) status = DS_FRAME_CRC16;
+            else if (soft) status = DS_MALFORMED;
         }
     }
     cd.status = status;
