@@ -71,3 +71,20 @@ def test_decode_without_gpu_fails_loudly(built):
     assert (d.sample_rate, d.channels, d.bits_per_sample, d.channel_mask) == (44100, 2, 16, 0x3)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         d.read(4096)
+
+
+def test_reference_fixture_streaminfo(built):
+    """STREAMINFO of the reference's fixtures: metadata blocks in any order, channel masks by channel count
+    (test/flac-nomask*.flac, flac-disordered.flac), an ID3 prefix is not FLAC for the C entry points"""
+    import os
+    import b200flac
+    d = os.path.join(helpers.ROOT, "tests", "golden", "flac")
+    got = {}
+    for name in ("flac-allframes.flac", "flac-disordered.flac", "flac-nomask1.flac", "flac-nomask3.flac", "1h.flac"):
+        i = b200flac.read_streaminfo(open(os.path.join(d, name), "rb").read())
+        got[name] = (i.sample_rate, i.channels, i.bits_per_sample, i.total_pcm_frames, i.max_block_size, i.channel_mask)
+    assert got == {"flac-allframes.flac": (44100, 1, 16, 80, 4096, 0x4), "flac-disordered.flac": (44100, 2, 16, 304844, 4096, 0x3),
+                   "flac-nomask1.flac": (44100, 6, 16, 44100, 4096, 0x3F), "flac-nomask3.flac": (44100, 2, 24, 44100, 4096, 0x3),
+                   "1h.flac": (8000, 2, 16, 28800000, 32768, 0x3)}
+    with pytest.raises(ValueError, match="not a FLAC file"):
+        b200flac.read_streaminfo(open(os.path.join(d, "flac-id3.flac"), "rb").read())

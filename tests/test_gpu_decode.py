@@ -357,3 +357,24 @@ def test_decode_fuzz_same_verdict_and_message_as_the_reference(seed, tmp_path, b
             want = r.stderr.decode().strip().replace("*** Error: ", "").replace("*** ", "")
             want = {"I/O Error reading frame": "EOF reading frame"}.get(want, want)
             assert mine == want, (seed, case, kind)
+
+
+def _decode_golden():
+    import json
+    with open(os.path.join(helpers.ROOT, "tests", "golden", "decode_golden.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("name", sorted(_decode_golden()))
+def test_decode_reference_fixtures(name, built):
+    """the reference's own FLAC fixtures (test/*.flac: written by other encoders -- libFLAC tones, every
+    subframe type, metadata in unusual order, ID3 prefix, blank MD5, 32768-sample blocks) through the
+    standalone driver: exit status, stderr and PCM equal what the compiled reference decoder produced
+    (tests/golden/make_decode_golden.py)"""
+    import subprocess
+    want = _decode_golden()[name]
+    exe = os.path.join(helpers.ROOT, "python-audio-tools_b200", "b200flacdec")
+    r = subprocess.run([exe, os.path.join(helpers.ROOT, "tests", "golden", "flac", name)], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE)
+    assert (r.returncode, r.stderr.decode()) == (want["rc"], want["stderr"])
+    assert len(r.stdout) == want["pcm_bytes"] and hashlib.sha256(r.stdout).hexdigest() == want["pcm_sha256"]
