@@ -21,6 +21,19 @@ def _native_finalize(filename, offsets, seekpoint_interval, channel_mask):
     encoders.finalize_flac_metadata(filename, offsets, seekpoint_interval, channel_mask)
 
 
+def skip_id3v2_comment(f):
+    """seeks past the ID3v2 tags at the start of the stream, if any; returns the bytes skipped
+    (audiotools/id3.py:264-311)"""
+    start = f.tell()
+    head = f.read(10)
+    if len(head) < 10 or head[0:3] != b"ID3" or head[3] not in (2, 3, 4) or any(b & 0x80 for b in head[6:10]):
+        f.seek(start)
+        return 0
+    tag_size = (head[6] << 21) | (head[7] << 14) | (head[8] << 7) | head[9]     # decode_syncsafe32, id3.py:81-104
+    f.seek(tag_size, 1)
+    return 10 + tag_size + skip_id3v2_comment(f)
+
+
 class FlacMetaData(object):
     """ordered list of (block_id, payload) metadata blocks"""
 
@@ -85,20 +98,45 @@ class FlacAudio(object):
     def __init__(self, filename):
         from . import InvalidFLAC
         self.filename = filename
+        self.__samplerate__ = 0
+        self.__channels__ = 0
+        self.__bitspersample__ = 0
+        self.__total_frames__ = 0
         self.__stream_offset__ = 0
-        with open(filename, "rb") as f:
-            if f.read(4) != b"fLaC":
-                raise InvalidFLAC("not a FLAC file")
-            hdr = f.read(4)
-            if len(hdr) < 4 or (hdr[0] & 0x7F) != BLOCK_STREAMINFO:
-                raise InvalidFLAC("STREAMINFO not first metadata block")
-            si = f.read(34)
-        v = int.from_bytes(si[10:18], "big")
-        self.__samplerate__ = v >> 44
-        self.__channels__ = ((v >> 41) & 7) + 1
-        self.__bitspersample__ = ((v >> 36) & 31) + 1
-        self.__total_frames__ = v & ((1 << 36) - 1)
-        self.__md5__ = bytes(si[18:34])
+        self.__md5__ = bytes(16)
+        try:
+            self.__read_streaminfo__()
+        except IOError as msg:
+            raise InvalidFLAC(str(msg))
+
+    def __read_streaminfo__(self):
+        """flac.py:2420-2462: skips ID3v2 tags in front of the stream (__stream_offset__), then walks the
+        metadata blocks until STREAMINFO -- which need not be the first one"""
+        from . import InvalidFLAC
+        with open(self.filename, "rb") as f:
+            self.__stream_offset__ = skip_id3v2_comment(f)
+            f.read(4)
+            while True:
+                hdr = f.read(4)
+                if len(hdr) < 4:
+                    raise IOError("I/O error reading stream")
+                stop, header_type, length = hdr[0] >> 7, hdr[0] & 0x7F, int.from_bytes(hdr[1:4], "big")
+                if header_type > 6:
+                    raise InvalidFLAC("invalid metadata block type")       # ERR_FLAC_INVALID_BLOCK, text.py:576
+                if header_type == BLOCK_STREAMINFO:
+                    si = f.read(34)
+                    if len(si) < 34:
+                        raise IOError("I/O error reading stream")
+                    v = int.from_bytes(si[10:18], "big")
+                    self.__samplerate__ = v >> 44
+                    self.__channels__ = ((v >> 41) & 7) + 1
+                    self.__bitspersample__ = ((v >> 36) & 31) + 1
+                    self.__total_frames__ = v & ((1 << 36) - 1)
+                    self.__md5__ = bytes(si[18:34])
+                    break
+                f.seek(length, 1)
+                if stop:
+                    break
 
     def sample_rate(self):
         return self.__samplerate__

@@ -378,3 +378,23 @@ def test_decode_reference_fixtures(name, built):
                        stderr=subprocess.PIPE)
     assert (r.returncode, r.stderr.decode()) == (want["rc"], want["stderr"])
     assert len(r.stdout) == want["pcm_bytes"] and hashlib.sha256(r.stdout).hexdigest() == want["pcm_sha256"]
+
+
+@pytest.mark.parametrize("name", ["flac-id3.flac", "flac-id3-2.flac", "flac-disordered.flac"])
+def test_flacaudio_reads_id3_prefixed_and_disordered_fixtures(name, built):
+    """FlacAudio skips ID3v2 tags in front of the stream (flac.py:2420-2462, id3.py:264-311) and finds a
+    STREAMINFO that is not the first block; to_pcm() then decodes from the stream offset, and the decoded
+    PCM hashes to the STREAMINFO MD5"""
+    import audiotools
+    a = audiotools.FlacAudio(os.path.join(helpers.ROOT, "tests", "golden", "flac", name))
+    d = a.to_pcm()
+    assert (d.sample_rate, d.channels, d.bits_per_sample) == (a.sample_rate(), a.channels(), a.bits_per_sample())
+    h, frames = hashlib.md5(), 0
+    while True:
+        f = d.read(4096)
+        if f.frames == 0:
+            break
+        frames += f.frames
+        h.update(f.to_bytes(False, True))
+    assert frames == a.total_frames() and h.digest() == a.__md5__ and a.__md5__ != bytes(16)
+    d.close()
