@@ -279,6 +279,24 @@ struct DecBits {
             refill();
         }
     }
+    // one Rice code, (unary << k) | k low bits (flac.c:1190-1193).  The window always holds at least 32
+    // valid bits here, and nearly every code fits in them: then the zeros, the stop bit and the low bits
+    // come out of ONE 32-bit word with one consume and one refill; longer codes take the two general reads
+    __device__ __forceinline__ u32 rice(u32 k)
+    {
+        const u32 top = (u32)(buf >> 32);
+        const u32 z = (u32)__clz((int)top);
+        const u32 len = z + 1 + k;
+        if (len <= 32) {
+            const u32 low = k ? (((top << z) << 1) >> (32 - k)) : 0u;
+            buf <<= len;
+            avail -= (int)len;
+            refill();
+            return (z << k) | low;
+        }
+        const u32 msb = unary1();
+        return (msb << k) | read(k);
+    }
     __device__ __forceinline__ u64 bits_consumed() const { return next * 8 - (u64)avail; }
 };
 
@@ -388,9 +406,7 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
         left--;
         int r;
         if (!escape) {
-            const u32 msb = rd.unary1();
-            const u32 lsb = rd.read(k);
-            const u32 v = (msb << k) | lsb;
+            const u32 v = rd.rice(k);
             r = (int)(v >> 1) ^ -(int)(v & 1);
         } else {
             r = rd.read_signed(escape);
