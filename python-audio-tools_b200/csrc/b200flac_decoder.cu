@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/b200flac.h"
@@ -389,42 +390,50 @@ __device__ u32 dec_subframe(DecBits& rd, u32 n, u32 bps, int* __restrict__ row, 
         qf[j] = q[j];
         h[j] = ((u32)j < order) ? row[order - 1 - j] : 0;
     }
-    const bool fast = order <= DEC_FAST_ORDER;
     // ONE loop over the samples of the subframe, whatever the partition order: the lanes of a warp decode
     // different frames, and nested partition/sample loops would leave lanes with different partition
     // orders waiting for each other at every partition boundary.  The partition header (flac.c:1157-1186)
     // is a short predicated detour inside the sample loop instead.
+    // The loop exists twice, chosen once per subframe: predictors of up to DEC_FAST_ORDER taps run from the
+    // register history, longer ones from the row.  After the end of the data the reader hands out zeros and
+    // every loop here is bounded by the block size, so EOF is only looked at when the subframe is done.
     u32 part = 0, left = 0, k = 0, escape = 0;
+    auto samples = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll 4
-    for (u32 i = order; i < n; i++) {
-        while (left == 0) {
-            left = part == 0 ? plen - order : plen;
-            part++;
-            k = rd.read(kbits);
-            escape = (k == kesc) ? rd.read(5) : 0u;
-        }
-        left--;
-        int r;
-        if (!escape) {
-            const u32 v = rd.rice(k);
-            r = (int)(v >> 1) ^ -(int)(v & 1);
-        } else {
-            r = rd.read_signed(escape);
-        }
-        long long acc = 0;
-        if (fast) {
+        for (u32 i = order; i < n; i++) {
+            while (left == 0) {
+                left = part == 0 ? plen - order : plen;
+                part++;
+                k = rd.read(kbits);
+                escape = (k == kesc) ? rd.read(5) : 0u;
+            }
+            left--;
+            int r;
+            if (!escape) {
+                const u32 v = rd.rice(k);
+                r = (int)(v >> 1) ^ -(int)(v & 1);
+            } else {
+                r = rd.read_signed(escape);
+            }
+            long long acc = 0;
+            if (FAST) {
 #pragma unroll
-            for (int j = 0; j < DEC_FAST_ORDER; j++) acc += (long long)qf[j] * (long long)h[j];
-        } else {
-            for (u32 j = 0; j < order; j++) acc += (long long)q[j] * (long long)row[i - 1 - j];
-        }
-        const int s = (int)(acc >> shift) + r;
-        row[i] = s;
+                for (int j = 0; j < DEC_FAST_ORDER; j++) acc += (long long)qf[j] * (long long)h[j];
+            } else {
+                for (u32 j = 0; j < order; j++) acc += (long long)q[j] * (long long)row[i - 1 - j];
+            }
+            const int s = (int)(acc >> shift) + r;
+            row[i] = s;
+            if (FAST) {
 #pragma unroll
-        for (int j = DEC_FAST_ORDER - 1; j > 0; j--) h[j] = h[j - 1];
-        h[0] = s;
-        if (rd.eof) return DS_EOF;
-    }
+                for (int j = DEC_FAST_ORDER - 1; j > 0; j--) h[j] = h[j - 1];
+                h[0] = s;
+            }
+        }
+    };
+    if (order <= DEC_FAST_ORDER) samples(std::true_type());
+    else samples(std::false_type());
     for (; part < n_parts; part++) { // headers of partitions without residuals (order == partition length)
         if (rd.read(kbits) == kesc) rd.read(5);
     }
