@@ -234,6 +234,9 @@ struct DecBits {
             avail += 32;
             next += 4;
             ahead = word(next);
+            // each lane streams through its own frame once: at every 128-byte line it asks for the line two
+            // ahead, so that the word fetched above comes from cache rather than from DRAM
+            if ((next & 127) == 0 && next + 512 < n_bytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + next + 256));
         }
     }
     __device__ __forceinline__ void init(const u8* b, u64 n, u64 pos)
