@@ -311,6 +311,11 @@ int b200flac_decode_device(const b200flac_stream_info *info, const void *d_frame
 /* flacdec without output: decode everything, check every CRC-16 and the STREAMINFO MD5 */
 int b200flac_verify_file(const char *flac_filename, int device);
 
+/* FLAC file -> RIFF WAVE file in one call: WaveAudio.from_pcm(wave, FlacAudio(flac).to_pcm())
+ * (audiotools/wav.py:357-418 wave_header, :660-729 from_pcm), MD5 and every frame CRC checked on the way.
+ * Return codes as for b200flac_decode_memory; "total size too large for wave file" is a ValueError (1). */
+int b200flac_decode_to_wave(const char *flac_filename, const char *wave_filename, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,8 @@
 Reference: audiotools/wav.py of widgital/python-audio-tools (Python 2 only):
   parse_fmt      wav.py:288-354
   WaveReader     wav.py:421-553
-  WaveAudio      wav.py:580-757 (only what `WaveAudio(filename).to_pcm()` needs)
+  wave_header    wav.py:357-418
+  WaveAudio      wav.py:580-757 (what `WaveAudio(filename).to_pcm()` and `WaveAudio.from_pcm` need)
 
 WaveReader is the reference's PCMReader, method for method, so any consumer can call read() as
 before.  In addition it says where its PCM lies in the file (`b200_file_span`), which lets
@@ -51,6 +52,26 @@ def parse_fmt(f):
         return (channels, sample_rate, bits_per_sample, channel_mask)
     else:
         raise ValueError("unsupported WAVE compression")
+
+
+def wave_header(sample_rate, channels, channel_mask, bits_per_sample, total_pcm_frames):
+    """everything before a RIFF WAVE's PCM data (wav.py:357-418): a plain `fmt ` chunk for up to 2 channels at
+    up to 16 bits, WAVEFORMATEXTENSIBLE otherwise; ValueError when the file would pass 4 GB"""
+    avg_bytes_per_second = sample_rate * channels * (bits_per_sample // 8)
+    block_align = channels * (bits_per_sample // 8)
+    if (channels <= 2) and (bits_per_sample <= 16):
+        fmt = struct.pack("<HHIIHH", 1, channels, sample_rate, avg_bytes_per_second, block_align, bits_per_sample)
+    else:
+        if channel_mask == 0:
+            channel_mask = _MASK_BY_CHANNELS.get(channels, 0)
+        fmt = struct.pack("<HHIIHH", 0xFFFE, channels, sample_rate, avg_bytes_per_second, block_align, bits_per_sample) + \
+            struct.pack("<HHI", 22, bits_per_sample, int(channel_mask)) + PCM_SUB_FORMAT
+    data_size = (bits_per_sample // 8) * channels * total_pcm_frames
+    total_size = 4 + 8 + len(fmt) + 8 + data_size + (data_size % 2)
+    if total_size >= 2 ** 32:
+        raise ValueError("total size too large for wave file")
+    return (b"RIFF" + struct.pack("<I", total_size) + b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt +
+            b"data" + struct.pack("<I", data_size))
 
 
 class WaveReader(object):
@@ -167,6 +188,54 @@ class WaveAudio(object):
     def to_pcm(self):
         """returns a PCMReader object containing the track's PCM data (wav.py:652-657)"""
         return WaveReader(self.filename)
+
+    @classmethod
+    def from_pcm(cls, filename, pcmreader, compression=None, total_pcm_frames=None):
+        """writes a new RIFF WAVE file from pcmreader's data (wav.py:660-729), the reference's quirk included:
+        the pad byte after the data chunk follows the parity of the PCM *frame* count"""
+        import os
+        from . import EncodingError, FRAMELIST_SIZE
+        try:
+            header = wave_header(pcmreader.sample_rate, pcmreader.channels, pcmreader.channel_mask,
+                                 pcmreader.bits_per_sample, total_pcm_frames if total_pcm_frames is not None else 0)
+        except ValueError as err:
+            raise EncodingError(str(err))
+        try:
+            f = open(filename, "wb")
+        except IOError as err:
+            raise EncodingError(str(err))
+        frames_written = 0
+        f.write(header)
+        try:
+            # transfer_framelist_data(counter, f.write, signed = bits_per_sample > 8, big_endian = False)
+            while True:
+                frame = pcmreader.read(FRAMELIST_SIZE)
+                if len(frame) == 0:
+                    break
+                frames_written += frame.frames
+                f.write(frame.to_bytes(False, pcmreader.bits_per_sample > 8))
+            pcmreader.close()
+        except (IOError, ValueError) as err:
+            f.close()
+            os.unlink(filename)
+            raise EncodingError(str(err))
+        except Exception:
+            f.close()
+            os.unlink(filename)
+            raise
+        if frames_written % 2:
+            f.write(b"\x00")
+        if total_pcm_frames is not None:
+            if frames_written != total_pcm_frames:
+                f.close()
+                os.unlink(filename)
+                raise EncodingError("total_pcm_frames mismatch")
+        else:
+            f.seek(0, 0)
+            f.write(wave_header(pcmreader.sample_rate, pcmreader.channels, pcmreader.channel_mask,
+                                pcmreader.bits_per_sample, frames_written))
+        f.close()
+        return WaveAudio(filename)
 
     def total_frames(self):
         return self.__total_frames__

@@ -131,6 +131,7 @@ def lib():
     L.b200flac_decode_device.argtypes = [C.POINTER(StreamInfo), vp, C.c_uint64, C.c_int, vp, C.c_uint64, u64p,
                                          C.POINTER(C.c_float)]
     L.b200flac_verify_file.argtypes = [C.c_char_p, C.c_int]
+    L.b200flac_decode_to_wave.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     _lib = L
     return L
 
@@ -433,3 +434,10 @@ def verify_file(path, device=0):
     if rc:
         _raise_decode(rc)
     return True
+
+
+def decode_to_wave(flac_path, wave_path, device=0):
+    """FLAC file -> RIFF WAVE file (b200flac_decode_to_wave)"""
+    rc = lib().b200flac_decode_to_wave(os.fsencode(flac_path), os.fsencode(wave_path), device)
+    if rc:
+        _raise_decode(rc)

@@ -901,3 +901,65 @@ extern "C" int b200flac_verify_file(const char* flac_filename, int device)
     std::vector<uint8_t> pcm((size_t)(info.total_pcm_frames * info.channels * (info.bits_per_sample / 8)) + 1);
     return b200flac_decode_memory(data.data(), n, device, pcm.data(), pcm.size(), nullptr, 1, nullptr, nullptr, nullptr, nullptr);
 }
+
+// FLAC file -> RIFF WAVE file: WaveAudio.from_pcm(wave, FlacAudio(flac).to_pcm()) in one call
+// (audiotools/wav.py:357-418 wave_header, :660-729 from_pcm): plain `fmt ` for up to 2 channels at up to
+// 16 bits, WAVEFORMATEXTENSIBLE with the stream's channel mask otherwise, 8-bit samples unsigned, and the
+// reference's pad byte, which follows the parity of the PCM frame count.
+extern "C" int b200flac_decode_to_wave(const char* flac_filename, const char* wave_filename, int device)
+{
+    if (!flac_filename || !wave_filename) return dfail(3, "filename is NULL");
+    FILE* f = fopen(flac_filename, "rb");
+    if (!f) {
+        char msg[400];
+        snprintf(msg, sizeof(msg), "cannot open \"%.300s\" for reading", flac_filename);
+        return dfail(2, msg);
+    }
+    fseeko(f, 0, SEEK_END);
+    const u64 n = (u64)ftello(f);
+    fseeko(f, 0, SEEK_SET);
+    std::vector<uint8_t> data(n + 1);
+    const size_t got = fread(data.data(), 1, n, f);
+    fclose(f);
+    if (got != n) return dfail(2, "read error");
+    b200flac_stream_info info;
+    int rc = b200flac_read_streaminfo(data.data(), n, &info);
+    if (rc) return rc;
+    const u32 B = info.bits_per_sample / 8, C = info.channels;
+    const u64 data_size = info.total_pcm_frames * C * B;
+    std::vector<uint8_t> fmt;
+    auto le = [&](u64 v, int bytes) { for (int i = 0; i < bytes; i++) fmt.push_back((uint8_t)(v >> (8 * i))); };
+    const bool plain = C <= 2 && info.bits_per_sample <= 16;
+    le(plain ? 1 : 0xFFFE, 2); le(C, 2); le(info.sample_rate, 4); le((u64)info.sample_rate * C * B, 4); le(C * B, 2);
+    le(info.bits_per_sample, 2);
+    if (!plain) {
+        static const uint8_t guid[16] = {0x01, 0x00, 0x00, 0x00, 0x00, 0x00, 0x10, 0x00, 0x80, 0x00, 0x00, 0xaa, 0x00, 0x38, 0x9b, 0x71};
+        static const u32 by_count[7] = {0, 0x4, 0x3, 0x7, 0x33, 0x37, 0x3F};
+        u32 mask = info.channel_mask;
+        if (mask == 0) mask = C <= 6 ? by_count[C] : 0;
+        le(22, 2); le(info.bits_per_sample, 2); le(mask, 4);
+        fmt.insert(fmt.end(), guid, guid + 16);
+    }
+    const u64 total_size = 4 + 8 + fmt.size() + 8 + data_size + (data_size % 2);
+    if (total_size >= (1ull << 32)) return dfail(1, "total size too large for wave file");
+    std::vector<uint8_t> pcm((size_t)data_size + 1);
+    rc = b200flac_decode_memory(data.data(), n, device, pcm.data(), data_size, nullptr, 1, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (B == 1) for (u64 i = 0; i < data_size; i++) pcm[i] ^= 0x80; // to_bytes(False, signed = bits_per_sample > 8)
+    FILE* o = fopen(wave_filename, "wb");
+    if (!o) {
+        char msg[400];
+        snprintf(msg, sizeof(msg), "cannot open \"%.300s\" for writing", wave_filename);
+        return dfail(2, msg);
+    }
+    std::vector<uint8_t> head;
+    auto put = [&](const void* p, size_t k) { head.insert(head.end(), (const uint8_t*)p, (const uint8_t*)p + k); };
+    auto put32 = [&](u64 v) { for (int i = 0; i < 4; i++) head.push_back((uint8_t)(v >> (8 * i))); };
+    put("RIFF", 4); put32(total_size); put("WAVE", 4); put("fmt ", 4); put32(fmt.size()); put(fmt.data(), fmt.size());
+    put("data", 4); put32(data_size);
+    bool ok = fwrite(head.data(), 1, head.size(), o) == head.size() && (data_size == 0 || fwrite(pcm.data(), 1, data_size, o) == data_size);
+    if (ok && (info.total_pcm_frames % 2)) ok = fputc(0, o) != EOF; // wav.py:707-709
+    if (fclose(o) != 0) ok = false;
+    if (!ok) { remove(wave_filename); return dfail(2, "write error"); }
+    return 0;
+}

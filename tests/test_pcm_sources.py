@@ -323,3 +323,61 @@ def test_truncated_wave_fails_like_the_reader(tmp_path, built, monkeypatch):
         with pytest.raises(at.EncodingError, match="premature end of data chunk"):
             at.FlacAudio.from_pcm(out, audiotools.wav.WaveReader(src), "8")
         assert not os.path.exists(out)
+
+
+# ------------------------------------------------------------------------------------------ WAVE output
+def test_wave_header_matches_reference_layout(built):
+    """wave_header (wav.py:357-418): plain fmt for <= 2 channels at <= 16 bits, WAVEFORMATEXTENSIBLE otherwise with
+    the default channel mask when none is given; parsed back by WaveReader's own fmt parser"""
+    import io
+    at = _at()
+    h = at.wav.wave_header(44100, 2, 0x3, 16, 1000)
+    assert h == (b"RIFF" + struct.pack("<I", 4 + 8 + 16 + 8 + 4000) + b"WAVE" + b"fmt " + struct.pack("<I", 16) +
+                 fmt_plain(2, 44100, 16) + b"data" + struct.pack("<I", 4000))
+    h = at.wav.wave_header(96000, 6, 0, 24, 7)
+    assert h[20:22] == b"\xfe\xff" and len(h) == 12 + 8 + 40 + 8
+    assert at.wav.parse_fmt(io.BytesIO(h[20:60])) == (6, 96000, 24, 0x3F)
+    assert struct.unpack("<I", h[4:8])[0] == 4 + 8 + 40 + 8 + 126 and struct.unpack("<I", h[64:68])[0] == 126
+    h = at.wav.wave_header(8000, 1, 0x4, 8, 3)           # odd data size: counted padded in the RIFF size
+    assert struct.unpack("<I", h[4:8])[0] == 4 + 8 + 16 + 8 + 3 + 1
+    assert at.wav.parse_fmt(io.BytesIO(at.wav.wave_header(44100, 2, 0x3, 24, 1)[20:60])) == (2, 44100, 24, 0x3)
+    with pytest.raises(ValueError, match="total size too large for wave file"):
+        at.wav.wave_header(44100, 2, 0x3, 16, 2 ** 30)
+
+
+def test_wave_from_pcm_writes_what_the_reader_reads(tmp_path, built):
+    """WaveAudio.from_pcm (wav.py:660-729) with and without total_pcm_frames; the pad byte follows the parity of
+    the frame count (the reference's rule); a wrong total removes the file"""
+    at = _at()
+    for bps, ch, n in ((16, 2, 1001), (8, 1, 333), (24, 3, 500)):
+        pcm = helpers.synth_pcm(6, ch, bps, n)
+        for total in (None, n):
+            path = os.path.join(str(tmp_path), "o%d_%s.wav" % (bps, total))
+            w = at.WaveAudio.from_pcm(path, at.PCMBytesReader(pcm, 44100, ch, 0, bps), total_pcm_frames=total)
+            assert (w.sample_rate(), w.channels(), w.bits_per_sample(), w.total_frames()) == (44100, ch, bps, n)
+            data = open(path, "rb").read()
+            head = at.wav.wave_header(44100, ch, 0, bps, n)
+            assert data[:len(head)] == head
+            assert data[len(head):len(head) + len(pcm)] == le_to_wave_data(pcm, bps)
+            assert len(data) == len(head) + len(pcm) + (n % 2)
+    with pytest.raises(at.EncodingError, match="total_pcm_frames mismatch"):
+        at.WaveAudio.from_pcm(os.path.join(str(tmp_path), "bad.wav"), at.PCMBytesReader(pcm, 44100, 3, 0, 24), total_pcm_frames=499)
+    assert not os.path.exists(os.path.join(str(tmp_path), "bad.wav"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rate,ch,bps,n", [(44100, 2, 16, 4096 * 4 + 33), (8000, 1, 8, 5001), (96000, 6, 24, 4608 * 3 + 10)])
+def test_flac_to_wave_c_call_equals_python_path(rate, ch, bps, n, tmp_path, built):
+    """b200flac_decode_to_wave == WaveAudio.from_pcm(wave, FlacAudio(flac).to_pcm()), byte for byte, and
+    WAVE -> FLAC -> WAVE returns the WAVE it started from"""
+    import b200flac
+    at = _at()
+    pcm = helpers.synth_pcm(44, ch, bps, n)
+    src = os.path.join(str(tmp_path), "src.wav")
+    at.WaveAudio.from_pcm(src, at.PCMBytesReader(pcm, rate, ch, 0, bps))
+    flac = os.path.join(str(tmp_path), "x.flac")
+    at.FlacAudio.from_pcm(flac, at.WaveAudio(src).to_pcm(), "8")
+    a, b = os.path.join(str(tmp_path), "a.wav"), os.path.join(str(tmp_path), "b.wav")
+    b200flac.decode_to_wave(flac, a)
+    at.WaveAudio.from_pcm(b, at.FlacAudio(flac).to_pcm())
+    assert open(a, "rb").read() == open(b, "rb").read() == open(src, "rb").read()
