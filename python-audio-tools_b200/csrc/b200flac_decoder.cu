@@ -572,6 +572,91 @@ __global__ void k_dec_emit(const bf_dec_cand* __restrict__ cands, const bf_dec_e
     }
 }
 
+// ---- the frame chain on the device ----------------------------------------------------------------------
+// first frame -> its end -> the frame that starts there -> ...: a linked list through the candidates.
+// Positions are looked up through a hash table, every candidate learns its predecessor, and pointer
+// jumping (log2 rounds) gives each candidate the root of its list, the PCM frames and the FLAC frames in
+// front of it.  The candidates whose root is the candidate at offset 0 are the stream.  Anything unusual
+// -- a damaged or missing frame on the way, two candidates ending at the same place, a chain that does
+// not add up to STREAMINFO's total -- is left to the host walk below, which also words the error.
+#define DC_NONE 0xFFFFFFFFu
+struct bf_dec_chain_result { u32 bad, n_emit; u64 covered; };
+
+__device__ __forceinline__ u32 dc_slot(u64 pos, u32 bits) { return (u32)((pos * 0x9E3779B97F4A7C15ull) >> (64 - bits)); }
+
+__global__ void k_chain_insert(const bf_dec_cand* __restrict__ cands, u32 count, u32* __restrict__ table, u32 bits)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const u32 mask = (1u << bits) - 1;
+    for (u32 h = dc_slot(cands[i].pos, bits);; h = (h + 1) & mask)
+        if (atomicCAS(&table[h], 0u, i + 1) == 0u) return;
+}
+
+__global__ void k_chain_link(const bf_dec_cand* __restrict__ cands, u32 count, const u32* __restrict__ table, u32 bits,
+                             u32* __restrict__ prev, bf_dec_chain_result* __restrict__ res)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count || cands[i].status != DS_OK) return;
+    const u32 mask = (1u << bits) - 1;
+    const u64 end = cands[i].end;
+    for (u32 h = dc_slot(end, bits); table[h]; h = (h + 1) & mask) {
+        const u32 j = table[h] - 1;
+        if (cands[j].pos == end) {
+            if (atomicCAS(&prev[j], DC_NONE, i) != DC_NONE) atomicOr(&res->bad, 1u); // two frames end here
+            return;
+        }
+    }
+}
+
+__global__ void k_chain_init(const bf_dec_cand* __restrict__ cands, u32 count, const u32* __restrict__ prev,
+                             u32* __restrict__ up, u64* __restrict__ psum, u32* __restrict__ pcnt)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const u32 p = prev[i];
+    up[i] = p == DC_NONE ? i : p;                       // a root points at itself
+    psum[i] = p == DC_NONE ? 0ull : (u64)cands[p].block_size;
+    pcnt[i] = p == DC_NONE ? 0u : 1u;
+}
+
+__global__ void k_chain_jump(u32 count, const u32* __restrict__ up0, const u64* __restrict__ psum0, const u32* __restrict__ pcnt0,
+                             u32* __restrict__ up1, u64* __restrict__ psum1, u32* __restrict__ pcnt1)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const u32 a = up0[i];
+    psum1[i] = psum0[i] + (a == i ? 0ull : psum0[a]);
+    pcnt1[i] = pcnt0[i] + (a == i ? 0u : pcnt0[a]);
+    up1[i] = up0[a];
+}
+
+__global__ void k_chain_emit_list(const bf_dec_cand* __restrict__ cands, u32 count, const u32* __restrict__ table, u32 bits,
+                                  const u32* __restrict__ up, const u64* __restrict__ psum, const u32* __restrict__ pcnt,
+                                  u64 total, bf_dec_emit* __restrict__ emits, u64* __restrict__ offs, u32* __restrict__ lens,
+                                  bf_dec_chain_result* __restrict__ res)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    // the head: the candidate at offset 0
+    u32 head = DC_NONE;
+    const u32 mask = (1u << bits) - 1;
+    for (u32 h = dc_slot(0, bits); table[h]; h = (h + 1) & mask)
+        if (cands[table[h] - 1].pos == 0) { head = table[h] - 1; break; }
+    if (head == DC_NONE) { if (i == 0) atomicOr(&res->bad, 2u); return; }
+    if (up[i] != head || psum[i] >= total) return;      // not part of the stream (or past its end)
+    const bf_dec_cand cd = cands[i];
+    if (cd.status != DS_OK || cd.block_size > total - psum[i]) { atomicOr(&res->bad, 4u); return; }
+    const u32 k = pcnt[i];
+    bf_dec_emit e;
+    e.pcm_frame = psum[i]; e.cand = i; e.n = cd.block_size;
+    emits[k] = e;
+    offs[k] = cd.pos;
+    lens[k] = cd.block_size;
+    atomicAdd(&res->n_emit, 1u);
+    atomicMax((unsigned long long*)&res->covered, (unsigned long long)(psum[i] + cd.block_size));
+}
+
 // ---- host ------------------------------------------------------------------------------------------
 static int dfail(int rc, const char* msg)
 {
@@ -667,14 +752,15 @@ struct DecWork {
     bf_dec_emit* d_emits = nullptr; size_t cap_emits = 0;
     int* d_scratch = nullptr;    size_t cap_scratch = 0;
     u8* d_pcm = nullptr;         size_t cap_pcm = 0;
+    u8* d_chain = nullptr;       size_t cap_chain = 0;
     u32* d_count = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void release()
     {
         if (device >= 0) cudaSetDevice(device);
-        cudaFree(d_data); cudaFree(d_cands); cudaFree(d_emits); cudaFree(d_count); cudaFree(d_scratch); cudaFree(d_pcm);
+        cudaFree(d_data); cudaFree(d_cands); cudaFree(d_emits); cudaFree(d_count); cudaFree(d_scratch); cudaFree(d_pcm); cudaFree(d_chain);
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
-        d_data = nullptr; d_cands = nullptr; d_emits = nullptr; d_count = nullptr; d_scratch = nullptr; d_pcm = nullptr;
+        d_data = nullptr; d_cands = nullptr; d_emits = nullptr; d_count = nullptr; d_scratch = nullptr; d_pcm = nullptr; d_chain = nullptr; cap_chain = 0;
         cap_data = cap_cands = cap_emits = cap_scratch = cap_pcm = 0;
         device = -1;
     }
@@ -738,6 +824,10 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
     u32 cap = (u32)std::min<u64>(total / minb + n_bytes / (1u << 16) + 4096, 0x7FFFFFFFu);
     u32 count = 0;
     double t_d2h = 0.0;
+    bool chained = false;
+    u32 n_emit = 0;
+    u64* d_offs = nullptr;
+    u32* d_lens = nullptr;
     const u8* d_frames = nullptr;
     if (w.device != device) w.release();
     DCK(cudaSetDevice(device));
@@ -768,11 +858,45 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
     k_dec_frames<<<(count + 31) / 32, 32>>>(d_frames, n_bytes, S, w.d_cands, count, w.d_scratch, row_stride);
     DCK(cudaGetLastError());
     DCK(cudaEventRecord(w.ev[3]));
+    // ---- the chain on the device (the usual case) ----
+    if (!getenv("B200FLAC_DEC_HOST_CHAIN") && count < (1u << 30)) {
+        u32 bits = 4;
+        while ((1u << bits) < 2 * count) bits++;
+        const size_t T = (size_t)1 << bits, n8 = ((size_t)count + 1) & ~(size_t)1;
+        // u64 arrays first: psum0, psum1, offs; then u32: lens, prev, up0, up1, pcnt0, pcnt1, table; then the result
+        const size_t bytes = 3 * n8 * 8 + 6 * n8 * 4 + T * 4 + 64;
+        DCK(grow(&w.d_chain, &w.cap_chain, bytes));
+        u64* psum0 = (u64*)w.d_chain; u64* psum1 = psum0 + n8; d_offs = psum1 + n8;
+        d_lens = (u32*)(d_offs + n8);
+        u32* prev = d_lens + n8; u32* up0 = prev + n8; u32* up1 = up0 + n8; u32* pcnt0 = up1 + n8; u32* pcnt1 = pcnt0 + n8;
+        u32* table = pcnt1 + n8;
+        bf_dec_chain_result* d_res = (bf_dec_chain_result*)(table + T);
+        DCK(grow(&w.d_emits, &w.cap_emits, (size_t)count * sizeof(bf_dec_emit)));
+        DCK(cudaMemsetAsync(table, 0, T * 4 + 64));
+        DCK(cudaMemsetAsync(prev, 0xFF, n8 * 4));
+        const u32 g = (count + 255) / 256;
+        k_chain_insert<<<g, 256>>>(w.d_cands, count, table, bits);
+        k_chain_link<<<g, 256>>>(w.d_cands, count, table, bits, prev, d_res);
+        k_chain_init<<<g, 256>>>(w.d_cands, count, prev, up0, psum0, pcnt0);
+        u32 rounds = 1;
+        while ((1u << rounds) < count) rounds++;
+        for (u32 r = 0; r < rounds; r++) {
+            k_chain_jump<<<g, 256>>>(count, up0, psum0, pcnt0, up1, psum1, pcnt1);
+            std::swap(up0, up1); std::swap(psum0, psum1); std::swap(pcnt0, pcnt1);
+        }
+        k_chain_emit_list<<<g, 256>>>(w.d_cands, count, table, bits, up0, psum0, pcnt0, total, w.d_emits, d_offs, d_lens, d_res);
+        DCK(cudaGetLastError());
+        bf_dec_chain_result res;
+        DCK(cudaMemcpy(&res, d_res, sizeof(res), cudaMemcpyDeviceToHost));
+        if (res.bad == 0 && res.covered == total && res.n_emit > 0) { chained = true; n_emit = res.n_emit; }
+    }
+    if (!chained) {
     cands.resize(count);
     DCK(cudaMemcpy(cands.data(), w.d_cands, (size_t)count * sizeof(bf_dec_cand), cudaMemcpyDeviceToHost));
     t_d2h = dec_now();
 
-    // ---- the reference's frame loop (flac.c:196-268, :1402-1476) over the decoded candidates ----
+    // ---- the reference's frame loop (flac.c:196-268, :1402-1476) over the decoded candidates: the same walk on
+    // the host, for streams the device chain does not vouch for -- it finds and words the error ----
     {
         // position -> candidate through an open-addressing hash table (no sort: the walk itself visits the
         // frames in stream order; sorting 38,760 keys cost three times the rest of this block)
@@ -815,13 +939,19 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
             pos = cd->end;
         }
     }
-    if (getenv("B200FLAC_DEC_TIMING")) fprintf(stderr, "decode host: sort+walk %.3f ms (after the candidates' D2H)\n", (dec_now() - t_d2h) * 1e3);
+    if (getenv("B200FLAC_DEC_TIMING")) fprintf(stderr, "decode host: walk %.3f ms (after the candidates' D2H)\n", (dec_now() - t_d2h) * 1e3);
+    n_emit = (u32)emits.size();
+    DCK(grow(&w.d_emits, &w.cap_emits, emits.size() * sizeof(bf_dec_emit)));
+    DCK(cudaMemcpy(w.d_emits, emits.data(), emits.size() * sizeof(bf_dec_emit), cudaMemcpyHostToDevice));
+    } else if (frame_offsets || frame_pcm_frames) {
+        offs.resize(n_emit); lens.resize(n_emit);
+        DCK(cudaMemcpy(offs.data(), d_offs, (size_t)n_emit * sizeof(u64), cudaMemcpyDeviceToHost));
+        DCK(cudaMemcpy(lens.data(), d_lens, (size_t)n_emit * sizeof(u32), cudaMemcpyDeviceToHost));
+    }
     if (pcm_out) {
         u8* d_pcm = pcm_out;
         if (!pcm_on_device) { DCK(grow(&w.d_pcm, &w.cap_pcm, pcm_bytes + 64)); d_pcm = w.d_pcm; }
-        DCK(grow(&w.d_emits, &w.cap_emits, emits.size() * sizeof(bf_dec_emit)));
-        DCK(cudaMemcpy(w.d_emits, emits.data(), emits.size() * sizeof(bf_dec_emit), cudaMemcpyHostToDevice));
-        k_dec_emit<<<(u32)emits.size(), 256>>>(w.d_cands, w.d_emits, w.d_scratch, row_stride, S, d_pcm);
+        k_dec_emit<<<n_emit, 256>>>(w.d_cands, w.d_emits, w.d_scratch, row_stride, S, d_pcm);
         DCK(cudaGetLastError());
         DCK(cudaEventRecord(w.ev[4]));
         if (!pcm_on_device) DCK(cudaMemcpy(pcm_out, d_pcm, pcm_bytes, cudaMemcpyDeviceToHost));
@@ -829,10 +959,10 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
         if (kernel_ms) {
             DCK(cudaEventElapsedTime(&kernel_ms[0], w.ev[0], w.ev[1]));
             DCK(cudaEventElapsedTime(&kernel_ms[1], w.ev[2], w.ev[3]));
-            DCK(cudaEventElapsedTime(&kernel_ms[2], w.ev[3], w.ev[4])); // includes the host's chain walk
+            DCK(cudaEventElapsedTime(&kernel_ms[2], w.ev[3], w.ev[4])); // chain (device, or the host walk) + emit
         }
     }
-    if (n_frames) *n_frames = emits.size();
+    if (n_frames) *n_frames = n_emit;
     if (frame_offsets) {
         *frame_offsets = (uint64_t*)malloc((offs.size() ? offs.size() : 1) * sizeof(uint64_t));
         memcpy(*frame_offsets, offs.data(), offs.size() * sizeof(uint64_t));

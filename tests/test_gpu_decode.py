@@ -398,3 +398,14 @@ def test_flacaudio_reads_id3_prefixed_and_disordered_fixtures(name, built):
         h.update(f.to_bytes(False, True))
     assert frames == a.total_frames() and h.digest() == a.__md5__ and a.__md5__ != bytes(16)
     d.close()
+
+
+def test_device_chain_and_host_walk_agree(built, monkeypatch):
+    """the frame chain is normally resolved on the device (hash table + pointer jumping); the host walk that
+    words the errors of damaged streams must give the same frames and PCM on a good one"""
+    pcm = helpers.synth_pcm(61, 2, 16, 4096 * 40 + 11)
+    flac, offs = helpers.oracle_encode(pcm, 44100, 2, 16, helpers.options(**LEVELS["5"]), want_offsets=True)
+    info, got, frames, ms = _decode(flac, want_frames=True)
+    monkeypatch.setenv("B200FLAC_DEC_HOST_CHAIN", "1")
+    info2, got2, frames2, ms2 = _decode(flac, want_frames=True)
+    assert got == got2 == pcm and frames == frames2 == offs
