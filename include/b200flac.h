@@ -207,7 +207,8 @@ int b200flac_stream_close(b200flac_stream *s, int abort_encode, uint64_t **frame
                           uint32_t **frame_pcm_frames, uint64_t *n_frames);
 void b200flac_free(void *p);
 /* The stream layer keeps up to 16 (env B200FLAC_POOL) idle encoders (device buffers, pinned staging) for the next stream with
- * the same options and device: set-up costs ~100 ms, a short file a few ms.  This releases them. */
+ * the same options and device: set-up costs ~100 ms, a short file a few ms.  This releases them, and the
+ * device buffers the decode layer keeps between calls (candidates, sample rows, chain arrays). */
 void b200flac_pool_clear(void);
 
 /* Metadata finalisation of a finished file, host only: what FlacAudio.from_pcm does in Python after
