@@ -125,7 +125,12 @@ static PyObject *encoders_encode_flac(PyObject *dummy, PyObject *args, PyObject 
     stream = b200flac_stream_open(filename, &p, padding_size, NULL, NULL, 0);
     Py_END_ALLOW_THREADS
     if (!stream) {
-        PyErr_SetString(PyExc_RuntimeError, b200flac_last_error());
+        /* FlacAudio.from_pcm turns IOError/ValueError into EncodingError (flac.py:1833-1845) and callers of
+           the reference catch that: a rejected parameter is a ValueError, everything else (no usable device,
+           allocation, the output file) an IOError */
+        const char *msg = b200flac_last_error();
+        const int bad_param = strstr(msg, "must be") != NULL || strstr(msg, "unsupported") != NULL;
+        PyErr_SetString(bad_param ? PyExc_ValueError : PyExc_IOError, msg);
         pcmreader_del(reader);
         return NULL;
     }

@@ -409,7 +409,11 @@ def decode(flac, device=0, check_md5=True, want_frames=False):
     """a FLAC file image (bytes) -> (StreamInfo, PCM bytes[, [(frame offset, pcm frames)], kernel ms]):
     b200flac_decode_memory; raises ValueError / IOError with the reference decoder's messages"""
     import numpy as np
-    info = read_streaminfo(flac)
+    info = StreamInfo()
+    # sizing call: STREAMINFO's total is checked against the file size before a buffer is sized from it
+    rc = lib().b200flac_decode_memory(_buf_ptr(flac), len(flac), device, None, 0, C.byref(info), 0, None, None, None, None)
+    if rc:
+        _raise_decode(rc)
     nbytes = info.total_pcm_frames * info.channels * (info.bits_per_sample // 8)
     pcm = np.empty(max(nbytes, 1), dtype=np.uint8)
     offs, lens, n = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)(), C.c_uint64(0)

@@ -977,6 +977,40 @@ done:
     return rc;
 }
 
+
+// Reads a whole file; every failure (open, seek, tell, allocation, short read) is an error return, never an
+// exception through the C ABI.
+static int read_whole_file(const char* path, std::vector<uint8_t>& data)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        char msg[400];
+        snprintf(msg, sizeof(msg), "cannot open \"%.300s\" for reading", path);
+        return dfail(2, msg);
+    }
+    off_t end = -1;
+    if (fseeko(f, 0, SEEK_END) == 0) end = ftello(f);
+    if (end < 0 || fseeko(f, 0, SEEK_SET) != 0) { fclose(f); return dfail(2, "read error"); }
+    try { data.resize((size_t)end + 1); } catch (const std::bad_alloc&) { fclose(f); return dfail(3, "out of memory reading the file"); }
+    const size_t got = fread(data.data(), 1, (size_t)end, f);
+    fclose(f);
+    if (got != (size_t)end) return dfail(2, "read error");
+    data.resize((size_t)end);
+    return 0;
+}
+
+// STREAMINFO's total (36 bits, straight from the file) against what the file can hold: a frame is at least
+// 8 bytes and at most 65535 PCM frames, so a larger total can only end the way the reference's frame loop
+// ends on such a file -- at EOF (src/decoders/flac.c:196-268).  Checked before anything is sized from it.
+static int check_total_against_size(const b200flac_stream_info* info, uint64_t frame_bytes)
+{
+    if (info->bits_per_sample % 8 || info->bits_per_sample < 8 || info->bits_per_sample > 24 || info->channels < 1 ||
+        info->channels > B200FLAC_MAX_CHANNELS || info->max_block_size == 0)
+        return dfail(3, "unsupported stream parameters");
+    if (info->total_pcm_frames > (frame_bytes / 8 + 1) * 65535ull) return dfail(2, ds_strerror(DS_EOF));
+    return 0;
+}
+
 extern "C" int b200flac_decode_memory(const uint8_t* flac, uint64_t n_bytes, int device, uint8_t* pcm,
                                       uint64_t pcm_capacity, b200flac_stream_info* info_out, int check_md5,
                                       uint64_t** frame_offsets, uint32_t** frame_pcm_frames, uint64_t* n_frames,
@@ -986,7 +1020,9 @@ extern "C" int b200flac_decode_memory(const uint8_t* flac, uint64_t n_bytes, int
     int rc = b200flac_read_streaminfo(flac, n_bytes, &info);
     if (rc) return rc;
     if (info_out) *info_out = info;
-    if (!pcm) return 0; // sizing call
+    rc = check_total_against_size(&info, n_bytes - info.first_frame_offset);
+    if (rc) return rc;
+    if (!pcm) return 0; // sizing call: the caller may now size its buffer from info_out->total_pcm_frames
     rc = decode_core(&info, flac + info.first_frame_offset, n_bytes - info.first_frame_offset, 0, device, pcm, 0,
                      pcm_capacity, frame_offsets, frame_pcm_frames, n_frames, kernel_ms);
     if (rc) return rc;
@@ -1014,23 +1050,18 @@ extern "C" int b200flac_decode_device(const b200flac_stream_info* info, const vo
 extern "C" int b200flac_verify_file(const char* flac_filename, int device)
 {
     if (!flac_filename) return dfail(3, "filename is NULL");
-    FILE* f = fopen(flac_filename, "rb");
-    if (!f) {
-        char msg[400];
-        snprintf(msg, sizeof(msg), "cannot open \"%.300s\" for reading", flac_filename);
-        return dfail(2, msg);
-    }
-    fseeko(f, 0, SEEK_END);
-    const u64 n = (u64)ftello(f);
-    fseeko(f, 0, SEEK_SET);
-    std::vector<uint8_t> data(n + 1);
-    const size_t got = fread(data.data(), 1, n, f);
-    fclose(f);
-    if (got != n) return dfail(2, "read error");
-    b200flac_stream_info info;
-    int rc = b200flac_read_streaminfo(data.data(), n, &info);
+    std::vector<uint8_t> data;
+    int rc = read_whole_file(flac_filename, data);
     if (rc) return rc;
-    std::vector<uint8_t> pcm((size_t)(info.total_pcm_frames * info.channels * (info.bits_per_sample / 8)) + 1);
+    const u64 n = data.size();
+    b200flac_stream_info info;
+    rc = b200flac_read_streaminfo(data.data(), n, &info);
+    if (rc) return rc;
+    rc = check_total_against_size(&info, n - info.first_frame_offset);
+    if (rc) return rc;
+    std::vector<uint8_t> pcm;
+    try { pcm.resize((size_t)(info.total_pcm_frames * info.channels * (info.bits_per_sample / 8)) + 1); }
+    catch (const std::bad_alloc&) { return dfail(3, "out of memory for the decoded PCM"); }
     return b200flac_decode_memory(data.data(), n, device, pcm.data(), pcm.size(), nullptr, 1, nullptr, nullptr, nullptr, nullptr);
 }
 
@@ -1041,21 +1072,14 @@ extern "C" int b200flac_verify_file(const char* flac_filename, int device)
 extern "C" int b200flac_decode_to_wave(const char* flac_filename, const char* wave_filename, int device)
 {
     if (!flac_filename || !wave_filename) return dfail(3, "filename is NULL");
-    FILE* f = fopen(flac_filename, "rb");
-    if (!f) {
-        char msg[400];
-        snprintf(msg, sizeof(msg), "cannot open \"%.300s\" for reading", flac_filename);
-        return dfail(2, msg);
-    }
-    fseeko(f, 0, SEEK_END);
-    const u64 n = (u64)ftello(f);
-    fseeko(f, 0, SEEK_SET);
-    std::vector<uint8_t> data(n + 1);
-    const size_t got = fread(data.data(), 1, n, f);
-    fclose(f);
-    if (got != n) return dfail(2, "read error");
+    std::vector<uint8_t> data;
+    int rc = read_whole_file(flac_filename, data);
+    if (rc) return rc;
+    const u64 n = data.size();
     b200flac_stream_info info;
-    int rc = b200flac_read_streaminfo(data.data(), n, &info);
+    rc = b200flac_read_streaminfo(data.data(), n, &info);
+    if (rc) return rc;
+    rc = check_total_against_size(&info, n - info.first_frame_offset);
     if (rc) return rc;
     const u32 B = info.bits_per_sample / 8, C = info.channels;
     const u64 data_size = info.total_pcm_frames * C * B;
@@ -1074,7 +1098,8 @@ extern "C" int b200flac_decode_to_wave(const char* flac_filename, const char* wa
     }
     const u64 total_size = 4 + 8 + fmt.size() + 8 + data_size + (data_size % 2);
     if (total_size >= (1ull << 32)) return dfail(1, "total size too large for wave file");
-    std::vector<uint8_t> pcm((size_t)data_size + 1);
+    std::vector<uint8_t> pcm;
+    try { pcm.resize((size_t)data_size + 1); } catch (const std::bad_alloc&) { return dfail(3, "out of memory for the decoded PCM"); }
     rc = b200flac_decode_memory(data.data(), n, device, pcm.data(), data_size, nullptr, 1, nullptr, nullptr, nullptr, nullptr);
     if (rc) return rc;
     if (B == 1) for (u64 i = 0; i < data_size; i++) pcm[i] ^= 0x80; // to_bytes(False, signed = bits_per_sample > 8)

@@ -582,6 +582,10 @@ extern "C" int b200flac_stream_end_block(b200flac_stream* s)
     const uint32_t bs = s->params.block_size;
     if ((l.fill - l.seg_start) % bs == 0) return 0; // already on a boundary
     close_segment(s, l);
+    // every short read adds a segment (and a frame) to the batch; an encoder has room for 1024 segment
+    // tails per batch (b200flac_encoder_create), so a reader that keeps returning short reads ends the
+    // batch early instead of overflowing it
+    if (l.segs.size() >= 1000) return submit_current(s);
     return 0;
 }
 

@@ -88,3 +88,27 @@ def test_reference_fixture_streaminfo(built):
                    "1h.flac": (8000, 2, 16, 28800000, 32768, 0x3)}
     with pytest.raises(ValueError, match="not a FLAC file"):
         b200flac.read_streaminfo(open(os.path.join(d, "flac-id3.flac"), "rb").read())
+
+
+def test_crafted_total_is_rejected_before_allocation(built, tmp_path):
+    """a 42-byte file whose STREAMINFO claims 2^36 - 1 PCM frames of 8 x 24-bit channels (1.6 TB): the C entry
+    points report what the reference's frame loop would hit -- EOF -- instead of sizing a buffer from the
+    header (round-1 advisor finding); needs no GPU"""
+    import os
+    import b200flac
+    si = bytearray(34)
+    si[0:2] = si[2:4] = (4096).to_bytes(2, "big")
+    v = (96000 << 44) | (7 << 41) | (23 << 36) | ((1 << 36) - 1)
+    si[10:18] = v.to_bytes(8, "big")
+    data = b"fLaC" + bytes([0x80]) + (34).to_bytes(3, "big") + bytes(si)
+    assert len(data) == 42
+    path = os.path.join(str(tmp_path), "bomb.flac")
+    open(path, "wb").write(data)
+    with pytest.raises(IOError, match="EOF"):
+        b200flac.verify_file(path)
+    with pytest.raises(IOError, match="EOF"):
+        b200flac.decode_to_wave(path, os.path.join(str(tmp_path), "bomb.wav"))
+    with pytest.raises(IOError, match="EOF"):
+        b200flac.decode(data)
+    with pytest.raises(IOError):
+        b200flac.verify_file(os.path.join(str(tmp_path), "missing.flac"))

@@ -205,6 +205,34 @@ def test_stream_end_block_short_reads(tmp_path, built):
         assert helpers.ref_decode(got) == pcm
 
 
+def test_stream_every_read_short(tmp_path, built):
+    """a reader whose every read is shorter than block_size (a non-buffered pcmreader): thousands of
+    one-frame segments, more than one encoder batch holds tails for -- the stream layer must end
+    batches early instead of failing (round-1 advisor finding; reference behaviour flac.c:247,525)"""
+    b = _b200()
+    o = helpers.options(block_size=4096, max_lpc_order=4, max_residual_partition_order=2)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 1, 16, **kw)
+    n_reads, r = 2600, 96
+    pcm = helpers.synth_pcm(9, 1, 16, n_reads * r)
+    path = os.path.join(str(tmp_path), "short.flac")
+    s = b.Stream(path, p)
+    for i in range(n_reads):
+        s.write(pcm[i * r * 2:(i + 1) * r * 2])
+        s.end_block()
+    offs = s.close()
+    assert [n for _, n in offs] == [r] * n_reads
+    got = open(path, "rb").read()
+    frames = got[helpers.first_frame_offset(got):]
+    # spot-check frames against the oracle (frame numbers cross the 1-, 2- and 3-byte UTF-8 forms)
+    for i in (0, 1, 127, 128, 1023, 1024, 2047, 2048, n_reads - 1):
+        fr, _ = helpers.oracle_encode_range(pcm[i * r * 2:(i + 1) * r * 2], 44100, 1, 16, o, i)
+        a = offs[i][0]
+        assert frames[a:a + len(fr)] == fr, i
+    if helpers.have_ref():
+        assert helpers.ref_decode(got) == pcm
+
+
 def test_error_paths(tmp_path, built):
     b = _b200()
     p = b.make_params()

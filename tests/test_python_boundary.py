@@ -81,9 +81,14 @@ def test_encode_flac_without_gpu_fails_loudly(built, tmp_path):
     if encoders.b200_device_count() > 0:
         pytest.skip("a GPU is present")
     r = at.PCMBytesReader(helpers.synth_pcm(1, 2, 16, 100), 44100, 2, 0x3, 16)
-    with pytest.raises(RuntimeError) as e:
+    # an IOError, so that FlacAudio.from_pcm's EncodingError contract holds (flac.py:1833-1845)
+    with pytest.raises(IOError) as e:
         encoders.encode_flac(os.path.join(str(tmp_path), "a.flac"), r, 4096, 8, 0, 5)
     assert "no CPU fallback" in str(e.value)
+    with pytest.raises(at.EncodingError):
+        at.FlacAudio.from_pcm(os.path.join(str(tmp_path), "b.flac"),
+                              at.PCMBytesReader(helpers.synth_pcm(1, 2, 16, 100), 44100, 2, 0x3, 16))
+    assert not os.path.exists(os.path.join(str(tmp_path), "b.flac"))   # from_pcm unlinks the partial file
     with pytest.raises(IOError):
         encoders.encode_flac(os.path.join(str(tmp_path), "missing", "a.flac"), r, 4096, 8, 0, 5)
 
