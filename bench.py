@@ -199,6 +199,106 @@ def run_reference_arm(args, rank, world, emit):
 
 
 # ----------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, device resident (tier K), and their own rooflines
+# ----------------------------------------------------------------------------------------------
+OTHER_CONFIGS = [
+    # name, sample rate, channels, bits, seconds per GPU per step, options
+    ("config3 96 kHz/24-bit stereo, block 4096, lpc 12, -m -e (exhaustive), max partition order 8", 96000, 2, 24, 300.0,
+     dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=8, mid_side=True, exhaustive_model_search=True)),
+    ("config4 96 kHz/24-bit 5.1 (6 ch), block 4608, lpc 12, max partition order 6", 96000, 6, 24, 120.0,
+     dict(block_size=4608, max_lpc_order=12, max_residual_partition_order=6)),
+    ("level8 44.1 kHz/16-bit stereo, block 4096, lpc 12, -m -e, max partition order 6 (FlacAudio.from_pcm default, config5 setting)",
+     44100, 2, 16, 600.0,
+     dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, mid_side=True, exhaustive_model_search=True)),
+]
+
+
+def resident_config(b200flac, L, dev, rank, world, barrier, allmax, name, rate, ch, bps, seconds, opts, steps):
+    n = int(seconds * rate)
+    n -= n % opts["block_size"]
+    p = b200flac.make_params(rate, ch, bps, **opts)
+    enc = b200flac.Encoder(p, device=dev, max_pcm_frames_per_batch=n, n_slots=1)
+    nbytes = n * ch * (bps // 8)
+    cap = enc.output_bound(n, 1)
+    d_pcm = L.b200flac_device_alloc(dev, nbytes)
+    d_out = L.b200flac_device_alloc(dev, cap)
+    if not d_pcm or not d_out:
+        raise SystemExit("device allocation failed: " + L.b200flac_last_error().decode())
+    L.b200flac_device_synth_pcm(dev, d_pcm, 1236 + rank, ch, bps, 0, n)
+    for _ in range(3):
+        enc.encode_device(d_pcm, [(0, n, 0)], d_out, cap)
+    launches0 = enc.launch_count()
+    kms = [0.0] * 5
+    dev_ms = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out_bytes, nfr, ms = enc.encode_device(d_pcm, [(0, n, 0)], d_out, cap)
+        dev_ms += ms
+        for i, v in enumerate(enc.kernel_ms(0)):
+            kms[i] += v
+    barrier()
+    dt = allmax(time.perf_counter() - t0)
+    launches = enc.launch_count() - launches0
+    L.b200flac_device_free(dev, d_pcm)
+    L.b200flac_device_free(dev, d_out)
+    enc.close()
+    peak, peak_kind = peaks()
+    algo = nbytes + out_bytes
+    kms = [v / steps for v in kms]
+    names = ["lpc_model", "analyze", "select_scan", "pack", "crc16"]
+    dom = max(range(5), key=lambda i: kms[i])
+    res = {"workload": name + ", %.0f s per GPU per step" % seconds,
+           "value": world * n * ch * steps / dt / 1e6, "unit": UNIT, "ms_per_step": 1000.0 * dt / steps,
+           "device_ms_per_step": dev_ms / steps, "compressed_ratio": out_bytes / nbytes,
+           "kernel_ms": dict(zip(names, kms)),
+           "roofline": {"bound": "hbm", "kernel": names[dom], "peak": peak, "unit": "GB/s", "peak_kind": peak_kind,
+                        "algorithmic_bytes_per_launch": algo,
+                        "achieved": algo / (kms[dom] * 1e-3) / 1e9 if kms[dom] else None,
+                        "frac": algo / (kms[dom] * 1e-3) / 1e9 / peak if kms[dom] else None,
+                        "pipeline_achieved": algo / (dev_ms / steps * 1e-3) / 1e9,
+                        "pipeline_frac": algo / (dev_ms / steps * 1e-3) / 1e9 / peak,
+                        "bytes_per_sample": algo / (n * ch)}}
+    return res, launches
+
+
+def run_threads(fns):
+    import threading
+    errs = []
+
+    def wrap(f):
+        try:
+            f()
+        except BaseException as e:  # noqa: BLE001 (reported below)
+            errs.append(e)
+    th = [threading.Thread(target=wrap, args=(f,)) for f in fns]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise SystemExit("worker failed: %r" % (errs[0],))
+
+
+def traffic_for(kernel_name, hour):
+    """DRAM bytes of one launch of the dominant kernel, from the file profiles/summarize_ncu.py --json wrote
+    from the round's ncu --set full capture (valid for the default 3600 s workload only)"""
+    if not hour:
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+    except Exception:
+        return None, None
+    want = {"lpc_model": "k_lpc_autoc", "analyze": "k_analyze_v3", "pack": "k_pack_v3"}.get(kernel_name)
+    for k, v in t.get("kernels", {}).items():
+        if want and k.startswith(want):
+            return v.get("dram_bytes"), "profiles/r02_traffic.json (%s, %s)" % (t.get("source"), k)
+    return None, None
+
+
+# ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,12 +308,16 @@ def main():
     ap.add_argument("--seconds", type=float, default=3600.0, help="audio per GPU per step (default: the 1 h config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-api", action="store_true", help="skip the API-tier lines (single stream, encode_flac, many tracks)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--no-full-check", action="store_true", help="skip decoding the whole step on the GPU after the timed region")
-    ap.add_argument("--e2e-slots", type=int, default=4, help="batches in flight in the end-to-end arm")
-    ap.add_argument("--e2e-batch-blocks", type=int, default=2048, help="FLAC frames per end-to-end batch")
+    ap.add_argument("--e2e-slots", type=int, default=4, help="batches in flight in the frame-layer end-to-end arm")
+    ap.add_argument("--e2e-batch-blocks", type=int, default=2048, help="FLAC frames per frame-layer batch")
+    ap.add_argument("--tracks", type=int, default=1000, help="3-minute tracks of the config-5 line (all ranks together)")
     ap.add_argument("--verify-seconds", type=float, default=120.0,
                     help="correctness gate inside the CPU leg (SURVEY 8d): this much of the workload is encoded to a "
-                         "file through the stream layer and decoded by the compiled reference decoder; 0 skips")
+                         "file through the stream layer, decoded by the compiled reference decoder and compared byte "
+                         "for byte with the compiled reference encoder's file; 0 skips")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -233,6 +337,11 @@ def main():
         run_reference_arm(args, rank, world, emit)
         return
 
+    cores = os.cpu_count() or 1
+    threads = max(1, min(32, cores // world))       # host threads of this rank (its share of the box)
+    os.environ.setdefault("B200FLAC_POOL", str(max(16, threads + 4)))   # idle encoders kept by the stream layer
+
+    import hashlib
     import numpy as np
     import torch
     import b200flac
@@ -250,6 +359,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     L = b200flac.lib()
     dev = local_rank
     n_frames_pcm = int(args.seconds * SAMPLE_RATE)
@@ -257,6 +380,8 @@ def main():
     pcm_bytes = n_frames_pcm * frame_bytes
     params = b200flac.make_params(SAMPLE_RATE, CHANNELS, BPS, block_size=BLOCK, max_lpc_order=LPC,
                                   max_residual_partition_order=PO, adaptive_mid_side=True)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.TemporaryDirectory(dir=shm, prefix="b200bench%d_" % rank)
 
     # ---- device-resident arm -----------------------------------------------------------------
     enc = b200flac.Encoder(params, device=dev, max_pcm_frames_per_batch=n_frames_pcm, n_slots=1)
@@ -286,20 +411,16 @@ def main():
         for i, v in enumerate(enc.kernel_ms(0)):
             kernel_ms[i] += v
     barrier()
-    elapsed = time.perf_counter() - t0
+    elapsed = allmax(time.perf_counter() - t0)
     clocks.mark(w0, time.time())
     launches = enc.launch_count() - launches0
-    if dist is not None:
-        t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
     samples_per_step = n_frames_pcm * CHANNELS
     value = world * samples_per_step * args.steps / elapsed / 1e6
 
     # ---- whole-step check, outside the timed region: the frames the last step left in HBM are decoded by
     # the engine's own GPU decoder (every frame header CRC-8 and frame CRC-16 checked) and the
     # PCM must equal the step's input, all of it -- the size-independent round trip at full size.  (The
-    # reference decoder checks a sample of the workload in the CPU leg below.) ----
+    # reference decoder AND the reference encoder check a sample of the workload in the CPU leg below.) ----
     full_check = None
     if not args.no_full_check:
         info = b200flac.StreamInfo()
@@ -320,7 +441,7 @@ def main():
         same = bool(np.array_equal(a, b))
         del a, b
         L.b200flac_device_free(dev, d_dec)
-        L.b200flac_pool_clear()   # (releases the decoder's scratch before the end-to-end arm)
+        L.b200flac_pool_clear()   # (releases the decoder's scratch before the end-to-end arms)
         full_check = {"what": "GPU decode of the step's %d frames back to PCM, compared with the input" % nf.value,
                       "pcm_identical": same, "decode_ms": dec_s * 1e3,
                       "decode_kernel_ms": {"scan": kms[0], "frames": kms[1], "chain_emit": kms[2]}}
@@ -331,33 +452,83 @@ def main():
     # CRC kernel of the k_pack_v2 path; k_pack_v3 (the default) computes the CRC-16 inside "pack".
     names = ["lpc_model", "analyze", "select_scan", "pack", "crc16"]
     dom = max(range(5), key=lambda i: kernel_ms[i])
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, from the ncu --set full
-    # capture summarised in profiles/r01_v7_summary.txt (only valid for the default 3600 s workload)
-    traffic_ncu = {"lpc_model": 636.3e6 + 14.6e6, "analyze": 673.2e6 + 20.6e6, "pack": 655.5e6 + 403.7e6}
-    traffic = traffic_ncu.get(names[dom]) if n_frames_pcm == HOUR_FRAMES else None
+    traffic, traffic_source = traffic_for(names[dom], n_frames_pcm == HOUR_FRAMES)
     algo_bytes = pcm_bytes + out_bytes            # PCM in at native width + frame bytes out
     peak, peak_kind = peaks()
-    achieved = algo_bytes / (kernel_ms[dom] * 1e-3) / 1e9
-    pipeline = algo_bytes / (sum(kernel_ms) * 1e-3) / 1e9
+    achieved = algo_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] else None
+    pipeline = algo_bytes / (device_ms / args.steps * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                "traffic_source": "profiles/r01_v7_summary.txt (ncu --set full, bytes per launch)" if traffic else None,
+                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_kind": peak_kind,
+                "traffic_source": traffic_source,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": dict(zip(names, kernel_ms)),
                 "device_ms_per_step": device_ms / args.steps,
                 "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak,
                 "bytes_per_sample": algo_bytes / samples_per_step}
 
-    # ---- end-to-end arm: pinned host PCM -> H2D -> kernels -> D2H, through submit/collect ---------
-    e2e = None
-    if not args.no_e2e:
-        batch_frames = BLOCK * args.e2e_batch_blocks
-        nslots = args.e2e_slots
-        enc2 = b200flac.Encoder(params, device=dev, max_pcm_frames_per_batch=batch_frames, n_slots=nslots)
+    # the hour in page-locked host memory: input of every host-buffer arm below
+    h_pcm = None
+    if not (args.no_e2e and args.no_api):
         h_pcm = L.b200flac_host_alloc(pcm_bytes)
         if not h_pcm:
             raise SystemExit("pinned allocation failed")
         L.b200flac_device_download(dev, h_pcm, d_pcm, pcm_bytes)
+    dev1 = (C.c_int * 1)(dev)
+
+    def encode_file(path, off_frames, n, p=params):
+        if L.b200flac_encode_file(os.fsencode(path), C.byref(p), 4096, None, h_pcm + off_frames * frame_bytes, n, dev1, 1):
+            raise RuntimeError(L.b200flac_last_error().decode())
+
+    # ---- end-to-end arm (the headline): the plugin call.  b200flac_encode_file is the C-ABI entry that
+    # audiotools.encoders.encode_flac wraps (stream head, frame loop, STREAMINFO MD5 on a host thread, the
+    # final STREAMINFO rewrite, the file written to tmpfs).  The STREAMINFO MD5 is a serial chain per stream
+    # (one core hashes ~570 MB/s), so the step's hour is cut into one stream per host thread of this rank --
+    # the same cut the reference arm makes, whose encoder cannot split a stream either. ----
+    e2e = None
+    e2e_frame = None
+    if not args.no_e2e:
+        blocks = (n_frames_pcm + BLOCK - 1) // BLOCK
+        per = (blocks + threads - 1) // threads * BLOCK
+        parts = [(o, min(per, n_frames_pcm - o)) for o in range(0, n_frames_pcm, per)]
+        paths = [os.path.join(tmp.name, "e2e_%d.flac" % i) for i in range(len(parts))]
+
+        def e2e_stream_step():
+            run_threads([(lambda i=i: encode_file(paths[i], parts[i][0], parts[i][1])) for i in range(len(parts))])
+
+        for _ in range(2):
+            e2e_stream_step()
+        barrier()
+        lt0 = L.b200flac_launch_count_total()
+        w0 = time.time()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_stream_step()
+        barrier()
+        s_elapsed = allmax(time.perf_counter() - t0)
+        clocks.mark(w0, time.time())
+        file_bytes = sum(os.path.getsize(p) for p in paths)
+        streams_frames = sum((n + BLOCK - 1) // BLOCK for _, n in parts)
+        launches += L.b200flac_launch_count_total() - lt0
+        # the serial floor of this arm: OpenSSL's MD5 over one stream's PCM on one core
+        part0 = np.ctypeslib.as_array((C.c_uint8 * (parts[0][1] * frame_bytes)).from_address(h_pcm))
+        t0 = time.perf_counter()
+        hashlib.md5(part0).digest()
+        md5_s = time.perf_counter() - t0
+        e2e = {"value": world * samples_per_step * args.steps / s_elapsed / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": pcm_bytes, "d2h_bytes_per_step": int(file_bytes),
+               "ms_per_step": 1000.0 * s_elapsed / args.steps,
+               "what": "b200flac_encode_file (the C-ABI entry audiotools.encoders.encode_flac wraps: stream head, frame "
+                       "loop, STREAMINFO MD5, file written to tmpfs), host PCM in; the step's hour as %d independent "
+                       "streams, one per host thread of this rank (%d host cores / %d ranks)" % (len(parts), cores, world),
+               "streams_per_step": len(parts), "host_threads": threads,
+               "md5_floor_ms_per_step": 1000.0 * md5_s,
+               "md5_floor_note": "hashlib (OpenSSL) MD5 of one stream's PCM on one core: the serial part of every stream"}
+
+        # ---- frame-layer arm (tier D): b200flac_encoder_submit/collect = the reference's flacenc_write_frame
+        # seam for batches of frames; pinned host PCM -> H2D -> kernels -> D2H frame bytes, no MD5, no file ----
+        batch_frames = BLOCK * args.e2e_batch_blocks
+        nslots = args.e2e_slots
+        enc2 = b200flac.Encoder(params, device=dev, max_pcm_frames_per_batch=batch_frames, n_slots=nslots)
         bcap = enc2.output_bound(batch_frames, 1)
         fcap = batch_frames // BLOCK + 4
         h_out = [L.b200flac_host_alloc(bcap) for _ in range(nslots)]
@@ -399,30 +570,188 @@ def main():
         for _ in range(args.steps):
             e2e_bytes = e2e_step()
         barrier()
-        e_elapsed = time.perf_counter() - t0
+        e_elapsed = allmax(time.perf_counter() - t0)
         clocks.mark(w0, time.time())
         launches += enc2.launch_count() - launches_e0
-        if dist is not None:
-            t = torch.tensor([e_elapsed], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_elapsed = float(t.item())
-        assert e2e_bytes == out_bytes, "e2e arm produced %d bytes, resident arm %d" % (e2e_bytes, out_bytes)
-        e2e = {"value": world * samples_per_step * args.steps / e_elapsed / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": pcm_bytes, "d2h_bytes_per_step": int(e2e_bytes + 4 * n_flac_frames),
-               "ms_per_step": 1000.0 * e_elapsed / args.steps,
-               "what": "b200flac_encoder_submit/collect, pinned host PCM in, frame bytes out to pinned host "
-                       "memory, %d-block batches, %d in flight" % (batch_frames // BLOCK, nslots)}
+        assert e2e_bytes == out_bytes, "frame-layer arm produced %d bytes, resident arm %d" % (e2e_bytes, out_bytes)
         for p in h_out:
             L.b200flac_host_free(p)
-        L.b200flac_host_free(h_pcm)
         enc2.close()
+
+        # ---- the copies alone: the same bytes per step, H2D from and D2H to pinned memory, every rank at once,
+        # no kernels -- the floor the host/PCIe fabric of this box sets for the frame-layer arm at this N ----
+        hp = torch.empty(pcm_bytes, dtype=torch.uint8).pin_memory()
+        ho = torch.empty(int(out_bytes), dtype=torch.uint8).pin_memory()
+        dp = torch.empty(pcm_bytes, dtype=torch.uint8, device="cuda")
+        do = torch.empty(int(out_bytes), dtype=torch.uint8, device="cuda")
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copy_step():
+            with torch.cuda.stream(s_in):
+                dp.copy_(hp, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                ho.copy_(do, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+        copy_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            copy_step()
+        barrier()
+        c_elapsed = allmax(time.perf_counter() - t0)
+        del hp, ho, dp, do
+        e2e_frame = {"value": world * samples_per_step * args.steps / e_elapsed / 1e6, "unit": UNIT,
+                     "h2d_bytes_per_step": pcm_bytes, "d2h_bytes_per_step": int(e2e_bytes + 4 * n_flac_frames),
+                     "ms_per_step": 1000.0 * e_elapsed / args.steps,
+                     "copy_floor_ms": 1000.0 * c_elapsed / args.steps,
+                     "copy_floor_what": "the same H2D and D2H bytes per rank and step as pure pinned-memory copies on two "
+                                        "streams, all %d ranks at once, no kernels (max over ranks)" % world,
+                     "what": "b200flac_encoder_submit/collect (frame layer, the flacenc_write_frame seam): pinned host PCM "
+                             "in, frame bytes out to pinned host memory, %d-block batches, %d in flight; no MD5, no file"
+                             % (batch_frames // BLOCK, nslots)}
+
+    # ---- API tier lines (outside every timed region above) ----------------------------------------
+    api = None
+    if not args.no_api:
+        api = {}
+        # (1) one stream = the whole hour through the C entry, then through the CPython extension
+        one = os.path.join(tmp.name, "one.flac")
+        encode_file(one, 0, n_frames_pcm)
+        barrier()
+        t0 = time.perf_counter()
+        encode_file(one, 0, n_frames_pcm)
+        t_c = time.perf_counter() - t0
+        whole = np.ctypeslib.as_array((C.c_uint8 * pcm_bytes).from_address(h_pcm))
+        t0 = time.perf_counter()
+        hashlib.md5(whole).digest()
+        t_md5 = time.perf_counter() - t0
+        one_sha = hashlib.sha256(open(one, "rb").read()).hexdigest()
+        api["single_stream_encode_file"] = {
+            "value": samples_per_step / t_c / 1e6, "unit": UNIT, "ms": 1000.0 * t_c,
+            "md5_alone_ms": 1000.0 * t_md5, "md5_alone_value": samples_per_step / t_md5 / 1e6,
+            "what": "b200flac_encode_file, the step's whole hour as ONE stream on one GPU (host PCM -> file on tmpfs); "
+                    "md5_alone = hashlib MD5 of the same PCM on one core, the floor of any single stream"}
+        try:
+            import audiotools
+            from audiotools import encoders as at_enc
+            rd = audiotools.PCMBytesReader(whole, SAMPLE_RATE, CHANNELS, 0x3, BPS)
+            py = os.path.join(tmp.name, "py.flac")
+            t0 = time.perf_counter()
+            offs = at_enc.encode_flac(py, audiotools.BufferedPCMReader(rd), BLOCK, LPC, 0, PO, adaptive_mid_side=1)
+            t_py = time.perf_counter() - t0
+            same = hashlib.sha256(open(py, "rb").read()).hexdigest() == one_sha
+            api["single_stream_encode_flac"] = {
+                "value": samples_per_step / t_py / 1e6, "unit": UNIT, "ms": 1000.0 * t_py, "frames": len(offs),
+                "identical_to_encode_file": bool(same),
+                "what": "audiotools.encoders.encode_flac(filename, BufferedPCMReader(reader), 4096, 12, 0, 6, "
+                        "adaptive_mid_side=1) -- the entry point north_star names -- over a Python PCMReader handing out "
+                        "FrameLists, same hour, same GPU"}
+            if not same:
+                raise SystemExit("encode_flac and b200flac_encode_file wrote different files")
+        except ImportError as e:
+            api["single_stream_encode_flac"] = {"unavailable": "audiotools extension not importable: %s" % e}
+        del whole
+        # (2) config 5's shape: many 3-minute tracks at FlacAudio.from_pcm's default level 8, one host thread per
+        # core of this rank, every rank on its own GPU
+        tn = 7938000
+        if n_frames_pcm >= tn:
+            p8 = b200flac.make_params(SAMPLE_RATE, CHANNELS, BPS, block_size=4096, max_lpc_order=12,
+                                      max_residual_partition_order=6, mid_side=True, exhaustive_model_search=True)
+            distinct = n_frames_pcm // tn             # distinct track PCMs cut from the hour
+            my_tracks = max(threads, args.tracks // world)
+            nxt = [0]
+            import threading
+            lock = threading.Lock()
+
+            def track_worker(tid):
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= my_tracks:
+                        return
+                    encode_file(os.path.join(tmp.name, "trk_%d.flac" % tid), (i % distinct) * tn, tn, p8)
+
+            nxt[0] = max(0, my_tracks - 2 * threads)  # warm-up: fills the encoder pool for these options
+            run_threads([(lambda t=t: track_worker(t)) for t in range(threads)])
+            nxt[0] = 0
+            barrier()
+            t0 = time.perf_counter()
+            run_threads([(lambda t=t: track_worker(t)) for t in range(threads)])
+            barrier()
+            t_tr = allmax(time.perf_counter() - t0)
+            total_tracks = allsum(my_tracks)
+            api["many_tracks"] = {
+                "value": total_tracks * tn * CHANNELS / t_tr / 1e6, "unit": UNIT, "tracks": int(total_tracks),
+                "tracks_per_s": total_tracks / t_tr, "seconds": t_tr, "host_threads_per_rank": threads,
+                "projected_s_for_10000_tracks": 10000.0 * t_tr / total_tracks,
+                "what": "BASELINE config 5's shape: %d three-minute 44.1 kHz/16-bit stereo tracks (%d distinct PCMs cut from "
+                        "the hour, cycled) through b200flac_encode_file at level 8 (-m -e, lpc 12, the from_pcm default), "
+                        "%d host threads per rank, %d GPU(s), files on tmpfs" % (int(total_tracks), distinct, threads, world)}
+
+    # ---- the other BASELINE configurations, device resident ----
+    configs = None
+    if not args.no_configs:
+        if h_pcm:
+            L.b200flac_host_free(h_pcm)
+            h_pcm = None
+        L.b200flac_pool_clear()
+        configs = []
+        for (name, rate, ch, bps, seconds, opts) in OTHER_CONFIGS:
+            res, ln = resident_config(b200flac, L, dev, rank, world, barrier, allmax, name, rate, ch, bps, seconds, opts,
+                                      max(2, min(args.steps, 5)))
+            launches += ln
+            configs.append(res)
+
+    # ---- N > 1: ONE stream, frame-range sharded over the N GPUs by the stream layer (config 4's shape) ----
+    sharded = None
+    if world > 1 and not args.no_api:
+        barrier()
+        done_flag = os.path.join(tempfile.gettempdir(), "b200bench_sharded_%s" % os.environ.get("MASTER_PORT", "0"))
+        if rank == 0:
+            try:
+                rate, ch, bps, secs = 96000, 6, 24, 120.0
+                o4 = dict(block_size=4608, max_lpc_order=12, max_residual_partition_order=6)
+                n4 = int(secs * rate) // 4608 * 4608 + 1000
+                p4 = b200flac.make_params(rate, ch, bps, **o4)
+                pcm4 = b200flac.synth_pcm(1238, ch, bps, n4, device=dev)
+                res = {}
+                for label, devs in (("one", [dev]), ("all", list(range(world)))):
+                    path = os.path.join(tmp.name, "shard_%s.flac" % label)
+                    b200flac.encode_file(path, p4, pcm4, n4, devices=devs)        # warm (encoder pool)
+                    t0 = time.perf_counter()
+                    b200flac.encode_file(path, p4, pcm4, n4, devices=devs)
+                    res[label] = (time.perf_counter() - t0, hashlib.sha256(open(path, "rb").read()).hexdigest())
+                sharded = {"what": "one %d s 96 kHz/24-bit 6-channel stream (config 4's shape, block 4608) through "
+                                   "b200flac_encode_file with devices = all %d GPUs: the stream layer hands batches of "
+                                   "consecutive frames to the devices in turn and concatenates their frames in order on "
+                                   "the host; compared with the same call on one GPU" % (secs, world),
+                           "n_devices": world, "identical_to_one_gpu": res["one"][1] == res["all"][1],
+                           "sha256": res["all"][1], "ms_one_gpu": 1000.0 * res["one"][0], "ms_all_gpus": 1000.0 * res["all"][0],
+                           "value_all_gpus": n4 * ch / res["all"][0] / 1e6, "unit": UNIT,
+                           "note": "a single stream is bound by its serial STREAMINFO MD5 on one host core, not by the GPUs"}
+            finally:
+                open(done_flag, "w").close()
+            if sharded and not sharded["identical_to_one_gpu"]:
+                raise SystemExit("sharded stream differs from the single-GPU stream")
+        else:
+            while not os.path.exists(done_flag):    # (no collective here: a waiting NCCL kernel would sit on the GPUs)
+                time.sleep(0.05)
+        barrier()
+        if rank == 0:
+            try:
+                os.unlink(done_flag)
+            except OSError:
+                pass
 
     clk = clocks.stop()
 
     # ---- CPU leg (rank 0, N = 1): the compiled reference as baseline and as checker.  The only place this
-    # arm executes anything under oracle/: the reference encoder is timed, and the reference decoder
-    # (CRC-16 of every frame, STREAMINFO MD5) must return the input PCM for a sample of the workload
-    # encoded through the stream layer -- SURVEY 8(d)'s correctness gate, outside the timed regions ----
+    # arm executes anything under oracle/: the reference encoder is timed, and for a sample of the workload
+    # encoded through the stream layer (a) the reference decoder (CRC-16 of every frame, STREAMINFO MD5) must
+    # return the input PCM and (b) the file must equal the reference encoder's, byte for byte -- SURVEY 8(d)'s
+    # correctness gate, outside the timed regions ----
     base = None
     verified = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -432,16 +761,27 @@ def main():
             vn = min(n_frames_pcm, int(args.verify_seconds * SAMPLE_RATE))
             host = np.empty(vn * frame_bytes, dtype=np.uint8)
             L.b200flac_device_download(dev, host.ctypes.data, d_pcm, vn * frame_bytes)
-            shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
             with tempfile.TemporaryDirectory(dir=shm) as vd:
                 vpath = os.path.join(vd, "v.flac")
                 b200flac.encode_file(vpath, params, host, vn)
                 r = subprocess.run([REF_FLACDEC, vpath], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
                 ok = r.returncode == 0 and r.stdout == host.tobytes()
+                ppath, rpath = os.path.join(vd, "v.pcm"), os.path.join(vd, "ref.flac")
+                host.tofile(ppath)
+                flags = ["-c", str(CHANNELS), "-r", str(SAMPLE_RATE), "-b", str(BPS), "-B", str(BLOCK), "-l", str(LPC),
+                         "-R", str(PO), "-M"]
+                rr = subprocess.run([REF_FLACENC] + flags + [rpath], stdin=open(ppath, "rb"),
+                                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                ours, theirs = open(vpath, "rb").read(), open(rpath, "rb").read() if rr.returncode == 0 else b""
                 verified = {"decoder": "oracle/_ref/flacdec (reference src/decoders/flac.c)", "seconds": vn / SAMPLE_RATE,
-                            "lossless": bool(ok), "file_bytes": os.path.getsize(vpath)}
+                            "lossless": bool(ok), "file_bytes": len(ours),
+                            "encoder": "oracle/_ref/flacenc (reference src/encoders/flac.c) on the same PCM and options",
+                            "reference_file_bytes": len(theirs), "identical_to_reference_file": bool(ours == theirs),
+                            "size_ratio_to_reference": len(ours) / len(theirs) if theirs else None}
             if not ok:
                 raise SystemExit("correctness gate failed: the reference decoder did not return the input PCM")
+            if ours != theirs:
+                raise SystemExit("correctness gate failed: the file differs from the reference encoder's")
         if base is not None:
             base["checked"] = verified
 
@@ -457,15 +797,19 @@ def main():
                        "compressed_ratio": out_bytes / pcm_bytes,
                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (pcm_bytes / 1e6),
                        "sharding": "frame range per GPU, no collective"},
-            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "e2e_frame_layer": e2e_frame,
+            "api": api, "configs": configs, "sharded_stream": sharded, "gpu_launches": int(launches),
             "full_check": full_check,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
                        "samples": clk["samples"], "samples_in_timed_regions": clk["samples_in_timed_regions"]},
         }
         emit(line)
+    if h_pcm:
+        L.b200flac_host_free(h_pcm)
     L.b200flac_device_free(dev, d_pcm)
     L.b200flac_device_free(dev, d_out)
     enc.close()
+    tmp.cleanup()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -133,10 +133,20 @@ int b200flac_encoder_encode_device(b200flac_encoder *enc, int slot, const void *
  * [0] lpc model (window/autocorrelation, then Levinson/quantise), [1] subframe analysis,
  * [2] frame select + offset scan (+ output clear on the k_pack_v2 path), [3] frame packing
  * (k_pack_v3 computes the CRC-16 here too), [4] the separate CRC-16 kernel of the k_pack_v2 path (else ~0).
- * Returns the number of entries written. */
+ * Returns the number of entries written; 0 when the batch ran as a pipeline of chunks (kernels of different
+ * chunks overlap, so there is no per-kernel time: see b200flac_encoder_set_chunking). */
 int b200flac_encoder_last_kernel_ms(b200flac_encoder *enc, int slot, float *ms, int capacity);
+/* How a batch is scheduled on the device.  A batch of more than ~1.5 x chunk_frames FLAC frames runs as a
+ * software pipeline of chunks over three CUDA streams: the floating-point model kernels of the next
+ * `lookahead` chunks (FP64 pipe) overlap the integer analysis/packing kernels of the current one, and a chunk's
+ * PCM is re-read from L2 instead of HBM.  chunk_frames = 0: the whole batch is one chunk, kernels back to back
+ * on one stream (what b200flac_encoder_last_kernel_ms needs; the default -- on B200 the pipeline measured no faster).  Output bytes do not depend
+ * on it.  No reference counterpart (the reference encodes one frame at a time, flac.c:247-274). */
+int b200flac_encoder_set_chunking(b200flac_encoder *enc, uint32_t chunk_frames, uint32_t lookahead);
 /* number of kernel launches issued by this encoder so far */
 uint64_t b200flac_encoder_launch_count(const b200flac_encoder *enc);
+/* ... and by every encoder of this process together (the stream layer's pooled encoders included) */
+uint64_t b200flac_launch_count_total(void);
 
 /* page-locked host memory: PCM handed to submit() from such memory (or from
  * b200flac_encoder_slot_pcm) is copied host->device directly and asynchronously;
@@ -279,7 +289,8 @@ int b200flac_encode_aiff(const char *flac_filename, const char *aiff_filename, c
  * Frame-parallel restatement of the reference decoder, src/decoders/flac.c:174-286 (FlacDecoder_read),
  * :569-1270 (metadata, frame header, subframes, residuals, channel decorrelation) and :1340-1510 (flacdec):
  * every position holding a header that is valid for the stream is decoded speculatively by its own GPU
- * thread, the host follows the chain of frame ends as the reference's loop would, and a last kernel
+ * thread, the chain of frame ends is resolved on the device (the host walks it, as the reference's loop would,
+ * only for streams the device chain does not vouch for), and a last kernel
  * writes the interleaved PCM (signed little-endian, the bytes the STREAMINFO MD5 is taken over).
  * Return codes: 0; 1 = the reference raises ValueError (flacdec: "*** Error: <text>"), 2 = IOError
  * (EOF), 3 = engine error; b200flac_last_error() holds the reference's message text

@@ -2,7 +2,12 @@
 """Turns an .ncu-rep (ncu --set full) into the per-kernel text summary committed under profiles/.
 
     python profiles/summarize_ncu.py gpurun_out/prof_r01.ncu-rep > profiles/r01_xxx_summary.txt
+    python profiles/summarize_ncu.py gpurun_out/prof_r02.ncu-rep --json profiles/r02_traffic.json > ...
+
+--json also writes, per kernel, the DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum),
+its duration and issue-slot utilisation: the file bench.py reads `roofline.traffic` from.
 """
+import json
 import csv
 import io
 import subprocess
@@ -33,6 +38,26 @@ def main():
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     stall = [h for h in hdr if h.startswith("smsp__average_warp") and "issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
+    def num(r, name):
+        try:
+            v = float(r[idx[name]])
+        except (KeyError, ValueError):
+            return None
+        u = units[idx[name]].lower()
+        scale = {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}
+        return v * scale.get(u, 1.0)
+    if "--json" in sys.argv:
+        out = {"source": rep.split("/")[-1], "how": "ncu --set full --clock-control none, one launch per kernel", "kernels": {}}
+        for r in rows[2:]:
+            name = r[idx["Kernel Name"]]
+            short = name.split("(")[0].replace("void ", "").strip()
+            rd, wr = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum")
+            out["kernels"][short] = {"dram_bytes": (rd or 0) + (wr or 0), "dram_bytes_read": rd, "dram_bytes_write": wr,
+                                     "duration_ms": num(r, "gpu__time_duration.sum"),
+                                     "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                     "inst_executed": num(r, "smsp__inst_executed.sum")}
+        with open(sys.argv[sys.argv.index("--json") + 1], "w") as fh:
+            json.dump(out, fh, indent=1)
     for r in rows[2:]:
         print("=" * 100)
         print(r[idx["Kernel Name"]][:160])

@@ -96,8 +96,11 @@ def lib():
     L.b200flac_encoder_encode_device.argtypes = [vp, C.c_int, vp, C.POINTER(Segment), C.c_uint32, vp,
                                                  C.c_uint64, u64p, u32p, C.POINTER(C.c_float)]
     L.b200flac_encoder_last_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_int]
+    L.b200flac_encoder_set_chunking.restype = C.c_int
+    L.b200flac_encoder_set_chunking.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.b200flac_encoder_launch_count.restype = C.c_uint64
     L.b200flac_encoder_launch_count.argtypes = [vp]
+    L.b200flac_launch_count_total.restype = C.c_uint64
     L.b200flac_host_alloc.restype = vp
     L.b200flac_host_alloc.argtypes = [C.c_uint64]
     L.b200flac_host_free.argtypes = [vp]
@@ -234,6 +237,11 @@ class Encoder(object):
         ms = (C.c_float * 8)()
         n = lib().b200flac_encoder_last_kernel_ms(self.h, slot, ms, 8)
         return [ms[i] for i in range(n)]
+
+    def set_chunking(self, chunk_frames, lookahead=3):
+        """frames per pipeline chunk (0: one chunk per batch, kernels back to back: per-kernel times exist)"""
+        if lib().b200flac_encoder_set_chunking(self.h, chunk_frames, lookahead):
+            raise _err()
 
     def launch_count(self):
         return lib().b200flac_encoder_launch_count(self.h)

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <vector>
 
@@ -33,6 +34,16 @@
 #define BF_SMEM_OPTIN (200 * 1024)
 #define BF_MAX_SEGMENTS 65536
 #define BF_NUM_EVENTS 6
+#define BF_MAX_CHUNKS 64
+#define BF_MAX_MODEL_STREAMS 8
+
+// A batch runs as a pipeline of chunks: contiguous frame ranges, each a mini-batch of its own (every per-frame
+// and per-unit array is addressed from the chunk's first frame; task and odd-frame lists are chunk-relative).
+struct Chunk {
+    u32 frame0, n_frames;
+    u32 task0, n_tasks;
+    u32 odd0, n_odd;
+};
 
 static thread_local char g_err[512] = "";
 
@@ -90,6 +101,14 @@ struct Slot {
     bool busy = false;
     bool timed = false;
     std::vector<u32> frame_pcm;
+    // the software pipeline over chunks of a batch (see launch_batch)
+    cudaStream_t stream_b = nullptr;     // second analysis/packing stream (odd chunks)
+    cudaStream_t stream_hi[BF_MAX_MODEL_STREAMS] = {};   // streams of the floating-point model kernels
+    cudaStream_t stream_lo[BF_MAX_MODEL_STREAMS] = {};   // ... the same at normal priority (tuning)
+    cudaEvent_t ev_in = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_model[BF_MAX_CHUNKS] = {}, ev_an[BF_MAX_CHUNKS] = {}, ev_scan[BF_MAX_CHUNKS] = {};
+    u64* d_chunk_tot = nullptr;          // running output size after each chunk
+    std::vector<Chunk> chunks;
 };
 
 struct b200flac_encoder {
@@ -118,7 +137,21 @@ struct b200flac_encoder {
     u64 launches;
     int lpc_occ[2];       // resident one-warp CTAs per SM of k_lpc_autoc (G = 1, 2)
     int n_sms;
+    u32 chunk_frames;     // frames per pipeline chunk (0: a batch is one chunk, kernels back to back on one stream)
+    u32 lookahead;        // chunks the model streams may run ahead of the analysis
+    u32 model_streams;    // streams the model kernels of consecutive chunks rotate over
+    u32 model_priority;   // 1: those streams have high priority
+    u32 lpc_grid_cap;     // pipeline: at most this many one-warp CTAs per model launch (0: one per task)
 };
+
+// kernel launches of this process (every encoder, every thread): what bench.py reports as gpu_launches
+static std::atomic<unsigned long long> g_launches_total(0);
+static inline void count_launches(b200flac_encoder* enc, u64 k)
+{
+    enc->launches += k;
+    g_launches_total.fetch_add(k, std::memory_order_relaxed);
+}
+extern "C" uint64_t b200flac_launch_count_total(void) { return g_launches_total.load(); }
 
 // ---- derived options ------------------------------------------------------
 static u32 sample_rate_code(u32 sr) // flac.c:452-476
@@ -257,7 +290,20 @@ extern "C" uint64_t b200flac_encoder_output_bound(const b200flac_encoder* enc, u
 static void free_slot(Slot& s)
 {
     if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.stream_b) { cudaStreamSynchronize(s.stream_b); cudaStreamDestroy(s.stream_b); }
+    for (int i = 0; i < BF_MAX_MODEL_STREAMS; i++) {
+        if (s.stream_hi[i]) { cudaStreamSynchronize(s.stream_hi[i]); cudaStreamDestroy(s.stream_hi[i]); }
+        if (s.stream_lo[i]) { cudaStreamSynchronize(s.stream_lo[i]); cudaStreamDestroy(s.stream_lo[i]); }
+    }
     for (int i = 0; i < BF_NUM_EVENTS; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+    if (s.ev_in) cudaEventDestroy(s.ev_in);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
+    for (int i = 0; i < BF_MAX_CHUNKS; i++) {
+        if (s.ev_model[i]) cudaEventDestroy(s.ev_model[i]);
+        if (s.ev_an[i]) cudaEventDestroy(s.ev_an[i]);
+        if (s.ev_scan[i]) cudaEventDestroy(s.ev_scan[i]);
+    }
+    cudaFree(s.d_chunk_tot);
     if (s.h_pcm) cudaFreeHost(s.h_pcm);
     if (s.h_fd) cudaFreeHost(s.h_fd);
     if (s.h_win) cudaFreeHost(s.h_win);
@@ -351,6 +397,14 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
     enc->slots = nullptr;
     enc->windows = new std::map<u32, std::vector<double>>();
     enc->launches = 0;
+    enc->chunk_frames = 0;     // one chunk: the pipeline measured no faster on B200
+    enc->lookahead = 3;
+    enc->model_streams = 4; enc->model_priority = 1; enc->lpc_grid_cap = 0;
+    if (getenv("B200FLAC_NH")) enc->model_streams = (u32)atoi(getenv("B200FLAC_NH"));
+    if (getenv("B200FLAC_LPC_PRIO")) enc->model_priority = (u32)atoi(getenv("B200FLAC_LPC_PRIO"));
+    if (getenv("B200FLAC_LPC_GRID")) enc->lpc_grid_cap = (u32)atoi(getenv("B200FLAC_LPC_GRID"));
+    if (getenv("B200FLAC_CHUNK")) enc->chunk_frames = (u32)atoi(getenv("B200FLAC_CHUNK"));        // tuning knobs
+    if (getenv("B200FLAC_LOOKAHEAD")) enc->lookahead = (u32)std::max(1, atoi(getenv("B200FLAC_LOOKAHEAD")));
     const bf_dev_params& P = enc->P;
 
     const u32 bs = params->block_size;
@@ -547,7 +601,7 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         if (P.try_lpc) {
             ALLOC(s.d_autoc, U * (size_t)(lpc_maxl(P.max_lpc_order) + 1) * sizeof(double));
             ALLOC(s.d_lpc_wasted, U);
-            ALLOC(s.d_ticket, 64);
+            ALLOC(s.d_ticket, BF_MAX_CHUNKS * sizeof(u32));
             ALLOCH(s.h_tasks, maxf * sizeof(bf_lpc_task));
             ALLOC(s.d_tasks, maxf * sizeof(bf_lpc_task));
         }
@@ -557,6 +611,7 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         ALLOC(s.d_frame_bytes, maxf * sizeof(u32));
         ALLOC(s.d_frame_off, maxf * sizeof(u64));
         ALLOC(s.d_total, 64);
+        ALLOC(s.d_chunk_tot, BF_MAX_CHUNKS * sizeof(u64));
         ALLOCH(s.h_frame_bytes, maxf * sizeof(u32));
         ALLOCH(s.h_total, 64);
         if (!P.samples_in_smem) ALLOC(s.d_gsamples, U * 2 * (size_t)P.samp_stride * sizeof(int));
@@ -672,21 +727,48 @@ static long build_batch(b200flac_encoder* enc, Slot& s, const b200flac_segment* 
         }
     }
     if (need > enc->max_pcm_frames) { set_err("batch has more PCM frames than the encoder was created for"); return -1; }
-    s.n_odd = 0;
-    for (u64 f = 0; f < nf; f++) if (s.h_fd[f].nsamp != bs) s.h_odd[s.n_odd++] = (u32)f;
-    if (want_windows) {
-        // tasks of the autocorrelation kernel: runs of up to 32/K consecutive frames of one length
-        const u32 per = 32 / enc->P.K;
-        u32 nt = 0;
-        for (u64 f = 0; f < nf;) {
-            u32 c = 1;
-            while (c < per && f + c < nf && s.h_fd[f + c].nsamp == s.h_fd[f].nsamp) c++;
-            s.h_tasks[nt].first_frame = (u32)f;
-            s.h_tasks[nt].n_frames = c;
-            nt++;
-            f += c;
+    // ---- chunks of the pipeline: frame ranges of about chunk_frames frames; every list below is cut at the
+    // chunk boundaries and holds indices relative to its chunk's first frame ----
+    s.chunks.clear();
+    {
+        u32 per_chunk = (u32)nf;
+        if (enc->fast && enc->p3 && enc->chunk_frames && nf >= (u64)enc->chunk_frames + enc->chunk_frames / 2) {
+            per_chunk = enc->chunk_frames;
+            const u32 floor_ = (u32)((nf + BF_MAX_CHUNKS - 1) / BF_MAX_CHUNKS);
+            if (per_chunk < floor_) per_chunk = floor_;
         }
-        s.n_tasks = nt;
+        for (u64 f = 0; f < nf; f += per_chunk) {
+            Chunk c;
+            memset(&c, 0, sizeof(c));
+            c.frame0 = (u32)f;
+            c.n_frames = (u32)std::min<u64>(per_chunk, nf - f);
+            // (a short last chunk joins its predecessor)
+            if (nf - f - c.n_frames < per_chunk / 2) c.n_frames = (u32)(nf - f);
+            s.chunks.push_back(c);
+            if (c.n_frames != per_chunk) break;
+        }
+    }
+    s.n_odd = 0;
+    s.n_tasks = 0;
+    for (Chunk& c : s.chunks) {
+        c.odd0 = s.n_odd;
+        for (u32 f = 0; f < c.n_frames; f++) if (s.h_fd[c.frame0 + f].nsamp != bs) s.h_odd[s.n_odd++] = f;
+        c.n_odd = s.n_odd - c.odd0;
+        c.task0 = s.n_tasks;
+        if (want_windows) {
+            // tasks of the autocorrelation kernel: runs of up to 32/K consecutive frames of one length
+            const u32 per = 32 / enc->P.K;
+            const bf_frame_desc* fd = s.h_fd + c.frame0;
+            for (u32 f = 0; f < c.n_frames;) {
+                u32 k = 1;
+                while (k < per && f + k < c.n_frames && fd[f + k].nsamp == fd[f].nsamp) k++;
+                s.h_tasks[s.n_tasks].first_frame = f;
+                s.h_tasks[s.n_tasks].n_frames = k;
+                s.n_tasks++;
+                f += k;
+            }
+        }
+        c.n_tasks = s.n_tasks - c.task0;
     }
     *pcm_frames_needed = need;
     s.n_frames = (u32)nf;
@@ -714,54 +796,162 @@ static void launch_analyze_pack(b200flac_encoder* enc, Slot& s, const uint8_t* d
     cudaEventRecord(s.ev[4], st);
     k_frame_crc16<<<(nf * 32 + 127) / 128, 128, 0, st>>>(s.d_frame_off, s.d_frame_bytes, nf, d_out, s.d_total, out_cap);
     cudaEventRecord(s.ev[5], st);
-    enc->launches += 6;
+    count_launches(enc, 6);
 }
 
-static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
+// the slot's arrays as one chunk sees them: from its first frame / first unit
+struct ChunkView {
+    const bf_frame_desc* fd;
+    u32 nf, U;
+    bf_lpc_head* heads;
+    short* coefs;
+    double* autoc;
+    uint8_t* wasted;
+    b200flac_plan* plans;
+    uint8_t* rice;
+    bf_frame_choice* choice;
+    u32* frame_bytes;
+    u64* frame_off;
+    const bf_lpc_task* tasks;
+    u32 n_tasks;
+    const u32* odd;
+    u32 n_odd;
+    u32* ticket;
+};
+
+static ChunkView chunk_view(const b200flac_encoder* enc, const Slot& s, u32 ci)
 {
     const bf_dev_params& P = enc->P;
-    const u32 nf = s.n_frames, U = nf * P.K;
-    cudaStream_t st = s.stream;
-    u32 gridv2 = U;
+    const Chunk& c = s.chunks[ci];
+    const size_t u0 = (size_t)c.frame0 * P.K;
+    ChunkView v;
+    v.fd = s.d_fd + c.frame0;
+    v.nf = c.n_frames;
+    v.U = c.n_frames * P.K;
+    v.heads = s.d_heads + u0;
+    v.coefs = s.d_coefs + u0 * P.model_stride;
+    v.autoc = s.d_autoc ? s.d_autoc + u0 * (lpc_maxl(P.max_lpc_order) + 1) : nullptr;
+    v.wasted = s.d_lpc_wasted ? s.d_lpc_wasted + u0 : nullptr;
+    v.plans = s.d_plans + u0;
+    v.rice = s.d_rice + u0 * P.rice_stride;
+    v.choice = s.d_choice + c.frame0;
+    v.frame_bytes = s.d_frame_bytes + c.frame0;
+    v.frame_off = s.d_frame_off + c.frame0;
+    v.tasks = s.d_tasks ? s.d_tasks + c.task0 : nullptr;
+    v.n_tasks = c.n_tasks;
+    v.odd = s.d_odd + c.odd0;
+    v.n_odd = c.n_odd;
+    v.ticket = s.d_ticket ? s.d_ticket + ci : nullptr;
+    return v;
+}
+
+// window + autocorrelation, then Levinson-Durbin / order estimate / quantisation, of one chunk
+static void stage_model(b200flac_encoder* enc, const ChunkView& v, cudaStream_t st, const uint8_t* d_pcm,
+                        const double* d_win, bool piped)
+{
+    const bf_dev_params& P = enc->P;
+    // persistent one-warp CTAs drawing (32 units, lag group) tasks from a ticket counter; the lag
+    // split halves a thread's sequential work, which is what a small batch's duration is made of --
+    // inside the pipeline the other chunks' kernels fill the machine, so the split's duplicated unpacking
+    // is not paid there
+    const u32 maxl = lpc_maxl(P.max_lpc_order);
+    const u32 groups = v.n_tasks;
+    bool split = maxl == 32 || (!piped && groups < (u32)enc->n_sms * 12u);
+    if (getenv("B200FLAC_LPC_G") && maxl != 32) split = atoi(getenv("B200FLAC_LPC_G")) == 2; // tuning knob
+    const u32 G = split ? 2 : 1;
+    const u32 n_tasks = groups * G;
+    const int occ = enc->lpc_occ[G - 1] > 0 ? enc->lpc_occ[G - 1] : 1;
+    size_t lsm = lpc_geometry(P.K, P.channels * P.bytes_ps, maxl + 1).smem_bytes;
+    u32 grid = (u32)enc->n_sms * (u32)occ;
+    if (piped && enc->lpc_grid_cap && grid > enc->lpc_grid_cap) grid = enc->lpc_grid_cap;
+    if (n_tasks < grid) {
+        grid = n_tasks;
+        if (!piped) {
+            // few tasks: the block scheduler fills an SM before it moves to the next, so pad the
+            // shared-memory request until only ceil(tasks / SMs) CTAs fit on one
+            const u32 per_sm = (n_tasks + enc->n_sms - 1) / enc->n_sms;
+            const size_t pad = (size_t)(220 * 1024) / per_sm - 1024;
+            if (pad > lsm) lsm = pad < (size_t)(200 * 1024) ? pad : (size_t)(200 * 1024);
+        }
+    }
+#define LPC_LAUNCH(MAXL_, G_) k_lpc_autoc<MAXL_, G_><<<grid, 32, lsm, st>>>(d_pcm, v.fd, v.nf, d_win, P, v.tasks, n_tasks, v.ticket, v.autoc, v.wasted)
+    if (maxl == 8) { if (split) LPC_LAUNCH(8, 2); else LPC_LAUNCH(8, 1); }
+    else if (maxl == 12) { if (split) LPC_LAUNCH(12, 2); else LPC_LAUNCH(12, 1); }
+    else if (maxl == 16) { if (split) LPC_LAUNCH(16, 2); else LPC_LAUNCH(16, 1); }
+    else LPC_LAUNCH(32, 2);
+#undef LPC_LAUNCH
+    const u32 fb = (v.U + 127) / 128;
+    if (maxl == 8) k_lpc_finish<8><<<fb, 128, 0, st>>>(v.fd, v.nf, P, v.autoc, v.wasted, v.heads, v.coefs);
+    else if (maxl == 12) k_lpc_finish<12><<<fb, 128, 0, st>>>(v.fd, v.nf, P, v.autoc, v.wasted, v.heads, v.coefs);
+    else if (maxl == 16) k_lpc_finish<16><<<fb, 128, 0, st>>>(v.fd, v.nf, P, v.autoc, v.wasted, v.heads, v.coefs);
+    else k_lpc_finish<32><<<fb, 128, 0, st>>>(v.fd, v.nf, P, v.autoc, v.wasted, v.heads, v.coefs);
+    count_launches(enc, 2);
+}
+
+// model search of one chunk (fast kernels)
+static void stage_analyze(b200flac_encoder* enc, const ChunkView& v, cudaStream_t st, const uint8_t* d_pcm)
+{
+    const bf_dev_params& P = enc->P;
+    u32 gridv2 = v.U;
     const u32* flist = nullptr;
     if (enc->v3) {
         // one CTA per unit.  (The kernel also runs as a persistent grid -- B200FLAC_V3_GRID=740 is one wave
         // -- but CTAs that start together stay in the same phase of the unit and overlap their load and
         // search phases worse: 3.16 ms against 2.87 ms per hour on B200.)
-        u32 g3 = U;
+        u32 g3 = v.U;
         if (getenv("B200FLAC_V3_GRID")) g3 = (u32)atoi(getenv("B200FLAC_V3_GRID"));   // tuning knob
-        if (g3 > U || g3 == 0) g3 = U;
-#define V3_LAUNCH(MINB_, EXH_, SC_) k_analyze_v3<MINB_, EXH_, SC_><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, s.d_fd, P, enc->v3_S, enc->v3_F, U, s.d_heads, s.d_coefs, s.d_plans, s.d_rice)
+        if (g3 > v.U || g3 == 0) g3 = v.U;
+#define V3_LAUNCH(MINB_, EXH_, SC_) k_analyze_v3<MINB_, EXH_, SC_><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice)
         if (enc->v3_NT <= 128 && enc->v3_S == 32) { if (P.exhaustive) V3_LAUNCH(5, true, 32); else V3_LAUNCH(5, false, 32); }
         else if (enc->v3_NT <= 128) { if (P.exhaustive) V3_LAUNCH(5, true, 0); else V3_LAUNCH(5, false, 0); }
         else if (enc->v3_NT <= 256) { if (P.exhaustive) V3_LAUNCH(3, true, 0); else V3_LAUNCH(3, false, 0); }
         else { if (P.exhaustive) V3_LAUNCH(1, true, 0); else V3_LAUNCH(1, false, 0); }
 #undef V3_LAUNCH
-        enc->launches += 1;
-        gridv2 = s.n_odd * P.K;      // the other block lengths (a stream's last block)
-        flist = s.d_odd;
+        count_launches(enc, 1);
+        gridv2 = v.n_odd * P.K;      // the other block lengths (a stream's last block)
+        flist = v.odd;
     }
     if (gridv2) {
         if (enc->NT <= 192)
-            k_analyze_v2<192, 4><<<gridv2, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice, flist);
+            k_analyze_v2<192, 4><<<gridv2, enc->NT, enc->smem_analyze, st>>>(d_pcm, v.fd, P, (u32)enc->S, v.heads, v.coefs, v.plans, v.rice, flist);
         else
-            k_analyze_v2<512, 1><<<gridv2, enc->NT, enc->smem_analyze, st>>>(d_pcm, s.d_fd, P, (u32)enc->S, s.d_heads, s.d_coefs, s.d_plans, s.d_rice, flist);
+            k_analyze_v2<512, 1><<<gridv2, enc->NT, enc->smem_analyze, st>>>(d_pcm, v.fd, P, (u32)enc->S, v.heads, v.coefs, v.plans, v.rice, flist);
+        count_launches(enc, 1);
     }
+}
+
+static void stage_pack_v3(b200flac_encoder* enc, const ChunkView& v, cudaStream_t st, const uint8_t* d_pcm,
+                          uint8_t* d_out, u64 out_cap, const u64* d_total)
+{
+    const bf_dev_params& P = enc->P;
+#define P3_LAUNCH(NTMAX_, MINB_, SC_) k_pack_v3<NTMAX_, MINB_, SC_><<<v.nf, 2 * enc->NT, enc->p3_smem, st>>>( \
+            d_pcm, v.fd, P, (u32)enc->S, v.plans, v.rice, v.choice, v.frame_off, d_out, d_total, out_cap, \
+            enc->p3_img_words, enc->d_crc_tab, enc->d_crc_tab + 512)
+    if (2 * enc->NT <= 256 && enc->S == 32) P3_LAUNCH(256, 4, 32);
+    else if (2 * enc->NT <= 256) P3_LAUNCH(256, 4, 0);
+    else P3_LAUNCH(1024, 1, 0);
+#undef P3_LAUNCH
+    count_launches(enc, 1);
+}
+
+// the fast kernels of a batch that is a single chunk: back to back on the slot's stream, one event between
+// stages (b200flac_encoder_last_kernel_ms)
+static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
+{
+    const bf_dev_params& P = enc->P;
+    const ChunkView v = chunk_view(enc, s, 0);
+    const u32 nf = v.nf;
+    cudaStream_t st = s.stream;
+    stage_analyze(enc, v, st, d_pcm);
     cudaEventRecord(s.ev[2], st);
     k_frame_select<<<(nf + 127) / 128, 128, 0, st>>>(s.d_fd, nf, P, s.d_plans, s.d_choice, s.d_frame_bytes);
     k_scan_offsets<<<1, 1024, 0, st>>>(s.d_frame_bytes, nf, s.d_frame_off, s.d_total);
+    count_launches(enc, 2);
     if (enc->p3) {
         cudaEventRecord(s.ev[3], st);
-#define P3_LAUNCH(NTMAX_, MINB_, SC_) k_pack_v3<NTMAX_, MINB_, SC_><<<nf, 2 * enc->NT, enc->p3_smem, st>>>( \
-            d_pcm, s.d_fd, P, (u32)enc->S, s.d_plans, s.d_rice, s.d_choice, s.d_frame_off, d_out, s.d_total, out_cap, \
-            enc->p3_img_words, enc->d_crc_tab, enc->d_crc_tab + 512)
-        if (2 * enc->NT <= 256 && enc->S == 32) P3_LAUNCH(256, 4, 32);
-        else if (2 * enc->NT <= 256) P3_LAUNCH(256, 4, 0);
-        else P3_LAUNCH(1024, 1, 0);
-#undef P3_LAUNCH
+        stage_pack_v3(enc, v, st, d_pcm, d_out, out_cap, s.d_total);
         cudaEventRecord(s.ev[4], st);
         cudaEventRecord(s.ev[5], st);
-        enc->launches += 3 + (gridv2 ? 1 : 0);
         return;
     }
     k_zero_output<<<148 * 4, 256, 0, st>>>((uint4*)d_out, s.d_total, out_cap);
@@ -777,49 +967,91 @@ static void launch_analyze_pack_v2(b200flac_encoder* enc, Slot& s, const uint8_t
     cudaEventRecord(s.ev[4], st);
     k_frame_crc16<<<(nf * 32 + 127) / 128, 128, 0, st>>>(s.d_frame_off, s.d_frame_bytes, nf, d_out, s.d_total, out_cap);
     cudaEventRecord(s.ev[5], st);
-    enc->launches += 5 + (gridv2 ? 1 : 0);
+    count_launches(enc, 3);
 }
 
-// enqueue the kernels of one batch on the slot's stream
+// streams and events of the chunk pipeline, created on a slot's first pipelined batch
+static int ensure_pipeline(Slot& s)
+{
+    if (s.stream_b) return 0;
+    int lo = 0, hi = 0;
+    CU_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi), 1);
+    CU_CHECK(cudaStreamCreateWithFlags(&s.stream_b, cudaStreamNonBlocking), 1);
+    for (int i = 0; i < BF_MAX_MODEL_STREAMS; i++) {
+        CU_CHECK(cudaStreamCreateWithPriority(&s.stream_hi[i], cudaStreamNonBlocking, hi), 1);
+        CU_CHECK(cudaStreamCreateWithFlags(&s.stream_lo[i], cudaStreamNonBlocking), 1);
+    }
+    CU_CHECK(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming), 1);
+    CU_CHECK(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming), 1);
+    for (int i = 0; i < BF_MAX_CHUNKS; i++) {
+        CU_CHECK(cudaEventCreateWithFlags(&s.ev_model[i], cudaEventDisableTiming), 1);
+        CU_CHECK(cudaEventCreateWithFlags(&s.ev_an[i], cudaEventDisableTiming), 1);
+        CU_CHECK(cudaEventCreateWithFlags(&s.ev_scan[i], cudaEventDisableTiming), 1);
+    }
+    return 0;
+}
+
+// A batch of several chunks as a software pipeline over three streams.  The floating-point model kernels
+// (FP64 pipe) of chunk c + 1 .. c + lookahead run on a high-priority stream while the integer kernels (ALU /
+// FMA pipes) of chunk c run on two alternating streams, so the pipes that sat idle in turn are busy together,
+// and a chunk's PCM (~33 MB) is still in the 126 MB L2 when its second and third readers come.  The frame
+// offsets are chained through the per-chunk running totals (k_scan_offsets' carry-in).
+static int launch_pipeline(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
+{
+    const bf_dev_params& P = enc->P;
+    if (ensure_pipeline(s)) return 1;
+    const u32 NC = (u32)s.chunks.size();
+    cudaStream_t main_st = s.stream;
+    u32 NH = enc->model_streams;
+    if (NH < 1) NH = 1;
+    if (NH > BF_MAX_MODEL_STREAMS) NH = BF_MAX_MODEL_STREAMS;
+    cudaStream_t* hs = enc->model_priority ? s.stream_hi : s.stream_lo;
+    const u32 la = std::max(enc->lookahead, NH);
+    if (P.try_lpc) cudaMemsetAsync(s.d_ticket, 0, NC * sizeof(u32), main_st);
+    cudaEventRecord(s.ev_in, main_st);                 // inputs (PCM, descriptors, tasks, windows) are on the device
+    cudaStreamWaitEvent(s.stream_b, s.ev_in, 0);
+    if (P.try_lpc) for (u32 h = 0; h < NH; h++) cudaStreamWaitEvent(hs[h], s.ev_in, 0);
+    for (u32 ci = 0; ci < NC; ci++) {
+        const ChunkView v = chunk_view(enc, s, ci);
+        cudaStream_t st = (ci & 1) ? s.stream_b : main_st;
+        if (P.try_lpc) {
+            cudaStream_t h = hs[ci % NH];
+            if (ci >= la) cudaStreamWaitEvent(h, s.ev_an[ci - la], 0);
+            stage_model(enc, v, h, d_pcm, s.d_win, true);
+            cudaEventRecord(s.ev_model[ci], h);
+            cudaStreamWaitEvent(st, s.ev_model[ci], 0);
+        }
+        stage_analyze(enc, v, st, d_pcm);
+        cudaEventRecord(s.ev_an[ci], st);
+        k_frame_select<<<(v.nf + 127) / 128, 128, 0, st>>>(v.fd, v.nf, P, v.plans, v.choice, v.frame_bytes);
+        if (ci) cudaStreamWaitEvent(st, s.ev_scan[ci - 1], 0);
+        k_scan_offsets<<<1, 1024, 0, st>>>(v.frame_bytes, v.nf, v.frame_off, s.d_chunk_tot + ci,
+                                           ci ? s.d_chunk_tot + ci - 1 : nullptr, ci + 1 == NC ? s.d_total : nullptr);
+        cudaEventRecord(s.ev_scan[ci], st);
+        stage_pack_v3(enc, v, st, d_pcm, d_out, out_cap, s.d_chunk_tot + ci);
+        count_launches(enc, 2);
+    }
+    cudaEventRecord(s.ev_join, s.stream_b);
+    cudaStreamWaitEvent(main_st, s.ev_join, 0);
+    for (int i = 1; i <= 5; i++) cudaEventRecord(s.ev[i], main_st);
+    return 0;
+}
+
+// enqueue the kernels of one batch
 static int launch_batch(b200flac_encoder* enc, Slot& s, const uint8_t* d_pcm, uint8_t* d_out, u64 out_cap)
 {
     const bf_dev_params& P = enc->P;
-    const u32 nf = s.n_frames, U = nf * P.K;
     cudaStream_t st = s.stream;
     cudaEventRecord(s.ev[0], st);
+    if (s.chunks.size() > 1) {
+        if (launch_pipeline(enc, s, d_pcm, d_out, out_cap)) return 1;
+        CU_CHECK(cudaGetLastError(), 1);
+        s.timed = false;          // kernels of different chunks overlap: there is no per-kernel time
+        return 0;
+    }
     if (P.try_lpc) {
-        // persistent one-warp CTAs drawing (32 units, lag group) tasks from a ticket counter; the lag
-        // split halves a thread's sequential work, which is what a small batch's duration is made of
-        const u32 maxl = lpc_maxl(P.max_lpc_order);
-        const u32 groups = s.n_tasks;
-        bool split = maxl == 32 || groups < (u32)enc->n_sms * 12u;
-        if (getenv("B200FLAC_LPC_G") && maxl != 32) split = atoi(getenv("B200FLAC_LPC_G")) == 2; // tuning knob
-        const u32 G = split ? 2 : 1;
-        const u32 n_tasks = groups * G;
-        const int occ = enc->lpc_occ[G - 1] > 0 ? enc->lpc_occ[G - 1] : 1;
-        size_t lsm = lpc_geometry(P.K, P.channels * P.bytes_ps, maxl + 1).smem_bytes;
-        u32 grid = (u32)enc->n_sms * (u32)occ;
-        if (n_tasks < grid) {
-            // few tasks: the block scheduler fills an SM before it moves to the next, so pad the
-            // shared-memory request until only ceil(tasks / SMs) CTAs fit on one
-            grid = n_tasks;
-            const u32 per_sm = (n_tasks + enc->n_sms - 1) / enc->n_sms;
-            const size_t pad = (size_t)(220 * 1024) / per_sm - 1024;
-            if (pad > lsm) lsm = pad < (size_t)(200 * 1024) ? pad : (size_t)(200 * 1024);
-        }
         cudaMemsetAsync(s.d_ticket, 0, sizeof(u32), st);
-#define LPC_LAUNCH(MAXL_, G_) k_lpc_autoc<MAXL_, G_><<<grid, 32, lsm, st>>>(d_pcm, s.d_fd, nf, s.d_win, P, s.d_tasks, n_tasks, s.d_ticket, s.d_autoc, s.d_lpc_wasted)
-        if (maxl == 8) { if (split) LPC_LAUNCH(8, 2); else LPC_LAUNCH(8, 1); }
-        else if (maxl == 12) { if (split) LPC_LAUNCH(12, 2); else LPC_LAUNCH(12, 1); }
-        else if (maxl == 16) { if (split) LPC_LAUNCH(16, 2); else LPC_LAUNCH(16, 1); }
-        else LPC_LAUNCH(32, 2);
-#undef LPC_LAUNCH
-        const u32 fb = (U + 127) / 128;
-        if (maxl == 8) k_lpc_finish<8><<<fb, 128, 0, st>>>(s.d_fd, nf, P, s.d_autoc, s.d_lpc_wasted, s.d_heads, s.d_coefs);
-        else if (maxl == 12) k_lpc_finish<12><<<fb, 128, 0, st>>>(s.d_fd, nf, P, s.d_autoc, s.d_lpc_wasted, s.d_heads, s.d_coefs);
-        else if (maxl == 16) k_lpc_finish<16><<<fb, 128, 0, st>>>(s.d_fd, nf, P, s.d_autoc, s.d_lpc_wasted, s.d_heads, s.d_coefs);
-        else k_lpc_finish<32><<<fb, 128, 0, st>>>(s.d_fd, nf, P, s.d_autoc, s.d_lpc_wasted, s.d_heads, s.d_coefs);
-        enc->launches += 2;
+        stage_model(enc, chunk_view(enc, s, 0), st, d_pcm, s.d_win, false);
     }
     cudaEventRecord(s.ev[1], st);
     if (enc->fast) {
@@ -947,6 +1179,18 @@ extern "C" int b200flac_encoder_last_kernel_ms(b200flac_encoder* enc, int slot, 
         cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]);
     }
     return n;
+}
+
+extern "C" int b200flac_encoder_set_chunking(b200flac_encoder* enc, uint32_t chunk_frames, uint32_t lookahead)
+{
+    if (!enc) { set_err("encoder is NULL"); return 1; }
+    for (int i = 0; i < enc->n_slots; i++) if (enc->slots[i].busy) { set_err("a slot is busy"); return 1; }
+    enc->chunk_frames = chunk_frames;
+    enc->lookahead = lookahead ? lookahead : 1;
+    if (getenv("B200FLAC_NH")) enc->model_streams = (u32)atoi(getenv("B200FLAC_NH"));            // tuning knobs
+    if (getenv("B200FLAC_LPC_PRIO")) enc->model_priority = (u32)atoi(getenv("B200FLAC_LPC_PRIO"));
+    if (getenv("B200FLAC_LPC_GRID")) enc->lpc_grid_cap = (u32)atoi(getenv("B200FLAC_LPC_GRID"));
+    return 0;
 }
 
 extern "C" uint64_t b200flac_encoder_launch_count(const b200flac_encoder* enc) { return enc ? enc->launches : 0; }

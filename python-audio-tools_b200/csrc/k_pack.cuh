@@ -79,13 +79,16 @@ __global__ void k_frame_select(const bf_frame_desc* __restrict__ fd, u32 n_frame
     frame_bytes[f] = ch.frame_bytes;
 }
 
-// single-CTA exclusive scan (n_frames is at most a few 10^5)
+// single-CTA exclusive scan (n_frames is at most a few 10^5).  carry_in: where the frames of this range start
+// in the output (the running total left by the previous chunk of the batch; NULL = 0); the new running total
+// goes to *total and, when given, *total2.
 __global__ void k_scan_offsets(const u32* __restrict__ frame_bytes, u32 n_frames, u64* __restrict__ frame_off,
-                               u64* __restrict__ total)
+                               u64* __restrict__ total, const u64* __restrict__ carry_in = nullptr,
+                               u64* __restrict__ total2 = nullptr)
 {
     __shared__ u64 red[40];
     __shared__ u64 carry;
-    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry = carry_in ? *carry_in : 0ull;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (u32 base = 0; base < n_frames; base += blockDim.x) {
@@ -115,7 +118,7 @@ __global__ void k_scan_offsets(const u32* __restrict__ frame_bytes, u32 n_frames
         if (threadIdx.x == 0) carry += red[32];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry;
+    if (threadIdx.x == 0) { *total = carry; if (total2) *total2 = carry; }
 }
 
 __global__ void k_zero_output(uint4* __restrict__ out, const u64* __restrict__ total, u64 capacity_bytes)

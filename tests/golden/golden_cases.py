@@ -74,6 +74,12 @@ for n in (4095, 4097):
     _add("fractional_%d" % n, ("synth", 1243, n), 44100, 2, 16, dict(block_size=2048, max_lpc_order=8, max_residual_partition_order=6, adaptive_mid_side=True))
 # many frames so the UTF-8 frame number grows to 2 and 3 bytes (H7)
 _add("framenum_utf8", ("synth", 1244, 16 * 2100), 44100, 1, 8, dict(block_size=16, max_lpc_order=2, max_residual_partition_order=1))
+# BASELINE.json config #1 as written: the PCM of the reference's own fixture test/1m.flac (60 s of 44.1 kHz/16-bit
+# stereo, 2,646,000 PCM frames = 645 full blocks + 4080; the fixture is digital silence, so every subframe is
+# CONSTANT and the frame-number field grows from 1 to 2 bytes at frame 128), block_size 4096, max_lpc_order 8
+for r in (3, 6):
+    _add("config1_1m_flac_R%d" % r, ("flacfile", "1m.flac"), 44100, 2, 16,
+         dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=r))
 
 
 def case_pcm(case):
@@ -87,6 +93,15 @@ def case_pcm(case):
         return helpers.wasted_bps16(g[1])
     if g[0] == "sine":
         return helpers.sine_pcm(bps, ch, g[1], case["rate"], g[2])
+    if g[0] == "flacfile":
+        # decoded by the compiled reference decoder where it exists (that is how the golden manifest was made),
+        # else by the engine's own GPU decoder; the manifest's pcm_sha256 pins either
+        with open(os.path.join(helpers.GOLDEN, "flac", g[1]), "rb") as fh:
+            data = fh.read()
+        if helpers.have_ref():
+            return helpers.ref_decode(data)
+        import b200flac
+        return b200flac.decode(data)[1]
     if g[0] == "random":
         rng = np.random.RandomState(g[1])
         lo, hi = -(1 << (g[3] - 1)), (1 << (g[3] - 1))

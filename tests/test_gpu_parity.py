@@ -70,6 +70,31 @@ def test_synth_file_identical(case, tmp_path, built):
     _check(tmp_path, pcm, rate, ch, bps, helpers.options(**o))
 
 
+@pytest.mark.parametrize("bs", [576, 1024])
+@pytest.mark.parametrize("chunk,lookahead", [(7, 1), (16, 3), (33, 2), (0, 3)])
+def test_chunk_pipeline_same_frames(chunk, lookahead, bs, built):
+    """b200flac_encoder_set_chunking: a batch run as a pipeline of chunks over three streams (model kernels
+    ahead on a high-priority stream, offsets chained through the running totals) yields the oracle's frames,
+    for chunk sizes that do and do not divide the batch, with short blocks (two segment tails) inside;
+    block 576 runs on k_analyze_v2, block 1024 on k_analyze_v3 (+ v2 for the tails)"""
+    b = _b200()
+    o = helpers.options(block_size=bs, max_lpc_order=12, max_residual_partition_order=4, adaptive_mid_side=True)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 2, 16, **kw)
+    n1, n2 = bs * 83 + 100, bs * 60 + 7
+    pcm = helpers.synth_pcm(321, 2, 16, n1 + n2)
+    enc = b.Encoder(p, max_pcm_frames_per_batch=n1 + n2, n_slots=1)
+    enc.set_chunking(chunk, lookahead)
+    for _ in range(2):     # twice: the pipeline's streams and events are reused
+        out, fbytes, fpcm = enc.encode(pcm, n1 + n2, segments=[(0, n1, 0), (n1, n2, 500)])
+    w1, _ = helpers.oracle_encode_range(pcm[:n1 * 4], 44100, 2, 16, o, 0)
+    w2, _ = helpers.oracle_encode_range(pcm[n1 * 4:], 44100, 2, 16, o, 500)
+    assert out.tobytes() == w1 + w2
+    assert int(fbytes.sum()) == len(w1) + len(w2) and list(fpcm) == [bs] * 83 + [100] + [bs] * 60 + [7]
+    assert (len(enc.kernel_ms(0)) == 0) == (chunk != 0)
+    enc.close()
+
+
 def test_device_synth_matches_oracle_generator(built):
     b = _b200()
     import ctypes as C
@@ -101,6 +126,7 @@ def test_golden_reference_outputs(case, tmp_path, built):
     """the engine's file == the reference encoder's file (sha256 recorded from oracle/_ref/flacenc)"""
     g = GOLD[case["name"]]
     pcm = case_pcm(case)
+    assert hashlib.sha256(pcm).hexdigest() == g["pcm_sha256"], "input drifted"
     got = _encode_b200(tmp_path, pcm, case["rate"], case["channels"], case["bps"], helpers.options(**case["options"]))
     ff = helpers.first_frame_offset(got)
     assert got[ff:ff + 64].hex() == g["first_frame_bytes"]
@@ -231,6 +257,42 @@ def test_stream_every_read_short(tmp_path, built):
         assert frames[a:a + len(fr)] == fr, i
     if helpers.have_ref():
         assert helpers.ref_decode(got) == pcm
+
+
+def test_stream_frame_ranges_over_two_devices(tmp_path, built):
+    """ONE stream whose frame ranges go to several GPUs (b200flac_stream_open(devices, n)): batches of
+    consecutive blocks are handed to the devices in turn, their frames concatenated in order on the host, frame
+    numbers and the offsets list continuous, one MD5 over the whole stream.  Needs two devices."""
+    b = _b200()
+    if b.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    # (a) small blocks, 5+ batches of 2048 blocks: bytes equal to the oracle's
+    o = helpers.options(block_size=256, max_lpc_order=4, max_residual_partition_order=3, adaptive_mid_side=True)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 2, 16, **kw)
+    n = 256 * 2048 * 5 + 256 * 300 + 77
+    pcm = helpers.synth_pcm(88, 2, 16, n)
+    path = os.path.join(str(tmp_path), "two.flac")
+    s = b.Stream(path, p, devices=[0, 1])
+    s.write(pcm)
+    offs = s.close()
+    want, want_offs = helpers.oracle_encode(pcm, 44100, 2, 16, o, want_offsets=True)
+    assert open(path, "rb").read() == want
+    assert offs == want_offs
+    # (b) config 4's shape (96 kHz/24-bit 5.1, block 4608), 2100 blocks: the two-device file equals the one-device
+    # file, and the reference decoder returns the PCM
+    o4 = helpers.options(block_size=4608, max_lpc_order=12, max_residual_partition_order=6)
+    kw4 = {k: v for k, v in o4.items() if k != "padding_size"}
+    p4 = b.make_params(96000, 6, 24, **kw4)
+    n4 = 4608 * 2100 + 1000
+    pcm4 = b.synth_pcm(89, 6, 24, n4)
+    one, two = os.path.join(str(tmp_path), "c4_one.flac"), os.path.join(str(tmp_path), "c4_two.flac")
+    b.encode_file(one, p4, pcm4, n4, devices=[0])
+    b.encode_file(two, p4, pcm4, n4, devices=[1, 0])
+    a, c = open(one, "rb").read(), open(two, "rb").read()
+    assert a == c
+    info, back = b.decode(c)
+    assert back == pcm4 and info.total_pcm_frames == n4
 
 
 def test_error_paths(tmp_path, built):
