@@ -96,6 +96,9 @@ uint64_t b200flac_encoder_output_bound(const b200flac_encoder *enc, uint64_t n_p
                                        uint32_t n_segments);
 /* pinned host staging buffer of a slot (write PCM here to skip one host copy) */
 uint8_t *b200flac_encoder_slot_pcm(b200flac_encoder *enc, int slot);
+/* pinned host buffer of a slot for collect()'s `out` (large enough for any batch of this encoder; *capacity
+ * receives its size): the device->host copy of the frames is then a direct asynchronous DMA */
+uint8_t *b200flac_encoder_slot_out(b200flac_encoder *enc, int slot, uint64_t *capacity);
 
 /* Asynchronous: copy PCM host->device (pinned if pcm == slot buffer), run the
  * kernels, start the device->host copy of the per-frame sizes.  Returns 0 on

@@ -89,6 +89,8 @@ def lib():
     L.b200flac_encoder_output_bound.argtypes = [vp, C.c_uint64, C.c_uint32]
     L.b200flac_encoder_slot_pcm.restype = vp
     L.b200flac_encoder_slot_pcm.argtypes = [vp, C.c_int]
+    L.b200flac_encoder_slot_out.restype = vp
+    L.b200flac_encoder_slot_out.argtypes = [vp, C.c_int, u64p]
     L.b200flac_encoder_submit.argtypes = [vp, C.c_int, vp, C.POINTER(Segment), C.c_uint32]
     L.b200flac_encoder_collect.argtypes = [vp, C.c_int, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, u32p]
     L.b200flac_encoder_encode.argtypes = [vp, vp, C.POINTER(Segment), C.c_uint32, vp, C.c_uint64, u64p,

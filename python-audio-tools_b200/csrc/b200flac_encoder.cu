@@ -68,6 +68,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[BF_NUM_EVENTS] = {};
     uint8_t* h_pcm = nullptr;      // pinned
+    uint8_t* h_out = nullptr;      // pinned (b200flac_encoder_slot_out), out_cap bytes
     uint8_t* d_pcm = nullptr;
     bf_frame_desc* h_fd = nullptr; // pinned
     bf_frame_desc* d_fd = nullptr;
@@ -105,6 +106,7 @@ struct Slot {
     cudaStream_t stream_b = nullptr;     // second analysis/packing stream (odd chunks)
     cudaStream_t stream_hi[BF_MAX_MODEL_STREAMS] = {};   // streams of the floating-point model kernels
     cudaStream_t stream_lo[BF_MAX_MODEL_STREAMS] = {};   // ... the same at normal priority (tuning)
+    cudaEvent_t ev_done = nullptr;       // blocking-sync event: a host thread waiting for the slot sleeps instead of spinning
     cudaEvent_t ev_in = nullptr, ev_join = nullptr;
     cudaEvent_t ev_model[BF_MAX_CHUNKS] = {}, ev_an[BF_MAX_CHUNKS] = {}, ev_scan[BF_MAX_CHUNKS] = {};
     u64* d_chunk_tot = nullptr;          // running output size after each chunk
@@ -296,6 +298,7 @@ static void free_slot(Slot& s)
         if (s.stream_lo[i]) { cudaStreamSynchronize(s.stream_lo[i]); cudaStreamDestroy(s.stream_lo[i]); }
     }
     for (int i = 0; i < BF_NUM_EVENTS; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_in) cudaEventDestroy(s.ev_in);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
     for (int i = 0; i < BF_MAX_CHUNKS; i++) {
@@ -305,6 +308,7 @@ static void free_slot(Slot& s)
     }
     cudaFree(s.d_chunk_tot);
     if (s.h_pcm) cudaFreeHost(s.h_pcm);
+    if (s.h_out) cudaFreeHost(s.h_out);
     if (s.h_fd) cudaFreeHost(s.h_fd);
     if (s.h_win) cudaFreeHost(s.h_win);
     if (s.h_frame_bytes) cudaFreeHost(s.h_frame_bytes);
@@ -589,6 +593,7 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
             set_err("cudaStreamCreate failed"); b200flac_encoder_destroy(enc); return nullptr;
         }
         for (int k = 0; k < BF_NUM_EVENTS; k++) cudaEventCreate(&s.ev[k]);
+        cudaEventCreateWithFlags(&s.ev_done, cudaEventBlockingSync | cudaEventDisableTiming);
         ALLOCH(s.h_fd, maxf * sizeof(bf_frame_desc));
         ALLOCH(s.h_odd, maxf * sizeof(u32));
         ALLOC(s.d_odd, maxf * sizeof(u32));
@@ -649,6 +654,16 @@ extern "C" uint8_t* b200flac_encoder_slot_pcm(b200flac_encoder* enc, int slot)
     if (cudaSetDevice(enc->device) != cudaSuccess) return nullptr;
     if (ensure_host_path(enc, enc->slots[slot], true)) return nullptr;
     return enc->slots[slot].h_pcm;
+}
+
+extern "C" uint8_t* b200flac_encoder_slot_out(b200flac_encoder* enc, int slot, uint64_t* capacity)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots) return nullptr;
+    if (cudaSetDevice(enc->device) != cudaSuccess) return nullptr;
+    Slot& s = enc->slots[slot];
+    if (!s.h_out) CU_CHECK(cudaMallocHost((void**)&s.h_out, enc->out_cap + 64), nullptr);
+    if (capacity) *capacity = enc->out_cap;
+    return s.h_out;
 }
 
 extern "C" void* b200flac_host_alloc(uint64_t bytes)
@@ -1094,6 +1109,7 @@ extern "C" int b200flac_encoder_submit(b200flac_encoder* enc, int slot, const ui
     if (launch_batch(enc, s, s.d_pcm, s.d_out, enc->out_cap)) return 1;
     CU_CHECK(cudaMemcpyAsync(s.h_frame_bytes, s.d_frame_bytes, (size_t)nf * sizeof(u32), cudaMemcpyDeviceToHost, st), 1);
     CU_CHECK(cudaMemcpyAsync(s.h_total, s.d_total, sizeof(u64), cudaMemcpyDeviceToHost, st), 1);
+    CU_CHECK(cudaEventRecord(s.ev_done, st), 1);
     s.busy = true;
     return 0;
 }
@@ -1108,15 +1124,18 @@ extern "C" int b200flac_encoder_collect(b200flac_encoder* enc, int slot, uint8_t
     CU_CHECK(cudaSetDevice(enc->device), 1);
     s.busy = false;
     if (s.n_frames == 0) { if (out_bytes) *out_bytes = 0; if (n_frames) *n_frames = 0; return 0; }
-    CU_CHECK(cudaStreamSynchronize(s.stream), 1);
+    // (an event with cudaEventBlockingSync: the many-streams case runs one host thread per stream next to the
+    // streams' MD5 threads, and a spinning wait took a core from them)
+    CU_CHECK(cudaEventSynchronize(s.ev_done), 1);
     const u64 total = *s.h_total;
     if (total + 16 > enc->out_cap) { set_err("encoded batch exceeds the device output buffer (VERBATIM disabled?)"); return 1; }
     if (total > out_capacity) { set_err("output buffer too small"); return 1; }
     if (s.n_frames > frame_capacity && (frame_bytes || frame_pcm)) { set_err("frame arrays too small"); return 1; }
     CU_CHECK(cudaMemcpyAsync(out, s.d_out, (size_t)total, cudaMemcpyDeviceToHost, s.stream), 1);
+    CU_CHECK(cudaEventRecord(s.ev_done, s.stream), 1);
     if (frame_bytes) memcpy(frame_bytes, s.h_frame_bytes, (size_t)s.n_frames * sizeof(u32));
     if (frame_pcm) memcpy(frame_pcm, s.frame_pcm.data(), (size_t)s.n_frames * sizeof(u32));
-    CU_CHECK(cudaStreamSynchronize(s.stream), 1);
+    CU_CHECK(cudaEventSynchronize(s.ev_done), 1);
     if (out_bytes) *out_bytes = total;
     if (n_frames) *n_frames = s.n_frames;
     return 0;

@@ -160,7 +160,6 @@ struct b200flac_stream {
     uint64_t current_offset;
     std::vector<uint64_t> offsets;
     std::vector<uint32_t> lengths;
-    std::vector<uint8_t> out;
     std::vector<uint32_t> fbytes, fpcm;
     bool failed;
     // md5 worker
@@ -403,13 +402,15 @@ extern "C" b200flac_stream* b200flac_stream_open(const char* filename, const b20
 static int collect_oldest(b200flac_stream* s)
 {
     Lane& l = s->lanes[s->oldest];
-    const uint64_t bound = b200flac_encoder_output_bound(l.enc, l.fill, (uint32_t)l.segs.size());
-    if (s->out.size() < bound) s->out.resize(bound);
+    // the frames land in the slot's pinned output buffer (a direct DMA) and are written to the file from there
+    uint64_t out_cap = 0;
+    uint8_t* out = b200flac_encoder_slot_out(l.enc, l.slot, &out_cap);
+    if (!out) { stream_err(b200flac_last_error()); s->failed = true; return 1; }
     const size_t maxf = (size_t)(l.fill / s->params.block_size + l.segs.size() + 2);
     if (s->fbytes.size() < maxf) { s->fbytes.resize(maxf); s->fpcm.resize(maxf); }
     uint64_t nbytes = 0;
     uint32_t nfr = 0;
-    if (b200flac_encoder_collect(l.enc, l.slot, s->out.data(), s->out.size(), &nbytes, s->fbytes.data(),
+    if (b200flac_encoder_collect(l.enc, l.slot, out, out_cap, &nbytes, s->fbytes.data(),
                                  s->fpcm.data(), (uint32_t)maxf, &nfr)) {
         stream_err(b200flac_last_error());
         s->failed = true;
@@ -424,7 +425,7 @@ static int collect_oldest(b200flac_stream* s)
         if (s->fbytes[i] > s->max_frame) s->max_frame = s->fbytes[i];
         s->current_offset += s->fbytes[i];
     }
-    if (nbytes && fwrite(s->out.data(), 1, (size_t)nbytes, s->f) != nbytes) {
+    if (nbytes && fwrite(out, 1, (size_t)nbytes, s->f) != nbytes) {
         stream_err("write error"); s->failed = true; return 1;
     }
     l.in_flight = false;
