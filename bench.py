@@ -340,6 +340,7 @@ def main():
     cores = os.cpu_count() or 1
     threads = max(1, min(32, cores // world))       # host threads of this rank (its share of the box)
     os.environ.setdefault("B200FLAC_POOL", str(max(16, threads + 4)))   # idle encoders kept by the stream layer
+    os.environ["B200FLAC_DEVICE"] = str(local_rank)   # the device of calls that carry no device list (encode_flac)
 
     import hashlib
     import numpy as np
@@ -355,6 +356,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
+        torch.cuda.set_device(local_rank)
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -362,6 +364,7 @@ def main():
     def allmax(x):
         if dist is None:
             return x
+        torch.cuda.set_device(local_rank)
         t = torch.tensor([x], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
@@ -369,6 +372,7 @@ def main():
     def allsum(x):
         if dist is None:
             return x
+        torch.cuda.set_device(local_rank)
         t = torch.tensor([x], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())

@@ -124,7 +124,10 @@ int b200flac_encoder_encode(b200flac_encoder *enc, const uint8_t *pcm,
 
 /* Device-resident variant (inputs already in HBM, frames left in HBM): `d_pcm`
  * and `d_out` are device pointers on the encoder's device.  d_out must be
- * 4-byte aligned and hold b200flac_encoder_output_bound() bytes.  Returns the
+ * 16-byte aligned and hold b200flac_encoder_output_bound() bytes; d_pcm must be
+ * 4-byte aligned, and the 16-byte lines holding its first and last PCM byte must
+ * be readable (rows are staged with 16-byte aligned bulk copies; memory from
+ * b200flac_device_alloc, which adds 64 bytes, or any interior pointer qualifies).  Returns the
  * total through *out_bytes (host) after synchronising the slot's stream.
  * elapsed_ms (optional) receives the CUDA-event time of the kernels alone. */
 int b200flac_encoder_encode_device(b200flac_encoder *enc, int slot, const void *d_pcm,

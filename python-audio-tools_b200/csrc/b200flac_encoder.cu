@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <vector>
 
@@ -154,6 +155,20 @@ static inline void count_launches(b200flac_encoder* enc, u64 k)
     g_launches_total.fetch_add(k, std::memory_order_relaxed);
 }
 extern "C" uint64_t b200flac_launch_count_total(void) { return g_launches_total.load(); }
+
+// Wait for a slot's event: poll for a short while (a batch in a running pipeline is usually done or nearly so, and
+// waking a sleeping thread costs more than the wait), then sleep on the blocking-sync event, so that the many
+// host threads of the many-streams case do not spin against the streams' MD5 threads.
+static cudaError_t wait_event(cudaEvent_t ev)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const cudaError_t e = cudaEventQuery(ev);
+        if (e != cudaErrorNotReady) return e;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(1000)) break;
+    }
+    return cudaEventSynchronize(ev);
+}
 
 // ---- derived options ------------------------------------------------------
 static u32 sample_rate_code(u32 sr) // flac.c:452-476
@@ -600,7 +615,7 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         ALLOC(s.d_fd, maxf * sizeof(bf_frame_desc));
         s.win_cap = (size_t)bs * 4;
         ALLOCH(s.h_win, s.win_cap * sizeof(double));
-        ALLOC(s.d_win, s.win_cap * sizeof(double));
+        ALLOC(s.d_win, s.win_cap * sizeof(double) + 64);   // (+ slack: bulk copies round a tile up to 16 bytes)
         ALLOC(s.d_heads, U * sizeof(bf_lpc_head));
         ALLOC(s.d_coefs, U * P.model_stride * sizeof(short));
         if (P.try_lpc) {
@@ -719,7 +734,7 @@ static long build_batch(b200flac_encoder* enc, Slot& s, const b200flac_segment* 
                         size_t ncap = s.win_cap * 2 + n;
                         double *nh = nullptr, *nd = nullptr;
                         if (cudaMallocHost((void**)&nh, ncap * sizeof(double)) != cudaSuccess ||
-                            cudaMalloc((void**)&nd, ncap * sizeof(double)) != cudaSuccess) {
+                            cudaMalloc((void**)&nd, ncap * sizeof(double) + 64) != cudaSuccess) {
                             set_err("out of memory growing the window table"); return -1;
                         }
                         cudaStreamSynchronize(s.stream);
@@ -1126,7 +1141,7 @@ extern "C" int b200flac_encoder_collect(b200flac_encoder* enc, int slot, uint8_t
     if (s.n_frames == 0) { if (out_bytes) *out_bytes = 0; if (n_frames) *n_frames = 0; return 0; }
     // (an event with cudaEventBlockingSync: the many-streams case runs one host thread per stream next to the
     // streams' MD5 threads, and a spinning wait took a core from them)
-    CU_CHECK(cudaEventSynchronize(s.ev_done), 1);
+    CU_CHECK(wait_event(s.ev_done), 1);
     const u64 total = *s.h_total;
     if (total + 16 > enc->out_cap) { set_err("encoded batch exceeds the device output buffer (VERBATIM disabled?)"); return 1; }
     if (total > out_capacity) { set_err("output buffer too small"); return 1; }
@@ -1135,7 +1150,7 @@ extern "C" int b200flac_encoder_collect(b200flac_encoder* enc, int slot, uint8_t
     CU_CHECK(cudaEventRecord(s.ev_done, s.stream), 1);
     if (frame_bytes) memcpy(frame_bytes, s.h_frame_bytes, (size_t)s.n_frames * sizeof(u32));
     if (frame_pcm) memcpy(frame_pcm, s.frame_pcm.data(), (size_t)s.n_frames * sizeof(u32));
-    CU_CHECK(cudaEventSynchronize(s.ev_done), 1);
+    CU_CHECK(wait_event(s.ev_done), 1);
     if (out_bytes) *out_bytes = total;
     if (n_frames) *n_frames = s.n_frames;
     return 0;

@@ -352,8 +352,14 @@ extern "C" b200flac_stream* b200flac_stream_open(const char* filename, const b20
     while (blocks > 1 && blocks * bs * frame_bytes > (64ull << 20)) blocks /= 2;
     s->batch_frames = blocks * bs;
 
+    // no device list (the Python entry point has no such parameter): device 0, or what B200FLAC_DEVICE names --
+    // how one process per GPU (torchrun, a job scheduler) points the unchanged encode_flac call at its own GPU
     int dev0 = 0;
-    if (!devices || n_devices <= 0) { devices = &dev0; n_devices = 1; }
+    if (!devices || n_devices <= 0) {
+        const char* e = getenv("B200FLAC_DEVICE");
+        if (e && *e) dev0 = atoi(e);
+        devices = &dev0; n_devices = 1;
+    }
     const int slots_per_dev = 2;
     s->slots_per_dev = slots_per_dev;
     s->reusable = true;

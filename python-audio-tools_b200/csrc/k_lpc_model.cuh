@@ -23,8 +23,10 @@
 // tasks of a batch land on whichever SMs are free (a static grid's last wave
 // was packed onto a few SMs by the block scheduler and ran at a third of the
 // speed).  A task's PCM rows (the frames its units belong to) are staged through
-// shared memory in tiles with cp.async, double buffered, together with the
-// matching tile of the Tukey window; every lane then walks its own row.
+// shared memory in tiles, double buffered, together with the matching tile of the
+// Tukey window: one bulk asynchronous copy (cp.async.bulk, the TMA engine) per row
+// and tile, completing on the buffer's mbarrier -- 9 copy instructions per tile
+// where per-lane cp.async took ~20 issue slots per lane; every lane then walks its own row.
 #pragma once
 #include "flac_common.cuh"
 
@@ -92,27 +94,72 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- bulk asynchronous copies (TMA engine, UBLKCP in SASS) completing on a shared-memory mbarrier ----
+// One instruction moves a whole staged row: 16-byte aligned source and destination, size a multiple of 16.
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, u32 bytes, u64* bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+
 // staging area of a warp (dynamic shared memory):
-//   hdr | window tiles [2][T] (double) | PCM tiles [2][rows][row_words] (u32)
+//   hdr | window tiles [2][WT] (double) | PCM tiles [2][rows][row_words] (u32)
 struct LpcStageHdr {
     u64 row_byte0[LPC_MAX_ROWS];   // byte offset of the row's first PCM frame
     u32 row_n[LPC_MAX_ROWS];       // PCM frames in the row (0: no such frame)
+    u64 bar[2];                    // mbarriers of the two tile buffers (bulk staging)
 };
 
 // tile geometry, shared by host and device: T = PCM frames per staged tile (>= the longest ring),
-// rows = frames a task can span, row_words = u32 words per staged row (odd: rows start in
-// different banks)
-struct LpcGeom { u32 T, rows, row_words, smem_bytes; };
+// rows = frames a task can span, row_words = u32 words per staged row.  Bulk staging (rows <= 8, i.e. K >= 4):
+// a row is one bulk copy from the 16-byte aligned address at or below its first byte, so rows are 16-byte
+// aligned and 4 x odd words apart (the <= 8 rows of a task then start in different banks); otherwise rows are
+// an odd number of words apart and filled with 4-byte cp.async.
+struct LpcGeom { u32 T, WT, rows, row_words, smem_bytes, bulk; };   // WT: doubles per window tile (even: 16-byte aligned tiles)
 __host__ __device__ inline LpcGeom lpc_geometry(u32 K, u32 rowbytes, u32 ring)
 {
     LpcGeom g;
     g.rows = 32 / K;
+    g.bulk = g.rows <= 8 ? 1u : 0u;
     u32 T = 4608 / (g.rows * rowbytes);           // ~4.5 KB per PCM tile: 20 one-warp CTAs per SM fit at any sample width
     if (T > 160) T = 160;
     if (T < ring) T = ring;
     g.T = T;
-    g.row_words = (((T * rowbytes + 6) >> 2) + 1) | 1u;
-    g.smem_bytes = (u32)sizeof(LpcStageHdr) + 2 * T * 8 + 2 * g.rows * g.row_words * 4 + 16;
+    g.WT = (T + 3) & ~1u;
+    if (g.bulk) {
+        u32 w = (T * rowbytes + 15 + 15 + 3) >> 2;   // <= 15 bytes before the first frame, size rounded up to 16
+        w = (w + 3) & ~3u;
+        if (((w >> 2) & 1u) == 0) w += 4;            // 4 x odd
+        g.row_words = w;
+    } else {
+        g.row_words = (((T * rowbytes + 6) >> 2) + 1) | 1u;
+    }
+    g.smem_bytes = (u32)sizeof(LpcStageHdr) + 2 * g.WT * 8 + 2 * g.rows * g.row_words * 4 + 16;
     return g;
 }
 
@@ -139,17 +186,18 @@ __device__ __forceinline__ int stereo16_coef(u32 cand) { return cand == 0 ? 0x00
 // flight while tile t is consumed.
 // FAST: 16-bit stereo (one 32-bit load and a dot product per sample); otherwise samples are
 // assembled from the staged bytes.
-template <int LB, int NL, bool FAST>
+template <int LB, int NL, bool FAST, bool BULK>
 __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                                            const double* __restrict__ windows, const bf_dev_params& P,
                                            const LpcGeom& g, u32 f0, u32 nrows, unsigned char* smem,
-                                           double* __restrict__ autoc_out, u32 autoc_stride, uint8_t* __restrict__ wasted_out)
+                                           double* __restrict__ autoc_out, u32 autoc_stride, uint8_t* __restrict__ wasted_out,
+                                           u32 (&phase)[2])
 {
     constexpr int H = LB + NL;
     const int lane = threadIdx.x & 31;
     LpcStageHdr* hdr = (LpcStageHdr*)smem;
-    double* wbuf = (double*)(smem + sizeof(LpcStageHdr));
-    u32* tbuf = (u32*)(wbuf + 2 * g.T);
+    double* wbuf = (double*)(smem + sizeof(LpcStageHdr));     // two tiles of WT doubles
+    u32* tbuf = (u32*)(wbuf + 2 * g.WT);
     const u32 K = P.K, C = P.channels, B = P.bytes_ps;
     const u32 rowbytes = C * B;
     const u32 row_words = g.row_words;
@@ -185,6 +233,38 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
 
     auto issue_tile = [&](u32 i0, u32 b) {
         u32* base = tbuf + (size_t)b * g.rows * row_words;
+        if (BULK) {
+            // lane r < nrows: one bulk copy of row r's tile, from the aligned address at or below its first byte;
+            // lane 31: the window tile.  Lane 0 arms the buffer's mbarrier with the byte total first.
+            const void* src = nullptr;
+            void* dst = nullptr;
+            u32 bytes = 0;
+            if ((u32)lane < nrows) {
+                const u32 rn = hdr->row_n[lane];
+                if (i0 < rn) {
+                    const u32 take = min(TS, rn - i0);
+                    const uintptr_t a = (uintptr_t)pcm + hdr->row_byte0[lane] + (u64)i0 * rowbytes;
+                    const u32 mis = (u32)(a & 15);
+                    src = (const void*)(a - mis);
+                    dst = base + (u32)lane * row_words;
+                    bytes = (mis + take * rowbytes + 15) & ~15u;
+                }
+            } else if (lane == 31) {
+                const u32 take = min(TS, nmax - i0);
+                const uintptr_t a = (uintptr_t)(windows + woff0 + i0);
+                const u32 mis = (u32)(a & 15);
+                src = (const void*)(a - mis);
+                dst = wbuf + b * g.WT;
+                bytes = (mis + take * 8 + 15) & ~15u;
+            }
+            const u32 total = __reduce_add_sync(0xFFFFFFFFu, bytes);
+            // the buffer's previous contents were read through the generic proxy; the copies write through the async one
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            if (lane == 0) mbar_expect_tx(&hdr->bar[b], total);
+            __syncwarp();
+            if (bytes) bulk_g2s(dst, src, bytes, &hdr->bar[b]);
+            return;
+        }
         for (u32 r = 0; r < nrows; r++) {
             const u32 rn = hdr->row_n[r];
             if (i0 < rn) {
@@ -198,8 +278,14 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
             }
         }
         const u32 take = min(TS, nmax - i0);
-        for (u32 w = lane; w < take; w += 32) cp_async8(wbuf + b * g.T + w, windows + woff0 + i0 + w);
+        for (u32 w = lane; w < take; w += 32) cp_async8(wbuf + b * g.WT + w, windows + woff0 + i0 + w);
         cp_async_commit();
+    };
+    // wait until tile buffer b holds its data; `more`: another tile is in flight behind it
+    auto wait_tile = [&](u32 b, bool more) {
+        if (BULK) { mbar_wait(&hdr->bar[b], phase[b]); phase[b] ^= 1u; }
+        else if (more) cp_async_wait<1>();
+        else cp_async_wait<0>();
     };
 
     const u64 my_byte0 = hdr->row_byte0[myrow];
@@ -211,12 +297,15 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
     issue_tile(0, 0);
     u32 b = 0;
     for (u32 i0 = 0; i0 < nmax; i0 += TS, b ^= 1) {
-        if (i0 + TS < nmax) { issue_tile(i0 + TS, b ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
+        const bool more = i0 + TS < nmax;
+        if (more) issue_tile(i0 + TS, b ^ 1);
+        wait_tile(b, more);
         __syncwarp();
+        const u32 amask = BULK ? 15u : 3u;
         const uint8_t* row = (const uint8_t*)(tbuf + ((size_t)b * g.rows + myrow) * row_words) +
-                             (u32)((my_byte0 + (u64)i0 * rowbytes) & 3);
-        const double* wt = wbuf + b * g.T;
+                             (u32)(((BULK ? (uintptr_t)pcm : (uintptr_t)0) + my_byte0 + (u64)i0 * rowbytes) & amask);
+        const double* wt = wbuf + b * g.WT +
+                           (BULK ? (u32)(((uintptr_t)(windows + woff0 + i0) & 15) >> 3) : 0u);
 #pragma unroll 1
         for (u32 m = 0; m < M; m++) {
             const u32 tbase = m * H;
@@ -293,20 +382,29 @@ k_lpc_autoc(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ f
     const int lane = threadIdx.x & 31;
     const LpcGeom g = lpc_geometry(P.K, P.channels * P.bytes_ps, MAXL + 1);
     const bool st16 = P.stereo && P.bytes_ps == 2;
+    u32 phase[2] = {0u, 0u};        // parity of the next completion of each tile buffer's mbarrier
+    if (g.bulk) {
+        LpcStageHdr* hdr = (LpcStageHdr*)lpc_smem;
+        if (lane == 0) { mbar_init(&hdr->bar[0], 1); mbar_init(&hdr->bar[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        __syncwarp();
+    }
+#define AUTOC_TASK(LB_, NL_) \
+    do { \
+        if (st16) autoc_task<LB_, NL_, true, true>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out, phase); \
+        else if (g.bulk) autoc_task<LB_, NL_, false, true>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out, phase); \
+        else autoc_task<LB_, NL_, false, false>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out, phase); \
+    } while (0)
     for (;;) {
         u32 t = 0;
         if (lane == 0) t = atomicAdd(ticket, 1u);
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
         if (t >= n_tasks) break;
         const bf_lpc_task tk = tasks[t / G];
-        if (G == 1 || (t % G) == 0) {
-            if (st16) autoc_task<0, NL0, true>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out);
-            else autoc_task<0, NL0, false>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out);
-        } else if constexpr (G == 2) {
-            if (st16) autoc_task<NL0, NL1, true>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out);
-            else autoc_task<NL0, NL1, false>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out);
-        }
+        if (G == 1 || (t % G) == 0) AUTOC_TASK(0, NL0);
+        else if constexpr (G == 2) AUTOC_TASK(NL0, NL1);
     }
+#undef AUTOC_TASK
 }
 
 // Levinson-Durbin, order estimate and quantisation: one thread per unit.
