@@ -200,6 +200,80 @@ def ref_decode(flac_bytes):
         return r.stdout
 
 
+# ---- TTA: the compiled reference (oracle/_ref/ttaenc, ttadec) and the plain-C oracle ----
+REF_TTAENC = os.path.join(ROOT, "oracle", "_ref", "ttaenc")
+REF_TTADEC = os.path.join(ROOT, "oracle", "_ref", "ttadec")
+_tta = None
+
+
+def have_tta_ref():
+    return os.path.exists(REF_TTAENC) and os.path.exists(REF_TTADEC)
+
+
+def ref_tta_encode(pcm, sample_rate, channels, bits_per_sample):
+    """file image from the COMPILED REFERENCE TTA encoder (src/encoders/tta.c, -DSTANDALONE)"""
+    n = len(pcm) // (channels * (bits_per_sample // 8))
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.tta")
+        subprocess.run([REF_TTAENC, "-c", str(channels), "-r", str(sample_rate), "-b", str(bits_per_sample),
+                        "-T", str(n), out], input=pcm, stdout=subprocess.DEVNULL, check=True)
+        with open(out, "rb") as fh:
+            return fh.read()
+
+
+def ref_tta_decode(tta_bytes):
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "i.tta")
+        with open(p, "wb") as fh:
+            fh.write(tta_bytes)
+        r = subprocess.run([REF_TTADEC, p], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if r.returncode != 0:
+            raise RuntimeError("reference ttadec rejected the stream: %s" % r.stderr[-300:])
+        return r.stdout
+
+
+def tta_orc():
+    global _tta
+    if _tta is None:
+        path = os.path.join(ROOT, "oracle", "liboracle_tta.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle_tta.so"], check=True)
+        L = C.CDLL(path)
+        L.tta_oracle_encode_file.restype = C.c_uint64
+        L.tta_oracle_encode_file.argtypes = [C.c_char_p, C.c_uint64, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]
+        L.tta_oracle_encode_frames.restype = C.c_uint
+        L.tta_oracle_encode_frames.argtypes = [C.c_char_p, C.c_uint64, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_uint32),
+                                               C.c_uint, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.tta_oracle_free.argtypes = [C.c_void_p]
+        _tta = L
+    return _tta
+
+
+def oracle_tta_file(pcm, sample_rate, channels, bits_per_sample):
+    """whole .tta file from the CPU oracle (oracle/tta_oracle.c)"""
+    n = len(pcm) // (channels * (bits_per_sample // 8))
+    out = C.c_void_p()
+    ln = tta_orc().tta_oracle_encode_file(bytes(pcm), n, sample_rate, channels, bits_per_sample, C.byref(out))
+    data = C.string_at(out, ln)
+    tta_orc().tta_oracle_free(out)
+    return data
+
+
+def oracle_tta_frames(pcm, sample_rate, channels, bits_per_sample, frame_lengths=None):
+    """(frame bytes, [sizes]) from the CPU oracle; frame_lengths: the reader's read sizes"""
+    n = len(pcm) // (channels * (bits_per_sample // 8))
+    block = (sample_rate * 256) // 245
+    cap = (len(frame_lengths) if frame_lengths else (n + block - 1) // block) + 1
+    sizes = (C.c_uint32 * cap)()
+    lens = (C.c_uint32 * len(frame_lengths))(*frame_lengths) if frame_lengths else None
+    out, nb = C.c_void_p(), C.c_uint64(0)
+    nf = tta_orc().tta_oracle_encode_frames(bytes(pcm), n, sample_rate, channels, bits_per_sample, lens,
+                                            len(frame_lengths) if frame_lengths else 0, C.byref(out), C.byref(nb), sizes)
+    data = C.string_at(out, nb.value) if nb.value else b""
+    tta_orc().tta_oracle_free(out)
+    return data, list(sizes[:nf])
+
+
 # ---- generators restating the reference's test streams (test/test_streams.py) ----
 def sine_pcm(bits_per_sample, channels, n_frames, sample_rate, freqs_amps):
     """integer sines in the spirit of test_streams.Sine16_Stereo etc. (src/decoders/sine.c):
