@@ -20,6 +20,7 @@
 
 #include "pcm.h"
 #include "../../include/b200flac.h"
+#include "../../include/b200tta.h"
 
 struct py_pcmreader {
     PyObject *obj;            /* the Python PCMReader */
@@ -275,6 +276,98 @@ error:
     return NULL;
 }
 
+/* encode_tta(file, pcmreader) -> [frame size, ...]      src/encoders/tta.c:31-117
+ * Same keyword names ("file", "pcmreader", tta.c:44-46), same protocol: block_size = sample_rate * 256 / 245
+ * PCM frames are asked of the reader per call and WHATEVER comes back is one TTA frame (tta.c:69-83); the frames
+ * are written to the file object (any object with write(); the reference needs a concrete py2 file) and the
+ * list of their sizes in bytes is returned -- what TrueAudio.from_pcm builds the seektable from.  The reader is
+ * not closed (the reference only drops its reference).  All frames are encoded in one GPU batch at the end. */
+static PyObject *encoders_encode_tta(PyObject *dummy, PyObject *args, PyObject *keywds)
+{
+    static char *kwlist[] = {"file", "pcmreader", NULL};
+    PyObject *file_obj;
+    struct py_pcmreader *reader = NULL;
+    uint8_t *pcm = NULL, *out = NULL;
+    size_t cap = 0, used = 0;
+    uint32_t *lengths = NULL, *sizes = NULL;
+    size_t n_len = 0, len_cap = 0;
+    uint64_t total_frames = 0, out_bytes = 0;
+    uint32_t n_frames = 0;
+    PyObject *result = NULL;
+    b200tta_params p;
+
+    if (!PyArg_ParseTupleAndKeywords(args, keywds, "OO&", kwlist, &file_obj, pcmreader_converter, &reader)) return NULL;
+    p.sample_rate = reader->sample_rate;
+    p.channels = reader->channels;
+    p.bits_per_sample = reader->bits_per_sample;
+    const unsigned bytes_ps = p.bits_per_sample / 8;
+    const unsigned block_size = b200tta_block_size(p.sample_rate);
+    if (block_size == 0 || (bytes_ps != 1 && bytes_ps != 2 && bytes_ps != 3)) {
+        PyErr_SetString(PyExc_ValueError, "unsupported sample rate or bits_per_sample");
+        goto done;
+    }
+    for (;;) {
+        PyObject *fl_obj = PyObject_CallMethod(reader->obj, "read", "i", (int)block_size);
+        if (!fl_obj) goto done;
+        if ((PyObject *)Py_TYPE(fl_obj) != reader->framelist_type) {
+            Py_DECREF(fl_obj);
+            PyErr_SetString(PyExc_TypeError, "results from pcmreader.read() must be FrameLists");
+            goto done;
+        }
+        pcm_FrameList *fl = (pcm_FrameList *)fl_obj;
+        if (fl->frames == 0) { Py_DECREF(fl_obj); break; }   /* tta.c:71 */
+        if (fl->channels != p.channels || fl->bits_per_sample != p.bits_per_sample) {
+            Py_DECREF(fl_obj);
+            PyErr_SetString(PyExc_ValueError, "FrameList does not match the pcmreader's channels / bits_per_sample");
+            goto done;
+        }
+        const size_t need = used + (size_t)fl->samples_length * bytes_ps;
+        if (need > cap) {
+            size_t ncap = cap ? cap * 2 : (1u << 22);
+            while (ncap < need) ncap *= 2;
+            uint8_t *np_ = (uint8_t *)realloc(pcm, ncap);
+            if (!np_) { Py_DECREF(fl_obj); PyErr_NoMemory(); goto done; }
+            pcm = np_; cap = ncap;
+        }
+        if (n_len == len_cap) {
+            len_cap = len_cap ? len_cap * 2 : 1024;
+            uint32_t *nl = (uint32_t *)realloc(lengths, len_cap * sizeof(uint32_t));
+            if (!nl) { Py_DECREF(fl_obj); PyErr_NoMemory(); goto done; }
+            lengths = nl;
+        }
+        pack_le_signed(fl, pcm + used);
+        used = need;
+        lengths[n_len++] = fl->frames;
+        total_frames += fl->frames;
+        Py_DECREF(fl_obj);
+    }
+    {
+        int rc;
+        Py_BEGIN_ALLOW_THREADS     /* tta.c:73-79 drops the GIL around encode_frame as well */
+        rc = b200tta_encode_frames(&p, pcm, total_frames, lengths, (uint32_t)n_len, 0, &out, &out_bytes, &sizes, &n_frames, NULL);
+        Py_END_ALLOW_THREADS
+        if (rc) { PyErr_SetString(PyExc_IOError, b200tta_last_error()); goto done; }
+    }
+    if (out_bytes) {
+        PyObject *r = PyObject_CallMethod(file_obj, "write", "y#", (const char *)out, (Py_ssize_t)out_bytes);
+        if (!r) goto done;
+        Py_DECREF(r);
+    }
+    result = PyList_New((Py_ssize_t)n_frames);
+    for (uint32_t i = 0; result && i < n_frames; i++) {
+        PyObject *v = PyLong_FromUnsignedLong(sizes[i]);
+        if (!v) { Py_CLEAR(result); break; }
+        PyList_SET_ITEM(result, (Py_ssize_t)i, v);
+    }
+done:
+    free(pcm);
+    free(lengths);
+    b200tta_free(out);
+    b200tta_free(sizes);
+    pcmreader_del(reader);
+    return result;
+}
+
 static PyObject *encoders_device_count(PyObject *dummy, PyObject *args)
 {
     return PyLong_FromLong(b200flac_device_count());
@@ -324,6 +417,8 @@ static PyMethodDef module_methods[] = {
      "max_residual_partition_order, mid_side=0, adaptive_mid_side=0, exhaustive_model_search=0, "
      "disable_verbatim_subframes=0, disable_constant_subframes=0, disable_fixed_subframes=0, "
      "disable_lpc_subframes=0, padding_size=4096) -> [(byte_offset, pcm_frames), ...]"},
+    {"encode_tta", (PyCFunction)encoders_encode_tta, METH_VARARGS | METH_KEYWORDS,
+     "encode_tta(file, pcmreader) -> [frame_size, ...]: TTA frames written to file (src/encoders/tta.c:31-117)"},
     {"finalize_flac_metadata", (PyCFunction)encoders_finalize_flac_metadata, METH_VARARGS | METH_KEYWORDS,
      "finalize_flac_metadata(filename, offsets, seekpoint_interval=0, channel_mask=0): SEEKTABLE from the "
      "encoder's offsets, channel-mask tag, PADDING adjustment -- FlacAudio.from_pcm's tail in C"},

@@ -20,8 +20,8 @@
 //                    (src/common/tta_crc.c): 256-byte segments, slicing-by-4 tables per thread, segment CRCs
 //                    moved to their place with one carry-less multiply by a tabulated power of x and XOR-reduced.
 //
-// Same bytes as the reference: tests/test_tta_gpu.py compares with oracle/tta_oracle.c, which is pinned to the
-// compiled reference encoder.  No CPU fallback.
+// Same bytes as the reference: tests/test_tta_gpu.py compares with the tests' CPU checker, which is pinned to
+// the compiled reference encoder.  No CPU fallback.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -64,18 +64,12 @@ struct TtaFrame {
 // code descriptor: low word = length in bits (ones + stop bit + k), high word = k << 27 | low bits
 __device__ __forceinline__ u64 tta_desc(u32 msb, u32 k, u32 lsb) { return (u64)(msb + 1u + k) | ((u64)((k << 27) | lsb) << 32); }
 
-__device__ __forceinline__ int tta_ld(const uint8_t* __restrict__ p, u32 B)
-{
-    if (B == 2) return (int)(*(const short*)p);
-    if (B == 1) return (int)(*(const signed char*)p);
-    return ((int)((u32)p[0] << 8 | (u32)p[1] << 16 | (u32)p[2] << 24)) >> 8;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // one thread per (frame, channel)
 // ---------------------------------------------------------------------------------------------------------
+template <u32 B>
 __global__ void __launch_bounds__(32)
-k_tta_residual(const uint8_t* __restrict__ pcm, const TtaFrame* __restrict__ frames, u32 n_frames, u32 C, u32 B, u32 bps,
+k_tta_residual(const uint8_t* __restrict__ pcm, const TtaFrame* __restrict__ frames, u32 n_frames, u32 C, u32 bps,
                u64* __restrict__ desc, u64 plane, u64* __restrict__ bits_out)
 {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,64 +94,96 @@ k_tta_residual(const uint8_t* __restrict__ pcm, const TtaFrame* __restrict__ fra
     u64 bits = 0;
     u64* out = desc + (u64)c * plane + fr.ebase;
     u64 d4[4];
-    for (u32 i = 0; i < n; i++) {
-        const uint8_t* p = src + (size_t)i * C * B;
-        const int a = tta_ld(p + ca * B, B);
-        int x = a;
-        if (C > 1) {
-            const int b = tta_ld(p + cb * B, B);
-            x = last ? b - ((b - a) / 2) : b - a;
-        }
-        // fixed_prediction, tta.c:306-310
-        int pred = x;
-        if (i) pred = x - (int)(((((long long)prevx) << fshift) - prevx) >> fshift);
-        prevx = x;
-        // hybrid_filter, tta.c:329-397: the sum is 32-bit wrap-around arithmetic (every operand is int32_t)
-        int r;
-        if (i == 0) {
-            r = pred;
-        } else {
-            const int sgn = (rprev > 0) - (rprev < 0);
-            u32 sum = round;
+    // The channel is walked in blocks of 8 samples; the next block's PCM is fetched before the current one is
+    // filtered, so no load sits on the serial chain.
+    constexpr int TB = 8;
+    // raw loads only: nothing that depends on a load's result is issued before the block that uses it (a sign
+    // extension right behind the load made the warp wait for memory on the spot)
+    u32 ra[TB][B == 3 ? 3 : 1], rb[TB][B == 3 ? 3 : 1];
+    auto raw = [&](const uint8_t* p, u32 (&w)[B == 3 ? 3 : 1]) {
+        if (B == 2) w[0] = *(const unsigned short*)p;
+        else if (B == 1) w[0] = *p;
+        else { w[0] = p[0]; w[1 % (B == 3 ? 3 : 1)] = p[1]; w[2 % (B == 3 ? 3 : 1)] = p[2]; }
+    };
+    auto cook = [&](const u32 (&w)[B == 3 ? 3 : 1]) -> int {
+        if (B == 2) return (int)(short)w[0];
+        if (B == 1) return (int)(signed char)w[0];
+        return ((int)(w[0] << 8 | w[1 % (B == 3 ? 3 : 1)] << 16 | w[2 % (B == 3 ? 3 : 1)] << 24)) >> 8;
+    };
+    auto fetch = [&](u32 i0) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) { qm[j] += (u32)(sgn * dx[j]); sum += dl[j] * qm[j]; }
-            r = pred - ((int)sum >> hshift);
+        for (int j = 0; j < TB; j++) {
+            const u32 i = min(i0 + (u32)j, n - 1);
+            const uint8_t* p = src + (size_t)i * C * B;
+            raw(p + ca * B, ra[j]);
+            if (C > 1) raw(p + cb * B, rb[j]);
         }
-        rprev = r;
-        dx[0] = dx[1]; dx[1] = dx[2]; dx[2] = dx[3]; dx[3] = dx[4];
-        dx[4] = ((int)dl[4] >= 0) ? 1 : -1;
-        dx[5] = ((int)dl[5] >= 0) ? 2 : -2;
-        dx[6] = ((int)dl[6] >= 0) ? 2 : -2;
-        dx[7] = ((int)dl[7] >= 0) ? 4 : -4;
-        {
-            const u32 pp = (u32)pred, t7 = pp - dl[7], t6 = t7 - dl[6], t5 = t6 - dl[5];
-            dl[0] = dl[1]; dl[1] = dl[2]; dl[2] = dl[3]; dl[3] = dl[4];
-            dl[4] = t5; dl[5] = t6; dl[6] = t7; dl[7] = pp;
+    };
+    fetch(0);
+    for (u32 i0 = 0; i0 < n; i0 += TB) {
+        int pr[TB];
+        // correlate_channels + fixed_prediction (tta.c:306-310) of the block: independent of the filter.  (The
+        // reference forms (x << shift) - x in 64 bits; samples of at most 25 bits keep it inside 32.)
+#pragma unroll
+        for (int j = 0; j < TB; j++) {
+            const int a = cook(ra[j]), b = C > 1 ? cook(rb[j]) : 0;
+            const int x = C == 1 ? a : (last ? b - ((b - a) / 2) : b - a);
+            pr[j] = (i0 + j) ? x - (((int)((u32)prevx << fshift) - prevx) >> fshift) : x;
+            prevx = x;
         }
-        // adaptive Rice code, tta.c:201-246
-        const u32 u = r > 0 ? ((u32)r * 2u) - 1u : (u32)(-r) * 2u;
-        u64 d;
-        if (u < (1u << k0)) {
-            d = tta_desc(0, k0, u);
-        } else {
-            const u32 shifted = u - (1u << k0);
-            const u32 msb = 1u + (shifted >> k1);
-            const u32 lsb = shifted - ((msb - 1u) << k1);
-            d = tta_desc(msb, k1, lsb);
-            sum1 += shifted - (sum1 >> 4);
-            if (k1 > 0 && (int)sum1 < (1 << (k1 + 4))) k1 -= 1;
-            else if ((int)sum1 > (1 << (k1 + 5))) k1 += 1;
-        }
-        sum0 += u - (sum0 >> 4);
-        if (k0 > 0 && (int)sum0 < (1 << (k0 + 4))) k0 -= 1;
-        else if ((int)sum0 > (1 << (k0 + 5))) k0 += 1;
-        if ((u32)(d >> 59) > 27u) __trap();      // (a Rice parameter beyond the descriptor's field: input outside any PCM width)
-        bits += (u32)d;
-        // descriptors leave in 32-byte pieces (a frame's plane region starts on a multiple of 4)
-        d4[i & 3] = d;
-        if ((i & 3) == 3) {
-            *(ulonglong2*)(out + i - 3) = make_ulonglong2(d4[0], d4[1]);
-            *(ulonglong2*)(out + i - 1) = make_ulonglong2(d4[2], d4[3]);
+        if (i0 + TB < n) fetch(i0 + TB);
+#pragma unroll
+        for (int j = 0; j < TB; j++) {
+            const u32 i = i0 + j;
+            if (i >= n) break;
+            const int pred = pr[j];
+            // hybrid_filter, tta.c:329-397.  The sum is 32-bit wrap-around arithmetic (every operand is int32_t), so
+            // it may be regrouped freely: with s = sign of the previous residual, sum of dl * (qm + s dx) =
+            // (round + sum of dl * qm) + s * (sum of dl * dx) -- both sums are formed before s is known, which
+            // leaves sign -> multiply-add -> shift -> subtract on the serial chain instead of eight multiply-adds.
+            u32 sa = round, sb = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) { sa += dl[t] * qm[t]; sb += dl[t] * (u32)dx[t]; }
+            const int sgn = i ? (rprev > 0) - (rprev < 0) : 0;
+            const int r = i ? pred - ((int)(sa + (u32)sgn * sb) >> hshift) : pred;
+#pragma unroll
+            for (int t = 0; t < 8; t++) qm[t] += (u32)(sgn * dx[t]);
+            rprev = r;
+            dx[0] = dx[1]; dx[1] = dx[2]; dx[2] = dx[3]; dx[3] = dx[4];
+            dx[4] = ((int)dl[4] >= 0) ? 1 : -1;
+            dx[5] = ((int)dl[5] >= 0) ? 2 : -2;
+            dx[6] = ((int)dl[6] >= 0) ? 2 : -2;
+            dx[7] = ((int)dl[7] >= 0) ? 4 : -4;
+            {
+                const u32 pp = (u32)pred, t7 = pp - dl[7], t6 = t7 - dl[6], t5 = t6 - dl[5];
+                dl[0] = dl[1]; dl[1] = dl[2]; dl[2] = dl[3]; dl[3] = dl[4];
+                dl[4] = t5; dl[5] = t6; dl[6] = t7; dl[7] = pp;
+            }
+            // adaptive Rice code, tta.c:201-246
+            const u32 u = r > 0 ? ((u32)r * 2u) - 1u : (u32)(-r) * 2u;
+            u64 d;
+            if (u < (1u << k0)) {
+                d = tta_desc(0, k0, u);
+            } else {
+                const u32 shifted = u - (1u << k0);
+                const u32 msb = 1u + (shifted >> k1);
+                const u32 lsb = shifted - ((msb - 1u) << k1);
+                d = tta_desc(msb, k1, lsb);
+                sum1 += shifted - (sum1 >> 4);
+                if (k1 > 0 && (int)sum1 < (1 << (k1 + 4))) k1 -= 1;
+                else if ((int)sum1 > (1 << (k1 + 5))) k1 += 1;
+            }
+            sum0 += u - (sum0 >> 4);
+            if (k0 > 0 && (int)sum0 < (1 << (k0 + 4))) k0 -= 1;
+            else if ((int)sum0 > (1 << (k0 + 5))) k0 += 1;
+            if ((u32)(d >> 59) > 27u) __trap();      // (a Rice parameter beyond the descriptor's field: input outside any PCM width)
+            bits += (u32)d;
+            // descriptors leave in 32-byte pieces (a frame's plane region starts on a multiple of 4)
+            d4[j & 3] = d;
+            if ((j & 3) == 3) {
+                *(ulonglong2*)(out + i - 3) = make_ulonglong2(d4[0], d4[1]);
+                *(ulonglong2*)(out + i - 1) = make_ulonglong2(d4[2], d4[3]);
+            }
         }
     }
     for (u32 i = n & ~3u; i < n; i++) out[i] = d4[i & 3];
@@ -472,7 +498,9 @@ static int encode_core(const b200tta_params* p, const uint8_t* d_pcm, uint64_t n
     TCK(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(u32), cudaMemcpyHostToDevice));
     TCK(cudaMemcpy(d_fr, fr.data(), nf * sizeof(TtaFrame), cudaMemcpyHostToDevice));
     TCK(cudaEventRecord(ev[0]));
-    k_tta_residual<<<(nf * C + 31) / 32, 32>>>(d_pcm, d_fr, nf, C, B, p->bits_per_sample, d_desc, plane, d_bits);
+    if (B == 2) k_tta_residual<2><<<(nf * C + 31) / 32, 32>>>(d_pcm, d_fr, nf, C, p->bits_per_sample, d_desc, plane, d_bits);
+    else if (B == 3) k_tta_residual<3><<<(nf * C + 31) / 32, 32>>>(d_pcm, d_fr, nf, C, p->bits_per_sample, d_desc, plane, d_bits);
+    else k_tta_residual<1><<<(nf * C + 31) / 32, 32>>>(d_pcm, d_fr, nf, C, p->bits_per_sample, d_desc, plane, d_bits);
     TCK(cudaGetLastError());
     TCK(cudaEventRecord(ev[1]));
     k_tta_sizes<<<1, 1024>>>(d_bits, nf, C, d_fbytes, d_off, d_total);

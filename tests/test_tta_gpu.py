@@ -80,3 +80,27 @@ def test_tta_empty_and_errors(built, tmp_path):
         b200tta.encode_frames(b"\0" * 40, 10, 44100, 2, 16, frame_lengths=[4, 4])
     with pytest.raises(b200tta.B200TtaError):
         b200tta.encode_file(os.path.join(str(tmp_path), "no", "dir", "x.tta"), b"\0" * 40, 10, 44100, 2, 16)
+
+
+def test_encode_tta_python_entry(built, tmp_path):
+    """audiotools.encoders.encode_tta(file, pcmreader) (src/encoders/tta.c:31-117): frames to the file object,
+    the list of frame sizes back; every read() of the reader is one frame -- a reader with short reads included"""
+    import io
+    import audiotools
+    from audiotools import encoders
+    rate, ch, bps, n = 44100, 2, 16, 46080 * 2 + 999
+    pcm = helpers.synth_pcm(55, ch, bps, n)
+    f = io.BytesIO()
+    sizes = encoders.encode_tta(f, audiotools.BufferedPCMReader(audiotools.PCMBytesReader(pcm, rate, ch, 0x3, bps)))
+    want, want_sizes = helpers.oracle_tta_frames(pcm, rate, ch, bps)
+    assert f.getvalue() == want and sizes == want_sizes
+    # keyword form, and a reader that hands out 1000 frames at a time whatever it is asked for
+    class Short(audiotools.PCMBytesReader):
+        def read(self, pcm_frames):
+            return audiotools.PCMBytesReader.read(self, min(pcm_frames, 1000))
+    f2 = io.BytesIO()
+    sizes2 = encoders.encode_tta(file=f2, pcmreader=Short(pcm[:4 * 3500], rate, ch, 0x3, bps))
+    want2, want_sizes2 = helpers.oracle_tta_frames(pcm[:4 * 3500], rate, ch, bps, [1000, 1000, 1000, 500])
+    assert f2.getvalue() == want2 and sizes2 == want_sizes2
+    with pytest.raises(TypeError):
+        encoders.encode_tta(f2)
