@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200flac.so")
+LIB_PATH = os.environ.get("B200FLAC_LIB") or os.path.join(_HERE, "libb200flac.so")   # (the override is for A/B builds of tools/)
 
 MAX_LPC_ORDER = 32
 

@@ -516,14 +516,14 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
             enc->p3 = true; enc->p3_img_words = iw; enc->p3_smem = sm;
             // CRC-16 tables: byte tables, x^(8 r) for r <= CHUNK, x^(8 * CHUNK * j)
             const u32 nchunks = (u32)(fb / P3_CHUNK_BYTES + 4);
-            std::vector<unsigned short> t(512 + P3_CHUNK_BYTES + 1 + nchunks);
+            std::vector<unsigned short> t(1024 + P3_CHUNK_BYTES + 1 + nchunks);
             for (u32 b = 0; b < 256; b++) {
                 u32 c = b << 8;
                 for (int k = 0; k < 8; k++) c = (c & 0x8000) ? ((c << 1) ^ 0x8005) & 0xFFFF : (c << 1) & 0xFFFF;
                 t[b] = (unsigned short)c;
             }
-            // t[256 n + x]: CRC of byte x followed by n zero bytes (slicing by two)
-            for (u32 n = 1; n < 2; n++)
+            // t[256 n + x]: CRC of byte x followed by n zero bytes (slicing by four)
+            for (u32 n = 1; n < 4; n++)
                 for (u32 b = 0; b < 256; b++) {
                     const u32 c = t[256 * (n - 1) + b];
                     t[256 * n + b] = (unsigned short)(((c << 8) & 0xFFFF) ^ t[c >> 8]);
@@ -535,10 +535,10 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
                 return r;
             };
             u32 x8 = 0x100, acc = 1;                 // x^8
-            for (u32 r = 0; r <= P3_CHUNK_BYTES; r++) { t[512 + r] = (unsigned short)acc; acc = mul(acc, x8); }
-            const u32 xc = t[512 + P3_CHUNK_BYTES];  // x^(8 * CHUNK)
+            for (u32 r = 0; r <= P3_CHUNK_BYTES; r++) { t[1024 + r] = (unsigned short)acc; acc = mul(acc, x8); }
+            const u32 xc = t[1024 + P3_CHUNK_BYTES];  // x^(8 * CHUNK)
             acc = 1;
-            for (u32 j = 0; j < nchunks; j++) { t[512 + P3_CHUNK_BYTES + 1 + j] = (unsigned short)acc; acc = mul(acc, xc); }
+            for (u32 j = 0; j < nchunks; j++) { t[1024 + P3_CHUNK_BYTES + 1 + j] = (unsigned short)acc; acc = mul(acc, xc); }
             if (cudaMalloc((void**)&enc->d_crc_tab, t.size() * sizeof(unsigned short)) != cudaSuccess ||
                 cudaMemcpy(enc->d_crc_tab, t.data(), t.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess) {
                 enc->p3 = false;
@@ -956,7 +956,7 @@ static void stage_pack_v3(b200flac_encoder* enc, const ChunkView& v, cudaStream_
     const bf_dev_params& P = enc->P;
 #define P3_LAUNCH(NTMAX_, MINB_, SC_) k_pack_v3<NTMAX_, MINB_, SC_><<<v.nf, 2 * enc->NT, enc->p3_smem, st>>>( \
             d_pcm, v.fd, P, (u32)enc->S, v.plans, v.rice, v.choice, v.frame_off, d_out, d_total, out_cap, \
-            enc->p3_img_words, enc->d_crc_tab, enc->d_crc_tab + 512)
+            enc->p3_img_words, enc->d_crc_tab, enc->d_crc_tab + 1024)
     if (2 * enc->NT <= 256 && enc->S == 32) P3_LAUNCH(256, 4, 32);
     else if (2 * enc->NT <= 256) P3_LAUNCH(256, 4, 0);
     else P3_LAUNCH(1024, 1, 0);

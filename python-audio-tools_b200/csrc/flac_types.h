@@ -84,6 +84,8 @@ typedef struct bf_frame_choice {
     uint8_t  n_sub;
     uint8_t  side_slot;                      /* slot coded at bps+1, 0xFF if none */
     uint8_t  pad;
+    uint32_t header_words[4];                /* the frame header with its CRC-8 (header_bytes bytes, zero padded),
+                                                as big-endian words: what k_pack_v3 ORs into the frame image */
 } bf_frame_choice;
 
 #endif

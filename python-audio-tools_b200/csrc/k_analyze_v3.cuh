@@ -22,6 +22,16 @@
 #include "k_analyze_v2.cuh"
 
 #define V3_CH 8
+// The chunk loops stay rolled even where the trip count is a compile-time constant (SC = 32 gives four
+// iterations): unrolled, the kernel's hot code was ~40 KB against a 32 KB instruction cache.
+#ifndef V3_ROLL
+#define V3_ROLL 1
+#endif
+#if V3_ROLL
+#define V3_LOOP _Pragma("unroll 1")
+#else
+#define V3_LOOP
+#endif
 #define V3_SK(i) ((i) + (((i) >> 5) << 2))      // four words of skew per 32 samples
 #define V3_MAX_F 7                               // finest partition order handled (<= 128 partitions; order 8 measured slower than k_analyze_v2,
                                                  // with and without the exhaustive search: 96 kHz/24-bit -e R8 10.6 vs 7.2 ms per 5 minutes)
@@ -43,7 +53,7 @@ struct V3Shared {
     u32 red_or[16], red_diff[16];
     u32 lpc_narrow;       // LPC sum provably fits 32 bits
     short q[BF_MAX_ORDER];
-    bf_lpc_head head;
+    alignas(4) bf_lpc_head head;      // (copied as words)
     uint8_t kheap[2][V3_HEAP];
     uint8_t kbest[V3_HEAP / 2];   // exhaustive search: Rice parameters of the best LPC order so far
 };
@@ -81,6 +91,7 @@ __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_e
         for (u32 p = lane; p < nfine; p += 32) {
             const u64* r = runs + (size_t)p * g;
             u64 sum = p == 0 ? first_extra : 0ull;
+#pragma unroll 1
             for (u32 j = 0; j < g; j++) sum += r[j];
             const u32 plength = (n >> F) - (p == 0 ? order : 0u);
             u32 k;
@@ -105,6 +116,7 @@ __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_e
             if (p < nfine) {
                 const u64* r = runs + (size_t)p * g;
                 u64 sum = p == 0 ? first_extra : 0ull;
+#pragma unroll 1
                 for (u32 j = 0; j < g; j++) sum += r[j];
                 run += sum;
                 pre[p] = run;
@@ -195,6 +207,7 @@ __device__ __forceinline__ void v3_fixed_sums(const int* __restrict__ samp, u32 
     u32 prev, p1, p2, p3;
     v3_fixed_history(samp, base, prev, p1, p2, p3);
     SumT f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+    V3_LOOP
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
         const int4 va = *(const int4*)(samp + V3_SK(i0));
         const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
@@ -275,6 +288,7 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
         w[t] = h.x; w[t + 1] = h.y; w[t + 2] = h.z; w[t + 3] = h.w;
     }
     u64 run = 0;
+    V3_LOOP
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
         const int4 va = *(const int4*)(samp + V3_SK(i0));
         const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
@@ -331,12 +345,13 @@ __device__ __forceinline__ V3FixedCoef v3_fixed_coef(u32 order)
 // sum of (zigzag(r) >> k) over the thread's run for the FIXED residual of `order`, recomputed from the
 // samples (the sum fits 32 bits: see the Rice parameter rule, flac.c:1478).  skip: this is run 0, whose
 // first `order` positions are warm-up samples and do not count.
-template <bool KZERO>
+// (k >= 1; a Rice parameter of 0 -- a partition of near silence -- takes v3_fixed_bits_k0: one hot copy of the loop)
 __device__ __forceinline__ u32 v3_fixed_bits_loop(const int* __restrict__ samp, u32 base, u32 S, u32 km1, const V3FixedCoef c)
 {
     int4 h = make_int4(0, 0, 0, 0);                       // samples base-4 .. base-1
     if (base) h = *(const int4*)(samp + V3_SK(base - 4));
     u32 acc = 0;
+    V3_LOOP
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
         const int4 va = *(const int4*)(samp + V3_SK(i0));
         const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
@@ -344,9 +359,22 @@ __device__ __forceinline__ u32 v3_fixed_bits_loop(const int* __restrict__ samp, 
 #pragma unroll
         for (int j = 0; j < V3_CH; j++) {
             const int r = w[j + 4] + c.c1 * w[j + 3] + c.c2 * w[j + 2] + c.c3 * w[j + 1] + c.c4 * w[j];
-            acc += KZERO ? zigzag(r) : v3_fold_shift(r, km1);
+            acc += v3_fold_shift(r, km1);
         }
         h = vb;
+    }
+    return acc;
+}
+
+// the same sum for k == 0, one sample per iteration: rare, so small code matters more than speed
+__device__ __noinline__ u32 v3_fixed_bits_k0(const int* __restrict__ samp, u32 base, u32 S, const V3FixedCoef c)
+{
+    u32 acc = 0;
+#pragma unroll 1
+    for (u32 i = base; i < base + S; i++) {
+        const int s1 = i >= 1 ? samp[V3_SK(i - 1)] : 0, s2 = i >= 2 ? samp[V3_SK(i - 2)] : 0;
+        const int s3 = i >= 3 ? samp[V3_SK(i - 3)] : 0, s4 = i >= 4 ? samp[V3_SK(i - 4)] : 0;
+        acc += zigzag(samp[V3_SK(i)] + c.c1 * s1 + c.c2 * s2 + c.c3 * s3 + c.c4 * s4);
     }
     return acc;
 }
@@ -354,9 +382,10 @@ __device__ __forceinline__ u32 v3_fixed_bits_loop(const int* __restrict__ samp, 
 __device__ __forceinline__ u32 v3_fixed_bits_any(const int* __restrict__ samp, u32 base, u32 S, u32 k, u32 order, u32 skip)
 {
     const V3FixedCoef c = v3_fixed_coef(order);
-    u32 acc = k ? v3_fixed_bits_loop<false>(samp, base, S, k - 1, c) : v3_fixed_bits_loop<true>(samp, base, S, 0, c);
+    u32 acc = k ? v3_fixed_bits_loop(samp, base, S, k - 1, c) : v3_fixed_bits_k0(samp, base, S, c);
     if (skip) {
         // run 0: take the warm-up positions back out (they were evaluated with zeros before the block)
+#pragma unroll 1
         for (u32 j = 0; j < order; j++) {
             const int s0 = samp[V3_SK(j)];
             const int s1 = j >= 1 ? samp[V3_SK(j - 1)] : 0, s2 = j >= 2 ? samp[V3_SK(j - 2)] : 0;
@@ -375,6 +404,7 @@ __device__ __forceinline__ u32 v3_stored_bits(const int* __restrict__ resid, u32
     u32 acc = 0;
     if (k) {
         const u32 km1 = k - 1;
+        V3_LOOP
         for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
             const int4 va = *(const int4*)(resid + V3_SK(i0));
             const int4 vb = *(const int4*)(resid + V3_SK(i0) + 4);
@@ -382,13 +412,10 @@ __device__ __forceinline__ u32 v3_stored_bits(const int* __restrict__ resid, u32
             acc += v3_fold_shift(vb.x, km1) + v3_fold_shift(vb.y, km1) + v3_fold_shift(vb.z, km1) + v3_fold_shift(vb.w, km1);
         }
     } else {
-        for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
-            const int4 va = *(const int4*)(resid + V3_SK(i0));
-            const int4 vb = *(const int4*)(resid + V3_SK(i0) + 4);
-            acc += zigzag(va.x) + zigzag(va.y) + zigzag(va.z) + zigzag(va.w);
-            acc += zigzag(vb.x) + zigzag(vb.y) + zigzag(vb.z) + zigzag(vb.w);
-        }
+#pragma unroll 1
+        for (u32 i = base; i < base + S; i++) acc += zigzag(resid[V3_SK(i)]);      // (rare: small code, not speed)
     }
+#pragma unroll 1
     for (u32 i = 0; i < skip; i++) acc -= zigzag(resid[V3_SK(base + i)]) >> k;
     return acc;
 }
@@ -407,7 +434,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
 {
     const u32 S = SC ? (u32)SC : S_rt;       // samples per thread: a compile-time 32 for the common shapes
     const u32 tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    const u32 frame = unit / P.K, cand = unit % P.K;
+    const u32 frame = P.K == 4 ? unit >> 2 : unit / P.K, cand = P.K == 4 ? unit & 3u : unit % P.K;
     const bf_frame_desc d = fd[frame];
     const u32 n = d.nsamp;
     if (n != P.block_size) return;
@@ -423,7 +450,9 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     // ---- LPC model of the unit (last warp; overlaps the PCM load of the others) ----
     const short* mycoef = coefs + (size_t)unit * P.model_stride;
     if (warp == nw - 1) {
-        if (lane == 0) sh.head = heads[unit];
+        // (36 bytes of byte-sized fields: copied as nine words, one per lane -- the struct assignment was 87 instructions)
+        static_assert(sizeof(bf_lpc_head) == 36, "bf_lpc_head is copied as nine 32-bit words");
+        if (lane < 9) ((u32*)&sh.head)[lane] = ((const u32*)(heads + unit))[lane];
         __syncwarp();
         if (!EXH) {
             const u32 o = sh.head.best_order;
@@ -447,15 +476,17 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
             if ((((uintptr_t)src) & 15) == 0) {
                 const uint4* s4 = (const uint4*)src;
                 // all the loads of a batch are issued before the first is used: one memory latency
-                // per batch of 8 x 16 bytes, not per load
+                // per batch of 4 x 16 bytes, not per load (batches of 8, unrolled, were 100 instructions more
+                // of hot code for the same time)
                 const u32 stride = nt * 4;
                 u32 i = tid * 4;
-                for (; i + 7 * stride < n; i += 8 * stride) {
-                    uint4 w8[8];
+                V3_LOOP
+                for (; i + 3 * stride < n; i += 4 * stride) {
+                    uint4 w8[4];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) w8[q] = __ldg(s4 + ((i + q * stride) >> 2));
+                    for (int q = 0; q < 4; q++) w8[q] = __ldg(s4 + ((i + q * stride) >> 2));
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
+                    for (int q = 0; q < 4; q++) {
                         int4 v;
                         v.x = __dp2a_lo((int)w8[q].x, coef, 0) >> shv; v.y = __dp2a_lo((int)w8[q].y, coef, 0) >> shv;
                         v.z = __dp2a_lo((int)w8[q].z, coef, 0) >> shv; v.w = __dp2a_lo((int)w8[q].w, coef, 0) >> shv;
@@ -493,8 +524,8 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     diff = __reduce_or_sync(0xFFFFFFFFu, diff);
     if (lane == 0) { sh.red_or[warp] = orv; sh.red_diff[warp] = diff; }
     __syncthreads();                                                             // (1)
-    orv = 0; diff = 0;
-    for (u32 w = 0; w < nw; w++) { orv |= sh.red_or[w]; diff |= sh.red_diff[w]; }
+    orv = __reduce_or_sync(0xFFFFFFFFu, lane < nw ? sh.red_or[lane] : 0u);
+    diff = __reduce_or_sync(0xFFFFFFFFu, lane < nw ? sh.red_diff[lane] : 0u);
 
     if (diff == 0) {
         // CONSTANT, always written with wasted = 0 (H8)
@@ -521,11 +552,13 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
             v3_fixed_sums<u32>(samp, base, S, e);
             if (tid == 0) v3_fixed_head<u32>(samp, e, sh.corr);
 #pragma unroll
+            for (int k = 0; k < 5; k++) runsF[k * nt + tid] = (u64)e[k];
+            // 32 runs x 2^26 fit 32 bits; the two halves are summed over <= 16 warps with native
+            // 32-bit shared atomics (a 64-bit one is a compare-and-swap loop).  One rolled copy of the
+            // reduction for the five orders (each thread reads its own sums back).
+#pragma unroll 1
             for (int k = 0; k < 5; k++) {
-                runsF[k * nt + tid] = (u64)e[k];
-                // 32 runs x 2^26 fit 32 bits; the two halves are summed over <= 16 warps with native
-                // 32-bit shared atomics (a 64-bit one is a compare-and-swap loop)
-                const u32 ws = __reduce_add_sync(0xFFFFFFFFu, e[k]);
+                const u32 ws = __reduce_add_sync(0xFFFFFFFFu, (u32)runsF[k * nt + tid]);
                 if (lane == 0) { atomicAdd(&sh.totF16[k][0], ws & 0xFFFFu); atomicAdd(&sh.totF16[k][1], ws >> 16); }
             }
         } else {
@@ -533,9 +566,10 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
             v3_fixed_sums<u64>(samp, base, S, e);
             if (tid == 0) v3_fixed_head<u64>(samp, e, sh.corr);
 #pragma unroll
+            for (int k = 0; k < 5; k++) runsF[k * nt + tid] = e[k];
+#pragma unroll 1
             for (int k = 0; k < 5; k++) {
-                runsF[k * nt + tid] = e[k];
-                u64 ws = e[k];
+                u64 ws = runsF[k * nt + tid];
 #pragma unroll
                 for (int o = 16; o; o >>= 1) ws += __shfl_xor_sync(0xFFFFFFFFu, ws, o);
                 if (lane == 0) atomicAdd(&sh.totF[k], ws);
@@ -558,7 +592,10 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
                                        : v3_lpc_residual<12, true>(samp, resid, base, S, sh.q, shift);
         else run = narrow ? v3_lpc_residual<32, false>(samp, resid, base, S, sh.q, shift)
                           : v3_lpc_residual<32, true>(samp, resid, base, S, sh.q, shift);
-        if (tid == 0) for (u32 i = 0; i < o; i++) run -= (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions
+        if (tid == 0) {
+#pragma unroll 1
+            for (u32 i = 0; i < o; i++) run -= (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions
+        }
         return run;
     };
     if (!EXH) {
@@ -583,13 +620,11 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     {
         const u32 role = (nw & (nw - 1)) == 0 ? ((warp - unit) & (nw - 1)) : (warp + nw - unit % nw) % nw;
         for (u32 task = role; task < (EXH ? 2u : 4u); task += nw) {
-            // prefix sums go to the run-sum rows of two FIXED orders that lost
-            if (task < 2)
-                v3_levels(runsF + (size_t)fixed_order * nt, sh.corr[fixed_order], S, n, fixed_order, F, P.max_rice,
-                          sh.kheap[0], sh.lvl[0], runsF + (size_t)((fixed_order + 1) % 5) * nt, task);
-            else
-                v3_levels(runsL, 0ull, S, n, lpc_order, F, P.max_rice,
-                          sh.kheap[1], sh.lvl[1], runsF + (size_t)((fixed_order + 2) % 5) * nt, task - 2);
+            // prefix sums go to the run-sum rows of two FIXED orders that lost; one call site for both models
+            const bool lpc = task >= 2;
+            v3_levels(lpc ? runsL : runsF + (size_t)fixed_order * nt, lpc ? 0ull : sh.corr[fixed_order], S, n,
+                      lpc ? lpc_order : fixed_order, F, P.max_rice, sh.kheap[lpc ? 1 : 0], sh.lvl[lpc ? 1 : 0],
+                      runsF + (size_t)((fixed_order + (lpc ? 2u : 1u)) % 5) * nt, task & 1u);
         }
     }
     __syncthreads();                                                             // (3)
@@ -675,26 +710,26 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
         const u32 koff = (1u << poL) - 1u;
         for (u32 p = tid; p < (1u << poL); p += nt) my_rice[p] = EXH ? sh.kbest[p] : sh.kheap[1][koff + p];
     }
-    if (tid == 0) {
-        b200flac_plan plan;
-        memset(&plan, 0, sizeof(plan));
-        plan.wasted = (uint8_t)wasted;
-        if (choice == BF_FIXED) {
-            plan.type = BF_FIXED; plan.order = (uint8_t)fixed_order;
-            plan.coding_method = (uint8_t)methodF; plan.partition_order = (uint8_t)poF;
-            plan.bits = fb;
-        } else if (choice == BF_LPC) {
-            plan.type = BF_LPC; plan.order = (uint8_t)lpc_order;
-            plan.precision = (uint8_t)precision; plan.shift = (int8_t)lpc_shift;
-            plan.coding_method = (uint8_t)methodL; plan.partition_order = (uint8_t)poL;
-            plan.flags = lpc_narrow ? 2 : 0;          // packer may accumulate in 32 bits
-            plan.bits = lb;
-            for (u32 j = 0; j < lpc_order; j++) plan.coeffs[j] = EXH ? mycoef[(lpc_order * (lpc_order - 1)) / 2 + j] : sh.q[j];
-        } else {
-            plan.type = BF_VERBATIM;
-            plan.bits = hdr_bits + sub_bps * n;       // flac.c:832-854
+    // the plan goes out as 19 words, one per thread: two of byte fields, the size, sixteen pairs of coefficients
+    // (the struct assignment it replaces was ~100 instructions for thread 0)
+    static_assert(sizeof(b200flac_plan) == 76 && B200FLAC_MAX_LPC_ORDER == 32, "b200flac_plan is written as 19 words");
+    if (tid < 19) {
+        u32 word = 0;
+        const bool is_lpc = choice == BF_LPC, is_fixed = choice == BF_FIXED;
+        if (tid == 0)      // type | order | wasted | precision
+            word = choice | ((is_fixed ? fixed_order : is_lpc ? lpc_order : 0u) << 8) | (wasted << 16) | ((is_lpc ? precision : 0u) << 24);
+        else if (tid == 1) // shift | coding method | partition order | flags (bit 1: the packer may accumulate in 32 bits)
+            word = (is_lpc ? ((u32)lpc_shift & 0xFFu) : 0u) | ((is_fixed ? methodF : is_lpc ? methodL : 0u) << 8) |
+                   ((is_fixed ? poF : is_lpc ? poL : 0u) << 16) | ((is_lpc && lpc_narrow ? 2u : 0u) << 24);
+        else if (tid == 2) // exact size; VERBATIM: flac.c:832-854
+            word = is_fixed ? fb : is_lpc ? lb : hdr_bits + sub_bps * n;
+        else if (is_lpc) {
+            const u32 j = 2 * (tid - 3);
+            const short c0 = j < lpc_order ? (EXH ? mycoef[(lpc_order * (lpc_order - 1)) / 2 + j] : sh.q[j]) : (short)0;
+            const short c1 = j + 1 < lpc_order ? (EXH ? mycoef[(lpc_order * (lpc_order - 1)) / 2 + j + 1] : sh.q[j + 1]) : (short)0;
+            word = (u32)(unsigned short)c0 | ((u32)(unsigned short)c1 << 16);
         }
-        plans[unit] = plan;
+        ((u32*)(plans + unit))[tid] = word;
     }
 }
 

@@ -263,8 +263,7 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
             if (lane == 0) mbar_expect_tx(&hdr->bar[b], total);
             __syncwarp();
             if (bytes) bulk_g2s(dst, src, bytes, &hdr->bar[b]);
-            return;
-        }
+        } else {
         for (u32 r = 0; r < nrows; r++) {
             const u32 rn = hdr->row_n[r];
             if (i0 < rn) {
@@ -280,6 +279,7 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
         const u32 take = min(TS, nmax - i0);
         for (u32 w = lane; w < take; w += 32) cp_async8(wbuf + b * g.WT + w, windows + woff0 + i0 + w);
         cp_async_commit();
+        }
     };
     // wait until tile buffer b holds its data; `more`: another tile is in flight behind it
     auto wait_tile = [&](u32 b, bool more) {

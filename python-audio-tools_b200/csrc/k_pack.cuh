@@ -37,6 +37,35 @@ __device__ __forceinline__ u32 block_size_code(u32 bs)
     }
 }
 
+// the bytes of a frame header, flac.c:488-517, CRC-8 included; returns their number (6..16)
+__device__ inline u32 build_frame_header(uint8_t (&h)[16], const bf_frame_desc& d, const bf_dev_params& P, u32 assignment)
+{
+    u32 nb = 0;
+    const u32 bsc = block_size_code(d.nsamp);
+    h[nb++] = 0xFF;
+    h[nb++] = 0xF8;                                   // sync, reserved 0, blocking strategy 0
+    h[nb++] = (uint8_t)((bsc << 4) | P.sr_code);
+    h[nb++] = (uint8_t)((assignment << 4) | (P.bps_code << 1));
+    const u32 v = d.frame_number;
+    if (v <= 0x7F) {
+        h[nb++] = (uint8_t)v;
+    } else {
+        const u32 tb = utf8_bytes(v);
+        int shift = (int)(tb - 1) * 6;
+        h[nb++] = (uint8_t)(((0xFFu << (8 - tb)) & 0xFF) | ((v >> shift) & ((1u << (7 - tb)) - 1u)));
+        for (shift -= 6; shift >= 0; shift -= 6) h[nb++] = (uint8_t)(0x80 | ((v >> shift) & 0x3F));
+    }
+    if (bsc == 6) h[nb++] = (uint8_t)(d.nsamp - 1);
+    else if (bsc == 7) { h[nb++] = (uint8_t)((d.nsamp - 1) >> 8); h[nb++] = (uint8_t)(d.nsamp - 1); }
+    if (P.sr_code == 0xC) h[nb++] = (uint8_t)(P.sample_rate / 1000);
+    else if (P.sr_code == 0xD) { h[nb++] = (uint8_t)(P.sample_rate >> 8); h[nb++] = (uint8_t)P.sample_rate; }
+    else if (P.sr_code == 0xE) { h[nb++] = (uint8_t)((P.sample_rate / 10) >> 8); h[nb++] = (uint8_t)(P.sample_rate / 10); }
+    u32 crc = 0;
+    for (u32 i = 0; i < nb; i++) crc = crc8_byte(crc, h[i]);
+    h[nb++] = (uint8_t)crc;
+    return nb;
+}
+
 __global__ void k_frame_select(const bf_frame_desc* __restrict__ fd, u32 n_frames, bf_dev_params P,
                                const b200flac_plan* __restrict__ plans, bf_frame_choice* __restrict__ choice,
                                u32* __restrict__ frame_bytes)
@@ -75,6 +104,15 @@ __global__ void k_frame_select(const bf_frame_desc* __restrict__ fd, u32 n_frame
         bits += plans[ch.unit[s]].bits;
     }
     ch.frame_bytes = (u32)((bits + 7) >> 3) + 2;
+    {
+        // the header's bytes are made here, once per frame by one thread of a tiny kernel, not by thread 0 of the
+        // packing CTA (where they were ~150 instructions of an instruction-fetch-bound kernel's hot code)
+        uint8_t h[16];
+        for (int i = 0; i < 16; i++) h[i] = 0;
+        build_frame_header(h, d, P, ch.assignment);
+        for (int w = 0; w < 4; w++)
+            ch.header_words[w] = ((u32)h[4 * w] << 24) | ((u32)h[4 * w + 1] << 16) | ((u32)h[4 * w + 2] << 8) | (u32)h[4 * w + 3];
+    }
     choice[f] = ch;
     frame_bytes[f] = ch.frame_bytes;
 }
@@ -144,29 +182,7 @@ template <class Sink>
 __device__ void put_frame_header(Sink& bs, const bf_frame_desc& d, const bf_dev_params& P, u32 assignment)
 {
     uint8_t h[16];
-    u32 nb = 0;
-    const u32 bsc = block_size_code(d.nsamp);
-    h[nb++] = 0xFF;
-    h[nb++] = 0xF8;                                   // sync, reserved 0, blocking strategy 0
-    h[nb++] = (uint8_t)((bsc << 4) | P.sr_code);
-    h[nb++] = (uint8_t)((assignment << 4) | (P.bps_code << 1));
-    const u32 v = d.frame_number;
-    if (v <= 0x7F) {
-        h[nb++] = (uint8_t)v;
-    } else {
-        const u32 tb = utf8_bytes(v);
-        int shift = (int)(tb - 1) * 6;
-        h[nb++] = (uint8_t)(((0xFFu << (8 - tb)) & 0xFF) | ((v >> shift) & ((1u << (7 - tb)) - 1u)));
-        for (shift -= 6; shift >= 0; shift -= 6) h[nb++] = (uint8_t)(0x80 | ((v >> shift) & 0x3F));
-    }
-    if (bsc == 6) h[nb++] = (uint8_t)(d.nsamp - 1);
-    else if (bsc == 7) { h[nb++] = (uint8_t)((d.nsamp - 1) >> 8); h[nb++] = (uint8_t)(d.nsamp - 1); }
-    if (P.sr_code == 0xC) h[nb++] = (uint8_t)(P.sample_rate / 1000);
-    else if (P.sr_code == 0xD) { h[nb++] = (uint8_t)(P.sample_rate >> 8); h[nb++] = (uint8_t)P.sample_rate; }
-    else if (P.sr_code == 0xE) { h[nb++] = (uint8_t)((P.sample_rate / 10) >> 8); h[nb++] = (uint8_t)(P.sample_rate / 10); }
-    u32 crc = 0;
-    for (u32 i = 0; i < nb; i++) crc = crc8_byte(crc, h[i]);
-    h[nb++] = (uint8_t)crc;
+    const u32 nb = build_frame_header(h, d, P, assignment);
     for (u32 i = 0; i < nb; i++) bs.put(h[i], 8);
 }
 

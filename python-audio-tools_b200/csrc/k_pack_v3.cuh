@@ -86,6 +86,36 @@ struct RunSink3 {
     }
 };
 
+// one field of 1..32 bits (v < 2^nbits) at a known bit position of the zero-initialised image.  A single,
+// not inlined copy serves every header field, warm-up sample and coefficient: the inlined writers these
+// replace were ~150 instructions of hot code executed by a handful of threads.
+#ifndef P3_FIELD_INLINE
+#define P3_FIELD_INLINE 1      /* (a real call cost 0.28 ms per hour: measured) */
+#endif
+#if P3_FIELD_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void p3_field(u32* img, u32 bitpos, u32 v, u32 nbits)
+{
+    const u32 w = bitpos >> 5, o = bitpos & 31;
+    const u64 x = (u64)v << (64 - o - nbits);
+    if ((u32)(x >> 32)) atomicOr(img + w, (u32)(x >> 32));
+    if ((u32)x) atomicOr(img + w + 1, (u32)x);
+}
+__device__ __forceinline__ void p3_field_signed(u32* img, u32 bitpos, int v, u32 nbits)
+{
+    p3_field(img, bitpos, nbits >= 32 ? (u32)v : ((u32)v & ((1u << nbits) - 1u)), nbits);
+}
+// subframe header (flac.c:820-826 / 897-905 / 977-985): 0 | type (6 bits) | wasted flag, then the unary
+// count of wasted bits -- zeros that are already there and a one
+__device__ __forceinline__ void p3_subframe_header(u32* img, u32 bit0, u32 type_bits, u32 wasted)
+{
+    p3_field(img, bit0, ((type_bits & 0x3F) << 1) | (wasted ? 1u : 0u), 8);
+    if (wasted) p3_field(img, bit0 + 8 + wasted - 1, 1, 1);
+}
+
 // a Rice code longer than 32 bits: a run of zeros, then the stop bit and the k low bits (rare)
 __device__ __forceinline__ void p3_put_long(RunSink3& bs, u32 msb, u32 code, u32 k)
 {
@@ -98,8 +128,8 @@ __device__ __forceinline__ void p3_put_long(RunSink3& bs, u32 msb, u32 code, u32
 __device__ __forceinline__ u32 p3_gf16_mul(u32 a, u32 b, const unsigned short* tab)
 {
     u32 r = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) r ^= ((b >> i) & 1u) ? (a << i) : 0u;
+#pragma unroll 1
+    for (int i = 0; i < 16; i++) r ^= ((b >> i) & 1u) ? (a << i) : 0u;       // (once per thread: rolled, small code)
     const u32 hi = r >> 16;
     return (r & 0xFFFFu) ^ (u32)tab[256 + (hi >> 8)] ^ (u32)tab[hi & 0xFF];
 }
@@ -216,11 +246,11 @@ __device__ __forceinline__ u32 p3_fixed_inplace(int* __restrict__ buf, u32 base,
 __host__ __device__ inline size_t p3_smem_bytes(u32 block_size, u32 img_words)
 {
     const size_t padn = ((size_t)V3_SK(block_size) + 8 + 3) & ~(size_t)3;
-    return 2 * padn * 4 + (size_t)(img_words + 12) * 4 + 1024 + 32;
+    return 2 * padn * 4 + (size_t)(img_words + 12) * 4 + 2048 + 32;
 }
 
 // blockDim.x = 2 * gt; gt * S >= block_size; S a multiple of 8.
-//   crc_tab[2][256]: CRC-16 of one byte followed by 0..1 zero bytes; crc_pow[0..CHUNK] = x^(8 r), crc_pow[CHUNK + 1 + j] = x^(8 * CHUNK * j), CHUNK = 60 bytes, mod the
+//   crc_tab[4][256]: CRC-16 of one byte followed by 0..3 zero bytes; crc_pow[0..CHUNK] = x^(8 r), crc_pow[CHUNK + 1 + j] = x^(8 * CHUNK * j), CHUNK = 60 bytes, mod the
 //   CRC-16 polynomial (built by the host).
 template <int NTMAX, int MINB, int SC>
 __global__ void __launch_bounds__(NTMAX, MINB)
@@ -241,10 +271,11 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
     const size_t padn = ((size_t)V3_SK(P.block_size) + 8 + 3) & ~(size_t)3;     // keeps the image 16-byte aligned
     int* buf = (int*)dyn_smem + (size_t)g * padn;
     u32* img = (u32*)((int*)dyn_smem + 2 * padn);
-    unsigned short* tab = (unsigned short*)(img + ((img_words + 8 + 3) & ~3u));   // past the zeroing's overshoot
+    unsigned short* tab = (unsigned short*)(img + ((img_words + 8 + 3) & ~3u));   // past the zeroing's overshoot; 4 x 256 entries
 
     if (tid == 0) sh.choice = choice[frame];
-    for (u32 t = tid; t < 256; t += nt) ((u32*)tab)[t] = ((const u32*)crc_tab)[t];      // 2 x 256 entries
+#pragma unroll 1
+    for (u32 t = tid; t < 512; t += nt) ((u32*)tab)[t] = ((const u32*)crc_tab)[t];      // 4 x 256 entries
     const bf_frame_desc d = fd[frame];
     const u32 n = d.nsamp;
     // the whole image is cleared (not just this frame's extent) so that one barrier covers everything
@@ -253,11 +284,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
     const u32 frame_bytes = sh.choice.frame_bytes, n_sub = sh.choice.n_sub;
     const u32 nwords = (frame_bytes + 3) >> 2;
     if (nwords + 2 > img_words + 4) __trap();    // cannot happen: the image is sized for the largest frame
-    if (tid == 0) {
-        SmemSink hs; hs.init(img, 0);
-        put_frame_header(hs, d, P, sh.choice.assignment);
-        hs.flush();
-    }
+    if (tid < 4 && sh.choice.header_words[tid]) atomicOr(img + tid, sh.choice.header_words[tid]);   // frame header + CRC-8 (k_frame_select)
 
     const u32 base = gtid * S;
     const u32 end = min(base + S, n);
@@ -265,11 +292,11 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
         const u32 slot = slot0 + g;
         if (slot >= n_sub) break;                // this group is done (group-uniform)
         const u32 unit = sh.choice.unit[slot];
-        const u32 cand = unit % P.K;
+        const u32 cand = P.K == 4 ? unit & 3u : unit % P.K;
         const u32 bps = candidate_bps(cand, P);
         const u32 bit0 = sh.choice.bitoff[slot];
         const uint8_t* krice = rice + (size_t)unit * P.rice_stride;
-        if (gtid == 0) sh.plan[g] = plans[unit];
+        if (gtid < 19) ((u32*)&sh.plan[g])[gtid] = ((const u32*)(plans + unit))[gtid];     // 76 bytes as 19 words
         if (gtid < BF_MAX_ORDER) {
             const b200flac_plan* gp = plans + unit;
             sh.q[g][gtid] = (gp->type == BF_LPC && gtid < gp->order) ? gp->coeffs[gtid] : (short)0;
@@ -316,10 +343,8 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
 
         if (ptype == BF_CONSTANT) {
             if (gtid == 0) {
-                SmemSink bs; bs.init(img, bit0);
-                put_subframe_header_s(bs, 0, 0);
-                bs.put_signed(buf[0], bps);
-                bs.flush();
+                p3_subframe_header(img, bit0, 0, 0);
+                p3_field_signed(img, bit0 + 8, buf[0], bps);
             }
         } else {
             if (wasted) {
@@ -327,11 +352,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                 p3_group_bar(g, gt);
             }
             if (ptype == BF_VERBATIM) {
-                if (gtid == 0) {
-                    SmemSink bs; bs.init(img, bit0);
-                    put_subframe_header_s(bs, 1, wasted);
-                    bs.flush();
-                }
+                if (gtid == 0) p3_subframe_header(img, bit0, 1, wasted);
                 if (base < n) {
                     RunSink3 bs; bs.init(img, bit0 + 8 + wasted + base * sub_bps);
                     const u32 mask = sub_bps >= 32 ? 0xFFFFFFFFu : ((1u << sub_bps) - 1u);
@@ -347,31 +368,17 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                 // header, warm-up samples and coefficients, every field at its known bit position: lane i
                 // writes warm-up sample i and coefficient i (read before anyone passes the barrier below)
                 if (gtid < order) {
-                    SmemSink bs; bs.init(img, bit0 + 8 + wasted + gtid * sub_bps);
-                    bs.put_signed(buf[V3_SK(gtid)], sub_bps);
-                    bs.flush();
+                    p3_field_signed(img, bit0 + 8 + wasted + gtid * sub_bps, buf[V3_SK(gtid)], sub_bps);
                     if (ptype == BF_LPC) {
                         const u32 prec = sh.plan[g].precision;
-                        SmemSink cs; cs.init(img, bit0 + 8 + wasted + order * sub_bps + 9 + gtid * prec);
-                        cs.put_signed(sh.plan[g].coeffs[gtid], prec);
-                        cs.flush();
+                        p3_field_signed(img, bit0 + 8 + wasted + order * sub_bps + 9 + gtid * prec, sh.plan[g].coeffs[gtid], prec);
                     }
                 }
                 if (gtid == 0) {
-                    SmemSink bs; bs.init(img, bit0);
-                    if (ptype == BF_FIXED) put_subframe_header_s(bs, 0x8 | order, wasted);
-                    else put_subframe_header_s(bs, 0x20 | (order - 1), wasted);
-                    bs.flush();
-                    if (ptype == BF_LPC) {
-                        SmemSink ps; ps.init(img, bit0 + 8 + wasted + order * sub_bps);
-                        ps.put(sh.plan[g].precision - 1, 4);
-                        ps.put_signed(sh.plan[g].shift, 5);
-                        ps.flush();
-                    }
-                    SmemSink ms; ms.init(img, hdr_end);
-                    ms.put(sh.plan[g].coding_method, 2);
-                    ms.put(po, 4);
-                    ms.flush();
+                    p3_subframe_header(img, bit0, ptype == BF_FIXED ? (0x8 | order) : (0x20 | (order - 1)), wasted);
+                    if (ptype == BF_LPC)    // 4 bits of precision - 1, 5 bits of signed shift
+                        p3_field(img, bit0 + 8 + wasted + order * sub_bps, ((sh.plan[g].precision - 1) << 5) | ((u32)sh.plan[g].shift & 31u), 9);
+                    p3_field(img, hdr_end, (sh.plan[g].coding_method << 4) | po, 6);
                 }
                 const u32 res0 = hdr_end + 6;
                 const int shift = sh.plan[g].shift;
@@ -384,7 +391,7 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                 const u32 p_first = (have && !under) ? c.lo / plen : 0u;
                 u32 lead = 0;
                 if (have) {
-                    if (c.lo == order) lead = under ? 1u : (c.lo / plen + 1u);    // partitions 0..p_first (an empty leading one too)
+                    if (c.lo == order) lead = under ? 1u : (p_first + 1u);        // partitions 0..p_first (an empty leading one too)
                     else if (!under && c.lo == p_first * plen) lead = 1;
                 }
                 const u32 next0 = under ? 0xFFFFFFFFu : (p_first + 1) * plen;
@@ -441,11 +448,8 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                     if (n == order) first_trailing = 0;
                     else if (under) first_trailing = 1;
                     else first_trailing = 1u << po;
-                    if (first_trailing < (1u << po)) {
-                        SmemSink bs; bs.init(img, res0 + totalbits);
-                        for (u32 p = first_trailing; p < (1u << po); p++) bs.put(krice[p], kbits);
-                        bs.flush();
-                    }
+#pragma unroll 1
+                    for (u32 p = first_trailing; p < (1u << po); p++) p3_field(img, res0 + totalbits + (p - first_trailing) * kbits, krice[p], kbits);
                 }
             }
         }
@@ -462,13 +466,12 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
         const u32* wp = img + c * P3_CHUNK_WORDS;
         u32 crc = 0;
         u32 b = b0;
+#pragma unroll 1
         for (; b + 4 <= b1; b += 4) {
-            // two bytes at once: tab[256 + x] = CRC of byte x followed by a zero byte
-            const u32 w = *wp++;
-            const u32 a = (w >> 16) ^ crc;
-            crc = (u32)tab[256 + (a >> 8)] ^ (u32)tab[a & 0xFF];
-            const u32 b2 = (w & 0xFFFF) ^ crc;
-            crc = (u32)tab[256 + (b2 >> 8)] ^ (u32)tab[b2 & 0xFF];
+            // four bytes at once: tab[256 n + x] = CRC of byte x followed by n zero bytes, so the four lookups
+            // of a word are independent of each other (one shared-memory latency per word on the serial chain)
+            const u32 a = *wp++ ^ (crc << 16);
+            crc = (u32)tab[768 + (a >> 24)] ^ (u32)tab[512 + ((a >> 16) & 0xFF)] ^ (u32)tab[256 + ((a >> 8) & 0xFF)] ^ (u32)tab[a & 0xFF];
         }
         if (b < b1) {
             const u32 w = *wp;
@@ -499,6 +502,12 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
     u32* dw = (u32*)(dst + hb);
     // output byte i of word j is image byte h + 4 j + i: bytes h..3 of img[j], then 0..h-1 of img[j + 1]
     const u32 sel = h == 0 ? 0x0123u : h == 1 ? 0x7012u : h == 2 ? 0x6701u : 0x5670u;
+#ifndef P3_COPY_UNROLL
+#define P3_COPY_UNROLL 1
+#endif
+#define P3_PRAGMA_(x) _Pragma(#x)
+#define P3_UNROLL_(n) P3_PRAGMA_(unroll n)
+    P3_UNROLL_(P3_COPY_UNROLL)
     for (u32 j = tid; j < body; j += nt) dw[j] = __byte_perm(img[j], img[j + 1], sel);
     const u32 done = hb + 4 * body;
     if (tid < nb - done) {
