@@ -33,8 +33,9 @@
 #define V3_LOOP
 #endif
 #define V3_SK(i) ((i) + (((i) >> 5) << 2))      // four words of skew per 32 samples
+#ifndef V3_MAX_F
 #define V3_MAX_F 7                               // finest partition order handled (<= 128 partitions; order 8 measured slower than k_analyze_v2,
-                                                 // with and without the exhaustive search: 96 kHz/24-bit -e R8 10.6 vs 7.2 ms per 5 minutes)
+#endif                                           // with and without the exhaustive search: 96 kHz/24-bit -e R8 10.6 vs 7.2 ms per 5 minutes)
 #define V3_HEAP (2 << V3_MAX_F)
 
 // totals of one partition order of one model (written by whichever warp evaluated the level)
@@ -45,14 +46,18 @@ struct V3Level {
 };
 
 struct V3Shared {
-    V3Level lvl[2][V3_MAX_F + 1];
+    V3Level lvl[2][V3_MAX_F + 3];   // [..][V3_MAX_F + 1], [V3_MAX_F + 2]: the two halves of a finest level evaluated by two warps
     u64 totF[5];          // FIXED: block totals of the error sums (flac.c:877-893), wide blocks
     u32 totF16[5][2];     // ... narrow blocks: sums of the low 16 bits / the rest of the warp sums
     u32 bits16[2][2];     // exact sum of (u >> k), per model, split the same way
     u64 corr[5];          // FIXED: sum of |r_k[i]| for k <= i < 4 (in the partition sums, not in the order choice)
     u32 red_or[16], red_diff[16];
-    u32 lpc_narrow;       // LPC sum provably fits 32 bits
+    u32 lpc_narrow;       // sum of |coefficient| of the staged order (turned into "the sum fits 32 bits" by its readers)
+    u32 lpc_narrow2[2];   // exhaustive search: the same for the two staged orders
+    u32 bitsL[2][2];      // exhaustive search: exact sum of (u >> k) of the orders in flight (by order parity)
     short q[BF_MAX_ORDER];
+    short q2[2][BF_MAX_ORDER];                  // exhaustive search: coefficients of the order being run and the next
+    uint8_t kheapL[2][V3_HEAP];                 // exhaustive search: Rice parameters of the two orders in flight
     alignas(4) bf_lpc_head head;      // (copied as words)
     uint8_t kheap[2][V3_HEAP];
     uint8_t kbest[V3_HEAP / 2];   // exhaustive search: Rice parameters of the best LPC order so far
@@ -79,16 +84,20 @@ __device__ __forceinline__ u64 v3_warp_sum_u64(u64 v)
 //   part 0: the finest order F -- a node is g consecutive run sums;
 //   part 1: every order below F -- nodes are differences of the prefix sums of the finest sums,
 //           which this warp builds in `pre` (shared, nfine entries) first.
-// The two parts are independent, so two warps can run them side by side.
+// The two parts are independent, so two warps can run them side by side.  Each part also comes in two halves
+// for four warps (the exhaustive search runs one model at a time): parts 2 and 3 take alternate steps of the
+// finest order and leave their totals in lvl[V3_MAX_F + 1] / [V3_MAX_F + 2] (v3_pick_level adds them up),
+// part 4 takes orders 0..4 (nodes 1..31), part 5 the orders from 5 up; 4 and 5 each build their own prefix sums.
 __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_extra, u32 S, u32 n, u32 order,
                                        u32 F, u32 max_rice, uint8_t* kheap, V3Level* lvl, u64* pre, u32 part)
 {
     const u32 lane = threadIdx.x & 31;
     const u32 nfine = 1u << F;
     const u32 g = (n >> F) / S;                          // thread runs per finest partition
-    if (part == 0) {
+    if (part == 0 || part == 2 || part == 3) {
         u64 est_acc = 0; u32 cnt_acc = 0, k_acc = 0;
-        for (u32 p = lane; p < nfine; p += 32) {
+        const u32 p0 = part == 3 ? 32u : 0u, pstep = part == 0 ? 32u : 64u;
+        for (u32 p = p0 + lane; p < nfine; p += pstep) {
             const u64* r = runs + (size_t)p * g;
             u64 sum = p == 0 ? first_extra : 0ull;
 #pragma unroll 1
@@ -103,7 +112,8 @@ __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_e
         const u64 tot = v3_warp_sum_u64(est_acc);
         const u32 cnt = __reduce_add_sync(0xFFFFFFFFu, cnt_acc);
         const u32 mk = __reduce_max_sync(0xFFFFFFFFu, k_acc);
-        if (lane == 0) { lvl[F].tot = tot; lvl[F].cnt = cnt; lvl[F].maxk = mk; }
+        V3Level* out = part == 0 ? lvl + F : lvl + V3_MAX_F + (part - 1);
+        if (lane == 0) { out->tot = tot; out->cnt = cnt; out->maxk = mk; }
         return;
     }
     if (F == 0) return;
@@ -132,7 +142,7 @@ __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_e
         for (u32 i = 0; i < c; i++) if (b + i < nfine) pre[b + i] += excl;
     }
     __syncwarp();
-    for (u32 node0 = 0; node0 < nfine; node0 += 32) {
+    for (u32 node0 = part == 5 ? 32u : 0u; node0 < (part == 4 ? 32u : nfine); node0 += 32) {
         const u32 node = node0 + lane;
         const bool act = node >= 1 && node < nfine;
         u32 l = 0, k = 0, cnt = 0;
@@ -175,18 +185,23 @@ __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_e
 
 // every warp: first strict minimum of the estimates over the partition orders (flac.c:1365-1400);
 // lane l looks at order l, the minimum of (estimate, order) pairs is taken with two warp reductions
-__device__ __forceinline__ void v3_pick_level(const V3Level* lvl, u32 F, u32* po_out, u32* method_out, u64* side_bits)
+// split: the finest order's totals are the sums of the two halves left by parts 2 and 3 of v3_levels
+__device__ __forceinline__ void v3_pick_level(const V3Level* lvl, u32 F, u32* po_out, u32* method_out, u64* side_bits,
+                                              bool split = false)
 {
     const u32 lane = threadIdx.x & 31;
-    const u64 tot = lane <= F ? lvl[lane].tot : ~0ull;
+    const V3Level* h0 = lvl + V3_MAX_F + 1;
+    const V3Level* h1 = lvl + V3_MAX_F + 2;
+    const u64 tot = lane > F ? ~0ull : (split && lane == F) ? h0->tot + h1->tot : lvl[lane].tot;
     const u32 hi = (u32)(tot >> 32), lo = (u32)tot;
     const u32 mhi = __reduce_min_sync(0xFFFFFFFFu, hi);
     const u32 mlo = __reduce_min_sync(0xFFFFFFFFu, hi == mhi ? lo : 0xFFFFFFFFu);
     const u32 po = __reduce_min_sync(0xFFFFFFFFu, (hi == mhi && lo == mlo) ? lane : 32u);
-    const u32 maxk = lvl[po].maxk;
+    const bool fin = split && po == F;
+    const u32 maxk = fin ? max(h0->maxk, h1->maxk) : lvl[po].maxk;
     *po_out = po;
     *method_out = maxk > 14 ? 1u : 0u;
-    *side_bits = 6ull + (u64)(1u << po) * (maxk > 14 ? 5ull : 4ull) + (u64)lvl[po].cnt;
+    *side_bits = 6ull + (u64)(1u << po) * (maxk > 14 ? 5ull : 4ull) + (u64)(fin ? h0->cnt + h1->cnt : lvl[po].cnt);
 }
 
 // predictor history of a FIXED pass: differences of the four samples before `base` (zeros for run 0)
@@ -581,17 +596,17 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     bool lpc_narrow = false;
     int lpc_shift = 0;
     // residual of order o with the coefficients staged in sh.q; returns the thread's run sum
-    auto lpc_pass = [&](u32 o, int shift, bool narrow) -> u64 {
+    auto lpc_pass = [&](u32 o, int shift, bool narrow, const short* qs) -> u64 {
         u64 run;
         // (no 8-tap variant: a second hot copy of the residual loop costs more in instruction fetch than
         // the four extra multiply-adds of a padded low order cost on the otherwise idle FMA pipe)
         // (the exhaustive search walks every order, so there the 8-tap copy pays for itself)
-        if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, false>(samp, resid, base, S, sh.q, shift)
-                                        : v3_lpc_residual<8, true>(samp, resid, base, S, sh.q, shift);
-        else if (o <= 12) run = narrow ? v3_lpc_residual<12, false>(samp, resid, base, S, sh.q, shift)
-                                       : v3_lpc_residual<12, true>(samp, resid, base, S, sh.q, shift);
-        else run = narrow ? v3_lpc_residual<32, false>(samp, resid, base, S, sh.q, shift)
-                          : v3_lpc_residual<32, true>(samp, resid, base, S, sh.q, shift);
+        if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, false>(samp, resid, base, S, qs, shift)
+                                        : v3_lpc_residual<8, true>(samp, resid, base, S, qs, shift);
+        else if (o <= 12) run = narrow ? v3_lpc_residual<12, false>(samp, resid, base, S, qs, shift)
+                                       : v3_lpc_residual<12, true>(samp, resid, base, S, qs, shift);
+        else run = narrow ? v3_lpc_residual<32, false>(samp, resid, base, S, qs, shift)
+                          : v3_lpc_residual<32, true>(samp, resid, base, S, qs, shift);
         if (tid == 0) {
 #pragma unroll 1
             for (u32 i = 0; i < o; i++) run -= (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions
@@ -601,7 +616,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     if (!EXH) {
         lpc_shift = sh.head.shift[lpc_order - 1];
         lpc_narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
-        runsL[tid] = lpc_pass(lpc_order, lpc_shift, lpc_narrow);
+        runsL[tid] = lpc_pass(lpc_order, lpc_shift, lpc_narrow, sh.q);
     }
     __syncthreads();                                                             // (2)
 
@@ -656,44 +671,63 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
                    (u64)sh.bits16[1][0] + ((u64)sh.bits16[1][1] << 16);
     } else {
         // ---- every LPC order in turn; `unsigned best_bits = UINT_MAX`, strict <, ascending (flac.c:1079-1108) ----
+        // Two block-wide barriers per order (after the residual pass, after the Rice search): the next order's
+        // coefficients are staged while this one runs, and an order's exact size is looked at one iteration later,
+        // after the barrier that follows the next residual pass -- Rice parameters and bit sums of two orders are
+        // in flight, by order parity.  (It was four barriers per order; barriers were the top stall, 3.1 per issue.)
         u32 best32 = 0xFFFFFFFFu;
         bool have = false;
         const u32 role = (nw & (nw - 1)) == 0 ? ((warp - unit) & (nw - 1)) : (warp + nw - unit % nw) % nw;
-        for (u32 o = 1; o <= P.max_lpc_order; o++) {
-            if (warp == nw - 1) {
-                const int q = lane < o ? (int)mycoef[(o * (o - 1)) / 2 + lane] : 0;
-                sh.q[lane] = (short)q;
-                const u32 sumq = __reduce_add_sync(0xFFFFFFFFu, (u32)abs(q));
-                if (lane == 0) sh.lpc_narrow = sumq;
-            }
-            __syncthreads();
-            if (tid < 2) sh.bits16[1][tid] = 0u;     // everyone has read the previous order's sum by now
-            const int shift = sh.head.shift[o - 1];
-            const bool narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
-            runsL[tid] = lpc_pass(o, shift, narrow);
-            __syncthreads();
-            for (u32 task = role; task < 2; task += nw)
-                v3_levels(runsL, 0ull, S, n, o, F, P.max_rice, sh.kheap[1], sh.lvl[1],
-                          runsF + (size_t)((fixed_order + 2) % 5) * nt, task);
-            __syncthreads();
-            u32 po, method;
-            u64 side;
-            v3_pick_level(sh.lvl[1], F, &po, &method, &side);
-            const u32 kL = sh.kheap[1][(1u << po) - 1u + (pF >> (F - po))];
-            const u32 bL = __reduce_add_sync(0xFFFFFFFFu, v3_stored_bits(resid, base, S, kL, tid == 0 ? o : 0u));
-            if (lane == 0) { atomicAdd(&sh.bits16[1][0], bL & 0xFFFFu); atomicAdd(&sh.bits16[1][1], bL >> 16); }
-            __syncthreads();
-            const u64 bits = hdr_bits + (u64)o * sub_bps + 4 + 5 + (u64)o * precision + side +
-                             (u64)sh.bits16[1][0] + ((u64)sh.bits16[1][1] << 16);
+        const u32 L = P.max_lpc_order;
+        auto stage = [&](u32 o) {            // warp nw - 1: coefficients of order o -> q2[o & 1]
+            const int q = lane < o ? (int)mycoef[(o * (o - 1)) / 2 + lane] : 0;
+            sh.q2[o & 1][lane] = (short)q;
+            const u32 sumq = __reduce_add_sync(0xFFFFFFFFu, (u32)abs(q));
+            if (lane == 0) sh.lpc_narrow2[o & 1] = sumq;
+        };
+        // what the iteration before left to be decided
+        u32 pend_po = 0, pend_method = 0;
+        u64 pend_side = 0;
+        int pend_shift = 0;
+        bool pend_narrow = false;
+        auto decide = [&](u32 o) {           // order o's exact size is complete: first strict minimum
+            const u64 bits = hdr_bits + (u64)o * sub_bps + 4 + 5 + (u64)o * precision + pend_side +
+                             (u64)sh.bitsL[o & 1][0] + ((u64)sh.bitsL[o & 1][1] << 16);
             if (!have || (u32)bits < best32) {
                 have = true;
                 best32 = (u32)bits;
-                lpc_bits = bits; lpc_order = o; lpc_shift = shift; lpc_narrow = narrow;
-                poL = po; methodL = method;
-                const u32 koff = (1u << po) - 1u;
-                for (u32 p = tid; p < (1u << po); p += nt) sh.kbest[p] = sh.kheap[1][koff + p];
+                lpc_bits = bits; lpc_order = o; lpc_shift = pend_shift; lpc_narrow = pend_narrow;
+                poL = pend_po; methodL = pend_method;
+                const u32 koff = (1u << pend_po) - 1u;
+                for (u32 p = tid; p < (1u << pend_po); p += nt) sh.kbest[p] = sh.kheapL[o & 1][koff + p];
             }
+        };
+        if (tid < 4) sh.bitsL[tid >> 1][tid & 1] = 0u;
+        if (warp == nw - 1) stage(1);
+        __syncthreads();
+#pragma unroll 1
+        for (u32 o = 1; o <= L; o++) {
+            const int shift = sh.head.shift[o - 1];
+            const bool narrow = ((u64)sh.lpc_narrow2[o & 1] << (sub_bps - 1)) < (1ull << 31);
+            runsL[tid] = lpc_pass(o, shift, narrow, sh.q2[o & 1]);
+            if (warp == nw - 1 && o < L) stage(o + 1);      // (its buffer was last read by order o - 1's pass)
+            __syncthreads();
+            if (o > 1) decide(o - 1);
+            // the Rice search of the order as four warp tasks (both halves of the finest order, orders 0..4, orders 5..)
+            for (u32 task = role; task < 4; task += nw)
+                v3_levels(runsL, 0ull, S, n, o, F, P.max_rice, sh.kheapL[o & 1], sh.lvl[1],
+                          runsF + (size_t)((fixed_order + 2 + (task & 1u)) % 5) * nt, 2u + task);
+            __syncthreads();
+            if (tid < 2) sh.bitsL[(o + 1) & 1][tid] = 0u;   // order o - 1's sum has been read by everyone
+            u64 side;
+            v3_pick_level(sh.lvl[1], F, &pend_po, &pend_method, &side, true);
+            pend_side = side; pend_shift = shift; pend_narrow = narrow;
+            const u32 kL = sh.kheapL[o & 1][(1u << pend_po) - 1u + (pF >> (F - pend_po))];
+            const u32 bL = __reduce_add_sync(0xFFFFFFFFu, v3_stored_bits(resid, base, S, kL, tid == 0 ? o : 0u));
+            if (lane == 0) { atomicAdd(&sh.bitsL[o & 1][0], bL & 0xFFFFu); atomicAdd(&sh.bitsL[o & 1][1], bL >> 16); }
         }
+        __syncthreads();
+        decide(L);
         __syncthreads();
     }
 
