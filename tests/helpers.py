@@ -274,6 +274,68 @@ def oracle_tta_frames(pcm, sample_rate, channels, bits_per_sample, frame_lengths
     return data, list(sizes[:nf])
 
 
+# ---- ALAC: the compiled reference (oracle/_ref/alacenc) and the plain-C oracle ----
+REF_ALACENC = os.path.join(ROOT, "oracle", "_ref", "alacenc")
+_alac = None
+
+
+def have_alac_ref():
+    return os.path.exists(REF_ALACENC)
+
+
+def ref_alac_encode(pcm, channels, bits_per_sample, block_size=4096):
+    """the mdat atom from the COMPILED REFERENCE ALAC encoder (src/encoders/alac.c, -DSTANDALONE; history 10/40, k 14)"""
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.m4a")
+        subprocess.run([REF_ALACENC, "-c", str(channels), "-r", "44100", "-b", str(bits_per_sample), "-B", str(block_size), out],
+                       input=pcm, stdout=subprocess.DEVNULL, check=True)
+        with open(out, "rb") as fh:
+            return fh.read()
+
+
+def alac_orc():
+    global _alac
+    if _alac is None:
+        path = os.path.join(ROOT, "oracle", "liboracle_alac.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle_alac.so"], check=True)
+        L = C.CDLL(path)
+        L.alac_oracle_encode_mdat.restype = C.c_uint64
+        L.alac_oracle_encode_mdat.argtypes = [C.c_char_p, C.c_uint64] + [C.c_uint] * 6 + [C.POINTER(C.c_void_p)]
+        L.alac_oracle_encode_framesets.restype = C.c_uint
+        L.alac_oracle_encode_framesets.argtypes = [C.c_char_p, C.c_uint64] + [C.c_uint] * 8 + [
+            C.POINTER(C.c_uint32), C.c_uint, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.alac_oracle_free.argtypes = [C.c_void_p]
+        _alac = L
+    return _alac
+
+
+def oracle_alac_mdat(pcm, channels, bits_per_sample, block_size=4096, initial_history=10, history_multiplier=40, maximum_k=14):
+    n = len(pcm) // (channels * (bits_per_sample // 8))
+    out = C.c_void_p()
+    ln = alac_orc().alac_oracle_encode_mdat(bytes(pcm), n, channels, bits_per_sample, block_size, initial_history,
+                                            history_multiplier, maximum_k, C.byref(out))
+    data = C.string_at(out, ln)
+    alac_orc().alac_oracle_free(out)
+    return data
+
+
+def oracle_alac_framesets(pcm, channels, bits_per_sample, block_size=4096, initial_history=10, history_multiplier=40,
+                          maximum_k=14, min_leftweight=0, max_leftweight=4, frame_lengths=None):
+    """(frameset bytes, [sizes]) from the CPU oracle; frame_lengths: the reader's read sizes"""
+    n = len(pcm) // (channels * (bits_per_sample // 8))
+    cap = (len(frame_lengths) if frame_lengths else (n + block_size - 1) // block_size) + 1
+    sizes = (C.c_uint32 * cap)()
+    lens = (C.c_uint32 * len(frame_lengths))(*frame_lengths) if frame_lengths else None
+    out, nb = C.c_void_p(), C.c_uint64(0)
+    nf = alac_orc().alac_oracle_encode_framesets(bytes(pcm), n, channels, bits_per_sample, block_size, initial_history,
+                                                 history_multiplier, maximum_k, min_leftweight, max_leftweight, lens,
+                                                 len(frame_lengths) if frame_lengths else 0, C.byref(out), C.byref(nb), sizes)
+    data = C.string_at(out, nb.value) if nb.value else b""
+    alac_orc().alac_oracle_free(out)
+    return data, list(sizes[:nf])
+
+
 # ---- generators restating the reference's test streams (test/test_streams.py) ----
 def sine_pcm(bits_per_sample, channels, n_frames, sample_rate, freqs_amps):
     """integer sines in the spirit of test_streams.Sine16_Stereo etc. (src/decoders/sine.c):
