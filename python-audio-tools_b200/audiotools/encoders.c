@@ -21,6 +21,7 @@
 #include "pcm.h"
 #include "../../include/b200flac.h"
 #include "../../include/b200tta.h"
+#include "../../include/b200alac.h"
 
 struct py_pcmreader {
     PyObject *obj;            /* the Python PCMReader */
@@ -368,6 +369,127 @@ done:
     return result;
 }
 
+/* encode_alac(file, pcmreader, block_size, initial_history, history_multiplier, maximum_k,
+ *             minimum_interlacing_leftweight=0, maximum_interlacing_leftweight=4) -> ([frameset byte sizes], total PCM frames)
+ * src/encoders/alac.c:30-214: same keyword names (:34-42) and format "OO&iiii|ii", same protocol: an 8-byte mdat
+ * header (size placeholder, "mdat"), one frameset per pcmreader.read(block_size) -- whatever length comes back --,
+ * then the header's size rewritten (the reference uses fgetpos/fsetpos on the FILE*; here the file object's
+ * tell()/seek()), and alac_log_output's tuple returned (:1289-1325).  The reader is not closed. */
+static PyObject *encoders_encode_alac(PyObject *dummy, PyObject *args, PyObject *keywds)
+{
+    static char *kwlist[] = {"file", "pcmreader", "block_size", "initial_history", "history_multiplier", "maximum_k",
+                             "minimum_interlacing_leftweight", "maximum_interlacing_leftweight", NULL};
+    PyObject *file_obj;
+    struct py_pcmreader *reader = NULL;
+    int block_size, initial_history, history_multiplier, maximum_k, min_lw = 0, max_lw = 4;
+    uint8_t *pcm = NULL, *out = NULL;
+    size_t cap = 0, used = 0;
+    uint32_t *lengths = NULL, *sizes = NULL;
+    size_t n_len = 0, len_cap = 0;
+    uint64_t total_frames = 0, out_bytes = 0;
+    uint32_t n_frames = 0;
+    PyObject *result = NULL, *list = NULL, *start = NULL, *r = NULL;
+    b200alac_params p;
+
+    if (!PyArg_ParseTupleAndKeywords(args, keywds, "OO&iiii|ii", kwlist, &file_obj, pcmreader_converter, &reader,
+                                     &block_size, &initial_history, &history_multiplier, &maximum_k, &min_lw, &max_lw))
+        return NULL;
+    if (reader->bits_per_sample != 16 && reader->bits_per_sample != 24) {       /* alac.c:76-80 */
+        PyErr_SetString(PyExc_ValueError, "bits per sample must be 16 or 24");
+        goto done;
+    }
+    if (block_size <= 0) { PyErr_SetString(PyExc_ValueError, "block_size must be positive"); goto done; }
+    p.channels = reader->channels;
+    p.bits_per_sample = reader->bits_per_sample;
+    p.block_size = (uint32_t)block_size;
+    p.initial_history = (uint32_t)initial_history;
+    p.history_multiplier = (uint32_t)history_multiplier;
+    p.maximum_k = (uint32_t)maximum_k;
+    p.minimum_interlacing_leftweight = (uint32_t)min_lw;
+    p.maximum_interlacing_leftweight = (uint32_t)max_lw;
+    const unsigned bytes_ps = p.bits_per_sample / 8;
+    for (;;) {
+        PyObject *fl_obj = PyObject_CallMethod(reader->obj, "read", "i", block_size);
+        if (!fl_obj) goto done;
+        if ((PyObject *)Py_TYPE(fl_obj) != reader->framelist_type) {
+            Py_DECREF(fl_obj);
+            PyErr_SetString(PyExc_TypeError, "results from pcmreader.read() must be FrameLists");
+            goto done;
+        }
+        pcm_FrameList *fl = (pcm_FrameList *)fl_obj;
+        if (fl->frames == 0) { Py_DECREF(fl_obj); break; }   /* alac.c:165 */
+        if (fl->channels != p.channels || fl->bits_per_sample != p.bits_per_sample) {
+            Py_DECREF(fl_obj);
+            PyErr_SetString(PyExc_ValueError, "FrameList does not match the pcmreader's channels / bits_per_sample");
+            goto done;
+        }
+        const size_t need = used + (size_t)fl->samples_length * bytes_ps;
+        if (need > cap) {
+            size_t ncap = cap ? cap * 2 : (1u << 22);
+            while (ncap < need) ncap *= 2;
+            uint8_t *np_ = (uint8_t *)realloc(pcm, ncap);
+            if (!np_) { Py_DECREF(fl_obj); PyErr_NoMemory(); goto done; }
+            pcm = np_; cap = ncap;
+        }
+        if (n_len == len_cap) {
+            len_cap = len_cap ? len_cap * 2 : 1024;
+            uint32_t *nl = (uint32_t *)realloc(lengths, len_cap * sizeof(uint32_t));
+            if (!nl) { Py_DECREF(fl_obj); PyErr_NoMemory(); goto done; }
+            lengths = nl;
+        }
+        pack_le_signed(fl, pcm + used);
+        used = need;
+        lengths[n_len++] = fl->frames;
+        total_frames += fl->frames;
+        Py_DECREF(fl_obj);
+    }
+    {
+        int rc;
+        Py_BEGIN_ALLOW_THREADS     /* alac.c:166-181 drops the GIL around write_frameset as well */
+        rc = b200alac_encode_framesets(&p, pcm, total_frames, lengths, (uint32_t)n_len, 0, &out, &out_bytes, &sizes, &n_frames, NULL);
+        Py_END_ALLOW_THREADS
+        if (rc) {
+            const char *msg = b200alac_last_error();
+            PyErr_SetString(strstr(msg, "must be") || strstr(msg, "unsupported") ? PyExc_ValueError : PyExc_IOError, msg);
+            goto done;
+        }
+    }
+    {
+        /* placeholder header, framesets, then the size at the header's position (alac.c:153-157, 185-189) */
+        const uint32_t size = (uint32_t)(out_bytes + 8);
+        const char head[8] = {(char)(size >> 24), (char)(size >> 16), (char)(size >> 8), (char)size, 'm', 'd', 'a', 't'};
+        if ((start = PyObject_CallMethod(file_obj, "tell", NULL)) == NULL) goto done;
+        if ((r = PyObject_CallMethod(file_obj, "write", "y#", head, (Py_ssize_t)8)) == NULL) goto done;
+        Py_CLEAR(r);
+        if (out_bytes) {
+            if ((r = PyObject_CallMethod(file_obj, "write", "y#", (const char *)out, (Py_ssize_t)out_bytes)) == NULL) goto done;
+            Py_CLEAR(r);
+        }
+        /* (the reference leaves the file position just after the rewritten size, alac.c:187-189) */
+        if ((r = PyObject_CallMethod(file_obj, "seek", "O", start)) == NULL) goto done;
+        Py_CLEAR(r);
+        if ((r = PyObject_CallMethod(file_obj, "write", "y#", head, (Py_ssize_t)4)) == NULL) goto done;
+        Py_CLEAR(r);
+    }
+    list = PyList_New((Py_ssize_t)n_frames);
+    for (uint32_t i = 0; list && i < n_frames; i++) {
+        PyObject *v = PyLong_FromUnsignedLong(sizes[i]);
+        if (!v) { Py_CLEAR(list); break; }
+        PyList_SET_ITEM(list, (Py_ssize_t)i, v);
+    }
+    if (list) result = Py_BuildValue("(O,K)", list, (unsigned long long)total_frames);   /* alac.c:1318-1320 */
+done:
+    Py_XDECREF(list);
+    Py_XDECREF(start);
+    Py_XDECREF(r);
+    free(pcm);
+    free(lengths);
+    b200alac_free(out);
+    b200alac_free(sizes);
+    pcmreader_del(reader);
+    return result;
+}
+
 static PyObject *encoders_device_count(PyObject *dummy, PyObject *args)
 {
     return PyLong_FromLong(b200flac_device_count());
@@ -419,6 +541,10 @@ static PyMethodDef module_methods[] = {
      "disable_lpc_subframes=0, padding_size=4096) -> [(byte_offset, pcm_frames), ...]"},
     {"encode_tta", (PyCFunction)encoders_encode_tta, METH_VARARGS | METH_KEYWORDS,
      "encode_tta(file, pcmreader) -> [frame_size, ...]: TTA frames written to file (src/encoders/tta.c:31-117)"},
+    {"encode_alac", (PyCFunction)encoders_encode_alac, METH_VARARGS | METH_KEYWORDS,
+     "encode_alac(file, pcmreader, block_size, initial_history, history_multiplier, maximum_k, "
+     "minimum_interlacing_leftweight=0, maximum_interlacing_leftweight=4) -> ([frameset sizes], total_pcm_frames): "
+     "the mdat atom written to file (src/encoders/alac.c:30-214)"},
     {"finalize_flac_metadata", (PyCFunction)encoders_finalize_flac_metadata, METH_VARARGS | METH_KEYWORDS,
      "finalize_flac_metadata(filename, offsets, seekpoint_interval=0, channel_mask=0): SEEKTABLE from the "
      "encoder's offsets, channel-mask tag, PADDING adjustment -- FlacAudio.from_pcm's tail in C"},

@@ -211,12 +211,31 @@ struct AWrite {      // MSB-first writer into zeroed big-endian words of global 
 
 __device__ __forceinline__ u32 alac_log2(u32 v) { return v ? 31u - (u32)__clz((int)v) : 0xFFFFFFFFu; }   // LOG2, alac.c:1020-1031
 
+// value / (2^k - 1) and the remainder for the values ALAC codes (below 2^25): a float quotient, corrected by one
+__device__ __forceinline__ void alac_divmod(u32 value, u32 d, u32& q, u32& r)
+{
+    q = (u32)(__fdividef((float)value, (float)d));
+    int rem = (int)value - (int)(q * d);
+    if (rem < 0) { q--; rem += (int)d; }
+    else if (rem >= (int)d) { q++; rem -= (int)d; }
+    r = (u32)rem;
+}
+
 // write_residual, alac.c:1102-1122
+__device__ __forceinline__ void alac_write_residual(ACount& s, u32 value, u32 k, u32 sample_size)
+{
+    // (counting only: no branches -- the lanes of a warp walk different channels)
+    u32 msb, lsb;
+    alac_divmod(value, (1u << k) - 1u, msb, lsb);
+    const u32 tail = k > 1 ? (lsb > 0 ? k : k - 1) : 0u;
+    s.bits += msb > 8 ? 9u + sample_size : msb + 1u + tail;
+}
+
 template <class Sink>
 __device__ __forceinline__ void alac_write_residual(Sink& s, u32 value, u32 k, u32 sample_size)
 {
-    const u32 d = (1u << k) - 1u;
-    const u32 msb = value / d, lsb = value - msb * d;
+    u32 msb, lsb;
+    alac_divmod(value, (1u << k) - 1u, msb, lsb);
     if (msb > 8) {
         s.put(0x1FF, 9);
         s.put(value, sample_size);
@@ -262,29 +281,20 @@ __device__ __forceinline__ bool alac_chain(const ASrc& src, u32 n, u32 sample_si
             const int t = (s - base - (int)sum) & smask;
             int error = (t & sbit) ? t - (1 << sample_size) : t;
             res = error;
-            // the coefficients follow the sign of the error (alac.c:986-1008)
-            if (error > 0) {
-                bool live = true;
+            // the coefficients follow the sign of the error (alac.c:986-1008); its two mirrored branches as one
+            // loop over se = sign(error): coefficient -= se * sign(diff), error -= ((diff * se * sign(diff)) >> 9) * (j + 1),
+            // until the error has changed sign -- lanes of a warp take different paths, so no branch here
+            {
+                const int se = (error > 0) - (error < 0);
+                bool live = se != 0;
 #pragma unroll
                 for (int j = 0; j < CC; j++) {
+                    const int diff = base - w[CC - 1 - j];              // base - s[i - CC + j]
+                    const int sg = ((diff > 0) - (diff < 0)) * se;
                     if (live) {
-                        const int diff = base - w[CC - 1 - j];              // base - s[i - CC + j]
-                        const int sg = (diff > 0) - (diff < 0);
                         coef[CC - j - 1] -= sg;
                         error -= ((diff * sg) >> 9) * (j + 1);
-                        if (error <= 0) live = false;
-                    }
-                }
-            } else if (error < 0) {
-                bool live = true;
-#pragma unroll
-                for (int j = 0; j < CC; j++) {
-                    if (live) {
-                        const int diff = base - w[CC - 1 - j];
-                        const int sg = (diff > 0) - (diff < 0);
-                        coef[CC - j - 1] += sg;
-                        error -= ((diff * -sg) >> 9) * (j + 1);
-                        if (error >= 0) live = false;
+                        if (error * se <= 0) live = false;
                     }
                 }
             }
@@ -327,9 +337,11 @@ __global__ void __launch_bounds__(64)
 k_alac_size(const uint8_t* __restrict__ pcm, const AFrameset* __restrict__ fsets, u32 n_chains, ADev D,
             const AModel* __restrict__ models, u32* __restrict__ bits, u32* __restrict__ overflow)
 {
-    const u32 chain = blockIdx.x * blockDim.x + threadIdx.x;
-    if (chain >= n_chains) return;
-    const u32 unit = chain >> 1, oi = chain & 1;
+    // blockIdx.y is the order (4 or 8): a warp runs ONE instantiation of the walk (with the two orders in
+    // alternate lanes every warp executed both, each with half its lanes)
+    const u32 unit = blockIdx.x * blockDim.x + threadIdx.x, oi = blockIdx.y;
+    if (unit * 2 >= n_chains) return;
+    const u32 chain = unit * 2 + oi;
     const u32 fg = unit / D.upf, r = unit % D.upf, lwi = r >> 1, ch = r & 1;
     const u32 f = fg / D.ng, g = fg % D.ng;
     if (D.grp[g].nch == 1 && r != 0) return;
@@ -682,7 +694,7 @@ static int encode_core(const b200alac_params* p, const uint8_t* d_pcm, uint64_t 
     k_alac_model<<<(n_units + 63) / 64, 64>>>(d_pcm, d_fs, n_units, D, d_win, d_models);
     ACK(cudaGetLastError());
     ACK(cudaEventRecord(ev[1]));
-    k_alac_size<<<(n_chains + 63) / 64, 64>>>(d_pcm, d_fs, n_chains, D, d_models, d_bits, d_ov);
+    k_alac_size<<<dim3((n_units + 63) / 64, 2), 64>>>(d_pcm, d_fs, n_chains, D, d_models, d_bits, d_ov);
     ACK(cudaGetLastError());
     ACK(cudaEventRecord(ev[2]));
     k_alac_select<<<(nf + 127) / 128, 128>>>(d_fs, nf, D, d_models, d_bits, d_ov, d_choice, d_fbytes);

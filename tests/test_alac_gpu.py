@@ -80,3 +80,25 @@ def test_alac_empty_and_errors(built, tmp_path):
         b200alac.encode_framesets(b"\0" * 40, 10, b200alac.make_params(), frame_lengths=[4, 4])
     with pytest.raises(b200alac.B200AlacError):
         b200alac.encode_mdat(os.path.join(str(tmp_path), "no", "dir", "x.m4a"), b"\0" * 40, 10, b200alac.make_params())
+
+
+def test_encode_alac_python_entry(built):
+    """audiotools.encoders.encode_alac(file, pcmreader, block_size, initial_history, history_multiplier, maximum_k)
+    (src/encoders/alac.c:30-214): the mdat atom in the file object, (frameset sizes, total PCM frames) back"""
+    import io
+    import audiotools
+    from audiotools import encoders
+    ch, bps, n = 2, 16, 4096 * 3 + 777
+    pcm = helpers.synth_pcm(66, ch, bps, n)
+    f = io.BytesIO(b"head")
+    f.seek(4)
+    sizes, total = encoders.encode_alac(f, audiotools.BufferedPCMReader(audiotools.PCMBytesReader(pcm, 44100, ch, 0x3, bps)),
+                                        4096, 10, 40, 14)
+    want = helpers.oracle_alac_mdat(pcm, ch, bps)
+    _, want_sizes = helpers.oracle_alac_framesets(pcm, ch, bps)
+    assert f.getvalue() == b"head" + want and sizes == want_sizes and total == n
+    assert f.tell() == 8          # just after the rewritten size, like the reference's fsetpos + write
+    with pytest.raises(ValueError, match="16 or 24"):
+        encoders.encode_alac(io.BytesIO(), audiotools.PCMBytesReader(b"\0" * 100, 44100, 2, 0x3, 8), 4096, 10, 40, 14)
+    with pytest.raises(TypeError):
+        encoders.encode_alac(io.BytesIO(), audiotools.PCMBytesReader(pcm, 44100, ch, 0x3, bps))
