@@ -708,6 +708,31 @@ def main():
             launches += ln
             configs.append(res)
 
+    # ---- the sibling encoders of SURVEY 8(f)-4 on the same runtime: TTA and ALAC, device resident, rank 0 ----
+    siblings = None
+    if rank == 0 and not args.no_configs:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import alac_perf
+            import tta_perf
+            peak, peak_kind = peaks()
+            siblings = {}
+            for name, mod, secs in (("tta", tta_perf, 3600.0), ("alac", alac_perf, 3600.0)):
+                r = mod.measure(secs, device=dev)
+                r["what"] = ("%s encode of %.0f s synthetic 44.1 kHz/16-bit stereo, PCM resident in HBM, frames left in HBM; "
+                             "value = samples / CUDA-event time of its kernels" % (name.upper(), secs))
+                r["roofline"] = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_kind": peak_kind,
+                                 "achieved": r["algorithmic_bytes"] / (r["kernels_ms"] * 1e-3) / 1e9,
+                                 "frac": r["algorithmic_bytes"] / (r["kernels_ms"] * 1e-3) / 1e9 / peak,
+                                 "note": "latency-bound by construction: both codecs adapt their predictor and their Rice/Golomb "
+                                         "state after every sample, so a channel of a frame is one serial chain per thread"}
+                if world == 1 and not args.no_cpu_baseline:
+                    r["cpu_baseline"] = mod.reference_single_core()
+                siblings[name] = r
+            launches += 3 * 3 + 7 * 3
+        except Exception as e:          # (reported, not fatal: the FLAC line is the bench)
+            siblings = {"error": repr(e)}
+
     # ---- N > 1: ONE stream, frame-range sharded over the N GPUs by the stream layer (config 4's shape) ----
     sharded = None
     if world > 1 and not args.no_api:
@@ -802,7 +827,7 @@ def main():
                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (pcm_bytes / 1e6),
                        "sharding": "frame range per GPU, no collective"},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "e2e_frame_layer": e2e_frame,
-            "api": api, "configs": configs, "sharded_stream": sharded, "gpu_launches": int(launches),
+            "api": api, "configs": configs, "siblings": siblings, "sharded_stream": sharded, "gpu_launches": int(launches),
             "full_check": full_check,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
                        "samples": clk["samples"], "samples_in_timed_regions": clk["samples_in_timed_regions"]},

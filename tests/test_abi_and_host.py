@@ -184,6 +184,71 @@ def test_native_metadata_finalisation_matches_python(padding, mask, rate, n, tmp
     shutil.copy(os.path.join(str(tmp_path), "a.flac"), os.path.join(str(tmp_path), "c.flac"))
 
 
+def _hand_built_flac(total_frames, padding, frames_blob, rate=100, channels=2, bps=16):
+    """a FLAC file image assembled byte by byte here (no encoder, no restatement involved): fLaC, STREAMINFO,
+    VORBIS_COMMENT (the encoder's vendor string, no comments), PADDING as the last block, then opaque frame bytes"""
+    import struct
+    si = struct.pack(">HH", 1000, 1000) + (700).to_bytes(3, "big") + (800).to_bytes(3, "big") + \
+        ((rate << 44) | ((channels - 1) << 41) | ((bps - 1) << 36) | total_frames).to_bytes(8, "big") + bytes(range(16))
+    vendor = b"Python Audio Tools 2.22alpha1"
+    vc = struct.pack("<I", len(vendor)) + vendor + struct.pack("<I", 0)
+    return (b"fLaC" + bytes([0x00]) + (34).to_bytes(3, "big") + si + bytes([0x04]) + len(vc).to_bytes(3, "big") + vc +
+            bytes([0x81]) + padding.to_bytes(3, "big") + bytes(padding) + frames_blob), si, vendor
+
+
+def test_native_metadata_finalisation_hand_computed_fixture(tmp_path, built):
+    """(f)1 pinned independently of this repo's Python restatement: the expected file is written out here from the
+    reference's own arithmetic.  FlacAudio.seektable (audiotools/flac.py:1847-1876): offsets [(0, 1000), (700, 1000),
+    (1500, 500)] give sample_offsets [0, 1000, 2000]; for pcm_frame in xrange(0, total_frames = 2500, interval = 1000)
+    the points are (0, 0, 1000), (1000, 700, 1000), (2000, 1500, 500).  Flac_SEEKTABLE.build (:611-615) writes each as
+    64 + 64 + 16 bits; FlacMetaData.add_block (:53-75) puts block 3 before the VORBIS_COMMENT; update_metadata
+    (:1396-1424) takes the 4 + 54 bytes of growth out of the PADDING block (4096 -> 4038) and rewrites the head in
+    place, so the frames do not move.  With a channel mask (from_pcm :1827-1832) the VORBIS_COMMENT gains
+    "WAVEFORMATEXTENSIBLE_CHANNEL_MASK=0x003F" (4 + 40 bytes) and the padding shrinks to 3994."""
+    import struct
+    import b200flac
+    frames = b"\xff\xf8" + bytes((i * 7 + 3) & 0xFF for i in range(2198))
+    offsets = [(0, 1000), (700, 1000), (1500, 500)]
+    seek = b"".join(struct.pack(">QQH", *p) for p in [(0, 0, 1000), (1000, 700, 1000), (2000, 1500, 500)])
+    assert len(seek) == 54
+    # --- the PADDING takes the growth ---
+    data, si, vendor = _hand_built_flac(2500, 4096, frames)
+    path = os.path.join(str(tmp_path), "hand.flac")
+    open(path, "wb").write(data)
+    b200flac.finalize_metadata(path, offsets, 1000, 0)
+    vc = struct.pack("<I", len(vendor)) + vendor + struct.pack("<I", 0)
+    want = (b"fLaC" + bytes([0x00, 0, 0, 34]) + si + bytes([0x03, 0, 0, 54]) + seek +
+            bytes([0x04]) + len(vc).to_bytes(3, "big") + vc + bytes([0x81]) + (4038).to_bytes(3, "big") + bytes(4038) + frames)
+    assert len(want) == len(data)
+    assert open(path, "rb").read() == want
+    # --- the same with a channel mask: one comment more, less padding ---
+    open(path, "wb").write(data)
+    b200flac.finalize_metadata(path, offsets, 1000, 0x3F)
+    comment = b"WAVEFORMATEXTENSIBLE_CHANNEL_MASK=0x003F"
+    assert len(comment) == 40
+    vc1 = struct.pack("<I", len(vendor)) + vendor + struct.pack("<I", 1) + struct.pack("<I", 40) + comment
+    want = (b"fLaC" + bytes([0x00, 0, 0, 34]) + si + bytes([0x03, 0, 0, 54]) + seek +
+            bytes([0x04]) + len(vc1).to_bytes(3, "big") + vc1 + bytes([0x81]) + (3994).to_bytes(3, "big") + bytes(3994) + frames)
+    assert open(path, "rb").read() == want
+    # --- interval 0 = ten seconds of the STREAMINFO rate (flac.py:1856-1857): 100 Hz -> 1000 frames, the same table ---
+    open(path, "wb").write(data)
+    b200flac.finalize_metadata(path, offsets, 0, 0)
+    assert open(path, "rb").read()[:len(want) - len(frames)][42:42 + 58] == bytes([0x03, 0, 0, 54]) + seek
+    # --- a PADDING of 10 bytes cannot take 58: the file is rewritten (:1425-1462), blocks keep their sizes ---
+    small, _, _ = _hand_built_flac(2500, 10, frames)
+    open(path, "wb").write(small)
+    b200flac.finalize_metadata(path, offsets, 1000, 0)
+    want = (b"fLaC" + bytes([0x00, 0, 0, 34]) + si + bytes([0x03, 0, 0, 54]) + seek +
+            bytes([0x04]) + len(vc).to_bytes(3, "big") + vc + bytes([0x81, 0, 0, 10]) + bytes(10) + frames)
+    assert open(path, "rb").read() == want
+    # --- a seek point between frame starts belongs to the frame that contains it (bisect_right - 1, :1869) ---
+    open(path, "wb").write(data)
+    b200flac.finalize_metadata(path, offsets, 900, 0)      # points at 0, 900, 1800 -> frames starting at 0, 0, 1000
+    got = open(path, "rb").read()
+    pts = [struct.unpack(">QQH", got[46 + 18 * i:64 + 18 * i]) for i in range(3)]
+    assert pts == [(0, 0, 1000), (0, 0, 1000), (1000, 700, 1000)]
+
+
 def test_native_metadata_finalisation_errors(tmp_path, built):
     import b200flac
     with pytest.raises(b200flac.B200FlacError):

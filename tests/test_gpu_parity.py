@@ -295,6 +295,35 @@ def test_stream_frame_ranges_over_two_devices(tmp_path, built):
     assert back == pcm4 and info.total_pcm_frames == n4
 
 
+def test_lpc_order_estimate_stress(tmp_path, built):
+    """The order estimate (flac.c:1233-1268) is the one place where the device's libm (log) is not the host's: an
+    ulp of difference could only matter where two orders' estimates agree to ~1e-15.  6,000 short blocks of
+    synthetic resonances whose LPC error curves are deliberately flat (pole radius close to 1, orders beyond the
+    model all equally good), so that neighbouring orders' estimates are as close as real signals make them: every
+    block's chosen order, coefficients and bytes must equal the oracle's (which runs the host libm)."""
+    from scipy.signal import lfilter
+    rng = np.random.RandomState(2024)
+    n_blocks, bs = 6000, 192
+    x = np.zeros(n_blocks * bs)
+    e = rng.standard_normal(n_blocks * bs)
+    for b in range(n_blocks):
+        # an AR(2) or AR(4) resonance per block, excitation level varied over 60 dB
+        r1, f1 = rng.uniform(0.90, 0.9995), rng.uniform(0.01, 0.45)
+        a = [2 * r1 * np.cos(2 * np.pi * f1), -r1 * r1]
+        if b & 1:
+            r2, f2 = rng.uniform(0.5, 0.999), rng.uniform(0.01, 0.45)
+            p = np.polymul([1, -a[0], -a[1]], [1, -2 * r2 * np.cos(2 * np.pi * f2), r2 * r2])
+            a = list(-p[1:])
+        g = 10 ** rng.uniform(0, 3)
+        y = lfilter([g], np.concatenate([[1.0], -np.asarray(a)]), e[b * bs:(b + 1) * bs])
+        m = np.max(np.abs(y))
+        x[b * bs:(b + 1) * bs] = y * (rng.uniform(200, 30000) / m if m > 0 else 0)
+    pcm = helpers.pack_pcm(np.round(x).astype(np.int32), 16)
+    for o in (dict(block_size=bs, max_lpc_order=12, max_residual_partition_order=3),
+              dict(block_size=bs, max_lpc_order=32, max_residual_partition_order=2)):
+        _check(tmp_path, pcm, 44100, 1, 16, helpers.options(**o))
+
+
 def test_error_paths(tmp_path, built):
     b = _b200()
     p = b.make_params()
