@@ -12,8 +12,8 @@ src/encoders/flac.c:1647), frames sharded by range: every rank (GPU) encodes its
 A step = one pass of the hot path (6 kernels: autocorrelation, Levinson/quantise, model search,
 frame select, offset scan, frame pack + CRC-16) over the rank's whole hour.
   value : whole-job Msamples/s with the PCM already resident in HBM and the frames left in
-          HBM (b200flac_encoder_encode_device), wall clock around K steps bracketed by
-          barrier + device synchronize, max over ranks.
+          HBM (b200flac_encoder_submit_device / collect_device on two slots), wall clock around
+          K steps bracketed by barrier + device synchronize, max over ranks.
   e2e   : same metric through the host-buffer C-ABI calls (b200flac_encoder_submit/collect):
           pinned host PCM -> H2D -> kernels -> D2H frame bytes, every step, 3 batches in flight.
   roofline : dominant kernel, algorithmic bytes (PCM in + frame bytes out) / its CUDA-event time.
@@ -388,11 +388,14 @@ def main():
     tmp = tempfile.TemporaryDirectory(dir=shm, prefix="b200bench%d_" % rank)
 
     # ---- device-resident arm -----------------------------------------------------------------
-    enc = b200flac.Encoder(params, device=dev, max_pcm_frames_per_batch=n_frames_pcm, n_slots=1)
+    # two slots: while the kernels of step k run, the host prepares step k + 1 (frame descriptors, task lists,
+    # their upload) through the asynchronous halves of the device-resident call; every step is the whole hour
+    enc = b200flac.Encoder(params, device=dev, max_pcm_frames_per_batch=n_frames_pcm, n_slots=2)
     out_cap = enc.output_bound(n_frames_pcm, 1)
     d_pcm = L.b200flac_device_alloc(dev, pcm_bytes)
-    d_out = L.b200flac_device_alloc(dev, out_cap)
-    if not d_pcm or not d_out:
+    d_outs = [L.b200flac_device_alloc(dev, out_cap) for _ in range(2)]
+    d_out = d_outs[0]
+    if not d_pcm or not all(d_outs):
         raise SystemExit("device allocation failed: " + L.b200flac_last_error().decode())
     if L.b200flac_device_synth_pcm(dev, d_pcm, 1235 + rank, CHANNELS, BPS, 0, n_frames_pcm):
         raise SystemExit("synth failed")
@@ -403,23 +406,33 @@ def main():
     clocks.start()
     for _ in range(max(args.warmup, 3)):
         out_bytes, n_flac_frames, _ = enc.encode_device(d_pcm, segs, d_out, out_cap)
+        enc.encode_device(d_pcm, segs, d_outs[1], out_cap, slot=1)
     launches0 = enc.launch_count()
     barrier()
     w0 = time.time()
-    kernel_ms = [0.0] * 5
-    device_ms = 0.0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out_bytes, n_flac_frames, dev_ms = enc.encode_device(d_pcm, segs, d_out, out_cap)
-        device_ms += dev_ms
-        for i, v in enumerate(enc.kernel_ms(0)):
-            kernel_ms[i] += v
+    for k in range(args.steps):
+        enc.submit_device(d_pcm, segs, d_outs[k & 1], out_cap, slot=k & 1)
+        if k:
+            enc.collect_device(slot=(k - 1) & 1)
+    last = enc.collect_device(slot=(args.steps - 1) & 1)
     barrier()
     elapsed = allmax(time.perf_counter() - t0)
     clocks.mark(w0, time.time())
     launches = enc.launch_count() - launches0
+    d_out = d_outs[(args.steps - 1) & 1]
+    out_bytes, n_flac_frames = last[0], last[1]
     samples_per_step = n_frames_pcm * CHANNELS
     value = world * samples_per_step * args.steps / elapsed / 1e6
+    # kernel times: the same step alone on the device (one slot, synchronous), CUDA events recorded by the library
+    # on the stream it launches on -- in the timed region above the end of one step overlaps the start of the next
+    kernel_ms = [0.0] * 5
+    device_ms = 0.0
+    for _ in range(args.steps):
+        _, _, dev_ms = enc.encode_device(d_pcm, segs, d_outs[(args.steps) & 1], out_cap)
+        device_ms += dev_ms
+        for i, v in enumerate(enc.kernel_ms(0)):
+            kernel_ms[i] += v
 
     # ---- whole-step check, outside the timed region: the frames the last step left in HBM are decoded by
     # the engine's own GPU decoder (every frame header CRC-8 and frame CRC-16 checked) and the
@@ -836,7 +849,8 @@ def main():
     if h_pcm:
         L.b200flac_host_free(h_pcm)
     L.b200flac_device_free(dev, d_pcm)
-    L.b200flac_device_free(dev, d_out)
+    for p_ in d_outs:
+        L.b200flac_device_free(dev, p_)
     enc.close()
     tmp.cleanup()
     if dist is not None:

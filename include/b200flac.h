@@ -135,6 +135,15 @@ int b200flac_encoder_encode_device(b200flac_encoder *enc, int slot, const void *
                                    void *d_out, uint64_t out_capacity, uint64_t *out_bytes,
                                    uint32_t *n_frames, float *elapsed_ms);
 
+/* The same in two halves, so that a caller with two slots keeps the device busy: submit_device does the host's
+ * share (frame descriptors, task lists, their upload, the launches) and returns; collect_device waits for the
+ * slot and returns the totals.  Same argument rules as b200flac_encoder_encode_device. */
+int b200flac_encoder_submit_device(b200flac_encoder *enc, int slot, const void *d_pcm,
+                                   const b200flac_segment *segments, uint32_t n_segments,
+                                   void *d_out, uint64_t out_capacity);
+int b200flac_encoder_collect_device(b200flac_encoder *enc, int slot, uint64_t *out_bytes,
+                                    uint32_t *n_frames, float *elapsed_ms);
+
 /* per-kernel CUDA-event times of the slot's last batch, in ms:
  * [0] lpc model (window/autocorrelation, then Levinson/quantise), [1] subframe analysis,
  * [2] frame select + offset scan (+ output clear on the k_pack_v2 path), [3] frame packing

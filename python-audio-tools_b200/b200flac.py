@@ -97,6 +97,8 @@ def lib():
                                           vp, vp, C.c_uint32, u32p]
     L.b200flac_encoder_encode_device.argtypes = [vp, C.c_int, vp, C.POINTER(Segment), C.c_uint32, vp,
                                                  C.c_uint64, u64p, u32p, C.POINTER(C.c_float)]
+    L.b200flac_encoder_submit_device.argtypes = [vp, C.c_int, vp, C.POINTER(Segment), C.c_uint32, vp, C.c_uint64]
+    L.b200flac_encoder_collect_device.argtypes = [vp, C.c_int, u64p, u32p, C.POINTER(C.c_float)]
     L.b200flac_encoder_last_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_int]
     L.b200flac_encoder_set_chunking.restype = C.c_int
     L.b200flac_encoder_set_chunking.argtypes = [vp, C.c_uint32, C.c_uint32]
@@ -232,6 +234,19 @@ class Encoder(object):
         nbytes, nfr, ms = C.c_uint64(0), C.c_uint32(0), C.c_float(0)
         if lib().b200flac_encoder_encode_device(self.h, slot, d_pcm, arr, len(segments), d_out, out_capacity,
                                                 C.byref(nbytes), C.byref(nfr), C.byref(ms)):
+            raise _err()
+        return nbytes.value, nfr.value, ms.value
+
+    def submit_device(self, d_pcm, segments, d_out, out_capacity, slot=0):
+        """asynchronous half of encode_device: host work and launches, no wait"""
+        arr = self._segments(segments)
+        if lib().b200flac_encoder_submit_device(self.h, slot, d_pcm, arr, len(segments), d_out, out_capacity):
+            raise _err()
+
+    def collect_device(self, slot=0):
+        """waits for the slot: (bytes, frames, kernel ms)"""
+        nbytes, nfr, ms = C.c_uint64(0), C.c_uint32(0), C.c_float(0)
+        if lib().b200flac_encoder_collect_device(self.h, slot, C.byref(nbytes), C.byref(nfr), C.byref(ms)):
             raise _err()
         return nbytes.value, nfr.value, ms.value
 

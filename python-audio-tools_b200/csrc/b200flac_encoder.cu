@@ -100,6 +100,7 @@ struct Slot {
     u64* d_gheap = nullptr;
     uint8_t* d_gkarr = nullptr;
     u32 n_frames = 0;
+    u64 dev_cap = 0;               // capacity of the caller's output buffer (device-resident batches)
     bool busy = false;
     bool timed = false;
     std::vector<u32> frame_pcm;
@@ -1166,10 +1167,11 @@ extern "C" int b200flac_encoder_encode(b200flac_encoder* enc, const uint8_t* pcm
     return b200flac_encoder_collect(enc, 0, out, out_capacity, out_bytes, frame_bytes, frame_pcm, frame_capacity, n_frames);
 }
 
-extern "C" int b200flac_encoder_encode_device(b200flac_encoder* enc, int slot, const void* d_pcm,
+// device-resident batches, asynchronous: enqueue (host work + launches) now, wait later -- with two slots the
+// host's share of batch k + 1 (descriptors, task lists, their upload) runs under the kernels of batch k
+extern "C" int b200flac_encoder_submit_device(b200flac_encoder* enc, int slot, const void* d_pcm,
                                               const b200flac_segment* segments, uint32_t n_segments,
-                                              void* d_out, uint64_t out_capacity, uint64_t* out_bytes,
-                                              uint32_t* n_frames, float* elapsed_ms)
+                                              void* d_out, uint64_t out_capacity)
 {
     if (!enc || slot < 0 || slot >= enc->n_slots) { set_err("bad encoder or slot"); return 1; }
     if (!d_pcm || !d_out || !segments || n_segments == 0) { set_err("bad arguments"); return 1; }
@@ -1180,24 +1182,47 @@ extern "C" int b200flac_encoder_encode_device(b200flac_encoder* enc, int slot, c
     u64 need = 0;
     const long nf = build_batch(enc, s, segments, n_segments, &need);
     if (nf < 0) return 1;
-    if (nf == 0) { if (out_bytes) *out_bytes = 0; if (n_frames) *n_frames = 0; return 0; }
+    s.dev_cap = out_capacity & ~15ull;
+    s.busy = true;
+    if (nf == 0) { s.timed = false; *s.h_total = 0; return 0; }
     cudaStream_t st = s.stream;
     CU_CHECK(cudaMemcpyAsync(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), cudaMemcpyHostToDevice, st), 1);
     if (s.n_odd) CU_CHECK(cudaMemcpyAsync(s.d_odd, s.h_odd, (size_t)s.n_odd * sizeof(u32), cudaMemcpyHostToDevice, st), 1);
     if (enc->P.try_lpc) CU_CHECK(cudaMemcpyAsync(s.d_tasks, s.h_tasks, (size_t)s.n_tasks * sizeof(bf_lpc_task), cudaMemcpyHostToDevice, st), 1);
     const size_t wused = (size_t)s.h_total[1];
     if (wused) CU_CHECK(cudaMemcpyAsync(s.d_win, s.h_win, wused * sizeof(double), cudaMemcpyHostToDevice, st), 1);
-    const u64 cap = out_capacity & ~15ull;
-    if (launch_batch(enc, s, (const uint8_t*)d_pcm, (uint8_t*)d_out, cap)) return 1;
+    if (launch_batch(enc, s, (const uint8_t*)d_pcm, (uint8_t*)d_out, s.dev_cap)) { s.busy = false; return 1; }
     CU_CHECK(cudaMemcpyAsync(s.h_total, s.d_total, sizeof(u64), cudaMemcpyDeviceToHost, st), 1);
     CU_CHECK(cudaMemcpyAsync(s.h_frame_bytes, s.d_frame_bytes, (size_t)nf * sizeof(u32), cudaMemcpyDeviceToHost, st), 1);
-    CU_CHECK(cudaStreamSynchronize(st), 1);
+    CU_CHECK(cudaEventRecord(s.ev_done, st), 1);
+    return 0;
+}
+
+extern "C" int b200flac_encoder_collect_device(b200flac_encoder* enc, int slot, uint64_t* out_bytes,
+                                               uint32_t* n_frames, float* elapsed_ms)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots) { set_err("bad encoder or slot"); return 1; }
+    Slot& s = enc->slots[slot];
+    if (!s.busy) { set_err("slot has no batch in flight"); return 1; }
+    CU_CHECK(cudaSetDevice(enc->device), 1);
+    s.busy = false;
+    if (s.n_frames == 0) { if (out_bytes) *out_bytes = 0; if (n_frames) *n_frames = 0; return 0; }
+    CU_CHECK(wait_event(s.ev_done), 1);
     const u64 total = *s.h_total;
-    if (total + 16 > cap) { set_err("encoded batch exceeds the output buffer"); return 1; }
+    if (total + 16 > s.dev_cap) { set_err("encoded batch exceeds the output buffer"); return 1; }
     if (out_bytes) *out_bytes = total;
-    if (n_frames) *n_frames = (u32)nf;
+    if (n_frames) *n_frames = s.n_frames;
     if (elapsed_ms) cudaEventElapsedTime(elapsed_ms, s.ev[0], s.ev[5]);
     return 0;
+}
+
+extern "C" int b200flac_encoder_encode_device(b200flac_encoder* enc, int slot, const void* d_pcm,
+                                              const b200flac_segment* segments, uint32_t n_segments,
+                                              void* d_out, uint64_t out_capacity, uint64_t* out_bytes,
+                                              uint32_t* n_frames, float* elapsed_ms)
+{
+    if (b200flac_encoder_submit_device(enc, slot, d_pcm, segments, n_segments, d_out, out_capacity)) return 1;
+    return b200flac_encoder_collect_device(enc, slot, out_bytes, n_frames, elapsed_ms);
 }
 
 extern "C" int b200flac_encoder_last_kernel_ms(b200flac_encoder* enc, int slot, float* ms, int capacity)

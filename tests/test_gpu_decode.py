@@ -243,6 +243,56 @@ def test_flacdecoder_reads_frame_by_frame(tmp_path, built):
     assert flac.verify() is True
 
 
+def test_flacdecoder_seek_follows_the_seektable(tmp_path, built):
+    """FlacDecoder.seek (src/decoders/flac.c:288-356): the latest SEEKTABLE point at or before the requested PCM
+    frame -- from_pcm writes one every 10 s --, its PCM frame number returned, reading resumes at that frame, the
+    MD5 is only validated when decoding restarts from 0; without a table every seek lands on frame 0"""
+    import audiotools
+    rate, n = 8000, 8000 * 35 + 123
+    pcm = helpers.synth_pcm(12, 1, 16, n)
+    path = os.path.join(str(tmp_path), "s.flac")
+    flac = audiotools.FlacAudio.from_pcm(path, audiotools.PCMBytesReader(pcm, rate, 1, 0x4, 16), "5")
+    samples = helpers.unpack_pcm(pcm, 16)
+    d = flac.to_pcm()
+    # seek points at 0, 80000, 160000, 240000 PCM frames -> the 4096-frame blocks containing them
+    starts = [(t // 4096) * 4096 for t in (0, 80000, 160000, 240000)]
+    assert starts == [0, 77824, 159744, 237568]
+    # (a point's sample number is its frame's first sample, so 159744..159999 already belong to the third point)
+    for want_frame, target in ((starts[0], 0), (starts[0], 4096 * 3), (starts[1], 80000), (starts[1], 159743),
+                               (starts[2], 159744), (starts[2], 160000), (starts[3], n + 5000)):
+        assert d.seek(target) == want_frame
+        f = d.read(4096)
+        assert list(f) == list(samples[want_frame:want_frame + f.frames]) and f.frames == min(4096, n - want_frame)
+    # read to the end after a seek into the middle: no MD5 verdict (validation is off), an empty FrameList ends it
+    d.seek(200000)
+    total = 0
+    while True:
+        f = d.read(4096)
+        if f.frames == 0:
+            break
+        total += f.frames
+    assert total == n - starts[2]
+    # back to the start: the whole stream again, MD5 checked
+    assert d.seek(0) == 0
+    total = 0
+    while True:
+        f = d.read(4096)
+        if f.frames == 0:
+            break
+        total += f.frames
+    assert total == n
+    with pytest.raises(ValueError, match="negative"):
+        d.seek(-1)
+    d.close()
+    with pytest.raises(ValueError, match="cannot seek closed stream"):
+        d.seek(0)
+    # a stream without a SEEKTABLE (the encoder's own output): every seek goes to the start
+    raw = os.path.join(str(tmp_path), "raw.flac")
+    open(raw, "wb").write(helpers.oracle_encode(pcm, rate, 1, 16, helpers.options()))
+    d = audiotools.FlacAudio(raw).to_pcm()
+    assert d.seek(100000) == 0 and list(d.read(4096)) == list(samples[:4096])
+
+
 def test_flacdecoder_md5_mismatch_at_end_of_stream(tmp_path, built):
     import audiotools
     import audiotools.decoders

@@ -95,6 +95,41 @@ def test_chunk_pipeline_same_frames(chunk, lookahead, bs, built):
     enc.close()
 
 
+def test_device_resident_async_two_slots(built):
+    """b200flac_encoder_submit_device / collect_device: two batches in flight on two slots give what the
+    synchronous call gives, and the oracle's frames"""
+    b = _b200()
+    L = b.lib()
+    o = helpers.options(block_size=1024, max_lpc_order=8, max_residual_partition_order=4, adaptive_mid_side=True)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 2, 16, **kw)
+    n = 1024 * 50 + 300
+    enc = b.Encoder(p, max_pcm_frames_per_batch=n, n_slots=2)
+    cap = enc.output_bound(n, 1)
+    bufs = []
+    for seed in (5, 6):
+        d_pcm, d_out = L.b200flac_device_alloc(0, n * 4), L.b200flac_device_alloc(0, cap)
+        assert L.b200flac_device_synth_pcm(0, d_pcm, seed, 2, 16, 0, n) == 0
+        bufs.append((seed, d_pcm, d_out))
+    for rep in range(2):
+        for slot, (seed, d_pcm, d_out) in enumerate(bufs):
+            enc.submit_device(d_pcm, [(0, n, 0)], d_out, cap, slot=slot)
+        with pytest.raises(b.B200FlacError, match="busy"):
+            enc.submit_device(bufs[0][1], [(0, n, 0)], bufs[0][2], cap, slot=0)
+        for slot, (seed, d_pcm, d_out) in enumerate(bufs):
+            nbytes, nfr, ms = enc.collect_device(slot=slot)
+            host = np.empty(nbytes, dtype=np.uint8)
+            assert L.b200flac_device_download(0, host.ctypes.data, d_out, nbytes) == 0
+            want, _ = helpers.oracle_encode_range(helpers.synth_pcm(seed, 2, 16, n), 44100, 2, 16, o, 0)
+            assert nfr == 51 and host.tobytes() == want and ms > 0
+    with pytest.raises(b.B200FlacError, match="no batch"):
+        enc.collect_device(slot=0)
+    for _, d_pcm, d_out in bufs:
+        L.b200flac_device_free(0, d_pcm)
+        L.b200flac_device_free(0, d_out)
+    enc.close()
+
+
 def test_device_synth_matches_oracle_generator(built):
     b = _b200()
     import ctypes as C
