@@ -664,6 +664,8 @@ static bool is_pinned(const void* p)
     return a.type == cudaMemoryTypeHost;
 }
 
+extern "C" int b200flac_internal_is_pinned(const void* p) { return is_pinned(p) ? 1 : 0; }   // (stream layer)
+
 extern "C" uint8_t* b200flac_encoder_slot_pcm(b200flac_encoder* enc, int slot)
 {
     if (!enc || slot < 0 || slot >= enc->n_slots) return nullptr;

@@ -19,6 +19,7 @@
 #include "../../include/b200flac.h"
 
 extern "C" void b200flac_internal_set_error(const char* msg); // b200flac_encoder.cu
+extern "C" int b200flac_internal_is_pinned(const void* p);    // b200flac_encoder.cu
 
 // ---------------------------------------------------------------------------
 // MD5 (RFC 1321).  The reference hashes the PCM as signed little-endian bytes
@@ -130,6 +131,7 @@ struct Lane {
     b200flac_encoder* enc;
     int slot;
     uint8_t* pcm;          // pinned staging of this lane
+    const uint8_t* ext;    // this batch's PCM lies in the caller's own page-locked memory (no staging copy)
     uint64_t fill;         // PCM frames staged
     uint64_t md5_enq;      // PCM frames of this batch already handed to the MD5 thread
     std::vector<b200flac_segment> segs;
@@ -373,7 +375,7 @@ extern "C" b200flac_stream* b200flac_stream_open(const char* filename, const b20
         for (int i = 0; i < n_devices; i++) {
             Lane l;
             l.enc = s->encs[i]; l.slot = k; l.pcm = b200flac_encoder_slot_pcm(l.enc, k);
-            l.fill = 0; l.md5_enq = 0; l.seg_start = 0; l.in_flight = false; l.md5_ticket = 0;
+            l.fill = 0; l.md5_enq = 0; l.seg_start = 0; l.in_flight = false; l.md5_ticket = 0; l.ext = nullptr;
             s->lanes.push_back(l);
         }
 
@@ -437,6 +439,7 @@ static int collect_oldest(b200flac_stream* s)
     l.in_flight = false;
     l.fill = 0;
     l.md5_enq = 0;
+    l.ext = nullptr;
     l.segs.clear();
     s->oldest = (s->oldest + 1) % s->lanes.size();
     s->n_in_flight--;
@@ -467,7 +470,7 @@ static void md5_enqueue(b200flac_stream* s, Lane& l, size_t min_bytes)
     const size_t pending = (size_t)(l.fill - l.md5_enq) * frame_bytes;
     if (pending == 0 || pending < min_bytes) return;
     pthread_mutex_lock(&s->mu);
-    s->jobs.push_back(Md5Job{l.pcm + (size_t)l.md5_enq * frame_bytes, pending});
+    s->jobs.push_back(Md5Job{(l.ext ? l.ext : l.pcm) + (size_t)l.md5_enq * frame_bytes, pending});
     l.md5_ticket = ++s->jobs_submitted;
     pthread_cond_signal(&s->cv_job);
     pthread_mutex_unlock(&s->mu);
@@ -481,7 +484,7 @@ static int submit_current(b200flac_stream* s)
     close_segment(s, l);
     if (l.segs.empty()) return 0;
     md5_enqueue(s, l, 0); // whatever of this batch the MD5 thread has not been given yet
-    if (b200flac_encoder_submit(l.enc, l.slot, l.pcm, l.segs.data(), (uint32_t)l.segs.size())) {
+    if (b200flac_encoder_submit(l.enc, l.slot, l.ext ? l.ext : l.pcm, l.segs.data(), (uint32_t)l.segs.size())) {
         stream_err(b200flac_last_error());
         s->failed = true;
         return 1;
@@ -492,7 +495,7 @@ static int submit_current(b200flac_stream* s)
     Lane& nx = s->lanes[s->cur];
     if (nx.in_flight && collect_oldest(s)) return 1; // lanes are reused in order, so nx is the oldest
     md5_wait(s, nx.md5_ticket);                      // its staging must not be hashed any more
-    nx.fill = 0; nx.md5_enq = 0; nx.seg_start = 0; nx.segs.clear();
+    nx.fill = 0; nx.md5_enq = 0; nx.seg_start = 0; nx.segs.clear(); nx.ext = nullptr;
     return 0;
 }
 
@@ -631,6 +634,32 @@ extern "C" int b200flac_stream_close(b200flac_stream* s, int abort_encode, uint6
 
 extern "C" void b200flac_free(void* p) { free(p); }
 
+// b200flac_stream_write for PCM in the caller's own page-locked memory that stays valid until the stream is closed
+// (b200flac_encode_file): whole batches go to the device straight from it and the MD5 thread hashes it in place --
+// no copy into the lanes' staging.  Only on a lane that holds nothing yet.
+static int stream_write_in_place(b200flac_stream* s, const uint8_t* pcm, uint64_t n_pcm_frames)
+{
+    const size_t frame_bytes = (size_t)s->params.channels * (s->params.bits_per_sample / 8);
+    const uint32_t bs = s->params.block_size;
+    const uint64_t cap = s->batch_frames / bs * bs;
+    while (n_pcm_frames) {
+        Lane& l = s->lanes[s->cur];
+        if (l.fill != 0 || l.seg_start != 0 || !l.segs.empty()) return b200flac_stream_write(s, pcm, n_pcm_frames);
+        const uint64_t take = n_pcm_frames < cap ? n_pcm_frames : cap;
+        l.ext = pcm;
+        // the hash runs ahead in pieces, as it does under the staging copy
+        const uint64_t piece = MD5_PIECE / frame_bytes + 1;
+        while (l.fill < take) {
+            l.fill += (take - l.fill) < piece ? (take - l.fill) : piece;
+            md5_enqueue(s, l, 0);
+        }
+        if (submit_current(s)) return 1;
+        pcm += (size_t)take * frame_bytes;
+        n_pcm_frames -= take;
+    }
+    return 0;
+}
+
 extern "C" int b200flac_encode_file(const char* filename, const b200flac_params* params,
                                     uint32_t padding_size, const char* version,
                                     const uint8_t* pcm, uint64_t n_pcm_frames,
@@ -638,6 +667,10 @@ extern "C" int b200flac_encode_file(const char* filename, const b200flac_params*
 {
     b200flac_stream* s = b200flac_stream_open(filename, params, padding_size, version, devices, n_devices);
     if (!s) return 1;
-    if (b200flac_stream_write(s, pcm, n_pcm_frames)) { b200flac_stream_close(s, 1, nullptr, nullptr, nullptr); return 1; }
+    const int in_place = n_pcm_frames && b200flac_internal_is_pinned(pcm);
+    if (in_place ? stream_write_in_place(s, pcm, n_pcm_frames) : b200flac_stream_write(s, pcm, n_pcm_frames)) {
+        b200flac_stream_close(s, 1, nullptr, nullptr, nullptr);
+        return 1;
+    }
     return b200flac_stream_close(s, 0, nullptr, nullptr, nullptr);
 }

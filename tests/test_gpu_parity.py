@@ -95,6 +95,28 @@ def test_chunk_pipeline_same_frames(chunk, lookahead, bs, built):
     enc.close()
 
 
+def test_encode_file_from_pinned_memory_in_place(tmp_path, built):
+    """b200flac_encode_file with the PCM in page-locked memory (b200flac_host_alloc): batches go to the device and
+    to the MD5 thread straight from the caller's buffer -- same file as from pageable memory and as the oracle's;
+    several batches (block 256 -> 2048-block batches) and a ragged tail"""
+    import ctypes as C
+    b = _b200()
+    L = b.lib()
+    o = helpers.options(block_size=256, max_lpc_order=4, max_residual_partition_order=3, adaptive_mid_side=True)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 2, 16, **kw)
+    n = 256 * 2048 * 3 + 256 * 11 + 5
+    pcm = helpers.synth_pcm(90, 2, 16, n)
+    h = L.b200flac_host_alloc(len(pcm))
+    assert h
+    C.memmove(h, pcm, len(pcm))
+    path = os.path.join(str(tmp_path), "pinned.flac")
+    dev = (C.c_int * 1)(0)
+    assert L.b200flac_encode_file(os.fsencode(path), C.byref(p), 4096, None, h, n, dev, 1) == 0
+    L.b200flac_host_free(h)
+    assert open(path, "rb").read() == helpers.oracle_encode(pcm, 44100, 2, 16, o)
+
+
 def test_device_resident_async_two_slots(built):
     """b200flac_encoder_submit_device / collect_device: two batches in flight on two slots give what the
     synchronous call gives, and the oracle's frames"""
