@@ -14,10 +14,22 @@ frame select, offset scan, frame pack + CRC-16) over the rank's whole hour.
   value : whole-job Msamples/s with the PCM already resident in HBM and the frames left in
           HBM (b200flac_encoder_submit_device / collect_device on two slots), wall clock around
           K steps bracketed by barrier + device synchronize, max over ranks.
-  e2e   : same metric through the host-buffer C-ABI calls (b200flac_encoder_submit/collect):
-          pinned host PCM -> H2D -> kernels -> D2H frame bytes, every step, 3 batches in flight.
-  roofline : dominant kernel, algorithmic bytes (PCM in + frame bytes out) / its CUDA-event time.
-  cpu_baseline : oracle/_ref/flacenc (the compiled reference) on the box's host cores, N=1 only.
+  e2e   : the same metric through the call the reference's user makes -- the stream layer
+          (b200flac_stream_open / write / close: what audiotools.encoders.encode_flac binds): pageable host
+          PCM in, a finished .flac (STREAMINFO with MD5, frames) written to a file on tmpfs, every step;
+          host<->device copies, the MD5 thread and the file write are inside the timed region.
+  e2e_frame_layer : the host-buffer frame calls (b200flac_encoder_submit / collect): pinned host PCM -> H2D ->
+          kernels -> D2H frame bytes, 3 batches in flight, with `copy_floor_ms` = the same bytes moved with
+          no kernels (what PCIe alone costs on this box at this N).
+  api   : the Python boundary (audiotools.encoders.encode_flac with a PCMReader), whole hour and many short tracks.
+  configs : BASELINE.json configs[0], [2], [3], [4] resident on one GPU (N=1), byte-compared on a sample with the
+          compiled reference encoder; siblings: the TTA and ALAC encoders on the same hour.
+  sharded_stream : N>1 only -- ONE hour cut by frame range across the ranks, the shards concatenated on rank 0
+          and compared byte for byte with the single-GPU stream.
+  roofline : dominant kernel, algorithmic bytes (PCM in + frame bytes out) / its CUDA-event time; `traffic`
+          from profiles/r02_traffic.json (ncu --set full of the same kernels).
+  cpu_baseline : oracle/_ref/flacenc (the compiled reference) on the box's host cores, N=1 only; its output on
+          the sample is also byte-compared with this engine's.
 
 One JSON line on stdout (rank 0).
 """
