@@ -134,7 +134,7 @@ struct b200flac_encoder {
     u32 p3_img_words;
     size_t p3_smem;
     unsigned short* d_crc_tab;   // [256] byte table + [69 + n] powers of x (see k_pack_v3)
-    u32 v3_S, v3_F, v3_NT;
+    u32 v3_S, v3_F, v3_NT, v3_sub;   // v3_sub: run sums per thread run (2: partition order 8)
     size_t v3_smem;
     int v3_occ;           // resident CTAs per SM of k_analyze_v3 (the kernel is persistent)
     std::map<u32, std::vector<double>>* windows;
@@ -471,7 +471,15 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         const char* force = getenv("B200FLAC_NO_V3");
         const u32 F = std::min<u32>(P.po_lim, (u32)__builtin_ctz(bs));
         if (enc->fast && P.try_lpc && P.try_fixed && P.try_constant && P.try_verbatim &&
-            F <= V3_MAX_F && bs > P.max_lpc_order + 1 && !(force && force[0] == '1')) {
+            F <= V3_MAX_F + 1 && bs > P.max_lpc_order + 1 && !(force && force[0] == '1')) {
+            enc->v3_sub = 1;
+            if (F == V3_MAX_F + 1) {
+                // partition order 8: 128 threads x 32 samples, a finest partition is half a thread run (run sums per half)
+                if (bs == 32u * 128u && P.max_lpc_order <= 16) {
+                    enc->v3 = true; enc->v3_S = 32; enc->v3_F = F; enc->v3_NT = 128; enc->v3_sub = 2;
+                    enc->v3_smem = v3_smem_bytes(bs, 128, 2);
+                }
+            } else
             for (u32 S3 = 32; S3 >= 8; S3 -= 8) {
                 if (bs % S3 || (bs >> F) % S3) continue;
                 const u32 nt = bs / S3;
@@ -485,13 +493,17 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
         if (enc->v3) {
             const bool s32 = enc->v3_NT <= 128 && enc->v3_S == 32;   // samples per thread known at compile time
 #define V3_ATTR(MINB_, EXH_, SC_) cudaFuncSetAttribute(k_analyze_v3<MINB_, EXH_, SC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
-            if (P.exhaustive) e = s32 ? V3_ATTR(5, true, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, true, 0) : enc->v3_NT <= 256 ? V3_ATTR(3, true, 0) : V3_ATTR(1, true, 0);
+            if (enc->v3_sub == 2)
+                e = P.exhaustive ? cudaFuncSetAttribute(k_analyze_v3<4, true, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
+                                 : cudaFuncSetAttribute(k_analyze_v3<4, false, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
+            else if (P.exhaustive) e = s32 ? V3_ATTR(5, true, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, true, 0) : enc->v3_NT <= 256 ? V3_ATTR(3, true, 0) : V3_ATTR(1, true, 0);
             else e = s32 ? V3_ATTR(5, false, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, false, 0) : enc->v3_NT <= 256 ? V3_ATTR(3, false, 0) : V3_ATTR(1, false, 0);
 #undef V3_ATTR
             if (e != cudaSuccess) enc->v3 = false;
             enc->v3_occ = 1;
             if (enc->v3) {
-                if (enc->v3_NT <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<5, false, 0>, (int)enc->v3_NT, enc->v3_smem);
+                if (enc->v3_sub == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<4, false, 32, 2>, (int)enc->v3_NT, enc->v3_smem);
+                else if (enc->v3_NT <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<5, false, 0>, (int)enc->v3_NT, enc->v3_smem);
                 else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->v3_occ, k_analyze_v3<1, false, 0>, (int)enc->v3_NT, enc->v3_smem);
                 if (enc->v3_occ < 1) enc->v3_occ = 1;
             }
@@ -935,7 +947,11 @@ static void stage_analyze(b200flac_encoder* enc, const ChunkView& v, cudaStream_
         if (getenv("B200FLAC_V3_GRID")) g3 = (u32)atoi(getenv("B200FLAC_V3_GRID"));   // tuning knob
         if (g3 > v.U || g3 == 0) g3 = v.U;
 #define V3_LAUNCH(MINB_, EXH_, SC_) k_analyze_v3<MINB_, EXH_, SC_><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice)
-        if (enc->v3_NT <= 128 && enc->v3_S == 32) { if (P.exhaustive) V3_LAUNCH(5, true, 32); else V3_LAUNCH(5, false, 32); }
+        if (enc->v3_sub == 2) {
+            if (P.exhaustive) k_analyze_v3<4, true, 32, 2><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice);
+            else k_analyze_v3<4, false, 32, 2><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice);
+        }
+        else if (enc->v3_NT <= 128 && enc->v3_S == 32) { if (P.exhaustive) V3_LAUNCH(5, true, 32); else V3_LAUNCH(5, false, 32); }
         else if (enc->v3_NT <= 128) { if (P.exhaustive) V3_LAUNCH(5, true, 0); else V3_LAUNCH(5, false, 0); }
         else if (enc->v3_NT <= 256) { if (P.exhaustive) V3_LAUNCH(3, true, 0); else V3_LAUNCH(3, false, 0); }
         else { if (P.exhaustive) V3_LAUNCH(1, true, 0); else V3_LAUNCH(1, false, 0); }

@@ -190,7 +190,7 @@ __device__ __forceinline__ int fixed_residual(const int* samp, u32 i, u32 order)
 __device__ __forceinline__ int lpc_residual(const int* samp, u32 i, u32 order, const short* q, int shift)
 {
     long long acc = 0;
-    for (u32 j = 0; j < order; j++) acc += (long long)q[j] * (long long)samp[PADI(i - 1 - j)];
+    for (u32 j = 0; j < order; j++) acc = mad_wide((int)q[j], samp[PADI(i - 1 - j)], acc);
     acc >>= shift;
     return (int)((u32)samp[PADI(i)] - (u32)(int)acc);
 }

@@ -17,17 +17,22 @@
 #include "flac_common.cuh"
 #include "k_analyze.cuh"
 
-// Rice parameter + estimate of one partition, same results as partition_estimate():
-// closed form when no shift of the reference's loop can wrap 32 bits, the loop itself otherwise.
+// Rice parameter + estimate of one partition, same results as partition_estimate(): closed form when the 32-bit
+// wrap of the reference's shift (H3) cannot change the outcome, the loop itself otherwise.
+// With kc the smallest k such that plength * 2^k >= S_ in exact arithmetic: for k < kc the wrapped value is at
+// most the exact one, hence still below S_ and the loop goes on; at kc the exact value is below 2 * S_ (kc is
+// minimal), so for S_ < 2^31 it has not wrapped and the loop stops there -- whatever max_rice is.  (The earlier
+// test, "no shift up to max_rice wraps", sent every 24-bit partition of four samples or more through the loop:
+// max_rice is 30 there.)
 __device__ __forceinline__ u64 partition_estimate_fast(u32 plength, u64 S_, u32 max_rice, u32* k_out)
 {
     u32 k;
     if (S_ <= (u64)plength) {
         k = 0;
-    } else if (plength == 0 || ((u64)plength << max_rice) >= (1ull << 32)) {
+    } else if (plength == 0 || S_ >= (1ull << 31)) {
         return partition_estimate(plength, S_, max_rice, k_out);
     } else {
-        // smallest k with (plength << k) >= S_; none of the shifts up to max_rice wraps
+        // smallest k with (plength << k) >= S_
         int kc = (64 - __clzll((long long)S_)) - (32 - __clz((int)plength)) - 1;
         if (kc < 0) kc = 0;
         while (((u64)plength << kc) < S_) kc++;
@@ -350,7 +355,7 @@ __device__ __forceinline__ void lpc_residual_v2(const V2Ctx& c, const short* q_s
             if (WIDE) {
                 long long acc = 0;
 #pragma unroll
-                for (int t = 0; t < OG; t++) acc += (long long)q[t] * (long long)w[OG + j - 1 - t];
+                for (int t = 0; t < OG; t++) acc = mad_wide(q[t], w[OG + j - 1 - t], acc);
                 pred = (int)(acc >> shift);
             } else {
                 int acc = 0;

@@ -33,10 +33,13 @@
 #define V3_LOOP
 #endif
 #define V3_SK(i) ((i) + (((i) >> 5) << 2))      // four words of skew per 32 samples
-#ifndef V3_MAX_F
-#define V3_MAX_F 7                               // finest partition order handled (<= 128 partitions; order 8 measured slower than k_analyze_v2,
-#endif                                           // with and without the exhaustive search: 96 kHz/24-bit -e R8 10.6 vs 7.2 ms per 5 minutes)
-#define V3_HEAP (2 << V3_MAX_F)
+// Finest partition order handled: 7 (<= 128 partitions, one or more whole thread runs each), or 8 in the SUB = 2
+// instantiations, where a thread's run of 32 samples is TWO finest partitions of 16 and every run sum is kept per
+// half run.  (Order 8 with 256 threads x 16 samples was slower than k_analyze_v2: 10.6 vs 7.2 ms per 5 minutes of
+// 96 kHz/24-bit -e -R8; the extra shared memory of order 8 costs the common shapes a resident CTA, hence the template.)
+#define V3_MAX_F 7
+#define V3_LVL_H0 9                              // lvl[..][9], [10]: the two halves of a finest level evaluated by two warps
+#define V3_LVL_H1 10
 
 // totals of one partition order of one model (written by whichever warp evaluated the level)
 struct V3Level {
@@ -45,8 +48,10 @@ struct V3Level {
     u32 maxk;
 };
 
-struct V3Shared {
-    V3Level lvl[2][V3_MAX_F + 3];   // [..][V3_MAX_F + 1], [V3_MAX_F + 2]: the two halves of a finest level evaluated by two warps
+template <int MF>
+struct V3SharedT {
+    static constexpr int HEAP = 2 << MF;
+    V3Level lvl[2][11];
     u64 totF[5];          // FIXED: block totals of the error sums (flac.c:877-893), wide blocks
     u32 totF16[5][2];     // ... narrow blocks: sums of the low 16 bits / the rest of the warp sums
     u32 bits16[2][2];     // exact sum of (u >> k), per model, split the same way
@@ -57,17 +62,18 @@ struct V3Shared {
     u32 bitsL[2][2];      // exhaustive search: exact sum of (u >> k) of the orders in flight (by order parity)
     short q[BF_MAX_ORDER];
     short q2[2][BF_MAX_ORDER];                  // exhaustive search: coefficients of the order being run and the next
-    uint8_t kheapL[2][V3_HEAP];                 // exhaustive search: Rice parameters of the two orders in flight
+    uint8_t kheapL[2][HEAP];                    // exhaustive search: Rice parameters of the two orders in flight
     alignas(4) bf_lpc_head head;      // (copied as words)
-    uint8_t kheap[2][V3_HEAP];
-    uint8_t kbest[V3_HEAP / 2];   // exhaustive search: Rice parameters of the best LPC order so far
+    uint8_t kheap[2][HEAP];
+    uint8_t kbest[HEAP / 2];   // exhaustive search: Rice parameters of the best LPC order so far
 };
 
 // host and device agree on the dynamic shared memory through this
-__host__ __device__ inline size_t v3_smem_bytes(u32 n, u32 NT)
+// (sub: run sums kept per thread run, 1 or 2)
+__host__ __device__ inline size_t v3_smem_bytes(u32 n, u32 NT, u32 sub = 1)
 {
     const size_t padn = (size_t)V3_SK(n) + 8;
-    return 2 * padn * 4 + (size_t)5 * NT * 8 + (size_t)NT * 8 + 32;
+    return 2 * padn * 4 + (size_t)6 * NT * sub * 8 + 32;
 }
 
 __device__ __forceinline__ u64 v3_warp_sum_u64(u64 v)
@@ -86,8 +92,9 @@ __device__ __forceinline__ u64 v3_warp_sum_u64(u64 v)
 //           which this warp builds in `pre` (shared, nfine entries) first.
 // The two parts are independent, so two warps can run them side by side.  Each part also comes in two halves
 // for four warps (the exhaustive search runs one model at a time): parts 2 and 3 take alternate steps of the
-// finest order and leave their totals in lvl[V3_MAX_F + 1] / [V3_MAX_F + 2] (v3_pick_level adds them up),
-// part 4 takes orders 0..4 (nodes 1..31), part 5 the orders from 5 up; 4 and 5 each build their own prefix sums.
+// finest order and leave their totals in lvl[V3_LVL_H0] / [V3_LVL_H1] (v3_pick_level adds them up),
+// part 4 takes orders 0..4 (nodes 1..31) and order 7 if there is one below the finest, part 5 orders 5 and 6;
+// 4 and 5 each build their own prefix sums.  S: samples per run sum.
 __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_extra, u32 S, u32 n, u32 order,
                                        u32 F, u32 max_rice, uint8_t* kheap, V3Level* lvl, u64* pre, u32 part)
 {
@@ -112,7 +119,7 @@ __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_e
         const u64 tot = v3_warp_sum_u64(est_acc);
         const u32 cnt = __reduce_add_sync(0xFFFFFFFFu, cnt_acc);
         const u32 mk = __reduce_max_sync(0xFFFFFFFFu, k_acc);
-        V3Level* out = part == 0 ? lvl + F : lvl + V3_MAX_F + (part - 1);
+        V3Level* out = part == 0 ? lvl + F : lvl + V3_LVL_H0 + (part - 2);
         if (lane == 0) { out->tot = tot; out->cnt = cnt; out->maxk = mk; }
         return;
     }
@@ -142,7 +149,8 @@ __device__ __noinline__ void v3_levels(const u64* __restrict__ runs, u64 first_e
         for (u32 i = 0; i < c; i++) if (b + i < nfine) pre[b + i] += excl;
     }
     __syncwarp();
-    for (u32 node0 = part == 5 ? 32u : 0u; node0 < (part == 4 ? 32u : nfine); node0 += 32) {
+    for (u32 node0 = part == 5 ? 32u : 0u; node0 < (part == 5 ? min(nfine, 128u) : nfine); node0 += 32) {
+        if (part == 4 && node0 == 32) { node0 = 96; continue; }        // (orders 5 and 6 are part 5's)
         const u32 node = node0 + lane;
         const bool act = node >= 1 && node < nfine;
         u32 l = 0, k = 0, cnt = 0;
@@ -190,8 +198,8 @@ __device__ __forceinline__ void v3_pick_level(const V3Level* lvl, u32 F, u32* po
                                               bool split = false)
 {
     const u32 lane = threadIdx.x & 31;
-    const V3Level* h0 = lvl + V3_MAX_F + 1;
-    const V3Level* h1 = lvl + V3_MAX_F + 2;
+    const V3Level* h0 = lvl + V3_LVL_H0;
+    const V3Level* h1 = lvl + V3_LVL_H1;
     const u64 tot = lane > F ? ~0ull : (split && lane == F) ? h0->tot + h1->tot : lvl[lane].tot;
     const u32 hi = (u32)(tot >> 32), lo = (u32)tot;
     const u32 mhi = __reduce_min_sync(0xFFFFFFFFu, hi);
@@ -216,14 +224,21 @@ __device__ __forceinline__ void v3_fixed_history(const int* __restrict__ samp, u
 
 // FIXED error sums of orders 0..4 over the thread's run: e[k] = sum of |r_k[i]| (flac.c:877-893).
 // Run 0 is summed like the others (zero history) and corrected by v3_fixed_head afterwards.
-template <typename SumT>
-__device__ __forceinline__ void v3_fixed_sums(const int* __restrict__ samp, u32 base, u32 S, SumT (&e)[5])
+// SUB = 2: the sums of the first half run go to half0[k * stride] when the half ends, e[] gets the second half's.
+template <typename SumT, int SUB>
+__device__ __forceinline__ void v3_fixed_sums(const int* __restrict__ samp, u32 base, u32 S, SumT (&e)[5],
+                                              u64* __restrict__ half0, u32 stride)
 {
     u32 prev, p1, p2, p3;
     v3_fixed_history(samp, base, prev, p1, p2, p3);
     SumT f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
     V3_LOOP
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+        if (SUB == 2 && i0 == base + (S >> 1)) {
+            half0[0] = (u64)f0; half0[stride] = (u64)f1; half0[2 * stride] = (u64)f2; half0[3 * stride] = (u64)f3;
+            half0[4 * stride] = (u64)f4;
+            f0 = 0; f1 = 0; f2 = 0; f3 = 0; f4 = 0;
+        }
         const int4 va = *(const int4*)(samp + V3_SK(i0));
         const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
         const int xs[V3_CH] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
@@ -264,13 +279,15 @@ __device__ __forceinline__ void v3_fixed_sums(const int* __restrict__ samp, u32 
 // run 0 only: the reference sums the errors from sample 4 for every order, so take samples 0..3
 // (as v3_fixed_sums counted them, with zero history) out of e[], and collect in corr[k] the true
 // residuals |r_k[i]|, k <= i < 4, which the partition sums of order k do contain
-template <typename SumT>
-__device__ __forceinline__ void v3_fixed_head(const int* __restrict__ samp, SumT (&e)[5], u64* corr)
+// (returned in g[], the caller subtracts them from run 0's -- or half run 0's -- sums)
+__device__ __forceinline__ void v3_fixed_head(const int* __restrict__ samp, u32 (&g)[5], u64* corr)
 {
     const int4 v = *(const int4*)samp;
     const u32 xs[4] = {(u32)v.x, (u32)v.y, (u32)v.z, (u32)v.w};
     u32 prev = 0, p1 = 0, p2 = 0, p3 = 0;
-    u32 g[5] = {0, 0, 0, 0, 0}, c[5] = {0, 0, 0, 0, 0};
+    u32 c[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 5; k++) g[k] = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const u32 x = xs[j];
@@ -281,15 +298,16 @@ __device__ __forceinline__ void v3_fixed_head(const int* __restrict__ samp, SumT
         prev = x; p1 = d1; p2 = d2; p3 = d3;
     }
 #pragma unroll
-    for (int k = 0; k < 5; k++) { e[k] -= (SumT)g[k]; corr[k] = (u64)c[k]; }
+    for (int k = 0; k < 5; k++) corr[k] = (u64)c[k];
 }
 
 // LPC residual of the thread's run (flac.c:999-1008) into resid, chunks of 8, history window in
 // registers; returns the run's sum of |r|.  OG: taps (coefficients zero-padded, exact).
 // WIDE: 64-bit accumulate, otherwise 32-bit (only chosen when the sum provably fits).
-template <int OG, bool WIDE>
+// SUB = 2: the sum of the first half run goes to *half0 when the half ends, the second half's is returned.
+template <int OG, bool WIDE, int SUB>
 __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int* __restrict__ resid, u32 base, u32 S,
-                                               const short* q_sm, int shift)
+                                               const short* q_sm, int shift, u64* __restrict__ half0)
 {
     int q[OG];
 #pragma unroll
@@ -305,6 +323,7 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
     u64 run = 0;
     V3_LOOP
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+        if (SUB == 2 && i0 == base + (S >> 1)) { *half0 = run; run = 0; }
         const int4 va = *(const int4*)(samp + V3_SK(i0));
         const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
         w[OG + 0] = va.x; w[OG + 1] = va.y; w[OG + 2] = va.z; w[OG + 3] = va.w;
@@ -316,7 +335,7 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
             if (WIDE) {
                 long long acc = 0;
 #pragma unroll
-                for (int t = 0; t < OG; t++) acc += (long long)q[t] * (long long)w[OG + j - 1 - t];
+                for (int t = 0; t < OG; t++) acc = mad_wide(q[t], w[OG + j - 1 - t], acc);
                 pred = (int)(acc >> shift);
             } else {
                 int acc = 0;
@@ -440,8 +459,9 @@ __device__ __forceinline__ u32 v3_stored_bits(const int* __restrict__ resid, u32
 // left to k_analyze_v2 (launched over the same grid, which skips the others).
 // EXH: exhaustive order search (flac.c:1070-1120): FIXED as usual, then every LPC order 1..max in turn
 // (residual, Rice search, exact bits), keeping the first strict minimum of the exact sizes.
-template <bool EXH, int SC>
-__device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u32 unit,
+// SUB: run sums per thread run (2: the finest partition is half a run, see V3_MAX_F).
+template <bool EXH, int SC, int SUB>
+__device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB == 2 ? 8 : V3_MAX_F)>& sh, u32 unit,
                                         const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                                         const bf_dev_params& P, u32 S_rt, u32 F,
                                         const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
@@ -459,8 +479,9 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     const size_t padn = (size_t)V3_SK(n) + 8;
     int* samp = (int*)dyn_smem;
     int* resid = samp + padn;
-    u64* runsF = (u64*)(resid + padn);          // [5][nt]
-    u64* runsL = runsF + 5 * (size_t)nt;        // [nt]
+    const u32 R = nt * SUB;                     // run sums per row: entry SUB * tid + h is half h of thread tid's run
+    u64* runsF = (u64*)(resid + padn);          // [5][R]
+    u64* runsL = runsF + 5 * (size_t)R;         // [R]
 
     // ---- LPC model of the unit (last warp; overlaps the PCM load of the others) ----
     const short* mycoef = coefs + (size_t)unit * P.model_stride;
@@ -562,29 +583,37 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
 
     // ---- pass A: FIXED sums of all orders + LPC residual, run sums to shared memory ----
     {
+        u64* mine = runsF + SUB * tid;             // this thread's (first) entry of order 0's row
         if (sub_bps <= 23) {
             u32 e[5];
-            v3_fixed_sums<u32>(samp, base, S, e);
-            if (tid == 0) v3_fixed_head<u32>(samp, e, sh.corr);
+            v3_fixed_sums<u32, SUB>(samp, base, S, e, mine, R);
 #pragma unroll
-            for (int k = 0; k < 5; k++) runsF[k * nt + tid] = (u64)e[k];
+            for (int k = 0; k < 5; k++) mine[k * R + (SUB - 1)] = (u64)e[k];
+        } else {
+            u64 e[5];
+            v3_fixed_sums<u64, SUB>(samp, base, S, e, mine, R);
+#pragma unroll
+            for (int k = 0; k < 5; k++) mine[k * R + (SUB - 1)] = e[k];
+        }
+        if (tid == 0) {
+            u32 g[5];
+            v3_fixed_head(samp, g, sh.corr);
+#pragma unroll
+            for (int k = 0; k < 5; k++) runsF[k * R] -= (u64)g[k];
+        }
+        // block totals; each thread reads its own sums back, one rolled copy of the reduction for the five orders
+        if (sub_bps <= 23) {
             // 32 runs x 2^26 fit 32 bits; the two halves are summed over <= 16 warps with native
-            // 32-bit shared atomics (a 64-bit one is a compare-and-swap loop).  One rolled copy of the
-            // reduction for the five orders (each thread reads its own sums back).
+            // 32-bit shared atomics (a 64-bit one is a compare-and-swap loop)
 #pragma unroll 1
             for (int k = 0; k < 5; k++) {
-                const u32 ws = __reduce_add_sync(0xFFFFFFFFu, (u32)runsF[k * nt + tid]);
+                const u32 ws = __reduce_add_sync(0xFFFFFFFFu, (u32)mine[k * R] + (SUB == 2 ? (u32)mine[k * R + 1] : 0u));
                 if (lane == 0) { atomicAdd(&sh.totF16[k][0], ws & 0xFFFFu); atomicAdd(&sh.totF16[k][1], ws >> 16); }
             }
         } else {
-            u64 e[5];
-            v3_fixed_sums<u64>(samp, base, S, e);
-            if (tid == 0) v3_fixed_head<u64>(samp, e, sh.corr);
-#pragma unroll
-            for (int k = 0; k < 5; k++) runsF[k * nt + tid] = e[k];
 #pragma unroll 1
             for (int k = 0; k < 5; k++) {
-                u64 ws = runsF[k * nt + tid];
+                u64 ws = mine[k * R] + (SUB == 2 ? mine[k * R + 1] : 0ull);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) ws += __shfl_xor_sync(0xFFFFFFFFu, ws, o);
                 if (lane == 0) atomicAdd(&sh.totF[k], ws);
@@ -595,28 +624,31 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
     const u32 precision = sh.head.precision;
     bool lpc_narrow = false;
     int lpc_shift = 0;
-    // residual of order o with the coefficients staged in sh.q; returns the thread's run sum
-    auto lpc_pass = [&](u32 o, int shift, bool narrow, const short* qs) -> u64 {
+    // residual of order o with the coefficients staged in qs; leaves the thread's run sum(s) in runsL
+    auto lpc_pass = [&](u32 o, int shift, bool narrow, const short* qs) {
         u64 run;
+        u64* h0 = runsL + SUB * tid;
         // (no 8-tap variant: a second hot copy of the residual loop costs more in instruction fetch than
         // the four extra multiply-adds of a padded low order cost on the otherwise idle FMA pipe)
         // (the exhaustive search walks every order, so there the 8-tap copy pays for itself)
-        if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, false>(samp, resid, base, S, qs, shift)
-                                        : v3_lpc_residual<8, true>(samp, resid, base, S, qs, shift);
-        else if (o <= 12) run = narrow ? v3_lpc_residual<12, false>(samp, resid, base, S, qs, shift)
-                                       : v3_lpc_residual<12, true>(samp, resid, base, S, qs, shift);
-        else run = narrow ? v3_lpc_residual<32, false>(samp, resid, base, S, qs, shift)
-                          : v3_lpc_residual<32, true>(samp, resid, base, S, qs, shift);
+        if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, false, SUB>(samp, resid, base, S, qs, shift, h0)
+                                        : v3_lpc_residual<8, true, SUB>(samp, resid, base, S, qs, shift, h0);
+        else if (o <= 12) run = narrow ? v3_lpc_residual<12, false, SUB>(samp, resid, base, S, qs, shift, h0)
+                                       : v3_lpc_residual<12, true, SUB>(samp, resid, base, S, qs, shift, h0);
+        else run = narrow ? v3_lpc_residual<32, false, SUB>(samp, resid, base, S, qs, shift, h0)
+                          : v3_lpc_residual<32, true, SUB>(samp, resid, base, S, qs, shift, h0);
+        h0[SUB - 1] = run;
         if (tid == 0) {
+            u64 warm = 0;
 #pragma unroll 1
-            for (u32 i = 0; i < o; i++) run -= (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions
+            for (u32 i = 0; i < o; i++) warm += (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions (o <= 32 / SUB)
+            runsL[0] -= warm;
         }
-        return run;
     };
     if (!EXH) {
         lpc_shift = sh.head.shift[lpc_order - 1];
         lpc_narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
-        runsL[tid] = lpc_pass(lpc_order, lpc_shift, lpc_narrow, sh.q);
+        lpc_pass(lpc_order, lpc_shift, lpc_narrow, sh.q);
     }
     __syncthreads();                                                             // (2)
 
@@ -637,29 +669,41 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
         for (u32 task = role; task < (EXH ? 2u : 4u); task += nw) {
             // prefix sums go to the run-sum rows of two FIXED orders that lost; one call site for both models
             const bool lpc = task >= 2;
-            v3_levels(lpc ? runsL : runsF + (size_t)fixed_order * nt, lpc ? 0ull : sh.corr[fixed_order], S, n,
+            v3_levels(lpc ? runsL : runsF + (size_t)fixed_order * R, lpc ? 0ull : sh.corr[fixed_order], S / SUB, n,
                       lpc ? lpc_order : fixed_order, F, P.max_rice, sh.kheap[lpc ? 1 : 0], sh.lvl[lpc ? 1 : 0],
-                      runsF + (size_t)((fixed_order + (lpc ? 2u : 1u)) % 5) * nt, task & 1u);
+                      runsF + (size_t)((fixed_order + (lpc ? 2u : 1u)) % 5) * R, task & 1u);
         }
     }
     __syncthreads();                                                             // (3)
 
     // ---- pass B: exact bits of both models ----
-    // finest partition this thread's run lies in (its partition at order po is pF >> (F - po))
-    const u32 gruns = (n >> F) / S;
-    const u32 pF = (gruns & (gruns - 1)) == 0 ? tid >> (31 - __clz((int)gruns)) : tid / gruns;
+    // finest partition this thread's run lies in (its partition at order po is pF >> (F - po)); SUB = 2: the
+    // run is the finest partitions pF and pF + 1, and has two Rice parameters when the finest order is chosen
+    const u32 gruns = SUB == 2 ? 1u : (n >> F) / S;
+    const u32 pF = SUB == 2 ? 2u * tid : (gruns & (gruns - 1)) == 0 ? tid >> (31 - __clz((int)gruns)) : tid / gruns;
+    // exact bits of the thread's run for a model whose Rice parameters are kh[] at partition order po
+    auto run_bits = [&](const uint8_t* kh, u32 po, bool fixed, u32 order) -> u32 {
+        const u32 nseg = (SUB == 2 && po == F) ? 2u : 1u, len = S / nseg;
+        u32 acc = 0;
+#pragma unroll 1
+        for (u32 h = 0; h < nseg; h++) {
+            const u32 k = kh[(1u << po) - 1u + ((pF + h) >> (F - po))];
+            const u32 skip = (tid == 0 && h == 0) ? 1u : 0u;
+            acc += fixed ? v3_fixed_bits_any(samp, base + h * len, len, k, order, skip)
+                         : v3_stored_bits(resid, base + h * len, len, k, skip ? order : 0u);
+        }
+        return acc;
+    };
     u32 poF, poL = 0, methodF, methodL = 0;
     u64 sideF, sideL = 0;
     v3_pick_level(sh.lvl[0], F, &poF, &methodF, &sideF);
     if (!EXH) v3_pick_level(sh.lvl[1], F, &poL, &methodL, &sideL);
     {
-        const u32 kF = sh.kheap[0][(1u << poF) - 1u + (pF >> (F - poF))];
         // a warp's sum stays far below 2^32 (each run's is bounded by ~2 * partition length + 32 * 2^18)
-        const u32 bF = __reduce_add_sync(0xFFFFFFFFu, v3_fixed_bits_any(samp, base, S, kF, fixed_order, tid == 0 ? 1u : 0u));
+        const u32 bF = __reduce_add_sync(0xFFFFFFFFu, run_bits(sh.kheap[0], poF, true, fixed_order));
         if (lane == 0) { atomicAdd(&sh.bits16[0][0], bF & 0xFFFFu); atomicAdd(&sh.bits16[0][1], bF >> 16); }
         if (!EXH) {
-            const u32 kL = sh.kheap[1][(1u << poL) - 1u + (pF >> (F - poL))];
-            const u32 bL = __reduce_add_sync(0xFFFFFFFFu, v3_stored_bits(resid, base, S, kL, tid == 0 ? lpc_order : 0u));
+            const u32 bL = __reduce_add_sync(0xFFFFFFFFu, run_bits(sh.kheap[1], poL, false, lpc_order));
             if (lane == 0) { atomicAdd(&sh.bits16[1][0], bL & 0xFFFFu); atomicAdd(&sh.bits16[1][1], bL >> 16); }
         }
     }
@@ -709,21 +753,20 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
         for (u32 o = 1; o <= L; o++) {
             const int shift = sh.head.shift[o - 1];
             const bool narrow = ((u64)sh.lpc_narrow2[o & 1] << (sub_bps - 1)) < (1ull << 31);
-            runsL[tid] = lpc_pass(o, shift, narrow, sh.q2[o & 1]);
+            lpc_pass(o, shift, narrow, sh.q2[o & 1]);
             if (warp == nw - 1 && o < L) stage(o + 1);      // (its buffer was last read by order o - 1's pass)
             __syncthreads();
             if (o > 1) decide(o - 1);
             // the Rice search of the order as four warp tasks (both halves of the finest order, orders 0..4, orders 5..)
             for (u32 task = role; task < 4; task += nw)
-                v3_levels(runsL, 0ull, S, n, o, F, P.max_rice, sh.kheapL[o & 1], sh.lvl[1],
-                          runsF + (size_t)((fixed_order + 2 + (task & 1u)) % 5) * nt, 2u + task);
+                v3_levels(runsL, 0ull, S / SUB, n, o, F, P.max_rice, sh.kheapL[o & 1], sh.lvl[1],
+                          runsF + (size_t)((fixed_order + 2 + (task & 1u)) % 5) * R, 2u + task);
             __syncthreads();
             if (tid < 2) sh.bitsL[(o + 1) & 1][tid] = 0u;   // order o - 1's sum has been read by everyone
             u64 side;
             v3_pick_level(sh.lvl[1], F, &pend_po, &pend_method, &side, true);
             pend_side = side; pend_shift = shift; pend_narrow = narrow;
-            const u32 kL = sh.kheapL[o & 1][(1u << pend_po) - 1u + (pF >> (F - pend_po))];
-            const u32 bL = __reduce_add_sync(0xFFFFFFFFu, v3_stored_bits(resid, base, S, kL, tid == 0 ? o : 0u));
+            const u32 bL = __reduce_add_sync(0xFFFFFFFFu, run_bits(sh.kheapL[o & 1], pend_po, false, o));
             if (lane == 0) { atomicAdd(&sh.bitsL[o & 1][0], bL & 0xFFFFu); atomicAdd(&sh.bitsL[o & 1][1], bL >> 16); }
         }
         __syncthreads();
@@ -770,16 +813,16 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3Shared& sh, u
 // The grid is normally one CTA per unit; any smaller grid walks the units with the grid's stride
 // (measured: a persistent single wave keeps the CTAs of an SM in the same phase of the unit, which
 // overlaps their load and search phases worse than staggered CTAs do).
-template <int MINB, bool EXH, int SC>
-__global__ void __launch_bounds__(MINB >= 5 ? 128 : MINB >= 3 ? 256 : 512, MINB)
+template <int MINB, bool EXH, int SC, int SUB = 1>
+__global__ void __launch_bounds__(MINB >= 4 ? 128 : MINB >= 3 ? 256 : 512, MINB)
 k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S, u32 F,
              u32 n_units, const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
              b200flac_plan* __restrict__ plans, uint8_t* __restrict__ rice_out)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ V3Shared sh;
+    __shared__ V3SharedT<(SUB == 2 ? 8 : V3_MAX_F)> sh;
     for (u32 unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        v3_unit<EXH, SC>(dyn_smem, sh, unit, pcm, fd, P, S, F, heads, coefs, plans, rice_out);
+        v3_unit<EXH, SC, SUB>(dyn_smem, sh, unit, pcm, fd, P, S, F, heads, coefs, plans, rice_out);
         __syncthreads();        // shared memory is reused by the next unit
     }
 }

@@ -198,7 +198,7 @@ __device__ __forceinline__ u32 p3_lpc_inplace(int* __restrict__ buf, u32 base, u
             if (WIDE) {
                 long long acc = 0;
 #pragma unroll
-                for (int t = 0; t < OG; t++) acc += (long long)q[t] * (long long)w[OG + j - 1 - t];
+                for (int t = 0; t < OG; t++) acc = mad_wide(q[t], w[OG + j - 1 - t], acc);
                 pred = (int)(acc >> shift);
             } else {
                 int acc = 0;

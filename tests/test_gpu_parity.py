@@ -441,6 +441,16 @@ V3_GRID = [
                                       exhaustive_model_search=True)),
     # partition order 0 only
     (44100, 2, 16, 4096 * 2 + 77, dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=0, adaptive_mid_side=True)),
+    # partition order 8 (a finest partition is half a thread run: the SUB = 2 instantiations), with and without
+    # the exhaustive search, 16 and 24 bits, BASELINE config 3's options
+    (44100, 2, 16, 4096 * 4 + 321, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=8, mid_side=True)),
+    (44100, 2, 16, 4096 * 4 + 321, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=8, mid_side=True,
+                                       exhaustive_model_search=True)),
+    (96000, 2, 24, 4096 * 4 + 99, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=8, mid_side=True,
+                                      exhaustive_model_search=True)),
+    (96000, 1, 24, 4096 * 3 + 5, dict(block_size=4096, max_lpc_order=16, max_residual_partition_order=8)),
+    (48000, 6, 16, 4096 * 2 + 1000, dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=8,
+                                        exhaustive_model_search=True)),
 ]
 
 
@@ -475,6 +485,9 @@ def _special_signal(bps, n_blocks, block):
     (16, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, adaptive_mid_side=True)),
     (16, dict(block_size=4096, max_lpc_order=8, max_residual_partition_order=5, mid_side=True)),
     (24, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, mid_side=True)),
+    (16, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=8, mid_side=True)),
+    (16, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=8, adaptive_mid_side=True, exhaustive_model_search=True)),
+    (24, dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=8, mid_side=True, exhaustive_model_search=True)),
 ])
 def test_v3_special_blocks(bps, opts, tmp_path, built):
     block = opts["block_size"]
@@ -502,10 +515,10 @@ def _with_env(env, fn):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("case", [0, 1, 3])
+@pytest.mark.parametrize("case", [0, 1, 3, 4, 5])
 def test_kernel_generations_agree(case, tmp_path, built):
     """the v3 kernels, the v2 kernels and the generic kernels write the same file"""
-    rate, ch, bps, n, o = (GRID[1], V3_GRID[1], V3_GRID[3], V3_GRID[0])[case]
+    rate, ch, bps, n, o = (GRID[1], V3_GRID[1], V3_GRID[3], V3_GRID[0], V3_GRID[12], V3_GRID[13])[case]
     pcm = helpers.synth_pcm(99 + case, ch, bps, n)
     opts = helpers.options(**o)
     a = _encode_b200(tmp_path, pcm, rate, ch, bps, opts, "a.flac")
