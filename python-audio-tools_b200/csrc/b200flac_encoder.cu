@@ -491,7 +491,8 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
             }
         }
         if (enc->v3) {
-            const bool s32 = enc->v3_NT <= 128 && enc->v3_S == 32;   // samples per thread known at compile time
+            // samples per thread known at compile time (the exhaustive instantiation also assumes four warps)
+            const bool s32 = enc->v3_S == 32 && (P.exhaustive ? enc->v3_NT == 128 : enc->v3_NT <= 128);
 #define V3_ATTR(MINB_, EXH_, SC_) cudaFuncSetAttribute(k_analyze_v3<MINB_, EXH_, SC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
             if (enc->v3_sub == 2)
                 e = P.exhaustive ? cudaFuncSetAttribute(k_analyze_v3<4, true, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
@@ -951,7 +952,7 @@ static void stage_analyze(b200flac_encoder* enc, const ChunkView& v, cudaStream_
             if (P.exhaustive) k_analyze_v3<4, true, 32, 2><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice);
             else k_analyze_v3<4, false, 32, 2><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice);
         }
-        else if (enc->v3_NT <= 128 && enc->v3_S == 32) { if (P.exhaustive) V3_LAUNCH(5, true, 32); else V3_LAUNCH(5, false, 32); }
+        else if (enc->v3_S == 32 && (P.exhaustive ? enc->v3_NT == 128 : enc->v3_NT <= 128)) { if (P.exhaustive) V3_LAUNCH(5, true, 32); else V3_LAUNCH(5, false, 32); }
         else if (enc->v3_NT <= 128) { if (P.exhaustive) V3_LAUNCH(5, true, 0); else V3_LAUNCH(5, false, 0); }
         else if (enc->v3_NT <= 256) { if (P.exhaustive) V3_LAUNCH(3, true, 0); else V3_LAUNCH(3, false, 0); }
         else { if (P.exhaustive) V3_LAUNCH(1, true, 0); else V3_LAUNCH(1, false, 0); }

@@ -212,6 +212,127 @@ __device__ __forceinline__ void v3_pick_level(const V3Level* lvl, u32 F, u32* po
     *side_bits = 6ull + (u64)(1u << po) * (maxk > 14 ? 5ull : 4ull) + (u64)(fin ? h0->cnt + h1->cnt : lvl[po].cnt);
 }
 
+// ---- exhaustive search, 128 threads x 32 samples (n = 4096): the Rice search of one LPC order straight from the
+// threads' run sums, which never leave the registers.  A warp's 32 runs are 1/4 of the block, so every partition of
+// orders 2 and up lies inside one warp: each warp evaluates the nodes under its own runs -- order 8 (two per thread,
+// SUB = 2), order 7 (one per thread), orders 6..2 (16 + 8 + 4 + 2 + 1 = 31 nodes, one per lane, from a warp prefix
+// sum) -- with no barrier before it, and leaves per-level totals for v3_pick_own, which adds the four warps up and
+// evaluates the three nodes of orders 1 and 0 after the order's single barrier.
+#define V3_OWN_LEVELS 7                          // per-warp totals of orders 2..8
+template <int SUB>
+__device__ __forceinline__ void v3_search_own(u64 s0, u64 s1, u32 order, u32 F, u32 n, u32 max_rice,
+                                              uint8_t* __restrict__ kheap, V3Level* __restrict__ part, u64* __restrict__ wsum)
+{
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 warm = tid == 0 ? order : 0u;
+    const u64 r = SUB == 2 ? s0 + s1 : s0;
+    if (SUB == 2 && F >= 8) {
+        u64 est = 0; u32 cnt = 0, mk = 0;
+#pragma unroll 1
+        for (u32 h = 0; h < 2; h++) {
+            const u32 pl = (n >> 8) - (h ? 0u : warm);
+            u32 k;
+            est += partition_estimate_fast(pl, h ? s1 : s0, max_rice, &k);
+            kheap[255u + 2u * tid + h] = (uint8_t)k;
+            cnt += (1u + k) * pl; mk = max(mk, k);
+        }
+        const u64 tot = v3_warp_sum_u64(est);
+        const u32 cs = __reduce_add_sync(0xFFFFFFFFu, cnt), km = __reduce_max_sync(0xFFFFFFFFu, mk);
+        if (lane == 0) { part[6].tot = tot; part[6].cnt = cs; part[6].maxk = km; }
+    }
+    if (F >= 7) {
+        const u32 pl = (n >> 7) - warm;
+        u32 k;
+        const u64 est = partition_estimate_fast(pl, r, max_rice, &k);
+        kheap[127u + tid] = (uint8_t)k;
+        const u64 tot = v3_warp_sum_u64(est);
+        const u32 cs = __reduce_add_sync(0xFFFFFFFFu, (1u + k) * pl), km = __reduce_max_sync(0xFFFFFFFFu, k);
+        if (lane == 0) { part[5].tot = tot; part[5].cnt = cs; part[5].maxk = km; }
+    }
+    // inclusive prefix sums of the warp's run sums
+    u64 inc = r;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (u32)o) inc += t;
+    }
+    if (lane == 31) *wsum = inc;
+    // lane j >= 1: node j of the warp's tree -- local level l = floor(log2 j) (order l + 2), w = 32 >> l runs wide
+    {
+        const u32 l = 31u - (u32)__clz((int)(lane | 1u));
+        const u32 idx = lane - (1u << l), w = 32u >> l;
+        const u64 hi = __shfl_sync(0xFFFFFFFFu, inc, (idx + 1u) * w - 1u);
+        const u64 lo = __shfl_sync(0xFFFFFFFFu, inc, (idx * w - 1u) & 31u);
+        const bool act = lane >= 1 && l + 2u <= F;
+        u32 k = 0, cnt = 0;
+        u64 est = 0;
+        if (act) {
+            const u32 p = (warp << l) + idx;
+            const u32 pl = (n >> (l + 2u)) - (p == 0 ? order : 0u);
+            est = partition_estimate_fast(pl, hi - (idx ? lo : 0ull), max_rice, &k);
+            kheap[(4u << l) - 1u + p] = (uint8_t)k;
+            cnt = (1u + k) * pl;
+        }
+        // level l occupies lanes 2^l .. 2^(l+1)-1: sums within aligned groups of 2^l lanes
+        const u32 gs = 1u << l;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const u64 te = __shfl_xor_sync(0xFFFFFFFFu, est, o);
+            const u32 tc = __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+            const u32 tk = __shfl_xor_sync(0xFFFFFFFFu, k, o);
+            if ((u32)o < gs) { est += te; cnt += tc; k = max(k, tk); }
+        }
+        if (act && lane == gs) { part[l].tot = est; part[l].cnt = cnt; part[l].maxk = k; }
+    }
+}
+
+// after the barrier, every warp: totals of orders 2..F from the four warps' parts (lane = order), the three nodes of
+// orders 1 and 0 from the warps' sums (lanes 29..31, moved to lanes 0 and 1), then the first strict minimum of the
+// estimates (flac.c:1365-1400).  All warps write the same three Rice parameters.
+__device__ __forceinline__ void v3_pick_own(const V3Level* __restrict__ parts, const u64* __restrict__ wsum, u32 order,
+                                            u32 F, u32 n, u32 max_rice, uint8_t* __restrict__ kheap,
+                                            u32* po_out, u32* method_out, u64* side_bits)
+{
+    const u32 lane = threadIdx.x & 31;
+    u64 tot = ~0ull;
+    u32 cnt = 0, mk = 0;
+    if (lane >= 2 && lane <= F) {
+        tot = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const V3Level v = parts[w * V3_OWN_LEVELS + (lane - 2)];
+            tot += v.tot; cnt += v.cnt; mk = max(mk, v.maxk);
+        }
+    }
+    u64 te = 0;
+    u32 tc = 0, tk = 0;
+    if (lane >= 29) {
+        const u64 a = wsum[0] + wsum[1], b = wsum[2] + wsum[3];
+        const u32 L = lane == 29 ? 0u : 1u;
+        const u32 pl = (n >> L) - (lane == 31 ? 0u : order);
+        te = partition_estimate_fast(pl, lane == 29 ? a + b : lane == 30 ? a : b, max_rice, &tk);
+        kheap[lane - 29u] = (uint8_t)tk;
+        tc = (1u + tk) * pl;
+    }
+    {
+        const u64 e0 = __shfl_sync(0xFFFFFFFFu, te, 29), e1 = __shfl_sync(0xFFFFFFFFu, te, 30), e2 = __shfl_sync(0xFFFFFFFFu, te, 31);
+        const u32 c0 = __shfl_sync(0xFFFFFFFFu, tc, 29), c1 = __shfl_sync(0xFFFFFFFFu, tc, 30), c2 = __shfl_sync(0xFFFFFFFFu, tc, 31);
+        const u32 k0 = __shfl_sync(0xFFFFFFFFu, tk, 29), k1 = __shfl_sync(0xFFFFFFFFu, tk, 30), k2 = __shfl_sync(0xFFFFFFFFu, tk, 31);
+        if (lane == 0) { tot = e0; cnt = c0; mk = k0; }
+        if (lane == 1 && F >= 1) { tot = e1 + e2; cnt = c1 + c2; mk = max(k1, k2); }
+    }
+    __syncwarp();
+    const u32 hi = (u32)(tot >> 32), lo = (u32)tot;
+    const u32 mhi = __reduce_min_sync(0xFFFFFFFFu, hi);
+    const u32 mlo = __reduce_min_sync(0xFFFFFFFFu, hi == mhi ? lo : 0xFFFFFFFFu);
+    const u32 po = __reduce_min_sync(0xFFFFFFFFu, (hi == mhi && lo == mlo) ? lane : 32u);
+    const u32 maxk = __shfl_sync(0xFFFFFFFFu, mk, po);
+    const u32 c = __shfl_sync(0xFFFFFFFFu, cnt, po);
+    *po_out = po;
+    *method_out = maxk > 14 ? 1u : 0u;
+    *side_bits = 6ull + (u64)(1u << po) * (maxk > 14 ? 5ull : 4ull) + (u64)c;
+}
+
 // predictor history of a FIXED pass: differences of the four samples before `base` (zeros for run 0)
 __device__ __forceinline__ void v3_fixed_history(const int* __restrict__ samp, u32 base, u32& prev, u32& p1, u32& p2, u32& p3)
 {
@@ -624,10 +745,11 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
     const u32 precision = sh.head.precision;
     bool lpc_narrow = false;
     int lpc_shift = 0;
-    // residual of order o with the coefficients staged in qs; leaves the thread's run sum(s) in runsL
-    auto lpc_pass = [&](u32 o, int shift, bool narrow, const short* qs) {
+    // residual of order o with the coefficients staged in qs; s0 (and s1, SUB = 2) get the thread's run sum(s)
+    auto lpc_pass = [&](u32 o, int shift, bool narrow, const short* qs, u64& s0, u64& s1) {
         u64 run;
-        u64* h0 = runsL + SUB * tid;
+        u64 first = 0;
+        u64* h0 = &first;
         // (no 8-tap variant: a second hot copy of the residual loop costs more in instruction fetch than
         // the four extra multiply-adds of a padded low order cost on the otherwise idle FMA pipe)
         // (the exhaustive search walks every order, so there the 8-tap copy pays for itself)
@@ -637,18 +759,21 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
                                        : v3_lpc_residual<12, true, SUB>(samp, resid, base, S, qs, shift, h0);
         else run = narrow ? v3_lpc_residual<32, false, SUB>(samp, resid, base, S, qs, shift, h0)
                           : v3_lpc_residual<32, true, SUB>(samp, resid, base, S, qs, shift, h0);
-        h0[SUB - 1] = run;
+        if (SUB == 2) { s0 = first; s1 = run; } else { s0 = run; s1 = 0; }
         if (tid == 0) {
             u64 warm = 0;
 #pragma unroll 1
             for (u32 i = 0; i < o; i++) warm += (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions (o <= 32 / SUB)
-            runsL[0] -= warm;
+            s0 -= warm;
         }
     };
+    auto store_runs = [&](u64 s0, u64 s1) { runsL[SUB * tid] = s0; if (SUB == 2) runsL[2 * tid + 1] = s1; };
     if (!EXH) {
         lpc_shift = sh.head.shift[lpc_order - 1];
         lpc_narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
-        lpc_pass(lpc_order, lpc_shift, lpc_narrow, sh.q);
+        u64 s0, s1;
+        lpc_pass(lpc_order, lpc_shift, lpc_narrow, sh.q, s0, s1);
+        store_runs(s0, s1);
     }
     __syncthreads();                                                             // (2)
 
@@ -746,6 +871,59 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
                 for (u32 p = tid; p < (1u << pend_po); p += nt) sh.kbest[p] = sh.kheapL[o & 1][koff + p];
             }
         };
+        if constexpr (SC == 32) {
+            // 128 threads x 32 samples: ONE barrier per order.  The run sums stay in registers and every warp searches the
+            // partitions under its own runs before the barrier (v3_search_own); after it every warp adds the four
+            // warps' level totals up, picks the order (v3_pick_own) and counts the exact bits of its runs.  The residual
+            // buffer is only ever read and written by the thread that owns the run, so the next pass may start at once.
+            // Rice parameters and bit sums of three orders are in flight (o mod 3): order o's are written before and
+            // after barrier o, read by decide(o) after barrier o + 1, while order o + 1's search is already writing.
+            V3Level* parts = (V3Level*)runsL;                        // [2][4][V3_OWN_LEVELS], by order parity
+            u64* wsum = (u64*)(parts + 2 * 4 * V3_OWN_LEVELS);       // [2][4]
+            auto kbuf = [&](u32 o) -> uint8_t* { const u32 m = o % 3u; return m == 0 ? sh.kheapL[0] : m == 1 ? sh.kheapL[1] : sh.kheap[1]; };
+            auto bbuf = [&](u32 o) -> u32* { const u32 m = o % 3u; return m == 0 ? sh.bitsL[0] : m == 1 ? sh.bitsL[1] : sh.bits16[1]; };
+            auto decide3 = [&](u32 o) {
+                const u32* b = bbuf(o);
+                const u64 bits = hdr_bits + (u64)o * sub_bps + 4 + 5 + (u64)o * precision + pend_side + (u64)b[0] + ((u64)b[1] << 16);
+                if (!have || (u32)bits < best32) {
+                    have = true;
+                    best32 = (u32)bits;
+                    lpc_bits = bits; lpc_order = o; lpc_shift = pend_shift; lpc_narrow = pend_narrow;
+                    poL = pend_po; methodL = pend_method;
+                    const u32 koff = (1u << pend_po) - 1u;
+                    const uint8_t* kb = kbuf(o);
+                    for (u32 p = tid; p < (1u << pend_po); p += nt) sh.kbest[p] = kb[koff + p];
+                }
+            };
+            if (tid < 4) sh.bitsL[tid >> 1][tid & 1] = 0u;
+            if (tid < 2) sh.bits16[1][tid] = 0u;
+            if (warp == nw - 1) stage(1);
+            __syncthreads();
+#pragma unroll 1
+            for (u32 o = 1; o <= L; o++) {
+                const int shift = sh.head.shift[o - 1];
+                const bool narrow = ((u64)sh.lpc_narrow2[o & 1] << (sub_bps - 1)) < (1ull << 31);
+                u64 s0, s1;
+                lpc_pass(o, shift, narrow, sh.q2[o & 1], s0, s1);
+                if (warp == nw - 1 && o < L) stage(o + 1);      // (its buffer was last read by order o - 1's pass)
+                uint8_t* kb = kbuf(o);
+                v3_search_own<SUB>(s0, s1, o, F, n, P.max_rice, kb, parts + ((o & 1u) * 4u + warp) * V3_OWN_LEVELS,
+                                   wsum + (o & 1u) * 4u + warp);
+                __syncthreads();
+                if (o > 1) decide3(o - 1);
+                if (tid < 2) bbuf(o + 1)[tid] = 0u;             // last read by decide(o - 2), before this barrier
+                u64 side;
+                v3_pick_own(parts + (o & 1u) * 4u * V3_OWN_LEVELS, wsum + (o & 1u) * 4u, o, F, n, P.max_rice, kb,
+                            &pend_po, &pend_method, &side);
+                pend_side = side; pend_shift = shift; pend_narrow = narrow;
+                const u32 bL = __reduce_add_sync(0xFFFFFFFFu, run_bits(kb, pend_po, false, o));
+                u32* bb = bbuf(o);
+                if (lane == 0) { atomicAdd(&bb[0], bL & 0xFFFFu); atomicAdd(&bb[1], bL >> 16); }
+            }
+            __syncthreads();
+            decide3(L);
+            __syncthreads();
+        } else {
         if (tid < 4) sh.bitsL[tid >> 1][tid & 1] = 0u;
         if (warp == nw - 1) stage(1);
         __syncthreads();
@@ -753,7 +931,9 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
         for (u32 o = 1; o <= L; o++) {
             const int shift = sh.head.shift[o - 1];
             const bool narrow = ((u64)sh.lpc_narrow2[o & 1] << (sub_bps - 1)) < (1ull << 31);
-            lpc_pass(o, shift, narrow, sh.q2[o & 1]);
+            u64 s0, s1;
+            lpc_pass(o, shift, narrow, sh.q2[o & 1], s0, s1);
+            store_runs(s0, s1);
             if (warp == nw - 1 && o < L) stage(o + 1);      // (its buffer was last read by order o - 1's pass)
             __syncthreads();
             if (o > 1) decide(o - 1);
@@ -772,6 +952,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
         __syncthreads();
         decide(L);
         __syncthreads();
+        }
     }
 
     // ---- choice, flac.c:727-809 (every subframe type enabled) ----
