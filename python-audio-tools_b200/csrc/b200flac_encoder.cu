@@ -477,14 +477,14 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
                 // partition order 8: 128 threads x 32 samples, a finest partition is half a thread run (run sums per half)
                 if (bs == 32u * 128u && P.max_lpc_order <= 16) {
                     enc->v3 = true; enc->v3_S = 32; enc->v3_F = F; enc->v3_NT = 128; enc->v3_sub = 2;
-                    enc->v3_smem = v3_smem_bytes(bs, 128, 2);
+                    enc->v3_smem = v3_smem_bytes(bs, 128, 2, P.exhaustive != 0);
                 }
             } else
             for (u32 S3 = 32; S3 >= 8; S3 -= 8) {
                 if (bs % S3 || (bs >> F) % S3) continue;
                 const u32 nt = bs / S3;
                 if (nt % 32 || nt < 32 || nt > 512) continue;
-                const size_t sm = v3_smem_bytes(bs, nt);
+                const size_t sm = v3_smem_bytes(bs, nt, 1, P.exhaustive && S3 == 32 && nt == 128);
                 if (sm > 200 * 1024) continue;
                 enc->v3 = true; enc->v3_S = S3; enc->v3_F = F; enc->v3_NT = nt; enc->v3_smem = sm;
                 break;
@@ -495,7 +495,7 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
             const bool s32 = enc->v3_S == 32 && (P.exhaustive ? enc->v3_NT == 128 : enc->v3_NT <= 128);
 #define V3_ATTR(MINB_, EXH_, SC_) cudaFuncSetAttribute(k_analyze_v3<MINB_, EXH_, SC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
             if (enc->v3_sub == 2)
-                e = P.exhaustive ? cudaFuncSetAttribute(k_analyze_v3<4, true, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
+                e = P.exhaustive ? cudaFuncSetAttribute(k_analyze_v3<5, true, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
                                  : cudaFuncSetAttribute(k_analyze_v3<4, false, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
             else if (P.exhaustive) e = s32 ? V3_ATTR(5, true, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, true, 0) : enc->v3_NT <= 256 ? V3_ATTR(3, true, 0) : V3_ATTR(1, true, 0);
             else e = s32 ? V3_ATTR(5, false, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, false, 0) : enc->v3_NT <= 256 ? V3_ATTR(3, false, 0) : V3_ATTR(1, false, 0);
@@ -949,7 +949,7 @@ static void stage_analyze(b200flac_encoder* enc, const ChunkView& v, cudaStream_
         if (g3 > v.U || g3 == 0) g3 = v.U;
 #define V3_LAUNCH(MINB_, EXH_, SC_) k_analyze_v3<MINB_, EXH_, SC_><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice)
         if (enc->v3_sub == 2) {
-            if (P.exhaustive) k_analyze_v3<4, true, 32, 2><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice);
+            if (P.exhaustive) k_analyze_v3<5, true, 32, 2><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice);
             else k_analyze_v3<4, false, 32, 2><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice);
         }
         else if (enc->v3_S == 32 && (P.exhaustive ? enc->v3_NT == 128 : enc->v3_NT <= 128)) { if (P.exhaustive) V3_LAUNCH(5, true, 32); else V3_LAUNCH(5, false, 32); }

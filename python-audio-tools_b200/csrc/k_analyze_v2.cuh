@@ -32,11 +32,13 @@ __device__ __forceinline__ u64 partition_estimate_fast(u32 plength, u64 S_, u32 
     } else if (plength == 0 || S_ >= (1ull << 31)) {
         return partition_estimate(plength, S_, max_rice, k_out);
     } else {
-        // smallest k with (plength << k) >= S_
-        int kc = (64 - __clzll((long long)S_)) - (32 - __clz((int)plength)) - 1;
-        if (kc < 0) kc = 0;
-        while (((u64)plength << kc) < S_) kc++;
-        k = (u32)kc < max_rice ? (u32)kc : max_rice;
+        // smallest k with (plength << k) >= S_: with a, b the bit lengths of S_ and plength (a >= b here),
+        // plength << (a - b - 1) < 2^(a-1) <= S_ and plength << (a - b + 1) >= 2^a > S_, so it is a - b or a - b + 1;
+        // everything fits 32 bits (plength << (a - b) < 2^a <= 2^31)
+        const u32 s32 = (u32)S_;
+        u32 kc = (u32)(__clz((int)plength) - __clz((int)s32));
+        if ((plength << kc) < s32) kc++;
+        k = kc < max_rice ? kc : max_rice;
     }
     u64 est;
     if (k > 0) est = 4ull + (S_ >> (k - 1)) + (u64)(u32)((1u + k) * plength) - (u64)(plength / 2);

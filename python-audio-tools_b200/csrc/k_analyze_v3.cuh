@@ -69,11 +69,12 @@ struct V3SharedT {
 };
 
 // host and device agree on the dynamic shared memory through this
-// (sub: run sums kept per thread run, 1 or 2)
-__host__ __device__ inline size_t v3_smem_bytes(u32 n, u32 NT, u32 sub = 1)
+// (sub: run sums kept per thread run, 1 or 2; own: the exhaustive 128 x 32 instantiations, whose run sums stay in
+// registers -- they only need 1 KB for the warps' level totals)
+__host__ __device__ inline size_t v3_smem_bytes(u32 n, u32 NT, u32 sub = 1, bool own = false)
 {
     const size_t padn = (size_t)V3_SK(n) + 8;
-    return 2 * padn * 4 + (size_t)6 * NT * sub * 8 + 32;
+    return 2 * padn * 4 + (own ? (size_t)1024 : (size_t)6 * NT * sub * 8) + 32;
 }
 
 __device__ __forceinline__ u64 v3_warp_sum_u64(u64 v)
@@ -601,8 +602,11 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
     int* samp = (int*)dyn_smem;
     int* resid = samp + padn;
     const u32 R = nt * SUB;                     // run sums per row: entry SUB * tid + h is half h of thread tid's run
-    u64* runsF = (u64*)(resid + padn);          // [5][R]
-    u64* runsL = runsF + 5 * (size_t)R;         // [R]
+    constexpr bool OWN = EXH && SC == 32;       // run sums in registers, searched by their own warps (v3_search_own)
+    u64* runsF = (u64*)(resid + padn);          // [5][R]   (not OWN)
+    u64* runsL = OWN ? runsF : runsF + 5 * (size_t)R;         // [R]; OWN: 1 KB of level totals
+    V3Level* parts = (V3Level*)runsL;                        // OWN: [2][4][V3_OWN_LEVELS], by order parity
+    u64* wsum = (u64*)(parts + 2 * 4 * V3_OWN_LEVELS);       // OWN: [2][4]
 
     // ---- LPC model of the unit (last warp; overlaps the PCM load of the others) ----
     const short* mycoef = coefs + (size_t)unit * P.model_stride;
@@ -669,6 +673,27 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
                     orv |= (u32)v; diff |= (u32)(v ^ first);
                 }
             }
+        } else if (P.stereo && P.bytes_ps == 3 && (n & 7u) == 0 && (((uintptr_t)(pcm + d.pcm_off * 6)) & 15) == 0) {
+            // 24-bit stereo: eight PCM frames are 48 bytes, three 128-bit loads; one PRMT per sample picks its three
+            // bytes and replicates the sign of the top one.  (The generic loop below is one dependent load per
+            // sample: a tenth of the kernel's time at 24 bits.)
+            const uint4* s4 = (const uint4*)(pcm + d.pcm_off * 6);
+#pragma unroll 2
+            for (u32 g = tid; g < (n >> 3); g += nt) {
+                const uint4 a = __ldg(s4 + 3 * g), b = __ldg(s4 + 3 * g + 1), c = __ldg(s4 + 3 * g + 2);
+                const u32 w[13] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, 0u};
+                int v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int oL = 6 * j, oR = 6 * j + 3;
+                    const int L = s24_from_words(w[oL >> 2], w[(oL >> 2) + 1], oL & 3);
+                    const int R = s24_from_words(w[oR >> 2], w[(oR >> 2) + 1], oR & 3);
+                    v[j] = cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
+                    orv |= (u32)v[j]; diff |= (u32)(v[j] ^ first);
+                }
+                *(int4*)(samp + V3_SK(8 * g)) = make_int4(v[0], v[1], v[2], v[3]);
+                *(int4*)(samp + V3_SK(8 * g) + 4) = make_int4(v[4], v[5], v[6], v[7]);
+            }
         } else {
             for (u32 i = tid; i < n; i += nt) {
                 const int v = ld_candidate(pcm, d.pcm_off + i, cand, P);
@@ -703,8 +728,38 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
     const u32 hdr_bits = 8 + wasted;
 
     // ---- pass A: FIXED sums of all orders + LPC residual, run sums to shared memory ----
+    u64 ownE[5] = {0, 0, 0, 0, 0}, ownH[5] = {0, 0, 0, 0, 0};   // OWN: FIXED sums of the run (second half, SUB = 2) / first half
     {
         u64* mine = runsF + SUB * tid;             // this thread's (first) entry of order 0's row
+        if constexpr (OWN) {
+            if (sub_bps <= 23) {
+                u32 e[5];
+                v3_fixed_sums<u32, SUB>(samp, base, S, e, ownH, 1);
+#pragma unroll
+                for (int k = 0; k < 5; k++) ownE[k] = (u64)e[k];
+            } else {
+                v3_fixed_sums<u64, SUB>(samp, base, S, ownE, ownH, 1);
+            }
+            if (tid == 0) {
+                u32 g[5];
+                v3_fixed_head(samp, g, sh.corr);
+#pragma unroll
+                for (int k = 0; k < 5; k++) { if (SUB == 2) ownH[k] -= (u64)g[k]; else ownE[k] -= (u64)g[k]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const u64 mysum = ownE[k] + (SUB == 2 ? ownH[k] : 0ull);
+                if (sub_bps <= 23) {
+                    const u32 ws = __reduce_add_sync(0xFFFFFFFFu, (u32)mysum);
+                    if (lane == 0) { atomicAdd(&sh.totF16[k][0], ws & 0xFFFFu); atomicAdd(&sh.totF16[k][1], ws >> 16); }
+                } else {
+                    u64 ws = mysum;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) ws += __shfl_xor_sync(0xFFFFFFFFu, ws, o);
+                    if (lane == 0) atomicAdd(&sh.totF[k], ws);
+                }
+            }
+        } else {
         if (sub_bps <= 23) {
             u32 e[5];
             v3_fixed_sums<u32, SUB>(samp, base, S, e, mine, R);
@@ -739,6 +794,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
                 for (int o = 16; o; o >>= 1) ws += __shfl_xor_sync(0xFFFFFFFFu, ws, o);
                 if (lane == 0) atomicAdd(&sh.totF[k], ws);
             }
+        }
         }
     }
     u32 lpc_order = sh.head.best_order;
@@ -789,7 +845,15 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
     }
     // ---- the two Rice searches as four warp tasks (model x part, see v3_levels); the tasks rotate
     // over the warps with the unit so that no scheduler always gets the extra work ----
-    {
+    if constexpr (OWN) {
+        auto sel5 = [&](const u64 (&a)[5]) -> u64 {
+            return fixed_order == 0 ? a[0] : fixed_order == 1 ? a[1] : fixed_order == 2 ? a[2] : fixed_order == 3 ? a[3] : a[4];
+        };
+        u64 s0 = SUB == 2 ? sel5(ownH) : sel5(ownE);
+        const u64 s1 = SUB == 2 ? sel5(ownE) : 0ull;
+        if (tid == 0) s0 += sh.corr[fixed_order];     // |r[i]| of order <= i < 4, which the partition sums do contain
+        v3_search_own<SUB>(s0, s1, fixed_order, F, n, P.max_rice, sh.kheap[0], parts + warp * V3_OWN_LEVELS, wsum + warp);
+    } else {
         const u32 role = (nw & (nw - 1)) == 0 ? ((warp - unit) & (nw - 1)) : (warp + nw - unit % nw) % nw;
         for (u32 task = role; task < (EXH ? 2u : 4u); task += nw) {
             // prefix sums go to the run-sum rows of two FIXED orders that lost; one call site for both models
@@ -821,7 +885,8 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
     };
     u32 poF, poL = 0, methodF, methodL = 0;
     u64 sideF, sideL = 0;
-    v3_pick_level(sh.lvl[0], F, &poF, &methodF, &sideF);
+    if constexpr (OWN) v3_pick_own(parts, wsum, fixed_order, F, n, P.max_rice, sh.kheap[0], &poF, &methodF, &sideF);
+    else v3_pick_level(sh.lvl[0], F, &poF, &methodF, &sideF);
     if (!EXH) v3_pick_level(sh.lvl[1], F, &poL, &methodL, &sideL);
     {
         // a warp's sum stays far below 2^32 (each run's is bounded by ~2 * partition length + 32 * 2^18)
@@ -878,8 +943,6 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
             // buffer is only ever read and written by the thread that owns the run, so the next pass may start at once.
             // Rice parameters and bit sums of three orders are in flight (o mod 3): order o's are written before and
             // after barrier o, read by decide(o) after barrier o + 1, while order o + 1's search is already writing.
-            V3Level* parts = (V3Level*)runsL;                        // [2][4][V3_OWN_LEVELS], by order parity
-            u64* wsum = (u64*)(parts + 2 * 4 * V3_OWN_LEVELS);       // [2][4]
             auto kbuf = [&](u32 o) -> uint8_t* { const u32 m = o % 3u; return m == 0 ? sh.kheapL[0] : m == 1 ? sh.kheapL[1] : sh.kheap[1]; };
             auto bbuf = [&](u32 o) -> u32* { const u32 m = o % 3u; return m == 0 ? sh.bitsL[0] : m == 1 ? sh.bitsL[1] : sh.bits16[1]; };
             auto decide3 = [&](u32 o) {
