@@ -215,12 +215,12 @@ def run_reference_arm(args, rank, world, emit):
 # ----------------------------------------------------------------------------------------------
 OTHER_CONFIGS = [
     # name, sample rate, channels, bits, seconds per GPU per step, options
-    ("config3 96 kHz/24-bit stereo, block 4096, lpc 12, -m -e (exhaustive), max partition order 8", 96000, 2, 24, 300.0,
+    ("config3 96 kHz/24-bit stereo, block 4096, lpc 12, -m -e (exhaustive), max partition order 8", 96000, 2, 24, 1800.0,
      dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=8, mid_side=True, exhaustive_model_search=True)),
-    ("config4 96 kHz/24-bit 5.1 (6 ch), block 4608, lpc 12, max partition order 6", 96000, 6, 24, 120.0,
+    ("config4 96 kHz/24-bit 5.1 (6 ch), block 4608, lpc 12, max partition order 6", 96000, 6, 24, 600.0,
      dict(block_size=4608, max_lpc_order=12, max_residual_partition_order=6)),
     ("level8 44.1 kHz/16-bit stereo, block 4096, lpc 12, -m -e, max partition order 6 (FlacAudio.from_pcm default, config5 setting)",
-     44100, 2, 16, 600.0,
+     44100, 2, 16, 3600.0,
      dict(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, mid_side=True, exhaustive_model_search=True)),
 ]
 

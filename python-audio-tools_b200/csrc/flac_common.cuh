@@ -153,6 +153,13 @@ __device__ __forceinline__ u32 block_exscan_u32(u32 v, u64* red, u32* total)
 // residual helpers
 // ---------------------------------------------------------------------------
 // zig-zag fold of flac.c:1424-1428
+// int -> double without the (quarter-rate) I2F.F64: 2^52 + 2^31 + v is exact for any 32-bit v,
+// and so is the subtraction that follows
+__device__ __forceinline__ double int2double_exact(int v)
+{
+    return __dsub_rn(__hiloint2double(0x43300000, (int)((u32)v ^ 0x80000000u)), 4503601774854144.0);
+}
+
 // acc + a * b as a 32 x 32 -> 64-bit multiply-add: ONE instruction (IMAD.WIDE).  Inline PTX on purpose: given
 // (long long)a * (long long)b with both operands live across an unrolled loop, the compiler keeps them sign-extended
 // and emits a 64 x 64-bit multiply per tap (IMAD.WIDE.U32 + 2 IMAD + IADD3 -- measured: 2.9 instructions per tap

@@ -427,7 +427,9 @@ __device__ __forceinline__ void v3_fixed_head(const int* __restrict__ samp, u32 
 // registers; returns the run's sum of |r|.  OG: taps (coefficients zero-padded, exact).
 // WIDE: 64-bit accumulate, otherwise 32-bit (only chosen when the sum provably fits).
 // SUB = 2: the sum of the first half run goes to *half0 when the half ends, the second half's is returned.
-template <int OG, bool WIDE, int SUB>
+#define V3_ACC_I32 0
+#define V3_ACC_I64 1
+template <int OG, int WIDE, int SUB>
 __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int* __restrict__ resid, u32 base, u32 S,
                                                const short* q_sm, int shift, u64* __restrict__ half0)
 {
@@ -466,6 +468,56 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
                 pred = acc >> shift;
             }
             res[j] = (int)((u32)w[OG + j] - (u32)pred);
+        }
+#pragma unroll
+        for (int j = 0; j < V3_CH; j++) run += (u64)(u32)abs(res[j]);
+        *(int4*)(resid + V3_SK(i0)) = make_int4(res[0], res[1], res[2], res[3]);
+        *(int4*)(resid + V3_SK(i0) + 4) = make_int4(res[4], res[5], res[6], res[7]);
+#pragma unroll
+        for (int t = 0; t < OG; t++) w[t] = w[t + V3_CH];
+    }
+    return run;
+}
+
+// The same pass for wide samples (more than 32 bits of sum) in FP64: coefficients of at most 16 bits times samples of
+// at most 26 are exact products, and up to 32 of them add up below 2^53, so the DFMA chain IS the reference's 64-bit
+// integer sum -- one instruction per tap on the otherwise idle FP64 pipe, where the integer form costs two (ptxas
+// splits mad.wide into IMAD.WIDE + 64-bit IADD3: the accumulating form runs at half rate) on the pipe that limits
+// this kernel.  floor(acc / 2^shift) mod 2^32 -- the reference's arithmetic shift and truncating cast -- is one more
+// DFMA: acc * 2^-shift + 1.5 * 2^52, rounded DOWN, has the integer in its low mantissa word.  No I2F/F2I (quarter rate).
+template <int OG, int SUB>
+__device__ __forceinline__ u64 v3_lpc_residual_f64(const int* __restrict__ samp, int* __restrict__ resid, u32 base, u32 S,
+                                                   const short* q_sm, int shift, u64* __restrict__ half0)
+{
+    double q[OG];
+#pragma unroll
+    for (int t = 0; t < OG; t++) q[t] = int2double_exact((int)q_sm[t]);
+    double w[OG + V3_CH];
+#pragma unroll
+    for (int t = 0; t < OG; t += 4) {
+        int4 h = make_int4(0, 0, 0, 0);
+        if (base >= (u32)(OG - t)) h = *(const int4*)(samp + V3_SK(base - (OG - t)));
+        w[t] = int2double_exact(h.x); w[t + 1] = int2double_exact(h.y);
+        w[t + 2] = int2double_exact(h.z); w[t + 3] = int2double_exact(h.w);
+    }
+    const double scale = __hiloint2double((1023 - shift) << 20, 0);      // 2^-shift
+    u64 run = 0;
+    V3_LOOP
+    for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+        if (SUB == 2 && i0 == base + (S >> 1)) { *half0 = run; run = 0; }
+        const int4 va = *(const int4*)(samp + V3_SK(i0));
+        const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
+        const int xs[V3_CH] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int j = 0; j < V3_CH; j++) w[OG + j] = int2double_exact(xs[j]);
+        int res[V3_CH];
+#pragma unroll
+        for (int j = 0; j < V3_CH; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < OG; t++) acc = __fma_rn(q[t], w[OG + j - 1 - t], acc);
+            const int pred = __double2loint(__fma_rd(acc, scale, 6755399441055744.0));
+            res[j] = (int)((u32)xs[j] - (u32)pred);
         }
 #pragma unroll
         for (int j = 0; j < V3_CH; j++) run += (u64)(u32)abs(res[j]);
@@ -809,12 +861,17 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
         // (no 8-tap variant: a second hot copy of the residual loop costs more in instruction fetch than
         // the four extra multiply-adds of a padded low order cost on the otherwise idle FMA pipe)
         // (the exhaustive search walks every order, so there the 8-tap copy pays for itself)
-        if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, false, SUB>(samp, resid, base, S, qs, shift, h0)
-                                        : v3_lpc_residual<8, true, SUB>(samp, resid, base, S, qs, shift, h0);
-        else if (o <= 12) run = narrow ? v3_lpc_residual<12, false, SUB>(samp, resid, base, S, qs, shift, h0)
-                                       : v3_lpc_residual<12, true, SUB>(samp, resid, base, S, qs, shift, h0);
-        else run = narrow ? v3_lpc_residual<32, false, SUB>(samp, resid, base, S, qs, shift, h0)
-                          : v3_lpc_residual<32, true, SUB>(samp, resid, base, S, qs, shift, h0);
+        // wide sums of up to 12 taps go through the FP64 pipe (exact: see v3_lpc_residual_f64); sub_bps <= 26 and
+        // |coefficient| < 2^15 keep every partial sum below 2^45, and shift >= 0
+        const bool f64 = !narrow && sub_bps <= 26 && shift >= 0;
+        if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
+                                 : f64 ? v3_lpc_residual_f64<8, SUB>(samp, resid, base, S, qs, shift, h0)
+                                       : v3_lpc_residual<12, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
+        else if (o <= 12) run = narrow ? v3_lpc_residual<12, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
+                                : f64 ? v3_lpc_residual_f64<12, SUB>(samp, resid, base, S, qs, shift, h0)
+                                      : v3_lpc_residual<12, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
+        else run = narrow ? v3_lpc_residual<32, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
+                          : v3_lpc_residual<32, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
         if (SUB == 2) { s0 = first; s1 = run; } else { s0 = run; s1 = 0; }
         if (tid == 0) {
             u64 warm = 0;

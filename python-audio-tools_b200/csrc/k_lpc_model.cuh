@@ -163,13 +163,6 @@ __host__ __device__ inline LpcGeom lpc_geometry(u32 K, u32 rowbytes, u32 ring)
     return g;
 }
 
-// int -> double without the (quarter-rate) I2F.F64: 2^52 + 2^31 + v is exact for any 32-bit v,
-// and so is the subtraction that follows
-__device__ __forceinline__ double int2double_exact(int v)
-{
-    return __dsub_rn(__hiloint2double(0x43300000, (int)((u32)v ^ 0x80000000u)), 4503601774854144.0);
-}
-
 // candidate signal of a 16-bit stereo pair (flacenc_average_difference, flac.c:1507-1529) as ONE
 // dot product: (cl*L + cr*R) >> sh with (cl, cr, sh) = (1,0,0) left, (0,1,0) right, (1,1,1) average,
 // (1,-1,0) difference; coef packs cl and cr as two signed bytes (IDP.2A.LO.S16.S8).  One code path
