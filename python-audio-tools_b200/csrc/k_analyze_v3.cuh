@@ -469,8 +469,16 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
             }
             res[j] = (int)((u32)w[OG + j] - (u32)pred);
         }
+        if (WIDE == V3_ACC_I32) {
+            // every |residual| is below 2^29 here (see is_narrow): |a - 0| + c is one VABSDIFF
+            u32 cs = 0;
 #pragma unroll
-        for (int j = 0; j < V3_CH; j++) run += (u64)(u32)abs(res[j]);
+            for (int j = 0; j < V3_CH; j++) cs = __sad(res[j], 0, cs);
+            run += cs;
+        } else {
+#pragma unroll
+            for (int j = 0; j < V3_CH; j++) run += (u64)(u32)abs(res[j]);
+        }
         *(int4*)(resid + V3_SK(i0)) = make_int4(res[0], res[1], res[2], res[3]);
         *(int4*)(resid + V3_SK(i0) + 4) = make_int4(res[4], res[5], res[6], res[7]);
 #pragma unroll
@@ -851,6 +859,12 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
     }
     u32 lpc_order = sh.head.best_order;
     const u32 precision = sh.head.precision;
+    // "narrow": the prediction sum fits 32 bits (sum of |coefficient| * 2^(sub_bps - 1) < 2^31) AND every |residual|
+    // stays below 2^29 (|prediction| <= 2^31 >> shift with shift >= 3, |sample| < 2^27), so that eight of them add up
+    // in 32 bits (v3_lpc_residual sums a chunk with VABSDIFF).  Anything else takes the wide paths.
+    auto is_narrow = [&](u32 sum_abs_q, int shift) -> bool {
+        return ((u64)sum_abs_q << (sub_bps - 1)) < (1ull << 31) && shift >= 3 && sub_bps <= 28;
+    };
     bool lpc_narrow = false;
     int lpc_shift = 0;
     // residual of order o with the coefficients staged in qs; s0 (and s1, SUB = 2) get the thread's run sum(s)
@@ -883,7 +897,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
     auto store_runs = [&](u64 s0, u64 s1) { runsL[SUB * tid] = s0; if (SUB == 2) runsL[2 * tid + 1] = s1; };
     if (!EXH) {
         lpc_shift = sh.head.shift[lpc_order - 1];
-        lpc_narrow = ((u64)sh.lpc_narrow << (sub_bps - 1)) < (1ull << 31);
+        lpc_narrow = is_narrow(sh.lpc_narrow, lpc_shift);
         u64 s0, s1;
         lpc_pass(lpc_order, lpc_shift, lpc_narrow, sh.q, s0, s1);
         store_runs(s0, s1);
@@ -1022,7 +1036,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
 #pragma unroll 1
             for (u32 o = 1; o <= L; o++) {
                 const int shift = sh.head.shift[o - 1];
-                const bool narrow = ((u64)sh.lpc_narrow2[o & 1] << (sub_bps - 1)) < (1ull << 31);
+                const bool narrow = is_narrow(sh.lpc_narrow2[o & 1], shift);
                 u64 s0, s1;
                 lpc_pass(o, shift, narrow, sh.q2[o & 1], s0, s1);
                 if (warp == nw - 1 && o < L) stage(o + 1);      // (its buffer was last read by order o - 1's pass)
@@ -1050,7 +1064,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
 #pragma unroll 1
         for (u32 o = 1; o <= L; o++) {
             const int shift = sh.head.shift[o - 1];
-            const bool narrow = ((u64)sh.lpc_narrow2[o & 1] << (sub_bps - 1)) < (1ull << 31);
+            const bool narrow = is_narrow(sh.lpc_narrow2[o & 1], shift);
             u64 s0, s1;
             lpc_pass(o, shift, narrow, sh.q2[o & 1], s0, s1);
             store_runs(s0, s1);
