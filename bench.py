@@ -718,6 +718,36 @@ def main():
                 "what": "BASELINE config 5's shape: %d three-minute 44.1 kHz/16-bit stereo tracks (%d distinct PCMs cut from "
                         "the hour, cycled) through b200flac_encode_file at level 8 (-m -e, lpc 12, the from_pcm default), "
                         "%d host threads per rank, %d GPU(s), files on tmpfs" % (int(total_tracks), distinct, threads, world)}
+            # (3) the same tracks as ONE job per rank: b200flac_encode_files packs them into many-segment batches and
+            # hashes every track's MD5 on the device; files are byte-identical to (2)'s (checked on a sample)
+            names = [os.path.join(tmp.name, "bt_%d.flac" % i) for i in range(my_tracks)]
+            c_names = (C.c_char_p * my_tracks)(*[os.fsencode(x) for x in names])
+            c_ptrs = (C.c_void_p * my_tracks)(*[h_pcm + (i % distinct) * tn * frame_bytes for i in range(my_tracks)])
+            c_lens = (C.c_uint64 * my_tracks)(*([tn] * my_tracks))
+
+            def batch_job(k):
+                if L.b200flac_encode_files(k, c_names, C.byref(p8), 4096, None, c_ptrs, c_lens, dev, threads):
+                    raise SystemExit("b200flac_encode_files failed: " + L.b200flac_last_error().decode())
+            batch_job(min(my_tracks, 64))           # warm-up: device ring, pinned buffers, encoder
+            barrier()
+            t0 = time.perf_counter()
+            batch_job(my_tracks)
+            barrier()
+            t_bt = allmax(time.perf_counter() - t0)
+            encode_file(os.path.join(tmp.name, "bt_check.flac"), ((my_tracks - 1) % distinct) * tn, tn, p8)
+            same = open(os.path.join(tmp.name, "bt_check.flac"), "rb").read() == open(names[my_tracks - 1], "rb").read()
+            if not same:
+                raise SystemExit("b200flac_encode_files and b200flac_encode_file wrote different files")
+            for x in names:
+                os.unlink(x)
+            api["many_tracks_batch"] = {
+                "value": total_tracks * tn * CHANNELS / t_bt / 1e6, "unit": UNIT, "tracks": int(total_tracks),
+                "tracks_per_s": total_tracks / t_bt, "seconds": t_bt, "host_threads_per_rank": threads,
+                "projected_s_for_10000_tracks": 10000.0 * t_bt / total_tracks, "identical_to_encode_file": True,
+                "speedup_over_one_call_per_file": t_tr / t_bt,
+                "what": "the same tracks as ONE b200flac_encode_files job per rank: many-segment batches of the frame "
+                        "layer, every track's STREAMINFO MD5 computed on the device (one thread per track), %d host "
+                        "threads write the files to tmpfs; PCM read from page-locked memory" % threads}
 
     # ---- the other BASELINE configurations, device resident ----
     configs = None

@@ -144,6 +144,11 @@ int b200flac_encoder_submit_device(b200flac_encoder *enc, int slot, const void *
 int b200flac_encoder_collect_device(b200flac_encoder *enc, int slot, uint64_t *out_bytes,
                                     uint32_t *n_frames, float *elapsed_ms);
 
+/* After collect_device (or collect) on `slot`: the size in bytes and the PCM-frame count of every FLAC frame of the
+ * batch, in order -- host arrays owned by the slot, valid until its next submit. */
+const uint32_t *b200flac_encoder_slot_frame_bytes(b200flac_encoder *enc, int slot);
+const uint32_t *b200flac_encoder_slot_frame_pcm(b200flac_encoder *enc, int slot);
+
 /* per-kernel CUDA-event times of the slot's last batch, in ms:
  * [0] lpc model (window/autocorrelation, then Levinson/quantise), [1] subframe analysis,
  * [2] frame select + offset scan (+ output clear on the k_pack_v2 path), [3] frame packing
@@ -253,6 +258,20 @@ int b200flac_encode_file(const char *filename, const b200flac_params *params,
                          uint32_t padding_size, const char *version,
                          const uint8_t *pcm, uint64_t n_pcm_frames,
                          const int *devices, int n_devices);
+
+/* Many tracks -> many files in one call: BASELINE.json config 5 ("a batch of 10,000 three-minute tracks").  No
+ * reference counterpart -- FlacAudio.from_pcm (audiotools/flac.py:1235-1330) calls encoders.encode_flac once per
+ * file -- and no new format: file i is byte for byte what b200flac_encode_file(filenames[i], params, padding_size,
+ * version, pcm[i], n_pcm_frames[i], ...) writes.  The difference is where the time goes: tracks are packed into
+ * many-segment batches of the frame layer, and the STREAMINFO MD5 of every track (the per-stream serial step that
+ * bounds the one-call-per-file path: ~50 ms of one core per three-minute track) is computed on the device, one thread
+ * per track, from the PCM that is there for the encoder anyway.  pcm[i] should be page-locked (b200flac_host_alloc)
+ * for full copy speed.  device < 0: B200FLAC_DEVICE or 0.  host_threads (<= 0: 8) write the files.
+ * Returns 0 on success. */
+int b200flac_encode_files(uint32_t n_tracks, const char *const *filenames, const b200flac_params *params,
+                          uint32_t padding_size, const char *version,
+                          const uint8_t *const *pcm, const uint64_t *n_pcm_frames,
+                          int device, int host_threads);
 
 /* ---- file-backed PCM feed ----
  * The reference feeds the encoder through a Python PCMReader: WaveReader / AiffReader read the file,

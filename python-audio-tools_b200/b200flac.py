@@ -126,6 +126,9 @@ def lib():
     L.b200flac_finalize_metadata.argtypes = [C.c_char_p, u64p, u32p, C.c_uint64, C.c_uint32, C.c_uint32]
     L.b200flac_encode_file.argtypes = [C.c_char_p, C.POINTER(Params), C.c_uint32, C.c_char_p, vp,
                                        C.c_uint64, C.POINTER(C.c_int), C.c_int]
+    L.b200flac_encode_files.argtypes = [C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(Params), C.c_uint32, C.c_char_p,
+                                        C.POINTER(vp), u64p, C.c_int, C.c_int]
+    L.b200flac_internal_device_md5.argtypes = [C.c_int, vp, C.c_uint64, vp]
     L.b200flac_wave_probe.argtypes = [C.c_char_p, C.POINTER(PcmSource)]
     L.b200flac_aiff_probe.argtypes = [C.c_char_p, C.POINTER(PcmSource)]
     L.b200flac_stream_write_file.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32]
@@ -311,6 +314,26 @@ def encode_file(filename, params, pcm, n_pcm_frames, padding_size=4096, version=
     if lib().b200flac_encode_file(os.fsencode(filename), C.byref(params), padding_size, v, _buf_ptr(pcm),
                                   n_pcm_frames, devs, ndev):
         raise _err()
+
+
+def encode_files(filenames, params, pcms, n_pcm_frames, padding_size=4096, version=None, device=-1, host_threads=0):
+    """many tracks -> many files in one call (b200flac_encode_files): pcms[i] is a buffer or an address holding
+    n_pcm_frames[i] frames; every file equals what encode_file writes for that track"""
+    n = len(filenames)
+    names = (C.c_char_p * n)(*[os.fsencode(f) for f in filenames])
+    ptrs = (C.c_void_p * n)(*[_buf_ptr(b) for b in pcms])
+    lens = (C.c_uint64 * n)(*[int(v) for v in n_pcm_frames])
+    v = version.encode() if version else None
+    if lib().b200flac_encode_files(n, names, C.byref(params), padding_size, v, ptrs, lens, device, host_threads):
+        raise _err()
+
+
+def device_md5(data, device=0):
+    """test hook: MD5 of a byte string computed by the batch entry's device kernel"""
+    out = (C.c_uint8 * 16)()
+    if lib().b200flac_internal_device_md5(device, _buf_ptr(data), len(data), out):
+        raise _err()
+    return bytes(out)
 
 
 class Stream(object):

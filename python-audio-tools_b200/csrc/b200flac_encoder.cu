@@ -1235,6 +1235,18 @@ extern "C" int b200flac_encoder_collect_device(b200flac_encoder* enc, int slot, 
     return 0;
 }
 
+extern "C" const uint32_t* b200flac_encoder_slot_frame_bytes(b200flac_encoder* enc, int slot)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots) return nullptr;
+    return enc->slots[slot].h_frame_bytes;
+}
+
+extern "C" const uint32_t* b200flac_encoder_slot_frame_pcm(b200flac_encoder* enc, int slot)
+{
+    if (!enc || slot < 0 || slot >= enc->n_slots) return nullptr;
+    return enc->slots[slot].frame_pcm.data();
+}
+
 extern "C" int b200flac_encoder_encode_device(b200flac_encoder* enc, int slot, const void* d_pcm,
                                               const b200flac_segment* segments, uint32_t n_segments,
                                               void* d_out, uint64_t out_capacity, uint64_t* out_bytes,

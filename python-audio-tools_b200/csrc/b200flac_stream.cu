@@ -211,19 +211,51 @@ static void put_be(uint8_t* p, uint64_t v, int bytes)
 }
 
 // STREAMINFO body, flac.c:376-409
-static void build_streaminfo(const b200flac_stream* s, const uint8_t md5[16], uint8_t out[34])
+static void streaminfo_body(const b200flac_params& p, uint32_t min_frame, uint32_t max_frame, uint64_t total_samples,
+                            const uint8_t md5[16], uint8_t out[34])
 {
-    const b200flac_params& p = s->params;
     auto clampu = [](uint64_t v, uint64_t hi) { return v > hi ? hi : v; };
     put_be(out + 0, clampu(p.block_size, 0xFFFF), 2);
     put_be(out + 2, clampu(p.block_size, 0xFFFF), 2);
-    put_be(out + 4, clampu(s->min_frame, 0xFFFFFF), 3);
-    put_be(out + 7, clampu(s->max_frame, 0xFFFFFF), 3);
+    put_be(out + 4, clampu(min_frame, 0xFFFFFF), 3);
+    put_be(out + 7, clampu(max_frame, 0xFFFFFF), 3);
     // 20 bits rate | 3 bits channels-1 | 5 bits bps-1 | 36 bits total samples
     const uint64_t v = (clampu(p.sample_rate, 0xFFFFF) << 44) | (clampu(p.channels - 1, 7) << 41) |
-                       (clampu(p.bits_per_sample - 1, 31) << 36) | (s->total_samples & 0xFFFFFFFFFull);
+                       (clampu(p.bits_per_sample - 1, 31) << 36) | (total_samples & 0xFFFFFFFFFull);
     put_be(out + 10, v, 8);
     memcpy(out + 18, md5, 16);
+}
+static void build_streaminfo(const b200flac_stream* s, const uint8_t md5[16], uint8_t out[34])
+{
+    streaminfo_body(s->params, s->min_frame, s->max_frame, s->total_samples, md5, out);
+}
+
+// The bytes before the first frame, flac.c:209-238: "fLaC", STREAMINFO, VORBIS_COMMENT (vendor string only), PADDING.
+// The STREAMINFO body is bytes 8..41 (the MD5 its last 16).  Shared with the many-files entry (b200flac_batch.cu).
+void b200flac_internal_stream_head(const b200flac_params* params, uint32_t padding_size, const char* version,
+                                   uint32_t min_frame, uint32_t max_frame, uint64_t total_samples,
+                                   const uint8_t md5[16], std::vector<uint8_t>& head)
+{
+    char vendor[300];
+    snprintf(vendor, sizeof(vendor), "Python Audio Tools %s", version ? version : "2.22alpha1");
+    const uint32_t L = (uint32_t)strlen(vendor);
+    head.clear();
+    const uint8_t magic[4] = {0x66, 0x4C, 0x61, 0x43};
+    head.insert(head.end(), magic, magic + 4);
+    uint8_t bh[4];
+    bh[0] = 0x00; put_be(bh + 1, 34, 3);                 // not last | STREAMINFO | 34
+    head.insert(head.end(), bh, bh + 4);
+    uint8_t si[34];
+    streaminfo_body(*params, min_frame, max_frame, total_samples, md5, si);
+    head.insert(head.end(), si, si + 34);
+    bh[0] = 0x04; put_be(bh + 1, 4 + L + 4, 3);          // VORBIS_COMMENT
+    head.insert(head.end(), bh, bh + 4);
+    for (int i = 0; i < 4; i++) head.push_back((uint8_t)(L >> (8 * i))); // little-endian fields
+    head.insert(head.end(), vendor, vendor + L);
+    for (int i = 0; i < 4; i++) head.push_back(0);
+    bh[0] = 0x81; put_be(bh + 1, padding_size, 3);       // last | PADDING
+    head.insert(head.end(), bh, bh + 4);
+    head.resize(head.size() + padding_size, 0);
 }
 
 // ---- encoder pool -------------------------------------------------------------------------------
@@ -280,10 +312,12 @@ static void pool_release(const b200flac_params* p, int device, uint64_t batch_fr
 }
 
 extern "C" void b200flac_internal_decoder_clear(void); // b200flac_decoder.cu
+extern "C" void b200flac_internal_batch_clear(void);   // b200flac_batch.cu
 
 extern "C" void b200flac_pool_clear(void)
 {
     b200flac_internal_decoder_clear();
+    b200flac_internal_batch_clear();
     std::vector<PoolEntry> all;
     pthread_mutex_lock(&g_pool_mu);
     all.swap(g_pool);
@@ -380,26 +414,9 @@ extern "C" b200flac_stream* b200flac_stream_open(const char* filename, const b20
         }
 
     // ---- stream head, flac.c:209-238 ----
-    char vendor[300];
-    snprintf(vendor, sizeof(vendor), "Python Audio Tools %s", version ? version : "2.22alpha1");
-    const uint32_t L = (uint32_t)strlen(vendor);
     std::vector<uint8_t> head;
-    const uint8_t magic[4] = {0x66, 0x4C, 0x61, 0x43};
-    head.insert(head.end(), magic, magic + 4);
-    uint8_t bh[4];
-    bh[0] = 0x00; put_be(bh + 1, 34, 3);                 // not last | STREAMINFO | 34
-    head.insert(head.end(), bh, bh + 4);
-    uint8_t si[34], zero_md5[16] = {0};
-    build_streaminfo(s, zero_md5, si);
-    head.insert(head.end(), si, si + 34);
-    bh[0] = 0x04; put_be(bh + 1, 4 + L + 4, 3);          // VORBIS_COMMENT
-    head.insert(head.end(), bh, bh + 4);
-    for (int i = 0; i < 4; i++) head.push_back((uint8_t)(L >> (8 * i))); // little-endian fields
-    head.insert(head.end(), vendor, vendor + L);
-    for (int i = 0; i < 4; i++) head.push_back(0);
-    bh[0] = 0x81; put_be(bh + 1, padding_size, 3);       // last | PADDING
-    head.insert(head.end(), bh, bh + 4);
-    head.resize(head.size() + padding_size, 0);
+    const uint8_t zero_md5[16] = {0};
+    b200flac_internal_stream_head(params, padding_size, version, s->min_frame, s->max_frame, s->total_samples, zero_md5, head);
     if (fwrite(head.data(), 1, head.size(), f) != head.size()) {
         stream_err("write error"); destroy_stream(s); return nullptr;
     }

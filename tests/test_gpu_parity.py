@@ -579,3 +579,59 @@ def test_standalone_driver_matches_reference_driver(tmp_path, built):
         want = helpers.ref_encode(pcm, rate, ch, bps, helpers.options(**o)) if helpers.have_ref() else \
             helpers.oracle_encode(pcm, rate, ch, bps, helpers.options(**o))
         assert got == want
+
+
+# ---------------------------------------------------------------------------------------------
+# many tracks -> many files in one call (b200flac_encode_files): batches of many segments, the
+# STREAMINFO MD5 of every track computed on the device
+# ---------------------------------------------------------------------------------------------
+def test_device_md5_matches_hashlib(built):
+    """the per-track MD5 kernel against hashlib at every padding boundary (0, 55|56, 63|64|65, 119|120, two blocks)
+    and on a long string"""
+    b = _b200()
+    rng = np.random.RandomState(5)
+    for n in (0, 1, 3, 55, 56, 57, 63, 64, 65, 119, 120, 121, 127, 128, 129, 1000, 4096 * 4 + 2, (1 << 20) + 3):
+        data = rng.randint(0, 256, size=n).astype(np.uint8).tobytes()
+        assert b.device_md5(data) == hashlib.md5(data).digest(), "length %d" % n
+
+
+@pytest.mark.parametrize("shape", ["16bit_stereo", "24bit_6ch", "level8", "small_batches"])
+def test_encode_files_equals_encode_file(shape, tmp_path, built):
+    """every file of b200flac_encode_files is byte for byte what b200flac_encode_file writes for the same track:
+    ragged lengths (empty track, shorter than a block, byte counts that are not a multiple of 64), several batches,
+    region reuse in the device ring (B200FLAC_FILES_BATCH_MB=1, B200FLAC_FILES_RING=4)"""
+    b = _b200()
+    if shape == "24bit_6ch":
+        rate, ch, bps = 96000, 6, 24
+        o = helpers.options(block_size=4608, max_lpc_order=12, max_residual_partition_order=6)
+        lengths = [4608 * 3 + 17, 100, 4608, 0, 4608 * 2 - 1, 9001]
+    elif shape == "level8":
+        rate, ch, bps = 44100, 2, 16
+        o = helpers.options(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, mid_side=True,
+                            exhaustive_model_search=True)
+        lengths = [4096 * 5 + 333, 4096 * 2, 7, 4096 * 3 + 4095]
+    else:
+        rate, ch, bps = 44100, 2, 16
+        o = helpers.options(block_size=4096, max_lpc_order=12, max_residual_partition_order=6, adaptive_mid_side=True)
+        lengths = [4096 * 4 + 99, 0, 1, 15, 16, 17, 4096, 4097, 4096 * 7 + 4095, 50000, 3, 4096 * 2 + 8]
+        if shape == "small_batches":
+            lengths = [30000 + 977 * i for i in range(40)]            # ~120-280 KB each: dozens of 1 MB batches
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(rate, ch, bps, **kw)
+    pcms = [helpers.synth_pcm(700 + i, ch, bps, n) if n else b"" for i, n in enumerate(lengths)]
+    want = []
+    for i, (pcm, n) in enumerate(zip(pcms, lengths)):
+        path = os.path.join(str(tmp_path), "one_%d.flac" % i)
+        b.encode_file(path, p, pcm if n else b"\0", n, padding_size=o["padding_size"])
+        want.append(open(path, "rb").read())
+    names = [os.path.join(str(tmp_path), "many_%d.flac" % i) for i in range(len(lengths))]
+    bufs = [np.frombuffer(pcm if n else b"\0" * 16, dtype=np.uint8).copy() for pcm, n in zip(pcms, lengths)]
+    env = {"B200FLAC_FILES_BATCH_MB": "1", "B200FLAC_FILES_RING": "4"} if shape == "small_batches" else {}
+    _with_env(env, lambda: b.encode_files(names, p, bufs, lengths, padding_size=o["padding_size"], device=0, host_threads=3))
+    b.lib().b200flac_pool_clear()
+    for i, name in enumerate(names):
+        got = open(name, "rb").read()
+        assert got == want[i], "track %d (%d PCM frames) differs at byte %d" % (i, lengths[i], _first_diff(got, want[i]))
+    # and the hash in the STREAMINFO is the MD5 of the PCM (flac.c:187-188)
+    for i, name in enumerate(names):
+        assert open(name, "rb").read()[26:42] == hashlib.md5(pcms[i]).digest()
