@@ -19,7 +19,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "python-audio-tools_b200", "libb200flac.so")
+LIB = os.environ.get("B200FLAC_LIB") or os.path.join(ROOT, "python-audio-tools_b200", "libb200flac.so")
 SRC = os.path.join(ROOT, "python-audio-tools_b200", "csrc")
 
 

@@ -126,9 +126,10 @@ def lib():
     L.b200flac_finalize_metadata.argtypes = [C.c_char_p, u64p, u32p, C.c_uint64, C.c_uint32, C.c_uint32]
     L.b200flac_encode_file.argtypes = [C.c_char_p, C.POINTER(Params), C.c_uint32, C.c_char_p, vp,
                                        C.c_uint64, C.POINTER(C.c_int), C.c_int]
-    L.b200flac_encode_files.argtypes = [C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(Params), C.c_uint32, C.c_char_p,
-                                        C.POINTER(vp), u64p, C.c_int, C.c_int]
-    L.b200flac_internal_device_md5.argtypes = [C.c_int, vp, C.c_uint64, vp]
+    if hasattr(L, "b200flac_encode_files"):        # (absent from older A/B builds loaded through B200FLAC_LIB)
+        L.b200flac_encode_files.argtypes = [C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(Params), C.c_uint32, C.c_char_p,
+                                            C.POINTER(vp), u64p, C.c_int, C.c_int]
+        L.b200flac_internal_device_md5.argtypes = [C.c_int, vp, C.c_uint64, vp]
     L.b200flac_wave_probe.argtypes = [C.c_char_p, C.POINTER(PcmSource)]
     L.b200flac_aiff_probe.argtypes = [C.c_char_p, C.POINTER(PcmSource)]
     L.b200flac_stream_write_file.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32]

@@ -60,6 +60,36 @@ __device__ __forceinline__ int ld_candidate(const uint8_t* __restrict__ pcm, u64
     return cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
 }
 
+// 24-bit stereo block -> candidate samples in shared memory (dst indexed through the 4-words-per-32 skew of the v3
+// kernels): eight PCM frames are 48 bytes, three 128-bit loads; one PRMT per sample picks its three bytes and
+// replicates the sign of the top one.  (The generic per-sample loop is one dependent load per sample: a tenth of
+// the analysis kernel's time at 24 bits.)  src 16-byte aligned, n a multiple of 8.  Out of line on purpose: the
+// 16-bit kernels' hot code must not grow by it (instruction cache, see profiles/r02_icache_analysis.txt).
+__device__ __noinline__ void load_stereo24_skewed(const uint8_t* __restrict__ src, int* __restrict__ dst, u32 n, u32 cand,
+                                                  u32 tid, u32 nt, int first, u32* orv_io, u32* diff_io)
+{
+    const uint4* s4 = (const uint4*)src;
+    u32 orv = 0, diff = 0;
+#pragma unroll 2
+    for (u32 g = tid; g < (n >> 3); g += nt) {
+        const uint4 a = __ldg(s4 + 3 * g), b = __ldg(s4 + 3 * g + 1), c = __ldg(s4 + 3 * g + 2);
+        const u32 w[13] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, 0u};
+        int v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int oL = 6 * j, oR = 6 * j + 3;
+            const int L = s24_from_words(w[oL >> 2], w[(oL >> 2) + 1], oL & 3);
+            const int R = s24_from_words(w[oR >> 2], w[(oR >> 2) + 1], oR & 3);
+            v[j] = cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
+            orv |= (u32)v[j]; diff |= (u32)(v[j] ^ first);
+        }
+        const u32 i = 8 * g, sk = i + ((i >> 5) << 2);
+        *(int4*)(dst + sk) = make_int4(v[0], v[1], v[2], v[3]);
+        *(int4*)(dst + sk + 4) = make_int4(v[4], v[5], v[6], v[7]);
+    }
+    *orv_io |= orv; *diff_io |= diff;
+}
+
 // bits-per-sample a candidate is coded at: the difference channel needs one more (flac.c:569)
 __device__ __forceinline__ u32 candidate_bps(u32 cand, const bf_dev_params& P)
 {

@@ -734,26 +734,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
                 }
             }
         } else if (P.stereo && P.bytes_ps == 3 && (n & 7u) == 0 && (((uintptr_t)(pcm + d.pcm_off * 6)) & 15) == 0) {
-            // 24-bit stereo: eight PCM frames are 48 bytes, three 128-bit loads; one PRMT per sample picks its three
-            // bytes and replicates the sign of the top one.  (The generic loop below is one dependent load per
-            // sample: a tenth of the kernel's time at 24 bits.)
-            const uint4* s4 = (const uint4*)(pcm + d.pcm_off * 6);
-#pragma unroll 2
-            for (u32 g = tid; g < (n >> 3); g += nt) {
-                const uint4 a = __ldg(s4 + 3 * g), b = __ldg(s4 + 3 * g + 1), c = __ldg(s4 + 3 * g + 2);
-                const u32 w[13] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, 0u};
-                int v[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int oL = 6 * j, oR = 6 * j + 3;
-                    const int L = s24_from_words(w[oL >> 2], w[(oL >> 2) + 1], oL & 3);
-                    const int R = s24_from_words(w[oR >> 2], w[(oR >> 2) + 1], oR & 3);
-                    v[j] = cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
-                    orv |= (u32)v[j]; diff |= (u32)(v[j] ^ first);
-                }
-                *(int4*)(samp + V3_SK(8 * g)) = make_int4(v[0], v[1], v[2], v[3]);
-                *(int4*)(samp + V3_SK(8 * g) + 4) = make_int4(v[4], v[5], v[6], v[7]);
-            }
+            load_stereo24_skewed(pcm + d.pcm_off * 6, samp, n, cand, tid, nt, first, &orv, &diff);
         } else {
             for (u32 i = tid; i < n; i += nt) {
                 const int v = ld_candidate(pcm, d.pcm_off + i, cand, P);

@@ -335,23 +335,8 @@ k_pack_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                 for (u32 i = gtid; i < n; i += gt) buf[V3_SK(i)] = __dp2a_lo((int)__ldg(s1 + i), coef, 0) >> shv;
             }
         } else if (P.stereo && P.bytes_ps == 3 && (n & 7u) == 0 && (((uintptr_t)(pcm + d.pcm_off * 6)) & 15) == 0) {
-            // 24-bit stereo: eight PCM frames are three 128-bit loads, one PRMT per sample (as in k_analyze_v3)
-            const uint4* s4 = (const uint4*)(pcm + d.pcm_off * 6);
-#pragma unroll 2
-            for (u32 grp = gtid; grp < (n >> 3); grp += gt) {
-                const uint4 a = __ldg(s4 + 3 * grp), b = __ldg(s4 + 3 * grp + 1), c = __ldg(s4 + 3 * grp + 2);
-                const u32 w[13] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, 0u};
-                int v[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int oL = 6 * j, oR = 6 * j + 3;
-                    const int L = s24_from_words(w[oL >> 2], w[(oL >> 2) + 1], oL & 3);
-                    const int R = s24_from_words(w[oR >> 2], w[(oR >> 2) + 1], oR & 3);
-                    v[j] = cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
-                }
-                *(int4*)(buf + V3_SK(8 * grp)) = make_int4(v[0], v[1], v[2], v[3]);
-                *(int4*)(buf + V3_SK(8 * grp) + 4) = make_int4(v[4], v[5], v[6], v[7]);
-            }
+            u32 o_ = 0, d_ = 0;
+            load_stereo24_skewed(pcm + d.pcm_off * 6, buf, n, cand, gtid, gt, 0, &o_, &d_);
         } else {
             for (u32 i = gtid; i < n; i += gt) buf[V3_SK(i)] = ld_candidate(pcm, d.pcm_off + i, cand, P);
         }
