@@ -494,9 +494,17 @@ extern "C" b200flac_encoder* b200flac_encoder_create(const b200flac_params* para
             // samples per thread known at compile time (the exhaustive instantiation also assumes four warps)
             const bool s32 = enc->v3_S == 32 && (P.exhaustive ? enc->v3_NT == 128 : enc->v3_NT <= 128);
 #define V3_ATTR(MINB_, EXH_, SC_) cudaFuncSetAttribute(k_analyze_v3<MINB_, EXH_, SC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
-            if (enc->v3_sub == 2)
+            // (orders up to 12 only: the instantiations without the 32-tap loops, for the shapes that have one)
+            const bool short_lpc = P.max_lpc_order <= 12;
+            if (enc->v3_sub == 2 && short_lpc)
+                e = P.exhaustive ? cudaFuncSetAttribute(k_analyze_v3<5, true, 32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
+                                 : cudaFuncSetAttribute(k_analyze_v3<4, false, 32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
+            else if (enc->v3_sub == 2)
                 e = P.exhaustive ? cudaFuncSetAttribute(k_analyze_v3<5, true, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
                                  : cudaFuncSetAttribute(k_analyze_v3<4, false, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
+            else if (s32 && short_lpc)
+                e = P.exhaustive ? cudaFuncSetAttribute(k_analyze_v3<5, true, 32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN)
+                                 : cudaFuncSetAttribute(k_analyze_v3<5, false, 32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_OPTIN);
             else if (P.exhaustive) e = s32 ? V3_ATTR(5, true, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, true, 0) : enc->v3_NT <= 256 ? V3_ATTR(3, true, 0) : V3_ATTR(1, true, 0);
             else e = s32 ? V3_ATTR(5, false, 32) : enc->v3_NT <= 128 ? V3_ATTR(5, false, 0) : enc->v3_NT <= 256 ? V3_ATTR(3, false, 0) : V3_ATTR(1, false, 0);
 #undef V3_ATTR
@@ -948,11 +956,17 @@ static void stage_analyze(b200flac_encoder* enc, const ChunkView& v, cudaStream_
         if (getenv("B200FLAC_V3_GRID")) g3 = (u32)atoi(getenv("B200FLAC_V3_GRID"));   // tuning knob
         if (g3 > v.U || g3 == 0) g3 = v.U;
 #define V3_LAUNCH(MINB_, EXH_, SC_) k_analyze_v3<MINB_, EXH_, SC_><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice)
+#define V3_LAUNCH5(MINB_, EXH_, SUB_, LONG_) k_analyze_v3<MINB_, EXH_, 32, SUB_, LONG_><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice)
+        const bool short_lpc = P.max_lpc_order <= 12;
         if (enc->v3_sub == 2) {
-            if (P.exhaustive) k_analyze_v3<5, true, 32, 2><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice);
-            else k_analyze_v3<4, false, 32, 2><<<g3, enc->v3_NT, enc->v3_smem, st>>>(d_pcm, v.fd, P, enc->v3_S, enc->v3_F, v.U, v.heads, v.coefs, v.plans, v.rice);
+            if (P.exhaustive) { if (short_lpc) V3_LAUNCH5(5, true, 2, false); else V3_LAUNCH5(5, true, 2, true); }
+            else { if (short_lpc) V3_LAUNCH5(4, false, 2, false); else V3_LAUNCH5(4, false, 2, true); }
         }
-        else if (enc->v3_S == 32 && (P.exhaustive ? enc->v3_NT == 128 : enc->v3_NT <= 128)) { if (P.exhaustive) V3_LAUNCH(5, true, 32); else V3_LAUNCH(5, false, 32); }
+        else if (enc->v3_S == 32 && (P.exhaustive ? enc->v3_NT == 128 : enc->v3_NT <= 128)) {
+            if (P.exhaustive) { if (short_lpc) V3_LAUNCH5(5, true, 1, false); else V3_LAUNCH(5, true, 32); }
+            else { if (short_lpc) V3_LAUNCH5(5, false, 1, false); else V3_LAUNCH(5, false, 32); }
+        }
+#undef V3_LAUNCH5
         else if (enc->v3_NT <= 128) { if (P.exhaustive) V3_LAUNCH(5, true, 0); else V3_LAUNCH(5, false, 0); }
         else if (enc->v3_NT <= 256) { if (P.exhaustive) V3_LAUNCH(3, true, 0); else V3_LAUNCH(3, false, 0); }
         else { if (P.exhaustive) V3_LAUNCH(1, true, 0); else V3_LAUNCH(1, false, 0); }

@@ -642,7 +642,9 @@ __device__ __forceinline__ u32 v3_stored_bits(const int* __restrict__ resid, u32
 // EXH: exhaustive order search (flac.c:1070-1120): FIXED as usual, then every LPC order 1..max in turn
 // (residual, Rice search, exact bits), keeping the first strict minimum of the exact sizes.
 // SUB: run sums per thread run (2: the finest partition is half a run, see V3_MAX_F).
-template <bool EXH, int SC, int SUB>
+// LONG: LPC orders above 12 may occur (the 32-tap residual loops, ~14 KB of code, are compiled in).  The common
+// shapes have an instantiation without them: the hot code of a kernel that never needs them stays in one piece.
+template <bool EXH, int SC, int SUB, bool LONG>
 __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB == 2 ? 8 : V3_MAX_F)>& sh, u32 unit,
                                         const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd,
                                         const bf_dev_params& P, u32 S_rt, u32 F,
@@ -865,8 +867,9 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
         else if (o <= 12) run = narrow ? v3_lpc_residual<12, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
                                 : f64 ? v3_lpc_residual_f64<12, SUB>(samp, resid, base, S, qs, shift, h0)
                                       : v3_lpc_residual<12, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
-        else run = narrow ? v3_lpc_residual<32, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
-                          : v3_lpc_residual<32, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
+        else if constexpr (LONG) run = narrow ? v3_lpc_residual<32, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
+                                              : v3_lpc_residual<32, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
+        else run = 0;       // (unreachable: the host launches this instantiation for max_lpc_order <= 12 only)
         if (SUB == 2) { s0 = first; s1 = run; } else { s0 = run; s1 = 0; }
         if (tid == 0) {
             u64 warm = 0;
@@ -1109,7 +1112,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
 // The grid is normally one CTA per unit; any smaller grid walks the units with the grid's stride
 // (measured: a persistent single wave keeps the CTAs of an SM in the same phase of the unit, which
 // overlaps their load and search phases worse than staggered CTAs do).
-template <int MINB, bool EXH, int SC, int SUB = 1>
+template <int MINB, bool EXH, int SC, int SUB = 1, bool LONG = true>
 __global__ void __launch_bounds__(MINB >= 4 ? 128 : MINB >= 3 ? 256 : 512, MINB)
 k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, bf_dev_params P, u32 S, u32 F,
              u32 n_units, const bf_lpc_head* __restrict__ heads, const short* __restrict__ coefs,
@@ -1118,7 +1121,7 @@ k_analyze_v3(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ 
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ V3SharedT<(SUB == 2 ? 8 : V3_MAX_F)> sh;
     for (u32 unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        v3_unit<EXH, SC, SUB>(dyn_smem, sh, unit, pcm, fd, P, S, F, heads, coefs, plans, rice_out);
+        v3_unit<EXH, SC, SUB, LONG>(dyn_smem, sh, unit, pcm, fd, P, S, F, heads, coefs, plans, rice_out);
         __syncthreads();        // shared memory is reused by the next unit
     }
 }
