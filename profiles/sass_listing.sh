@@ -13,7 +13,9 @@ one() {  # cubin, mangled-name pattern, output name
     echo "$3: $(grep -c "^ *//\*[0-9a-f]*\*/\|^ */\*[0-9a-f]*\*/" profiles/r02_sass_$3.txt) instructions"
 }
 one b200flac_encoder.sm_100a.cubin '_Z11k_lpc_autocILi12ELi1EE' k_lpc_autoc_12_1
-one b200flac_encoder.sm_100a.cubin '_Z12k_analyze_v3ILi5ELb0ELi32EE' k_analyze_v3_5_0_32
+one b200flac_encoder.sm_100a.cubin '_Z12k_analyze_v3ILi5ELb0ELi32ELi1ELb0EE' k_analyze_v3_5_0_32
+one b200flac_encoder.sm_100a.cubin '_Z12k_analyze_v3ILi5ELb1ELi32ELi2ELb0EE' k_analyze_v3_exhaustive_order8
+one b200flac_batch.sm_100a.cubin '_Z12k_md5_tracks' k_md5_tracks
 one b200flac_encoder.sm_100a.cubin '_Z9k_pack_v3ILi256ELi4ELi32EE' k_pack_v3_256_4_32
 one b200tta.sm_100a.cubin '_Z14k_tta_residualILj2EE' k_tta_residual_2
 one b200alac.sm_100a.cubin '_Z11k_alac_size' k_alac_size
