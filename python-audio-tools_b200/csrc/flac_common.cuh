@@ -34,13 +34,13 @@ __device__ __forceinline__ int ld_pcm(const uint8_t* __restrict__ pcm, u64 sidx,
     return *(const int*)p;
 }
 
-// 24-bit little-endian sample whose first byte is byte `sh` (0..3) of the word pair (lo, hi), sign extended: ONE
+// 24-bit little-endian sample whose first byte is byte `sh` (0..5) of the word pair (lo, hi), sign extended: ONE
 // PRMT -- the fourth selector nibble has bit 3 set, which replicates the sign of the selected (top) byte.
 // (prmt.b32 in PTX; __byte_perm documents only three selector bits per nibble.)
 __device__ __forceinline__ int s24_from_words(u32 lo, u32 hi, int sh)
 {
     int r;
-    const u32 sel = (u32)(sh | ((sh + 1) << 4) | ((sh + 2) << 8) | ((8 | (sh + 2)) << 12));
+    const u32 sel = 0xA210u + 0x1111u * (u32)sh;      // nibbles sh, sh+1, sh+2, 8|(sh+2): sh <= 5
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
     return r;
 }

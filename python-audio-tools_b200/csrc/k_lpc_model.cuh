@@ -223,6 +223,7 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
     for (int i = 0; i < NL; i++) a_[i] = 0.0;
     u32 orv = 0;
     const int coef = stereo16_coef(cand), sh = cand == 2 ? 1 : 0;
+    const int cl24 = cand == 1 ? 0 : 1, cr24 = cand == 0 ? 0 : cand == 3 ? -1 : 1;     // (L, R) weights of the candidate
 
     auto issue_tile = [&](u32 i0, u32 b) {
         u32* base = tbuf + (size_t)b * g.rows * row_words;
@@ -297,6 +298,8 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
         const u32 amask = BULK ? 15u : 3u;
         const uint8_t* row = (const uint8_t*)(tbuf + ((size_t)b * g.rows + myrow) * row_words) +
                              (u32)(((BULK ? (uintptr_t)pcm : (uintptr_t)0) + my_byte0 + (u64)i0 * rowbytes) & amask);
+        const u32 row_sa = (u32)__cvta_generic_to_shared((const void*)((uintptr_t)row & ~(uintptr_t)3));   // (24-bit stereo fetch)
+        const u32 row24 = (u32)((uintptr_t)row & 3);
         const double* wt = wbuf + b * g.WT +
                            (BULK ? (u32)(((uintptr_t)(windows + woff0 + i0) & 15) >> 3) : 0u);
 #pragma unroll 1
@@ -314,6 +317,20 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
             auto fetch = [&](u32 t) -> int {
                 if (FAST) return stereo16_candidate(((const u32*)row)[t], coef, sh);
                 if (!P.stereo) return ld_pcm(row, t * C + cand, B);
+                if (B == 3) {
+                    // a 24-bit stereo frame is six bytes at an even offset (4-byte aligned buffer, offsets that are
+                    // multiples of six): both samples lie in two aligned words, one PRMT each (byte select + sign).
+                    // The candidate is (cl * L + cr * R) >> sh like the 16-bit pair's dot product: the lanes of a
+                    // warp hold different candidates, and `cand == 0 ? L : ...` compiled to four divergent branches
+                    // per sample (a sixth of the kernel's instructions at 24 bits).  Explicit shared-memory loads:
+                    // the staging pointer reaches this function as a generic one.
+                    const u32 a = row24 + 6u * t;
+                    u32 w0, w1;
+                    asm("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(row_sa + (a & ~3u)));
+                    asm("ld.shared.u32 %0, [%1 + 4];" : "=r"(w1) : "r"(row_sa + (a & ~3u)));
+                    const int L = s24_from_words(w0, w1, (int)(a & 3u)), R = s24_from_words(w0, w1, (int)(a & 3u) + 3);
+                    return (cl24 * L + cr24 * R) >> sh;
+                }
                 const int L = ld_pcm(row, t * 2, B), R = ld_pcm(row, t * 2 + 1, B);
                 return cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
             };
