@@ -277,6 +277,151 @@ error:
     return NULL;
 }
 
+/* encode_flac_files(filenames, pcmreaders, block_size, max_lpc_order, min_residual_partition_order,
+ *                   max_residual_partition_order, mid_side=0, ..., padding_size=4096, host_threads=0) -> None
+ * Many tracks in one call (b200flac_encode_files; no reference counterpart -- the reference
+ * encodes one file per encode_flac call).  Same option names and defaults as encode_flac.  Every reader is read to
+ * its end and cut into block_size frames -- what encode_flac does with the BufferedPCMReader FlacAudio.from_pcm
+ * always passes -- and every file is byte for byte what encode_flac writes for that reader.  All readers must share
+ * sample rate, channels and bits per sample.  Readers are closed on success, like encode_flac's. */
+static PyObject *encoders_encode_flac_files(PyObject *dummy, PyObject *args, PyObject *keywds)
+{
+    static char *kwlist[] = {"filenames", "pcmreaders", "block_size", "max_lpc_order",
+                             "min_residual_partition_order", "max_residual_partition_order",
+                             "mid_side", "adaptive_mid_side", "exhaustive_model_search",
+                             "disable_verbatim_subframes", "disable_constant_subframes",
+                             "disable_fixed_subframes", "disable_lpc_subframes", "padding_size", "host_threads", NULL};
+    PyObject *names_obj, *readers_obj, *names = NULL, *readers = NULL, *result = NULL;
+    b200flac_params p;
+    unsigned padding_size = 4096;
+    int host_threads = 0;
+    Py_ssize_t n = 0;
+    struct py_pcmreader **rd = NULL;
+    PyObject **name_bytes = NULL;
+    const char **c_names = NULL;
+    uint8_t **bufs = NULL;
+    size_t *caps = NULL, *used = NULL;
+    uint64_t *frames = NULL;
+    uint8_t *arena = NULL;
+    const uint8_t **ptrs = NULL;
+
+    memset(&p, 0, sizeof(p));
+    if (!PyArg_ParseTupleAndKeywords(args, keywds, "OOIIII|iiiiiiiIi", kwlist, &names_obj, &readers_obj,
+                                     &p.block_size, &p.max_lpc_order, &p.min_residual_partition_order,
+                                     &p.max_residual_partition_order, &p.mid_side, &p.adaptive_mid_side,
+                                     &p.exhaustive_model_search, &p.no_verbatim_subframes, &p.no_constant_subframes,
+                                     &p.no_fixed_subframes, &p.no_lpc_subframes, &padding_size, &host_threads))
+        return NULL;
+    names = PySequence_Fast(names_obj, "filenames must be a sequence");
+    readers = names ? PySequence_Fast(readers_obj, "pcmreaders must be a sequence") : NULL;
+    if (!names || !readers) goto done;
+    n = PySequence_Fast_GET_SIZE(names);
+    if (n != PySequence_Fast_GET_SIZE(readers)) { PyErr_SetString(PyExc_ValueError, "one pcmreader per filename"); goto done; }
+    if (n == 0) { result = Py_None; Py_INCREF(result); goto done; }
+    if (p.block_size == 0 || p.block_size > (1u << 20)) { PyErr_SetString(PyExc_ValueError, "block_size must be 1..1048576"); goto done; }
+    rd = (struct py_pcmreader **)calloc((size_t)n, sizeof(*rd));
+    name_bytes = (PyObject **)calloc((size_t)n, sizeof(*name_bytes));
+    c_names = (const char **)calloc((size_t)n, sizeof(*c_names));
+    bufs = (uint8_t **)calloc((size_t)n, sizeof(*bufs));
+    caps = (size_t *)calloc((size_t)n, sizeof(*caps));
+    used = (size_t *)calloc((size_t)n, sizeof(*used));
+    frames = (uint64_t *)calloc((size_t)n, sizeof(*frames));
+    ptrs = (const uint8_t **)calloc((size_t)n, sizeof(*ptrs));
+    if (!rd || !name_bytes || !c_names || !bufs || !caps || !used || !frames || !ptrs) { PyErr_NoMemory(); goto done; }
+    for (Py_ssize_t i = 0; i < n; i++) {
+        if (!PyUnicode_FSConverter(PySequence_Fast_GET_ITEM(names, i), &name_bytes[i])) goto done;
+        c_names[i] = PyBytes_AS_STRING(name_bytes[i]);
+        void *r = NULL;
+        if (!pcmreader_converter(PySequence_Fast_GET_ITEM(readers, i), &r)) goto done;
+        rd[i] = (struct py_pcmreader *)r;
+        if (i == 0) {
+            p.sample_rate = rd[0]->sample_rate; p.channels = rd[0]->channels; p.bits_per_sample = rd[0]->bits_per_sample;
+        } else if (rd[i]->sample_rate != p.sample_rate || rd[i]->channels != p.channels || rd[i]->bits_per_sample != p.bits_per_sample) {
+            PyErr_SetString(PyExc_ValueError, "all pcmreaders of one call must share sample rate, channels and bits per sample");
+            goto done;
+        }
+        /* (encode_flac's IOError for a file that cannot be opened, flac.c:114-117) */
+        FILE *probe = fopen(c_names[i], "wb");
+        if (!probe) { PyErr_SetFromErrnoWithFilename(PyExc_IOError, c_names[i]); goto done; }
+        fclose(probe);
+    }
+    {
+        const unsigned bytes_ps = p.bits_per_sample / 8;
+        if (bytes_ps < 1 || bytes_ps > 3) { PyErr_SetString(PyExc_ValueError, "unsupported bits_per_sample"); goto done; }
+        const unsigned read_frames = p.block_size * 64;
+        size_t total = 0;
+        for (Py_ssize_t i = 0; i < n; i++) {
+            for (;;) {
+                PyObject *fl_obj = PyObject_CallMethod(rd[i]->obj, "read", "i", (int)read_frames);
+                if (!fl_obj) goto done;
+                if ((PyObject *)Py_TYPE(fl_obj) != rd[i]->framelist_type) {
+                    Py_DECREF(fl_obj);
+                    PyErr_SetString(PyExc_TypeError, "results from pcmreader.read() must be FrameLists");
+                    goto done;
+                }
+                pcm_FrameList *fl = (pcm_FrameList *)fl_obj;
+                if (fl->frames == 0) { Py_DECREF(fl_obj); break; }
+                if (fl->channels != p.channels || fl->bits_per_sample != p.bits_per_sample) {
+                    Py_DECREF(fl_obj);
+                    PyErr_SetString(PyExc_ValueError, "FrameList does not match the pcmreader's channels / bits_per_sample");
+                    goto done;
+                }
+                const size_t need = used[i] + (size_t)fl->samples_length * bytes_ps;
+                if (need > caps[i]) {
+                    size_t ncap = caps[i] ? caps[i] * 2 : (1u << 22);
+                    while (ncap < need) ncap *= 2;
+                    uint8_t *np_ = (uint8_t *)realloc(bufs[i], ncap);
+                    if (!np_) { Py_DECREF(fl_obj); PyErr_NoMemory(); goto done; }
+                    bufs[i] = np_; caps[i] = ncap;
+                }
+                pack_le_signed(fl, bufs[i] + used[i]);
+                used[i] = need;
+                frames[i] += fl->frames;
+                Py_DECREF(fl_obj);
+            }
+            total += (used[i] + 63) & ~(size_t)63;
+        }
+        /* one page-locked arena for all tracks: the engine copies to the device straight from it */
+        arena = (uint8_t *)b200flac_host_alloc(total ? total : 64);
+        if (!arena) { PyErr_SetString(PyExc_IOError, b200flac_last_error()); goto done; }
+        size_t off = 0;
+        for (Py_ssize_t i = 0; i < n; i++) {
+            if (used[i]) memcpy(arena + off, bufs[i], used[i]);
+            ptrs[i] = arena + off;
+            off += (used[i] + 63) & ~(size_t)63;
+            free(bufs[i]); bufs[i] = NULL;
+        }
+        int rc;
+        Py_BEGIN_ALLOW_THREADS
+        rc = b200flac_encode_files((uint32_t)n, c_names, &p, padding_size, NULL, ptrs, frames, -1, host_threads);
+        Py_END_ALLOW_THREADS
+        if (rc) {
+            const char *msg = b200flac_last_error();
+            const int bad_param = strstr(msg, "must be") != NULL || strstr(msg, "unsupported") != NULL;
+            PyErr_SetString(bad_param ? PyExc_ValueError : PyExc_IOError, msg);
+            goto done;
+        }
+    }
+    for (Py_ssize_t i = 0; i < n; i++) {
+        PyObject *r = PyObject_CallMethod(rd[i]->obj, "close", NULL);
+        if (!r) goto done;
+        Py_DECREF(r);
+    }
+    result = Py_None;
+    Py_INCREF(result);
+done:
+    if (arena) b200flac_host_free(arena);
+    for (Py_ssize_t i = 0; i < n; i++) {
+        if (rd && rd[i]) pcmreader_del(rd[i]);
+        if (name_bytes) Py_XDECREF(name_bytes[i]);
+        if (bufs) free(bufs[i]);
+    }
+    free(rd); free(name_bytes); free((void *)c_names); free(bufs); free(caps); free(used); free(frames); free((void *)ptrs);
+    Py_XDECREF(names);
+    Py_XDECREF(readers);
+    return result;
+}
+
 /* encode_tta(file, pcmreader) -> [frame size, ...]      src/encoders/tta.c:31-117
  * Same keyword names ("file", "pcmreader", tta.c:44-46), same protocol: block_size = sample_rate * 256 / 245
  * PCM frames are asked of the reader per call and WHATEVER comes back is one TTA frame (tta.c:69-83); the frames
@@ -539,6 +684,9 @@ static PyMethodDef module_methods[] = {
      "max_residual_partition_order, mid_side=0, adaptive_mid_side=0, exhaustive_model_search=0, "
      "disable_verbatim_subframes=0, disable_constant_subframes=0, disable_fixed_subframes=0, "
      "disable_lpc_subframes=0, padding_size=4096) -> [(byte_offset, pcm_frames), ...]"},
+    {"encode_flac_files", (PyCFunction)encoders_encode_flac_files, METH_VARARGS | METH_KEYWORDS,
+     "encode_flac_files(filenames, pcmreaders, block_size, max_lpc_order, min_residual_partition_order, "
+     "max_residual_partition_order, ...) -- many tracks in one call; every file equals encode_flac's"},
     {"encode_tta", (PyCFunction)encoders_encode_tta, METH_VARARGS | METH_KEYWORDS,
      "encode_tta(file, pcmreader) -> [frame_size, ...]: TTA frames written to file (src/encoders/tta.c:31-117)"},
     {"encode_alac", (PyCFunction)encoders_encode_alac, METH_VARARGS | METH_KEYWORDS,

@@ -226,3 +226,40 @@ def test_finalize_flac_metadata_extension_entry(tmp_path, built):
         encoders.finalize_flac_metadata(os.path.join(str(tmp_path), "nope.flac"), offsets)
     with pytest.raises(TypeError):
         encoders.finalize_flac_metadata(b, [("x", 1)])
+
+
+@pytest.mark.gpu
+def test_encode_flac_files_equals_encode_flac(tmp_path, built):
+    """audiotools.encoders.encode_flac_files (many tracks in one call): every file is byte
+    for byte what encode_flac writes for the same reader; readers are closed; mismatched readers are a ValueError"""
+    at = _at()
+    from audiotools import encoders
+    lengths = [30000, 4096 * 3, 1, 4097, 55555]
+    pcms = [helpers.synth_pcm(40 + i, 2, 16, n) for i, n in enumerate(lengths)]
+    opts = dict(block_size=4096, max_lpc_order=12, min_residual_partition_order=0, max_residual_partition_order=6,
+                mid_side=True, exhaustive_model_search=True, padding_size=2000)
+    want = []
+    for i, pcm in enumerate(pcms):
+        path = os.path.join(str(tmp_path), "one_%d.flac" % i)
+        encoders.encode_flac(path, pcmreader=at.BufferedPCMReader(at.PCMBytesReader(pcm, 44100, 2, 0x3, 16)), **opts)
+        want.append(open(path, "rb").read())
+
+    class Closing(at.PCMBytesReader):
+        closed = False
+
+        def close(self):
+            self.closed = True
+    names = [os.path.join(str(tmp_path), "many_%d.flac" % i) for i in range(len(pcms))]
+    readers = [Closing(pcm, 44100, 2, 0x3, 16) for pcm in pcms]
+    assert encoders.encode_flac_files(names, readers, host_threads=2, **opts) is None
+    for i, name in enumerate(names):
+        assert open(name, "rb").read() == want[i], "track %d" % i
+    assert all(r.closed for r in readers)
+    with pytest.raises(ValueError):
+        encoders.encode_flac_files(names[:2], [at.PCMBytesReader(pcms[0], 44100, 2, 0x3, 16),
+                                               at.PCMBytesReader(pcms[1], 48000, 2, 0x3, 16)], **opts)
+    with pytest.raises(ValueError):
+        encoders.encode_flac_files(names[:2], readers[:1], **opts)
+    with pytest.raises(IOError):
+        encoders.encode_flac_files([os.path.join(str(tmp_path), "no_such_dir", "x.flac")],
+                                   [at.PCMBytesReader(pcms[0], 44100, 2, 0x3, 16)], **opts)
