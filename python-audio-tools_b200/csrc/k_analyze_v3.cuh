@@ -527,8 +527,13 @@ __device__ __forceinline__ u64 v3_lpc_residual_f64(const int* __restrict__ samp,
             const int pred = __double2loint(__fma_rd(acc, scale, 6755399441055744.0));
             res[j] = (int)((u32)xs[j] - (u32)pred);
         }
+        {
+            // every |residual| is below 2^28 here (see is_f64): |a - 0| + c is one VABSDIFF
+            u32 cs = 0;
 #pragma unroll
-        for (int j = 0; j < V3_CH; j++) run += (u64)(u32)abs(res[j]);
+            for (int j = 0; j < V3_CH; j++) cs = __sad(res[j], 0, cs);
+            run += cs;
+        }
         *(int4*)(resid + V3_SK(i0)) = make_int4(res[0], res[1], res[2], res[3]);
         *(int4*)(resid + V3_SK(i0) + 4) = make_int4(res[4], res[5], res[6], res[7]);
 #pragma unroll
@@ -851,16 +856,21 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
     bool lpc_narrow = false;
     int lpc_shift = 0;
     // residual of order o with the coefficients staged in qs; s0 (and s1, SUB = 2) get the thread's run sum(s)
-    auto lpc_pass = [&](u32 o, int shift, bool narrow, const short* qs, u64& s0, u64& s1) {
+    // the FP64 pass (v3_lpc_residual_f64) takes wide sums of up to 12 taps: sub_bps <= 26 and |coefficient| < 2^15 keep
+    // every partial sum below 2^45; |prediction| <= sum|q| * 2^(sub_bps-1) >> shift < 2^27 keeps every |residual|
+    // below 2^28, so that it, too, may add eight of them up in 32 bits
+    auto is_f64 = [&](u32 sum_abs_q, int shift) -> bool {
+        return sub_bps <= 26 && shift >= 0 && (((u64)sum_abs_q << (sub_bps - 1)) >> shift) < (1ull << 27);
+    };
+    auto lpc_pass = [&](u32 o, int shift, bool narrow, bool f64ok, const short* qs, u64& s0, u64& s1) {
         u64 run;
         u64 first = 0;
         u64* h0 = &first;
         // (no 8-tap variant: a second hot copy of the residual loop costs more in instruction fetch than
         // the four extra multiply-adds of a padded low order cost on the otherwise idle FMA pipe)
         // (the exhaustive search walks every order, so there the 8-tap copy pays for itself)
-        // wide sums of up to 12 taps go through the FP64 pipe (exact: see v3_lpc_residual_f64); sub_bps <= 26 and
-        // |coefficient| < 2^15 keep every partial sum below 2^45, and shift >= 0
-        const bool f64 = !narrow && sub_bps <= 26 && shift >= 0;
+        // wide sums of up to 12 taps go through the FP64 pipe (exact: see v3_lpc_residual_f64 and is_f64)
+        const bool f64 = !narrow && f64ok;
         if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
                                  : f64 ? v3_lpc_residual_f64<8, SUB>(samp, resid, base, S, qs, shift, h0)
                                        : v3_lpc_residual<12, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
@@ -883,7 +893,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
         lpc_shift = sh.head.shift[lpc_order - 1];
         lpc_narrow = is_narrow(sh.lpc_narrow, lpc_shift);
         u64 s0, s1;
-        lpc_pass(lpc_order, lpc_shift, lpc_narrow, sh.q, s0, s1);
+        lpc_pass(lpc_order, lpc_shift, lpc_narrow, is_f64(sh.lpc_narrow, lpc_shift), sh.q, s0, s1);
         store_runs(s0, s1);
     }
     __syncthreads();                                                             // (2)
@@ -1022,7 +1032,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
                 const int shift = sh.head.shift[o - 1];
                 const bool narrow = is_narrow(sh.lpc_narrow2[o & 1], shift);
                 u64 s0, s1;
-                lpc_pass(o, shift, narrow, sh.q2[o & 1], s0, s1);
+                lpc_pass(o, shift, narrow, is_f64(sh.lpc_narrow2[o & 1], shift), sh.q2[o & 1], s0, s1);
                 if (warp == nw - 1 && o < L) stage(o + 1);      // (its buffer was last read by order o - 1's pass)
                 uint8_t* kb = kbuf(o);
                 v3_search_own<SUB>(s0, s1, o, F, n, P.max_rice, kb, parts + ((o & 1u) * 4u + warp) * V3_OWN_LEVELS,
@@ -1050,7 +1060,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
             const int shift = sh.head.shift[o - 1];
             const bool narrow = is_narrow(sh.lpc_narrow2[o & 1], shift);
             u64 s0, s1;
-            lpc_pass(o, shift, narrow, sh.q2[o & 1], s0, s1);
+            lpc_pass(o, shift, narrow, is_f64(sh.lpc_narrow2[o & 1], shift), sh.q2[o & 1], s0, s1);
             store_runs(s0, s1);
             if (warp == nw - 1 && o < L) stage(o + 1);      // (its buffer was last read by order o - 1's pass)
             __syncthreads();
