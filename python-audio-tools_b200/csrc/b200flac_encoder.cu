@@ -355,20 +355,27 @@ extern "C" void b200flac_encoder_destroy(b200flac_encoder* enc)
 
 static u32 lpc_maxl(u32 L) { return L <= 8 ? 8 : L <= 12 ? 12 : L <= 16 ? 16 : 32; }
 
-template <int MAXL>
+// staging mode of k_lpc_autoc for this stream shape (see the kernel)
+static int lpc_mode(const bf_dev_params& P)
+{
+    if (P.stereo && P.bytes_ps == 2) return 0;
+    return lpc_geometry(P.K, P.channels * P.bytes_ps, 13).bulk ? 1 : 2;
+}
+
+template <int MAXL, int MODE>
 static cudaError_t lpc_prepare_one(b200flac_encoder* enc, size_t smem)
 {
     // the opt-in limit is raised to the maximum so that a small batch can pad its request and
     // spread its few CTAs over all SMs (see launch_batch)
     const int lim = 200 * 1024;
-    cudaError_t e = cudaFuncSetAttribute(k_lpc_autoc<MAXL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaError_t e = cudaFuncSetAttribute(k_lpc_autoc<MAXL, 2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->lpc_occ[1], k_lpc_autoc<MAXL, 2>, 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->lpc_occ[1], k_lpc_autoc<MAXL, 2, MODE>, 32, smem);
     if (e != cudaSuccess) return e;
     if constexpr (MAXL <= 16) {
-        e = cudaFuncSetAttribute(k_lpc_autoc<MAXL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        e = cudaFuncSetAttribute(k_lpc_autoc<MAXL, 1, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->lpc_occ[0], k_lpc_autoc<MAXL, 1>, 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&enc->lpc_occ[0], k_lpc_autoc<MAXL, 1, MODE>, 32, smem);
     } else enc->lpc_occ[0] = 0;
     return e;
 }
@@ -379,8 +386,11 @@ static cudaError_t lpc_prepare(b200flac_encoder* enc)
     cudaDeviceGetAttribute(&enc->n_sms, cudaDevAttrMultiProcessorCount, enc->device);
     const u32 maxl = lpc_maxl(P.max_lpc_order);
     const size_t smem = lpc_geometry(P.K, P.channels * P.bytes_ps, maxl + 1).smem_bytes;
-    return maxl == 8 ? lpc_prepare_one<8>(enc, smem) : maxl == 12 ? lpc_prepare_one<12>(enc, smem)
-         : maxl == 16 ? lpc_prepare_one<16>(enc, smem) : lpc_prepare_one<32>(enc, smem);
+#define LPC_PREP(MODE_) (maxl == 8 ? lpc_prepare_one<8, MODE_>(enc, smem) : maxl == 12 ? lpc_prepare_one<12, MODE_>(enc, smem) \
+                         : maxl == 16 ? lpc_prepare_one<16, MODE_>(enc, smem) : lpc_prepare_one<32, MODE_>(enc, smem))
+    const int mode = lpc_mode(P);
+    return mode == 0 ? LPC_PREP(0) : mode == 1 ? LPC_PREP(1) : LPC_PREP(2);
+#undef LPC_PREP
 }
 
 template <int S>
@@ -928,7 +938,12 @@ static void stage_model(b200flac_encoder* enc, const ChunkView& v, cudaStream_t 
             if (pad > lsm) lsm = pad < (size_t)(200 * 1024) ? pad : (size_t)(200 * 1024);
         }
     }
-#define LPC_LAUNCH(MAXL_, G_) k_lpc_autoc<MAXL_, G_><<<grid, 32, lsm, st>>>(d_pcm, v.fd, v.nf, d_win, P, v.tasks, n_tasks, v.ticket, v.autoc, v.wasted)
+    const int mode = lpc_mode(P);
+#define LPC_LAUNCH(MAXL_, G_) do { \
+        if (mode == 0) k_lpc_autoc<MAXL_, G_, 0><<<grid, 32, lsm, st>>>(d_pcm, v.fd, v.nf, d_win, P, v.tasks, n_tasks, v.ticket, v.autoc, v.wasted); \
+        else if (mode == 1) k_lpc_autoc<MAXL_, G_, 1><<<grid, 32, lsm, st>>>(d_pcm, v.fd, v.nf, d_win, P, v.tasks, n_tasks, v.ticket, v.autoc, v.wasted); \
+        else k_lpc_autoc<MAXL_, G_, 2><<<grid, 32, lsm, st>>>(d_pcm, v.fd, v.nf, d_win, P, v.tasks, n_tasks, v.ticket, v.autoc, v.wasted); \
+    } while (0)
     if (maxl == 8) { if (split) LPC_LAUNCH(8, 2); else LPC_LAUNCH(8, 1); }
     else if (maxl == 12) { if (split) LPC_LAUNCH(12, 2); else LPC_LAUNCH(12, 1); }
     else if (maxl == 16) { if (split) LPC_LAUNCH(16, 2); else LPC_LAUNCH(16, 1); }

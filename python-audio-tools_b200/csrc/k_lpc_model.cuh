@@ -334,10 +334,18 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
                 const int L = ld_pcm(row, t * 2, B), R = ld_pcm(row, t * 2 + 1, B);
                 return cand == 0 ? L : cand == 1 ? R : cand == 2 ? ((L + R) >> 1) : (L - R);
             };
+            // Anything but 16-bit stereo: the rotation's samples are unpacked ONCE, ahead of the two variants of the
+            // loop below -- unpacking inside both put 29 KB of hot code into sixteen independent warps per SM
+            // (`no_instruction` 1.5 stalls per issue at 24 bits).  The 16-bit pair's two instructions stay where they were.
+            int pre[FAST ? 1 : H];
+            if constexpr (!FAST) {
+#pragma unroll
+                for (int u = 0; u < H; u++) pre[u] = (full || (ig + u < n)) ? fetch(tbase + u) : 0;
+            }
             if (flat) {
 #pragma unroll
                 for (int u = 0; u < H; u++) {
-                    const int sv = fetch(tbase + u);
+                    const int sv = FAST ? fetch(tbase + u) : pre[FAST ? 0 : u];
                     if (LB == 0) orv |= (u32)sv;
                     const double x = int2double_exact(sv);
                     hist[u] = x;
@@ -354,7 +362,7 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
 #pragma unroll
                 for (int u = 0; u < H; u++) {
                     const bool in = full || (ig + u < n);
-                    const int sv = in ? fetch(tbase + u) : 0;
+                    const int sv = FAST ? (in ? fetch(tbase + u) : 0) : pre[FAST ? 0 : u];
                     if (LB == 0) orv |= (u32)sv;
                     const double x = in ? __dmul_rn(int2double_exact(sv), wp[u]) : 0.0;
                     hist[u] = x;
@@ -380,7 +388,10 @@ __device__ __forceinline__ void autoc_task(const uint8_t* __restrict__ pcm, cons
 // G: lag groups a unit is split into (1 or 2; MAXL = 32 always uses 2 -- 33 sums and their ring do
 // not fit the register file).  Large batches use G = 1 (the unpack/window work is not duplicated),
 // small ones G = 2 (half the sequential work per thread, twice the warps).
-template <int MAXL, int G>
+// MODE: 0 = 16-bit stereo (one 32-bit load and a dot product per sample), 1 = any other shape with bulk staging,
+// 2 = per-lane staging (K < 4).  One kernel per mode: each gets its own register allocation -- the unpacking of the
+// general shapes costs 30 registers the 16-bit kernel must not pay in resident warps -- and a third of the code.
+template <int MAXL, int G, int MODE>
 __global__ void __launch_bounds__(32, LPC_MIN_CTAS)
 k_lpc_autoc(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ fd, u32 n_frames,
             const double* __restrict__ windows, bf_dev_params P, const bf_lpc_task* __restrict__ tasks,
@@ -391,9 +402,8 @@ k_lpc_autoc(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ f
     constexpr int NL0 = (G == 1) ? MAXL + 1 : (MAXL + 2) / 2, NL1 = MAXL + 1 - NL0;
     const int lane = threadIdx.x & 31;
     const LpcGeom g = lpc_geometry(P.K, P.channels * P.bytes_ps, MAXL + 1);
-    const bool st16 = P.stereo && P.bytes_ps == 2;
     u32 phase[2] = {0u, 0u};        // parity of the next completion of each tile buffer's mbarrier
-    if (g.bulk) {
+    if (MODE != 2) {
         LpcStageHdr* hdr = (LpcStageHdr*)lpc_smem;
         if (lane == 0) { mbar_init(&hdr->bar[0], 1); mbar_init(&hdr->bar[1], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -401,9 +411,7 @@ k_lpc_autoc(const uint8_t* __restrict__ pcm, const bf_frame_desc* __restrict__ f
     }
 #define AUTOC_TASK(LB_, NL_) \
     do { \
-        if (st16) autoc_task<LB_, NL_, true, true>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out, phase); \
-        else if (g.bulk) autoc_task<LB_, NL_, false, true>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out, phase); \
-        else autoc_task<LB_, NL_, false, false>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out, phase); \
+        autoc_task<LB_, NL_, MODE == 0, MODE != 2>(pcm, fd, windows, P, g, tk.first_frame, tk.n_frames, lpc_smem, autoc_out, MAXL + 1, wasted_out, phase); \
     } while (0)
     for (;;) {
         u32 t = 0;
