@@ -881,11 +881,13 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
                                               : v3_lpc_residual<32, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
         else run = 0;       // (unreachable: the host launches this instantiation for max_lpc_order <= 12 only)
         if (SUB == 2) { s0 = first; s1 = run; } else { s0 = run; s1 = 0; }
-        if (tid == 0) {
-            u64 warm = 0;
-#pragma unroll 1
-            for (u32 i = 0; i < o; i++) warm += (u64)(u32)abs(resid[V3_SK(i)]);   // warm-up positions (o <= 32 / SUB)
-            s0 -= warm;
+        if (warp == 0) {
+            // the warm-up positions (o <= 32 / SUB, all in thread 0's run) do not count: one lane each instead of a
+            // loop in thread 0 that every other warp of the CTA ends up waiting for
+            __syncwarp();
+            const u32 a = lane < o ? (u32)abs(resid[V3_SK(lane)]) : 0u;
+            const u64 warm = (u64)__reduce_add_sync(0xFFFFFFFFu, a & 0xFFFFu) + ((u64)__reduce_add_sync(0xFFFFFFFFu, a >> 16) << 16);
+            if (tid == 0) s0 -= warm;
         }
     };
     auto store_runs = [&](u64 s0, u64 s1) { runsL[SUB * tid] = s0; if (SUB == 2) runsL[2 * tid + 1] = s1; };
@@ -944,7 +946,15 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
             const u32 k = kh[(1u << po) - 1u + ((pF + h) >> (F - po))];
             const u32 skip = (tid == 0 && h == 0) ? 1u : 0u;
             acc += fixed ? v3_fixed_bits_any(samp, base + h * len, len, k, order, skip)
-                         : v3_stored_bits(resid, base + h * len, len, k, skip ? order : 0u);
+                         : v3_stored_bits(resid, base + h * len, len, k, 0u);
+        }
+        if (!fixed && warp == 0) {
+            // LPC: the warm-up positions (all in partition 0, thread 0's run) were counted above; take them back
+            // out, one lane each (thread 0 alone looped over them while the CTA waited)
+            const u32 k0 = kh[(1u << po) - 1u];
+            const u32 v = lane < order ? (zigzag(resid[V3_SK(lane)]) >> k0) : 0u;
+            const u32 sub = __reduce_add_sync(0xFFFFFFFFu, v);
+            if (tid == 0) acc -= sub;
         }
         return acc;
     };
