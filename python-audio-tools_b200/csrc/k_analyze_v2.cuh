@@ -26,25 +26,22 @@
 // max_rice is 30 there.)
 __device__ __forceinline__ u64 partition_estimate_fast(u32 plength, u64 S_, u32 max_rice, u32* k_out)
 {
-    u32 k;
-    if (S_ <= (u64)plength) {
-        k = 0;
-    } else if (plength == 0 || S_ >= (1ull << 31)) {
-        return partition_estimate(plength, S_, max_rice, k_out);
-    } else {
-        // smallest k with (plength << k) >= S_: with a, b the bit lengths of S_ and plength (a >= b here),
-        // plength << (a - b - 1) < 2^(a-1) <= S_ and plength << (a - b + 1) >= 2^a > S_, so it is a - b or a - b + 1;
-        // everything fits 32 bits (plength << (a - b) < 2^a <= 2^31)
-        const u32 s32 = (u32)S_;
+    if (plength == 0 || S_ >= (1ull << 31)) return partition_estimate(plength, S_, max_rice, k_out);
+    // from here on everything fits 32 bits: S < 2^31, and the estimate is at most 4 + 2 S + 32 plength
+    const u32 s32 = (u32)S_;
+    u32 k = 0;
+    if (s32 > plength) {
+        // smallest k with (plength << k) >= S: with a, b the bit lengths of S and plength (a >= b here),
+        // plength << (a - b - 1) < 2^(a-1) <= S and plength << (a - b + 1) >= 2^a > S, so it is a - b or a - b + 1
         u32 kc = (u32)(__clz((int)plength) - __clz((int)s32));
         if ((plength << kc) < s32) kc++;
         k = kc < max_rice ? kc : max_rice;
     }
-    u64 est;
-    if (k > 0) est = 4ull + (S_ >> (k - 1)) + (u64)(u32)((1u + k) * plength) - (u64)(plength / 2);
-    else       est = 4ull + (S_ << 1) + (u64)plength - (u64)(plength / 2);
     *k_out = k;
-    return est;
+    // k > 0: 4 + (S >> (k - 1)) + (1 + k) plength - plength / 2;  k == 0: 4 + 2 S + plength - plength / 2
+    // (S >> (k - 1) may exceed 32 bits only when k was clamped to max_rice with a huge S: widened below)
+    const u32 tail = 4u + (1u + k) * plength - (plength >> 1);
+    return (u64)tail + (k ? (u64)(s32 >> (k - 1)) : ((u64)s32 << 1));
 }
 
 // shared scratch of the Rice search (double buffered by search parity, see rice_search_v2)

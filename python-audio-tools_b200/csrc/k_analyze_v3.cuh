@@ -32,6 +32,14 @@
 #else
 #define V3_LOOP
 #endif
+#ifndef V3_F64_UNROLL
+#define V3_F64_UNROLL 2
+#endif
+#if V3_F64_UNROLL == 2
+#define V3_F64_LOOP _Pragma("unroll 2")
+#else
+#define V3_F64_LOOP _Pragma("unroll 1")
+#endif
 #define V3_SK(i) ((i) + (((i) >> 5) << 2))      // four words of skew per 32 samples
 // Finest partition order handled: 7 (<= 128 partitions, one or more whole thread runs each), or 8 in the SUB = 2
 // instantiations, where a thread's run of 32 samples is TWO finest partitions of 16 and every run sum is kept per
@@ -510,7 +518,9 @@ __device__ __forceinline__ u64 v3_lpc_residual_f64(const int* __restrict__ samp,
     }
     const double scale = __hiloint2double((1023 - shift) << 20, 0);      // 2^-shift
     u64 run = 0;
-    V3_LOOP
+    // (two chunks per iteration: the window of 8 + 8 doubles is back in place after 16 samples, that of 12 + 8
+    // has moved by 4 -- half or none of the 2 x OG register moves a single-chunk loop pays per chunk)
+    V3_F64_LOOP
     for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
         if (SUB == 2 && i0 == base + (S >> 1)) { *half0 = run; run = 0; }
         const int4 va = *(const int4*)(samp + V3_SK(i0));
