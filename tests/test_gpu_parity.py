@@ -635,3 +635,24 @@ def test_encode_files_equals_encode_file(shape, tmp_path, built):
     # and the hash in the STREAMINFO is the MD5 of the PCM (flac.c:187-188)
     for i, name in enumerate(names):
         assert open(name, "rb").read()[26:42] == hashlib.md5(pcms[i]).digest()
+
+
+def test_encode_files_error_then_reuse(tmp_path, built):
+    """a file that cannot be written fails the job (no hang, the other files are still produced or not -- unspecified),
+    and the next job on the same cached context works"""
+    b = _b200()
+    o = helpers.options(block_size=4096, max_lpc_order=8, max_residual_partition_order=4)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 2, 16, **kw)
+    lengths = [9000, 12000, 5000]
+    pcms = [helpers.synth_pcm(900 + i, 2, 16, n) for i, n in enumerate(lengths)]
+    bufs = [np.frombuffer(pcm, dtype=np.uint8).copy() for pcm in pcms]
+    names = [os.path.join(str(tmp_path), "a.flac"), os.path.join(str(tmp_path), "missing_dir", "b.flac"),
+             os.path.join(str(tmp_path), "c.flac")]
+    with pytest.raises(Exception):
+        b.encode_files(names, p, bufs, lengths, device=0, host_threads=2)
+    names[1] = os.path.join(str(tmp_path), "b.flac")
+    b.encode_files(names, p, bufs, lengths, device=0, host_threads=2)
+    for name, pcm in zip(names, pcms):
+        assert open(name, "rb").read() == helpers.oracle_encode(pcm, 44100, 2, 16, o)
+    b.lib().b200flac_pool_clear()
