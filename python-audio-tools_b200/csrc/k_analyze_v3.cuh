@@ -437,7 +437,10 @@ __device__ __forceinline__ void v3_fixed_head(const int* __restrict__ samp, u32 
 // SUB = 2: the sum of the first half run goes to *half0 when the half ends, the second half's is returned.
 #define V3_ACC_I32 0
 #define V3_ACC_I64 1
-template <int OG, int WIDE, int SUB>
+// UNR: chunks per loop iteration (2 in the exhaustive 128 x 32 kernel of partition orders <= 7 -- level 8's --, whose
+// instruction cache has room; at order 8, 24-bit territory, the narrow pass is cold code and only costs space: the history window is
+// back in place after 16 samples at 8 taps and has moved by 4 at 12 -- none or half of the register moves per chunk).
+template <int OG, int WIDE, int SUB, int UNR = 1>
 __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int* __restrict__ resid, u32 base, u32 S,
                                                const short* q_sm, int shift, u64* __restrict__ half0)
 {
@@ -454,7 +457,10 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
     }
     u64 run = 0;
     V3_LOOP
-    for (u32 i0 = base; i0 < base + S; i0 += V3_CH) {
+    for (u32 ib = base; ib < base + S; ib += UNR * V3_CH) {
+#pragma unroll
+      for (int un = 0; un < UNR; un++) {
+        const u32 i0 = ib + un * V3_CH;
         if (SUB == 2 && i0 == base + (S >> 1)) { *half0 = run; run = 0; }
         const int4 va = *(const int4*)(samp + V3_SK(i0));
         const int4 vb = *(const int4*)(samp + V3_SK(i0) + 4);
@@ -491,6 +497,7 @@ __device__ __forceinline__ u64 v3_lpc_residual(const int* __restrict__ samp, int
         *(int4*)(resid + V3_SK(i0) + 4) = make_int4(res[4], res[5], res[6], res[7]);
 #pragma unroll
         for (int t = 0; t < OG; t++) w[t] = w[t + V3_CH];
+      }
     }
     return run;
 }
@@ -881,10 +888,10 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
         // (the exhaustive search walks every order, so there the 8-tap copy pays for itself)
         // wide sums of up to 12 taps go through the FP64 pipe (exact: see v3_lpc_residual_f64 and is_f64)
         const bool f64 = !narrow && f64ok;
-        if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
+        if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, V3_ACC_I32, SUB, (SC == 32 && SUB == 1 ? 2 : 1)>(samp, resid, base, S, qs, shift, h0)
                                  : f64 ? v3_lpc_residual_f64<8, SUB>(samp, resid, base, S, qs, shift, h0)
                                        : v3_lpc_residual<12, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
-        else if (o <= 12) run = narrow ? v3_lpc_residual<12, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
+        else if (o <= 12) run = narrow ? v3_lpc_residual<12, V3_ACC_I32, SUB, (EXH && SC == 32 && SUB == 1 ? 2 : 1)>(samp, resid, base, S, qs, shift, h0)
                                 : f64 ? v3_lpc_residual_f64<12, SUB>(samp, resid, base, S, qs, shift, h0)
                                       : v3_lpc_residual<12, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
         else if constexpr (LONG) run = narrow ? v3_lpc_residual<32, V3_ACC_I32, SUB>(samp, resid, base, S, qs, shift, h0)
