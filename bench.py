@@ -266,7 +266,9 @@ def resident_config(b200flac, L, dev, rank, world, barrier, allmax, name, rate, 
     dom = max(range(5), key=lambda i: kms[i])
     res = {"workload": name + ", %.0f s per GPU per step" % seconds,
            "value": world * n * ch * steps / dt / 1e6, "unit": UNIT, "ms_per_step": 1000.0 * dt / steps,
-           "device_ms_per_step": dev_ms / steps, "compressed_ratio": out_bytes / nbytes,
+           "device_ms_per_step": dev_ms / steps, "best_ms_per_step": 1000.0 * min(walls),
+           "device_value": n * ch / (dev_ms / steps) / 1e3,      # this rank's samples / CUDA-event time of its kernels
+           "compressed_ratio": out_bytes / nbytes,
            "kernel_ms": dict(zip(names, kms)),
            "roofline": {"bound": "hbm", "kernel": names[dom], "peak": peak, "unit": "GB/s", "peak_kind": peak_kind,
                         "algorithmic_bytes_per_launch": algo,

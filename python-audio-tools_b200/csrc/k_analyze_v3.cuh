@@ -406,31 +406,6 @@ __device__ __forceinline__ void v3_fixed_sums(const int* __restrict__ samp, u32 
     e[0] = f0; e[1] = f1; e[2] = f2; e[3] = f3; e[4] = f4;
 }
 
-// run 0 only: the reference sums the errors from sample 4 for every order, so take samples 0..3
-// (as v3_fixed_sums counted them, with zero history) out of e[], and collect in corr[k] the true
-// residuals |r_k[i]|, k <= i < 4, which the partition sums of order k do contain
-// (returned in g[], the caller subtracts them from run 0's -- or half run 0's -- sums)
-__device__ __forceinline__ void v3_fixed_head(const int* __restrict__ samp, u32 (&g)[5], u64* corr)
-{
-    const int4 v = *(const int4*)samp;
-    const u32 xs[4] = {(u32)v.x, (u32)v.y, (u32)v.z, (u32)v.w};
-    u32 prev = 0, p1 = 0, p2 = 0, p3 = 0;
-    u32 c[5] = {0, 0, 0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < 5; k++) g[k] = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const u32 x = xs[j];
-        const u32 d1 = x - prev, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
-        const u32 a[5] = {(u32)abs((int)x), (u32)abs((int)d1), (u32)abs((int)d2), (u32)abs((int)d3), (u32)abs((int)d4)};
-#pragma unroll
-        for (int k = 0; k < 5; k++) { g[k] += a[k]; if (j >= k) c[k] += a[k]; }
-        prev = x; p1 = d1; p2 = d2; p3 = d3;
-    }
-#pragma unroll
-    for (int k = 0; k < 5; k++) corr[k] = (u64)c[k];
-}
-
 // LPC residual of the thread's run (flac.c:999-1008) into resid, chunks of 8, history window in
 // registers; returns the run's sum of |r|.  OG: taps (coefficients zero-padded, exact).
 // WIDE: 64-bit accumulate, otherwise 32-bit (only chosen when the sum provably fits).
@@ -578,6 +553,24 @@ __device__ __forceinline__ V3FixedCoef v3_fixed_coef(u32 order)
     c.c3 = order < 3 ? 0 : order == 3 ? -1 : -4;
     c.c4 = order == 4 ? 1 : 0;
     return c;
+}
+
+// Run 0 only: the reference sums the errors from sample 4 on for every order, so samples 0..3 (as v3_fixed_sums
+// counted them, with zero history) come out of thread 0's sums again -- g -- while the true residuals |r_k[i]|,
+// k <= i < 4, which the partition sums of order k do contain, are collected in c.  Lane k of a warp does order k
+// (closed form of the differences, zeros before the block): a fifth of the instructions thread 0 alone spent on it,
+// and of the hot code.
+__device__ __forceinline__ void v3_fixed_head_lane(const int* __restrict__ samp, u32 k, u32& g, u32& c)
+{
+    const int4 v = *(const int4*)samp;
+    const V3FixedCoef f = v3_fixed_coef(min(k, 4u));
+    const int r0 = v.x;
+    const int r1 = v.y + f.c1 * v.x;
+    const int r2 = v.z + f.c1 * v.y + f.c2 * v.x;
+    const int r3 = v.w + f.c1 * v.z + f.c2 * v.y + f.c3 * v.x;
+    const u32 a0 = (u32)abs(r0), a1 = (u32)abs(r1), a2 = (u32)abs(r2), a3 = (u32)abs(r3);
+    g = a0 + a1 + a2 + a3;
+    c = (k == 0 ? a0 : 0u) + (k <= 1 ? a1 : 0u) + (k <= 2 ? a2 : 0u) + (k <= 3 ? a3 : 0u);
 }
 
 // sum of (zigzag(r) >> k) over the thread's run for the FIXED residual of `order`, recomputed from the
@@ -805,11 +798,15 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
             } else {
                 v3_fixed_sums<u64, SUB>(samp, base, S, ownE, ownH, 1);
             }
-            if (tid == 0) {
-                u32 g[5];
-                v3_fixed_head(samp, g, sh.corr);
+            if (warp == 0) {
+                u32 g, c;
+                v3_fixed_head_lane(samp, lane, g, c);
+                if (lane < 5) sh.corr[lane] = (u64)c;
 #pragma unroll
-                for (int k = 0; k < 5; k++) { if (SUB == 2) ownH[k] -= (u64)g[k]; else ownE[k] -= (u64)g[k]; }
+                for (int k = 0; k < 5; k++) {
+                    const u32 gk = __shfl_sync(0xFFFFFFFFu, g, k);
+                    if (tid == 0) { if (SUB == 2) ownH[k] -= (u64)gk; else ownE[k] -= (u64)gk; }
+                }
             }
 #pragma unroll
             for (int k = 0; k < 5; k++) {
@@ -836,11 +833,12 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
 #pragma unroll
             for (int k = 0; k < 5; k++) mine[k * R + (SUB - 1)] = e[k];
         }
-        if (tid == 0) {
-            u32 g[5];
-            v3_fixed_head(samp, g, sh.corr);
-#pragma unroll
-            for (int k = 0; k < 5; k++) runsF[k * R] -= (u64)g[k];
+        if (warp == 0) {
+            __syncwarp();                   // thread 0's sums are in shared memory
+            u32 g, c;
+            v3_fixed_head_lane(samp, lane, g, c);
+            if (lane < 5) { runsF[lane * R] -= (u64)g; sh.corr[lane] = (u64)c; }
+            __syncwarp();                   // ... and corrected before it reads them back
         }
         // block totals; each thread reads its own sums back, one rolled copy of the reduction for the five orders
         if (sub_bps <= 23) {
@@ -879,7 +877,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
     auto is_f64 = [&](u32 sum_abs_q, int shift) -> bool {
         return sub_bps <= 26 && shift >= 0 && (((u64)sum_abs_q << (sub_bps - 1)) >> shift) < (1ull << 27);
     };
-    auto lpc_pass = [&](u32 o, int shift, bool narrow, bool f64ok, const short* qs, u64& s0, u64& s1) {
+    auto lpc_pass = [&](u32 o, int shift, bool narrow, u32 sum_abs_q, const short* qs, u64& s0, u64& s1) {
         u64 run;
         u64 first = 0;
         u64* h0 = &first;
@@ -887,7 +885,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
         // the four extra multiply-adds of a padded low order cost on the otherwise idle FMA pipe)
         // (the exhaustive search walks every order, so there the 8-tap copy pays for itself)
         // wide sums of up to 12 taps go through the FP64 pipe (exact: see v3_lpc_residual_f64 and is_f64)
-        const bool f64 = !narrow && f64ok;
+        const bool f64 = !narrow && is_f64(sum_abs_q, shift);
         if (EXH && o <= 8) run = narrow ? v3_lpc_residual<8, V3_ACC_I32, SUB, (SC == 32 && SUB == 1 ? 2 : 1)>(samp, resid, base, S, qs, shift, h0)
                                  : f64 ? v3_lpc_residual_f64<8, SUB>(samp, resid, base, S, qs, shift, h0)
                                        : v3_lpc_residual<12, V3_ACC_I64, SUB>(samp, resid, base, S, qs, shift, h0);
@@ -912,7 +910,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
         lpc_shift = sh.head.shift[lpc_order - 1];
         lpc_narrow = is_narrow(sh.lpc_narrow, lpc_shift);
         u64 s0, s1;
-        lpc_pass(lpc_order, lpc_shift, lpc_narrow, is_f64(sh.lpc_narrow, lpc_shift), sh.q, s0, s1);
+        lpc_pass(lpc_order, lpc_shift, lpc_narrow, sh.lpc_narrow, sh.q, s0, s1);
         store_runs(s0, s1);
     }
     __syncthreads();                                                             // (2)
@@ -1059,7 +1057,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
                 const int shift = sh.head.shift[o - 1];
                 const bool narrow = is_narrow(sh.lpc_narrow2[o & 1], shift);
                 u64 s0, s1;
-                lpc_pass(o, shift, narrow, is_f64(sh.lpc_narrow2[o & 1], shift), sh.q2[o & 1], s0, s1);
+                lpc_pass(o, shift, narrow, sh.lpc_narrow2[o & 1], sh.q2[o & 1], s0, s1);
                 if (warp == nw - 1 && o < L) stage(o + 1);      // (its buffer was last read by order o - 1's pass)
                 uint8_t* kb = kbuf(o);
                 v3_search_own<SUB>(s0, s1, o, F, n, P.max_rice, kb, parts + ((o & 1u) * 4u + warp) * V3_OWN_LEVELS,
@@ -1087,7 +1085,7 @@ __device__ __forceinline__ void v3_unit(unsigned char* dyn_smem, V3SharedT<(SUB 
             const int shift = sh.head.shift[o - 1];
             const bool narrow = is_narrow(sh.lpc_narrow2[o & 1], shift);
             u64 s0, s1;
-            lpc_pass(o, shift, narrow, is_f64(sh.lpc_narrow2[o & 1], shift), sh.q2[o & 1], s0, s1);
+            lpc_pass(o, shift, narrow, sh.lpc_narrow2[o & 1], sh.q2[o & 1], s0, s1);
             store_runs(s0, s1);
             if (warp == nw - 1 && o < L) stage(o + 1);      // (its buffer was last read by order o - 1's pass)
             __syncthreads();
