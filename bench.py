@@ -734,7 +734,7 @@ def main():
             def batch_job(k):
                 if L.b200flac_encode_files(k, c_names, C.byref(p8), 4096, None, c_ptrs, c_lens, dev, threads):
                     raise SystemExit("b200flac_encode_files failed: " + L.b200flac_last_error().decode())
-            batch_job(min(my_tracks, 64))           # warm-up: device ring, pinned buffers, encoder
+            batch_job(my_tracks)                    # warm-up: the device ring (one region per batch in flight), pinned buffers, encoder
             barrier()
             t0 = time.perf_counter()
             batch_job(my_tracks)
