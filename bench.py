@@ -752,7 +752,8 @@ def main():
                 "projected_s_for_10000_tracks": 10000.0 * t_bt / total_tracks, "identical_to_encode_file": True,
                 "speedup_over_one_call_per_file": t_tr / t_bt,
                 "what": "the same tracks as ONE b200flac_encode_files job per rank: many-segment batches of the frame "
-                        "layer, every track's STREAMINFO MD5 computed on the device (one thread per track), %d host "
+                        "layer, the tracks' STREAMINFO MD5s computed on the device (one thread per track, whole batches from the "
+                        "front of the list) and by idle pool threads (single tracks from its end), %d host "
                         "threads write the files to tmpfs; PCM read from page-locked memory" % threads}
 
     # ---- the other BASELINE configurations, device resident ----

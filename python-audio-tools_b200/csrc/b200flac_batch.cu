@@ -27,6 +27,9 @@
 #include "../../include/b200flac.h"
 
 extern "C" void b200flac_internal_set_error(const char* msg);                       // b200flac_encoder.cu
+extern "C" void b200flac_internal_md5_begin(void* state);                           // b200flac_stream.cu (96-byte state)
+extern "C" void b200flac_internal_md5_update(void* state, const uint8_t* p, size_t n);
+extern "C" void b200flac_internal_md5_end(void* state, uint8_t out[16]);
 void b200flac_internal_stream_head(const b200flac_params* params, uint32_t padding_size, const char* version,
                                    uint32_t min_frame, uint32_t max_frame, uint64_t total_samples,
                                    const uint8_t md5[16], std::vector<uint8_t>& head);  // b200flac_stream.cu
@@ -39,6 +42,12 @@ typedef unsigned long long u64;
 // (off 16-byte aligned).  Same round formulation as the host's md5_block (b200flac_stream.cu).
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ u32 md5_rol(u32 x, int s) { return __funnelshift_l(x, x, s); }
+__device__ __forceinline__ u32 md5_pre(u32 w, u32 xi, u32 k)
+{
+    u32 r;
+    asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(r) : "r"(xi), "r"(k), "r"(w));
+    return r;
+}
 
 __device__ __forceinline__ void md5_rounds(u32& a, u32& b, u32& c, u32& d, const u32 (&x)[16])
 {
@@ -47,39 +56,42 @@ __device__ __forceinline__ void md5_rounds(u32& a, u32& b, u32& c, u32& d, const
 #define MF2(x_, y, z) ((x_ & z) + (y & ~z))
 #define MF3(x_, y, z) (x_ ^ (y ^ z))
 #define MF4(x_, y, z) (y ^ (x_ | ~z))
-#define MSTEP(f, w, x_, y, z, data, s) (w = (w + (data)) + f(x_, y, z), w = md5_rol(w, s) + x_)
-    MSTEP(MF1, a, b, c, d, x[0] + 0xd76aa478u, 7);   MSTEP(MF1, d, a, b, c, x[1] + 0xe8c7b756u, 12);
-    MSTEP(MF1, c, d, a, b, x[2] + 0x242070dbu, 17);  MSTEP(MF1, b, c, d, a, x[3] + 0xc1bdceeeu, 22);
-    MSTEP(MF1, a, b, c, d, x[4] + 0xf57c0fafu, 7);   MSTEP(MF1, d, a, b, c, x[5] + 0x4787c62au, 12);
-    MSTEP(MF1, c, d, a, b, x[6] + 0xa8304613u, 17);  MSTEP(MF1, b, c, d, a, x[7] + 0xfd469501u, 22);
-    MSTEP(MF1, a, b, c, d, x[8] + 0x698098d8u, 7);   MSTEP(MF1, d, a, b, c, x[9] + 0x8b44f7afu, 12);
-    MSTEP(MF1, c, d, a, b, x[10] + 0xffff5bb1u, 17); MSTEP(MF1, b, c, d, a, x[11] + 0x895cd7beu, 22);
-    MSTEP(MF1, a, b, c, d, x[12] + 0x6b901122u, 7);  MSTEP(MF1, d, a, b, c, x[13] + 0xfd987193u, 12);
-    MSTEP(MF1, c, d, a, b, x[14] + 0xa679438eu, 17); MSTEP(MF1, b, c, d, a, x[15] + 0x49b40821u, 22);
-    MSTEP(MF2, a, b, c, d, x[1] + 0xf61e2562u, 5);   MSTEP(MF2, d, a, b, c, x[6] + 0xc040b340u, 9);
-    MSTEP(MF2, c, d, a, b, x[11] + 0x265e5a51u, 14); MSTEP(MF2, b, c, d, a, x[0] + 0xe9b6c7aau, 20);
-    MSTEP(MF2, a, b, c, d, x[5] + 0xd62f105du, 5);   MSTEP(MF2, d, a, b, c, x[10] + 0x02441453u, 9);
-    MSTEP(MF2, c, d, a, b, x[15] + 0xd8a1e681u, 14); MSTEP(MF2, b, c, d, a, x[4] + 0xe7d3fbc8u, 20);
-    MSTEP(MF2, a, b, c, d, x[9] + 0x21e1cde6u, 5);   MSTEP(MF2, d, a, b, c, x[14] + 0xc33707d6u, 9);
-    MSTEP(MF2, c, d, a, b, x[3] + 0xf4d50d87u, 14);  MSTEP(MF2, b, c, d, a, x[8] + 0x455a14edu, 20);
-    MSTEP(MF2, a, b, c, d, x[13] + 0xa9e3e905u, 5);  MSTEP(MF2, d, a, b, c, x[2] + 0xfcefa3f8u, 9);
-    MSTEP(MF2, c, d, a, b, x[7] + 0x676f02d9u, 14);  MSTEP(MF2, b, c, d, a, x[12] + 0x8d2a4c8au, 20);
-    MSTEP(MF3, a, b, c, d, x[5] + 0xfffa3942u, 4);   MSTEP(MF3, d, a, b, c, x[8] + 0x8771f681u, 11);
-    MSTEP(MF3, c, d, a, b, x[11] + 0x6d9d6122u, 16); MSTEP(MF3, b, c, d, a, x[14] + 0xfde5380cu, 23);
-    MSTEP(MF3, a, b, c, d, x[1] + 0xa4beea44u, 4);   MSTEP(MF3, d, a, b, c, x[4] + 0x4bdecfa9u, 11);
-    MSTEP(MF3, c, d, a, b, x[7] + 0xf6bb4b60u, 16);  MSTEP(MF3, b, c, d, a, x[10] + 0xbebfbc70u, 23);
-    MSTEP(MF3, a, b, c, d, x[13] + 0x289b7ec6u, 4);  MSTEP(MF3, d, a, b, c, x[0] + 0xeaa127fau, 11);
-    MSTEP(MF3, c, d, a, b, x[3] + 0xd4ef3085u, 16);  MSTEP(MF3, b, c, d, a, x[6] + 0x04881d05u, 23);
-    MSTEP(MF3, a, b, c, d, x[9] + 0xd9d4d039u, 4);   MSTEP(MF3, d, a, b, c, x[12] + 0xe6db99e5u, 11);
-    MSTEP(MF3, c, d, a, b, x[15] + 0x1fa27cf8u, 16); MSTEP(MF3, b, c, d, a, x[2] + 0xc4ac5665u, 23);
-    MSTEP(MF4, a, b, c, d, x[0] + 0xf4292244u, 6);   MSTEP(MF4, d, a, b, c, x[7] + 0x432aff97u, 10);
-    MSTEP(MF4, c, d, a, b, x[14] + 0xab9423a7u, 15); MSTEP(MF4, b, c, d, a, x[5] + 0xfc93a039u, 21);
-    MSTEP(MF4, a, b, c, d, x[12] + 0x655b59c3u, 6);  MSTEP(MF4, d, a, b, c, x[3] + 0x8f0ccc92u, 10);
-    MSTEP(MF4, c, d, a, b, x[10] + 0xffeff47du, 15); MSTEP(MF4, b, c, d, a, x[1] + 0x85845dd1u, 21);
-    MSTEP(MF4, a, b, c, d, x[8] + 0x6fa87e4fu, 6);   MSTEP(MF4, d, a, b, c, x[15] + 0xfe2ce6e0u, 10);
-    MSTEP(MF4, c, d, a, b, x[6] + 0xa3014314u, 15);  MSTEP(MF4, b, c, d, a, x[13] + 0x4e0811a1u, 21);
-    MSTEP(MF4, a, b, c, d, x[4] + 0xf7537e82u, 6);   MSTEP(MF4, d, a, b, c, x[11] + 0xbd3af235u, 10);
-    MSTEP(MF4, c, d, a, b, x[2] + 0x2ad7d2bbu, 15);  MSTEP(MF4, b, c, d, a, x[9] + 0xeb86d391u, 21);
+// w + x[i] + K does not depend on the previous step: it is formed by an asm the compiler cannot reassociate into the
+// chain, which is then LOP3 -> IADD3 -> LEA.HI (rotate and add in one) per step; left to itself the compiler
+// put x[i] and K behind the round function in two dependent adds (4 instructions deep, 76 MB/s per thread)
+#define MSTEP(f, w, x_, y, z, xi, k, s) (w = md5_pre(w, xi, k) + f(x_, y, z), w = md5_rol(w, s) + x_)
+    MSTEP(MF1, a, b, c, d, x[0], 0xd76aa478u, 7);   MSTEP(MF1, d, a, b, c, x[1], 0xe8c7b756u, 12);
+    MSTEP(MF1, c, d, a, b, x[2], 0x242070dbu, 17);  MSTEP(MF1, b, c, d, a, x[3], 0xc1bdceeeu, 22);
+    MSTEP(MF1, a, b, c, d, x[4], 0xf57c0fafu, 7);   MSTEP(MF1, d, a, b, c, x[5], 0x4787c62au, 12);
+    MSTEP(MF1, c, d, a, b, x[6], 0xa8304613u, 17);  MSTEP(MF1, b, c, d, a, x[7], 0xfd469501u, 22);
+    MSTEP(MF1, a, b, c, d, x[8], 0x698098d8u, 7);   MSTEP(MF1, d, a, b, c, x[9], 0x8b44f7afu, 12);
+    MSTEP(MF1, c, d, a, b, x[10], 0xffff5bb1u, 17); MSTEP(MF1, b, c, d, a, x[11], 0x895cd7beu, 22);
+    MSTEP(MF1, a, b, c, d, x[12], 0x6b901122u, 7);  MSTEP(MF1, d, a, b, c, x[13], 0xfd987193u, 12);
+    MSTEP(MF1, c, d, a, b, x[14], 0xa679438eu, 17); MSTEP(MF1, b, c, d, a, x[15], 0x49b40821u, 22);
+    MSTEP(MF2, a, b, c, d, x[1], 0xf61e2562u, 5);   MSTEP(MF2, d, a, b, c, x[6], 0xc040b340u, 9);
+    MSTEP(MF2, c, d, a, b, x[11], 0x265e5a51u, 14); MSTEP(MF2, b, c, d, a, x[0], 0xe9b6c7aau, 20);
+    MSTEP(MF2, a, b, c, d, x[5], 0xd62f105du, 5);   MSTEP(MF2, d, a, b, c, x[10], 0x02441453u, 9);
+    MSTEP(MF2, c, d, a, b, x[15], 0xd8a1e681u, 14); MSTEP(MF2, b, c, d, a, x[4], 0xe7d3fbc8u, 20);
+    MSTEP(MF2, a, b, c, d, x[9], 0x21e1cde6u, 5);   MSTEP(MF2, d, a, b, c, x[14], 0xc33707d6u, 9);
+    MSTEP(MF2, c, d, a, b, x[3], 0xf4d50d87u, 14);  MSTEP(MF2, b, c, d, a, x[8], 0x455a14edu, 20);
+    MSTEP(MF2, a, b, c, d, x[13], 0xa9e3e905u, 5);  MSTEP(MF2, d, a, b, c, x[2], 0xfcefa3f8u, 9);
+    MSTEP(MF2, c, d, a, b, x[7], 0x676f02d9u, 14);  MSTEP(MF2, b, c, d, a, x[12], 0x8d2a4c8au, 20);
+    MSTEP(MF3, a, b, c, d, x[5], 0xfffa3942u, 4);   MSTEP(MF3, d, a, b, c, x[8], 0x8771f681u, 11);
+    MSTEP(MF3, c, d, a, b, x[11], 0x6d9d6122u, 16); MSTEP(MF3, b, c, d, a, x[14], 0xfde5380cu, 23);
+    MSTEP(MF3, a, b, c, d, x[1], 0xa4beea44u, 4);   MSTEP(MF3, d, a, b, c, x[4], 0x4bdecfa9u, 11);
+    MSTEP(MF3, c, d, a, b, x[7], 0xf6bb4b60u, 16);  MSTEP(MF3, b, c, d, a, x[10], 0xbebfbc70u, 23);
+    MSTEP(MF3, a, b, c, d, x[13], 0x289b7ec6u, 4);  MSTEP(MF3, d, a, b, c, x[0], 0xeaa127fau, 11);
+    MSTEP(MF3, c, d, a, b, x[3], 0xd4ef3085u, 16);  MSTEP(MF3, b, c, d, a, x[6], 0x04881d05u, 23);
+    MSTEP(MF3, a, b, c, d, x[9], 0xd9d4d039u, 4);   MSTEP(MF3, d, a, b, c, x[12], 0xe6db99e5u, 11);
+    MSTEP(MF3, c, d, a, b, x[15], 0x1fa27cf8u, 16); MSTEP(MF3, b, c, d, a, x[2], 0xc4ac5665u, 23);
+    MSTEP(MF4, a, b, c, d, x[0], 0xf4292244u, 6);   MSTEP(MF4, d, a, b, c, x[7], 0x432aff97u, 10);
+    MSTEP(MF4, c, d, a, b, x[14], 0xab9423a7u, 15); MSTEP(MF4, b, c, d, a, x[5], 0xfc93a039u, 21);
+    MSTEP(MF4, a, b, c, d, x[12], 0x655b59c3u, 6);  MSTEP(MF4, d, a, b, c, x[3], 0x8f0ccc92u, 10);
+    MSTEP(MF4, c, d, a, b, x[10], 0xffeff47du, 15); MSTEP(MF4, b, c, d, a, x[1], 0x85845dd1u, 21);
+    MSTEP(MF4, a, b, c, d, x[8], 0x6fa87e4fu, 6);   MSTEP(MF4, d, a, b, c, x[15], 0xfe2ce6e0u, 10);
+    MSTEP(MF4, c, d, a, b, x[6], 0xa3014314u, 15);  MSTEP(MF4, b, c, d, a, x[13], 0x4e0811a1u, 21);
+    MSTEP(MF4, a, b, c, d, x[4], 0xf7537e82u, 6);   MSTEP(MF4, d, a, b, c, x[11], 0xbd3af235u, 10);
+    MSTEP(MF4, c, d, a, b, x[2], 0x2ad7d2bbu, 15);  MSTEP(MF4, b, c, d, a, x[9], 0xeb86d391u, 21);
 #undef MSTEP
 #undef MF1
 #undef MF2
@@ -167,6 +179,7 @@ struct Region {                 // one batch's PCM on the device + its hashes
     cudaStream_t st;            // its MD5 kernel's stream
     cudaEvent_t ev_h2d, ev_md5;
     int batch;                  // batch using it (-1: free)
+    bool dev_md5;               // its hashes are being computed by the device and have not been read back
 };
 
 struct OutBuf {                 // frames of one batch on the host
@@ -256,7 +269,7 @@ int ctx_prepare(Ctx& c, const b200flac_params* p, int device, u64 batch_bytes, u
         CK(cudaMallocHost((void**)&r.h_digest, 16 * (size_t)c.cap_tracks));
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        CK(cudaStreamCreateWithPriority(&r.st, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&r.st, cudaStreamNonBlocking, getenv("B200FLAC_FILES_MD5_LOW") ? lo : hi));
         CK(cudaEventCreateWithFlags(&r.ev_h2d, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&r.ev_md5, cudaEventDisableTiming));
         c.ring.push_back(r);
@@ -284,33 +297,100 @@ struct Job {
     std::deque<TrackOut> tasks;
     bool quit, failed;
     Ctx* ctx;
+    // The hashing is shared.  The device takes whole batches from the front of the list as their PCM arrives (a track
+    // costs one of its threads ~0.3 s whatever else happens, a thousand tracks at once cost the same 0.3 s); pool
+    // threads with no file to write take single tracks from the END of the list, out of the caller's memory (a core
+    // hashes a three-minute track in ~55 ms, but there are only host_threads of them).  The device stops claiming
+    // when the host would be done with everything left before the device could finish one more batch -- so a job
+    // of a few long tracks is hashed by the host alone and the last batches of a long job never leave the whole
+    // job waiting for one slow device thread.
+    bool host_md5;
+    const uint8_t* const* pcm;
+    u64 frame_bytes;
+    uint8_t* digests;
+    const u32* batch_of;        // per track
+    char* host_touched;         // per batch: the host has claimed one of its tracks
+    long long host_cursor;      // the next track the host claims (counts down)
+    long long dev_end_track;    // tracks [0, dev_end_track) are the device's
+    bool dev_stopped;
+    int host_inflight;
+    u64 unclaimed_bytes;
+    u64 host_bytes; double host_busy_s;   // hashed by the pool so far; seconds its threads spent on it
+    u32 host_tracks;
+    double t_start, write_busy_s;
 };
+
+bool write_track(Job* j, const TrackOut& t, std::vector<uint8_t>& head)
+{
+    static const uint8_t zero[16] = {0};
+    FILE* f = fopen(j->filenames[t.track], "wb");
+    if (!f) return false;
+    bool ok = true;
+    b200flac_internal_stream_head(j->params, j->padding_size, j->version, t.min_frame, t.max_frame,
+                                  j->n_pcm_frames[t.track], zero, head);
+    if (fwrite(head.data(), 1, head.size(), f) != head.size()) ok = false;
+    if (ok && t.bytes && fwrite(t.frames, 1, (size_t)t.bytes, f) != (size_t)t.bytes) ok = false;
+    if (fclose(f) != 0) ok = false;
+    return ok;
+}
+
+// (mutex held on entry and exit) write every queued file
+void drain_writes(Job* j, std::vector<uint8_t>& head)
+{
+    while (!j->tasks.empty()) {
+        const TrackOut t = j->tasks.front();
+        j->tasks.pop_front();
+        pthread_mutex_unlock(&j->mu);
+        const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        const bool ok = write_track(j, t, head);
+        const double t1 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        pthread_mutex_lock(&j->mu);
+        j->write_busy_s += t1 - t0;
+        if (!ok) j->failed = true;
+        if (--j->ctx->out[t.outbuf].pending == 0) pthread_cond_broadcast(&j->cv_done);
+    }
+}
 
 void* writer_main(void* arg)
 {
     Job* j = (Job*)arg;
     std::vector<uint8_t> head;
-    const uint8_t zero[16] = {0};
+    const size_t PIECE = 4u << 20;          // files come first: a hashing thread looks for them every few milliseconds
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     pthread_mutex_lock(&j->mu);
     for (;;) {
-        while (j->tasks.empty() && !j->quit) pthread_cond_wait(&j->cv_task, &j->mu);
-        if (j->tasks.empty()) break;
-        const TrackOut t = j->tasks.front();
-        j->tasks.pop_front();
-        pthread_mutex_unlock(&j->mu);
-        bool ok = true;
-        FILE* f = fopen(j->filenames[t.track], "wb");
-        if (!f) ok = false;
-        else {
-            b200flac_internal_stream_head(j->params, j->padding_size, j->version, t.min_frame, t.max_frame,
-                                          j->n_pcm_frames[t.track], zero, head);
-            if (fwrite(head.data(), 1, head.size(), f) != head.size()) ok = false;
-            if (ok && t.bytes && fwrite(t.frames, 1, (size_t)t.bytes, f) != (size_t)t.bytes) ok = false;
-            if (fclose(f) != 0) ok = false;
+        if (!j->tasks.empty()) { drain_writes(j, head); continue; }
+        if (j->host_md5 && !j->quit && j->host_cursor >= j->dev_end_track) {
+            const u32 t = (u32)j->host_cursor--;
+            const u64 nb = j->n_pcm_frames[t] * j->frame_bytes;
+            j->host_touched[j->batch_of[t]] = 1;
+            j->unclaimed_bytes -= nb;
+            j->host_inflight++;
+            pthread_mutex_unlock(&j->mu);
+            unsigned char st[96];
+            double busy = 0;
+            b200flac_internal_md5_begin(st);
+            for (u64 done = 0; done < nb;) {
+                const size_t n = (size_t)std::min<u64>(PIECE, nb - done);
+                const double t0 = now();
+                b200flac_internal_md5_update(st, j->pcm[t] + done, n);
+                busy += now() - t0;
+                done += n;
+                if (done < nb) {
+                    pthread_mutex_lock(&j->mu);
+                    drain_writes(j, head);
+                    pthread_mutex_unlock(&j->mu);
+                }
+            }
+            b200flac_internal_md5_end(st, j->digests + 16 * (size_t)t);
+            pthread_mutex_lock(&j->mu);
+            j->host_inflight--;
+            j->host_bytes += nb; j->host_busy_s += busy; j->host_tracks++;
+            pthread_cond_broadcast(&j->cv_done);
+            continue;
         }
-        pthread_mutex_lock(&j->mu);
-        if (!ok) j->failed = true;
-        if (--j->ctx->out[t.outbuf].pending == 0) pthread_cond_broadcast(&j->cv_done);
+        if (j->quit) break;
+        pthread_cond_wait(&j->cv_task, &j->mu);
     }
     pthread_mutex_unlock(&j->mu);
     return nullptr;
@@ -351,15 +431,16 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
     u64 longest = 0;
     for (u32 t = 0; t < n_tracks; t++) longest = std::max<u64>(longest, padded(n_pcm_frames[t] * frame_bytes));
     if (longest > batch_bytes) batch_bytes = (longest + 0xFFFFF) & ~0xFFFFFull;
-    struct Batch { u32 first, count; u64 bytes; };
+    struct Batch { u32 first, count; u64 bytes; u64 raw, longest; };   // bytes: padded; raw, longest: PCM bytes
     std::vector<Batch> batches;
     u32 cap_tracks = 1;
     {
-        Batch b = {0, 0, 0};
+        Batch b = {0, 0, 0, 0, 0};
         for (u32 t = 0; t < n_tracks; t++) {
-            const u64 tb = padded(n_pcm_frames[t] * frame_bytes);
-            if (b.count && (b.bytes + tb > batch_bytes || b.count >= 4096)) { batches.push_back(b); b = {t, 0, 0}; }
-            b.count++; b.bytes += tb;
+            const u64 nb = n_pcm_frames[t] * frame_bytes;
+            const u64 tb = padded(nb);
+            if (b.count && (b.bytes + tb > batch_bytes || b.count >= 4096)) { batches.push_back(b); b = {t, 0, 0, 0, 0}; }
+            b.count++; b.bytes += tb; b.raw += nb; b.longest = std::max(b.longest, nb);
         }
         batches.push_back(b);
         for (auto& x : batches) cap_tracks = std::max(cap_tracks, x.count);
@@ -374,45 +455,111 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
     Ctx& c = g_ctx;
     int rc = ctx_prepare(c, params, device, batch_bytes, cap_tracks, ring_regions);
     if (rc) { ctx_destroy(c); pthread_mutex_unlock(&g_ctx_mu); return 1; }
-    for (auto& r : c.ring) r.batch = -1;
+    for (auto& r : c.ring) { r.batch = -1; r.dev_md5 = false; }
     for (int i = 0; i < NS; i++) c.out[i].pending = 0;
+    const int dbg = getenv("B200FLAC_FILES_DEBUG") ? atoi(getenv("B200FLAC_FILES_DEBUG")) : 0;   // timing experiments only -- 1: no hashing, 2: frames neither copied back nor written, 4: PCM copied once (region reuse without copies)
+    std::vector<uint8_t> digests((size_t)n_tracks * 16, 0);
+    std::vector<u32> batch_of((size_t)n_tracks);
+    std::vector<char> host_touched(batches.size(), 0);
+    u64 all_bytes = 0;
+    for (size_t b = 0; b < batches.size(); b++) {
+        for (u32 i = 0; i < batches[b].count; i++) batch_of[batches[b].first + i] = (u32)b;
+        all_bytes += batches[b].raw;
+    }
 
     Job job;
     job.filenames = filenames; job.params = params; job.padding_size = padding_size; job.version = version;
     job.n_pcm_frames = n_pcm_frames; job.quit = false; job.failed = false; job.ctx = &c;
+    // B200FLAC_FILES_HOST_MD5=0: every hash on the device (A/B measurements)
+    { const char* e = getenv("B200FLAC_FILES_HOST_MD5"); job.host_md5 = !(e && atoi(e) == 0) && !(dbg & 1); }
+    job.pcm = pcm; job.frame_bytes = frame_bytes; job.digests = digests.data(); job.batch_of = batch_of.data();
+    job.host_touched = host_touched.data(); job.host_cursor = (long long)n_tracks - 1; job.dev_end_track = 0;
+    job.dev_stopped = false; job.host_inflight = 0; job.unclaimed_bytes = all_bytes;
+    job.host_bytes = 0; job.host_busy_s = 0; job.host_tracks = 0; job.write_busy_s = 0;
+    // what a device thread hashes per second (measured on a B200: the chain is LOP3 -> IADD -> LEA.HI per step)
+    double dev_rate = 95e6;
+    { const char* e = getenv("B200FLAC_FILES_DEV_MD5_MBS"); if (e && atof(e) > 0) dev_rate = atof(e) * 1e6; }
     pthread_mutex_init(&job.mu, nullptr);
     pthread_cond_init(&job.cv_task, nullptr);
     pthread_cond_init(&job.cv_done, nullptr);
     std::vector<pthread_t> writers((size_t)host_threads);
     for (auto& w : writers) pthread_create(&w, nullptr, writer_main, &job);
 
-    std::vector<uint8_t> digests((size_t)n_tracks * 16, 0);
     std::vector<b200flac_segment> segs;
     const u32 bs = params->block_size;
     // B200FLAC_FILES_TRACE=1: where the orchestrating thread waited, to stderr
     const bool trace = getenv("B200FLAC_FILES_TRACE") != nullptr;
-    const int dbg = getenv("B200FLAC_FILES_DEBUG") ? atoi(getenv("B200FLAC_FILES_DEBUG")) : 0;   // 1: no hashing (timing experiments only)
     double w_ring = 0, w_h2d = 0, w_collect = 0, w_writers = 0, w_d2h = 0, w_tail_files = 0, w_tail_md5 = 0, w_submit = 0;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now();
+    job.t_start = t_start;
     std::vector<char> submitted((size_t)NB, 0);
     int next_h2d = 0;                      // next batch whose copy has not been issued
-    int md5_collected = 0;                 // batches whose digests have been read back
     bool fail = false;
 
-    // copy batch b to its region of the ring and start hashing it as soon as it is there.  must: the encoder needs
+    // Start hashing every batch whose copy has ARRIVED (asked, not waited for).  Two traps, both measured:
+    //  * the digests are written by the kernel straight into page-locked host memory -- a device->host copy queued
+    //    behind this (long) kernel would sit at the head of the copy engine's queue and hold every later copy of
+    //    frames back until the kernel is done (63 ms per batch instead of 7);
+    //  * the kernel is launched only once its input is there, never queued behind a cudaStreamWaitEvent on a copy
+    //    that is still hundreds of milliseconds away: streams share a handful of hardware queues, and an entry
+    //    waiting at the head of one holds back the encoder's kernels that happen to map to the same queue
+    //    (the encoder ran at 20 ms per batch instead of 11).
+    int next_md5 = 0;
+    u32 dev_tracks = 0;
+    // does the device hash batch b?  (see Job)
+    auto claim_for_device = [&](int b) -> bool {
+        const Batch& bb = batches[(size_t)b];
+        bool dev = true;
+        pthread_mutex_lock(&job.mu);
+        if (job.host_md5) {
+            if (job.dev_stopped || job.host_touched[(size_t)b]) dev = false;
+            else {
+                // what the pool has hashed per second of the job so far -- next to writing the files, which is most
+                // of its work (before there is a measurement: half of what its threads could do undisturbed)
+                const double el = now() - job.t_start;
+                const double host_rate = (el > 0.05 && job.host_bytes) ? (double)job.host_bytes / el : 0.5 * 550e6 * host_threads;
+                dev = (double)bb.longest / dev_rate < (double)job.unclaimed_bytes / host_rate;
+            }
+            if (!dev) job.dev_stopped = true;
+        }
+        if (dev) { job.dev_end_track = (long long)bb.first + bb.count; job.unclaimed_bytes -= bb.raw; dev_tracks += bb.count; }
+        pthread_mutex_unlock(&job.mu);
+        return dev;
+    };
+    auto launch_ready_md5 = [&](int upto_must) -> int {
+        while (next_md5 < next_h2d) {
+            Region& r = c.ring[(size_t)next_md5 % c.ring.size()];
+            if (next_md5 > upto_must && cudaEventQuery(r.ev_h2d) != cudaSuccess) break;
+            if (next_md5 <= upto_must) CK(cudaEventSynchronize(r.ev_h2d));
+            const Batch& bb = batches[(size_t)next_md5];
+            r.dev_md5 = claim_for_device(next_md5);
+            if (r.dev_md5) {
+                if (!(dbg & 1))
+                    k_md5_tracks<<<(bb.count + 31) / 32, 32, 0, r.st>>>(r.d_pcm, r.d_meta, r.d_meta + c.cap_tracks, bb.count, r.h_digest);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(r.ev_md5, r.st));
+            }
+            next_md5++;
+        }
+        return 0;
+    };
+    // copy batch b to its region of the ring.  must: the encoder needs
     // this batch now (otherwise the call gives up, returning 2, while the region's previous hashes are not done)
     auto issue_h2d = [&](int b, bool must) -> int {
         Region& r = c.ring[(size_t)b % c.ring.size()];
         if (r.batch >= 0) {
             // the region's previous batch: its encode has been collected; its hashes must be done, then kept
-            if (!must && cudaEventQuery(r.ev_md5) != cudaSuccess) return 2;
-            const double t0 = now();
-            CK(cudaEventSynchronize(r.ev_md5));
-            w_ring += now() - t0;
-            const Batch& ob = batches[(size_t)r.batch];
-            memcpy(&digests[(size_t)ob.first * 16], r.h_digest, (size_t)ob.count * 16);
-            md5_collected++;
+            if (r.batch >= next_md5) { if (!must) return 2; if (launch_ready_md5(r.batch)) return 1; }
+            if (r.dev_md5) {
+                if (!must && cudaEventQuery(r.ev_md5) != cudaSuccess) return 2;
+                const double t0 = now();
+                CK(cudaEventSynchronize(r.ev_md5));
+                w_ring += now() - t0;
+                const Batch& ob = batches[(size_t)r.batch];
+                memcpy(&digests[(size_t)ob.first * 16], r.h_digest, (size_t)ob.count * 16);
+                r.dev_md5 = false;
+            }
         }
         r.batch = b;
         const Batch& bb = batches[(size_t)b];
@@ -422,19 +569,11 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
             const u64 nb = n_pcm_frames[t] * frame_bytes;
             r.h_meta[i] = off;
             r.h_meta[c.cap_tracks + i] = nb;
-            if (nb) CK(cudaMemcpyAsync(r.d_pcm + off, pcm[t], nb, cudaMemcpyHostToDevice, c.st_h2d));
+            if (nb && !((dbg & 4) && b >= (int)c.ring.size())) CK(cudaMemcpyAsync(r.d_pcm + off, pcm[t], nb, cudaMemcpyHostToDevice, c.st_h2d));
             off += padded(nb);
         }
         CK(cudaMemcpyAsync(r.d_meta, r.h_meta, 2 * sizeof(u64) * c.cap_tracks, cudaMemcpyHostToDevice, c.st_h2d));
         CK(cudaEventRecord(r.ev_h2d, c.st_h2d));
-        // the digests are written straight into page-locked host memory: a device->host copy queued behind this
-        // (long) kernel would sit at the head of the copy engine's queue and hold every later copy of frames
-        // back until the kernel is done (measured: 63 ms per batch instead of 7)
-        CK(cudaStreamWaitEvent(r.st, r.ev_h2d, 0));
-        if (!(dbg & 1))
-            k_md5_tracks<<<(bb.count + 31) / 32, 32, 0, r.st>>>(r.d_pcm, r.d_meta, r.d_meta + c.cap_tracks, bb.count, r.h_digest);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(r.ev_md5, r.st));
         return 0;
     };
     // frames of batch b are in d_out[b % NS]: bring them to the host and queue the file writes
@@ -453,7 +592,7 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
         while (c.out[ob].pending > 0) pthread_cond_wait(&job.cv_done, &job.mu);
         pthread_mutex_unlock(&job.mu);
         w_writers += now() - t0;
-        CK(cudaMemcpyAsync(c.out[ob].h, c.d_out[ob], out_bytes, cudaMemcpyDeviceToHost, c.st_d2h));
+        if (!(dbg & 2)) CK(cudaMemcpyAsync(c.out[ob].h, c.d_out[ob], out_bytes, cudaMemcpyDeviceToHost, c.st_d2h));
         CK(cudaEventRecord(c.out[ob].ev, c.st_d2h));
         // per-track extents while the copy runs
         const Batch& bb = batches[(size_t)b];
@@ -479,6 +618,7 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
         w_d2h += now() - t0;
         pthread_mutex_lock(&job.mu);
         c.out[ob].pending = (int)bb.count;
+        if (dbg & 2) for (auto& o : outs) { o.bytes = 0; o.frames = nullptr; }
         for (auto& o : outs) job.tasks.push_back(o);
         pthread_cond_broadcast(&job.cv_task);
         pthread_mutex_unlock(&job.mu);
@@ -503,6 +643,7 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
             double t0 = now();
             CK(cudaEventSynchronize(r.ev_h2d));
             w_h2d += now() - t0;
+            if (launch_ready_md5(b)) return 1;
             segs.clear();
             for (u32 i = 0; i < bb.count; i++) {
                 b200flac_segment sg;
@@ -543,20 +684,23 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
     const double t_run = now();
     pthread_mutex_lock(&job.mu);
     if (!fail) for (int i = 0; i < NS; i++) while (c.out[i].pending > 0) pthread_cond_wait(&job.cv_done, &job.mu);
+    w_tail_files = now() - t_run;
+    // (every batch has been offered to the device by now: what it did not take is the host's, down to the last track)
+    if (!fail && job.host_md5)
+        while (job.host_cursor >= job.dev_end_track || job.host_inflight > 0) pthread_cond_wait(&job.cv_done, &job.mu);
     job.quit = true;
     pthread_cond_broadcast(&job.cv_task);
     pthread_mutex_unlock(&job.mu);
     for (auto& w : writers) pthread_join(w, nullptr);
     if (job.failed) { b200flac_internal_set_error("cannot write an output file"); fail = true; }
-    w_tail_files = now() - t_run;
-    const double t_md5 = now();
+    const double t_md5 = t_run + w_tail_files;
     if (!fail) {
         for (auto& r : c.ring) {
-            if (r.batch < 0) continue;
+            if (r.batch < 0 || !r.dev_md5) { r.batch = -1; continue; }
             if (cudaEventSynchronize(r.ev_md5) != cudaSuccess) { b200flac_internal_set_error("device MD5 failed"); fail = true; break; }
             const Batch& ob = batches[(size_t)r.batch];
             memcpy(&digests[(size_t)ob.first * 16], r.h_digest, (size_t)ob.count * 16);
-            r.batch = -1;
+            r.batch = -1; r.dev_md5 = false;
         }
     }
     if (!fail) {
@@ -570,9 +714,11 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
     w_tail_md5 = now() - t_md5;
     if (trace)
         fprintf(stderr, "b200flac_encode_files: %u tracks, %d batches, ring %zu: total %.3f s; waits: ring(md5) %.3f h2d %.3f "
-                "submit %.3f collect %.3f writers %.3f d2h %.3f | tail: files %.3f md5+patch %.3f\n",
+                "submit %.3f collect %.3f writers %.3f d2h %.3f | tail: files %.3f md5+patch %.3f | hashed: device %u tracks, "
+                "host %u (%.0f MB/s per thread, %.2f thread-s); files %.2f thread-s\n",
                 n_tracks, NB, c.ring.size(), now() - t_start, w_ring, w_h2d, w_submit, w_collect, w_writers, w_d2h,
-                w_tail_files, w_tail_md5);
+                w_tail_files, w_tail_md5, dev_tracks, job.host_tracks,
+                job.host_busy_s > 0 ? job.host_bytes / job.host_busy_s / 1e6 : 0.0, job.host_busy_s, job.write_busy_s);
     pthread_mutex_destroy(&job.mu);
     pthread_cond_destroy(&job.cv_task);
     pthread_cond_destroy(&job.cv_done);

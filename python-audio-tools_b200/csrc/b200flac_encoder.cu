@@ -1215,6 +1215,23 @@ extern "C" int b200flac_encoder_encode(b200flac_encoder* enc, const uint8_t* pcm
     return b200flac_encoder_collect(enc, 0, out, out_capacity, out_bytes, frame_bytes, frame_pcm, frame_capacity, n_frames);
 }
 
+// Small transfers between page-locked host memory and the device done by a kernel over the mapped host pointer
+// instead of a copy-engine job.  The device-resident entry is used by callers that keep the copy engines busy with
+// their own traffic (b200flac_encode_files queues hundreds of MB of PCM ahead of the encoder): a batch's descriptors
+// queued as an ordinary copy wait behind everything already in the engine's queue, and the kernels with them.
+__global__ void k_copy_words(u32* __restrict__ dst, const u32* __restrict__ src, size_t n_words)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+static void copy_by_kernel(void* dst, const void* src, size_t bytes, cudaStream_t st)
+{
+    const size_t n = bytes / 4;       // (every table copied this way is a whole number of words)
+    if (!n) return;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 296);
+    k_copy_words<<<blocks, 256, 0, st>>>((u32*)dst, (const u32*)src, n);
+}
+
 // device-resident batches, asynchronous: enqueue (host work + launches) now, wait later -- with two slots the
 // host's share of batch k + 1 (descriptors, task lists, their upload) runs under the kernels of batch k
 extern "C" int b200flac_encoder_submit_device(b200flac_encoder* enc, int slot, const void* d_pcm,
@@ -1234,14 +1251,15 @@ extern "C" int b200flac_encoder_submit_device(b200flac_encoder* enc, int slot, c
     s.busy = true;
     if (nf == 0) { s.timed = false; *s.h_total = 0; return 0; }
     cudaStream_t st = s.stream;
-    CU_CHECK(cudaMemcpyAsync(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), cudaMemcpyHostToDevice, st), 1);
-    if (s.n_odd) CU_CHECK(cudaMemcpyAsync(s.d_odd, s.h_odd, (size_t)s.n_odd * sizeof(u32), cudaMemcpyHostToDevice, st), 1);
-    if (enc->P.try_lpc) CU_CHECK(cudaMemcpyAsync(s.d_tasks, s.h_tasks, (size_t)s.n_tasks * sizeof(bf_lpc_task), cudaMemcpyHostToDevice, st), 1);
+    copy_by_kernel(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), st);
+    if (s.n_odd) copy_by_kernel(s.d_odd, s.h_odd, (size_t)s.n_odd * sizeof(u32), st);
+    if (enc->P.try_lpc) copy_by_kernel(s.d_tasks, s.h_tasks, (size_t)s.n_tasks * sizeof(bf_lpc_task), st);
     const size_t wused = (size_t)s.h_total[1];
-    if (wused) CU_CHECK(cudaMemcpyAsync(s.d_win, s.h_win, wused * sizeof(double), cudaMemcpyHostToDevice, st), 1);
+    if (wused) copy_by_kernel(s.d_win, s.h_win, wused * sizeof(double), st);
     if (launch_batch(enc, s, (const uint8_t*)d_pcm, (uint8_t*)d_out, s.dev_cap)) { s.busy = false; return 1; }
-    CU_CHECK(cudaMemcpyAsync(s.h_total, s.d_total, sizeof(u64), cudaMemcpyDeviceToHost, st), 1);
-    CU_CHECK(cudaMemcpyAsync(s.h_frame_bytes, s.d_frame_bytes, (size_t)nf * sizeof(u32), cudaMemcpyDeviceToHost, st), 1);
+    copy_by_kernel(s.h_total, s.d_total, sizeof(u64), st);
+    copy_by_kernel(s.h_frame_bytes, s.d_frame_bytes, (size_t)nf * sizeof(u32), st);
+    CU_CHECK(cudaGetLastError(), 1);
     CU_CHECK(cudaEventRecord(s.ev_done, st), 1);
     return 0;
 }

@@ -637,6 +637,34 @@ def test_encode_files_equals_encode_file(shape, tmp_path, built):
         assert open(name, "rb").read()[26:42] == hashlib.md5(pcms[i]).digest()
 
 
+@pytest.mark.parametrize("mode", ["device_only", "host_only", "device_first"])
+def test_encode_files_hash_sharing(mode, tmp_path, built):
+    """the STREAMINFO MD5s are shared between the device (whole batches from the front of the list) and the pool's idle
+    host threads (single tracks from its end): whoever hashes a track, the digest is hashlib's -- all on the device
+    (B200FLAC_FILES_HOST_MD5=0), all on the host (a device rate so low that it never claims a batch), and the two
+    fronts meeting somewhere in the list (a device rate so high that it claims every batch the host has not touched)"""
+    b = _b200()
+    o = helpers.options(block_size=4096, max_lpc_order=8, max_residual_partition_order=4)
+    kw = {k: v for k, v in o.items() if k != "padding_size"}
+    p = b.make_params(44100, 2, 16, **kw)
+    lengths = [20000 + 1777 * (i % 9) for i in range(60)] + [0, 1, 4097]
+    pcms = [helpers.synth_pcm(1300 + i, 2, 16, n) if n else b"" for i, n in enumerate(lengths)]
+    bufs = [np.frombuffer(pcm if n else b"\0" * 16, dtype=np.uint8).copy() for pcm, n in zip(pcms, lengths)]
+    names = [os.path.join(str(tmp_path), "h_%d.flac" % i) for i in range(len(lengths))]
+    env = {"B200FLAC_FILES_BATCH_MB": "1", "B200FLAC_FILES_RING": "5"}
+    env.update({"device_only": {"B200FLAC_FILES_HOST_MD5": "0"}, "host_only": {"B200FLAC_FILES_DEV_MD5_MBS": "0.000001"},
+                "device_first": {"B200FLAC_FILES_DEV_MD5_MBS": "1000000"}}[mode])
+    for threads in (1, 4):
+        _with_env(env, lambda: b.encode_files(names, p, bufs, lengths, device=0, host_threads=threads))
+        for i, name in enumerate(names):
+            got = open(name, "rb").read()
+            assert got[26:42] == hashlib.md5(pcms[i]).digest(), "track %d of %d, %s, %d threads" % (i, len(names), mode, threads)
+            if i % 7 == 0:
+                assert got == helpers.oracle_encode(pcms[i], 44100, 2, 16, o)
+            os.unlink(name)
+    b.lib().b200flac_pool_clear()
+
+
 def test_encode_files_error_then_reuse(tmp_path, built):
     """a file that cannot be written fails the job (no hang, the other files are still produced or not -- unspecified),
     and the next job on the same cached context works"""
