@@ -576,8 +576,9 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
         CK(cudaEventRecord(r.ev_h2d, c.st_h2d));
         return 0;
     };
-    // frames of batch b are in d_out[b % NS]: bring them to the host and queue the file writes
-    auto finish_batch = [&](int b) -> int {
+    // frames of batch b are in d_out[b % NS]: start bringing them to the host ...
+    std::vector<TrackOut> outs_of[NS];
+    auto start_d2h = [&](int b) -> int {
         const int ob = b % NS;
         uint64_t out_bytes = 0;
         uint32_t nfr = 0;
@@ -596,7 +597,8 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
         CK(cudaEventRecord(c.out[ob].ev, c.st_d2h));
         // per-track extents while the copy runs
         const Batch& bb = batches[(size_t)b];
-        std::vector<TrackOut> outs(bb.count);
+        std::vector<TrackOut>& outs = outs_of[ob];
+        outs.assign(bb.count, TrackOut());
         u64 pos = 0;
         u32 f = 0;
         for (u32 i = 0; i < bb.count; i++) {
@@ -613,11 +615,19 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
             pos += o.bytes;
         }
         if (f != nfr || pos != out_bytes) { b200flac_internal_set_error("internal: batch frame accounting"); return 1; }
-        t0 = now();
+        return 0;
+    };
+    // ... and, an iteration later, queue the file writes: the copy runs under the next batch's submit and the wait
+    // for the encoder.  (Measured neutral on a 16-core box: with the pool writing files and hashing, the two copy
+    // directions together make 59 GB/s and pace the job whichever of the two the thread waits for.)
+    auto complete_d2h = [&](int b) -> int {
+        const int ob = b % NS;
+        std::vector<TrackOut>& outs = outs_of[ob];
+        const double t0 = now();
         CK(cudaEventSynchronize(c.out[ob].ev));
         w_d2h += now() - t0;
         pthread_mutex_lock(&job.mu);
-        c.out[ob].pending = (int)bb.count;
+        c.out[ob].pending += (int)outs.size();
         if (dbg & 2) for (auto& o : outs) { o.bytes = 0; o.frames = nullptr; }
         for (auto& o : outs) job.tasks.push_back(o);
         pthread_cond_broadcast(&job.cv_task);
@@ -652,6 +662,8 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
                 sg.first_frame_number = 0; sg.reserved = 0;
                 if (sg.n_pcm_frames) segs.push_back(sg);
             }
+            // (the slot's output buffer on the device is free once the copy of batch b - NS has arrived)
+            if (b >= NS && submitted[(size_t)(b - NS)] && complete_d2h(b - NS)) return 1;
             if (!segs.empty()) {
                 t0 = now();
                 if (b200flac_encoder_submit_device(c.enc, ob, r.d_pcm, segs.data(), (u32)segs.size(), c.d_out[ob], c.out_cap))
@@ -659,12 +671,11 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
                 w_submit += now() - t0;
                 submitted[(size_t)b] = 1;
             }
-            if (b >= NS - 1 && submitted[(size_t)(b - (NS - 1))] && finish_batch(b - (NS - 1))) return 1;
+            if (b >= NS - 1 && submitted[(size_t)(b - (NS - 1))] && start_d2h(b - (NS - 1))) return 1;
             if (segs.empty()) {
                 // a batch of empty tracks: nothing was submitted; give the writers their (frameless) files
                 pthread_mutex_lock(&job.mu);
-                while (c.out[ob].pending > 0) pthread_cond_wait(&job.cv_done, &job.mu);
-                c.out[ob].pending = (int)bb.count;
+                c.out[ob].pending += (int)bb.count;
                 for (u32 i = 0; i < bb.count; i++) {
                     TrackOut o; o.track = bb.first + i; o.frames = nullptr; o.bytes = 0; o.min_frame = 0xFFFFFF; o.max_frame = 0; o.outbuf = ob;
                     job.tasks.push_back(o);
@@ -674,8 +685,11 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
             }
         }
         // (the last batches; a batch of empty tracks was not submitted and its files are queued already)
-        for (int b = std::max(0, NB - (NS - 1)); b < NB; b++)
-            if (submitted[(size_t)b] && finish_batch(b)) return 1;
+        for (int b = NB; b < NB + NS; b++) {
+            if (b >= NS && submitted[(size_t)(b - NS)] && complete_d2h(b - NS)) return 1;
+            const int s_ = b - (NS - 1);
+            if (s_ >= 0 && s_ < NB && submitted[(size_t)s_] && start_d2h(s_)) return 1;
+        }
         return 0;
     };
     if (run()) fail = true;
