@@ -12,7 +12,7 @@ one() {  # cubin, mangled-name pattern, output name
         on { print }' > "profiles/r02_sass_$3.txt"
     echo "$3: $(grep -c "^ *//\*[0-9a-f]*\*/\|^ */\*[0-9a-f]*\*/" profiles/r02_sass_$3.txt) instructions"
 }
-one b200flac_encoder.sm_100a.cubin '_Z11k_lpc_autocILi12ELi1EE' k_lpc_autoc_12_1
+one b200flac_encoder.sm_100a.cubin '_Z11k_lpc_autocILi12ELi1ELi0EE' k_lpc_autoc_12_1
 one b200flac_encoder.sm_100a.cubin '_Z12k_analyze_v3ILi5ELb0ELi32ELi1ELb0EE' k_analyze_v3_5_0_32
 one b200flac_encoder.sm_100a.cubin '_Z12k_analyze_v3ILi5ELb1ELi32ELi2ELb0EE' k_analyze_v3_exhaustive_order8
 one b200flac_batch.sm_100a.cubin '_Z12k_md5_tracks' k_md5_tracks
