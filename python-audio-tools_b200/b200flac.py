@@ -329,6 +329,20 @@ def encode_files(filenames, params, pcms, n_pcm_frames, padding_size=4096, versi
         raise _err()
 
 
+def host_md5_many(datas):
+    """test hook: MD5 of up to sixteen byte strings hashed side by side on one host core (csrc/md5_lanes.cpp)"""
+    n = len(datas)
+    keep = [bytes(d) if len(d) else b"\0" for d in datas]
+    ptr = (C.c_char_p * n)(*keep)
+    lens = (C.c_uint64 * n)(*[len(d) for d in datas])
+    out = (C.c_uint8 * (16 * n))()
+    fn = lib().b200flac_internal_md5_many
+    fn.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    if fn(ptr, lens, n, out, 1 << 16, None, None):
+        raise _err()
+    return [bytes(out[16 * i:16 * i + 16]) for i in range(n)]
+
+
 def device_md5(data, device=0):
     """test hook: MD5 of a byte string computed by the batch entry's device kernel"""
     out = (C.c_uint8 * 16)()

@@ -27,9 +27,9 @@
 #include "../../include/b200flac.h"
 
 extern "C" void b200flac_internal_set_error(const char* msg);                       // b200flac_encoder.cu
-extern "C" void b200flac_internal_md5_begin(void* state);                           // b200flac_stream.cu (96-byte state)
-extern "C" void b200flac_internal_md5_update(void* state, const uint8_t* p, size_t n);
-extern "C" void b200flac_internal_md5_end(void* state, uint8_t out[16]);
+extern "C" void b200flac_internal_md5(const uint8_t* p, size_t n, uint8_t out[16]);  // b200flac_stream.cu (one string, scalar)
+extern "C" int b200flac_internal_md5_many(const uint8_t* const* ptr, const uint64_t* nbytes, uint32_t n, uint8_t* digests,
+                                          uint64_t piece_bytes, int (*between)(void*), void* arg);   // md5_lanes.cpp
 void b200flac_internal_stream_head(const b200flac_params* params, uint32_t padding_size, const char* version,
                                    uint32_t min_frame, uint32_t max_frame, uint64_t total_samples,
                                    const uint8_t md5[16], std::vector<uint8_t>& head);  // b200flac_stream.cu
@@ -299,8 +299,9 @@ struct Job {
     Ctx* ctx;
     // The hashing is shared.  The device takes whole batches from the front of the list as their PCM arrives (a track
     // costs one of its threads ~0.3 s whatever else happens, a thousand tracks at once cost the same 0.3 s); pool
-    // threads with no file to write take single tracks from the END of the list, out of the caller's memory (a core
-    // hashes a three-minute track in ~55 ms, but there are only host_threads of them).  The device stops claiming
+    // threads with no file to write take up to sixteen tracks at a time from the END of the list and hash them side by
+    // side out of the caller's memory (md5_lanes.cpp: several GB/s per thread, but there are only host_threads of them
+    // and they compete with the copies for the host's memory).  The device stops claiming
     // when the host would be done with everything left before the device could finish one more batch -- so a job
     // of a few long tracks is hashed by the host alone and the last batches of a long job never leave the whole
     // job waiting for one slow device thread.
@@ -313,11 +314,19 @@ struct Job {
     long long host_cursor;      // the next track the host claims (counts down)
     long long dev_end_track;    // tracks [0, dev_end_track) are the device's
     bool dev_stopped;
+    // the host's zone: tracks with at most zone_bytes of PCM from themselves to the end of the list -- what arrives on
+    // the device during the last (one device hash) of the job and could not be hashed there in time.  The pool takes
+    // nothing in front of it while the device is still claiming: hashing more than that on the host only takes
+    // memory bandwidth from the copies (measured: 696 of 1,000 tracks hashed by the pool, copies 15 % slower).
+    const u64* suffix_bytes;    // per track: PCM bytes of tracks t .. n - 1
+    u64 zone_bytes;
     int host_inflight;
     u64 unclaimed_bytes;
     u64 host_bytes; double host_busy_s;   // hashed by the pool so far; seconds its threads spent on it
     u32 host_tracks;
     double t_start, write_busy_s;
+    u64 written_bytes, written_pcm_bytes;
+    int n_threads;
 };
 
 bool write_track(Job* j, const TrackOut& t, std::vector<uint8_t>& head)
@@ -346,46 +355,74 @@ void drain_writes(Job* j, std::vector<uint8_t>& head)
         const double t1 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
         pthread_mutex_lock(&j->mu);
         j->write_busy_s += t1 - t0;
+        j->written_bytes += t.bytes; j->written_pcm_bytes += j->n_pcm_frames[t.track] * j->frame_bytes;
         if (!ok) j->failed = true;
         if (--j->ctx->out[t.outbuf].pending == 0) pthread_cond_broadcast(&j->cv_done);
     }
+}
+
+struct Between { Job* j; std::vector<uint8_t>* head; double spent; };
+
+// between two pieces of hashing: the files that have become ready come first
+int between_pieces(void* arg)
+{
+    Between* b = (Between*)arg;
+    pthread_mutex_lock(&b->j->mu);
+    if (!b->j->tasks.empty()) {
+        const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        drain_writes(b->j, *b->head);
+        b->spent += std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
+    }
+    const bool stop = b->j->quit;
+    pthread_mutex_unlock(&b->j->mu);
+    return stop ? 1 : 0;
 }
 
 void* writer_main(void* arg)
 {
     Job* j = (Job*)arg;
     std::vector<uint8_t> head;
-    const size_t PIECE = 4u << 20;          // files come first: a hashing thread looks for them every few milliseconds
+    Between btw = {j, &head, 0.0};
+    const u64 PIECE = 256u << 10;           // per lane: a hashing thread looks for files to write every ~4 MB
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     pthread_mutex_lock(&j->mu);
     for (;;) {
         if (!j->tasks.empty()) { drain_writes(j, head); continue; }
-        if (j->host_md5 && !j->quit && j->host_cursor >= j->dev_end_track) {
-            const u32 t = (u32)j->host_cursor--;
-            const u64 nb = j->n_pcm_frames[t] * j->frame_bytes;
-            j->host_touched[j->batch_of[t]] = 1;
+        if (j->host_md5 && !j->quit && j->host_cursor >= j->dev_end_track &&
+            (j->dev_stopped || j->suffix_bytes[j->host_cursor] <= j->zone_bytes)) {
+            // up to sixteen tracks from the end of the list, hashed side by side in the lanes of one vector
+            // (md5_lanes.cpp: the chain of one track is as slow as ever, sixteen cost the same)
+            const uint8_t* ptr[16];
+            uint64_t len[16];
+            u32 first = 0, n = 0;
+            u64 nb = 0;
+            // (a fair share of what is there: sixteen lanes cost the time of one, but one lane alone is three times
+            // slower than the scalar code -- a job of a few long tracks gives every thread one track)
+            const long long avail = j->host_cursor - j->dev_end_track + 1;
+            const u32 share = (u32)std::min<long long>(16, std::max<long long>(1, avail / j->n_threads));
+            while (n < share && j->host_cursor >= j->dev_end_track &&
+                   (j->dev_stopped || j->suffix_bytes[j->host_cursor] <= j->zone_bytes)) {
+                const u32 t = (u32)j->host_cursor--;
+                j->host_touched[j->batch_of[t]] = 1;
+                first = t; n++;
+                nb += j->n_pcm_frames[t] * j->frame_bytes;
+            }
+            for (u32 i = 0; i < n; i++) { ptr[i] = j->pcm[first + i]; len[i] = j->n_pcm_frames[first + i] * j->frame_bytes; }
             j->unclaimed_bytes -= nb;
             j->host_inflight++;
             pthread_mutex_unlock(&j->mu);
-            unsigned char st[96];
-            double busy = 0;
-            b200flac_internal_md5_begin(st);
-            for (u64 done = 0; done < nb;) {
-                const size_t n = (size_t)std::min<u64>(PIECE, nb - done);
-                const double t0 = now();
-                b200flac_internal_md5_update(st, j->pcm[t] + done, n);
-                busy += now() - t0;
-                done += n;
-                if (done < nb) {
-                    pthread_mutex_lock(&j->mu);
-                    drain_writes(j, head);
-                    pthread_mutex_unlock(&j->mu);
+            const double t0 = now();
+            btw.spent = 0;
+            if (n >= 4) b200flac_internal_md5_many(ptr, len, n, j->digests + 16 * (size_t)first, PIECE, between_pieces, &btw);
+            else
+                for (u32 i = 0; i < n; i++) {
+                    b200flac_internal_md5(ptr[i], (size_t)len[i], j->digests + 16 * (size_t)(first + i));
+                    if (between_pieces(&btw)) break;
                 }
-            }
-            b200flac_internal_md5_end(st, j->digests + 16 * (size_t)t);
+            const double busy = now() - t0 - btw.spent;     // (hashing alone: the files written in between are not its time)
             pthread_mutex_lock(&j->mu);
             j->host_inflight--;
-            j->host_bytes += nb; j->host_busy_s += busy; j->host_tracks++;
+            j->host_bytes += nb; j->host_busy_s += busy; j->host_tracks += n;
             pthread_cond_broadcast(&j->cv_done);
             continue;
         }
@@ -467,7 +504,10 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
         all_bytes += batches[b].raw;
     }
 
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     Job job;
+    job.t_start = t_start;
     job.filenames = filenames; job.params = params; job.padding_size = padding_size; job.version = version;
     job.n_pcm_frames = n_pcm_frames; job.quit = false; job.failed = false; job.ctx = &c;
     // B200FLAC_FILES_HOST_MD5=0: every hash on the device (A/B measurements)
@@ -475,10 +515,40 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
     job.pcm = pcm; job.frame_bytes = frame_bytes; job.digests = digests.data(); job.batch_of = batch_of.data();
     job.host_touched = host_touched.data(); job.host_cursor = (long long)n_tracks - 1; job.dev_end_track = 0;
     job.dev_stopped = false; job.host_inflight = 0; job.unclaimed_bytes = all_bytes;
-    job.host_bytes = 0; job.host_busy_s = 0; job.host_tracks = 0; job.write_busy_s = 0;
+    std::vector<u64> suffix_bytes((size_t)n_tracks + 1, 0);
+    for (u32 t = n_tracks; t-- > 0;) suffix_bytes[t] = suffix_bytes[t + 1] + n_pcm_frames[t] * frame_bytes;
+    job.suffix_bytes = suffix_bytes.data();
+    job.host_bytes = 0; job.host_busy_s = 0; job.host_tracks = 0; job.write_busy_s = 0; job.n_threads = host_threads;
+    job.written_bytes = 0; job.written_pcm_bytes = 0;
     // what a device thread hashes per second (measured on a B200: the chain is LOP3 -> IADD -> LEA.HI per step)
     double dev_rate = 95e6;
     { const char* e = getenv("B200FLAC_FILES_DEV_MD5_MBS"); if (e && atof(e) > 0) dev_rate = atof(e) * 1e6; }
+    // (until the copies have shown their pace: 36 GB/s, a B200's inbound copies next to outbound ones and a busy pool)
+    u64 longest_track = 0;
+    for (u32 t = 0; t < n_tracks; t++) longest_track = std::max<u64>(longest_track, n_pcm_frames[t] * frame_bytes);
+    const double dev_hash_s = (double)longest_track / dev_rate;
+    u64 arrived_bytes = 0;
+    // How much of the end of the list is the pool's (mutex held).  With the copies arriving at `pace`, a batch is hashed
+    // on the device dev_hash_s after it arrives, so the device is done in time with everything but the last
+    // pace * dev_hash_s bytes; the pool takes those if it can hash them by then -- at the rate its threads have shown,
+    // with the threads that writing the files (which comes first) leaves over -- and otherwise as much as makes the
+    // two finish together.  Every quantity is the job's own measurement once there is one.
+    const char* zone_forced = getenv("B200FLAC_FILES_HOST_ZONE_MB");     // tests: a fixed zone
+    auto host_zone = [&]() -> u64 {
+        if (zone_forced) return (u64)(atof(zone_forced) * 1048576.0);
+        const double el = now() - job.t_start;
+        const double pace = (el > 0.05 && arrived_bytes) ? (double)arrived_bytes / el : 36e9;
+        const double t_run = (double)all_bytes / pace;
+        const double write_rate = job.write_busy_s > 0.02 ? (double)job.written_bytes / job.write_busy_s : 2.0e9;   // per thread
+        const double ratio = job.written_pcm_bytes ? (double)job.written_bytes / (double)job.written_pcm_bytes : 0.7;
+        const double write_s = (double)all_bytes * ratio / write_rate;                                           // thread-seconds
+        const double spare = (double)host_threads - write_s / (t_run + dev_hash_s);
+        if (spare <= 0) return 0;
+        const double hash_rate = job.host_busy_s > 0.02 ? (double)job.host_bytes / job.host_busy_s : 2.5e9;     // per thread
+        const double hr = 0.8 * hash_rate * spare;
+        return (u64)std::min(pace * dev_hash_s, (t_run + dev_hash_s) / (1.0 / hr + 1.0 / pace));
+    };
+    job.zone_bytes = host_zone();
     pthread_mutex_init(&job.mu, nullptr);
     pthread_cond_init(&job.cv_task, nullptr);
     pthread_cond_init(&job.cv_done, nullptr);
@@ -490,9 +560,6 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
     // B200FLAC_FILES_TRACE=1: where the orchestrating thread waited, to stderr
     const bool trace = getenv("B200FLAC_FILES_TRACE") != nullptr;
     double w_ring = 0, w_h2d = 0, w_collect = 0, w_writers = 0, w_d2h = 0, w_tail_files = 0, w_tail_md5 = 0, w_submit = 0;
-    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_start = now();
-    job.t_start = t_start;
     std::vector<char> submitted((size_t)NB, 0);
     int next_h2d = 0;                      // next batch whose copy has not been issued
     bool fail = false;
@@ -513,15 +580,12 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
         bool dev = true;
         pthread_mutex_lock(&job.mu);
         if (job.host_md5) {
-            if (job.dev_stopped || job.host_touched[(size_t)b]) dev = false;
-            else {
-                // what the pool has hashed per second of the job so far -- next to writing the files, which is most
-                // of its work (before there is a measurement: half of what its threads could do undisturbed)
-                const double el = now() - job.t_start;
-                const double host_rate = (el > 0.05 && job.host_bytes) ? (double)job.host_bytes / el : 0.5 * 550e6 * host_threads;
-                dev = (double)bb.longest / dev_rate < (double)job.unclaimed_bytes / host_rate;
-            }
+            arrived_bytes += bb.raw;
+            job.zone_bytes = host_zone();
+            // in front of the zone: the device's; the first batch that reaches into it ends the device's share
+            dev = !job.dev_stopped && !job.host_touched[(size_t)b] && job.suffix_bytes[bb.first + bb.count - 1] > job.zone_bytes;
             if (!dev) job.dev_stopped = true;
+            pthread_cond_broadcast(&job.cv_task);       // (the zone has moved, or the rest is the pool's)
         }
         if (dev) { job.dev_end_track = (long long)bb.first + bb.count; job.unclaimed_bytes -= bb.raw; dev_tracks += bb.count; }
         pthread_mutex_unlock(&job.mu);

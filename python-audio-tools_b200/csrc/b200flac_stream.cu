@@ -126,12 +126,6 @@ extern "C" void b200flac_internal_md5(const uint8_t* p, size_t n, uint8_t out[16
     md5_final(&m, out);
 }
 
-// the same digest in pieces (b200flac_batch.cu: a pool thread hashes a track between file writes);
-// `state` is 96 bytes the caller owns
-extern "C" void b200flac_internal_md5_begin(void* state) { static_assert(sizeof(Md5) <= 96, "Md5 state"); md5_init((Md5*)state); }
-extern "C" void b200flac_internal_md5_update(void* state, const uint8_t* p, size_t n) { md5_update((Md5*)state, p, n); }
-extern "C" void b200flac_internal_md5_end(void* state, uint8_t out[16]) { md5_final((Md5*)state, out); }
-
 // ---------------------------------------------------------------------------
 struct Lane {
     b200flac_encoder* enc;

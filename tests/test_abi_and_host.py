@@ -278,3 +278,15 @@ def test_standalone_driver_cli(tmp_path, built):
         r = subprocess.run([exe, "-q", os.path.join(str(tmp_path), "x.flac")], input=b"\0" * 64, stdout=subprocess.PIPE,
                            stderr=subprocess.PIPE)
         assert r.returncode == 1 and b"no CPU fallback" in r.stderr
+
+
+def test_host_md5_lanes_match_hashlib(built):
+    """csrc/md5_lanes.cpp (sixteen MD5 chains side by side, the host's share of b200flac_encode_files' hashing):
+    ragged lengths around every padding boundary, fewer than sixteen strings, lanes that finish at different blocks"""
+    import hashlib
+    import b200flac
+    rng = np.random.RandomState(11)
+    for lens in ([0, 1, 3, 55, 56, 57, 63, 64, 65, 119, 120, 121, 127, 128, 129, 1000],
+                 [4096 * 4 + 2, (1 << 20) + 3, 5], [100000 + 977 * i for i in range(16)], [64 * 1000] * 16, [7], [0]):
+        datas = [rng.randint(0, 256, size=n).astype(np.uint8).tobytes() for n in lens]
+        assert b200flac.host_md5_many(datas) == [hashlib.md5(d).digest() for d in datas], lens

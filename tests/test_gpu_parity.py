@@ -641,8 +641,8 @@ def test_encode_files_equals_encode_file(shape, tmp_path, built):
 def test_encode_files_hash_sharing(mode, tmp_path, built):
     """the STREAMINFO MD5s are shared between the device (whole batches from the front of the list) and the pool's idle
     host threads (single tracks from its end): whoever hashes a track, the digest is hashlib's -- all on the device
-    (B200FLAC_FILES_HOST_MD5=0), all on the host (a device rate so low that it never claims a batch), and the two
-    fronts meeting somewhere in the list (a device rate so high that it claims every batch the host has not touched)"""
+    (B200FLAC_FILES_HOST_MD5=0), all on the host (a device rate so low that the whole list is the host's zone), and
+    the two fronts meeting in the middle of the list (a host zone fixed at half of the job's PCM)"""
     b = _b200()
     o = helpers.options(block_size=4096, max_lpc_order=8, max_residual_partition_order=4)
     kw = {k: v for k, v in o.items() if k != "padding_size"}
@@ -653,7 +653,7 @@ def test_encode_files_hash_sharing(mode, tmp_path, built):
     names = [os.path.join(str(tmp_path), "h_%d.flac" % i) for i in range(len(lengths))]
     env = {"B200FLAC_FILES_BATCH_MB": "1", "B200FLAC_FILES_RING": "5"}
     env.update({"device_only": {"B200FLAC_FILES_HOST_MD5": "0"}, "host_only": {"B200FLAC_FILES_DEV_MD5_MBS": "0.000001"},
-                "device_first": {"B200FLAC_FILES_DEV_MD5_MBS": "1000000"}}[mode])
+                "device_first": {"B200FLAC_FILES_HOST_ZONE_MB": "3"}}[mode])
     for threads in (1, 4):
         _with_env(env, lambda: b.encode_files(names, p, bufs, lengths, device=0, host_threads=threads))
         for i, name in enumerate(names):

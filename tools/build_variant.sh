@@ -10,5 +10,5 @@ nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler
      -c -o build/obj_$tag/b200flac_encoder.o csrc/b200flac_encoder.cu
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o libb200flac_$tag.so build/obj_$tag/b200flac_encoder.o \
      build/obj/b200flac_stream.o build/obj/b200flac_batch.o build/obj/b200flac_metadata.o build/obj/b200flac_pcmfile.o build/obj/b200flac_decoder.o \
-     build/obj/b200tta.o build/obj/b200alac.o -lpthread
+     build/obj/b200tta.o build/obj/b200alac.o build/obj/md5_lanes.o -lpthread
 echo built libb200flac_$tag.so
