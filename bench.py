@@ -753,7 +753,7 @@ def main():
                 "speedup_over_one_call_per_file": t_tr / t_bt,
                 "what": "the same tracks as ONE b200flac_encode_files job per rank: many-segment batches of the frame "
                         "layer, the tracks' STREAMINFO MD5s computed on the device (one thread per track, whole batches from the "
-                        "front of the list) and by idle pool threads (single tracks from its end), %d host "
+                        "front of the list) and by spare pool threads (the end of the list, sixteen tracks at a time in vector lanes), %d host "
                         "threads write the files to tmpfs; PCM read from page-locked memory" % threads}
 
     # ---- the other BASELINE configurations, device resident ----

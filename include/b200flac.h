@@ -266,8 +266,8 @@ int b200flac_encode_file(const char *filename, const b200flac_params *params,
  * many-segment batches of the frame layer, and the STREAMINFO MD5 of every track (the per-stream serial step that
  * bounds the one-call-per-file path: ~50 ms of one core per three-minute track) is computed on the device, one thread
  * per track, from the PCM that is there for the encoder anyway -- whole batches from the front of the list as they
- * arrive -- while host threads with no file to write hash single tracks from the end of the list out of pcm[i]; the
- * device stops claiming batches when the host would finish what is left sooner (a few long tracks: host only).
+ * arrive -- while host threads with no file to write hash the end of the list (what the device could not finish in
+ * time) out of pcm[i], sixteen tracks at a time in the lanes of one vector (a few long tracks: host only).
  * pcm[i] should be page-locked (b200flac_host_alloc) for full copy speed.  device < 0: B200FLAC_DEVICE or 0.
  * host_threads (<= 0: 8) write the files and share the hashing.
  * Returns 0 on success. */
