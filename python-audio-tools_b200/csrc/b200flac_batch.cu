@@ -9,9 +9,11 @@
 //     caller's memory, and encoded as many-segment batches of the frame layer (one segment per track);
 //   * the MD5 of every track is computed ON THE DEVICE from the PCM that is there anyway: MD5 is serial inside a
 //     stream but the streams are independent -- one thread per track, a warp hashes 32 tracks in lockstep.  A track
-//     takes a thread ~0.3 s, so the regions stay alive in a ring until their kernel is done;
-//   * frames come back through two pinned buffers and a pool of host threads writes the files (head, frames);
-//     the 16 bytes of MD5 are patched into each STREAMINFO when the batch's hashes arrive.
+//     takes a thread ~0.3 s, so the regions stay alive in a ring until their kernel is done -- and the END of the
+//     list, which the device could not hash in time, is hashed by the pool's spare host threads, sixteen tracks at a
+//     time in the lanes of one vector (md5_lanes.cpp);
+//   * frames come back through three pinned buffers and a pool of host threads writes the files (head, frames);
+//     the 16 bytes of MD5 are patched into each STREAMINFO at the end.
 // Every file is byte for byte what b200flac_encode_file writes for the same track (tests/test_gpu_parity.py).
 #include <cuda_runtime.h>
 #include <pthread.h>
@@ -269,7 +271,7 @@ int ctx_prepare(Ctx& c, const b200flac_params* p, int device, u64 batch_bytes, u
         CK(cudaMallocHost((void**)&r.h_digest, 16 * (size_t)c.cap_tracks));
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        CK(cudaStreamCreateWithPriority(&r.st, cudaStreamNonBlocking, getenv("B200FLAC_FILES_MD5_LOW") ? lo : hi));
+        CK(cudaStreamCreateWithPriority(&r.st, cudaStreamNonBlocking, hi));
         CK(cudaEventCreateWithFlags(&r.ev_h2d, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&r.ev_md5, cudaEventDisableTiming));
         c.ring.push_back(r);
@@ -301,10 +303,9 @@ struct Job {
     // costs one of its threads ~0.3 s whatever else happens, a thousand tracks at once cost the same 0.3 s); pool
     // threads with no file to write take up to sixteen tracks at a time from the END of the list and hash them side by
     // side out of the caller's memory (md5_lanes.cpp: several GB/s per thread, but there are only host_threads of them
-    // and they compete with the copies for the host's memory).  The device stops claiming
-    // when the host would be done with everything left before the device could finish one more batch -- so a job
-    // of a few long tracks is hashed by the host alone and the last batches of a long job never leave the whole
-    // job waiting for one slow device thread.
+    // and they compete with the copies for the host's memory).  The device's share ends at the first batch that
+    // reaches into the host's zone (below) -- so the last batches of a long job never leave the whole job waiting
+    // for one slow device thread, and a job of a few long tracks is hashed by the host alone.
     bool host_md5;
     const uint8_t* const* pcm;
     u64 frame_bytes;
@@ -321,7 +322,6 @@ struct Job {
     const u64* suffix_bytes;    // per track: PCM bytes of tracks t .. n - 1
     u64 zone_bytes;
     int host_inflight;
-    u64 unclaimed_bytes;
     u64 host_bytes; double host_busy_s;   // hashed by the pool so far; seconds its threads spent on it
     u32 host_tracks;
     double t_start, write_busy_s;
@@ -408,7 +408,6 @@ void* writer_main(void* arg)
                 nb += j->n_pcm_frames[t] * j->frame_bytes;
             }
             for (u32 i = 0; i < n; i++) { ptr[i] = j->pcm[first + i]; len[i] = j->n_pcm_frames[first + i] * j->frame_bytes; }
-            j->unclaimed_bytes -= nb;
             j->host_inflight++;
             pthread_mutex_unlock(&j->mu);
             const double t0 = now();
@@ -514,7 +513,7 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
     { const char* e = getenv("B200FLAC_FILES_HOST_MD5"); job.host_md5 = !(e && atoi(e) == 0) && !(dbg & 1); }
     job.pcm = pcm; job.frame_bytes = frame_bytes; job.digests = digests.data(); job.batch_of = batch_of.data();
     job.host_touched = host_touched.data(); job.host_cursor = (long long)n_tracks - 1; job.dev_end_track = 0;
-    job.dev_stopped = false; job.host_inflight = 0; job.unclaimed_bytes = all_bytes;
+    job.dev_stopped = false; job.host_inflight = 0;
     std::vector<u64> suffix_bytes((size_t)n_tracks + 1, 0);
     for (u32 t = n_tracks; t-- > 0;) suffix_bytes[t] = suffix_bytes[t + 1] + n_pcm_frames[t] * frame_bytes;
     job.suffix_bytes = suffix_bytes.data();
@@ -587,7 +586,7 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
             if (!dev) job.dev_stopped = true;
             pthread_cond_broadcast(&job.cv_task);       // (the zone has moved, or the rest is the pool's)
         }
-        if (dev) { job.dev_end_track = (long long)bb.first + bb.count; job.unclaimed_bytes -= bb.raw; dev_tracks += bb.count; }
+        if (dev) { job.dev_end_track = (long long)bb.first + bb.count; dev_tracks += bb.count; }
         pthread_mutex_unlock(&job.mu);
         return dev;
     };
