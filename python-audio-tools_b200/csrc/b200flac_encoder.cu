@@ -1224,10 +1224,11 @@ __global__ void k_copy_words(u32* __restrict__ dst, const u32* __restrict__ src,
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
     __threadfence_system();
 }
-static void copy_by_kernel(void* dst, const void* src, size_t bytes, cudaStream_t st)
+static void copy_by_kernel(b200flac_encoder* enc, void* dst, const void* src, size_t bytes, cudaStream_t st)
 {
     const size_t n = bytes / 4;       // (every table copied this way is a whole number of words)
     if (!n) return;
+    count_launches(enc, 1);
     const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 296);
     k_copy_words<<<blocks, 256, 0, st>>>((u32*)dst, (const u32*)src, n);
 }
@@ -1251,14 +1252,14 @@ extern "C" int b200flac_encoder_submit_device(b200flac_encoder* enc, int slot, c
     s.busy = true;
     if (nf == 0) { s.timed = false; *s.h_total = 0; return 0; }
     cudaStream_t st = s.stream;
-    copy_by_kernel(s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), st);
-    if (s.n_odd) copy_by_kernel(s.d_odd, s.h_odd, (size_t)s.n_odd * sizeof(u32), st);
-    if (enc->P.try_lpc) copy_by_kernel(s.d_tasks, s.h_tasks, (size_t)s.n_tasks * sizeof(bf_lpc_task), st);
+    copy_by_kernel(enc, s.d_fd, s.h_fd, (size_t)nf * sizeof(bf_frame_desc), st);
+    if (s.n_odd) copy_by_kernel(enc, s.d_odd, s.h_odd, (size_t)s.n_odd * sizeof(u32), st);
+    if (enc->P.try_lpc) copy_by_kernel(enc, s.d_tasks, s.h_tasks, (size_t)s.n_tasks * sizeof(bf_lpc_task), st);
     const size_t wused = (size_t)s.h_total[1];
-    if (wused) copy_by_kernel(s.d_win, s.h_win, wused * sizeof(double), st);
+    if (wused) copy_by_kernel(enc, s.d_win, s.h_win, wused * sizeof(double), st);
     if (launch_batch(enc, s, (const uint8_t*)d_pcm, (uint8_t*)d_out, s.dev_cap)) { s.busy = false; return 1; }
-    copy_by_kernel(s.h_total, s.d_total, sizeof(u64), st);
-    copy_by_kernel(s.h_frame_bytes, s.d_frame_bytes, (size_t)nf * sizeof(u32), st);
+    copy_by_kernel(enc, s.h_total, s.d_total, sizeof(u64), st);
+    copy_by_kernel(enc, s.h_frame_bytes, s.d_frame_bytes, (size_t)nf * sizeof(u32), st);
     CU_CHECK(cudaGetLastError(), 1);
     CU_CHECK(cudaEventRecord(s.ev_done, st), 1);
     return 0;
