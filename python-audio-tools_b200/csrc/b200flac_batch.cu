@@ -115,9 +115,14 @@ k_md5_tracks(const uint8_t* __restrict__ base, const u64* __restrict__ off, cons
     // the next block's four loads are in flight while this one is hashed
     uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, n2 = n0, n3 = n0;
     if (nblocks) { n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); }
+    // ... and the lines eight blocks further on are asked into L2: every lane walks its own track, so each load is a
+    // DRAM access of its own, and one block of hashing (~1,000 cycles) does not cover it (ncu: the warp waited on the
+    // long scoreboard half of its time)
+    const u64 AHEAD = 8;
 #pragma unroll 1
     for (u64 i = 0; i < nblocks; i++) {
         const u32 x[16] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, n3.z, n3.w};
+        if (i + 1 + AHEAD < nblocks) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 4 * (i + 1 + AHEAD)));
         if (i + 1 < nblocks) {
             const uint4* q = p + 4 * (i + 1);
             n0 = __ldg(q); n1 = __ldg(q + 1); n2 = __ldg(q + 2); n3 = __ldg(q + 3);
@@ -519,8 +524,9 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
     job.suffix_bytes = suffix_bytes.data();
     job.host_bytes = 0; job.host_busy_s = 0; job.host_tracks = 0; job.write_busy_s = 0; job.n_threads = host_threads;
     job.written_bytes = 0; job.written_pcm_bytes = 0;
-    // what a device thread hashes per second (measured on a B200: the chain is LOP3 -> IADD -> LEA.HI per step)
-    double dev_rate = 95e6;
+    // what a device thread hashes per second inside a job (measured on a B200; alone, with the chain at LOP3 -> IADD ->
+    // LEA.HI per step and the lines ahead asked into L2, it makes 107-121 MB/s: tools/md5_rate.py)
+    double dev_rate = 100e6;
     { const char* e = getenv("B200FLAC_FILES_DEV_MD5_MBS"); if (e && atof(e) > 0) dev_rate = atof(e) * 1e6; }
     // (until the copies have shown their pace: 36 GB/s, a B200's inbound copies next to outbound ones and a busy pool)
     u64 longest_track = 0;
