@@ -647,7 +647,8 @@ def test_encode_files_hash_sharing(mode, tmp_path, built):
     o = helpers.options(block_size=4096, max_lpc_order=8, max_residual_partition_order=4)
     kw = {k: v for k, v in o.items() if k != "padding_size"}
     p = b.make_params(44100, 2, 16, **kw)
-    lengths = [20000 + 1777 * (i % 9) for i in range(60)] + [0, 1, 4097]
+    # (one track longer than a whole batch in the middle of the list, an empty one and two tiny ones at its end)
+    lengths = [20000 + 1777 * (i % 9) for i in range(30)] + [800000] + [20000 + 1777 * (i % 9) for i in range(30)] + [0, 1, 4097]
     pcms = [helpers.synth_pcm(1300 + i, 2, 16, n) if n else b"" for i, n in enumerate(lengths)]
     bufs = [np.frombuffer(pcm if n else b"\0" * 16, dtype=np.uint8).copy() for pcm, n in zip(pcms, lengths)]
     names = [os.path.join(str(tmp_path), "h_%d.flac" % i) for i in range(len(lengths))]
