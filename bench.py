@@ -740,6 +740,8 @@ def main():
             batch_job(my_tracks)
             barrier()
             t_bt = allmax(time.perf_counter() - t0)
+            st = (C.c_double * 6)()
+            L.b200flac_internal_batch_stats(st)
             encode_file(os.path.join(tmp.name, "bt_check.flac"), ((my_tracks - 1) % distinct) * tn, tn, p8)
             same = open(os.path.join(tmp.name, "bt_check.flac"), "rb").read() == open(names[my_tracks - 1], "rb").read()
             if not same:
@@ -751,6 +753,9 @@ def main():
                 "tracks_per_s": total_tracks / t_bt, "seconds": t_bt, "host_threads_per_rank": threads,
                 "projected_s_for_10000_tracks": 10000.0 * t_bt / total_tracks, "identical_to_encode_file": True,
                 "speedup_over_one_call_per_file": t_tr / t_bt,
+                "hashed_rank0": {"device_tracks": int(st[0]), "host_tracks": int(st[1]),
+                                 "host_hash_mb_per_s_per_thread": st[2] / 1e6, "file_write_mb_per_s_per_thread": st[3] / 1e6,
+                                 "host_hash_thread_s": st[4], "file_write_thread_s": st[5]},
                 "what": "the same tracks as ONE b200flac_encode_files job per rank: many-segment batches of the frame "
                         "layer, the tracks' STREAMINFO MD5s computed on the device (one thread per track, whole batches from the "
                         "front of the list) and by spare pool threads (the end of the list, sixteen tracks at a time in vector lanes), %d host "

@@ -439,6 +439,15 @@ void* writer_main(void* arg)
 
 } // namespace
 
+// who hashed the tracks of the last job, and at what rates (bench.py reports it next to the job's time)
+static double g_last_stats[6];
+extern "C" void b200flac_internal_batch_stats(double out[6])
+{
+    pthread_mutex_lock(&g_ctx_mu);
+    for (int i = 0; i < 6; i++) out[i] = g_last_stats[i];
+    pthread_mutex_unlock(&g_ctx_mu);
+}
+
 extern "C" void b200flac_internal_batch_clear(void)
 {
     pthread_mutex_lock(&g_ctx_mu);
@@ -802,6 +811,10 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
                 n_tracks, NB, c.ring.size(), now() - t_start, w_ring, w_h2d, w_submit, w_collect, w_writers, w_d2h,
                 w_tail_files, w_tail_md5, dev_tracks, job.host_tracks,
                 job.host_busy_s > 0 ? job.host_bytes / job.host_busy_s / 1e6 : 0.0, job.host_busy_s, job.write_busy_s);
+    g_last_stats[0] = dev_tracks; g_last_stats[1] = job.host_tracks;
+    g_last_stats[2] = job.host_busy_s > 0 ? job.host_bytes / job.host_busy_s : 0.0;          // bytes per second per pool thread, hashing
+    g_last_stats[3] = job.write_busy_s > 0 ? job.written_bytes / job.write_busy_s : 0.0;    // bytes per second per pool thread, writing files
+    g_last_stats[4] = job.host_busy_s; g_last_stats[5] = job.write_busy_s;                  // thread-seconds
     pthread_mutex_destroy(&job.mu);
     pthread_cond_destroy(&job.cv_task);
     pthread_cond_destroy(&job.cv_done);
