@@ -20,6 +20,57 @@ typedef uint32_t vu32 __attribute__((vector_size(4 * LANES)));
 #define F4(x, y, z) ((y) ^ ((x) | ~(z)))
 #define STEP(f, w, x, y, z, data, k, s) (w += f(x, y, z) + (data) + (uint32_t)(k), w = ROL(w, s) + (x))
 
+// the 64 steps on quantities a, b, c, d and message words x[16] of any type with +, ^, &, |, ~, <<, >> (one string: uint32_t;
+// sixteen strings: a vector)
+#define MD5_ROUNDS \
+    STEP(F1, a, b, c, d, x[0], 0xd76aa478, 7);   STEP(F1, d, a, b, c, x[1], 0xe8c7b756, 12); \
+    STEP(F1, c, d, a, b, x[2], 0x242070db, 17);  STEP(F1, b, c, d, a, x[3], 0xc1bdceee, 22); \
+    STEP(F1, a, b, c, d, x[4], 0xf57c0faf, 7);   STEP(F1, d, a, b, c, x[5], 0x4787c62a, 12); \
+    STEP(F1, c, d, a, b, x[6], 0xa8304613, 17);  STEP(F1, b, c, d, a, x[7], 0xfd469501, 22); \
+    STEP(F1, a, b, c, d, x[8], 0x698098d8, 7);   STEP(F1, d, a, b, c, x[9], 0x8b44f7af, 12); \
+    STEP(F1, c, d, a, b, x[10], 0xffff5bb1, 17); STEP(F1, b, c, d, a, x[11], 0x895cd7be, 22); \
+    STEP(F1, a, b, c, d, x[12], 0x6b901122, 7);  STEP(F1, d, a, b, c, x[13], 0xfd987193, 12); \
+    STEP(F1, c, d, a, b, x[14], 0xa679438e, 17); STEP(F1, b, c, d, a, x[15], 0x49b40821, 22); \
+    STEP(F2, a, b, c, d, x[1], 0xf61e2562, 5);   STEP(F2, d, a, b, c, x[6], 0xc040b340, 9); \
+    STEP(F2, c, d, a, b, x[11], 0x265e5a51, 14); STEP(F2, b, c, d, a, x[0], 0xe9b6c7aa, 20); \
+    STEP(F2, a, b, c, d, x[5], 0xd62f105d, 5);   STEP(F2, d, a, b, c, x[10], 0x02441453, 9); \
+    STEP(F2, c, d, a, b, x[15], 0xd8a1e681, 14); STEP(F2, b, c, d, a, x[4], 0xe7d3fbc8, 20); \
+    STEP(F2, a, b, c, d, x[9], 0x21e1cde6, 5);   STEP(F2, d, a, b, c, x[14], 0xc33707d6, 9); \
+    STEP(F2, c, d, a, b, x[3], 0xf4d50d87, 14);  STEP(F2, b, c, d, a, x[8], 0x455a14ed, 20); \
+    STEP(F2, a, b, c, d, x[13], 0xa9e3e905, 5);  STEP(F2, d, a, b, c, x[2], 0xfcefa3f8, 9); \
+    STEP(F2, c, d, a, b, x[7], 0x676f02d9, 14);  STEP(F2, b, c, d, a, x[12], 0x8d2a4c8a, 20); \
+    STEP(F3, a, b, c, d, x[5], 0xfffa3942, 4);   STEP(F3, d, a, b, c, x[8], 0x8771f681, 11); \
+    STEP(F3, c, d, a, b, x[11], 0x6d9d6122, 16); STEP(F3, b, c, d, a, x[14], 0xfde5380c, 23); \
+    STEP(F3, a, b, c, d, x[1], 0xa4beea44, 4);   STEP(F3, d, a, b, c, x[4], 0x4bdecfa9, 11); \
+    STEP(F3, c, d, a, b, x[7], 0xf6bb4b60, 16);  STEP(F3, b, c, d, a, x[10], 0xbebfbc70, 23); \
+    STEP(F3, a, b, c, d, x[13], 0x289b7ec6, 4);  STEP(F3, d, a, b, c, x[0], 0xeaa127fa, 11); \
+    STEP(F3, c, d, a, b, x[3], 0xd4ef3085, 16);  STEP(F3, b, c, d, a, x[6], 0x04881d05, 23); \
+    STEP(F3, a, b, c, d, x[9], 0xd9d4d039, 4);   STEP(F3, d, a, b, c, x[12], 0xe6db99e5, 11); \
+    STEP(F3, c, d, a, b, x[15], 0x1fa27cf8, 16); STEP(F3, b, c, d, a, x[2], 0xc4ac5665, 23); \
+    STEP(F4, a, b, c, d, x[0], 0xf4292244, 6);   STEP(F4, d, a, b, c, x[7], 0x432aff97, 10); \
+    STEP(F4, c, d, a, b, x[14], 0xab9423a7, 15); STEP(F4, b, c, d, a, x[5], 0xfc93a039, 21); \
+    STEP(F4, a, b, c, d, x[12], 0x655b59c3, 6);  STEP(F4, d, a, b, c, x[3], 0x8f0ccc92, 10); \
+    STEP(F4, c, d, a, b, x[10], 0xffeff47d, 15); STEP(F4, b, c, d, a, x[1], 0x85845dd1, 21); \
+    STEP(F4, a, b, c, d, x[8], 0x6fa87e4f, 6);   STEP(F4, d, a, b, c, x[15], 0xfe2ce6e0, 10); \
+    STEP(F4, c, d, a, b, x[6], 0xa3014314, 15);  STEP(F4, b, c, d, a, x[13], 0x4e0811a1, 21); \
+    STEP(F4, a, b, c, d, x[4], 0xf7537e82, 6);   STEP(F4, d, a, b, c, x[11], 0xbd3af235, 10); \
+    STEP(F4, c, d, a, b, x[2], 0x2ad7d2bb, 15);  STEP(F4, b, c, d, a, x[9], 0xeb86d391, 21);
+
+// one string, scalar: what a lane falls back to when it is (nearly) alone -- one chain in a sixteen-lane vector runs at
+// a third of the scalar code's speed
+static void md5_scalar_blocks(uint32_t st[4], const uint8_t* p, size_t nblocks)
+{
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3];
+    for (size_t blk = 0; blk < nblocks; blk++, p += 64) {
+        uint32_t x[16];
+        memcpy(x, p, 64);           // little-endian host
+        const uint32_t a0 = a, b0 = b, c0 = c, d0 = d;
+        MD5_ROUNDS
+        a += a0; b += b0; c += c0; d += d0;
+    }
+    st[0] = a; st[1] = b; st[2] = c; st[3] = d;
+}
+
 // state[q][lane], q = a, b, c, d; lane l consumes `nblocks` 64-byte blocks at ptr[l], ptr[l] + stride[l], ...
 // (stride 64, or 0 for a lane that has nothing to hash and rereads one dummy block)
 __attribute__((target_clones("avx512f", "avx2", "default")))
@@ -39,38 +90,7 @@ static void md5_lanes_blocks(uint32_t state[4][LANES], const uint8_t* const ptr[
             memcpy(&x[i], col, sizeof(col));
         }
         const vu32 a0 = a, b0 = b, c0 = c, d0 = d;
-        STEP(F1, a, b, c, d, x[0], 0xd76aa478, 7);   STEP(F1, d, a, b, c, x[1], 0xe8c7b756, 12);
-        STEP(F1, c, d, a, b, x[2], 0x242070db, 17);  STEP(F1, b, c, d, a, x[3], 0xc1bdceee, 22);
-        STEP(F1, a, b, c, d, x[4], 0xf57c0faf, 7);   STEP(F1, d, a, b, c, x[5], 0x4787c62a, 12);
-        STEP(F1, c, d, a, b, x[6], 0xa8304613, 17);  STEP(F1, b, c, d, a, x[7], 0xfd469501, 22);
-        STEP(F1, a, b, c, d, x[8], 0x698098d8, 7);   STEP(F1, d, a, b, c, x[9], 0x8b44f7af, 12);
-        STEP(F1, c, d, a, b, x[10], 0xffff5bb1, 17); STEP(F1, b, c, d, a, x[11], 0x895cd7be, 22);
-        STEP(F1, a, b, c, d, x[12], 0x6b901122, 7);  STEP(F1, d, a, b, c, x[13], 0xfd987193, 12);
-        STEP(F1, c, d, a, b, x[14], 0xa679438e, 17); STEP(F1, b, c, d, a, x[15], 0x49b40821, 22);
-        STEP(F2, a, b, c, d, x[1], 0xf61e2562, 5);   STEP(F2, d, a, b, c, x[6], 0xc040b340, 9);
-        STEP(F2, c, d, a, b, x[11], 0x265e5a51, 14); STEP(F2, b, c, d, a, x[0], 0xe9b6c7aa, 20);
-        STEP(F2, a, b, c, d, x[5], 0xd62f105d, 5);   STEP(F2, d, a, b, c, x[10], 0x02441453, 9);
-        STEP(F2, c, d, a, b, x[15], 0xd8a1e681, 14); STEP(F2, b, c, d, a, x[4], 0xe7d3fbc8, 20);
-        STEP(F2, a, b, c, d, x[9], 0x21e1cde6, 5);   STEP(F2, d, a, b, c, x[14], 0xc33707d6, 9);
-        STEP(F2, c, d, a, b, x[3], 0xf4d50d87, 14);  STEP(F2, b, c, d, a, x[8], 0x455a14ed, 20);
-        STEP(F2, a, b, c, d, x[13], 0xa9e3e905, 5);  STEP(F2, d, a, b, c, x[2], 0xfcefa3f8, 9);
-        STEP(F2, c, d, a, b, x[7], 0x676f02d9, 14);  STEP(F2, b, c, d, a, x[12], 0x8d2a4c8a, 20);
-        STEP(F3, a, b, c, d, x[5], 0xfffa3942, 4);   STEP(F3, d, a, b, c, x[8], 0x8771f681, 11);
-        STEP(F3, c, d, a, b, x[11], 0x6d9d6122, 16); STEP(F3, b, c, d, a, x[14], 0xfde5380c, 23);
-        STEP(F3, a, b, c, d, x[1], 0xa4beea44, 4);   STEP(F3, d, a, b, c, x[4], 0x4bdecfa9, 11);
-        STEP(F3, c, d, a, b, x[7], 0xf6bb4b60, 16);  STEP(F3, b, c, d, a, x[10], 0xbebfbc70, 23);
-        STEP(F3, a, b, c, d, x[13], 0x289b7ec6, 4);  STEP(F3, d, a, b, c, x[0], 0xeaa127fa, 11);
-        STEP(F3, c, d, a, b, x[3], 0xd4ef3085, 16);  STEP(F3, b, c, d, a, x[6], 0x04881d05, 23);
-        STEP(F3, a, b, c, d, x[9], 0xd9d4d039, 4);   STEP(F3, d, a, b, c, x[12], 0xe6db99e5, 11);
-        STEP(F3, c, d, a, b, x[15], 0x1fa27cf8, 16); STEP(F3, b, c, d, a, x[2], 0xc4ac5665, 23);
-        STEP(F4, a, b, c, d, x[0], 0xf4292244, 6);   STEP(F4, d, a, b, c, x[7], 0x432aff97, 10);
-        STEP(F4, c, d, a, b, x[14], 0xab9423a7, 15); STEP(F4, b, c, d, a, x[5], 0xfc93a039, 21);
-        STEP(F4, a, b, c, d, x[12], 0x655b59c3, 6);  STEP(F4, d, a, b, c, x[3], 0x8f0ccc92, 10);
-        STEP(F4, c, d, a, b, x[10], 0xffeff47d, 15); STEP(F4, b, c, d, a, x[1], 0x85845dd1, 21);
-        STEP(F4, a, b, c, d, x[8], 0x6fa87e4f, 6);   STEP(F4, d, a, b, c, x[15], 0xfe2ce6e0, 10);
-        STEP(F4, c, d, a, b, x[6], 0xa3014314, 15);  STEP(F4, b, c, d, a, x[13], 0x4e0811a1, 21);
-        STEP(F4, a, b, c, d, x[4], 0xf7537e82, 6);   STEP(F4, d, a, b, c, x[11], 0xbd3af235, 10);
-        STEP(F4, c, d, a, b, x[2], 0x2ad7d2bb, 15);  STEP(F4, b, c, d, a, x[9], 0xeb86d391, 21);
+        MD5_ROUNDS
         a += a0; b += b0; c += c0; d += d0;
     }
     memcpy(state[0], &a, sizeof(a)); memcpy(state[1], &b, sizeof(b));
@@ -111,10 +131,23 @@ extern "C" int b200flac_internal_md5_many(const uint8_t* const* ptr, const uint6
             p[l] = idle[l] ? nothing : ptr[l] + 64 * done[l];
             stride[l] = idle[l] ? 0 : 64;
         }
-        md5_lanes_blocks(st, p, stride, (size_t)step);
-        for (int l = 0; l < LANES; l++) {
-            if (idle[l]) for (int q = 0; q < 4; q++) st[q][l] = keep[q][l];
-            else done[l] += step;
+        int active = 0;
+        for (int l = 0; l < LANES; l++) active += idle[l] ? 0 : 1;
+        if (active <= 2) {
+            // (ragged lists: the long track that is left over when its neighbours are done)
+            for (int l = 0; l < LANES; l++) {
+                if (idle[l]) continue;
+                uint32_t one[4] = {st[0][l], st[1][l], st[2][l], st[3][l]};
+                md5_scalar_blocks(one, p[l], (size_t)step);
+                for (int q = 0; q < 4; q++) st[q][l] = one[q];
+                done[l] += step;
+            }
+        } else {
+            md5_lanes_blocks(st, p, stride, (size_t)step);
+            for (int l = 0; l < LANES; l++) {
+                if (idle[l]) for (int q = 0; q < 4; q++) st[q][l] = keep[q][l];
+                else done[l] += step;
+            }
         }
         if (between && between(arg)) return 1;
     }
