@@ -855,7 +855,20 @@ static int decode_core(const b200flac_stream_info* info, const uint8_t* frames, 
         cap = count; // more look-alikes than allowed for: size for what was found
     }
     if (count == 0) { rc = dfail(1, "invalid sync code"); goto done; }
-    DCK(grow(&w.d_scratch, &w.cap_scratch, (size_t)count * C * row_stride * sizeof(int)));
+    {
+        // one int32 row per (candidate, channel) for the whole stream: bounded by what the device has, said in words
+        // (a file stuffed with header look-alikes has a candidate count of its author's choosing)
+        const size_t need = (size_t)count * C * row_stride * sizeof(int);
+        size_t free_b = 0, total_b = 0;
+        if (need > w.cap_scratch && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need > free_b + w.cap_scratch) {
+            char m[200];
+            snprintf(m, sizeof(m), "stream needs %.1f GB of decode scratch (%u frame candidates x %u channels x %u samples); "
+                     "the device has %.1f GB free", need / 1e9, count, C, row_stride, (free_b + w.cap_scratch) / 1e9);
+            rc = dfail(3, m);
+            goto done;
+        }
+        DCK(grow(&w.d_scratch, &w.cap_scratch, need));
+    }
     DCK(cudaEventRecord(w.ev[2]));
     k_dec_frames<<<(count + 31) / 32, 32>>>(d_frames, n_bytes, S, w.d_cands, count, w.d_scratch, row_stride);
     DCK(cudaGetLastError());
