@@ -439,6 +439,24 @@ void* writer_main(void* arg)
 
 } // namespace
 
+// The host's zone of a many-files job (see Job): how many bytes at the END of the track list the pool hashes.
+// With the copies arriving at `pace` bytes/s, a batch is hashed on the device dev_hash_s after it arrives, so the
+// device is done in time with everything but the last pace * dev_hash_s bytes; the pool takes those if it can hash
+// them by then -- at hash_rate per thread, with the threads that writing the files (which comes first: all_bytes *
+// ratio bytes at write_rate per thread) leaves over -- and otherwise as much as makes the two finish together.
+// Defaults before a job has measurements of its own: pace 36 GB/s (a B200's inbound copies next to outbound ones
+// and a busy pool), 2 GB/s of file per thread, compressed ratio 0.7, 2.5 GB/s of hashing per thread.
+extern "C" uint64_t b200flac_internal_host_zone(uint64_t all_bytes, double pace, double dev_hash_s, int host_threads,
+                                                double write_rate, double ratio, double hash_rate)
+{
+    const double t_run = (double)all_bytes / pace;
+    const double write_s = (double)all_bytes * ratio / write_rate;                 // thread-seconds
+    const double spare = (double)host_threads - write_s / (t_run + dev_hash_s);    // threads left for hashing
+    if (spare <= 0) return 0;
+    const double hr = 0.8 * hash_rate * spare;
+    return (uint64_t)std::min(pace * dev_hash_s, (t_run + dev_hash_s) / (1.0 / hr + 1.0 / pace));
+}
+
 // who hashed the tracks of the last job, and at what rates (bench.py reports it next to the job's time)
 static double g_last_stats[6];
 extern "C" void b200flac_internal_batch_stats(double out[6])
@@ -542,25 +560,17 @@ extern "C" int b200flac_encode_files(uint32_t n_tracks, const char* const* filen
     for (u32 t = 0; t < n_tracks; t++) longest_track = std::max<u64>(longest_track, n_pcm_frames[t] * frame_bytes);
     const double dev_hash_s = (double)longest_track / dev_rate;
     u64 arrived_bytes = 0;
-    // How much of the end of the list is the pool's (mutex held).  With the copies arriving at `pace`, a batch is hashed
-    // on the device dev_hash_s after it arrives, so the device is done in time with everything but the last
-    // pace * dev_hash_s bytes; the pool takes those if it can hash them by then -- at the rate its threads have shown,
-    // with the threads that writing the files (which comes first) leaves over -- and otherwise as much as makes the
-    // two finish together.  Every quantity is the job's own measurement once there is one.
+    // how much of the end of the list is the pool's (mutex held): b200flac_internal_host_zone with the job's own
+    // measurements once there are any
     const char* zone_forced = getenv("B200FLAC_FILES_HOST_ZONE_MB");     // tests: a fixed zone
     auto host_zone = [&]() -> u64 {
         if (zone_forced) return (u64)(atof(zone_forced) * 1048576.0);
         const double el = now() - job.t_start;
         const double pace = (el > 0.05 && arrived_bytes) ? (double)arrived_bytes / el : 36e9;
-        const double t_run = (double)all_bytes / pace;
-        const double write_rate = job.write_busy_s > 0.02 ? (double)job.written_bytes / job.write_busy_s : 2.0e9;   // per thread
+        const double write_rate = job.write_busy_s > 0.02 ? (double)job.written_bytes / job.write_busy_s : 2.0e9;
         const double ratio = job.written_pcm_bytes ? (double)job.written_bytes / (double)job.written_pcm_bytes : 0.7;
-        const double write_s = (double)all_bytes * ratio / write_rate;                                           // thread-seconds
-        const double spare = (double)host_threads - write_s / (t_run + dev_hash_s);
-        if (spare <= 0) return 0;
-        const double hash_rate = job.host_busy_s > 0.02 ? (double)job.host_bytes / job.host_busy_s : 2.5e9;     // per thread
-        const double hr = 0.8 * hash_rate * spare;
-        return (u64)std::min(pace * dev_hash_s, (t_run + dev_hash_s) / (1.0 / hr + 1.0 / pace));
+        const double hash_rate = job.host_busy_s > 0.02 ? (double)job.host_bytes / job.host_busy_s : 2.5e9;
+        return b200flac_internal_host_zone(all_bytes, pace, dev_hash_s, host_threads, write_rate, ratio, hash_rate);
     };
     job.zone_bytes = host_zone();
     pthread_mutex_init(&job.mu, nullptr);

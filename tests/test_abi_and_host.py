@@ -290,3 +290,27 @@ def test_host_md5_lanes_match_hashlib(built):
                  [4096 * 4 + 2, (1 << 20) + 3, 5], [100000 + 977 * i for i in range(16)], [64 * 1000] * 16, [7], [0]):
         datas = [rng.randint(0, 256, size=n).astype(np.uint8).tobytes() for n in lens]
         assert b200flac.host_md5_many(datas) == [hashlib.md5(d).digest() for d in datas], lens
+
+
+def test_many_files_host_zone_model(built):
+    """the split of b200flac_encode_files' hashing between the device and the pool (csrc/b200flac_batch.cu,
+    b200flac_internal_host_zone): the pool takes the end of the list the device cannot hash in time -- pace x one device
+    hash -- unless file writing leaves it no threads, and never more than it can hash by the time the device is done"""
+    import b200flac
+    fn = b200flac.lib().b200flac_internal_host_zone
+    fn.restype = C.c_uint64
+    fn.argtypes = [C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
+    track = 7938000 * 4
+    hash_s = track / 100e6
+    zone = lambda tracks, threads, pace=36e9: fn(tracks * track, pace, hash_s, threads, 2.0e9, 0.7, 2.5e9)
+    # 1,000 and 3,000 tracks, 16 threads: what arrives during the last device hash (11.4 GB at 36 GB/s)
+    assert abs(zone(1000, 16) - 36e9 * hash_s) < 1e6 and abs(zone(3000, 16) - 36e9 * hash_s) < 1e6
+    # a pool of 4 threads is saturated by writing 1,000 tracks' files: no zone, every hash on the device
+    assert zone(1000, 4) == 0
+    # ... but has time left over on one rank's share of an 8-GPU job
+    assert 0 < zone(125, 4) < 125 * track
+    # a job of 16 long tracks is all zone (the device's 0.3 s per track would be the whole job)
+    assert zone(16, 16) >= 16 * track
+    # slower copies (eight ranks sharing the host fabric): a smaller zone; more threads: never a smaller one
+    assert zone(1000, 16, pace=17e9) < zone(1000, 16)
+    assert all(zone(1000, t + 1) >= zone(1000, t) for t in range(1, 32))
