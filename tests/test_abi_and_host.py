@@ -314,3 +314,24 @@ def test_many_files_host_zone_model(built):
     # slower copies (eight ranks sharing the host fabric): a smaller zone; more threads: never a smaller one
     assert zone(1000, 16, pace=17e9) < zone(1000, 16)
     assert all(zone(1000, t + 1) >= zone(1000, t) for t in range(1, 32))
+
+
+def test_host_md5_lanes_callback_between_pieces(built):
+    """the hashing thread looks after more urgent work between pieces (b200flac_encode_files: files to write) and
+    gives up when told to: the callback runs once per piece and a non-zero return ends the call with 1"""
+    import hashlib
+    import b200flac
+    fn = b200flac.lib().b200flac_internal_md5_many
+    CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
+    fn.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p, C.c_uint64, CB, C.c_void_p]
+    datas = [bytes([i]) * (64 * 40 + i) for i in range(8)]
+    ptr = (C.c_char_p * 8)(*datas)
+    lens = (C.c_uint64 * 8)(*[len(d) for d in datas])
+    out = (C.c_uint8 * 128)()
+    calls = []
+    assert fn(ptr, lens, 8, out, 64 * 10, CB(lambda arg: calls.append(1) or 0), None) == 0
+    assert len(calls) == 4                                           # 40 blocks per string, 10 per piece
+    assert [bytes(out[16 * i:16 * i + 16]) for i in range(8)] == [hashlib.md5(d).digest() for d in datas]
+    calls = []
+    assert fn(ptr, lens, 8, out, 64 * 10, CB(lambda arg: calls.append(1) or (len(calls) == 2)), None) == 1
+    assert len(calls) == 2
